@@ -1,0 +1,121 @@
+/*
+ * pasta_b200.h — C ABI of the B200-native PASTA-GAN operator hot path.
+ *
+ * The reference has no C ABI: its native code is reached through two pybind11 modules
+ * JIT-built by torch.utils.cpp_extension (torch_utils/custom_ops.py:46-124):
+ *
+ *     _plugin.upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain)
+ *                                                    torch_utils/ops/upfirdn2d.cpp:16-94, :98-101
+ *     _plugin.bias_act(x, b, xref, yref, dy, grad, dim, act, alpha, gain, clamp)
+ *                                                    torch_utils/ops/bias_act.cpp:32-90, :94-97
+ *
+ * and every convolution is torch.nn.functional.conv2d / conv_transpose2d (cuDNN) called from
+ * torch_utils/ops/conv2d_gradfix.py:35-43 via conv2d_resample.py:29-54.
+ *
+ * This header is what a binding for that path binds instead: plain pointers, sizes and
+ * scalars, no torch types.  Conventions shared by every entry point:
+ *
+ *   - All data pointers are DEVICE pointers on the current CUDA device.  Inputs are borrowed and
+ *     never written; outputs are caller-allocated (ownership stays with the caller, exactly like
+ *     the torch::empty tensors of upfirdn2d.cpp:35 / bias_act.cpp:55).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Launches are
+ *     asynchronous; no entry point synchronises the host (upfirdn2d.cpp:92, bias_act.cpp:88).
+ *   - Return value: 0 on success, a PG_ERR_* code otherwise; pg_last_error() returns a
+ *     thread-local human-readable message for the last failing call on the calling thread
+ *     (the reference raises RuntimeError through TORCH_CHECK / AT_CUDA_CHECK).
+ *   - Entry points are re-entrant and keep no mutable global state: they are called under the GIL
+ *     from the forward pass and from autograd worker threads in backward.
+ *   - There is no CPU implementation behind any of these symbols.
+ */
+#ifndef PASTA_B200_H_
+#define PASTA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PG_ABI_VERSION 1
+
+enum {
+    PG_OK = 0,
+    PG_ERR_INVALID_ARGUMENT = 1,   /* TORCH_CHECK failures of the reference launchers            */
+    PG_ERR_UNSUPPORTED = 2,        /* valid request this build has no kernel for                 */
+    PG_ERR_CUDA = 3,               /* cudaLaunchKernel / runtime error (AT_CUDA_CHECK)           */
+    PG_ERR_NO_DEVICE = 4           /* no sm_100 device / kernel image not loadable on this device */
+};
+
+/* element types of activations (the reference dispatches AT_DISPATCH_FLOATING_TYPES_AND_HALF,
+ * upfirdn2d.cpp:59, bias_act.cpp:77); all arithmetic is fp32 (fp64 for PG_F64), cf. upfirdn2d.cu:15-18 */
+enum { PG_F32 = 0, PG_F16 = 1, PG_F64 = 2 };
+
+/* activation indices == the reference's `cuda_idx` (bias_act.py:23-33) */
+enum {
+    PG_ACT_LINEAR = 1, PG_ACT_RELU = 2, PG_ACT_LRELU = 3, PG_ACT_TANH = 4, PG_ACT_SIGMOID = 5,
+    PG_ACT_ELU = 6, PG_ACT_SELU = 7, PG_ACT_SOFTPLUS = 8, PG_ACT_SWISH = 9
+};
+
+int         pg_abi_version(void);
+const char* pg_last_error(void);
+/* 0 if the current device can run the sm_100a kernel images in this library. */
+int         pg_check_device(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * bias_act  — replaces _plugin.bias_act (bias_act.cpp:32-90; kernel bias_act.cu:23-147).
+ *
+ *   grad == 0 :  y = clamp( act(x + b) * gain )
+ *   grad == 1 :  y = x * gain * act'(.)          with `x` the incoming gradient, act' evaluated from
+ *                yref (or xref + b for swish); zero where |yref| >= clamp
+ *   grad == 2 :  y = x * dy * gain * act''(.)    (tanh, sigmoid, elu, selu, softplus, swish only)
+ *
+ * NULL for b / xref / yref / dy means "absent" (the reference passes empty tensors).
+ * clamp < 0 means "no clamp".  The bias element used for flat index i is b[(i / step_b) % size_b]
+ * (bias_act.cu:44) — step_b is x.stride(dim) in elements; x, xref, yref, dy, y share one dense
+ * layout of size_x elements.  size_x must be <= INT32_MAX ("x is too large", bias_act.cpp:41).
+ */
+int pg_bias_act(const void* x, const void* b, const void* xref, const void* yref, const void* dy, void* y,
+                int64_t size_x, int32_t size_b, int64_t step_b,
+                int32_t grad, int32_t act, float alpha, float gain, float clamp,
+                int32_t dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * upfirdn2d — replaces _plugin.upfirdn2d (upfirdn2d.cpp:16-94; kernels upfirdn2d.cu:29-200).
+ *
+ *   y = decimate_down( FIR_f( pad( zero_insert_up(x) ) ) ) * gain          per (n, c) plane
+ *
+ * sizes are {N, C, H, W}; strides are in ELEMENTS in the same order (NCHW-contiguous and
+ * channels_last are both expressed this way, upfirdn2d.cpp:48-55).  f is float32 [fh, fw] with
+ * element strides {f_stride_h, f_stride_w}; flip == 0 means true convolution (the filter is
+ * flipped before correlating), flip != 0 means correlation (upfirdn2d.py:195-196).  Padding may be
+ * negative (crop).  out_size must equal
+ *   outW = (W*upx + padx0 + padx1 - fw + downx) / downx,   outH likewise     (upfirdn2d.cpp:32-33)
+ * and every tensor must hold <= INT32_MAX elements.
+ */
+int pg_upfirdn2d(const void* x, const float* f, void* y,
+                 const int32_t in_size[4], const int64_t in_stride[4],
+                 const int32_t out_size[4], const int64_t out_stride[4],
+                 int32_t fh, int32_t fw, int64_t f_stride_h, int64_t f_stride_w,
+                 int32_t upx, int32_t upy, int32_t downx, int32_t downy,
+                 int32_t padx0, int32_t padx1, int32_t pady0, int32_t pady1,
+                 int32_t flip, float gain, int32_t dtype, void* stream);
+
+/* Same resampling with the bias_act epilogue of the calling layer fused in (north_star kernel 1):
+ *   y = clamp( act( upfirdn2d(x) + b[c] ) * act_gain )
+ * i.e. upfirdn2d(...) followed by bias_act(dim=1) in one pass over HBM (Conv2dLayer.forward,
+ * training/networks.py:170-179; SynthesisLayer.forward :296-315).  b may be NULL.
+ * act must be linear / relu / lrelu (the activations whose backward needs only y). */
+int pg_upfirdn2d_bias_act(const void* x, const float* f, const void* b, void* y,
+                          const int32_t in_size[4], const int64_t in_stride[4],
+                          const int32_t out_size[4], const int64_t out_stride[4],
+                          int32_t fh, int32_t fw, int64_t f_stride_h, int64_t f_stride_w,
+                          int32_t upx, int32_t upy, int32_t downx, int32_t downy,
+                          int32_t padx0, int32_t padx1, int32_t pady0, int32_t pady1,
+                          int32_t flip, float gain,
+                          int32_t act, float alpha, float act_gain, float clamp,
+                          int32_t dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PASTA_B200_H_ */

@@ -1,0 +1,101 @@
+"""ctypes binding of libpasta_b200.so (include/pasta_b200.h) — the only way the Python layer reaches
+the GPU kernels.  Replaces the reference's pybind11 plugin modules (torch_utils/custom_ops.py:46-124,
+upfirdn2d.cpp:98-101, bias_act.cpp:94-97).  There is NO fallback: a missing library, a missing symbol
+or a non-sm_100 device raises instead of routing anywhere else."""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, 'lib', 'libpasta_b200.so')
+
+_lib = None
+_lock = threading.Lock()
+_device_checked = False
+
+c_int = ctypes.c_int
+c_i32 = ctypes.c_int32
+c_i64 = ctypes.c_int64
+c_f32 = ctypes.c_float
+c_ptr = ctypes.c_void_p
+I32x4 = ctypes.c_int32 * 4
+I64x4 = ctypes.c_int64 * 4
+
+# name -> argtypes; must list every symbol include/pasta_b200.h declares (tests check this)
+SIGNATURES = {
+    'pg_abi_version': [],
+    'pg_last_error': [],
+    'pg_check_device': [],
+    'pg_bias_act': [c_ptr] * 6 + [c_i64, c_i32, c_i64, c_i32, c_i32, c_f32, c_f32, c_f32, c_i32, c_ptr],
+    'pg_upfirdn2d': [c_ptr, c_ptr, c_ptr, I32x4, I64x4, I32x4, I64x4, c_i32, c_i32, c_i64, c_i64] + [c_i32] * 8 +
+                    [c_i32, c_f32, c_i32, c_ptr],
+    'pg_upfirdn2d_bias_act': [c_ptr, c_ptr, c_ptr, c_ptr, I32x4, I64x4, I32x4, I64x4, c_i32, c_i32, c_i64, c_i64] + [c_i32] * 8 +
+                             [c_i32, c_f32, c_i32, c_f32, c_f32, c_f32, c_i32, c_ptr],
+}
+
+
+class PastaB200Error(RuntimeError):
+    """Raised for every non-zero return of the C ABI (the reference raises RuntimeError via TORCH_CHECK)."""
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load():
+    """dlopen libpasta_b200.so once per process; raise loudly if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(_LIB_PATH):
+            raise PastaB200Error(
+                f'{_LIB_PATH} is missing: build it with `python pasta-gan_b200/build.py` (or __graft_entry__.build()). '
+                'pasta-b200 has no CPU or PyTorch fallback for the operator hot path.')
+        lib = ctypes.CDLL(_LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(lib, name)                     # AttributeError if the symbol is not exported
+            fn.argtypes = argtypes
+            fn.restype = ctypes.c_char_p if name == 'pg_last_error' else c_int
+        if lib.pg_abi_version() != 1:
+            raise PastaB200Error(f'ABI mismatch: library reports {lib.pg_abi_version()}, binding expects 1')
+        _lib = lib
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().pg_last_error()
+        raise PastaB200Error(f'{what}: {msg.decode() if msg else "error"} (code {rc})')
+
+
+def require_device():
+    """Call once before the first launch: the current CUDA device must be able to run the sm_100a images."""
+    global _device_checked
+    if not _device_checked:
+        check(load().pg_check_device(), 'pg_check_device')
+        _device_checked = True
+
+
+DTYPE_CODES = {'torch.float32': 0, 'torch.float16': 1, 'torch.float64': 2}
+
+
+def dtype_code(dtype):
+    try:
+        return DTYPE_CODES[str(dtype)]
+    except KeyError:
+        raise PastaB200Error(f'unsupported dtype {dtype}: the operator path handles float32, float16 and float64') from None
+
+
+def ptr(t):
+    """Device pointer of a tensor, or NULL for None / empty (the reference passes empty tensors for 'absent')."""
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def current_stream(device):
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream

@@ -1,0 +1,289 @@
+// upfirdn2d for sm_100a: pad -> zero-insert upsample -> 2-D FIR -> decimate, optionally with the
+// bias_act epilogue of the calling layer fused in.
+//
+// Replaces the reference's upfirdn2d_kernel_small / upfirdn2d_kernel_large
+// (torch_utils/ops/upfirdn2d.cu:29-200, launcher upfirdn2d.cpp:16-94).  Two kernels:
+//
+//   band kernel     NCHW-contiguous planes, up = 1, down in {1, 2}, 4x4 filter, non-negative pad.
+//                   This is >95 % of the bytes PASTA-GAN moves through upfirdn2d (the (2H+1)^2 ->
+//                   (2H)^2 filter after every up-sampling conv, the pad-2 filter before every
+//                   stride-2 conv, the down-2 skip filter, and their backward forms).  One CTA owns a
+//                   full-width band of output rows of one plane: because rows are full width, the
+//                   input rows it needs are ONE contiguous span of global memory regardless of the odd
+//                   (2H+1) row length, so loads are perfectly coalesced; the span is staged in shared
+//                   memory once (halo rows re-read from L2 only), each thread then slides a 4-row
+//                   register window down one output column (16 taps, 4 shared loads per output), and
+//                   stores are coalesced along the row.
+//   generic kernel  any filter size, any up/down, negative padding, flips, any strides
+//                   (channels_last included): one thread per output element gathers its taps through
+//                   the read-only path.  Serves AugmentPipe-style filters, the 3-channel RGB up-2 and
+//                   every tiny plane (< 32 px wide) where launch latency, not bandwidth, is the cost.
+#include "pg_common.cuh"
+
+namespace pg {
+
+struct Epilogue {           // y = clamp(act(v + b[c]) * act_gain)
+    const void* b; int act; float alpha, act_gain, clamp; int enabled;
+};
+
+template <class S>
+__device__ __forceinline__ S apply_epilogue(const Epilogue& e, S v, S bias) {
+    v += bias;
+    if (e.act == PG_ACT_RELU)  v = v > (S)0 ? v : (S)0;
+    if (e.act == PG_ACT_LRELU) v = v > (S)0 ? v : v * (S)e.alpha;
+    v *= (S)e.act_gain;
+    if (e.clamp >= 0.f) { const S c = (S)e.clamp; v = v > c ? c : (v < -c ? -c : v); }
+    return v;
+}
+
+struct UpfirdnParams {
+    const void* x; const float* f; void* y;
+    int N, C, inH, inW, outH, outW;
+    int64_t xs[4], ys[4];          // element strides {n, c, h, w}
+    int fh, fw; int64_t fsh, fsw;
+    int upx, upy, downx, downy, padx0, pady0, flip; float gain;
+    Epilogue epi;
+    // band kernel only
+    int band_rows, bands_per_plane, tile_rows, pitch;
+};
+
+// floor division / modulo for possibly negative numerators
+__device__ __forceinline__ int floordiv(int a, int b) { int q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
+__device__ __forceinline__ int posmod(int a, int b)   { int m = a % b; return m < 0 ? m + b : m; }
+
+// ------------------------------------------------------------------------------------ generic
+template <class T, bool EPI>
+__global__ void __launch_bounds__(256) upfirdn2d_generic_kernel(UpfirdnParams p) {
+    typedef typename Acc<T>::type S;
+    const T* __restrict__ x = (const T*)p.x;
+    T* __restrict__ y = (T*)p.y;
+    const int64_t total = (int64_t)p.N * p.C * p.outH * p.outW;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int ox = (int)(idx % p.outW);
+        int64_t r = idx / p.outW;
+        const int oy = (int)(r % p.outH); r /= p.outH;
+        const int c = (int)(r % p.C);
+        const int n = (int)(r / p.C);
+        // position of tap (0,0) in the zero-inserted (un-padded) image
+        const int ux0 = ox * p.downx - p.padx0;
+        const int uy0 = oy * p.downy - p.pady0;
+        // first tap that lands on a real sample: (u0 + j) % up == 0
+        const int j0 = posmod(-ux0, p.upx);
+        const int i0 = posmod(-uy0, p.upy);
+        const T* xp = x + n * p.xs[0] + c * p.xs[1];
+        S acc = (S)0;
+        for (int i = i0; i < p.fh; i += p.upy) {
+            const int iy = (uy0 + i) / p.upy;            // exact: numerator is a multiple of upy
+            if (iy < 0 || iy >= p.inH) continue;
+            const int fi = p.flip ? i : p.fh - 1 - i;
+            for (int j = j0; j < p.fw; j += p.upx) {
+                const int ix = (ux0 + j) / p.upx;
+                if (ix < 0 || ix >= p.inW) continue;
+                const int fj = p.flip ? j : p.fw - 1 - j;
+                acc += (S)__ldg(p.f + fi * p.fsh + fj * p.fsw) * to_acc<T>(__ldg(xp + iy * p.xs[2] + ix * p.xs[3]));
+            }
+        }
+        acc *= (S)p.gain;
+        if (EPI) acc = apply_epilogue<S>(p.epi, acc, p.epi.b ? to_acc<T>(__ldg((const T*)p.epi.b + c)) : (S)0);
+        y[n * p.ys[0] + c * p.ys[1] + oy * p.ys[2] + ox * p.ys[3]] = from_acc<T, S>(acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------ band (4x4, up=1)
+// grid.x = plane * bands_per_plane + band; 256 threads; dynamic smem = tile_rows * pitch floats.
+template <class T, int D, bool EPI>
+__global__ void __launch_bounds__(256) upfirdn2d_band_kernel(UpfirdnParams p) {
+    constexpr int F = 4;
+    extern __shared__ float tile[];
+    const T* __restrict__ x = (const T*)p.x;
+    T* __restrict__ y = (T*)p.y;
+    const int plane = blockIdx.x / p.bands_per_plane;
+    const int band  = blockIdx.x - plane * p.bands_per_plane;
+    const int oy0   = band * p.band_rows;
+    const int rows  = min(p.band_rows, p.outH - oy0);
+    const int iy0   = oy0 * D - p.pady0;                       // input row of tile row 0
+    const int need  = (rows - 1) * D + F;                      // tile rows actually used
+    const T* xp = x + (size_t)plane * p.inH * p.inW;
+
+    // taps, flipped for true convolution, gain folded in
+    float k[F][F];
+#pragma unroll
+    for (int i = 0; i < F; i++)
+#pragma unroll
+        for (int j = 0; j < F; j++)
+            k[i][j] = __ldg(p.f + (p.flip ? i : F - 1 - i) * p.fsh + (p.flip ? j : F - 1 - j) * p.fsw) * p.gain;
+
+    // stage: tile[r][c] = x[iy0 + r][c - padx0], zero outside the image
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < need; r += 8) {
+        const int iy = iy0 + r;
+        const bool row_ok = (iy >= 0) && (iy < p.inH);
+        const T* src = xp + (ptrdiff_t)iy * p.inW - p.padx0;
+        float* dst = tile + r * p.pitch;
+#pragma unroll 4
+        for (int c = lane; c < p.pitch; c += 32) {
+            const int ix = c - p.padx0;
+            float v = 0.f;
+            if (row_ok && ix >= 0 && ix < p.inW) v = (float)to_acc<T>(__ldg(src + c));
+            dst[c] = v;
+        }
+    }
+    __syncthreads();
+
+    // compute: work item = (row group g, column ox); each item slides a window down `rpg` rows
+    constexpr int RPG = 8;                                     // rows per group
+    const int groups = (rows + RPG - 1) / RPG;
+    const int items = groups * p.outW;
+    const int c_ch = plane % p.C;
+    float bias = 0.f;
+    if (EPI && p.epi.b) bias = (float)to_acc<T>(__ldg((const T*)p.epi.b + c_ch));
+    T* yp = y + (size_t)plane * p.outH * p.outW;
+    for (int item = threadIdx.x; item < items; item += 256) {
+        const int g = item / p.outW;
+        const int ox = item - g * p.outW;
+        const int r0 = g * RPG;
+        const int nr = min(RPG, rows - r0);
+        const float* col = tile + (r0 * D) * p.pitch + ox * D;
+        float w[F][F];                                         // register window: rows x taps
+#pragma unroll
+        for (int i = 0; i < F - D; i++)
+#pragma unroll
+            for (int j = 0; j < F; j++) w[i + D][j] = col[i * p.pitch + j];
+        col += (F - D) * p.pitch;
+        for (int r = 0; r < nr; r++) {
+            // shift the window up by D rows and load D new rows
+#pragma unroll
+            for (int i = 0; i < F - D; i++)
+#pragma unroll
+                for (int j = 0; j < F; j++) w[i][j] = w[i + D][j];
+#pragma unroll
+            for (int i = F - D; i < F; i++)
+#pragma unroll
+                for (int j = 0; j < F; j++) w[i][j] = col[(i - (F - D)) * p.pitch + j];
+            col += D * p.pitch;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int j = 0; j < F; j++) {
+                a0 = fmaf(k[0][j], w[0][j], a0);
+                a1 = fmaf(k[1][j], w[1][j], a1);
+                a2 = fmaf(k[2][j], w[2][j], a2);
+                a3 = fmaf(k[3][j], w[3][j], a3);
+            }
+            float acc = (a0 + a1) + (a2 + a3);
+            if (EPI) acc = apply_epilogue<float>(p.epi, acc, bias);
+            yp[(size_t)(oy0 + r0 + r) * p.outW + ox] = from_acc<T, float>(acc);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ host side
+static bool contiguous_nchw(const int32_t sz[4], const int64_t st[4]) {
+    return st[3] == 1 && st[2] == sz[3] && st[1] == (int64_t)sz[2] * sz[3] && (st[0] == (int64_t)sz[1] * sz[2] * sz[3] || sz[0] == 1);
+}
+
+template <class T, bool EPI>
+static int launch_upfirdn2d(UpfirdnParams p, bool band_ok, cudaStream_t stream) {
+    if (band_ok) {
+        const int D = p.downx;
+        // band height: keep the staged tile <= ~40 KB so >= 5 CTAs fit per SM
+        int band_rows = (D == 1) ? 16 : 8;
+        while (band_rows > 8 && (size_t)((band_rows - 1) * D + 4) * p.pitch * sizeof(float) > 40 * 1024) band_rows /= 2;
+        p.band_rows = band_rows;
+        p.bands_per_plane = (p.outH + band_rows - 1) / band_rows;
+        p.tile_rows = (band_rows - 1) * D + 4;
+        const size_t smem = (size_t)p.tile_rows * p.pitch * sizeof(float);
+        const int64_t blocks = (int64_t)p.N * p.C * p.bands_per_plane;
+        if (smem <= 96 * 1024 && blocks <= INT32_MAX) {
+            auto kern = (D == 1) ? upfirdn2d_band_kernel<T, 1, EPI> : upfirdn2d_band_kernel<T, 2, EPI>;
+            if (smem > 48 * 1024) PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<(unsigned)blocks, 256, smem, stream>>>(p);
+            return launch_status("upfirdn2d(band)");
+        }
+    }
+    const int64_t total = (int64_t)p.N * p.C * p.outH * p.outW;
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = (int64_t)kNumSMs * 64;
+    if (blocks > cap) blocks = cap;
+    upfirdn2d_generic_kernel<T, EPI><<<(unsigned)blocks, 256, 0, stream>>>(p);
+    return launch_status("upfirdn2d(generic)");
+}
+
+static int upfirdn2d_entry(const void* x, const float* f, void* y,
+                           const int32_t in_size[4], const int64_t in_stride[4],
+                           const int32_t out_size[4], const int64_t out_stride[4],
+                           int32_t fh, int32_t fw, int64_t fsh, int64_t fsw,
+                           int32_t upx, int32_t upy, int32_t downx, int32_t downy,
+                           int32_t padx0, int32_t padx1, int32_t pady0, int32_t pady1,
+                           int32_t flip, float gain, const Epilogue& epi, int32_t dtype, void* stream) {
+    PG_REQUIRE(in_size && in_stride && out_size && out_stride, "size/stride arrays must not be NULL");
+    PG_REQUIRE(fh >= 1 && fw >= 1, "f must be at least 1x1");
+    PG_REQUIRE(upx >= 1 && upy >= 1, "upsampling factor must be at least 1");
+    PG_REQUIRE(downx >= 1 && downy >= 1, "downsampling factor must be at least 1");
+    for (int i = 0; i < 4; i++) PG_REQUIRE(in_size[i] >= 0 && out_size[i] >= 0, "negative size");
+    const int64_t in_numel = (int64_t)in_size[0] * in_size[1] * in_size[2] * in_size[3];
+    PG_REQUIRE(in_numel <= INT32_MAX, "x is too large");
+    PG_REQUIRE((int64_t)fh * fw <= INT32_MAX, "f is too large");
+    const int outW = (in_size[3] * upx + padx0 + padx1 - fw + downx) / downx;
+    const int outH = (in_size[2] * upy + pady0 + pady1 - fh + downy) / downy;
+    PG_REQUIRE(outW >= 1 && outH >= 1, "output must be at least 1x1");
+    PG_REQUIRE(out_size[0] == in_size[0] && out_size[1] == in_size[1] && out_size[2] == outH && out_size[3] == outW,
+               "out_size must be [%d, %d, %d, %d]", in_size[0], in_size[1], outH, outW);
+    const int64_t out_numel = (int64_t)out_size[0] * out_size[1] * outH * outW;
+    PG_REQUIRE(out_numel <= INT32_MAX, "output is too large");
+    if (out_numel == 0) return PG_OK;
+    PG_REQUIRE(x && f && y, "x, f and y must be device pointers");
+    if (epi.enabled)
+        PG_REQUIRE(epi.act == PG_ACT_LINEAR || epi.act == PG_ACT_RELU || epi.act == PG_ACT_LRELU,
+                   "fused epilogue supports linear / relu / lrelu only (act=%d)", epi.act);
+
+    UpfirdnParams p;
+    p.x = x; p.f = f; p.y = y;
+    p.N = in_size[0]; p.C = in_size[1]; p.inH = in_size[2]; p.inW = in_size[3]; p.outH = outH; p.outW = outW;
+    for (int i = 0; i < 4; i++) { p.xs[i] = in_stride[i]; p.ys[i] = out_stride[i]; }
+    p.fh = fh; p.fw = fw; p.fsh = fsh; p.fsw = fsw;
+    p.upx = upx; p.upy = upy; p.downx = downx; p.downy = downy; p.padx0 = padx0; p.pady0 = pady0; p.flip = flip ? 1 : 0; p.gain = gain;
+    p.epi = epi;
+    p.band_rows = p.bands_per_plane = p.tile_rows = 0;
+    // columns the band tile must hold: taps of the last output column reach (outW-1)*D + 3
+    p.pitch = ((outW - 1) * downx + 4) | 1;                     // odd pitch keeps row-to-row bank offsets distinct
+
+    const bool band_ok = dtype != PG_F64 && fh == 4 && fw == 4 && upx == 1 && upy == 1 && downx == downy && (downx == 1 || downx == 2) &&
+                         padx0 >= 0 && pady0 >= 0 && outW >= 32 &&
+                         contiguous_nchw(in_size, in_stride) && contiguous_nchw(out_size, out_stride);
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool e = epi.enabled != 0;
+    switch (dtype) {
+        case PG_F32: return e ? launch_upfirdn2d<float, true>(p, band_ok, s)  : launch_upfirdn2d<float, false>(p, band_ok, s);
+        case PG_F16: return e ? launch_upfirdn2d<__half, true>(p, band_ok, s) : launch_upfirdn2d<__half, false>(p, band_ok, s);
+        case PG_F64: return e ? launch_upfirdn2d<double, true>(p, false, s)   : launch_upfirdn2d<double, false>(p, false, s);
+    }
+    return fail(PG_ERR_INVALID_ARGUMENT, "unsupported dtype %d", dtype);
+}
+
+}  // namespace pg
+
+extern "C" int pg_upfirdn2d(const void* x, const float* f, void* y,
+                            const int32_t in_size[4], const int64_t in_stride[4],
+                            const int32_t out_size[4], const int64_t out_stride[4],
+                            int32_t fh, int32_t fw, int64_t f_stride_h, int64_t f_stride_w,
+                            int32_t upx, int32_t upy, int32_t downx, int32_t downy,
+                            int32_t padx0, int32_t padx1, int32_t pady0, int32_t pady1,
+                            int32_t flip, float gain, int32_t dtype, void* stream) {
+    pg::Epilogue e; e.b = nullptr; e.act = PG_ACT_LINEAR; e.alpha = 0.f; e.act_gain = 1.f; e.clamp = -1.f; e.enabled = 0;
+    return pg::upfirdn2d_entry(x, f, y, in_size, in_stride, out_size, out_stride, fh, fw, f_stride_h, f_stride_w,
+                               upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain, e, dtype, stream);
+}
+
+extern "C" int pg_upfirdn2d_bias_act(const void* x, const float* f, const void* b, void* y,
+                                     const int32_t in_size[4], const int64_t in_stride[4],
+                                     const int32_t out_size[4], const int64_t out_stride[4],
+                                     int32_t fh, int32_t fw, int64_t f_stride_h, int64_t f_stride_w,
+                                     int32_t upx, int32_t upy, int32_t downx, int32_t downy,
+                                     int32_t padx0, int32_t padx1, int32_t pady0, int32_t pady1,
+                                     int32_t flip, float gain,
+                                     int32_t act, float alpha, float act_gain, float clamp,
+                                     int32_t dtype, void* stream) {
+    pg::Epilogue e; e.b = b; e.act = act; e.alpha = alpha; e.act_gain = act_gain; e.clamp = clamp; e.enabled = 1;
+    return pg::upfirdn2d_entry(x, f, y, in_size, in_stride, out_size, out_stride, fh, fw, f_stride_h, f_stride_w,
+                               upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain, e, dtype, stream);
+}
