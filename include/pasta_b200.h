@@ -60,6 +60,8 @@ int         pg_abi_version(void);
 const char* pg_last_error(void);
 /* 0 if the current device can run the sm_100a kernel images in this library. */
 int         pg_check_device(void);
+/* Number of kernels this library has launched in this process so far (statistics only; relaxed atomic). */
+int64_t     pg_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * bias_act  — replaces _plugin.bias_act (bias_act.cpp:32-90; kernel bias_act.cu:23-147).

@@ -340,6 +340,78 @@ def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, res
     return y
 
 
+# -----------------------------------------------------------------------------
+# "Fast port": the same algorithm in the formulation a CPU implementation would actually ship — the FIR as a
+# depthwise conv2d and conv2d_resample lowered the way the reference lowers it (strided / transposed-strided conv,
+# conv2d_resample.py:107-147).  Used for the CPU-baseline timing so the baseline is not handicapped by the
+# definitional tap loops above; pinned to the same golden vectors (tests/test_oracle_golden.py).
+
+
+def upfirdn2d_fast(x, f, up=1, down=1, padding=0, flip_filter=False, gain=1):
+    n, c, h, w = x.shape
+    upx, upy = _pair(up)
+    downx, downy = _pair(down)
+    px0, px1, py0, py1 = _pad4(padding)
+    if f is None:
+        f = torch.ones([1, 1], dtype=torch.float32)
+    if upx > 1 or upy > 1:
+        z = x.new_zeros([n, c, h * upy, w * upx])
+        z[:, :, ::upy, ::upx] = x
+        x = z
+    x = torch.nn.functional.pad(x, [max(px0, 0), max(px1, 0), max(py0, 0), max(py1, 0)])
+    x = x[:, :, max(-py0, 0): x.shape[2] - max(-py1, 0), max(-px0, 0): x.shape[3] - max(-px1, 0)]
+    k = (f * (gain ** (f.ndim / 2))).to(x.dtype)
+    if not flip_filter:
+        k = k.flip(list(range(k.ndim)))
+    if k.ndim == 2:
+        x = torch.nn.functional.conv2d(x, k[None, None].repeat(c, 1, 1, 1), groups=c)
+    else:
+        x = torch.nn.functional.conv2d(x, k[None, None, None, :].repeat(c, 1, 1, 1), groups=c)
+        x = torch.nn.functional.conv2d(x, k[None, None, :, None].repeat(c, 1, 1, 1), groups=c)
+    return x[:, :, ::downy, ::downx]
+
+
+def conv2d_resample_fast(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False):
+    cout, cin_g, kh, kw = w.shape
+    fw, fh = _fsize(f)
+    px0, px1, py0, py1 = _pad4(padding)
+    if up > 1:
+        px0 += (fw + up - 1) // 2; px1 += (fw - up) // 2; py0 += (fh + up - 1) // 2; py1 += (fh - up) // 2
+    if down > 1:
+        px0 += (fw - down + 1) // 2; px1 += (fw - down) // 2; py0 += (fh - down + 1) // 2; py1 += (fh - down) // 2
+    if kw == 1 and kh == 1 and down > 1 and up == 1:
+        return _conv(upfirdn2d_fast(x, f, down=down, padding=[px0, px1, py0, py1], flip_filter=flip_filter), w, groups=groups, flip_weight=flip_weight)
+    if kw == 1 and kh == 1 and up > 1 and down == 1:
+        return upfirdn2d_fast(_conv(x, w, groups=groups, flip_weight=flip_weight), f, up=up, padding=[px0, px1, py0, py1], gain=up ** 2, flip_filter=flip_filter)
+    if down > 1 and up == 1:
+        return _conv(upfirdn2d_fast(x, f, padding=[px0, px1, py0, py1], flip_filter=flip_filter), w, stride=down, groups=groups, flip_weight=flip_weight)
+    if up > 1:
+        wt = w.transpose(0, 1) if groups == 1 else \
+            w.reshape(groups, cout // groups, cin_g, kh, kw).transpose(1, 2).reshape(groups * cin_g, cout // groups, kh, kw)
+        px0 -= kw - 1; px1 -= kw - up; py0 -= kh - 1; py1 -= kh - up
+        pxt, pyt = max(min(-px0, -px1), 0), max(min(-py0, -py1), 0)
+        wt = wt if not flip_weight else wt.flip([2, 3])          # transposed conv flips once more
+        x = torch.nn.functional.conv_transpose2d(x, wt, stride=up, padding=[pyt, pxt], groups=groups)
+        x = upfirdn2d_fast(x, f, padding=[px0 + pxt, px1 + pxt, py0 + pyt, py1 + pyt], gain=up ** 2, flip_filter=flip_filter)
+        return upfirdn2d_fast(x, f, down=down, flip_filter=flip_filter) if down > 1 else x
+    if px0 == px1 and py0 == py1 and px0 >= 0 and py0 >= 0:
+        return _conv(x, w, padding=[py0, px0], groups=groups, flip_weight=flip_weight)
+    return _conv(upfirdn2d_fast(x, None, padding=[px0, px1, py0, py1]), w, groups=groups, flip_weight=flip_weight)
+
+
+def modulated_conv2d_fast(x, weight, styles, noise=None, up=1, down=1, padding=0, resample_filter=None,
+                          demodulate=True, flip_weight=True, fused_modconv=True):
+    n = x.shape[0]
+    o, i, kh, kw = weight.shape
+    d = None
+    if demodulate:
+        d = (styles.square() @ weight.square().sum(dim=[2, 3]).t() + 1e-8).rsqrt()
+    y = conv2d_resample_fast(x * styles.reshape(n, i, 1, 1), weight, f=resample_filter, up=up, down=down, padding=padding, flip_weight=flip_weight)
+    if d is not None:
+        y = y * d.reshape(n, o, 1, 1)
+    return y if noise is None else y + noise
+
+
 # The operator table handed to the host-side network mirror when tests / the CPU
 # baseline want the whole generator evaluated by the oracle.
 class _Namespace:
@@ -347,7 +419,18 @@ class _Namespace:
         self.__dict__.update(kw)
 
 
-def operator_table():
+def operator_table(fast=False):
+    """fast=False: the definitional restatement (the parity checker).  fast=True: the lowered CPU port (the timing baseline)."""
+    if fast:
+        def up2(x, f, up=2, padding=0, flip_filter=False, gain=1):
+            upx, upy = _pair(up)
+            px0, px1, py0, py1 = _pad4(padding)
+            fw, fh = _fsize(f)
+            p = [px0 + (fw + upx - 1) // 2, px1 + (fw - upx) // 2, py0 + (fh + upy - 1) // 2, py1 + (fh - upy) // 2]
+            return upfirdn2d_fast(x, f, up=up, padding=p, flip_filter=flip_filter, gain=gain * upx * upy)
+        return _Namespace(name='oracle-cpu-fast', setup_filter=lambda f, device=None, **kw: setup_filter(f, **kw),
+                          upfirdn2d=upfirdn2d_fast, upsample2d=up2, bias_act=bias_act, conv2d_resample=conv2d_resample_fast,
+                          fma=fma, modulated_conv2d=modulated_conv2d_fast, act_def_gain={k: v[2] for k, v in ACT_TABLE.items()})
     return _Namespace(
         name='oracle-cpu',
         setup_filter=lambda f, device=None, **kw: setup_filter(f, **kw),

@@ -26,6 +26,7 @@ SIGNATURES = {
     'pg_abi_version': [],
     'pg_last_error': [],
     'pg_check_device': [],
+    'pg_launch_count': [],
     'pg_bias_act': [c_ptr] * 6 + [c_i64, c_i32, c_i64, c_i32, c_i32, c_f32, c_f32, c_f32, c_i32, c_ptr],
     'pg_upfirdn2d': [c_ptr, c_ptr, c_ptr, I32x4, I64x4, I32x4, I64x4, c_i32, c_i32, c_i64, c_i64] + [c_i32] * 8 +
                     [c_i32, c_f32, c_i32, c_ptr],
@@ -58,7 +59,7 @@ def load():
         for name, argtypes in SIGNATURES.items():
             fn = getattr(lib, name)                     # AttributeError if the symbol is not exported
             fn.argtypes = argtypes
-            fn.restype = ctypes.c_char_p if name == 'pg_last_error' else c_int
+            fn.restype = {'pg_last_error': ctypes.c_char_p, 'pg_launch_count': c_i64}.get(name, c_int)
         if lib.pg_abi_version() != 1:
             raise PastaB200Error(f'ABI mismatch: library reports {lib.pg_abi_version()}, binding expects 1')
         _lib = lib
@@ -96,6 +97,70 @@ def ptr(t):
     return t.data_ptr()
 
 
+def launch_count():
+    """Kernels launched by libpasta_b200.so in this process so far."""
+    return int(load().pg_launch_count())
+
+
 def current_stream(device):
     import torch
     return torch.cuda.current_stream(device).cuda_stream
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Optional per-launch timing (bench.py's roofline leg): CUDA events on the launching stream around each C-ABI call.
+# Disabled (zero work) unless a LaunchProfiler is installed; never active under CUDA-graph capture.
+
+_profiler = None
+
+
+class LaunchProfiler:
+    """Collects (kernel name, algorithmic bytes, algorithmic flops, start event, end event) per launch."""
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        global _profiler
+        _profiler = self
+        return self
+
+    def __exit__(self, *exc):
+        global _profiler
+        _profiler = None
+
+    def summary(self):
+        import torch
+        torch.cuda.synchronize()
+        agg = {}
+        for name, nbytes, flops, e0, e1 in self.records:
+            a = agg.setdefault(name, dict(launches=0, ms=0.0, bytes=0, flops=0))
+            a['launches'] += 1
+            a['ms'] += e0.elapsed_time(e1)
+            a['bytes'] += nbytes
+            a['flops'] += flops
+        return agg
+
+
+class _Span:
+    __slots__ = ('name', 'nbytes', 'flops', 'e0')
+
+    def __init__(self, name, nbytes, flops):
+        import torch
+        self.name, self.nbytes, self.flops = name, nbytes, flops
+        self.e0 = torch.cuda.Event(enable_timing=True)
+        self.e0.record()
+
+    def close(self):
+        import torch
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        if _profiler is not None:
+            _profiler.records.append((self.name, self.nbytes, self.flops, self.e0, e1))
+
+
+def span(name, nbytes=0, flops=0):
+    """Open a timing span if a profiler is installed; returns None otherwise (callers do `if s: s.close()`)."""
+    if _profiler is None:
+        return None
+    return _Span(name, nbytes, flops)

@@ -1,4 +1,5 @@
 // Error slot, ABI version and device check for libpasta_b200.so (include/pasta_b200.h).
+#include <atomic>
 #include "pg_common.cuh"
 
 namespace pg {
@@ -16,11 +17,16 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
 __global__ void probe_kernel(int* out) { if (out) *out = 100; }
 
 }  // namespace pg
 
 extern "C" int pg_abi_version(void) { return PG_ABI_VERSION; }
+
+extern "C" int64_t pg_launch_count(void) { return (int64_t)pg::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" const char* pg_last_error(void) { return pg::error_slot(); }
 

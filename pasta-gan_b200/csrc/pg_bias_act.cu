@@ -146,20 +146,23 @@ static int launch_bias_act(BiasActParams p, cudaStream_t stream) {
     const bool vec_ok = aligned16(p.x) && aligned16(p.y) && (!p.xref || aligned16(p.xref)) && (!p.yref || aligned16(p.yref)) &&
                         (!p.dy || aligned16(p.dy)) && (!p.b || p.step_b % V == 0) && p.size_x >= (uint32_t)V;
     uint32_t done = 0;
+    int launches = 0;
     if (vec_ok) {
+        launches++;
         const uint32_t nvec = p.size_x / V;
         const uint32_t blocks = (nvec + kThreads * kUnroll - 1) / (kThreads * kUnroll);
         bias_act_vec_kernel<T, A><<<blocks, kThreads, 0, stream>>>(p);
         done = nvec * V;
     }
     if (done < p.size_x) {
+        launches++;
         p.elem_begin = done;
         const uint64_t rest = p.size_x - done;
         uint64_t blocks = (rest + kThreads - 1) / kThreads;
         if (blocks > (uint64_t)kNumSMs * 32) blocks = (uint64_t)kNumSMs * 32;
         bias_act_scalar_kernel<T, A><<<(unsigned)blocks, kThreads, 0, stream>>>(p);
     }
-    return launch_status("bias_act");
+    return launch_status("bias_act", launches);
 }
 
 template <class T>

@@ -17,7 +17,10 @@ int   fail(int code, const char* fmt, ...);
 #define PG_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) \
     return ::pg::fail(PG_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); } while (0)
 
-inline int launch_status(const char* what) {
+void count_launch(int n = 1);
+
+inline int launch_status(const char* what, int launches = 1) {
+    count_launch(launches);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PG_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
     return PG_OK;

@@ -1,0 +1,555 @@
+"""Host-side mirror of the PASTA-GAN modules that CALL the operator hot path.
+
+These classes reproduce the module tree, parameter/buffer names and forward arithmetic of the reference's
+full-body generator so that (a) a reference ``state_dict`` loads into them key-for-key and (b) the try-on
+workload of BASELINE.json (256x192 full-body generator inference) can be driven end to end through the
+sm_100a operators.  They are a re-expression, not a copy: every layer is a thin composition over an
+*operator table* (``ops``) whose entries have the reference's ``torch_utils.ops`` semantics.
+
+    reference class (training/networks.py)          here
+    ------------------------------------------------------------------
+    modulated_conv2d               :37-94            modulated_conv2d
+    FullyConnectedLayer            :99-130           FullyConnectedLayer
+    Conv2dLayer                    :133-180          Conv2dLayer
+    MappingNetwork                 :184-262          MappingNetwork
+    SynthesisLayer                 :264-316          SynthesisLayer
+    ResBlock                       :529-558          ResBlock
+    ConstEncoderNetwork            :561-578          ConstEncoderNetwork
+    Dense                          :594-611          Dense
+    Spade_Conv2dLayer              :4305-4354        SpadeConv2dLayer
+    Spade_Norm_Block               :4358-4379        SpadeNormBlock
+    StyleEncoderNetworkV16         :4837-4883        StyleEncoderNetworkV16   (patch-routed style encoder)
+    Spade_ResBlockV2               :5230-5274        SpadeResBlockV2
+    ToRGBLayerFull                 :5583-5611        ToRGBLayerFull
+    SynthesisBlockFull             :5615-5719        SynthesisBlockFull
+    SynthesisNetworkFull           :5723-5840        SynthesisNetworkFull
+    GeneratorFull                  :5844-5880        GeneratorFull
+
+The default operator table is the CUDA product (``cuda_ops()``); tests and the CPU baseline inject the oracle's
+table with ``use_ops(module, table)``.  The product never imports the oracle.
+"""
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .torch_utils import misc
+
+# ----------------------------------------------------------------------------- operator tables
+
+_CUDA_OPS = None
+
+
+def cuda_ops():
+    """The product operator table: every entry lands in libpasta_b200.so (dense convs: see conv2d_gradfix)."""
+    global _CUDA_OPS
+    if _CUDA_OPS is None:
+        from .torch_utils.ops import upfirdn2d as U, bias_act as B, conv2d_resample as C, fma as F
+        _CUDA_OPS = types.SimpleNamespace(
+            name='sm100a',
+            setup_filter=U.setup_filter, upfirdn2d=U.upfirdn2d, filter2d=U.filter2d, upsample2d=U.upsample2d,
+            downsample2d=U.downsample2d, bias_act=B.bias_act, conv2d_resample=C.conv2d_resample, fma=F.fma,
+            modulated_conv2d=modulated_conv2d,
+            act_def_gain={k: float(v.def_gain) for k, v in B.activation_funcs.items()},
+        )
+    return _CUDA_OPS
+
+
+class OpsModule(nn.Module):
+    """nn.Module whose numerical work goes through an operator table (default: the CUDA product)."""
+    _ops = None
+
+    @property
+    def ops(self):
+        return self._ops if self._ops is not None else cuda_ops()
+
+
+def use_ops(module, table):
+    """Route every layer under ``module`` through ``table`` (None restores the CUDA product)."""
+    for m in module.modules():
+        if isinstance(m, OpsModule):
+            m._ops = table
+    return module
+
+
+_ACT_GAIN = dict(linear=1.0, relu=float(np.sqrt(2)), lrelu=float(np.sqrt(2)), tanh=1.0, sigmoid=1.0, elu=1.0, selu=1.0,
+                 softplus=1.0, swish=float(np.sqrt(2)))
+_FIR = [1, 3, 3, 1]
+
+
+def _fir_buffer(taps):
+    """[1,3,3,1] -> normalised 4x4 outer product (upfirdn2d.setup_filter), built without touching the op table."""
+    f = torch.as_tensor(taps, dtype=torch.float32)
+    if f.ndim == 1 and f.numel() < 8:
+        f = torch.outer(f, f)
+    return f / f.sum()
+
+
+# ----------------------------------------------------------------------------- functional pieces
+
+
+def normalize_2nd_moment(x, dim=1, eps=1e-8):
+    return x * (x.square().mean(dim=dim, keepdim=True) + eps).rsqrt()
+
+
+@misc.profiled_function
+def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, resample_filter=None, demodulate=True,
+                     flip_weight=True, fused_modconv=True):
+    """Style-modulated convolution with the reference's signature (networks.py:37-49).
+
+    Both values of ``fused_modconv`` evaluate  y = conv(x * s[n,i], W) * d[n,o] + noise  with
+    d[n,o] = rsqrt(sum_i s[n,i]^2 * sum_k W[o,i,k]^2 + 1e-8): the per-sample weight tensor [N,O,I,k,k] and the
+    groups=N convolution of the reference's fused branch (:84-94) are never materialised (SURVEY.md appendix A,
+    I7/I8).  The fp16 pre-normalisation of :57-59 is kept."""
+    from .torch_utils.ops import conv2d_resample as C, fma as F
+    n = int(x.shape[0])
+    cout, cin, kh, kw = weight.shape
+    misc.assert_shape(weight, [cout, cin, kh, kw])
+    misc.assert_shape(x, [n, cin, None, None])
+    misc.assert_shape(styles, [n, cin])
+    if x.dtype == torch.float16 and demodulate:
+        weight = weight * (1 / np.sqrt(cin * kh * kw) / weight.norm(float('inf'), dim=[1, 2, 3], keepdim=True))
+        styles = styles / styles.norm(float('inf'), dim=1, keepdim=True)
+    dcoefs = None
+    if demodulate:
+        wsq = weight.float().square().sum(dim=[2, 3])                        # [O, I]
+        dcoefs = torch.addmm(torch.full([1, 1], 1e-8, device=x.device), styles.float().square(), wsq.t()).rsqrt()
+    x = x * styles.to(x.dtype).reshape(n, cin, 1, 1)
+    x = C.conv2d_resample(x=x, w=weight.to(x.dtype), f=resample_filter, up=up, down=down, padding=padding, flip_weight=flip_weight)
+    if dcoefs is not None and noise is not None:
+        x = F.fma(x, dcoefs.to(x.dtype).reshape(n, cout, 1, 1), noise.to(x.dtype))
+    elif dcoefs is not None:
+        x = x * dcoefs.to(x.dtype).reshape(n, cout, 1, 1)
+    elif noise is not None:
+        x = x.add_(noise.to(x.dtype))
+    return x
+
+
+# ----------------------------------------------------------------------------- layers
+
+
+class FullyConnectedLayer(OpsModule):
+    def __init__(self, in_features, out_features, bias=True, activation='linear', lr_multiplier=1, bias_init=0):
+        super().__init__()
+        self.activation = activation
+        self.weight = nn.Parameter(torch.randn([out_features, in_features]) / lr_multiplier)
+        self.bias = nn.Parameter(torch.full([out_features], np.float32(bias_init))) if bias else None
+        self.weight_gain = lr_multiplier / np.sqrt(in_features)
+        self.bias_gain = lr_multiplier
+
+    def forward(self, x):
+        w = self.weight.to(x.dtype) * self.weight_gain
+        b = self.bias
+        if b is not None:
+            b = b.to(x.dtype)
+            if self.bias_gain != 1:
+                b = b * self.bias_gain
+        if self.activation == 'linear' and b is not None:
+            return torch.addmm(b.unsqueeze(0), x, w.t())
+        return self.ops.bias_act(x.matmul(w.t()), b, act=self.activation)
+
+
+class Conv2dLayer(OpsModule):
+    """conv2d_resample + bias_act.  ``pre_act`` selects the SPADE variant (activation BEFORE the convolution,
+    reference Spade_Conv2dLayer.forward :4342-4354); otherwise it is the plain Conv2dLayer (:170-179)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, bias=True, activation='linear', up=1, down=1,
+                 resample_filter=_FIR, conv_clamp=None, channels_last=False, trainable=True):
+        super().__init__()
+        self.activation, self.up, self.down, self.conv_clamp = activation, up, down, conv_clamp
+        self.register_buffer('resample_filter', _fir_buffer(resample_filter))
+        self.padding = kernel_size // 2
+        self.weight_gain = 1 / np.sqrt(in_channels * (kernel_size ** 2))
+        self.act_gain = _ACT_GAIN[activation]
+        w = torch.randn([out_channels, in_channels, kernel_size, kernel_size])
+        b = torch.zeros([out_channels]) if bias else None
+        if trainable:
+            self.weight = nn.Parameter(w)
+            self.bias = nn.Parameter(b) if b is not None else None
+        else:
+            self.register_buffer('weight', w)
+            if b is not None:
+                self.register_buffer('bias', b)
+            else:
+                self.bias = None
+
+    def _conv(self, x):
+        w = self.weight * self.weight_gain
+        return self.ops.conv2d_resample(x=x, w=w.to(x.dtype), f=self.resample_filter, up=self.up, down=self.down,
+                                        padding=self.padding, flip_weight=(self.up == 1))
+
+    def _act(self, x, gain):
+        b = self.bias.to(x.dtype) if self.bias is not None else None
+        clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
+        return self.ops.bias_act(x, b, act=self.activation, gain=self.act_gain * gain, clamp=clamp)
+
+    def forward(self, x, gain=1):
+        return self._act(self._conv(x), gain)
+
+
+class SpadeConv2dLayer(Conv2dLayer):
+    def __init__(self, in_channels, out_channels, kernel_size, bias=True, activation='relu', **kw):
+        super().__init__(in_channels, out_channels, kernel_size, bias=bias, activation=activation, **kw)
+
+    def forward(self, x, gain=1, no_act=False):
+        if not no_act:
+            x = self._act(x, gain)
+        return self._conv(x)
+
+
+class MappingNetwork(OpsModule):
+    def __init__(self, z_dim, c_dim, w_dim, num_ws, num_layers=8, embed_features=None, layer_features=None,
+                 activation='lrelu', lr_multiplier=0.01, w_avg_beta=0.995):
+        super().__init__()
+        self.z_dim, self.c_dim, self.w_dim, self.num_ws, self.num_layers, self.w_avg_beta = z_dim, c_dim, w_dim, num_ws, num_layers, w_avg_beta
+        embed_features = w_dim if embed_features is None else embed_features
+        if c_dim == 0:
+            embed_features = 0
+        layer_features = w_dim if layer_features is None else layer_features
+        feats = [z_dim + embed_features] + [layer_features] * (num_layers - 1) + [w_dim]
+        if c_dim > 0:
+            self.embed = FullyConnectedLayer(c_dim, embed_features)
+        for i in range(num_layers):
+            setattr(self, f'fc{i}', FullyConnectedLayer(feats[i], feats[i + 1], activation=activation, lr_multiplier=lr_multiplier))
+        if num_ws is not None and w_avg_beta is not None:
+            self.register_buffer('w_avg', torch.zeros([w_dim]))
+
+    def forward(self, z, c, truncation_psi=1, truncation_cutoff=None, skip_w_avg_update=False):
+        x = None
+        if self.z_dim > 0:
+            misc.assert_shape(z, [None, self.z_dim])
+            x = normalize_2nd_moment(z.to(torch.float32))
+        if self.c_dim > 0:
+            misc.assert_shape(c, [None, self.c_dim])
+            y = normalize_2nd_moment(self.embed(c.to(torch.float32)))
+            x = torch.cat([x, y], dim=1) if x is not None else y
+        for i in range(self.num_layers):
+            x = getattr(self, f'fc{i}')(x)
+        if self.w_avg_beta is not None and self.training and not skip_w_avg_update:
+            self.w_avg.copy_(x.detach().mean(dim=0).lerp(self.w_avg, self.w_avg_beta))
+        if self.num_ws is not None:
+            x = x.unsqueeze(1).repeat([1, self.num_ws, 1])
+        if truncation_psi != 1:
+            assert self.w_avg_beta is not None
+            if self.num_ws is None or truncation_cutoff is None:
+                x = self.w_avg.lerp(x, truncation_psi)
+            else:
+                x[:, :truncation_cutoff] = self.w_avg.lerp(x[:, :truncation_cutoff], truncation_psi)
+        return x
+
+
+class SynthesisLayer(OpsModule):
+    def __init__(self, in_channels, out_channels, w_dim, resolution, kernel_size=3, up=1, use_noise=True, activation='lrelu',
+                 resample_filter=_FIR, conv_clamp=None, channels_last=False):
+        super().__init__()
+        self.resolution, self.up, self.use_noise, self.activation, self.conv_clamp = resolution, up, use_noise, activation, conv_clamp
+        self.register_buffer('resample_filter', _fir_buffer(resample_filter))
+        self.padding = kernel_size // 2
+        self.act_gain = _ACT_GAIN[activation]
+        self.affine = FullyConnectedLayer(w_dim, in_channels, bias_init=1)
+        self.weight = nn.Parameter(torch.randn([out_channels, in_channels, kernel_size, kernel_size]))
+        if use_noise:
+            self.register_buffer('noise_const', torch.randn([resolution, resolution]))
+            self.noise_strength = nn.Parameter(torch.zeros([]))
+        self.bias = nn.Parameter(torch.zeros([out_channels]))
+
+    def forward(self, x, w, noise_mode='random', fused_modconv=True, gain=1):
+        assert noise_mode in ['random', 'const', 'none']
+        misc.assert_shape(x, [None, self.weight.shape[1], self.resolution // self.up, self.resolution // self.up])
+        styles = self.affine(w)
+        noise = None
+        if self.use_noise and noise_mode == 'random':
+            noise = torch.randn([x.shape[0], 1, self.resolution, self.resolution], device=x.device) * self.noise_strength
+        if self.use_noise and noise_mode == 'const':
+            noise = self.noise_const * self.noise_strength
+        x = self.ops.modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=noise, up=self.up, padding=self.padding,
+                                      resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv)
+        clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
+        return self.ops.bias_act(x, self.bias.to(x.dtype), act=self.activation, gain=self.act_gain * gain, clamp=clamp)
+
+
+class ToRGBLayerFull(OpsModule):
+    """1x1 modulated conv (no demodulation) to RGB; the last block of the style branch also predicts the 6-class
+    parsing map from the same styles."""
+
+    def __init__(self, in_channels, out_channels, w_dim, kernel_size=1, conv_clamp=None, channels_last=False, is_last=False, is_style=False):
+        super().__init__()
+        self.conv_clamp = conv_clamp
+        self.affine = FullyConnectedLayer(w_dim, in_channels, bias_init=1)
+        self.weight = nn.Parameter(torch.randn([out_channels, in_channels, kernel_size, kernel_size]))
+        self.bias = nn.Parameter(torch.zeros([out_channels]))
+        self.weight_gain = 1 / np.sqrt(in_channels * (kernel_size ** 2))
+        self.predicts_parsing = bool(is_last and is_style)
+        if self.predicts_parsing:
+            self.m_weight1 = nn.Parameter(torch.randn([6, in_channels, kernel_size, kernel_size]))
+            self.m_bias1 = nn.Parameter(torch.zeros([6]))
+
+    def forward(self, x, w, fused_modconv=True):
+        styles = self.affine(w) * self.weight_gain
+        parsing = None
+        if self.predicts_parsing:
+            parsing = self.ops.modulated_conv2d(x=x, weight=self.m_weight1, styles=styles, demodulate=False, fused_modconv=fused_modconv)
+            parsing = self.ops.bias_act(parsing, self.m_bias1.to(x.dtype), clamp=self.conv_clamp)
+        x = self.ops.modulated_conv2d(x=x, weight=self.weight, styles=styles, demodulate=False, fused_modconv=fused_modconv)
+        return self.ops.bias_act(x, self.bias.to(x.dtype), clamp=self.conv_clamp), parsing
+
+
+class ResBlock(OpsModule):
+    def __init__(self, in_channels, out_channels, kernel_size, bias=True, activation='linear', up=1, down=1,
+                 resample_filter=_FIR, conv_clamp=None, channels_last=False, trainable=True):
+        super().__init__()
+        self.register_buffer('resample_filter', _fir_buffer(resample_filter))
+        self.conv0 = Conv2dLayer(in_channels, out_channels, kernel_size=3, activation=activation, up=up, down=down, bias=bias,
+                                 resample_filter=resample_filter, conv_clamp=conv_clamp)
+        self.conv1 = Conv2dLayer(out_channels, out_channels, kernel_size=3, activation=activation, bias=bias,
+                                 resample_filter=resample_filter, conv_clamp=conv_clamp)
+        self.skip = Conv2dLayer(in_channels, out_channels, kernel_size=1, bias=False, up=up, down=down,
+                                resample_filter=resample_filter, conv_clamp=conv_clamp)
+
+    def forward(self, x):
+        y = self.skip(x, gain=np.sqrt(0.5))
+        x = self.conv1(self.conv0(x), gain=np.sqrt(0.5))
+        return y.add_(x)
+
+
+class ConstEncoderNetwork(OpsModule):
+    """Pose/retain encoder: 1x1 stem, then ``n_downsampling`` stride-2 3x3 convs (256^2 -> 4^2 x 512)."""
+
+    def __init__(self, input_nc, output_nc, ngf=64, n_downsampling=4):
+        super().__init__()
+        mult_in, mult_out = [1, 2, 4, 4, 4, 8], [2, 4, 4, 4, 8, 8]
+        layers = [Conv2dLayer(input_nc, ngf, kernel_size=1)]
+        layers += [Conv2dLayer(ngf * mult_in[i], ngf * mult_out[i], kernel_size=3, down=2) for i in range(n_downsampling)]
+        self.model = nn.Sequential(*layers)
+
+    def forward(self, x):
+        return self.model(x)
+
+
+class Dense(nn.Module):
+    """Per-pixel Linear -> InstanceNorm -> LeakyReLU(0.01) (plain torch in the reference as well)."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.bn = nn.InstanceNorm2d(out_channels)
+        self.activation = nn.LeakyReLU()
+        self.linear = nn.Linear(in_channels, out_channels)
+
+    def forward(self, x):
+        y = self.linear(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+        return self.activation(self.bn(y))
+
+
+class StyleEncoderNetworkV16(OpsModule):
+    """Patch-routed style encoder: the normalised garment patches (10 upper + 4 lower, RGB) -> 512-d style code; a second
+    small encoder turns the retained-person image into 64-channel features at 256/128/64/32 px for the merge convs."""
+
+    def __init__(self, input_nc, output_nc, ngf=64, n_downsampling=4):
+        super().__init__()
+        enc = [Conv2dLayer(input_nc, ngf, kernel_size=1)]
+        for m_in, m_out in zip([1, 2, 4], [2, 4, 8]):
+            enc += [Dense(ngf * m_in, ngf * m_in), Conv2dLayer(ngf * m_in, ngf * m_out, kernel_size=3, down=2)]
+        for _ in range(3):
+            enc += [Dense(ngf * 8, ngf * 8), Conv2dLayer(ngf * 8, ngf * 8, kernel_size=3)]
+        enc += [nn.AdaptiveAvgPool2d(1)]
+        self.model = nn.Sequential(*enc)
+        self.fc = FullyConnectedLayer(output_nc, output_nc)
+        feat = [Conv2dLayer(3, ngf, kernel_size=3)] + [Conv2dLayer(ngf, ngf, kernel_size=3, down=2) for _ in range(3)]
+        self.feat_enc = nn.Sequential(*feat)
+
+    def forward(self, x, const_input):
+        feats = []
+        for layer in self.feat_enc:
+            const_input = layer(const_input)
+            feats.append(const_input)
+        x = self.model(x)
+        return self.fc(x.view(x.size(0), -1)), feats
+
+
+class SpadeNormBlock(OpsModule):
+    def __init__(self, in_channels, norm_channels):
+        super().__init__()
+        self.conv_mlp = SpadeConv2dLayer(in_channels, norm_channels, kernel_size=3, bias=False)
+        self.conv_mlp_act = nn.ReLU()
+        self.conv_gamma = SpadeConv2dLayer(norm_channels, norm_channels, kernel_size=3, bias=False)
+        self.conv_beta = SpadeConv2dLayer(norm_channels, norm_channels, kernel_size=3, bias=False)
+        self.param_free_norm = nn.InstanceNorm2d(norm_channels, affine=False)
+
+    def forward(self, x, denorm_feats):
+        actv = self.conv_mlp_act(self.conv_mlp(denorm_feats, no_act=True))
+        gamma = self.conv_gamma(actv, no_act=True)
+        beta = self.conv_beta(actv, no_act=True)
+        return self.param_free_norm(x) * (1 + gamma) + beta
+
+
+class SpadeResBlockV2(OpsModule):
+    def __init__(self, in_channels, out_channels, resample_filter=_FIR, conv_clamp=None, resolution=128):
+        super().__init__()
+        self.register_buffer('resample_filter', _fir_buffer(resample_filter))
+        kw = dict(bias=False, resample_filter=resample_filter, conv_clamp=conv_clamp)
+        self.conv = SpadeConv2dLayer(in_channels, in_channels, kernel_size=3, **kw)
+        self.conv0 = SpadeConv2dLayer(in_channels, out_channels, kernel_size=3, **kw)
+        self.conv1 = SpadeConv2dLayer(out_channels, out_channels, kernel_size=3, **kw)
+        self.skip = SpadeConv2dLayer(in_channels, out_channels, kernel_size=1, **kw)
+        feat_channels = 128 * 2 if resolution == 128 else 64 * 2
+        self.spade_skip = SpadeNormBlock(feat_channels, in_channels)
+        self.spade0 = SpadeNormBlock(feat_channels, in_channels)
+        self.spade1 = SpadeNormBlock(feat_channels, out_channels)
+
+    def forward(self, x, denorm_feat):
+        x = self.conv(x, no_act=True)
+        y = self.skip(self.spade_skip(x, denorm_feat), gain=np.sqrt(0.5))
+        x = self.conv0(self.spade0(x, denorm_feat))
+        x = self.conv1(self.spade1(x, denorm_feat), gain=np.sqrt(0.5))
+        return y.add_(x)
+
+
+class SynthesisBlockFull(OpsModule):
+    def __init__(self, in_channels, out_channels, w_dim, resolution, img_channels, is_last, is_style=False, architecture='skip',
+                 resample_filter=_FIR, conv_clamp=None, use_fp16=False, fp16_channels_last=False, **layer_kwargs):
+        assert architecture in ['orig', 'skip', 'resnet']
+        super().__init__()
+        self.in_channels, self.w_dim, self.resolution, self.img_channels = in_channels, w_dim, resolution, img_channels
+        self.is_last, self.architecture = is_last, architecture
+        self.register_buffer('resample_filter', _fir_buffer(resample_filter))
+        self.num_conv = self.num_torgb = 0
+        if in_channels == 0:
+            self.const = nn.Parameter(torch.randn([out_channels, resolution, resolution]))   # kept for state_dict parity; unused
+        else:
+            self.conv0 = SynthesisLayer(in_channels, out_channels, w_dim=w_dim, resolution=resolution, up=2,
+                                        resample_filter=resample_filter, conv_clamp=conv_clamp, **layer_kwargs)
+            self.num_conv += 1
+        self.conv1 = SynthesisLayer(out_channels, out_channels, w_dim=w_dim, resolution=resolution, conv_clamp=conv_clamp, **layer_kwargs)
+        self.num_conv += 1
+        if is_last or architecture == 'skip':
+            self.torgb = ToRGBLayerFull(out_channels, img_channels, w_dim=w_dim, conv_clamp=conv_clamp, is_last=is_last, is_style=is_style)
+            self.num_torgb += 1
+        if in_channels != 0 and architecture == 'resnet':
+            self.skip = Conv2dLayer(in_channels, out_channels, kernel_size=1, bias=False, up=2, resample_filter=resample_filter)
+        if resolution > 16:
+            self.merge_conv = Conv2dLayer(out_channels + 64, out_channels, kernel_size=1, resample_filter=resample_filter)
+
+    def forward(self, x, img, ws, pose_feature, cat_feat, force_fp32=False, fused_modconv=None, **layer_kwargs):
+        misc.assert_shape(ws, [None, self.num_conv + self.num_torgb, self.w_dim])
+        w_iter = iter(ws.unbind(dim=1))
+        if fused_modconv is None:
+            fused_modconv = not self.training            # the generator always runs fp32 (reference :5747-5748, :5818)
+        if self.in_channels == 0:
+            x = pose_feature.to(torch.float32)
+            x = self.conv1(x, next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
+        elif self.architecture == 'resnet':
+            y = self.skip(x, gain=np.sqrt(0.5))
+            x = self.conv0(x, next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
+            x = self.conv1(x, next(w_iter), fused_modconv=fused_modconv, gain=np.sqrt(0.5), **layer_kwargs)
+            x = y.add_(x)
+        else:
+            misc.assert_shape(x, [None, self.in_channels, self.resolution // 2, self.resolution // 2])
+            x = self.conv0(x.to(torch.float32), next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
+            x = self.conv1(x, next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
+            if x.shape[2] > 16:                          # merge the warped retain-person features
+                x = self.merge_conv(torch.cat([x, cat_feat[str(x.shape[2])].to(torch.float32)], dim=1))
+        if img is not None:
+            misc.assert_shape(img, [None, self.img_channels, self.resolution // 2, self.resolution // 2])
+            img = self.ops.upsample2d(img, self.resample_filter)
+        parsing = None
+        if self.is_last or self.architecture == 'skip':
+            y, parsing = self.torgb(x, next(w_iter), fused_modconv=fused_modconv)
+            y = y.to(dtype=torch.float32)
+            img = img.add_(y) if img is not None else y
+        return x, img, parsing
+
+
+class SynthesisNetworkFull(OpsModule):
+    def __init__(self, w_dim, img_resolution, img_channels, channel_base=32768, channel_max=512, num_fp16_res=0, **block_kwargs):
+        assert img_resolution >= 4 and img_resolution & (img_resolution - 1) == 0
+        super().__init__()
+        self.w_dim, self.img_resolution, self.img_channels = w_dim, img_resolution, img_channels
+        self.img_resolution_log2 = int(np.log2(img_resolution))
+        self.block_resolutions = [2 ** i for i in range(2, self.img_resolution_log2 + 1)]
+        ch = {res: min(channel_base // res, channel_max) for res in self.block_resolutions}
+        self.num_ws = 0
+        for res in self.block_resolutions:
+            block = SynthesisBlockFull(ch[res // 2] if res > 4 else 0, ch[res], w_dim=w_dim, resolution=res, img_channels=img_channels,
+                                       is_last=(res == img_resolution), is_style=True, **block_kwargs)
+            self.num_ws += block.num_conv + (block.num_torgb if res == img_resolution else 0)
+            setattr(self, f'b{res}', block)
+        mid, top = self.block_resolutions[-2], self.block_resolutions[-1]
+        for k in (1, 2, 3):
+            setattr(self, f'spade_b128_{k}', SpadeResBlockV2(ch[mid], ch[mid]))
+        self.texture_b256 = SynthesisBlockFull(ch[top // 2], ch[top], w_dim=w_dim, resolution=top, img_channels=img_channels,
+                                               is_last=True, is_style=False, **block_kwargs)
+        ngf = 64
+        self.spade_encoder = nn.Sequential(Conv2dLayer(3, ngf, kernel_size=7, activation='relu'),
+                                           ResBlock(ngf, ngf, kernel_size=4, activation='relu'),
+                                           ResBlock(ngf, ngf * 2, kernel_size=4, activation='relu', down=2))
+
+    def get_spade_feat(self, mask_256, denorm_mask, denorm_input):
+        """Garment features at 128 px; pixels the predicted mask covers but the source garment does not are filled with the
+        garment's mean feature (reference :5777-5800)."""
+        half = lambda t: torch.nn.functional.interpolate(t, scale_factor=0.5)
+        binar = lambda t: (t > 0.9).to(mask_256.dtype)
+        mask_256 = binar(mask_256)
+        mask_128 = binar(half(mask_256))
+        denorm_mask_128 = binar(half(denorm_mask))
+        valid = ((mask_128 + denorm_mask_128) == 2.0).to(mask_256.dtype)
+        rest = mask_128 - valid
+        feat = self.spade_encoder(denorm_input * mask_256 - (1 - mask_256))
+        feat_sum = (feat * valid).sum(dim=(2, 3), keepdim=True)
+        count = valid.sum(dim=(2, 3), keepdim=True)
+        enough = (count > 10).to(mask_256.dtype)
+        count = count * enough + (128 * 128) * (1 - enough)
+        return feat * (1 - rest) + (feat_sum / count) * rest
+
+    def forward(self, ws, pose_feat, cat_feat, denorm_upper_input, denorm_lower_input, denorm_upper_mask, denorm_lower_mask, **block_kwargs):
+        misc.assert_shape(ws, [None, self.num_ws, self.w_dim])
+        ws = ws.to(torch.float32)
+        block_ws, idx = [], 0
+        for res in self.block_resolutions:
+            block = getattr(self, f'b{res}')
+            block_ws.append(ws.narrow(1, idx, block.num_conv + block.num_torgb))
+            idx += block.num_conv
+        x = img = parsing = None
+        for res, cur in zip(self.block_resolutions, block_ws):
+            x, img, parsing = getattr(self, f'b{res}')(x, img, cur, pose_feat, cat_feat, force_fp32=True, **block_kwargs)
+            if res == 128:
+                x_128, img_128 = x.clone(), img.clone()
+        label = torch.argmax(torch.softmax(parsing.detach(), dim=1), dim=1)[:, None].float()
+        upper = self.get_spade_feat((label == 1).float(), denorm_upper_mask, denorm_upper_input)
+        lower = self.get_spade_feat((label == 2).float(), denorm_lower_mask, denorm_lower_input)
+        spade_feat = torch.cat([upper, lower], dim=1)
+        x = x_128
+        for k in (1, 2, 3):
+            x = getattr(self, f'spade_b128_{k}')(x, spade_feat)
+        _, finetune_img, _ = self.texture_b256(x, img_128, block_ws[-1], pose_feat, cat_feat, force_fp32=True, **block_kwargs)
+        return img, finetune_img, parsing
+
+
+class GeneratorFull(OpsModule):
+    """The 256x192 full-body try-on generator (train_wo_flow_fullbody.py:190-201 builds exactly this)."""
+
+    def __init__(self, z_dim, c_dim, w_dim, img_resolution, img_channels, mapping_kwargs={}, synthesis_kwargs={}):
+        super().__init__()
+        self.z_dim, self.c_dim, self.w_dim, self.img_resolution, self.img_channels = z_dim, c_dim, w_dim, img_resolution, img_channels
+        self.synthesis = SynthesisNetworkFull(w_dim=w_dim, img_resolution=img_resolution, img_channels=img_channels, **synthesis_kwargs)
+        self.num_ws = self.synthesis.num_ws
+        self.mapping = MappingNetwork(z_dim=z_dim, c_dim=c_dim, w_dim=w_dim, num_ws=self.num_ws, **mapping_kwargs)
+        self.const_encoding = ConstEncoderNetwork(input_nc=3 + 3, output_nc=512, ngf=64, n_downsampling=6)
+        self.style_encoding = StyleEncoderNetworkV16(input_nc=(10 * 3 + 4 * 3), output_nc=512, ngf=64, n_downsampling=6)
+
+    def forward(self, z, c, retain, pose, denorm_upper_input, denorm_lower_input, denorm_upper_mask, denorm_lower_mask,
+                truncation_psi=1, truncation_cutoff=None, **synthesis_kwargs):
+        pose_feat = self.const_encoding(pose)
+        stylecode, feats = self.style_encoding(c, retain)
+        ws = self.mapping(z, stylecode, truncation_psi=truncation_psi, truncation_cutoff=truncation_cutoff)
+        cat_feats = {str(f.shape[2]): f for f in feats}
+        return self.synthesis(ws, pose_feat, cat_feats, denorm_upper_input, denorm_lower_input, denorm_upper_mask, denorm_lower_mask,
+                              **synthesis_kwargs)
+
+
+def build_generator_full(img_resolution=256, channel_base=16384, channel_max=512):
+    """GeneratorFull at the BASELINE config: z_dim 0, c_dim = w_dim = 512, 1 mapping layer, conv_clamp 256, noise on."""
+    return GeneratorFull(z_dim=0, c_dim=512, w_dim=512, img_resolution=img_resolution, img_channels=3,
+                         mapping_kwargs=dict(num_layers=1),
+                         synthesis_kwargs=dict(channel_base=channel_base, channel_max=channel_max, num_fp16_res=3, conv_clamp=256, use_noise=True))

@@ -78,10 +78,14 @@ def _kernel(x, b, xref, yref, dy, grad, dim, cfg):
     y = torch.empty_like(x)
     with torch.cuda.device(x.device):
         capi.require_device()
+        nops = 2 + (xref is not None) + (yref is not None) + (dy is not None)
+        sp = capi.span('bias_act' if grad == 0 else f'bias_act_grad{grad}', nops * x.numel() * x.element_size())
         rc = capi.load().pg_bias_act(capi.ptr(x), capi.ptr(b), capi.ptr(xref), capi.ptr(yref), capi.ptr(dy), capi.ptr(y),
                                      x.numel(), size_b, step_b, grad, act_idx, alpha, gain, clamp,
                                      capi.dtype_code(x.dtype), capi.current_stream(x.device))
         capi.check(rc, 'pg_bias_act')
+        if sp:
+            sp.close()
     return y
 
 
@@ -96,7 +100,11 @@ class _BiasAct(torch.autograd.Function):
         trivial = act == 'linear' and gain == 1 and clamp < 0
         y = x if (trivial and b is None) else _kernel(x, b, None, None, None, 0, dim, cfg)
         keep_x = 'x' in spec.ref or spec.has_2nd_grad
-        ctx.save_for_backward(x if keep_x else None, b if keep_x else None, y if 'y' in spec.ref else None)
+        # y is also kept for 'linear' when clamping: the gradient must vanish where the output saturated, as in the
+        # reference's impl='ref' path (autograd through x.clamp, bias_act.py:121-122).  The reference's CUDA plugin
+        # passes no yref for 'linear' (ref='' at :24) and therefore never masks — we follow the ref path.
+        keep_y = 'y' in spec.ref or (act == 'linear' and clamp >= 0)
+        ctx.save_for_backward(x if keep_x else None, b if keep_x else None, y if keep_y else None)
         ctx.dim, ctx.act, ctx.cfg, ctx.trivial = dim, act, cfg, trivial
         return y
 

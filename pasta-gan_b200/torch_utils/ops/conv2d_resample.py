@@ -9,6 +9,7 @@ All FIR stages run on the sm_100a upfirdn2d kernels.
 import torch
 
 from .. import misc
+from . import _backend
 from . import conv2d_gradfix
 from . import upfirdn2d
 from .upfirdn2d import _get_filter_size, _parse_padding
@@ -24,7 +25,16 @@ def _conv2d_wrapper(x, w, stride=1, padding=0, groups=1, transpose=False, flip_w
     if not flip_weight:
         w = w.flip([2, 3])
     op = conv2d_gradfix.conv_transpose2d if transpose else conv2d_gradfix.conv2d
-    return op(x, w, stride=stride, padding=padding, groups=groups)
+    sp = _backend.capi().span('library_conv(cudnn)') if x.is_cuda else None
+    y = op(x, w, stride=stride, padding=padding, groups=groups)
+    if sp:
+        kh, kw = int(w.shape[2]), int(w.shape[3])
+        taps = (x.shape[2] * x.shape[3]) if transpose else (y.shape[2] * y.shape[3])
+        cin_g, cout = (int(w.shape[0]) // groups, int(w.shape[1]) * groups) if transpose else (int(w.shape[1]), int(w.shape[0]))
+        sp.flops = 2 * int(x.shape[0]) * cout * cin_g * kh * kw * int(taps)
+        sp.nbytes = (x.numel() + y.numel() + w.numel()) * x.element_size()
+        sp.close()
+    return y
 
 
 @misc.profiled_function

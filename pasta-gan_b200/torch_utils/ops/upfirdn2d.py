@@ -104,6 +104,8 @@ def _launch(x, f2d, cfg, epilogue=None):
         stream = capi.current_stream(x.device)
         common = (capi.I32x4(n, c, h, w), capi.I64x4(*x.stride()), capi.I32x4(n, c, oh, ow), capi.I64x4(*y.stride()),
                   fh, fw, f2d.stride(0), f2d.stride(1), upx, upy, downx, downy, px0, px1, py0, py1, int(bool(flip)), float(gain))
+        esz = x.element_size()
+        sp = capi.span('upfirdn2d' if epilogue is None else 'upfirdn2d_bias_act', (x.numel() + y.numel()) * esz)
         if epilogue is None:
             rc = capi.load().pg_upfirdn2d(capi.ptr(x), capi.ptr(f2d), capi.ptr(y), *common, capi.dtype_code(x.dtype), stream)
             capi.check(rc, 'pg_upfirdn2d')
@@ -113,6 +115,8 @@ def _launch(x, f2d, cfg, epilogue=None):
                                                    act_idx, float(alpha), float(act_gain), float(clamp),
                                                    capi.dtype_code(x.dtype), stream)
             capi.check(rc, 'pg_upfirdn2d_bias_act')
+        if sp:
+            sp.close()
     return y
 
 

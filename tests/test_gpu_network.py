@@ -1,0 +1,70 @@
+"""GPU parity of the generator path: host-side mirror + sm_100a operator table against the golden outputs of the
+unmodified reference (impl='ref', CPU).  Tolerances (north_star): 1e-5-class fp32 agreement for the FIR / bias_act
+stages, 1e-2 relative on generator outputs once tensor-core convolutions are involved; fp32 library convolutions are
+held to 1e-4 per layer here."""
+import pytest
+import torch
+
+import procedural
+from conftest import rel_err
+from pasta_gan_b200 import networks as N
+from test_network_mirror import run_layer_case
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+@pytest.fixture(autouse=True)
+def _fp32_convs():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+@pytest.mark.parametrize('tag', ['synth_s1_eval', 'synth_s1_train', 'synth_up_eval', 'synth_up_train', 'torgb_eval', 'torgb_train',
+                                 'conv_plain', 'conv_down', 'conv_up', 'conv_7x7', 'resblock_down', 'fc_lrelu', 'fc_linear', 'dense', 'spade_norm'])
+def test_layers_cuda_vs_reference(golden, tag):
+    run_layer_case(golden, tag, None, device=DEV, tol=1e-4)
+
+
+@pytest.fixture(scope='module')
+def cuda_generator():
+    G = N.build_generator_full().eval()
+    procedural.fill_(G)
+    return G.to(DEV).requires_grad_(False)
+
+
+def test_generator_cuda_vs_reference(golden, cuda_generator):
+    g = golden('generator_full')
+    G = cuda_generator
+    inp = procedural.synth_inputs(2, device=DEV)
+    with torch.no_grad():
+        pose_feat = G.const_encoding(inp['pose'])
+        stylecode, feats = G.style_encoding(inp['c'], inp['retain'])
+        assert rel_err(pose_feat, g.t('pose_feat')) < 1e-2
+        assert rel_err(stylecode, g.t('stylecode')) < 1e-2
+        assert rel_err(feats[2][:, :, ::4, ::4], g.t('feat64')) < 1e-2
+        img, fimg, parsing = G(**inp, noise_mode='const')
+    errs = dict(img=rel_err(img, g.t('img', dtype=torch.float32)), fimg=rel_err(fimg, g.t('finetune_img', dtype=torch.float32)),
+                parsing=rel_err(parsing, g.t('pred_parsing', dtype=torch.float32)))
+    print('generator rel errs', errs)
+    assert all(v < 1e-2 for v in errs.values()), errs
+
+
+def test_session_graph_matches_eager(cuda_generator):
+    from pasta_gan_b200.inference import TryOnSession
+    inp = procedural.synth_inputs(2, device=DEV)
+    with torch.no_grad():
+        ref = cuda_generator(**inp, noise_mode='const')
+    sess = TryOnSession(cuda_generator, inp, DEV, use_graph=True)
+    out = sess.step()
+    sess.synchronize()
+    for a, b in zip(out, ref):
+        assert rel_err(a, b) < 1e-5
+    host = {k: v.cpu().pin_memory() for k, v in inp.items()}
+    hout = sess.step_from_host(host)
+    sess.synchronize()
+    assert rel_err(hout[0], ref[0]) < 1e-5 and rel_err(hout[1], ref[1]) < 1e-5
+    assert sess.h2d_bytes == sum(inp[k].numel() * 4 for k in inp if k != 'z')

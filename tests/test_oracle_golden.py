@@ -126,3 +126,32 @@ def test_float64_gradcheck_oracle():
     b = torch.randn(2, dtype=torch.float64, requires_grad=True)
     assert torch.autograd.gradcheck(lambda t, bb: O.bias_act(t, bb, act='lrelu', clamp=0.7), (x, b))
     assert torch.autograd.gradgradcheck(lambda t, bb: O.bias_act(t, bb, act='swish'), (x, b))
+
+
+# ---- the lowered "fast port" used for CPU-baseline timing is pinned to the same vectors
+@pytest.mark.parametrize('i', range(17))
+def test_fast_port_upfirdn2d(golden, i):
+    g = golden('upfirdn2d')
+    m = g.meta[i]
+    y = O.upfirdn2d_fast(g.t(f'{i}/x'), _flt(g, i, m), up=m['up'], down=m['down'], padding=m['padding'], flip_filter=m['flip'], gain=m['gain'])
+    assert rel_err(y, g.t(f'{i}/y')) < TOL
+
+
+@pytest.mark.parametrize('i', range(12))
+def test_fast_port_conv2d_resample(golden, i):
+    g = golden('conv2d_resample')
+    m = g.meta[i]
+    f = None if m.get('nofilter') else g.t('f4')
+    y = O.conv2d_resample_fast(g.t(f'{i}/x'), g.t(f'{i}/w'), f=f, up=m['up'], down=m['down'], padding=m['padding'], groups=m['groups'],
+                               flip_weight=m['flip_weight'])
+    assert rel_err(y, g.t(f'{i}/y')) < TOL_CONV
+
+
+@pytest.mark.parametrize('i', range(10))
+def test_fast_port_modulated_conv2d(golden, i):
+    g = golden('modulated_conv2d')
+    m = g.meta[i]
+    noise = g.t(f'{i}/noise') if g.has(f'{i}/noise') else None
+    y = O.modulated_conv2d_fast(g.t(f'{i}/x'), g.t(f'{i}/w'), g.t(f'{i}/s'), noise=noise, up=m['up'], padding=m['k'] // 2,
+                                resample_filter=g.t('f4'), demodulate=m['demod'], flip_weight=m['flip_weight'])
+    assert rel_err(y, g.t(f'{i}/y')) < TOL_CONV
