@@ -23,7 +23,7 @@
  *   - Return value: 0 on success, a PG_ERR_* code otherwise; pg_last_error() returns a
  *     thread-local human-readable message for the last failing call on the calling thread
  *     (the reference raises RuntimeError through TORCH_CHECK / AT_CUDA_CHECK).
- *   - Entry points are re-entrant and keep no mutable global state: they are called under the GIL
+ *   - Entry points are re-entrant and keep no mutable global state (bar a statistics counter): they are called under the GIL
  *     from the forward pass and from autograd worker threads in backward.
  *   - There is no CPU implementation behind any of these symbols.
  */
@@ -116,6 +116,34 @@ int pg_upfirdn2d_bias_act(const void* x, const float* f, const void* b, void* y,
                           int32_t flip, float gain,
                           int32_t act, float alpha, float act_gain, float clamp,
                           int32_t dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * conv2d_igemm — tcgen05 / TMEM implicit-GEMM convolution, fp32 NCHW in and out, fp16 or bf16 tensor-core
+ * operands with fp32 accumulation.  Replaces, in one launch, what the reference spreads over
+ *   conv2d_gradfix.conv2d / conv_transpose2d (cuDNN)           torch_utils/ops/conv2d_gradfix.py:35-43
+ *   conv2d_resample's up-2 lowering (convT + FIR, gain 4)      torch_utils/ops/conv2d_resample.py:125-142
+ *   weight modulation / demodulation / noise                   training/networks.py:64-93 (modulated_conv2d)
+ *   bias_act of the calling layer                              training/networks.py:176-179, :311-315, :4345-4349
+ *
+ *   y[n,o] = clamp( act( dcoefs[n,o] * conv( styles[n,c] * in_gain * in_act(x[n,c]) , w[o,c] ) + noise + bias[o] ) * gain )
+ *
+ * x [N,Cin,H,W] and y [N,Cout,H*up,W*up] are dense NCHW fp32.  w [Cout,Cin,k,k] fp32, k in {1,3}, stride 1, padding k/2
+ * ("same").  flip_weight != 0: cross-correlation (what conv2d computes); 0: true convolution (conv2d_resample.py:35-36).
+ * up == 2 (k == 3 only): the zero-insert + 4x4 FIR (gain 4) + 3x3 convolution of SynthesisLayer.conv0 evaluated in
+ * polyphase form on the low-resolution input; `fir` is the [4,4] float32 filter (ignored when up == 1).
+ * styles [N,Cin], dcoefs [N,Cout], bias [Cout], noise ([H*up,W*up] with noise_batch_stride 0, or per-sample with stride in
+ * elements) may each be NULL.  in_act / act: PG_ACT_LINEAR / RELU / LRELU.  clamp < 0: none.
+ * operand_format: 0 = fp16 (10-bit mantissa, saturating), 1 = bf16.
+ * workspace: device scratch of at least pg_conv2d_igemm_workspace_bytes(...) bytes (packed weights), caller-owned.
+ * Forward only: gradients of convolutions stay on conv2d_gradfix in this release.
+ */
+int64_t pg_conv2d_igemm_workspace_bytes(int32_t Cin, int32_t Cout, int32_t ksize, int32_t up);
+int pg_conv2d_igemm_fwd(const float* x, const float* w, const float* fir, const float* styles, const float* dcoefs,
+                        const float* noise, int64_t noise_batch_stride, const float* bias, float* y,
+                        int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t ksize, int32_t up,
+                        int32_t flip_weight, int32_t in_act, float in_alpha, float in_gain,
+                        int32_t act, float alpha, float gain, float clamp, int32_t operand_format,
+                        void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

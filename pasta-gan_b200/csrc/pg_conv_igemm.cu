@@ -1,0 +1,474 @@
+// Implicit-GEMM convolution for sm_100a: tcgen05.mma with TMEM accumulators, fp32 NCHW in / out.
+//
+// Replaces the cuDNN calls the reference makes for every convolution (torch_utils/ops/conv2d_gradfix.py:35-43 via
+// conv2d_resample.py:29-54) and the separate modulation / demodulation / noise / bias_act passes around them
+// (training/networks.py:37-94 modulated_conv2d, :296-315 SynthesisLayer.forward, :170-179 Conv2dLayer.forward,
+// :4342-4354 Spade_Conv2dLayer.forward).  One kernel computes
+//
+//     y[n,o,h,w] = clamp( act( d[n,o] * sum_{c,kh,kw} W[o,c,kh,kw] * (s[n,c] * in_act(x[n,c,h+kh-p,w+kw-p])) + noise[h,w] + b[o] ) * gain )
+//
+// for stride-1 "same" 3x3 and 1x1 convolutions (per-sample style s and demodulation d optional: s == 1, d == 1 is the
+// plain Conv2dLayer).  GEMM view: M = pixels of one sample, N = Cout, K = taps x Cin.
+//
+// Data layout / algorithm
+//   * The image of one sample is addressed as a flattened strip with pitch PW = W + 1: the extra column is the zero
+//     padding shared by the right edge of row h and the left edge of row h+1.  An output tile is BM = 128 * NACC
+//     consecutive strip positions; filter tap (kh, kw) of a 3x3 kernel reads strip position m + (kh-1)*PW + (kw-1).
+//   * A operand (activations): converter warps read fp32 NCHW from global/L2 (coalesced along w), apply the input
+//     activation and the per-sample style, convert to fp16/bf16 and store [plane = 8 channels][position][8 x 2 B] in
+//     shared memory.  This is the K-major SWIZZLE_NONE canonical layout with SBO = 128 B, i.e. GEMM rows are exactly
+//     16 B apart, so the nine taps are nine *descriptor start addresses* into the same staged tile: the im2col
+//     matrix is never materialised and every input element is staged once per 16-channel chunk.
+//   * B operand (weights): a prepack kernel writes fp16/bf16 tiles in the same canonical layout to a workspace
+//     ([n-tile][chunk][tap][plane][n][8]); one cp.async.bulk per chunk brings all taps of a 16-channel chunk in.
+//   * tcgen05.mma.cta_group::1.kind::f16, M = 128, N = BN (<= 256), K = 16, issued by one thread; NACC accumulators
+//     of BN fp32 columns live in TMEM (NACC * BN <= 512 columns).
+//   * Epilogue: tcgen05.ld 32x32b.x16 -> demodulate, add noise and bias, activation, gain, clamp -> coalesced fp32
+//     NCHW stores.  The convolution result never round-trips through HBM before bias_act.
+//   * mbarrier pipelines: A full/empty (converters <-> MMA), B full/empty (bulk copy <-> MMA), accumulator full.
+#include <cuda_bf16.h>
+#include "pg_common.cuh"
+
+namespace pg {
+
+constexpr int kConvWarps   = 8;                 // A converters, later the epilogue
+constexpr int kConvThreads = 64 + 32 * kConvWarps;
+constexpr int kKC          = 16;                // channels per pipeline chunk == one UMMA K step
+
+struct ConvParams {
+    const float* x; const void* wpack; const float* styles; const float* dcoefs; const float* noise; const float* bias; float* y;
+    long long noise_bstride;
+    int N, Cin, Cout, H, W, ks;
+    int PW, Lp, tiles_per_img, NACC, BN, nchunks, ntaps, PA;      // PA: staged strip positions (multiple of 32)
+    int SA, SB; uint32_t a_stage_bytes, b_stage_bytes, b_tile_bytes;
+    int in_act; float in_alpha, in_gain; int act; float alpha, gain, clamp; int fmt;
+    uint32_t idesc; uint32_t tmem_cols;
+    // up-2 polyphase mode: BN virtual channels = phases x couts (see launch code); 0 = plain
+    int up2; int cout_real;
+};
+
+// ---------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_NONE, rows 16 B apart (SBO = 128 B), K chunks `lbo_bytes` apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((128u >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;                          // descriptor version (sm_100)
+    return d;                                        // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
+    if (fmt == 0) {
+        a = fminf(fmaxf(a, -65504.f), 65504.f);      // fp16 operands saturate instead of overflowing to inf
+        b = fminf(fmaxf(b, -65504.f), 65504.f);
+        __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ---------------------------------------------------------------------------------------------- weight prepack
+// w [Cout, Cin, ks, ks] fp32  ->  [n-tile][chunk][tap][plane(2)][BN][8] fp16/bf16, zero padded in Cout and Cin.
+// flip_weight != 0: cross-correlation (taps as stored); 0: true convolution (taps mirrored).
+// up2 != 0: the 3x3 weights are first convolved with the 4x4 FIR (gain 4) into a 6x6 composite and split into the four
+// output-parity 3x3 kernels of the polyphase form; virtual channel v = phase * Cout + o.
+struct PackParams {
+    const float* w; const float* fir; void* out; int Cout, Cin, ks, BN, nchunks, ntaps, ntiles, flip_weight, fmt, up2;
+};
+
+__device__ float composite_tap(const PackParams& p, int o, int c, int a, int b, int th, int tw) {
+    // out[2y+a][2x+b] = sum_{th,tw} Kc[2*th+1-a][2*tw+1-b] * xpad1[y+th][x+tw],   Kc = w' (*) (4 k)   (6x6 full convolution)
+    // k = f flipped (upfirdn2d applies f as a true convolution), w' = w mirrored when flip_weight == 0 (true convolution with w,
+    // SynthesisLayer.conv0) or w as stored when flip_weight != 0.  Checked against the oracle to 2e-15 in fp64.
+    const int u = 2 * th + 1 - a, v = 2 * tw + 1 - b;
+    float acc = 0.f;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            const int fi = u - i, fj = v - j;
+            if (fi < 0 || fi > 3 || fj < 0 || fj > 3) continue;
+            const int wi = p.flip_weight ? i : 2 - i, wj = p.flip_weight ? j : 2 - j;
+            acc += p.w[((size_t)(o * p.Cin + c) * 3 + wi) * 3 + wj] * p.fir[(3 - fi) * 4 + (3 - fj)] * 4.f;
+        }
+    return acc;
+}
+
+__global__ void conv_prepack_kernel(PackParams p) {
+    const size_t total = (size_t)p.ntiles * p.nchunks * p.ntaps * 2 * p.BN * 8;
+    const int nvirt = p.up2 ? 4 * p.Cout : p.Cout;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        size_t r = idx;
+        const int e = r % 8; r /= 8;
+        const int nl = r % p.BN; r /= p.BN;
+        const int j = r % 2; r /= 2;
+        const int tap = r % p.ntaps; r /= p.ntaps;
+        const int ci = r % p.nchunks; r /= p.nchunks;
+        const int jn = (int)r;
+        const int v = jn * p.BN + nl, c = ci * kKC + j * 8 + e;
+        float val = 0.f;
+        if (v < nvirt && c < p.Cin) {
+            const int kh = tap / p.ks, kw = tap % p.ks;
+            if (p.up2) {
+                const int phase = v / p.Cout, o = v % p.Cout;
+                val = composite_tap(p, o, c, phase >> 1, phase & 1, kh, kw);
+            } else {
+                const int wh = p.flip_weight ? kh : p.ks - 1 - kh, ww = p.flip_weight ? kw : p.ks - 1 - kw;
+                val = p.w[((size_t)(v * p.Cin + c) * p.ks + wh) * p.ks + ww];
+            }
+        }
+        if (p.fmt == 0) ((__half*)p.out)[idx] = __float2half_rn(fminf(fmaxf(val, -65504.f), 65504.f));
+        else            ((__nv_bfloat16*)p.out)[idx] = __float2bfloat16_rn(val);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- main kernel
+__global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x % p.tiles_per_img;
+    const int n    = blockIdx.x / p.tiles_per_img;
+    const int jn   = blockIdx.y;
+    const int BM   = 128 * p.NACC;
+    const int m0   = tile * BM;
+    const int HW   = p.H * p.W;
+
+    uint8_t* a_base = smem;
+    uint8_t* b_base = a_base + (size_t)p.SA * p.a_stage_bytes;
+    float*   s_style = reinterpret_cast<float*>(b_base + (size_t)p.SB * p.b_stage_bytes);
+    const int cin_pad = p.nchunks * kKC;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_style + cin_pad);
+    uint64_t* a_full = bars, *a_empty = bars + p.SA, *b_full = bars + 2 * p.SA, *b_empty = bars + 2 * p.SA + p.SB;
+    uint64_t* acc_full = bars + 2 * p.SA + 2 * p.SB;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < p.SA; i++) { mbar_init(smem_u32(&a_full[i]), kConvWarps); mbar_init(smem_u32(&a_empty[i]), 1); }
+        for (int i = 0; i < p.SB; i++) { mbar_init(smem_u32(&b_full[i]), 1); mbar_init(smem_u32(&b_empty[i]), 1); }
+        mbar_init(smem_u32(acc_full), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // per-sample input scale: style * in_gain (1 * in_gain for plain convs); zero for padded channels
+    for (int c = threadIdx.x; c < cin_pad; c += kConvThreads)
+        s_style[c] = (c < p.Cin) ? (p.styles ? p.styles[(size_t)n * p.Cin + c] : 1.f) * p.in_gain : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== B producer: one bulk copy (all taps of a 16-channel chunk) per stage =====================
+        if (lane == 0) {
+            const uint8_t* src = (const uint8_t*)p.wpack + (size_t)jn * p.nchunks * p.b_stage_bytes;
+            int st = 0; uint32_t ph = 0;
+            for (int ci = 0; ci < p.nchunks; ci++) {
+                mbar_wait(smem_u32(&b_empty[st]), ph ^ 1);
+                mbar_expect_tx(smem_u32(&b_full[st]), p.b_stage_bytes);
+                bulk_g2s(smem_u32(b_base + (size_t)st * p.b_stage_bytes), src + (size_t)ci * p.b_stage_bytes, p.b_stage_bytes, smem_u32(&b_full[st]));
+                if (++st == p.SB) { st = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+            const uint32_t a_lbo = (uint32_t)p.PA * 16u, b_lbo = (uint32_t)p.BN * 16u;
+            for (int ci = 0; ci < p.nchunks; ci++) {
+                mbar_wait(smem_u32(&a_full[sa]), pa);
+                mbar_wait(smem_u32(&b_full[sb]), pb);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(a_base + (size_t)sa * p.a_stage_bytes);
+                const uint32_t b_addr = smem_u32(b_base + (size_t)sb * p.b_stage_bytes);
+                for (int tap = 0; tap < p.ntaps; tap++) {
+                    const int kh = tap / p.ks, kw = tap - kh * p.ks;
+                    const uint32_t s0 = (p.ks == 3) ? (uint32_t)(kh * p.PW + kw) : 0u;
+                    const uint64_t bdesc = umma_desc(b_addr + (uint32_t)tap * p.b_tile_bytes, b_lbo);
+                    for (int a = 0; a < p.NACC; a++) {
+                        const uint64_t adesc = umma_desc(a_addr + (s0 + (uint32_t)a * 128u) * 16u, a_lbo);
+                        umma_f16(tmem_base + (uint32_t)(a * p.BN), adesc, bdesc, p.idesc, (ci | tap) ? 1u : 0u);
+                    }
+                }
+                umma_commit(smem_u32(&a_empty[sa]));
+                umma_commit(smem_u32(&b_empty[sb]));
+                if (++sa == p.SA) { sa = 0; pa ^= 1; }
+                if (++sb == p.SB) { sb = 0; pb ^= 1; }
+            }
+            umma_commit(smem_u32(acc_full));
+        }
+    } else {
+        // ===================== A converters =====================
+        const int cw = warp - 2;
+        const int ngroups = p.PA / 32;
+        const int ntasks = ngroups * 2;                       // (position group, plane)
+        const int halo = (p.ks == 3) ? p.PW + 1 : 0;
+        const float* xn = p.x + (size_t)n * p.Cin * HW;
+        int st = 0; uint32_t ph = 0;
+        for (int ci = 0; ci < p.nchunks; ci++) {
+            mbar_wait(smem_u32(&a_empty[st]), ph ^ 1);
+            uint8_t* stage = a_base + (size_t)st * p.a_stage_bytes;
+            for (int t = cw; t < ntasks; t += 2 * kConvWarps) {
+                // two tasks per iteration so that 16 independent loads are in flight per thread
+                float v[2][8];
+                int   spos[2], plane[2];
+                bool  live[2];
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int tt = t + u * kConvWarps;
+                    live[u] = tt < ntasks;
+                    const int g = tt >> 1;
+                    plane[u] = tt & 1;
+                    spos[u] = g * 32 + lane;
+                    const int q = m0 - halo + spos[u];       // strip position of this staged row
+                    int h = 0, w = 0;
+                    bool ok = live[u] && q >= 0 && q < p.Lp;
+                    if (ok) { h = q / p.PW; w = q - h * p.PW; ok = w < p.W; }
+                    const int c0 = ci * kKC + plane[u] * 8;
+                    const float* src = xn + (size_t)c0 * HW + h * p.W + w;
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+                        v[u][i] = (ok && c0 + i < p.Cin) ? __ldg(src + (size_t)i * HW) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    if (!live[u]) continue;
+                    const float* sc = s_style + ci * kKC + plane[u] * 8;
+                    float t8[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        float a = v[u][i];
+                        if (p.in_act == PG_ACT_RELU)  a = fmaxf(a, 0.f);
+                        if (p.in_act == PG_ACT_LRELU) a = a > 0.f ? a : a * p.in_alpha;
+                        t8[i] = a * sc[i];
+                    }
+                    uint4 pk;
+                    pk.x = pack2(t8[0], t8[1], p.fmt); pk.y = pack2(t8[2], t8[3], p.fmt);
+                    pk.z = pack2(t8[4], t8[5], p.fmt); pk.w = pack2(t8[6], t8[7], p.fmt);
+                    *reinterpret_cast<uint4*>(stage + (size_t)plane[u] * p.PA * 16 + (size_t)spos[u] * 16) = pk;
+                }
+            }
+            fence_proxy_async();                               // generic-proxy stores -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&a_full[st]));
+            if (++st == p.SA) { st = 0; ph ^= 1; }
+        }
+
+        // ===================== epilogue (same warps) =====================
+        mbar_wait(smem_u32(acc_full), 0);
+        tc_fence_after();
+        const int quarter = warp & 3;                          // TMEM lane quarter this warp may read
+        const int half = cw >> 2;                              // the two warps of a quarter alternate 16-column chunks
+        const int ncol_chunks = p.BN / 16;
+        const float* dco = p.dcoefs ? p.dcoefs + (size_t)n * p.cout_real : nullptr;
+        for (int a = 0; a < p.NACC; a++) {
+            const int q = m0 + a * 128 + quarter * 32 + lane;
+            const int h = q / p.PW, w = q - h * p.PW;
+            const bool ok = q < p.Lp && w < p.W;
+            for (int cc = half; cc < ncol_chunks; cc += 2) {
+                uint32_t r[16];
+                tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.BN + cc * 16), r);
+                if (!ok) continue;
+                if (!p.up2) {
+                    const float nz = p.noise ? __ldg(p.noise + (size_t)n * p.noise_bstride + (size_t)h * p.W + w) : 0.f;
+                    float* yp = p.y + ((size_t)n * p.Cout) * HW + (size_t)h * p.W + w;
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const int o = jn * p.BN + cc * 16 + i;
+                        if (o >= p.Cout) break;
+                        float v = __uint_as_float(r[i]);
+                        if (dco) v *= __ldg(dco + o);
+                        v += nz;
+                        if (p.bias) v += __ldg(p.bias + o);
+                        if (p.act == PG_ACT_RELU)  v = fmaxf(v, 0.f);
+                        if (p.act == PG_ACT_LRELU) v = v > 0.f ? v : v * p.alpha;
+                        v *= p.gain;
+                        if (p.clamp >= 0.f) v = fminf(fmaxf(v, -p.clamp), p.clamp);
+                        yp[(size_t)o * HW] = v;
+                    }
+                } else {
+                    // polyphase up-2: virtual channel = phase * Cout + o, phase = 2*a_y + b_x; output is 2H x 2W
+                    const int W2 = 2 * p.W; const size_t HW4 = (size_t)4 * HW;
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const int vch = jn * p.BN + cc * 16 + i;
+                        if (vch >= 4 * p.cout_real) break;
+                        const int phase = vch / p.cout_real, o = vch - phase * p.cout_real;
+                        const int oy = 2 * h + (phase >> 1), ox = 2 * w + (phase & 1);
+                        float v = __uint_as_float(r[i]);
+                        if (dco) v *= __ldg(dco + o);
+                        if (p.noise) v += __ldg(p.noise + (size_t)n * p.noise_bstride + (size_t)oy * W2 + ox);
+                        if (p.bias) v += __ldg(p.bias + o);
+                        if (p.act == PG_ACT_RELU)  v = fmaxf(v, 0.f);
+                        if (p.act == PG_ACT_LRELU) v = v > 0.f ? v : v * p.alpha;
+                        v *= p.gain;
+                        if (p.clamp >= 0.f) v = fminf(fmaxf(v, -p.clamp), p.clamp);
+                        p.y[((size_t)n * p.cout_real + o) * HW4 + (size_t)oy * W2 + ox] = v;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+struct ConvPlan {
+    int BN, ntiles_n, nchunks, ntaps, NACC, PW, Lp, tiles_per_img, PA, SA, SB;
+    uint32_t a_stage, b_stage, b_tile; size_t smem; uint32_t tmem_cols; int nvirt;
+};
+
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int ks, int up2) {
+    pl.nvirt = up2 ? 4 * Cout : Cout;
+    pl.ntaps = ks * ks;
+    pl.nchunks = (Cin + kKC - 1) / kKC;
+    int bn = round_up(pl.nvirt, 16);
+    if (bn > 256) bn = 256;
+    if (up2 && pl.nvirt > 256) bn = (2 * Cout <= 256 && (2 * Cout) % 16 == 0) ? 2 * Cout : 256;   // keep both x-phases of a row parity together
+    pl.BN = bn;
+    pl.ntiles_n = (pl.nvirt + bn - 1) / bn;
+    pl.PW = (ks == 3) ? W + 1 : W;
+    pl.Lp = H * pl.PW;
+    const int max_acc = 512 / bn;
+    // accumulators per CTA: as many as fit, but keep >= 2 waves of CTAs on 148 SMs when the problem allows it
+    int nacc = 1;
+    for (int cand = (max_acc < 4 ? max_acc : 4); cand >= 1; cand >>= 1) {
+        const long long ctas = (long long)N * ((pl.Lp + 128 * cand - 1) / (128 * cand)) * pl.ntiles_n;
+        if (ctas >= 2 * kNumSMs || cand == 1) { nacc = cand; break; }
+    }
+    while (nacc > 1 && 128 * (nacc - 1) >= pl.Lp) nacc--;
+    pl.NACC = nacc;
+    const int BM = 128 * nacc;
+    pl.tiles_per_img = (pl.Lp + BM - 1) / BM;
+    const int halo = (ks == 3) ? 2 * pl.PW + 2 : 0;
+    pl.PA = round_up(BM + halo, 32);
+    pl.a_stage = (uint32_t)pl.PA * 32u;                        // 2 planes x 16 B per position
+    pl.b_tile = (uint32_t)bn * 32u;
+    pl.b_stage = pl.b_tile * pl.ntaps;
+    const size_t fixed = (size_t)pl.nchunks * kKC * 4 + 64 * 8;
+    pl.SA = 4; pl.SB = 4;
+    auto total = [&]() { return (size_t)pl.SA * pl.a_stage + (size_t)pl.SB * pl.b_stage + fixed + 128; };
+    const size_t budget = 200 * 1024;
+    while (total() > budget && (pl.SA > 2 || pl.SB > 2)) {
+        if (pl.SB > 2 && (size_t)pl.SB * pl.b_stage >= (size_t)pl.SA * pl.a_stage) pl.SB--; else if (pl.SA > 2) pl.SA--; else pl.SB--;
+    }
+    if (total() > 225 * 1024) return fail(PG_ERR_UNSUPPORTED, "conv2d_igemm: tile does not fit shared memory (W=%d, BN=%d)", W, bn);
+    if (pl.nchunks < pl.SA) pl.SA = pl.nchunks < 2 ? 2 : pl.nchunks;
+    if (pl.nchunks < pl.SB) pl.SB = pl.nchunks < 2 ? 2 : pl.nchunks;
+    pl.smem = total();
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(nacc * bn)) cols <<= 1;
+    pl.tmem_cols = cols;
+    return PG_OK;
+}
+
+}  // namespace pg
+
+extern "C" int64_t pg_conv2d_igemm_workspace_bytes(int32_t Cin, int32_t Cout, int32_t ksize, int32_t up) {
+    pg::ConvPlan pl;
+    if (pg::make_plan(pl, 1, Cin, Cout, 8, 8, ksize, up == 2) != PG_OK) return -1;
+    return (int64_t)pl.ntiles_n * pl.nchunks * pl.b_stage;
+}
+
+extern "C" int pg_conv2d_igemm_fwd(const float* x, const float* w, const float* fir, const float* styles, const float* dcoefs,
+                                   const float* noise, int64_t noise_batch_stride, const float* bias, float* y,
+                                   int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t ksize, int32_t up,
+                                   int32_t flip_weight, int32_t in_act, float in_alpha, float in_gain,
+                                   int32_t act, float alpha, float gain, float clamp, int32_t operand_format,
+                                   void* workspace, int64_t workspace_bytes, void* stream) {
+    using namespace pg;
+    PG_REQUIRE(ksize == 1 || ksize == 3, "conv2d_igemm: kernel size must be 1 or 3 (got %d)", ksize);
+    PG_REQUIRE(up == 1 || (up == 2 && ksize == 3), "conv2d_igemm: up must be 1, or 2 with a 3x3 kernel");
+    PG_REQUIRE(N >= 0 && Cin >= 1 && Cout >= 1 && H >= 1 && W >= 1, "conv2d_igemm: bad sizes");
+    PG_REQUIRE(operand_format == 0 || operand_format == 1, "conv2d_igemm: operand_format must be 0 (fp16) or 1 (bf16)");
+    PG_REQUIRE(act == PG_ACT_LINEAR || act == PG_ACT_RELU || act == PG_ACT_LRELU, "conv2d_igemm: epilogue act must be linear/relu/lrelu");
+    PG_REQUIRE(in_act == PG_ACT_LINEAR || in_act == PG_ACT_RELU || in_act == PG_ACT_LRELU, "conv2d_igemm: input act must be linear/relu/lrelu");
+    PG_REQUIRE((int64_t)N * Cin * H * W <= INT32_MAX && (int64_t)N * Cout * H * W * (up == 2 ? 4 : 1) <= INT32_MAX, "conv2d_igemm: tensor too large");
+    PG_REQUIRE(up == 1 || fir != nullptr, "conv2d_igemm: up=2 needs the 4x4 FIR");
+    if (N == 0) return PG_OK;
+    PG_REQUIRE(x && w && y && workspace, "conv2d_igemm: x, w, y and workspace must be device pointers");
+    ConvPlan pl;
+    int rc = make_plan(pl, N, Cin, Cout, H, W, ksize, up == 2);
+    if (rc != PG_OK) return rc;
+    const int64_t need = (int64_t)pl.ntiles_n * pl.nchunks * pl.b_stage;
+    PG_REQUIRE(workspace_bytes >= need, "conv2d_igemm: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
+    cudaStream_t s = (cudaStream_t)stream;
+
+    PackParams pp;
+    pp.w = w; pp.fir = fir; pp.out = workspace; pp.Cout = Cout; pp.Cin = Cin; pp.ks = ksize; pp.BN = pl.BN; pp.nchunks = pl.nchunks;
+    pp.ntaps = pl.ntaps; pp.ntiles = pl.ntiles_n; pp.flip_weight = flip_weight ? 1 : 0; pp.fmt = operand_format; pp.up2 = up == 2;
+    const size_t pack_total = (size_t)need / 2;
+    int pblocks = (int)((pack_total + 255) / 256);
+    if (pblocks > kNumSMs * 16) pblocks = kNumSMs * 16;
+    conv_prepack_kernel<<<pblocks, 256, 0, s>>>(pp);
+
+    ConvParams p;
+    p.x = x; p.wpack = workspace; p.styles = styles; p.dcoefs = dcoefs; p.noise = noise; p.bias = bias; p.y = y;
+    p.noise_bstride = noise_batch_stride;
+    p.N = N; p.Cin = Cin; p.Cout = pl.nvirt; p.H = H; p.W = W; p.ks = ksize;
+    p.PW = pl.PW; p.Lp = pl.Lp; p.tiles_per_img = pl.tiles_per_img; p.NACC = pl.NACC; p.BN = pl.BN; p.nchunks = pl.nchunks; p.ntaps = pl.ntaps;
+    p.PA = pl.PA; p.SA = pl.SA; p.SB = pl.SB; p.a_stage_bytes = pl.a_stage; p.b_stage_bytes = pl.b_stage; p.b_tile_bytes = pl.b_tile;
+    p.in_act = in_act; p.in_alpha = in_alpha; p.in_gain = in_gain; p.act = act; p.alpha = alpha; p.gain = gain; p.clamp = clamp; p.fmt = operand_format;
+    p.idesc = (1u << 4) | ((uint32_t)operand_format << 7) | ((uint32_t)operand_format << 10) | ((uint32_t)(pl.BN >> 3) << 17) | (8u << 24);
+    p.tmem_cols = pl.tmem_cols;
+    p.up2 = up == 2; p.cout_real = Cout;
+    PG_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    dim3 grid((unsigned)(N * pl.tiles_per_img), (unsigned)pl.ntiles_n);
+    conv_igemm_kernel<<<grid, kConvThreads, pl.smem, s>>>(p);
+    return launch_status("conv2d_igemm", 2);
+}

@@ -1,0 +1,87 @@
+"""tcgen05 / TMEM implicit-GEMM convolution (``pg_conv2d_igemm_fwd``) — the B200 replacement for the cuDNN calls behind
+``conv2d_gradfix`` plus the modulation / demodulation / noise / bias_act passes the reference runs around them
+(training/networks.py:37-94, :170-179, :296-315, :4342-4354).
+
+Forward only: it is used when no gradient is required (inference); under autograd the callers keep the
+``conv2d_gradfix`` route.  fp32 NCHW in / out, fp16 (default) or bf16 operands, fp32 accumulation in TMEM.
+"""
+import os
+
+import torch
+
+from . import _backend
+
+_ACT = {'linear': 1, 'relu': 2, 'lrelu': 3}
+_FMT = {'fp16': 0, 'bf16': 1}
+
+enabled = os.environ.get('PASTA_B200_CONV', '1') != '0'
+operand_format = os.environ.get('PASTA_B200_CONV_FMT', 'fp16')
+
+
+def supported(x, w, up=1, down=1, groups=1, f=None, padding=None, flip_filter=False):
+    """Shapes the kernel covers: dense fp32 NCHW on CUDA, 1x1 / 3x3, stride 1, 'same' padding, optional polyphase up-2."""
+    if not (enabled and x.is_cuda and x.dtype == torch.float32 and w.dtype == torch.float32 and x.ndim == 4):
+        return False
+    if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad):
+        return False
+    if groups != 1 or down != 1 or up not in (1, 2) or w.shape[2] != w.shape[3] or w.shape[2] not in (1, 3):
+        return False
+    k = int(w.shape[2])
+    if padding is not None and tuple(padding) != (k // 2,) * 4:
+        return False
+    if up == 2 and (k != 3 or f is None or f.ndim != 2 or tuple(f.shape) != (4, 4) or flip_filter):
+        return False
+    if x.numel() == 0 or x.numel() > 2 ** 31 - 1:
+        return False
+    return True
+
+
+def conv2d_igemm(x, w, f=None, up=1, flip_weight=True, styles=None, dcoefs=None, noise=None, bias=None,
+                 in_act='linear', in_alpha=0.2, in_gain=1.0, act='linear', alpha=0.2, gain=1.0, clamp=None, fmt=None):
+    """y = clamp(act(dcoefs * conv(styles * in_gain * in_act(x), w) + noise + bias) * gain); see include/pasta_b200.h."""
+    capi = _backend.capi()
+    _backend.require_cuda(x, 'conv2d_igemm')
+    n, cin, h, wd = (int(v) for v in x.shape)
+    cout, cin_w, k, _ = (int(v) for v in w.shape)
+    assert cin_w == cin, 'weight / input channel mismatch'
+    x = x.contiguous()
+    w = w.contiguous()
+    y = torch.empty([n, cout, h * up, wd * up], dtype=torch.float32, device=x.device)
+    lib = capi.load()
+    ws_bytes = int(lib.pg_conv2d_igemm_workspace_bytes(cin, cout, k, up))
+    if ws_bytes < 0:
+        capi.check(2, 'pg_conv2d_igemm_workspace_bytes')
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    nb_stride = 0
+    if noise is not None:
+        noise = noise.to(torch.float32).contiguous()
+        assert noise.shape[-2:] == (h * up, wd * up), 'noise must match the output resolution'
+        if noise.ndim == 4:
+            assert noise.shape[1] == 1
+            nb_stride = 0 if noise.shape[0] == 1 else h * up * wd * up
+        else:
+            assert noise.ndim == 2
+    opt = lambda t: None if t is None else t.to(torch.float32).contiguous()
+    styles, dcoefs, bias = opt(styles), opt(dcoefs), opt(bias)
+    if styles is not None:
+        assert tuple(styles.shape) == (n, cin)
+    if dcoefs is not None:
+        assert tuple(dcoefs.shape) == (n, cout)
+    if bias is not None:
+        assert tuple(bias.shape) == (cout,)
+    if up == 2:
+        f = f.to(torch.float32).contiguous()
+    with torch.cuda.device(x.device):
+        capi.require_device()
+        sp = capi.span('conv_igemm', flops=2 * n * cout * cin * k * k * h * wd * (4 if up == 2 else 1),
+                       nbytes=4 * (x.numel() + y.numel() + w.numel()))
+        rc = lib.pg_conv2d_igemm_fwd(capi.ptr(x), capi.ptr(w), capi.ptr(f) if up == 2 else None, capi.ptr(styles), capi.ptr(dcoefs),
+                                     capi.ptr(noise), nb_stride, capi.ptr(bias), capi.ptr(y),
+                                     n, cin, cout, h, wd, k, up, int(bool(flip_weight)),
+                                     _ACT[in_act], float(in_alpha), float(in_gain),
+                                     _ACT[act], float(alpha), float(gain), float(-1 if clamp is None else clamp),
+                                     _FMT[fmt or operand_format], capi.ptr(ws), ws_bytes, capi.current_stream(x.device))
+        capi.check(rc, 'pg_conv2d_igemm_fwd')
+        if sp:
+            sp.close()
+    return y

@@ -1,0 +1,96 @@
+"""GPU parity of the tcgen05 implicit-GEMM convolution against the CPU oracle (fp64 reference on the same inputs).
+
+Tolerance: operands are rounded to fp16 (10-bit mantissa, the TF32 mantissa) or bf16 (7-bit) before the tensor-core
+product, accumulation is fp32: 2e-3 relative (max-abs / max-abs) for fp16 operands, 1.5e-2 for bf16, per convolution.
+The north_star bound for this kernel is 1e-2 relative on generator outputs (checked in test_gpu_network.py)."""
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import ops_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+TOL = {'fp16': 2e-3, 'bf16': 1.5e-2}
+
+
+@pytest.fixture(scope='module')
+def cv():
+    from pasta_gan_b200.torch_utils.ops import conv_igemm
+    return conv_igemm
+
+
+PLAIN = [
+    # (N, Cin, Cout, H, W, k)
+    (1, 16, 16, 8, 8, 3), (2, 32, 16, 16, 16, 3), (1, 64, 64, 32, 32, 3), (2, 128, 128, 32, 32, 3),
+    (1, 64, 64, 64, 64, 1), (2, 48, 24, 20, 28, 3), (1, 3, 64, 33, 31, 3), (2, 42, 64, 16, 16, 1),
+    (1, 512, 512, 4, 4, 3), (1, 512, 512, 16, 16, 3), (1, 256, 128, 64, 64, 3), (2, 64, 3, 32, 32, 1),
+    (1, 192, 128, 40, 40, 1), (1, 64, 64, 128, 128, 3), (3, 20, 300, 12, 12, 3),
+]
+
+
+@pytest.mark.parametrize('shape', PLAIN, ids=[str(s) for s in PLAIN])
+@pytest.mark.parametrize('fmt', ['fp16', 'bf16'])
+def test_plain_conv(cv, shape, fmt):
+    n, cin, cout, h, w, k = shape
+    torch.manual_seed(sum(shape))
+    x = torch.randn(n, cin, h, w)
+    wt = torch.randn(cout, cin, k, k) / (cin * k * k) ** 0.5
+    for flip_weight in (True, False):
+        ref = O._conv(x.double(), wt.double(), padding=k // 2, flip_weight=flip_weight)
+        y = cv.conv2d_igemm(x.to(DEV), wt.to(DEV), flip_weight=flip_weight, fmt=fmt)
+        assert y.shape == ref.shape
+        assert rel_err(y, ref) < TOL[fmt], (shape, flip_weight)
+
+
+def test_fused_epilogue_and_modulation(cv):
+    """SynthesisLayer in one launch: styles, demodulation, noise, bias, lrelu, gain, clamp."""
+    torch.manual_seed(1)
+    n, cin, cout, h = 3, 64, 48, 24
+    x = torch.randn(n, cin, h, h)
+    wt = torch.randn(cout, cin, 3, 3)
+    s = 1 + 0.5 * torch.randn(n, cin)
+    noise = torch.randn(h, h) * 0.3
+    b = torch.randn(cout) * 0.2
+    ref = O.bias_act(O.modulated_conv2d(x.double(), wt.double(), s.double(), noise=noise.double(), padding=1), b.double(), act='lrelu', gain=1.2, clamp=1.5)
+    d = (s.square() @ wt.square().sum(dim=[2, 3]).t() + 1e-8).rsqrt()
+    y = cv.conv2d_igemm(x.to(DEV), wt.to(DEV), styles=s.to(DEV), dcoefs=d.to(DEV), noise=noise.to(DEV), bias=b.to(DEV),
+                        act='lrelu', gain=1.2, clamp=1.5)
+    assert rel_err(y, ref) < 3e-3
+    # per-sample (random-mode) noise and a SPADE-style pre-activation
+    nz = torch.randn(n, 1, h, h) * 0.3
+    ref2 = O._conv(O.bias_act(x.double(), act='relu', gain=2 ** 0.5), wt.double() / 24, padding=1) + nz.double()
+    y2 = cv.conv2d_igemm(x.to(DEV), (wt / 24).to(DEV), noise=nz.to(DEV), in_act='relu', in_gain=2 ** 0.5)
+    assert rel_err(y2, ref2) < 3e-3
+
+
+UP2 = [(1, 16, 16, 8, 8), (2, 64, 32, 16, 16), (1, 128, 64, 32, 32), (2, 32, 128, 12, 20), (1, 512, 512, 4, 4), (1, 128, 64, 128, 128)]
+
+
+@pytest.mark.parametrize('shape', UP2, ids=[str(s) for s in UP2])
+def test_up2_polyphase(cv, shape):
+    """conv2d_resample(up=2, k=3, padding=1) == zero-insert + FIR(gain 4) + conv, evaluated on the low-res input."""
+    n, cin, cout, h, w = shape
+    torch.manual_seed(sum(shape))
+    f = O.setup_filter([1, 3, 3, 1])
+    x = torch.randn(n, cin, h, w)
+    wt = torch.randn(cout, cin, 3, 3) / (cin * 9) ** 0.5
+    for flip_weight in (False, True):
+        ref = O.conv2d_resample(x.double(), wt.double(), f=f.double(), up=2, padding=1, flip_weight=flip_weight)
+        y = cv.conv2d_igemm(x.to(DEV), wt.to(DEV), f=f.to(DEV), up=2, flip_weight=flip_weight)
+        assert y.shape == ref.shape
+        assert rel_err(y, ref) < 3e-3, (shape, flip_weight)
+
+
+def test_linearity_at_baseline_size(cv):
+    """[16,128,128,128] -> 128 channels (the SPADE-block shape that carries 71 % of the generator's FLOPs): linear in x, and
+    one sample's first output channels match the oracle."""
+    torch.manual_seed(3)
+    x1 = torch.randn(16, 128, 128, 128, device=DEV)
+    x2 = torch.randn(16, 128, 128, 128, device=DEV)
+    wt = torch.randn(128, 128, 3, 3, device=DEV) / (128 * 9) ** 0.5
+    y1, y2 = cv.conv2d_igemm(x1, wt), cv.conv2d_igemm(x2, wt)
+    y12 = cv.conv2d_igemm(x1 + x2, wt)
+    assert rel_err(y12, y1 + y2) < 3e-3
+    ref = O._conv(x1[5:6].cpu().double(), wt[:8].cpu().double(), padding=1)
+    assert rel_err(y1[5:6, :8], ref) < 2e-3
