@@ -34,6 +34,7 @@ namespace pg {
 constexpr int kConvWarps   = 8;                 // A converters, later the epilogue
 constexpr int kConvThreads = 64 + 32 * kConvWarps;
 constexpr int kKC          = 16;                // channels per pipeline chunk == one UMMA K step
+constexpr int kTaskBatch   = 7;                 // converter tasks (8 channels x 32 positions) loaded back to back per warp
 
 struct ConvParams {
     const float* x; const void* wpack; const float* styles; const float* dcoefs; const float* noise; const float* bias; float* y;
@@ -257,32 +258,29 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         for (int ci = 0; ci < p.nchunks; ci++) {
             mbar_wait(smem_u32(&a_empty[st]), ph ^ 1);
             uint8_t* stage = a_base + (size_t)st * p.a_stage_bytes;
-            for (int t = cw; t < ntasks; t += 2 * kConvWarps) {
-                // two tasks per iteration so that 16 independent loads are in flight per thread
-                float v[2][8];
-                int   spos[2], plane[2];
-                bool  live[2];
+            for (int t = cw; t < ntasks; t += kTaskBatch * kConvWarps) {
+                // a whole batch of tasks is loaded before any is converted: up to 8 * kTaskBatch independent L2/HBM loads
+                // in flight per thread, so a chunk costs one memory latency instead of one per task
+                float v[kTaskBatch][8];
 #pragma unroll
-                for (int u = 0; u < 2; u++) {
+                for (int u = 0; u < kTaskBatch; u++) {
                     const int tt = t + u * kConvWarps;
-                    live[u] = tt < ntasks;
-                    const int g = tt >> 1;
-                    plane[u] = tt & 1;
-                    spos[u] = g * 32 + lane;
-                    const int q = m0 - halo + spos[u];       // strip position of this staged row
+                    const int q = m0 - halo + (tt >> 1) * 32 + lane;          // strip position of this staged row
                     int h = 0, w = 0;
-                    bool ok = live[u] && q >= 0 && q < p.Lp;
+                    bool ok = tt < ntasks && q >= 0 && q < p.Lp;
                     if (ok) { h = q / p.PW; w = q - h * p.PW; ok = w < p.W; }
-                    const int c0 = ci * kKC + plane[u] * 8;
+                    const int c0 = ci * kKC + (tt & 1) * 8;
                     const float* src = xn + (size_t)c0 * HW + h * p.W + w;
 #pragma unroll
                     for (int i = 0; i < 8; i++)
                         v[u][i] = (ok && c0 + i < p.Cin) ? __ldg(src + (size_t)i * HW) : 0.f;
                 }
 #pragma unroll
-                for (int u = 0; u < 2; u++) {
-                    if (!live[u]) continue;
-                    const float* sc = s_style + ci * kKC + plane[u] * 8;
+                for (int u = 0; u < kTaskBatch; u++) {
+                    const int tt = t + u * kConvWarps;
+                    if (tt >= ntasks) break;
+                    const int plane = tt & 1, spos = (tt >> 1) * 32 + lane;
+                    const float* sc = s_style + ci * kKC + plane * 8;
                     float t8[8];
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
@@ -294,7 +292,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                     uint4 pk;
                     pk.x = pack2(t8[0], t8[1], p.fmt); pk.y = pack2(t8[2], t8[3], p.fmt);
                     pk.z = pack2(t8[4], t8[5], p.fmt); pk.w = pack2(t8[6], t8[7], p.fmt);
-                    *reinterpret_cast<uint4*>(stage + (size_t)plane[u] * p.PA * 16 + (size_t)spos[u] * 16) = pk;
+                    *reinterpret_cast<uint4*>(stage + (size_t)plane * p.PA * 16 + (size_t)spos * 16) = pk;
                 }
             }
             fence_proxy_async();                               // generic-proxy stores -> visible to the tensor core (async proxy)

@@ -50,7 +50,7 @@ def cuda_ops():
             name='sm100a',
             setup_filter=U.setup_filter, upfirdn2d=U.upfirdn2d, filter2d=U.filter2d, upsample2d=U.upsample2d,
             downsample2d=U.downsample2d, bias_act=B.bias_act, conv2d_resample=C.conv2d_resample, fma=F.fma,
-            modulated_conv2d=modulated_conv2d,
+            modulated_conv2d=modulated_conv2d, conv_layer=conv_layer, modconv_layer=modconv_layer,
             act_def_gain={k: float(v.def_gain) for k, v in B.activation_funcs.items()},
         )
     return _CUDA_OPS
@@ -126,6 +126,44 @@ def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, res
     return x
 
 
+def conv_layer(x, w, b=None, f=None, up=1, down=1, padding=0, flip_weight=True, act='linear', act_gain=1.0, clamp=None,
+               in_act=None, in_gain=1.0):
+    """Product form of one plain conv layer: [in_act(x) * in_gain ->] conv2d_resample -> bias_act.  When the tcgen05 kernel covers
+    the shape the whole layer is ONE launch (bias, activation, gain and clamp live in the GEMM epilogue; the SPADE pre-activation
+    lives in the operand prologue); otherwise it is composed from the same operators the reference calls."""
+    from .torch_utils.ops import conv_igemm as K, conv2d_resample as C, bias_act as B
+    pad4 = (padding,) * 4 if isinstance(padding, int) else None
+    if act in ('linear', 'relu', 'lrelu') and in_act in (None, 'relu', 'lrelu') and \
+            K.supported(x, w, up=up, down=down, f=f, padding=pad4):
+        return K.conv2d_igemm(x, w, f=f, up=up, flip_weight=flip_weight, bias=b, in_act=in_act or 'linear', in_gain=in_gain,
+                              act=act, gain=act_gain, clamp=clamp)
+    if in_act is not None:
+        x = B.bias_act(x, None, act=in_act, gain=in_gain)
+    x = C.conv2d_resample(x=x, w=w, f=f, up=up, down=down, padding=padding, flip_weight=flip_weight)
+    if b is None and act == 'linear' and act_gain == 1 and clamp is None:
+        return x
+    return B.bias_act(x, b, act=act, gain=act_gain, clamp=clamp)
+
+
+def modconv_layer(x, weight, styles, noise=None, up=1, padding=0, resample_filter=None, demodulate=True, flip_weight=True,
+                  fused_modconv=True, bias=None, act='linear', act_gain=1.0, clamp=None):
+    """Product form of modulated_conv2d + bias_act (SynthesisLayer / ToRGB): one tcgen05 launch with the style folded into the
+    activation operand, demodulation / noise / bias / activation / clamp in the epilogue."""
+    from .torch_utils.ops import conv_igemm as K, bias_act as B
+    k = int(weight.shape[2])
+    if act in ('linear', 'relu', 'lrelu') and padding == k // 2 and \
+            K.supported(x, weight, up=up, f=resample_filter, padding=(padding,) * 4) and not styles.requires_grad:
+        dcoefs = None
+        if demodulate:
+            wsq = weight.square().sum(dim=[2, 3])
+            dcoefs = torch.addmm(torch.full([1, 1], 1e-8, device=x.device), styles.square(), wsq.t()).rsqrt()
+        return K.conv2d_igemm(x, weight, f=resample_filter, up=up, flip_weight=flip_weight, styles=styles, dcoefs=dcoefs, noise=noise,
+                              bias=bias, act=act, gain=act_gain, clamp=clamp)
+    x = modulated_conv2d(x=x, weight=weight, styles=styles, noise=noise, up=up, padding=padding, resample_filter=resample_filter,
+                         demodulate=demodulate, flip_weight=flip_weight, fused_modconv=fused_modconv)
+    return B.bias_act(x, bias, act=act, gain=act_gain, clamp=clamp)
+
+
 # ----------------------------------------------------------------------------- layers
 
 
@@ -184,8 +222,26 @@ class Conv2dLayer(OpsModule):
         clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
         return self.ops.bias_act(x, b, act=self.activation, gain=self.act_gain * gain, clamp=clamp)
 
+    def _fused(self, x, gain, pre_act):
+        """One-launch layer when the operator table offers it (the CUDA product does; the oracle table does not)."""
+        layer = getattr(self.ops, 'conv_layer', None)
+        if layer is None or self.down != 1:
+            return None
+        w = (self.weight * self.weight_gain).to(x.dtype)
+        b = self.bias.to(x.dtype) if self.bias is not None else None
+        clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
+        kw = dict(f=self.resample_filter, up=self.up, down=self.down, padding=self.padding, flip_weight=(self.up == 1))
+        if pre_act is None:
+            return layer(x, w, b, act=self.activation, act_gain=self.act_gain * gain, clamp=clamp, **kw)
+        if not pre_act:                                   # SPADE layer called with no_act=True: bare convolution
+            return layer(x, w, None, **kw)
+        if b is not None or clamp is not None or self.activation not in ('relu', 'lrelu'):
+            return None
+        return layer(x, w, None, in_act=self.activation, in_gain=self.act_gain * gain, **kw)
+
     def forward(self, x, gain=1):
-        return self._act(self._conv(x), gain)
+        y = self._fused(x, gain, None)
+        return y if y is not None else self._act(self._conv(x), gain)
 
 
 class SpadeConv2dLayer(Conv2dLayer):
@@ -193,6 +249,9 @@ class SpadeConv2dLayer(Conv2dLayer):
         super().__init__(in_channels, out_channels, kernel_size, bias=bias, activation=activation, **kw)
 
     def forward(self, x, gain=1, no_act=False):
+        y = self._fused(x, gain, not no_act)
+        if y is not None:
+            return y
         if not no_act:
             x = self._act(x, gain)
         return self._conv(x)
@@ -263,9 +322,14 @@ class SynthesisLayer(OpsModule):
             noise = torch.randn([x.shape[0], 1, self.resolution, self.resolution], device=x.device) * self.noise_strength
         if self.use_noise and noise_mode == 'const':
             noise = self.noise_const * self.noise_strength
+        clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
+        layer = getattr(self.ops, 'modconv_layer', None)
+        if layer is not None:
+            return layer(x, self.weight, styles, noise=noise, up=self.up, padding=self.padding, resample_filter=self.resample_filter,
+                         flip_weight=(self.up == 1), fused_modconv=fused_modconv, bias=self.bias.to(x.dtype), act=self.activation,
+                         act_gain=self.act_gain * gain, clamp=clamp)
         x = self.ops.modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=noise, up=self.up, padding=self.padding,
                                       resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv)
-        clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
         return self.ops.bias_act(x, self.bias.to(x.dtype), act=self.activation, gain=self.act_gain * gain, clamp=clamp)
 
 
@@ -287,12 +351,16 @@ class ToRGBLayerFull(OpsModule):
 
     def forward(self, x, w, fused_modconv=True):
         styles = self.affine(w) * self.weight_gain
-        parsing = None
-        if self.predicts_parsing:
-            parsing = self.ops.modulated_conv2d(x=x, weight=self.m_weight1, styles=styles, demodulate=False, fused_modconv=fused_modconv)
-            parsing = self.ops.bias_act(parsing, self.m_bias1.to(x.dtype), clamp=self.conv_clamp)
-        x = self.ops.modulated_conv2d(x=x, weight=self.weight, styles=styles, demodulate=False, fused_modconv=fused_modconv)
-        return self.ops.bias_act(x, self.bias.to(x.dtype), clamp=self.conv_clamp), parsing
+        layer = getattr(self.ops, 'modconv_layer', None)
+
+        def head(weight, bias):
+            if layer is not None:
+                return layer(x, weight, styles, demodulate=False, fused_modconv=fused_modconv, bias=bias.to(x.dtype), clamp=self.conv_clamp)
+            y = self.ops.modulated_conv2d(x=x, weight=weight, styles=styles, demodulate=False, fused_modconv=fused_modconv)
+            return self.ops.bias_act(y, bias.to(x.dtype), clamp=self.conv_clamp)
+
+        parsing = head(self.m_weight1, self.m_bias1) if self.predicts_parsing else None
+        return head(self.weight, self.bias), parsing
 
 
 class ResBlock(OpsModule):

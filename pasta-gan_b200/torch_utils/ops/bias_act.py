@@ -89,6 +89,11 @@ def _kernel(x, b, xref, yref, dy, grad, dim, cfg):
     return y
 
 
+def _sum_to_bias(t, dim):
+    dims = [i for i in range(t.ndim) if i != dim]
+    return t.sum(dims) if dims else t          # 1-D input: nothing to reduce (sum([]) would reduce everything)
+
+
 class _BiasAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, b, dim, act, cfg):
@@ -116,7 +121,7 @@ class _BiasAct(torch.autograd.Function):
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             dx = dy if ctx.trivial else _BiasActGrad.apply(dy, x, b, y, ctx.dim, ctx.act, ctx.cfg)
         if ctx.needs_input_grad[1]:
-            db = dx.sum([i for i in range(dx.ndim) if i != ctx.dim])
+            db = _sum_to_bias(dx, ctx.dim)
         return dx, db, None, None, None
 
 
@@ -143,7 +148,7 @@ class _BiasActGrad(torch.autograd.Function):
         if spec.has_2nd_grad and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]):
             d_x = _kernel(d_dx, b, x, y, dy, 2, ctx.dim, ctx.cfg)
         if spec.has_2nd_grad and ctx.needs_input_grad[2]:
-            d_b = d_x.sum([i for i in range(d_x.ndim) if i != ctx.dim])
+            d_b = _sum_to_bias(d_x, ctx.dim)
         return d_dy, d_x, d_b, None, None, None, None
 
 

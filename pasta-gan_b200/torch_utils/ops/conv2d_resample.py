@@ -11,6 +11,7 @@ import torch
 from .. import misc
 from . import _backend
 from . import conv2d_gradfix
+from . import conv_igemm
 from . import upfirdn2d
 from .upfirdn2d import _get_filter_size, _parse_padding
 
@@ -62,6 +63,11 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
         px1 += (fw - down) // 2
         py0 += (fh - down + 1) // 2
         py1 += (fh - down) // 2
+    # tcgen05 implicit-GEMM path (inference, dense fp32 NCHW): plain 'same' 1x1 / 3x3 convolutions, and the up-2 3x3 form
+    # evaluated polyphase on the low-resolution input (no (2H+1)^2 intermediate, no separate FIR pass).
+    if conv_igemm.supported(x, w, up=up, down=down, groups=groups, f=f, padding=_parse_padding(padding), flip_filter=flip_filter):
+        return conv_igemm.conv2d_igemm(x, w, f=f, up=up, flip_weight=flip_weight)
+
     pad = [px0, px1, py0, py1]
     pointwise = (kw == 1 and kh == 1)
 

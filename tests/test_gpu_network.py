@@ -26,7 +26,8 @@ def _fp32_convs():
 @pytest.mark.parametrize('tag', ['synth_s1_eval', 'synth_s1_train', 'synth_up_eval', 'synth_up_train', 'torgb_eval', 'torgb_train',
                                  'conv_plain', 'conv_down', 'conv_up', 'conv_7x7', 'resblock_down', 'fc_lrelu', 'fc_linear', 'dense', 'spade_norm'])
 def test_layers_cuda_vs_reference(golden, tag):
-    run_layer_case(golden, tag, None, device=DEV, tol=1e-4)
+    # convolutions run on the tcgen05 kernel with fp16 operands (10-bit mantissa): 3e-3 per layer; pure fp32 layers stay at 1e-4
+    run_layer_case(golden, tag, None, device=DEV, tol=(1e-4 if tag in ('fc_lrelu', 'fc_linear', 'dense') else 3e-3))
 
 
 @pytest.fixture(scope='module')

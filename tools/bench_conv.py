@@ -1,0 +1,75 @@
+#!/usr/bin/env python
+"""Convolution microbenchmark: tcgen05 implicit-GEMM (ours) vs the library convolution the reference calls (cuDNN, TF32 on
+and off), at the generator's layer shapes, N = 16.  FLOPs per SURVEY.md §8(d): 2*N*Cout*Cin*k*k*Hout*Wout (stride 1) and
+2*N*Cout*Cin*9*Hin*Win for up-2 (zero taps excluded)."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from pasta_gan_b200.torch_utils.ops import conv_igemm, conv2d_resample, upfirdn2d  # noqa: E402
+
+
+def timeit(fn, iters=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in evs)
+    return ts[len(ts) // 2] * 1e-3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--out', default=None)
+    ap.add_argument('--n', type=int, default=16)
+    a = ap.parse_args()
+    dev = torch.device('cuda:0')
+    N = a.n
+    peak = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['bf16_tflops'] if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else 1590.0
+    f = upfirdn2d.setup_filter([1, 3, 3, 1]).to(dev)
+    shapes = [  # (Cin, Cout, res_in, k, up)
+        (512, 512, 4, 3, 1), (512, 512, 8, 3, 1), (512, 512, 16, 3, 1), (512, 512, 32, 3, 1), (256, 256, 64, 3, 1), (128, 128, 128, 3, 1),
+        (256, 128, 128, 3, 1), (64, 64, 256, 3, 1), (128, 64, 256, 3, 1), (192, 128, 128, 1, 1), (128, 64, 256, 1, 1), (64, 3, 256, 1, 1),
+        (512, 512, 16, 3, 2), (512, 256, 32, 3, 2), (256, 128, 64, 3, 2), (128, 64, 128, 3, 2),
+    ]
+    lines = []
+    with torch.no_grad():
+        for cin, cout, res, k, up in shapes:
+            x = torch.randn(N, cin, res, res, device=dev)
+            w = torch.randn(cout, cin, k, k, device=dev) / (cin * k * k) ** 0.5
+            flops = 2 * N * cout * cin * k * k * res * res
+            ours = lambda: conv_igemm.conv2d_igemm(x, w, f=f if up == 2 else None, up=up, flip_weight=(up == 1))
+            conv_igemm.enabled = False
+            lib = lambda: conv2d_resample.conv2d_resample(x, w, f=f, up=up, padding=k // 2, flip_weight=(up == 1))
+            t_ours = timeit(ours)
+            torch.backends.cudnn.allow_tf32 = True
+            t_tf32 = timeit(lib)
+            torch.backends.cudnn.allow_tf32 = False
+            t_fp32 = timeit(lib)
+            torch.backends.cudnn.allow_tf32 = True
+            conv_igemm.enabled = True
+            exec_flops = flops * (4 if up == 2 else 1)
+            line = dict(cin=cin, cout=cout, res=res, k=k, up=up, N=N, gflop=round(flops / 1e9, 2),
+                        ours_us=round(t_ours * 1e6, 1), cudnn_tf32_us=round(t_tf32 * 1e6, 1), cudnn_fp32_us=round(t_fp32 * 1e6, 1),
+                        ours_tflops=round(flops / t_ours / 1e12, 1), ours_executed_tflops=round(exec_flops / t_ours / 1e12, 1),
+                        frac_of_bf16_peak=round(exec_flops / t_ours / 1e12 / peak, 3), speedup_vs_tf32=round(t_tf32 / t_ours, 2))
+            lines.append(line)
+            print(json.dumps(line), flush=True)
+    if a.out:
+        with open(a.out, 'w') as fh:
+            for ln in lines:
+                fh.write(json.dumps(ln) + '\n')
+
+
+if __name__ == '__main__':
+    main()
