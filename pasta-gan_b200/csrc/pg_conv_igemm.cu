@@ -41,11 +41,12 @@ struct ConvParams {
     long long noise_bstride;
     int N, Cin, Cout, H, W, ks;
     int PW, Lp, tiles_per_img, NACC, BN, nchunks, ntaps, PA;      // PA: staged strip positions (multiple of 32)
-    int SA, SB; uint32_t a_stage_bytes, b_stage_bytes, b_tile_bytes;
+    int SA, SB, tps; uint32_t a_stage_bytes, b_slot_bytes, b_tile_bytes;   // B ring: SB slots of `tps` taps each
     int in_act; float in_alpha, in_gain; int act; float alpha, gain, clamp; int fmt;
     uint32_t idesc; uint32_t tmem_cols;
     // up-2 polyphase mode: BN virtual channels = phases x couts (see launch code); 0 = plain
     int up2; int cout_real;
+    uint32_t pw_magic;         // ceil(2^32 / PW): q / PW == umulhi(q, pw_magic) for the strip positions that occur
 };
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
@@ -106,15 +107,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// two fp32 -> packed fp16x2 / bf16x2 (a in the low half), round-to-nearest, saturating to the largest finite value
 __device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
-    if (fmt == 0) {
-        a = fminf(fmaxf(a, -65504.f), 65504.f);      // fp16 operands saturate instead of overflowing to inf
-        b = fminf(fmaxf(b, -65504.f), 65504.f);
-        __half2 h = __floats2half2_rn(a, b);
-        return *reinterpret_cast<uint32_t*>(&h);
-    }
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
+    uint32_t r;
+    if (fmt == 0) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    else          asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
 }
 
 // ---------------------------------------------------------------------------------------------- weight prepack
@@ -170,6 +168,45 @@ __global__ void conv_prepack_kernel(PackParams p) {
     }
 }
 
+// MMA issue loop of one CTA (executed by a single thread).  KS = kernel size (1 or 3); B ring slots hold KS taps each.
+template <int KS>
+__device__ __forceinline__ void mma_issue_loop(const ConvParams& p, uint8_t* a_base, uint8_t* b_base, uint64_t* a_full, uint64_t* a_empty,
+                                               uint64_t* b_full, uint64_t* b_empty, uint64_t* acc_full, uint32_t tmem_base) {
+    const uint32_t hi = (128u >> 4) | (1u << 14);                         // SBO = 128 B, descriptor version 1 (bits 32..47)
+    const uint32_t a_lo_const = ((uint32_t)p.PA & 0x3FFF) << 16;          // LBO = PA * 16 B  (>> 4)
+    const uint32_t b_lo_const = ((uint32_t)p.BN & 0x3FFF) << 16;          // LBO = BN * 16 B  (>> 4)
+    const uint32_t b_tile16 = p.b_tile_bytes >> 4;
+    const uint32_t bn = (uint32_t)p.BN;
+    const int nacc = p.NACC;
+    int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+    for (int ci = 0; ci < p.nchunks; ci++) {
+        mbar_wait(smem_u32(&a_full[sa]), pa);
+        tc_fence_after();
+        const uint32_t a_lo = a_lo_const | (smem_u32(a_base + (size_t)sa * p.a_stage_bytes) >> 4);
+#pragma unroll
+        for (int kh = 0; kh < KS; kh++) {
+            mbar_wait(smem_u32(&b_full[sb]), pb);
+            tc_fence_after();
+            const uint32_t b_lo = b_lo_const | (smem_u32(b_base + (size_t)sb * p.b_slot_bytes) >> 4);
+#pragma unroll
+            for (int kw = 0; kw < KS; kw++) {
+                const uint32_t s0 = (KS == 3) ? (uint32_t)(kh * p.PW + kw) : 0u;     // tap shift in strip positions == 16-byte rows
+                const uint64_t bdesc = ((uint64_t)hi << 32) | (uint64_t)(b_lo + (uint32_t)kw * b_tile16);
+                const uint32_t acc_flag = (ci | kh | kw) ? 1u : 0u;
+                for (int a = 0; a < nacc; a++) {
+                    const uint64_t adesc = ((uint64_t)hi << 32) | (uint64_t)(a_lo + s0 + (uint32_t)a * 128u);
+                    umma_f16(tmem_base + (uint32_t)a * bn, adesc, bdesc, p.idesc, acc_flag);
+                }
+            }
+            umma_commit(smem_u32(&b_empty[sb]));
+            if (++sb == p.SB) { sb = 0; pb ^= 1; }
+        }
+        umma_commit(smem_u32(&a_empty[sa]));
+        if (++sa == p.SA) { sa = 0; pa ^= 1; }
+    }
+    umma_commit(smem_u32(acc_full));
+}
+
 // ---------------------------------------------------------------------------------------------- main kernel
 __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -183,9 +220,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
 
     uint8_t* a_base = smem;
     uint8_t* b_base = a_base + (size_t)p.SA * p.a_stage_bytes;
-    float*   s_style = reinterpret_cast<float*>(b_base + (size_t)p.SB * p.b_stage_bytes);
+    float*   s_style = reinterpret_cast<float*>(b_base + (size_t)p.SB * p.b_slot_bytes);
     const int cin_pad = p.nchunks * kKC;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_style + cin_pad);
+    float* s_scale = s_style + cin_pad;                     // per output column: dcoef * gain
+    float* s_shift = s_scale + p.BN;                        //                    bias * gain
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + p.BN);
     uint64_t* a_full = bars, *a_empty = bars + p.SA, *b_full = bars + 2 * p.SA, *b_empty = bars + 2 * p.SA + p.SB;
     uint64_t* acc_full = bars + 2 * p.SA + 2 * p.SB;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
@@ -203,49 +242,39 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     // per-sample input scale: style * in_gain (1 * in_gain for plain convs); zero for padded channels
     for (int c = threadIdx.x; c < cin_pad; c += kConvThreads)
         s_style[c] = (c < p.Cin) ? (p.styles ? p.styles[(size_t)n * p.Cin + c] : 1.f) * p.in_gain : 0.f;
+    // epilogue constants with the output gain folded in (relu / lrelu / linear are positively homogeneous, gain > 0)
+    for (int j = threadIdx.x; j < p.BN; j += kConvThreads) {
+        const int v = jn * p.BN + j;
+        const int o = p.up2 ? v % p.cout_real : v;
+        const bool live = v < p.Cout;
+        s_scale[j] = live ? (p.dcoefs ? p.dcoefs[(size_t)n * p.cout_real + o] : 1.f) * p.gain : 0.f;
+        s_shift[j] = live && p.bias ? p.bias[o] * p.gain : 0.f;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== B producer: one bulk copy (all taps of a 16-channel chunk) per stage =====================
+        // ===================== B producer: a ring of small bulk copies (`tps` taps each) keeps many copies in flight =====================
         if (lane == 0) {
-            const uint8_t* src = (const uint8_t*)p.wpack + (size_t)jn * p.nchunks * p.b_stage_bytes;
+            const uint8_t* src = (const uint8_t*)p.wpack + (size_t)jn * p.nchunks * p.ntaps * p.b_tile_bytes;
+            const int nslots = p.nchunks * (p.ntaps / p.tps);
             int st = 0; uint32_t ph = 0;
-            for (int ci = 0; ci < p.nchunks; ci++) {
+            for (int g = 0; g < nslots; g++) {
                 mbar_wait(smem_u32(&b_empty[st]), ph ^ 1);
-                mbar_expect_tx(smem_u32(&b_full[st]), p.b_stage_bytes);
-                bulk_g2s(smem_u32(b_base + (size_t)st * p.b_stage_bytes), src + (size_t)ci * p.b_stage_bytes, p.b_stage_bytes, smem_u32(&b_full[st]));
+                mbar_expect_tx(smem_u32(&b_full[st]), p.b_slot_bytes);
+                bulk_g2s(smem_u32(b_base + (size_t)st * p.b_slot_bytes), src + (size_t)g * p.b_slot_bytes, p.b_slot_bytes, smem_u32(&b_full[st]));
                 if (++st == p.SB) { st = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
+        // The issue loop must cost less than one MMA (64 cycles at N = 128): descriptors are a constant high word plus a
+        // 14-bit start-address field, so each MMA is two integer adds and the tcgen05.mma itself; taps are fully unrolled.
         if (lane == 0) {
-            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-            const uint32_t a_lbo = (uint32_t)p.PA * 16u, b_lbo = (uint32_t)p.BN * 16u;
-            for (int ci = 0; ci < p.nchunks; ci++) {
-                mbar_wait(smem_u32(&a_full[sa]), pa);
-                mbar_wait(smem_u32(&b_full[sb]), pb);
-                tc_fence_after();
-                const uint32_t a_addr = smem_u32(a_base + (size_t)sa * p.a_stage_bytes);
-                const uint32_t b_addr = smem_u32(b_base + (size_t)sb * p.b_stage_bytes);
-                for (int tap = 0; tap < p.ntaps; tap++) {
-                    const int kh = tap / p.ks, kw = tap - kh * p.ks;
-                    const uint32_t s0 = (p.ks == 3) ? (uint32_t)(kh * p.PW + kw) : 0u;
-                    const uint64_t bdesc = umma_desc(b_addr + (uint32_t)tap * p.b_tile_bytes, b_lbo);
-                    for (int a = 0; a < p.NACC; a++) {
-                        const uint64_t adesc = umma_desc(a_addr + (s0 + (uint32_t)a * 128u) * 16u, a_lbo);
-                        umma_f16(tmem_base + (uint32_t)(a * p.BN), adesc, bdesc, p.idesc, (ci | tap) ? 1u : 0u);
-                    }
-                }
-                umma_commit(smem_u32(&a_empty[sa]));
-                umma_commit(smem_u32(&b_empty[sb]));
-                if (++sa == p.SA) { sa = 0; pa ^= 1; }
-                if (++sb == p.SB) { sb = 0; pb ^= 1; }
-            }
-            umma_commit(smem_u32(acc_full));
+            if (p.ks == 3) mma_issue_loop<3>(p, a_base, b_base, a_full, a_empty, b_full, b_empty, acc_full, tmem_base);
+            else           mma_issue_loop<1>(p, a_base, b_base, a_full, a_empty, b_full, b_empty, acc_full, tmem_base);
         }
     } else {
         // ===================== A converters =====================
@@ -254,6 +283,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         const int ntasks = ngroups * 2;                       // (position group, plane)
         const int halo = (p.ks == 3) ? p.PW + 1 : 0;
         const float* xn = p.x + (size_t)n * p.Cin * HW;
+        const bool has_in_act = p.in_act != PG_ACT_LINEAR;
+        const float in_slope = (p.in_act == PG_ACT_RELU) ? 0.f : p.in_alpha;
         int st = 0; uint32_t ph = 0;
         for (int ci = 0; ci < p.nchunks; ci++) {
             mbar_wait(smem_u32(&a_empty[st]), ph ^ 1);
@@ -268,7 +299,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                     const int q = m0 - halo + (tt >> 1) * 32 + lane;          // strip position of this staged row
                     int h = 0, w = 0;
                     bool ok = tt < ntasks && q >= 0 && q < p.Lp;
-                    if (ok) { h = q / p.PW; w = q - h * p.PW; ok = w < p.W; }
+                    if (ok) { h = (int)__umulhi((uint32_t)q, p.pw_magic); w = q - h * p.PW; ok = w < p.W; }
                     const int c0 = ci * kKC + (tt & 1) * 8;
                     const float* src = xn + (size_t)c0 * HW + h * p.W + w;
 #pragma unroll
@@ -285,8 +316,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         float a = v[u][i];
-                        if (p.in_act == PG_ACT_RELU)  a = fmaxf(a, 0.f);
-                        if (p.in_act == PG_ACT_LRELU) a = a > 0.f ? a : a * p.in_alpha;
+                        if (has_in_act) a = fmaxf(a, 0.f) + in_slope * fminf(a, 0.f);
                         t8[i] = a * sc[i];
                     }
                     uint4 pk;
@@ -307,51 +337,48 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         const int quarter = warp & 3;                          // TMEM lane quarter this warp may read
         const int half = cw >> 2;                              // the two warps of a quarter alternate 16-column chunks
         const int ncol_chunks = p.BN / 16;
-        const float* dco = p.dcoefs ? p.dcoefs + (size_t)n * p.cout_real : nullptr;
+        const float slope = (p.act == PG_ACT_LINEAR) ? 1.f : (p.act == PG_ACT_RELU ? 0.f : p.alpha);   // act(v) = max(v,0) + slope*min(v,0)
+        const float cl = p.clamp >= 0.f ? p.clamp : __int_as_float(0x7f800000);
+        const int W2 = 2 * p.W;
         for (int a = 0; a < p.NACC; a++) {
             const int q = m0 + a * 128 + quarter * 32 + lane;
-            const int h = q / p.PW, w = q - h * p.PW;
+            const int h = (int)__umulhi((uint32_t)q, p.pw_magic), w = q - h * p.PW;
             const bool ok = q < p.Lp && w < p.W;
+            float nz0 = 0.f;
+            if (ok && p.noise && !p.up2) nz0 = __ldg(p.noise + (size_t)n * p.noise_bstride + (size_t)h * p.W + w) * p.gain;
             for (int cc = half; cc < ncol_chunks; cc += 2) {
                 uint32_t r[16];
                 tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.BN + cc * 16), r);
                 if (!ok) continue;
+                const int v0 = jn * p.BN + cc * 16;                  // first (virtual) output channel of this chunk
+                int nvalid = p.Cout - v0; nvalid = nvalid > 16 ? 16 : nvalid;
+                if (nvalid <= 0) continue;
+                float sc[16], sh[16];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float4 a4 = reinterpret_cast<const float4*>(s_scale + cc * 16)[i];
+                    const float4 b4 = reinterpret_cast<const float4*>(s_shift + cc * 16)[i];
+                    sc[4 * i] = a4.x; sc[4 * i + 1] = a4.y; sc[4 * i + 2] = a4.z; sc[4 * i + 3] = a4.w;
+                    sh[4 * i] = b4.x; sh[4 * i + 1] = b4.y; sh[4 * i + 2] = b4.z; sh[4 * i + 3] = b4.w;
+                }
+                float nz = nz0; float* yp; size_t ystride;
                 if (!p.up2) {
-                    const float nz = p.noise ? __ldg(p.noise + (size_t)n * p.noise_bstride + (size_t)h * p.W + w) : 0.f;
-                    float* yp = p.y + ((size_t)n * p.Cout) * HW + (size_t)h * p.W + w;
-#pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        const int o = jn * p.BN + cc * 16 + i;
-                        if (o >= p.Cout) break;
-                        float v = __uint_as_float(r[i]);
-                        if (dco) v *= __ldg(dco + o);
-                        v += nz;
-                        if (p.bias) v += __ldg(p.bias + o);
-                        if (p.act == PG_ACT_RELU)  v = fmaxf(v, 0.f);
-                        if (p.act == PG_ACT_LRELU) v = v > 0.f ? v : v * p.alpha;
-                        v *= p.gain;
-                        if (p.clamp >= 0.f) v = fminf(fmaxf(v, -p.clamp), p.clamp);
-                        yp[(size_t)o * HW] = v;
-                    }
+                    yp = p.y + ((size_t)n * p.Cout + v0) * HW + (size_t)h * p.W + w;
+                    ystride = (size_t)HW;
                 } else {
-                    // polyphase up-2: virtual channel = phase * Cout + o, phase = 2*a_y + b_x; output is 2H x 2W
-                    const int W2 = 2 * p.W; const size_t HW4 = (size_t)4 * HW;
+                    // polyphase up-2: virtual channel = phase * Cout + o (Cout % 16 == 0, so a chunk has one phase); output is 2H x 2W
+                    const int phase = v0 / p.cout_real, o0 = v0 - phase * p.cout_real;
+                    const int oy = 2 * h + (phase >> 1), ox = 2 * w + (phase & 1);
+                    if (p.noise) nz = __ldg(p.noise + (size_t)n * p.noise_bstride + (size_t)oy * W2 + ox) * p.gain;
+                    ystride = (size_t)4 * HW;
+                    yp = p.y + ((size_t)n * p.cout_real + o0) * ystride + (size_t)oy * W2 + ox;
+                }
 #pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        const int vch = jn * p.BN + cc * 16 + i;
-                        if (vch >= 4 * p.cout_real) break;
-                        const int phase = vch / p.cout_real, o = vch - phase * p.cout_real;
-                        const int oy = 2 * h + (phase >> 1), ox = 2 * w + (phase & 1);
-                        float v = __uint_as_float(r[i]);
-                        if (dco) v *= __ldg(dco + o);
-                        if (p.noise) v += __ldg(p.noise + (size_t)n * p.noise_bstride + (size_t)oy * W2 + ox);
-                        if (p.bias) v += __ldg(p.bias + o);
-                        if (p.act == PG_ACT_RELU)  v = fmaxf(v, 0.f);
-                        if (p.act == PG_ACT_LRELU) v = v > 0.f ? v : v * p.alpha;
-                        v *= p.gain;
-                        if (p.clamp >= 0.f) v = fminf(fmaxf(v, -p.clamp), p.clamp);
-                        p.y[((size_t)n * p.cout_real + o) * HW4 + (size_t)oy * W2 + ox] = v;
-                    }
+                for (int i = 0; i < 16; i++) {
+                    float v = fmaf(__uint_as_float(r[i]), sc[i], sh[i] + nz);
+                    v = fmaxf(v, 0.f) + slope * fminf(v, 0.f);
+                    v = fminf(fmaxf(v, -cl), cl);
+                    if (i < nvalid) yp[(size_t)i * ystride] = v;
                 }
             }
         }
@@ -365,8 +392,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
 
 // ---------------------------------------------------------------------------------------------- host side
 struct ConvPlan {
-    int BN, ntiles_n, nchunks, ntaps, NACC, PW, Lp, tiles_per_img, PA, SA, SB;
-    uint32_t a_stage, b_stage, b_tile; size_t smem; uint32_t tmem_cols; int nvirt;
+    int BN, ntiles_n, nchunks, ntaps, NACC, PW, Lp, tiles_per_img, PA, SA, SB, tps;
+    uint32_t a_stage, b_stage, b_slot, b_tile; size_t smem; uint32_t tmem_cols; int nvirt;
 };
 
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -398,16 +425,21 @@ static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int k
     pl.a_stage = (uint32_t)pl.PA * 32u;                        // 2 planes x 16 B per position
     pl.b_tile = (uint32_t)bn * 32u;
     pl.b_stage = pl.b_tile * pl.ntaps;
-    const size_t fixed = (size_t)pl.nchunks * kKC * 4 + 64 * 8;
-    pl.SA = 4; pl.SB = 4;
-    auto total = [&]() { return (size_t)pl.SA * pl.a_stage + (size_t)pl.SB * pl.b_stage + fixed + 128; };
+    const size_t fixed = (size_t)pl.nchunks * kKC * 4 + (size_t)bn * 8 + 96 * 8;
+    pl.tps = (ks == 3) ? 3 : 1;
+    pl.b_slot = pl.b_tile * pl.tps;
+    // shared-memory budget: 3 activation stages (2 if they are huge), the rest goes to the weight ring
     const size_t budget = 200 * 1024;
-    while (total() > budget && (pl.SA > 2 || pl.SB > 2)) {
-        if (pl.SB > 2 && (size_t)pl.SB * pl.b_stage >= (size_t)pl.SA * pl.a_stage) pl.SB--; else if (pl.SA > 2) pl.SA--; else pl.SB--;
-    }
-    if (total() > 225 * 1024) return fail(PG_ERR_UNSUPPORTED, "conv2d_igemm: tile does not fit shared memory (W=%d, BN=%d)", W, bn);
+    pl.SA = 3;
+    if ((size_t)pl.SA * pl.a_stage > budget / 2) pl.SA = 2;
     if (pl.nchunks < pl.SA) pl.SA = pl.nchunks < 2 ? 2 : pl.nchunks;
-    if (pl.nchunks < pl.SB) pl.SB = pl.nchunks < 2 ? 2 : pl.nchunks;
+    const size_t left = budget > (size_t)pl.SA * pl.a_stage + fixed + 128 ? budget - (size_t)pl.SA * pl.a_stage - fixed - 128 : 0;
+    pl.SB = (int)(left / pl.b_slot);
+    const int nslots = pl.nchunks * (pl.ntaps / pl.tps);
+    if (pl.SB > 24) pl.SB = 24;
+    if (pl.SB > nslots) pl.SB = nslots < 2 ? 2 : nslots;
+    if (pl.SB < 2) return fail(PG_ERR_UNSUPPORTED, "conv2d_igemm: tile does not fit shared memory (W=%d, BN=%d)", W, bn);
+    auto total = [&]() { return (size_t)pl.SA * pl.a_stage + (size_t)pl.SB * pl.b_slot + fixed + 128; };
     pl.smem = total();
     uint32_t cols = 32;
     while (cols < (uint32_t)(nacc * bn)) cols <<= 1;
@@ -438,6 +470,8 @@ extern "C" int pg_conv2d_igemm_fwd(const float* x, const float* w, const float* 
     PG_REQUIRE(in_act == PG_ACT_LINEAR || in_act == PG_ACT_RELU || in_act == PG_ACT_LRELU, "conv2d_igemm: input act must be linear/relu/lrelu");
     PG_REQUIRE((int64_t)N * Cin * H * W <= INT32_MAX && (int64_t)N * Cout * H * W * (up == 2 ? 4 : 1) <= INT32_MAX, "conv2d_igemm: tensor too large");
     PG_REQUIRE(up == 1 || fir != nullptr, "conv2d_igemm: up=2 needs the 4x4 FIR");
+    PG_REQUIRE(up == 1 || Cout % 16 == 0, "conv2d_igemm: up=2 needs Cout to be a multiple of 16");
+    PG_REQUIRE(gain > 0.f && in_gain > 0.f, "conv2d_igemm: gains must be positive (they are folded through the activation)");
     if (N == 0) return PG_OK;
     PG_REQUIRE(x && w && y && workspace, "conv2d_igemm: x, w, y and workspace must be device pointers");
     ConvPlan pl;
@@ -460,11 +494,12 @@ extern "C" int pg_conv2d_igemm_fwd(const float* x, const float* w, const float* 
     p.noise_bstride = noise_batch_stride;
     p.N = N; p.Cin = Cin; p.Cout = pl.nvirt; p.H = H; p.W = W; p.ks = ksize;
     p.PW = pl.PW; p.Lp = pl.Lp; p.tiles_per_img = pl.tiles_per_img; p.NACC = pl.NACC; p.BN = pl.BN; p.nchunks = pl.nchunks; p.ntaps = pl.ntaps;
-    p.PA = pl.PA; p.SA = pl.SA; p.SB = pl.SB; p.a_stage_bytes = pl.a_stage; p.b_stage_bytes = pl.b_stage; p.b_tile_bytes = pl.b_tile;
+    p.PA = pl.PA; p.SA = pl.SA; p.SB = pl.SB; p.tps = pl.tps; p.a_stage_bytes = pl.a_stage; p.b_slot_bytes = pl.b_slot; p.b_tile_bytes = pl.b_tile;
     p.in_act = in_act; p.in_alpha = in_alpha; p.in_gain = in_gain; p.act = act; p.alpha = alpha; p.gain = gain; p.clamp = clamp; p.fmt = operand_format;
     p.idesc = (1u << 4) | ((uint32_t)operand_format << 7) | ((uint32_t)operand_format << 10) | ((uint32_t)(pl.BN >> 3) << 17) | (8u << 24);
     p.tmem_cols = pl.tmem_cols;
     p.up2 = up == 2; p.cout_real = Cout;
+    p.pw_magic = (uint32_t)((0x100000000ull + (uint64_t)pl.PW - 1) / (uint64_t)pl.PW);
     PG_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     dim3 grid((unsigned)(N * pl.tiles_per_img), (unsigned)pl.ntiles_n);
     conv_igemm_kernel<<<grid, kConvThreads, pl.smem, s>>>(p);

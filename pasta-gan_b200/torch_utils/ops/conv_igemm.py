@@ -29,7 +29,7 @@ def supported(x, w, up=1, down=1, groups=1, f=None, padding=None, flip_filter=Fa
     k = int(w.shape[2])
     if padding is not None and tuple(padding) != (k // 2,) * 4:
         return False
-    if up == 2 and (k != 3 or f is None or f.ndim != 2 or tuple(f.shape) != (4, 4) or flip_filter):
+    if up == 2 and (k != 3 or f is None or f.ndim != 2 or tuple(f.shape) != (4, 4) or flip_filter or w.shape[0] % 16 != 0):
         return False
     if x.numel() == 0 or x.numel() > 2 ** 31 - 1:
         return False

@@ -187,6 +187,11 @@ def test_bias_act_vs_oracle(ops, cfg, shape, dtype):
     dy = torch.randn_like(y_ref)
     gr, = torch.autograd.grad(y_ref, xr, dy)
     gg, = torch.autograd.grad(y, xg, dy.to(DEV, dtype))
+    if dtype == torch.float16 and cfg['clamp']:
+        # the clamp mask is evaluated on the STORED y (fp16, as in the reference plugin, bias_act.cu:136-142): outputs that round onto
+        # the clamp value get a zero gradient, so elements within fp16 rounding distance of the clamp are excluded from the comparison
+        keep = ((y_ref.detach().abs() - cfg['clamp']).abs() > 0.01 * cfg['clamp']).to(gr.dtype)
+        gr, gg = gr * keep, gg.cpu().double() * keep
     assert rel_err(gg, gr) < (TOL if dtype == torch.float32 else 5e-3)
 
 
