@@ -138,6 +138,16 @@ int pg_upfirdn2d_bias_act(const void* x, const float* f, const void* b, void* y,
  * Forward only: gradients of convolutions stay on conv2d_gradfix in this release.
  */
 int64_t pg_conv2d_igemm_workspace_bytes(int32_t Cin, int32_t Cout, int32_t ksize, int32_t up);
+/* The same operation in two steps, so that inference can pack the weights once per parameter version:
+ *   prepack: w * w_scale (the layer's weight_gain, training/networks.py:171) -> fp16/bf16 GEMM tiles in `workspace`
+ *   run:     the convolution proper on packed weights.  pg_conv2d_igemm_fwd == prepack(w_scale = 1) + run. */
+int pg_conv2d_igemm_prepack(const float* w, const float* fir, float w_scale, int32_t Cin, int32_t Cout, int32_t ksize, int32_t up,
+                            int32_t flip_weight, int32_t operand_format, void* workspace, int64_t workspace_bytes, void* stream);
+int pg_conv2d_igemm_run(const float* x, const void* wpack, const float* styles, const float* dcoefs,
+                        const float* noise, int64_t noise_batch_stride, const float* bias, float* y,
+                        int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t ksize, int32_t up,
+                        int32_t in_act, float in_alpha, float in_gain,
+                        int32_t act, float alpha, float gain, float clamp, int32_t operand_format, void* stream);
 int pg_conv2d_igemm_fwd(const float* x, const float* w, const float* fir, const float* styles, const float* dcoefs,
                         const float* noise, int64_t noise_batch_stride, const float* bias, float* y,
                         int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t ksize, int32_t up,

@@ -31,6 +31,8 @@ SIGNATURES = {
     'pg_upfirdn2d': [c_ptr, c_ptr, c_ptr, I32x4, I64x4, I32x4, I64x4, c_i32, c_i32, c_i64, c_i64] + [c_i32] * 8 +
                     [c_i32, c_f32, c_i32, c_ptr],
     'pg_conv2d_igemm_workspace_bytes': [c_i32, c_i32, c_i32, c_i32],
+    'pg_conv2d_igemm_prepack': [c_ptr, c_ptr, c_f32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr, c_i64, c_ptr],
+    'pg_conv2d_igemm_run': [c_ptr] * 5 + [c_i64, c_ptr, c_ptr] + [c_i32] * 7 + [c_i32, c_f32, c_f32, c_i32, c_f32, c_f32, c_f32, c_i32, c_ptr],
     'pg_conv2d_igemm_fwd': [c_ptr] * 6 + [c_i64, c_ptr, c_ptr] + [c_i32] * 7 + [c_i32, c_i32, c_f32, c_f32, c_i32, c_f32, c_f32, c_f32, c_i32,
                             c_ptr, c_i64, c_ptr],
     'pg_upfirdn2d_bias_act': [c_ptr, c_ptr, c_ptr, c_ptr, I32x4, I64x4, I32x4, I64x4, c_i32, c_i32, c_i64, c_i64] + [c_i32] * 8 +

@@ -34,7 +34,7 @@ namespace pg {
 constexpr int kConvWarps   = 8;                 // A converters, later the epilogue
 constexpr int kConvThreads = 64 + 32 * kConvWarps;
 constexpr int kKC          = 16;                // channels per pipeline chunk == one UMMA K step
-constexpr int kTaskBatch   = 7;                 // converter tasks (8 channels x 32 positions) loaded back to back per warp
+constexpr int kTaskBatch   = 4;                 // converter tasks (8 channels x 32 positions) loaded back to back per warp
 
 struct ConvParams {
     const float* x; const void* wpack; const float* styles; const float* dcoefs; const float* noise; const float* bias; float* y;
@@ -121,7 +121,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
 // up2 != 0: the 3x3 weights are first convolved with the 4x4 FIR (gain 4) into a 6x6 composite and split into the four
 // output-parity 3x3 kernels of the polyphase form; virtual channel v = phase * Cout + o.
 struct PackParams {
-    const float* w; const float* fir; void* out; int Cout, Cin, ks, BN, nchunks, ntaps, ntiles, flip_weight, fmt, up2;
+    const float* w; const float* fir; void* out; int Cout, Cin, ks, BN, nchunks, ntaps, ntiles, flip_weight, fmt, up2; float w_scale;
 };
 
 __device__ float composite_tap(const PackParams& p, int o, int c, int a, int b, int th, int tw) {
@@ -163,6 +163,7 @@ __global__ void conv_prepack_kernel(PackParams p) {
                 val = p.w[((size_t)(v * p.Cin + c) * p.ks + wh) * p.ks + ww];
             }
         }
+        val *= p.w_scale;
         if (p.fmt == 0) ((__half*)p.out)[idx] = __float2half_rn(fminf(fmaxf(val, -65504.f), 65504.f));
         else            ((__nv_bfloat16*)p.out)[idx] = __float2bfloat16_rn(val);
     }
@@ -208,6 +209,8 @@ __device__ __forceinline__ void mma_issue_loop(const ConvParams& p, uint8_t* a_b
 }
 
 // ---------------------------------------------------------------------------------------------- main kernel
+// SCALE: the A operand needs a per-channel scale and/or an input activation (modulated / SPADE layers); plain layers skip both.
+template <bool SCALE>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -303,25 +306,34 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                     const int c0 = ci * kKC + (tt & 1) * 8;
                     const float* src = xn + (size_t)c0 * HW + h * p.W + w;
 #pragma unroll
-                    for (int i = 0; i < 8; i++)
-                        v[u][i] = (ok && c0 + i < p.Cin) ? __ldg(src + (size_t)i * HW) : 0.f;
+                    for (int i = 0; i < 8; i++) v[u][i] = 0.f;
+                    if (ok) {
+                        if (c0 + 8 <= p.Cin) {
+#pragma unroll
+                            for (int i = 0; i < 8; i++) v[u][i] = __ldg(src + i * HW);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; i++) if (c0 + i < p.Cin) v[u][i] = __ldg(src + i * HW);
+                        }
+                    }
                 }
 #pragma unroll
                 for (int u = 0; u < kTaskBatch; u++) {
                     const int tt = t + u * kConvWarps;
                     if (tt >= ntasks) break;
                     const int plane = tt & 1, spos = (tt >> 1) * 32 + lane;
-                    const float* sc = s_style + ci * kKC + plane * 8;
-                    float t8[8];
+                    if (SCALE) {
+                        const float* sc = s_style + ci * kKC + plane * 8;
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        float a = v[u][i];
-                        if (has_in_act) a = fmaxf(a, 0.f) + in_slope * fminf(a, 0.f);
-                        t8[i] = a * sc[i];
+                        for (int i = 0; i < 8; i++) {
+                            float a = v[u][i];
+                            if (has_in_act) a = fmaxf(a, 0.f) + in_slope * fminf(a, 0.f);
+                            v[u][i] = a * sc[i];
+                        }
                     }
                     uint4 pk;
-                    pk.x = pack2(t8[0], t8[1], p.fmt); pk.y = pack2(t8[2], t8[3], p.fmt);
-                    pk.z = pack2(t8[4], t8[5], p.fmt); pk.w = pack2(t8[6], t8[7], p.fmt);
+                    pk.x = pack2(v[u][0], v[u][1], p.fmt); pk.y = pack2(v[u][2], v[u][3], p.fmt);
+                    pk.z = pack2(v[u][4], v[u][5], p.fmt); pk.w = pack2(v[u][6], v[u][7], p.fmt);
                     *reinterpret_cast<uint4*>(stage + (size_t)plane * p.PA * 16 + (size_t)spos * 16) = pk;
                 }
             }
@@ -455,42 +467,58 @@ extern "C" int64_t pg_conv2d_igemm_workspace_bytes(int32_t Cin, int32_t Cout, in
     return (int64_t)pl.ntiles_n * pl.nchunks * pl.b_stage;
 }
 
-extern "C" int pg_conv2d_igemm_fwd(const float* x, const float* w, const float* fir, const float* styles, const float* dcoefs,
-                                   const float* noise, int64_t noise_batch_stride, const float* bias, float* y,
-                                   int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t ksize, int32_t up,
-                                   int32_t flip_weight, int32_t in_act, float in_alpha, float in_gain,
-                                   int32_t act, float alpha, float gain, float clamp, int32_t operand_format,
-                                   void* workspace, int64_t workspace_bytes, void* stream) {
+static int conv_validate(int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t ksize, int32_t up, int32_t operand_format) {
     using namespace pg;
     PG_REQUIRE(ksize == 1 || ksize == 3, "conv2d_igemm: kernel size must be 1 or 3 (got %d)", ksize);
     PG_REQUIRE(up == 1 || (up == 2 && ksize == 3), "conv2d_igemm: up must be 1, or 2 with a 3x3 kernel");
     PG_REQUIRE(N >= 0 && Cin >= 1 && Cout >= 1 && H >= 1 && W >= 1, "conv2d_igemm: bad sizes");
     PG_REQUIRE(operand_format == 0 || operand_format == 1, "conv2d_igemm: operand_format must be 0 (fp16) or 1 (bf16)");
-    PG_REQUIRE(act == PG_ACT_LINEAR || act == PG_ACT_RELU || act == PG_ACT_LRELU, "conv2d_igemm: epilogue act must be linear/relu/lrelu");
-    PG_REQUIRE(in_act == PG_ACT_LINEAR || in_act == PG_ACT_RELU || in_act == PG_ACT_LRELU, "conv2d_igemm: input act must be linear/relu/lrelu");
-    PG_REQUIRE((int64_t)N * Cin * H * W <= INT32_MAX && (int64_t)N * Cout * H * W * (up == 2 ? 4 : 1) <= INT32_MAX, "conv2d_igemm: tensor too large");
-    PG_REQUIRE(up == 1 || fir != nullptr, "conv2d_igemm: up=2 needs the 4x4 FIR");
     PG_REQUIRE(up == 1 || Cout % 16 == 0, "conv2d_igemm: up=2 needs Cout to be a multiple of 16");
-    PG_REQUIRE(gain > 0.f && in_gain > 0.f, "conv2d_igemm: gains must be positive (they are folded through the activation)");
-    if (N == 0) return PG_OK;
-    PG_REQUIRE(x && w && y && workspace, "conv2d_igemm: x, w, y and workspace must be device pointers");
+    return PG_OK;
+}
+
+extern "C" int pg_conv2d_igemm_prepack(const float* w, const float* fir, float w_scale, int32_t Cin, int32_t Cout, int32_t ksize, int32_t up,
+                                       int32_t flip_weight, int32_t operand_format, void* workspace, int64_t workspace_bytes, void* stream) {
+    using namespace pg;
+    int rc = conv_validate(1, Cin, Cout, 8, 8, ksize, up, operand_format);
+    if (rc != PG_OK) return rc;
+    PG_REQUIRE(up == 1 || fir != nullptr, "conv2d_igemm: up=2 needs the 4x4 FIR");
+    PG_REQUIRE(w && workspace, "conv2d_igemm: w and workspace must be device pointers");
     ConvPlan pl;
-    int rc = make_plan(pl, N, Cin, Cout, H, W, ksize, up == 2);
+    rc = make_plan(pl, 1, Cin, Cout, 8, 8, ksize, up == 2);
     if (rc != PG_OK) return rc;
     const int64_t need = (int64_t)pl.ntiles_n * pl.nchunks * pl.b_stage;
     PG_REQUIRE(workspace_bytes >= need, "conv2d_igemm: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
-    cudaStream_t s = (cudaStream_t)stream;
-
     PackParams pp;
     pp.w = w; pp.fir = fir; pp.out = workspace; pp.Cout = Cout; pp.Cin = Cin; pp.ks = ksize; pp.BN = pl.BN; pp.nchunks = pl.nchunks;
-    pp.ntaps = pl.ntaps; pp.ntiles = pl.ntiles_n; pp.flip_weight = flip_weight ? 1 : 0; pp.fmt = operand_format; pp.up2 = up == 2;
+    pp.ntaps = pl.ntaps; pp.ntiles = pl.ntiles_n; pp.flip_weight = flip_weight ? 1 : 0; pp.fmt = operand_format; pp.up2 = up == 2; pp.w_scale = w_scale;
     const size_t pack_total = (size_t)need / 2;
     int pblocks = (int)((pack_total + 255) / 256);
     if (pblocks > kNumSMs * 16) pblocks = kNumSMs * 16;
-    conv_prepack_kernel<<<pblocks, 256, 0, s>>>(pp);
+    conv_prepack_kernel<<<pblocks, 256, 0, (cudaStream_t)stream>>>(pp);
+    return launch_status("conv2d_igemm_prepack", 1);
+}
 
+extern "C" int pg_conv2d_igemm_run(const float* x, const void* wpack, const float* styles, const float* dcoefs,
+                                   const float* noise, int64_t noise_batch_stride, const float* bias, float* y,
+                                   int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t ksize, int32_t up,
+                                   int32_t in_act, float in_alpha, float in_gain,
+                                   int32_t act, float alpha, float gain, float clamp, int32_t operand_format, void* stream) {
+    using namespace pg;
+    int rc = conv_validate(N, Cin, Cout, H, W, ksize, up, operand_format);
+    if (rc != PG_OK) return rc;
+    PG_REQUIRE(act == PG_ACT_LINEAR || act == PG_ACT_RELU || act == PG_ACT_LRELU, "conv2d_igemm: epilogue act must be linear/relu/lrelu");
+    PG_REQUIRE(in_act == PG_ACT_LINEAR || in_act == PG_ACT_RELU || in_act == PG_ACT_LRELU, "conv2d_igemm: input act must be linear/relu/lrelu");
+    PG_REQUIRE((int64_t)N * Cin * H * W <= INT32_MAX && (int64_t)N * Cout * H * W * (up == 2 ? 4 : 1) <= INT32_MAX, "conv2d_igemm: tensor too large");
+    PG_REQUIRE(gain > 0.f && in_gain > 0.f, "conv2d_igemm: gains must be positive (they are folded through the activation)");
+    if (N == 0) return PG_OK;
+    PG_REQUIRE(x && wpack && y, "conv2d_igemm: x, packed weights and y must be device pointers");
+    ConvPlan pl;
+    rc = make_plan(pl, N, Cin, Cout, H, W, ksize, up == 2);
+    if (rc != PG_OK) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
     ConvParams p;
-    p.x = x; p.wpack = workspace; p.styles = styles; p.dcoefs = dcoefs; p.noise = noise; p.bias = bias; p.y = y;
+    p.x = x; p.wpack = wpack; p.styles = styles; p.dcoefs = dcoefs; p.noise = noise; p.bias = bias; p.y = y;
     p.noise_bstride = noise_batch_stride;
     p.N = N; p.Cin = Cin; p.Cout = pl.nvirt; p.H = H; p.W = W; p.ks = ksize;
     p.PW = pl.PW; p.Lp = pl.Lp; p.tiles_per_img = pl.tiles_per_img; p.NACC = pl.NACC; p.BN = pl.BN; p.nchunks = pl.nchunks; p.ntaps = pl.ntaps;
@@ -500,8 +528,22 @@ extern "C" int pg_conv2d_igemm_fwd(const float* x, const float* w, const float* 
     p.tmem_cols = pl.tmem_cols;
     p.up2 = up == 2; p.cout_real = Cout;
     p.pw_magic = (uint32_t)((0x100000000ull + (uint64_t)pl.PW - 1) / (uint64_t)pl.PW);
-    PG_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    const bool scale = styles != nullptr || in_act != PG_ACT_LINEAR || in_gain != 1.f;
+    auto kern = scale ? conv_igemm_kernel<true> : conv_igemm_kernel<false>;
+    PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     dim3 grid((unsigned)(N * pl.tiles_per_img), (unsigned)pl.ntiles_n);
-    conv_igemm_kernel<<<grid, kConvThreads, pl.smem, s>>>(p);
-    return launch_status("conv2d_igemm", 2);
+    kern<<<grid, kConvThreads, pl.smem, s>>>(p);
+    return launch_status("conv2d_igemm", 1);
+}
+
+extern "C" int pg_conv2d_igemm_fwd(const float* x, const float* w, const float* fir, const float* styles, const float* dcoefs,
+                                   const float* noise, int64_t noise_batch_stride, const float* bias, float* y,
+                                   int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t ksize, int32_t up,
+                                   int32_t flip_weight, int32_t in_act, float in_alpha, float in_gain,
+                                   int32_t act, float alpha, float gain, float clamp, int32_t operand_format,
+                                   void* workspace, int64_t workspace_bytes, void* stream) {
+    int rc = pg_conv2d_igemm_prepack(w, fir, 1.f, Cin, Cout, ksize, up, flip_weight, operand_format, workspace, workspace_bytes, stream);
+    if (rc != PG_OK) return rc;
+    return pg_conv2d_igemm_run(x, workspace, styles, dcoefs, noise, noise_batch_stride, bias, y, N, Cin, Cout, H, W, ksize, up,
+                               in_act, in_alpha, in_gain, act, alpha, gain, clamp, operand_format, stream);
 }

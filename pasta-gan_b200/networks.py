@@ -126,8 +126,37 @@ def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, res
     return x
 
 
+class _Eps:
+    """[1,1] tensors holding 1e-8 per device (the addmm bias of the demodulation GEMV), created once."""
+    def __init__(self):
+        self.t = {}
+
+    def get(self, device):
+        if device not in self.t:
+            self.t[device] = torch.full([1, 1], 1e-8, device=device)
+        return self.t[device]
+
+
+_EPS = _Eps()
+_WSQ_CACHE = {}
+
+
+def _weight_sq_sums(weight):
+    """sum_k W[o,i,k]^2  ([O, I]); cached per Parameter version (it only changes when the optimizer steps)."""
+    if not isinstance(weight, nn.Parameter) or torch.is_grad_enabled():
+        return weight.square().sum(dim=[2, 3])
+    key = (id(weight), weight._version, weight.data_ptr())
+    hit = _WSQ_CACHE.get(key)
+    if hit is None or hit[0] is not weight:
+        if len(_WSQ_CACHE) > 256:
+            _WSQ_CACHE.clear()
+        hit = (weight, weight.detach().square().sum(dim=[2, 3]))
+        _WSQ_CACHE[key] = hit
+    return hit[1]
+
+
 def conv_layer(x, w, b=None, f=None, up=1, down=1, padding=0, flip_weight=True, act='linear', act_gain=1.0, clamp=None,
-               in_act=None, in_gain=1.0):
+               in_act=None, in_gain=1.0, w_scale=1.0, cache_weights=False):
     """Product form of one plain conv layer: [in_act(x) * in_gain ->] conv2d_resample -> bias_act.  When the tcgen05 kernel covers
     the shape the whole layer is ONE launch (bias, activation, gain and clamp live in the GEMM epilogue; the SPADE pre-activation
     lives in the operand prologue); otherwise it is composed from the same operators the reference calls."""
@@ -136,10 +165,12 @@ def conv_layer(x, w, b=None, f=None, up=1, down=1, padding=0, flip_weight=True, 
     if act in ('linear', 'relu', 'lrelu') and in_act in (None, 'relu', 'lrelu') and \
             K.supported(x, w, up=up, down=down, f=f, padding=pad4):
         return K.conv2d_igemm(x, w, f=f, up=up, flip_weight=flip_weight, bias=b, in_act=in_act or 'linear', in_gain=in_gain,
-                              act=act, gain=act_gain, clamp=clamp)
+                              act=act, gain=act_gain, clamp=clamp, w_scale=w_scale, cache_weights=cache_weights)
     if in_act is not None:
         x = B.bias_act(x, None, act=in_act, gain=in_gain)
-    x = C.conv2d_resample(x=x, w=w, f=f, up=up, down=down, padding=padding, flip_weight=flip_weight)
+    if w_scale != 1.0:
+        w = w * w_scale
+    x = C.conv2d_resample(x=x, w=w.to(x.dtype), f=f, up=up, down=down, padding=padding, flip_weight=flip_weight)
     if b is None and act == 'linear' and act_gain == 1 and clamp is None:
         return x
     return B.bias_act(x, b, act=act, gain=act_gain, clamp=clamp)
@@ -155,10 +186,9 @@ def modconv_layer(x, weight, styles, noise=None, up=1, padding=0, resample_filte
             K.supported(x, weight, up=up, f=resample_filter, padding=(padding,) * 4) and not styles.requires_grad:
         dcoefs = None
         if demodulate:
-            wsq = weight.square().sum(dim=[2, 3])
-            dcoefs = torch.addmm(torch.full([1, 1], 1e-8, device=x.device), styles.square(), wsq.t()).rsqrt()
+            dcoefs = torch.addmm(_EPS.get(x.device), styles.square(), _weight_sq_sums(weight).t()).rsqrt()
         return K.conv2d_igemm(x, weight, f=resample_filter, up=up, flip_weight=flip_weight, styles=styles, dcoefs=dcoefs, noise=noise,
-                              bias=bias, act=act, gain=act_gain, clamp=clamp)
+                              bias=bias, act=act, gain=act_gain, clamp=clamp, cache_weights=isinstance(weight, nn.Parameter))
     x = modulated_conv2d(x=x, weight=weight, styles=styles, noise=noise, up=up, padding=padding, resample_filter=resample_filter,
                          demodulate=demodulate, flip_weight=flip_weight, fused_modconv=fused_modconv)
     return B.bias_act(x, bias, act=act, gain=act_gain, clamp=clamp)
@@ -227,10 +257,11 @@ class Conv2dLayer(OpsModule):
         layer = getattr(self.ops, 'conv_layer', None)
         if layer is None or self.down != 1:
             return None
-        w = (self.weight * self.weight_gain).to(x.dtype)
+        w = self.weight                                   # raw parameter: weight_gain is applied when the GEMM tiles are packed
         b = self.bias.to(x.dtype) if self.bias is not None else None
         clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
-        kw = dict(f=self.resample_filter, up=self.up, down=self.down, padding=self.padding, flip_weight=(self.up == 1))
+        kw = dict(f=self.resample_filter, up=self.up, down=self.down, padding=self.padding, flip_weight=(self.up == 1),
+                  w_scale=float(self.weight_gain), cache_weights=True)
         if pre_act is None:
             return layer(x, w, b, act=self.activation, act_gain=self.act_gain * gain, clamp=clamp, **kw)
         if not pre_act:                                   # SPADE layer called with no_act=True: bare convolution

@@ -36,22 +36,47 @@ def supported(x, w, up=1, down=1, groups=1, f=None, padding=None, flip_filter=Fa
     return True
 
 
+_pack_cache = {}          # (id(param), version, ...) -> (param, packed weights): inference packs each parameter once
+_PACK_CACHE_MAX = 512
+
+
+def _packed_weights(capi, w, f, w_scale, up, flip_weight, fmt_code, cache):
+    """fp16/bf16 GEMM tiles of ``w * w_scale`` (pg_conv2d_igemm_prepack).  With ``cache=True`` the caller promises that ``w`` is a
+    long-lived tensor (a Parameter / buffer): the packed copy is reused until the tensor's version counter changes."""
+    cout, cin, k, _ = (int(v) for v in w.shape)
+    key = None
+    if cache:
+        key = (id(w), w._version, w.data_ptr(), float(w_scale), up, bool(flip_weight), fmt_code)
+        hit = _pack_cache.get(key)
+        if hit is not None and hit[0] is w:
+            return hit[1]
+    lib = capi.load()
+    ws_bytes = int(lib.pg_conv2d_igemm_workspace_bytes(cin, cout, k, up))
+    if ws_bytes < 0:
+        capi.check(2, 'pg_conv2d_igemm_workspace_bytes')
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=w.device)
+    wc = w.detach().contiguous()
+    rc = lib.pg_conv2d_igemm_prepack(capi.ptr(wc), capi.ptr(f) if up == 2 else None, float(w_scale), cin, cout, k, up,
+                                     int(bool(flip_weight)), fmt_code, capi.ptr(ws), ws_bytes, capi.current_stream(w.device))
+    capi.check(rc, 'pg_conv2d_igemm_prepack')
+    if key is not None:
+        if len(_pack_cache) >= _PACK_CACHE_MAX:
+            _pack_cache.pop(next(iter(_pack_cache)))
+        _pack_cache[key] = (w, ws)
+    return ws
+
+
 def conv2d_igemm(x, w, f=None, up=1, flip_weight=True, styles=None, dcoefs=None, noise=None, bias=None,
-                 in_act='linear', in_alpha=0.2, in_gain=1.0, act='linear', alpha=0.2, gain=1.0, clamp=None, fmt=None):
-    """y = clamp(act(dcoefs * conv(styles * in_gain * in_act(x), w) + noise + bias) * gain); see include/pasta_b200.h."""
+                 in_act='linear', in_alpha=0.2, in_gain=1.0, act='linear', alpha=0.2, gain=1.0, clamp=None, fmt=None,
+                 w_scale=1.0, cache_weights=False):
+    """y = clamp(act(dcoefs * conv(styles * in_gain * in_act(x), w * w_scale) + noise + bias) * gain); see include/pasta_b200.h."""
     capi = _backend.capi()
     _backend.require_cuda(x, 'conv2d_igemm')
     n, cin, h, wd = (int(v) for v in x.shape)
     cout, cin_w, k, _ = (int(v) for v in w.shape)
     assert cin_w == cin, 'weight / input channel mismatch'
     x = x.contiguous()
-    w = w.contiguous()
     y = torch.empty([n, cout, h * up, wd * up], dtype=torch.float32, device=x.device)
-    lib = capi.load()
-    ws_bytes = int(lib.pg_conv2d_igemm_workspace_bytes(cin, cout, k, up))
-    if ws_bytes < 0:
-        capi.check(2, 'pg_conv2d_igemm_workspace_bytes')
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
     nb_stride = 0
     if noise is not None:
         noise = noise.to(torch.float32).contiguous()
@@ -71,17 +96,19 @@ def conv2d_igemm(x, w, f=None, up=1, flip_weight=True, styles=None, dcoefs=None,
         assert tuple(bias.shape) == (cout,)
     if up == 2:
         f = f.to(torch.float32).contiguous()
+    fmt_code = _FMT[fmt or operand_format]
     with torch.cuda.device(x.device):
         capi.require_device()
+        wpack = _packed_weights(capi, w, f, w_scale, up, flip_weight, fmt_code, cache_weights)
         sp = capi.span('conv_igemm', flops=2 * n * cout * cin * k * k * h * wd * (4 if up == 2 else 1),
                        nbytes=4 * (x.numel() + y.numel() + w.numel()))
-        rc = lib.pg_conv2d_igemm_fwd(capi.ptr(x), capi.ptr(w), capi.ptr(f) if up == 2 else None, capi.ptr(styles), capi.ptr(dcoefs),
-                                     capi.ptr(noise), nb_stride, capi.ptr(bias), capi.ptr(y),
-                                     n, cin, cout, h, wd, k, up, int(bool(flip_weight)),
-                                     _ACT[in_act], float(in_alpha), float(in_gain),
-                                     _ACT[act], float(alpha), float(gain), float(-1 if clamp is None else clamp),
-                                     _FMT[fmt or operand_format], capi.ptr(ws), ws_bytes, capi.current_stream(x.device))
-        capi.check(rc, 'pg_conv2d_igemm_fwd')
+        rc = capi.load().pg_conv2d_igemm_run(capi.ptr(x), capi.ptr(wpack), capi.ptr(styles), capi.ptr(dcoefs),
+                                             capi.ptr(noise), nb_stride, capi.ptr(bias), capi.ptr(y),
+                                             n, cin, cout, h, wd, k, up,
+                                             _ACT[in_act], float(in_alpha), float(in_gain),
+                                             _ACT[act], float(alpha), float(gain), float(-1 if clamp is None else clamp),
+                                             fmt_code, capi.current_stream(x.device))
+        capi.check(rc, 'pg_conv2d_igemm_run')
         if sp:
             sp.close()
     return y
