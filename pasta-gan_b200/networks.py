@@ -24,6 +24,10 @@ sm_100a operators.  They are a re-expression, not a copy: every layer is a thin 
     SynthesisBlockFull             :5615-5719        SynthesisBlockFull
     SynthesisNetworkFull           :5723-5840        SynthesisNetworkFull
     GeneratorFull                  :5844-5880        GeneratorFull
+    DiscriminatorBlock             :917-997          DiscriminatorBlock
+    MinibatchStdLayer              :1001-1023        MinibatchStdLayer
+    DiscriminatorEpilogue          :1027-1081        DiscriminatorEpilogue
+    Discriminator                  :1085-1143        Discriminator
 
 The default operator table is the CUDA product (``cuda_ops()``); tests and the CPU baseline inject the oracle's
 table with ``use_ops(module, table)``.  The product never imports the oracle.
@@ -645,6 +649,143 @@ class GeneratorFull(OpsModule):
         cat_feats = {str(f.shape[2]): f for f in feats}
         return self.synthesis(ws, pose_feat, cat_feats, denorm_upper_input, denorm_lower_input, denorm_upper_mask, denorm_lower_mask,
                               **synthesis_kwargs)
+
+
+# ----------------------------------------------------------------------------- discriminator (training path, R1 double backward)
+
+
+class DiscriminatorBlock(OpsModule):
+    """reference :917-997 — fromrgb (first block / skip arch), 3x3 conv, 3x3 down-2 conv, optional 1x1 down-2 residual skip."""
+
+    def __init__(self, in_channels, tmp_channels, out_channels, resolution, img_channels, first_layer_idx, architecture='resnet',
+                 activation='lrelu', resample_filter=_FIR, conv_clamp=None, use_fp16=False, fp16_channels_last=False, freeze_layers=0):
+        assert in_channels in [0, tmp_channels]
+        assert architecture in ['orig', 'skip', 'resnet']
+        super().__init__()
+        self.in_channels, self.resolution, self.img_channels = in_channels, resolution, img_channels
+        self.first_layer_idx, self.architecture, self.use_fp16 = first_layer_idx, architecture, use_fp16
+        self.channels_last = use_fp16 and fp16_channels_last
+        self.register_buffer('resample_filter', _fir_buffer(resample_filter))
+        self.num_layers = 0
+
+        def trainable():
+            t = (self.first_layer_idx + self.num_layers) >= freeze_layers
+            self.num_layers += 1
+            return t
+
+        if in_channels == 0 or architecture == 'skip':
+            self.fromrgb = Conv2dLayer(img_channels, tmp_channels, kernel_size=1, activation=activation, trainable=trainable(), conv_clamp=conv_clamp)
+        self.conv0 = Conv2dLayer(tmp_channels, tmp_channels, kernel_size=3, activation=activation, trainable=trainable(), conv_clamp=conv_clamp)
+        self.conv1 = Conv2dLayer(tmp_channels, out_channels, kernel_size=3, activation=activation, down=2, trainable=trainable(),
+                                 resample_filter=resample_filter, conv_clamp=conv_clamp)
+        if architecture == 'resnet':
+            self.skip = Conv2dLayer(tmp_channels, out_channels, kernel_size=1, bias=False, down=2, trainable=trainable(), resample_filter=resample_filter)
+
+    def forward(self, x, img, force_fp32=False):
+        dtype = torch.float16 if self.use_fp16 and not force_fp32 else torch.float32
+        mf = torch.channels_last if self.channels_last and not force_fp32 else torch.contiguous_format
+        if x is not None:
+            misc.assert_shape(x, [None, self.in_channels, self.resolution, self.resolution])
+            x = x.to(dtype=dtype, memory_format=mf)
+        if self.in_channels == 0 or self.architecture == 'skip':
+            misc.assert_shape(img, [None, self.img_channels, self.resolution, self.resolution])
+            img = img.to(dtype=dtype, memory_format=mf)
+            y = self.fromrgb(img)
+            x = x + y if x is not None else y
+            img = self.ops.downsample2d(img, self.resample_filter) if self.architecture == 'skip' else None
+        if self.architecture == 'resnet':
+            y = self.skip(x, gain=np.sqrt(0.5))
+            x = self.conv1(self.conv0(x), gain=np.sqrt(0.5))
+            x = y.add_(x)
+        else:
+            x = self.conv1(self.conv0(x))
+        assert x.dtype == dtype
+        return x, img
+
+
+class MinibatchStdLayer(nn.Module):
+    """Appends the per-group feature standard deviation as an extra channel (reference :1001-1023)."""
+
+    def __init__(self, group_size, num_channels=1):
+        super().__init__()
+        self.group_size, self.num_channels = group_size, num_channels
+
+    def forward(self, x):
+        n, c, h, w = x.shape
+        g = min(int(self.group_size), int(n)) if self.group_size is not None else int(n)
+        f = self.num_channels
+        y = x.reshape(g, -1, f, c // f, h, w)
+        y = y - y.mean(dim=0)
+        y = (y.square().mean(dim=0) + 1e-8).sqrt()
+        y = y.mean(dim=[2, 3, 4]).reshape(-1, f, 1, 1).repeat(g, 1, h, w)
+        return torch.cat([x, y], dim=1)
+
+
+class DiscriminatorEpilogue(OpsModule):
+    def __init__(self, in_channels, cmap_dim, resolution, img_channels, architecture='resnet', mbstd_group_size=4, mbstd_num_channels=1,
+                 activation='lrelu', conv_clamp=None):
+        assert architecture in ['orig', 'skip', 'resnet']
+        super().__init__()
+        self.in_channels, self.cmap_dim, self.resolution, self.img_channels, self.architecture = in_channels, cmap_dim, resolution, img_channels, architecture
+        if architecture == 'skip':
+            self.fromrgb = Conv2dLayer(img_channels, in_channels, kernel_size=1, activation=activation)
+        self.mbstd = MinibatchStdLayer(group_size=mbstd_group_size, num_channels=mbstd_num_channels) if mbstd_num_channels > 0 else None
+        self.conv = Conv2dLayer(in_channels + mbstd_num_channels, in_channels, kernel_size=3, activation=activation, conv_clamp=conv_clamp)
+        self.fc = FullyConnectedLayer(in_channels * (resolution ** 2), in_channels, activation=activation)
+        self.out = FullyConnectedLayer(in_channels, 1 if cmap_dim == 0 else cmap_dim)
+
+    def forward(self, x, img, cmap, force_fp32=False):
+        misc.assert_shape(x, [None, self.in_channels, self.resolution, self.resolution])
+        x = x.to(dtype=torch.float32, memory_format=torch.contiguous_format)
+        if self.architecture == 'skip':
+            x = x + self.fromrgb(img.to(torch.float32))
+        if self.mbstd is not None:
+            x = self.mbstd(x)
+        x = self.out(self.fc(self.conv(x).flatten(1)))
+        if self.cmap_dim > 0:
+            misc.assert_shape(cmap, [None, self.cmap_dim])
+            x = (x * cmap).sum(dim=1, keepdim=True) * (1 / np.sqrt(self.cmap_dim))
+        return x
+
+
+class Discriminator(OpsModule):
+    """reference :1085-1143.  Residual architecture, fp16 storage for the `num_fp16_res` highest resolutions, projection on c."""
+
+    def __init__(self, c_dim, img_resolution, img_channels, architecture='resnet', channel_base=32768, channel_max=512, num_fp16_res=0,
+                 conv_clamp=None, cmap_dim=None, block_kwargs={}, mapping_kwargs={}, epilogue_kwargs={}):
+        super().__init__()
+        self.c_dim, self.img_resolution, self.img_channels = c_dim, img_resolution, img_channels
+        self.img_resolution_log2 = int(np.log2(img_resolution))
+        self.block_resolutions = [2 ** i for i in range(self.img_resolution_log2, 2, -1)]
+        ch = {res: min(channel_base // res, channel_max) for res in self.block_resolutions + [4]}
+        fp16_resolution = max(2 ** (self.img_resolution_log2 + 1 - num_fp16_res), 8)
+        if cmap_dim is None:
+            cmap_dim = ch[4]
+        if c_dim == 0:
+            cmap_dim = 0
+        common = dict(img_channels=img_channels, architecture=architecture, conv_clamp=conv_clamp)
+        idx = 0
+        for res in self.block_resolutions:
+            block = DiscriminatorBlock(ch[res] if res < img_resolution else 0, ch[res], ch[res // 2], resolution=res, first_layer_idx=idx,
+                                       use_fp16=(res >= fp16_resolution), **block_kwargs, **common)
+            setattr(self, f'b{res}', block)
+            idx += block.num_layers
+        if c_dim > 0:
+            self.mapping = MappingNetwork(z_dim=0, c_dim=c_dim, w_dim=cmap_dim, num_ws=None, w_avg_beta=None, **mapping_kwargs)
+        self.b4 = DiscriminatorEpilogue(ch[4], cmap_dim=cmap_dim, resolution=4, **epilogue_kwargs, **common)
+
+    def forward(self, img, c, **block_kwargs):
+        x = None
+        for res in self.block_resolutions:
+            x, img = getattr(self, f'b{res}')(x, img, **block_kwargs)
+        cmap = self.mapping(None, c) if self.c_dim > 0 else None
+        return self.b4(x, img, cmap)
+
+
+def build_discriminator(img_resolution=256, channel_base=16384, channel_max=512, num_fp16_res=3):
+    """Discriminator at the BASELINE training config (train_wo_flow_fullbody.py:191-197): c_dim 512, conv_clamp 256, mbstd group 4."""
+    return Discriminator(c_dim=512, img_resolution=img_resolution, img_channels=3, channel_base=channel_base, channel_max=channel_max,
+                         num_fp16_res=num_fp16_res, conv_clamp=256, epilogue_kwargs=dict(mbstd_group_size=4))
 
 
 def build_generator_full(img_resolution=256, channel_base=16384, channel_max=512):

@@ -309,7 +309,33 @@ def gen_generator():
     save('generator_full', arrays, [meta])
 
 
+def gen_discriminator():
+    """Discriminator (fp32 blocks) at the BASELINE widths on a 4-image batch: logits, the R1 gradient wrt the image, the R1 penalty and a
+    few parameter gradients of the penalty (a full double backward through conv / upfirdn2d / bias_act-lrelu / mbstd / FC)."""
+    D = R_net.Discriminator(c_dim=512, img_resolution=256, img_channels=3, channel_base=16384, channel_max=512, num_fp16_res=0,
+                            conv_clamp=256, epilogue_kwargs=dict(mbstd_group_size=4))
+    procedural.fill_(D)
+    g = torch.Generator().manual_seed(4321)
+    img = (torch.rand(4, 3, 256, 256, generator=g) * 2 - 1).requires_grad_(True)
+    c = torch.randn(4, 512, generator=g)
+    logits = D(img, c)
+    r1_grad, = torch.autograd.grad(logits.sum(), img, create_graph=True)
+    penalty = r1_grad.square().sum([1, 2, 3])
+    (penalty.mean() * 5).backward()                       # r1_gamma / 2 = 5
+    names = ['b256.fromrgb.weight', 'b256.conv0.bias', 'b64.conv1.weight', 'b16.skip.weight', 'b4.conv.weight', 'b4.fc.bias', 'b4.out.weight', 'mapping.fc3.weight']
+    params = dict(D.named_parameters())
+    arrays = {'logits': logits, 'r1_grad': r1_grad[:, :, ::4, ::4], 'penalty': penalty}
+    for n in names:
+        gr = params[n].grad
+        arrays['grad/' + n] = gr if gr.numel() <= 70000 else gr.flatten()[::37]
+    fp = procedural.fingerprint(D)
+    pn = sorted(fp)
+    arrays['fp_sum'] = np.array([fp[n][0] for n in pn])
+    arrays['fp_abs'] = np.array([fp[n][1] for n in pn])
+    save('discriminator', arrays, [dict(names=pn, grad_names=names, n_params=sum(p.numel() for p in D.parameters()))])
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['upfirdn2d', 'bias_act', 'conv2d_resample', 'modulated_conv2d', 'layers', 'generator']
+    which = sys.argv[1:] or ['upfirdn2d', 'bias_act', 'conv2d_resample', 'modulated_conv2d', 'layers', 'generator', 'discriminator']
     for w in which:
         globals()['gen_' + w]()
