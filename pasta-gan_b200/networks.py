@@ -106,12 +106,18 @@ def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, res
     d[n,o] = rsqrt(sum_i s[n,i]^2 * sum_k W[o,i,k]^2 + 1e-8): the per-sample weight tensor [N,O,I,k,k] and the
     groups=N convolution of the reference's fused branch (:84-94) are never materialised (SURVEY.md appendix A,
     I7/I8).  The fp16 pre-normalisation of :57-59 is kept."""
-    from .torch_utils.ops import conv2d_resample as C, fma as F
+    from .torch_utils.ops import conv2d_resample as C, fma as F, conv_igemm as K
     n = int(x.shape[0])
     cout, cin, kh, kw = weight.shape
     misc.assert_shape(weight, [cout, cin, kh, kw])
     misc.assert_shape(x, [n, cin, None, None])
     misc.assert_shape(styles, [n, cin])
+    if kh == kw and padding == kh // 2 and not styles.requires_grad and \
+            K.supported(x, weight, up=up, down=down, f=resample_filter, padding=(padding,) * 4):
+        # inference on the tcgen05 kernel: style in the operand prologue, demodulation and noise in the epilogue, one launch
+        dcoefs = torch.addmm(_EPS.get(x.device), styles.square(), _weight_sq_sums(weight).t()).rsqrt() if demodulate else None
+        return K.conv2d_igemm(x, weight, f=resample_filter, up=up, flip_weight=flip_weight, styles=styles, dcoefs=dcoefs, noise=noise,
+                              cache_weights=isinstance(weight, nn.Parameter))
     if x.dtype == torch.float16 and demodulate:
         weight = weight * (1 / np.sqrt(cin * kh * kw) / weight.norm(float('inf'), dim=[1, 2, 3], keepdim=True))
         styles = styles / styles.norm(float('inf'), dim=1, keepdim=True)
