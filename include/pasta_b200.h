@@ -138,6 +138,8 @@ int pg_upfirdn2d_bias_act(const void* x, const float* f, const void* b, void* y,
  * Forward only: gradients of convolutions stay on conv2d_gradfix in this release.
  */
 int64_t pg_conv2d_igemm_workspace_bytes(int32_t Cin, int32_t Cout, int32_t ksize, int32_t up);
+/* Profiling aid: when non-NULL, every conv CTA writes 8 int64 clock64() phase stamps to buf[cta*8 ..] (tools/conv_timeline.py). */
+void    pg_debug_set_buffer(void* buf);
 /* The same operation in two steps, so that inference can pack the weights once per parameter version:
  *   prepack: w * w_scale (the layer's weight_gain, training/networks.py:171) -> fp16/bf16 GEMM tiles in `workspace`
  *   run:     the convolution proper on packed weights.  pg_conv2d_igemm_fwd == prepack(w_scale = 1) + run. */

@@ -46,8 +46,11 @@ struct ConvParams {
     uint32_t idesc; uint32_t tmem_cols;
     // up-2 polyphase mode: BN virtual channels = phases x couts (see launch code); 0 = plain
     int up2; int cout_real;
+    long long* dbg;            // optional per-CTA phase timestamps (pg_debug_set_buffer), NULL in production
     uint32_t pw_magic;         // ceil(2^32 / PW): q / PW == umulhi(q, pw_magic) for the strip positions that occur
 };
+
+#define PG_TS(slot) do { if (p.dbg) p.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (slot)] = clock64(); } while (0)
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -183,6 +186,7 @@ __device__ __forceinline__ void mma_issue_loop(const ConvParams& p, uint8_t* a_b
     for (int ci = 0; ci < p.nchunks; ci++) {
         mbar_wait(smem_u32(&a_full[sa]), pa);
         tc_fence_after();
+        if (ci == 0) PG_TS(2);
         const uint32_t a_lo = a_lo_const | (smem_u32(a_base + (size_t)sa * p.a_stage_bytes) >> 4);
 #pragma unroll
         for (int kh = 0; kh < KS; kh++) {
@@ -205,13 +209,14 @@ __device__ __forceinline__ void mma_issue_loop(const ConvParams& p, uint8_t* a_b
         umma_commit(smem_u32(&a_empty[sa]));
         if (++sa == p.SA) { sa = 0; pa ^= 1; }
     }
+    PG_TS(3);
     umma_commit(smem_u32(acc_full));
 }
 
 // ---------------------------------------------------------------------------------------------- main kernel
 // SCALE: the A operand needs a per-channel scale and/or an input activation (modulated / SPADE layers); plain layers skip both.
 template <bool SCALE>
-__global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x % p.tiles_per_img;
@@ -220,6 +225,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     const int BM   = 128 * p.NACC;
     const int m0   = tile * BM;
     const int HW   = p.H * p.W;
+    if (threadIdx.x == 0) PG_TS(0);
 
     uint8_t* a_base = smem;
     uint8_t* b_base = a_base + (size_t)p.SA * p.a_stage_bytes;
@@ -257,6 +263,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) PG_TS(1);
 
     if (warp == 0) {
         // ===================== B producer: a ring of small bulk copies (`tps` taps each) keeps many copies in flight =====================
@@ -293,8 +300,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             mbar_wait(smem_u32(&a_empty[st]), ph ^ 1);
             uint8_t* stage = a_base + (size_t)st * p.a_stage_bytes;
             for (int t = cw; t < ntasks; t += kTaskBatch * kConvWarps) {
-                // a whole batch of tasks is loaded before any is converted: up to 8 * kTaskBatch independent L2/HBM loads
-                // in flight per thread, so a chunk costs one memory latency instead of one per task
+                // a whole batch of tasks is loaded before any is converted: 8 * kTaskBatch independent L2/HBM loads in flight per thread
                 float v[kTaskBatch][8];
 #pragma unroll
                 for (int u = 0; u < kTaskBatch; u++) {
@@ -342,15 +348,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             if (lane == 0) mbar_arrive(smem_u32(&a_full[st]));
             if (++st == p.SA) { st = 0; ph ^= 1; }
         }
-
+        if (cw == 0 && lane == 0) PG_TS(6);
         // ===================== epilogue (same warps) =====================
         mbar_wait(smem_u32(acc_full), 0);
         tc_fence_after();
+        if (cw == 0 && lane == 0) PG_TS(4);
         const int quarter = warp & 3;                          // TMEM lane quarter this warp may read
-        const int half = cw >> 2;                              // the two warps of a quarter alternate 16-column chunks
+        const int part = cw >> 2;                              // the kConvWarps/4 warps of a quarter take 16-column chunks round-robin
         const int ncol_chunks = p.BN / 16;
         const float slope = (p.act == PG_ACT_LINEAR) ? 1.f : (p.act == PG_ACT_RELU ? 0.f : p.alpha);   // act(v) = max(v,0) + slope*min(v,0)
         const float cl = p.clamp >= 0.f ? p.clamp : __int_as_float(0x7f800000);
+        const bool do_act = p.act != PG_ACT_LINEAR, do_clamp = p.clamp >= 0.f;
         const int W2 = 2 * p.W;
         for (int a = 0; a < p.NACC; a++) {
             const int q = m0 + a * 128 + quarter * 32 + lane;
@@ -358,7 +366,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             const bool ok = q < p.Lp && w < p.W;
             float nz0 = 0.f;
             if (ok && p.noise && !p.up2) nz0 = __ldg(p.noise + (size_t)n * p.noise_bstride + (size_t)h * p.W + w) * p.gain;
-            for (int cc = half; cc < ncol_chunks; cc += 2) {
+            for (int cc = part; cc < ncol_chunks; cc += kConvWarps / 4) {
                 uint32_t r[16];
                 tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.BN + cc * 16), r);
                 if (!ok) continue;
@@ -385,16 +393,28 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                     ystride = (size_t)4 * HW;
                     yp = p.y + ((size_t)n * p.cout_real + o0) * ystride + (size_t)oy * W2 + ox;
                 }
+                float v[16];
 #pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    float v = fmaf(__uint_as_float(r[i]), sc[i], sh[i] + nz);
-                    v = fmaxf(v, 0.f) + slope * fminf(v, 0.f);
-                    v = fminf(fmaxf(v, -cl), cl);
-                    if (i < nvalid) yp[(size_t)i * ystride] = v;
+                for (int i = 0; i < 16; i++) v[i] = fmaf(__uint_as_float(r[i]), sc[i], sh[i] + nz);
+                if (do_act) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i], 0.f) + slope * fminf(v[i], 0.f);
+                }
+                if (do_clamp) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) v[i] = fminf(fmaxf(v[i], -cl), cl);
+                }
+                if (nvalid == 16) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) yp[(size_t)i * ystride] = v[i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) if (i < nvalid) yp[(size_t)i * ystride] = v[i];
                 }
             }
         }
     }
+    if (threadIdx.x == 64) PG_TS(5);
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -421,12 +441,15 @@ static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int k
     pl.ntiles_n = (pl.nvirt + bn - 1) / bn;
     pl.PW = (ks == 3) ? W + 1 : W;
     pl.Lp = H * pl.PW;
-    const int max_acc = 512 / bn;
-    // accumulators per CTA: as many as fit, but keep >= 2 waves of CTAs on 148 SMs when the problem allows it
+    // Two co-resident CTAs per SM when the N tile is narrow (BN <= 128): each gets half of TMEM (256 columns) and ~100 KB of shared
+    // memory, so one CTA's prologue / pipeline fill / epilogue overlaps the other's main loop.  Wide tiles (BN = 256) keep the SM alone.
+    const bool pair = bn <= 128;
+    const int tmem_budget = pair ? 256 : 512;
+    const int max_acc = tmem_budget / bn;
     int nacc = 1;
     for (int cand = (max_acc < 4 ? max_acc : 4); cand >= 1; cand >>= 1) {
         const long long ctas = (long long)N * ((pl.Lp + 128 * cand - 1) / (128 * cand)) * pl.ntiles_n;
-        if (ctas >= 2 * kNumSMs || cand == 1) { nacc = cand; break; }
+        if (ctas >= 2 * kNumSMs * (pair ? 2 : 1) || cand == 1) { nacc = cand; break; }
     }
     while (nacc > 1 && 128 * (nacc - 1) >= pl.Lp) nacc--;
     pl.NACC = nacc;
@@ -440,10 +463,10 @@ static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int k
     const size_t fixed = (size_t)pl.nchunks * kKC * 4 + (size_t)bn * 8 + 96 * 8;
     pl.tps = (ks == 3) ? 3 : 1;
     pl.b_slot = pl.b_tile * pl.tps;
-    // shared-memory budget: 3 activation stages (2 if they are huge), the rest goes to the weight ring
-    const size_t budget = 200 * 1024;
+    size_t budget = pair ? 100 * 1024 : 200 * 1024;
     pl.SA = 3;
     if ((size_t)pl.SA * pl.a_stage > budget / 2) pl.SA = 2;
+    if ((size_t)pl.SA * pl.a_stage + 2 * (size_t)pl.b_slot + fixed + 128 > budget) budget = 200 * 1024;   // large strips: one CTA per SM after all
     if (pl.nchunks < pl.SA) pl.SA = pl.nchunks < 2 ? 2 : pl.nchunks;
     const size_t left = budget > (size_t)pl.SA * pl.a_stage + fixed + 128 ? budget - (size_t)pl.SA * pl.a_stage - fixed - 128 : 0;
     pl.SB = (int)(left / pl.b_slot);
@@ -460,6 +483,9 @@ static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int k
 }
 
 }  // namespace pg
+
+static long long* g_conv_dbg = nullptr;
+extern "C" void pg_debug_set_buffer(void* buf) { g_conv_dbg = (long long*)buf; }
 
 extern "C" int64_t pg_conv2d_igemm_workspace_bytes(int32_t Cin, int32_t Cout, int32_t ksize, int32_t up) {
     pg::ConvPlan pl;
@@ -527,6 +553,7 @@ extern "C" int pg_conv2d_igemm_run(const float* x, const void* wpack, const floa
     p.idesc = (1u << 4) | ((uint32_t)operand_format << 7) | ((uint32_t)operand_format << 10) | ((uint32_t)(pl.BN >> 3) << 17) | (8u << 24);
     p.tmem_cols = pl.tmem_cols;
     p.up2 = up == 2; p.cout_real = Cout;
+    p.dbg = g_conv_dbg;
     p.pw_magic = (uint32_t)((0x100000000ull + (uint64_t)pl.PW - 1) / (uint64_t)pl.PW);
     const bool scale = styles != nullptr || in_act != PG_ACT_LINEAR || in_gain != 1.f;
     auto kern = scale ? conv_igemm_kernel<true> : conv_igemm_kernel<false>;

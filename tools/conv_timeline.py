@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""Per-CTA phase timeline of the tcgen05 conv kernel (clock64 stamps via pg_debug_set_buffer): prologue, pipeline fill, main loop,
+converter finish, epilogue.  usage: conv_timeline.py [--cin 128 --cout 128 --res 128 --k 3 --up 1 --n 16]"""
+import argparse, os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import pasta_gan_b200
+from pasta_gan_b200.torch_utils.ops import conv_igemm, upfirdn2d
+ap = argparse.ArgumentParser()
+for k, d in dict(cin=128, cout=128, res=128, k=3, up=1, n=16).items():
+    ap.add_argument('--' + k, type=int, default=d)
+a = ap.parse_args()
+dev = torch.device('cuda:0')
+x = torch.randn(a.n, a.cin, a.res, a.res, device=dev)
+w = torch.randn(a.cout, a.cin, a.k, a.k, device=dev) / (a.cin * a.k * a.k) ** 0.5
+f = upfirdn2d.setup_filter([1, 3, 3, 1]).to(dev)
+lib = pasta_gan_b200.capi.load()
+run = lambda: conv_igemm.conv2d_igemm(x, w, f=f if a.up == 2 else None, up=a.up)
+with torch.no_grad():
+    for _ in range(3):
+        run()
+    buf = torch.zeros(8 * 8192, dtype=torch.int64, device=dev)
+    lib.pg_debug_set_buffer(buf.data_ptr())
+    run(); torch.cuda.synchronize()
+    lib.pg_debug_set_buffer(None)
+t = buf.view(-1, 8).cpu()
+t = t[t[:, 0] != 0].double()
+names = ['prologue (start -> setup sync)', 'fill (setup -> first A stage ready at the MMA thread)', 'main loop (first A ready -> last MMA issued)',
+         'converters done (setup -> last stage stored)', 'accumulator ready seen by epilogue (setup -> acc_full)', 'epilogue (acc_full -> stores done)', 'total']
+vals = [t[:, 1] - t[:, 0], t[:, 2] - t[:, 1], t[:, 3] - t[:, 2], t[:, 6] - t[:, 1], t[:, 4] - t[:, 1], t[:, 5] - t[:, 4], t[:, 5] - t[:, 0]]
+print(f'{t.shape[0]} CTAs; cycles (median / p10 / p90)')
+for nme, v in zip(names, vals):
+    q = torch.quantile(v, torch.tensor([0.5, 0.1, 0.9], dtype=torch.float64))
+    print(f'  {nme:62s} {q[0]:9.0f} {q[1]:9.0f} {q[2]:9.0f}')
