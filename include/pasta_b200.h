@@ -157,6 +157,19 @@ int pg_conv2d_igemm_fwd(const float* x, const float* w, const float* fir, const 
                         int32_t act, float alpha, float gain, float clamp, int32_t operand_format,
                         void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * torgb_skip — the ToRGB skip path of a synthesis block in one streaming kernel (north_star kernel 3):
+ *
+ *   out[n,o] = upsample2d(img_in[n,o], fir)  +  clamp( sum_c w[o,c] * styles[n,c] * x[n,c] + bias[o] )
+ *
+ * Replaces upfirdn2d.upsample2d + modulated_conv2d(demodulate=False, 1x1) + bias_act(linear, clamp) + img.add_(y)
+ * (training/networks.py:5709-5715, ToRGBLayerFull.forward :5601-5611; upfirdn2d.py:308-343).
+ * x [N,C,H,W] fp32 dense NCHW (16-byte aligned, W % 4 == 0); w [O,C] (the 1x1 kernel), O <= 8; styles [N,C] or NULL (already
+ * multiplied by the layer's weight_gain); bias [O] or NULL; img_in [N,O,H/2,W/2] or NULL (first block: no skip image);
+ * fir: the [4,4] float32 resample filter (needed with img_in); clamp < 0: none; out [N,O,H,W].  Forward only. */
+int pg_torgb_skip(const float* x, const float* w, const float* styles, const float* bias, const float* img_in, const float* fir,
+                  float* out, int32_t N, int32_t C, int32_t O, int32_t H, int32_t W, float clamp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,6 +36,7 @@ SIGNATURES = {
     'pg_conv2d_igemm_run': [c_ptr] * 5 + [c_i64, c_ptr, c_ptr] + [c_i32] * 7 + [c_i32, c_f32, c_f32, c_i32, c_f32, c_f32, c_f32, c_i32, c_ptr],
     'pg_conv2d_igemm_fwd': [c_ptr] * 6 + [c_i64, c_ptr, c_ptr] + [c_i32] * 7 + [c_i32, c_i32, c_f32, c_f32, c_i32, c_f32, c_f32, c_f32, c_i32,
                             c_ptr, c_i64, c_ptr],
+    'pg_torgb_skip': [c_ptr] * 7 + [c_i32] * 5 + [c_f32, c_ptr],
     'pg_upfirdn2d_bias_act': [c_ptr, c_ptr, c_ptr, c_ptr, I32x4, I64x4, I32x4, I64x4, c_i32, c_i32, c_i64, c_i64] + [c_i32] * 8 +
                              [c_i32, c_f32, c_i32, c_f32, c_f32, c_f32, c_i32, c_ptr],
 }

@@ -54,7 +54,7 @@ def cuda_ops():
             name='sm100a',
             setup_filter=U.setup_filter, upfirdn2d=U.upfirdn2d, filter2d=U.filter2d, upsample2d=U.upsample2d,
             downsample2d=U.downsample2d, bias_act=B.bias_act, conv2d_resample=C.conv2d_resample, fma=F.fma,
-            modulated_conv2d=modulated_conv2d, conv_layer=conv_layer, modconv_layer=modconv_layer,
+            modulated_conv2d=modulated_conv2d, conv_layer=conv_layer, modconv_layer=modconv_layer, torgb_skip=_torgb_skip,
             act_def_gain={k: float(v.def_gain) for k, v in B.activation_funcs.items()},
         )
     return _CUDA_OPS
@@ -202,6 +202,14 @@ def modconv_layer(x, weight, styles, noise=None, up=1, padding=0, resample_filte
     x = modulated_conv2d(x=x, weight=weight, styles=styles, noise=noise, up=up, padding=padding, resample_filter=resample_filter,
                          demodulate=demodulate, flip_weight=flip_weight, fused_modconv=fused_modconv)
     return B.bias_act(x, bias, act=act, gain=act_gain, clamp=clamp)
+
+
+def _torgb_skip(x, weight, styles, bias, clamp, img, f):
+    """Product ToRGB skip: one streaming kernel when the shape allows it, else None (the caller composes the reference's four calls)."""
+    from .torch_utils.ops import torgb as T
+    if not T.supported(x, weight, img, f) or styles.requires_grad:
+        return None
+    return T.torgb_skip(x, weight, styles=styles, bias=bias, clamp=clamp, img=img, f=f)
 
 
 # ----------------------------------------------------------------------------- layers
@@ -390,6 +398,18 @@ class ToRGBLayerFull(OpsModule):
             self.m_weight1 = nn.Parameter(torch.randn([6, in_channels, kernel_size, kernel_size]))
             self.m_bias1 = nn.Parameter(torch.zeros([6]))
 
+    def forward_skip(self, x, w, img, resample_filter):
+        """Fused skip path: returns (upsample2d(img) + rgb, parsing) or None when the operator table has no fused kernel for this shape."""
+        fused = getattr(self.ops, 'torgb_skip', None)
+        if fused is None:
+            return None
+        styles = self.affine(w) * self.weight_gain
+        rgb = fused(x, self.weight, styles, self.bias, self.conv_clamp, img, resample_filter)
+        if rgb is None:
+            return None
+        parsing = fused(x, self.m_weight1, styles, self.m_bias1, self.conv_clamp, None, None) if self.predicts_parsing else None
+        return rgb, parsing
+
     def forward(self, x, w, fused_modconv=True):
         styles = self.affine(w) * self.weight_gain
         layer = getattr(self.ops, 'modconv_layer', None)
@@ -561,12 +581,20 @@ class SynthesisBlockFull(OpsModule):
                 x = self.merge_conv(torch.cat([x, cat_feat[str(x.shape[2])].to(torch.float32)], dim=1))
         if img is not None:
             misc.assert_shape(img, [None, self.img_channels, self.resolution // 2, self.resolution // 2])
-            img = self.ops.upsample2d(img, self.resample_filter)
         parsing = None
         if self.is_last or self.architecture == 'skip':
-            y, parsing = self.torgb(x, next(w_iter), fused_modconv=fused_modconv)
-            y = y.to(dtype=torch.float32)
-            img = img.add_(y) if img is not None else y
+            w_rgb = next(w_iter)
+            fused = self.torgb.forward_skip(x, w_rgb, img, self.resample_filter)
+            if fused is not None:                           # one streaming kernel: upsample2d(img) + clamp(1x1 modconv + b)
+                img, parsing = fused
+            else:
+                if img is not None:
+                    img = self.ops.upsample2d(img, self.resample_filter)
+                y, parsing = self.torgb(x, w_rgb, fused_modconv=fused_modconv)
+                y = y.to(dtype=torch.float32)
+                img = img.add_(y) if img is not None else y
+        elif img is not None:
+            img = self.ops.upsample2d(img, self.resample_filter)
         return x, img, parsing
 
 

@@ -94,3 +94,22 @@ def test_linearity_at_baseline_size(cv):
     assert rel_err(y12, y1 + y2) < 3e-3
     ref = O._conv(x1[5:6].cpu().double(), wt[:8].cpu().double(), padding=1)
     assert rel_err(y1[5:6, :8], ref) < 2e-3
+
+
+@pytest.mark.parametrize('shape', [(2, 64, 3, 32, 32, True), (1, 512, 3, 4, 4, False), (2, 128, 6, 16, 16, False), (1, 64, 3, 256, 256, True), (3, 20, 3, 8, 12, True)],
+                         ids=str)
+def test_torgb_skip_kernel(shape):
+    """img_out = upsample2d(img_in) + clamp(modulated 1x1 conv + b): fp32 SIMT kernel, 1e-5 relative vs the oracle composition."""
+    from pasta_gan_b200.torch_utils.ops import torgb
+    n, c, o, h, w, with_img = shape
+    torch.manual_seed(sum(shape[:5]))
+    f = O.setup_filter([1, 3, 3, 1])
+    x = torch.randn(n, c, h, w)
+    wt = torch.randn(o, c, 1, 1)
+    s = (1 + 0.5 * torch.randn(n, c)) / c ** 0.5
+    b = torch.randn(o) * 0.1
+    img = torch.randn(n, o, h // 2, w // 2) if with_img else None
+    y = O.bias_act(O.modulated_conv2d(x.double(), wt.double(), s.double(), demodulate=False), b.double(), clamp=1.0)
+    ref = y + O.upsample2d(img.double(), f.double()) if with_img else y
+    out = torgb.torgb_skip(x.to(DEV), wt.to(DEV), styles=s.to(DEV), bias=b.to(DEV), clamp=1.0, img=(img.to(DEV) if with_img else None), f=f.to(DEV))
+    assert rel_err(out, ref) < 1e-5
