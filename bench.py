@@ -43,6 +43,7 @@ def parse():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=16, help='images per GPU per step (test.sh: 16)')
+    ap.add_argument('--workload', default='gen256', choices=['gen256', 'gen512'], help='gen256 = BASELINE configs[1] (default); gen512 = configs[2]')
     ap.add_argument('--no-graph', action='store_true', help='eager launches instead of CUDA-graph replay')
     ap.add_argument('--skip-cpu-baseline', action='store_true')
     return ap.parse_args()
@@ -221,9 +222,15 @@ def run_b200(args, world, rank, local):
     capi = pasta_gan_b200.capi
     pk = peaks()
     torch.backends.cudnn.benchmark = True
-    G = N.build_generator_full().eval().requires_grad_(False)
+    if args.workload == 'gen512':
+        G = N.build_generator_512().eval().requires_grad_(False)
+        inp = procedural.synth_inputs_512(args.batch, seed=4321 + 100 * rank, device=dev)
+        wl = 'Generator_512 512x320 (512x512 padded) try-on inference, batch 16 per GPU (BASELINE configs[2]; the only 512-px generator in the reference tree)'
+    else:
+        G = N.build_generator_full().eval().requires_grad_(False)
+        inp = procedural.synth_inputs(args.batch, seed=1234 + 100 * rank, device=dev)
+        wl = 'GeneratorFull 256x192 (256x256 padded) full-body try-on inference, batch 16 per GPU (BASELINE configs[1])'
     procedural.fill_(G)
-    inp = procedural.synth_inputs(args.batch, seed=1234 + 100 * rank, device=dev)
     l0 = capi.launch_count()
     sess = TryOnSession(G, inp, dev, use_graph=not args.no_graph, warmup=max(3, args.warmup))
     # launches of our kernels in ONE forward (eager count: warm-up forwards + the captured one all issue the same sequence)
@@ -271,10 +278,10 @@ def run_b200(args, world, rank, local):
         cpu = {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
     act_bytes = sum(v['bytes'] for v in profile.values())
     line = {
-        'metric': METRIC, 'value': imgs / t_dev, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'metric': METRIC if args.workload == 'gen256' else METRIC.replace('256x192 padded to 256x256', '512x320 padded to 512x512'), 'value': imgs / t_dev, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * t_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'GeneratorFull 256x192 (256x256 padded) full-body try-on inference, batch 16 per GPU (BASELINE configs[1])',
+        'config': {'workload': wl,
                    'batch_per_gpu': args.batch, 'global_batch': world * args.batch, 'parallelism': f'replicas x{world} (batch-sharded, no collective)',
                    'cuda_graph': not args.no_graph,
                    'l2': f'no explicit flush: one step streams ~{act_bytes / 1e9:.1f} GB of activations through the operators (> 126 MB L2)',

@@ -14,9 +14,10 @@ class TryOnSession:
         self.G = generator.to(device).eval().requires_grad_(False)
         self.device = torch.device(device)
         self.batch = int(example_inputs['retain'].shape[0])
-        self.static_in = {k: torch.empty_like(example_inputs[k], device=self.device) for k in INPUT_KEYS}
+        self.keys = tuple(k for k in example_inputs if k != 'z')      # GeneratorFull: INPUT_KEYS; Generator512: c, retain, pose
+        self.static_in = {k: torch.empty_like(example_inputs[k], device=self.device) for k in self.keys}
         self.static_in['z'] = torch.zeros(self.batch, self.G.z_dim, device=self.device)
-        self.host_in = {k: torch.empty_like(example_inputs[k], device='cpu').pin_memory() for k in INPUT_KEYS}
+        self.host_in = {k: torch.empty_like(example_inputs[k], device='cpu').pin_memory() for k in self.keys}
         self.graph = None
         self.out = None
         self.stream = torch.cuda.Stream(self.device)
@@ -29,17 +30,18 @@ class TryOnSession:
             self.graph = torch.cuda.CUDAGraph()
             with torch.no_grad(), torch.cuda.graph(self.graph, stream=self.stream):
                 self.out = self._forward()
-        self.host_out = [torch.empty_like(o, device='cpu').pin_memory() for o in self.out[:2]]
-        self.h2d_bytes = sum(self.host_in[k].numel() * self.host_in[k].element_size() for k in INPUT_KEYS)
+        self.host_out = [torch.empty_like(o, device='cpu').pin_memory() for o in self.out[:2]]      # the image(s); parsing logits stay on device
+        self.h2d_bytes = sum(self.host_in[k].numel() * self.host_in[k].element_size() for k in self.keys)
         self.d2h_bytes = sum(o.numel() * o.element_size() for o in self.host_out)
 
     def _forward(self):
-        return self.G(**self.static_in, noise_mode='const')
+        out = self.G(**self.static_in, noise_mode='const')
+        return out if isinstance(out, (tuple, list)) else (out,)
 
     def load(self, inputs):
         """Device-resident inputs -> static buffers (no host traffic)."""
         with torch.cuda.stream(self.stream):
-            for k in INPUT_KEYS:
+            for k in self.keys:
                 self.static_in[k].copy_(inputs[k], non_blocking=True)
 
     def step(self):
@@ -56,7 +58,7 @@ class TryOnSession:
         call ``synchronize()`` before reading ``host_out``."""
         src = self.host_in if host_inputs is None else host_inputs
         with torch.cuda.stream(self.stream):
-            for k in INPUT_KEYS:
+            for k in self.keys:
                 self.static_in[k].copy_(src[k], non_blocking=True)
         out = self.step()
         with torch.cuda.stream(self.stream):

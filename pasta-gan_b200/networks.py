@@ -24,6 +24,11 @@ sm_100a operators.  They are a re-expression, not a copy: every layer is a thin 
     SynthesisBlockFull             :5615-5719        SynthesisBlockFull
     SynthesisNetworkFull           :5723-5840        SynthesisNetworkFull
     GeneratorFull                  :5844-5880        GeneratorFull
+    ToRGBLayer                     :320-336          ToRGBLayer
+    SynthesisBlockV_512            :3578-3677        SynthesisBlock512
+    SynthesisNetwork_512           :3680-3729        SynthesisNetwork512
+    StyleEncoderNetwork_512        :3732-3779        StyleEncoderNetwork512
+    Generator_512                  :3782-3815        Generator512
     DiscriminatorBlock             :917-997          DiscriminatorBlock
     MinibatchStdLayer              :1001-1023        MinibatchStdLayer
     DiscriminatorEpilogue          :1027-1081        DiscriminatorEpilogue
@@ -683,6 +688,149 @@ class GeneratorFull(OpsModule):
         cat_feats = {str(f.shape[2]): f for f in feats}
         return self.synthesis(ws, pose_feat, cat_feats, denorm_upper_input, denorm_lower_input, denorm_upper_mask, denorm_lower_mask,
                               **synthesis_kwargs)
+
+
+# ----------------------------------------------------------------------------- 512 x 512 generator (the only 512-px network in the reference tree)
+
+
+class ToRGBLayer(OpsModule):
+    """Plain ToRGB (reference :320-336): modulated 1x1 conv without demodulation + bias + clamp."""
+
+    def __init__(self, in_channels, out_channels, w_dim, kernel_size=1, conv_clamp=None, channels_last=False):
+        super().__init__()
+        self.conv_clamp = conv_clamp
+        self.affine = FullyConnectedLayer(w_dim, in_channels, bias_init=1)
+        self.weight = nn.Parameter(torch.randn([out_channels, in_channels, kernel_size, kernel_size]))
+        self.bias = nn.Parameter(torch.zeros([out_channels]))
+        self.weight_gain = 1 / np.sqrt(in_channels * (kernel_size ** 2))
+        self.predicts_parsing = False
+
+    forward_skip = ToRGBLayerFull.forward_skip
+
+    def forward(self, x, w, fused_modconv=True):
+        styles = self.affine(w) * self.weight_gain
+        layer = getattr(self.ops, 'modconv_layer', None)
+        if layer is not None:
+            return layer(x, self.weight, styles, demodulate=False, fused_modconv=fused_modconv, bias=self.bias.to(x.dtype), clamp=self.conv_clamp)
+        y = self.ops.modulated_conv2d(x=x, weight=self.weight, styles=styles, demodulate=False, fused_modconv=fused_modconv)
+        return self.ops.bias_act(y, self.bias.to(x.dtype), clamp=self.conv_clamp)
+
+
+class SynthesisBlock512(OpsModule):
+    """reference SynthesisBlockV_512 :3578-3677 (skip architecture; retain-person features merged above 32 px)."""
+
+    def __init__(self, in_channels, out_channels, w_dim, resolution, img_channels, is_last, architecture='skip', resample_filter=_FIR,
+                 conv_clamp=None, use_fp16=False, fp16_channels_last=False, **layer_kwargs):
+        assert architecture == 'skip'
+        super().__init__()
+        self.in_channels, self.w_dim, self.resolution, self.img_channels, self.is_last = in_channels, w_dim, resolution, img_channels, is_last
+        self.register_buffer('resample_filter', _fir_buffer(resample_filter))
+        self.num_conv = self.num_torgb = 0
+        if in_channels == 0:
+            self.const = nn.Parameter(torch.randn([out_channels, resolution, resolution]))      # state_dict parity; unused
+        else:
+            self.conv0 = SynthesisLayer(in_channels, out_channels, w_dim=w_dim, resolution=resolution, up=2, resample_filter=resample_filter,
+                                        conv_clamp=conv_clamp, **layer_kwargs)
+            self.num_conv += 1
+        self.conv1 = SynthesisLayer(out_channels, out_channels, w_dim=w_dim, resolution=resolution, conv_clamp=conv_clamp, **layer_kwargs)
+        self.num_conv += 1
+        self.torgb = ToRGBLayer(out_channels, img_channels, w_dim=w_dim, conv_clamp=conv_clamp)
+        self.num_torgb += 1
+        self.merge_conv = Conv2dLayer(out_channels + 64, out_channels, kernel_size=1, resample_filter=resample_filter)
+
+    def forward(self, x, img, ws, pose_feature, cat_feat, fused_modconv=None, **layer_kwargs):
+        misc.assert_shape(ws, [None, self.num_conv + self.num_torgb, self.w_dim])
+        w_iter = iter(ws.unbind(dim=1))
+        if fused_modconv is None:
+            fused_modconv = not self.training
+        if self.in_channels == 0:
+            x = self.conv1(pose_feature.to(torch.float32), next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
+        else:
+            x = self.conv0(x.to(torch.float32), next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
+            x = self.conv1(x, next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
+            if x.shape[2] > 32:
+                x = self.merge_conv(torch.cat([x, cat_feat[str(x.shape[2])].to(torch.float32)], dim=1))
+        w_rgb = next(w_iter)
+        fused = self.torgb.forward_skip(x, w_rgb, img, self.resample_filter)
+        if fused is not None:
+            img = fused[0]
+        else:
+            if img is not None:
+                img = self.ops.upsample2d(img, self.resample_filter)
+            y = self.torgb(x, w_rgb, fused_modconv=fused_modconv).to(torch.float32)
+            img = img.add_(y) if img is not None else y
+        return x, img
+
+
+class SynthesisNetwork512(OpsModule):
+    def __init__(self, w_dim, img_resolution, img_channels, channel_base=32768, channel_max=512, num_fp16_res=0, **block_kwargs):
+        assert img_resolution >= 8 and img_resolution & (img_resolution - 1) == 0
+        super().__init__()
+        self.w_dim, self.img_resolution, self.img_channels = w_dim, img_resolution, img_channels
+        self.block_resolutions = [2 ** i for i in range(3, int(np.log2(img_resolution)) + 1)]
+        ch = {res: min(channel_base // res, channel_max) for res in self.block_resolutions}
+        self.num_ws = 0
+        for res in self.block_resolutions:
+            block = SynthesisBlock512(ch[res // 2] if res > 8 else 0, ch[res], w_dim=w_dim, resolution=res, img_channels=img_channels,
+                                      is_last=(res == img_resolution), **block_kwargs)
+            self.num_ws += block.num_conv + (block.num_torgb if res == img_resolution else 0)
+            setattr(self, f'b{res}', block)
+
+    def forward(self, ws, pose_feat, cat_feat, **block_kwargs):
+        misc.assert_shape(ws, [None, self.num_ws, self.w_dim])
+        ws = ws.to(torch.float32)
+        x = img = None
+        idx = 0
+        for res in self.block_resolutions:
+            block = getattr(self, f'b{res}')
+            x, img = block(x, img, ws.narrow(1, idx, block.num_conv + block.num_torgb), pose_feat, cat_feat, **block_kwargs)
+            idx += block.num_conv
+        return img
+
+
+class StyleEncoderNetwork512(OpsModule):
+    def __init__(self, input_nc, output_nc, ngf=64, n_downsampling=4):
+        super().__init__()
+        enc = [Conv2dLayer(input_nc, ngf, kernel_size=1)]
+        for m_in, m_out in zip([1, 2, 4], [2, 4, 8]):
+            enc += [Dense(ngf * m_in, ngf * m_in), Conv2dLayer(ngf * m_in, ngf * m_out, kernel_size=3, down=2)]
+        enc += [nn.AdaptiveAvgPool2d(1)]
+        self.model = nn.Sequential(*enc)
+        self.fc = FullyConnectedLayer(output_nc, output_nc)
+        self.feat_enc = nn.Sequential(Conv2dLayer(3, ngf, kernel_size=3), *[Conv2dLayer(ngf, ngf, kernel_size=3, down=2) for _ in range(3)])
+
+    def forward(self, x, const_input):
+        feats = []
+        for layer in self.feat_enc:
+            const_input = layer(const_input)
+            feats.append(const_input)
+        x = self.model(x)
+        return self.fc(x.view(x.size(0), -1)), feats
+
+
+class Generator512(OpsModule):
+    """reference Generator_512 :3782-3815 — the only 512-px generator in the source tree (the released 512x320 pickle is not available;
+    BASELINE configs[2] therefore uses this network, as SURVEY.md §8(d) states)."""
+
+    def __init__(self, z_dim, c_dim, w_dim, img_resolution, img_channels, mapping_kwargs={}, synthesis_kwargs={}):
+        super().__init__()
+        self.z_dim, self.c_dim, self.w_dim, self.img_resolution, self.img_channels = z_dim, c_dim, w_dim, img_resolution, img_channels
+        self.synthesis = SynthesisNetwork512(w_dim=w_dim, img_resolution=img_resolution, img_channels=img_channels, **synthesis_kwargs)
+        self.num_ws = self.synthesis.num_ws
+        self.mapping = MappingNetwork(z_dim=z_dim, c_dim=c_dim, w_dim=w_dim, num_ws=self.num_ws, **mapping_kwargs)
+        self.const_encoding = ConstEncoderNetwork(input_nc=3 + 3, output_nc=512, ngf=64, n_downsampling=6)
+        self.style_encoding = StyleEncoderNetwork512(input_nc=24 * 2, output_nc=512, ngf=64, n_downsampling=6)
+
+    def forward(self, z, c, retain, pose, truncation_psi=1, truncation_cutoff=None, **synthesis_kwargs):
+        pose_feat = self.const_encoding(pose)
+        stylecode, feats = self.style_encoding(c, retain)
+        ws = self.mapping(z, stylecode, truncation_psi=truncation_psi, truncation_cutoff=truncation_cutoff)
+        return self.synthesis(ws, pose_feat, {str(f.shape[2]): f for f in feats}, **synthesis_kwargs)
+
+
+def build_generator_512(channel_base=16384, channel_max=512):
+    return Generator512(z_dim=0, c_dim=512, w_dim=512, img_resolution=512, img_channels=3, mapping_kwargs=dict(num_layers=1),
+                        synthesis_kwargs=dict(channel_base=channel_base, channel_max=channel_max, num_fp16_res=0, conv_clamp=256, use_noise=True))
 
 
 # ----------------------------------------------------------------------------- discriminator (training path, R1 double backward)

@@ -309,6 +309,20 @@ def gen_generator():
     save('generator_full', arrays, [meta])
 
 
+def gen_generator_512():
+    """Generator_512 (the only 512-px network in the tree) at channel_base 16384, N = 1, eval, const noise; fp16-stored output."""
+    G = R_net.Generator_512(z_dim=0, c_dim=512, w_dim=512, img_resolution=512, img_channels=3, mapping_kwargs=dict(num_layers=1),
+                            synthesis_kwargs=dict(channel_base=16384, channel_max=512, num_fp16_res=0, conv_clamp=256, use_noise=True)).eval()
+    procedural.fill_(G)
+    inp = procedural.synth_inputs_512(1)
+    with torch.no_grad():
+        img = G(**inp, noise_mode='const')
+    fp = procedural.fingerprint(G)
+    names = sorted(fp)
+    save('generator_512', {'img': img.half(), 'fp_sum': np.array([fp[n][0] for n in names]), 'fp_abs': np.array([fp[n][1] for n in names])},
+         [dict(names=names, n_params=sum(p.numel() for p in G.parameters()), num_ws=int(G.num_ws), img_absmax=float(img.abs().max()))])
+
+
 def gen_discriminator():
     """Discriminator (fp32 blocks) at the BASELINE widths on a 4-image batch: logits, the R1 gradient wrt the image, the R1 penalty and a
     few parameter gradients of the penalty (a full double backward through conv / upfirdn2d / bias_act-lrelu / mbstd / FC)."""
@@ -336,6 +350,6 @@ def gen_discriminator():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['upfirdn2d', 'bias_act', 'conv2d_resample', 'modulated_conv2d', 'layers', 'generator', 'discriminator']
+    which = sys.argv[1:] or ['upfirdn2d', 'bias_act', 'conv2d_resample', 'modulated_conv2d', 'layers', 'generator', 'discriminator', 'generator_512']
     for w in which:
         globals()['gen_' + w]()

@@ -99,3 +99,9 @@ def synth_inputs(batch, res=256, parts_ch=42, parts_res=64, seed=1234, content_w
         denorm_lower_mask=mask(6),
     )
     return {k: v.to(device) for k, v in d.items()}
+
+
+def synth_inputs_512(batch, seed=4321, device='cpu'):
+    """Inputs of the 512 x 512 generator (reference test_512.py:104-118 shapes): 48-channel 128 px garment patches, retain, pose."""
+    d = synth_inputs(batch, res=512, parts_ch=48, parts_res=128, seed=seed, content_w=320, device=device)
+    return {k: d[k] for k in ('z', 'c', 'retain', 'pose')}

@@ -78,3 +78,16 @@ def test_session_graph_matches_eager(cuda_generator):
     sess.synchronize()
     assert rel_err(hout[0], ref[0]) < 1e-5 and rel_err(hout[1], ref[1]) < 1e-5
     assert sess.h2d_bytes == sum(inp[k].numel() * 4 for k in inp if k != 'z')
+
+
+def test_generator_512_cuda_vs_reference(golden):
+    """512 x 512 generator (BASELINE configs[2]) on the sm_100a path vs the reference's CPU output: 1e-2 relative."""
+    g = golden('generator_512')
+    G = N.build_generator_512().eval()
+    procedural.fill_(G)
+    G.to(DEV).requires_grad_(False)
+    with torch.no_grad():
+        img = G(**procedural.synth_inputs_512(1, device=DEV), noise_mode='const')
+    err = rel_err(img, g.t('img', dtype=torch.float32))
+    print('generator_512 rel err', err)
+    assert err < 1e-2

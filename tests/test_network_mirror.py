@@ -94,3 +94,18 @@ def run_layer_case(golden, tag, table, device='cpu', tol=1e-4):
                                  'conv_plain', 'conv_down', 'conv_up', 'conv_7x7', 'resblock_down', 'fc_lrelu', 'fc_linear', 'dense', 'spade_norm'])
 def test_layers_oracle_vs_reference(golden, tag):
     run_layer_case(golden, tag, O.operator_table())
+
+
+def test_generator_512_mirror_matches_reference(golden):
+    """BASELINE configs[2] network (reference Generator_512, the only 512-px generator in the tree) on CPU through the oracle table."""
+    g = golden('generator_512')
+    meta = g.meta[0]
+    G = N.build_generator_512().eval()
+    procedural.fill_(G)
+    fp = procedural.fingerprint(G)
+    assert sorted(fp) == meta['names'] and G.num_ws == meta['num_ws']
+    np.testing.assert_allclose(np.array([fp[n][0] for n in meta['names']]), g.arrays['fp_sum'], rtol=1e-9, atol=1e-9)
+    N.use_ops(G, O.operator_table(fast=True))
+    with torch.no_grad():
+        img = G(**procedural.synth_inputs_512(1), noise_mode='const')
+    assert rel_err(img, g.t('img', dtype=torch.float32)) < 2e-3
