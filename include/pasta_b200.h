@@ -157,6 +157,18 @@ int pg_conv2d_igemm_fwd(const float* x, const float* w, const float* fir, const 
                         int32_t act, float alpha, float gain, float clamp, int32_t operand_format,
                         void* workspace, int64_t workspace_bytes, void* stream);
 
+/* SPADE normalisation fused into the epilogue of the convolution that produces its modulation maps (reference Spade_Norm_Block.forward,
+ * training/networks.py:4371-4379, plus the pre-activation of the Spade_Conv2dLayer that consumes the result, :4345-4349):
+ *
+ *   [gamma | beta] = conv(feat, [w_gamma ; w_beta])          (one GEMM, 2C output columns, k in {1,3}, 'same')
+ *   y[n,c]         = act( (x[n,c] - mean[n,c]) * rstd[n,c] * (1 + gamma[n,c]) + beta[n,c] ) * gain
+ *
+ * feat [N,Cin,H,W]; wpack_gamma_beta = pg_conv2d_igemm_prepack of the [2C,Cin,k,k] concatenation; x, y [N,C,H,W]; mean, rstd [N,C]
+ * (instance-norm statistics of x); 2C <= 256, C % 16 == 0.  gamma and beta never reach HBM. */
+int pg_conv2d_igemm_spade_run(const float* feat, const void* wpack_gamma_beta, const float* x, const float* mean, const float* rstd,
+                              float* y, int32_t N, int32_t Cin, int32_t C, int32_t H, int32_t W, int32_t ksize,
+                              int32_t act, float alpha, float gain, int32_t operand_format, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * torgb_skip — the ToRGB skip path of a synthesis block in one streaming kernel (north_star kernel 3):
  *

@@ -46,6 +46,7 @@ struct ConvParams {
     uint32_t idesc; uint32_t tmem_cols;
     // up-2 polyphase mode: BN virtual channels = phases x couts (see launch code); 0 = plain
     int up2; int cout_real;
+    const float* sp_x; const float* sp_mean; const float* sp_rstd; int spade;   // SPADE epilogue: y = act((x-mean)*rstd*(1+gamma)+beta)*gain
     long long* dbg;            // optional per-CTA phase timestamps (pg_debug_set_buffer), NULL in production
     uint32_t pw_magic;         // ceil(2^32 / PW): q / PW == umulhi(q, pw_magic) for the strip positions that occur
 };
@@ -256,6 +257,13 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
         const int v = jn * p.BN + j;
         const int o = p.up2 ? v % p.cout_real : v;
         const bool live = v < p.Cout;
+        if (p.spade) {
+            const int C = p.cout_real >> 1;
+            const float r = j < C ? p.sp_rstd[(size_t)n * C + j] : 0.f;
+            s_scale[j] = r;
+            s_shift[j] = j < C ? -p.sp_mean[(size_t)n * C + j] * r : 0.f;
+            continue;
+        }
         s_scale[j] = live ? (p.dcoefs ? p.dcoefs[(size_t)n * p.cout_real + o] : 1.f) * p.gain : 0.f;
         s_shift[j] = live && p.bias ? p.bias[o] * p.gain : 0.f;
     }
@@ -364,6 +372,29 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
             const int q = m0 + a * 128 + quarter * 32 + lane;
             const int h = (int)__umulhi((uint32_t)q, p.pw_magic), w = q - h * p.PW;
             const bool ok = q < p.Lp && w < p.W;
+            if (p.spade) {
+                // gamma = columns [0, C), beta = columns [C, 2C) of the same accumulator row; normalise x with the staged statistics
+                const int C = p.cout_real >> 1;
+                const float* xp = p.sp_x + (size_t)n * C * HW + (size_t)h * p.W + w;
+                float* yp = p.y + (size_t)n * C * HW + (size_t)h * p.W + w;
+                for (int cc = part; cc < C / 16; cc += kConvWarps / 4) {
+                    uint32_t rg[16], rb[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.BN + cc * 16), rg);
+                    tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.BN + C + cc * 16), rb);
+                    if (!ok) continue;
+                    float xv[16];
+#pragma unroll
+                    for (int i = 0; i < 16; i++) xv[i] = __ldg(xp + (size_t)(cc * 16 + i) * HW);
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const float xn_ = fmaf(xv[i], s_scale[cc * 16 + i], s_shift[cc * 16 + i]);
+                        float v = fmaf(xn_, 1.f + __uint_as_float(rg[i]), __uint_as_float(rb[i]));
+                        v = (fmaxf(v, 0.f) + slope * fminf(v, 0.f)) * p.gain;
+                        yp[(size_t)(cc * 16 + i) * HW] = v;
+                    }
+                }
+                continue;
+            }
             float nz0 = 0.f;
             if (ok && p.noise && !p.up2) nz0 = __ldg(p.noise + (size_t)n * p.noise_bstride + (size_t)h * p.W + w) * p.gain;
             for (int cc = part; cc < ncol_chunks; cc += kConvWarps / 4) {
@@ -525,11 +556,12 @@ extern "C" int pg_conv2d_igemm_prepack(const float* w, const float* fir, float w
     return launch_status("conv2d_igemm_prepack", 1);
 }
 
-extern "C" int pg_conv2d_igemm_run(const float* x, const void* wpack, const float* styles, const float* dcoefs,
-                                   const float* noise, int64_t noise_batch_stride, const float* bias, float* y,
-                                   int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t ksize, int32_t up,
-                                   int32_t in_act, float in_alpha, float in_gain,
-                                   int32_t act, float alpha, float gain, float clamp, int32_t operand_format, void* stream) {
+static int conv_run_impl(const float* x, const void* wpack, const float* styles, const float* dcoefs,
+                         const float* noise, int64_t noise_batch_stride, const float* bias, float* y,
+                         int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t ksize, int32_t up,
+                         int32_t in_act, float in_alpha, float in_gain,
+                         int32_t act, float alpha, float gain, float clamp, int32_t operand_format, void* stream,
+                         const float* sp_x, const float* sp_mean, const float* sp_rstd) {
     using namespace pg;
     int rc = conv_validate(N, Cin, Cout, H, W, ksize, up, operand_format);
     if (rc != PG_OK) return rc;
@@ -553,6 +585,9 @@ extern "C" int pg_conv2d_igemm_run(const float* x, const void* wpack, const floa
     p.idesc = (1u << 4) | ((uint32_t)operand_format << 7) | ((uint32_t)operand_format << 10) | ((uint32_t)(pl.BN >> 3) << 17) | (8u << 24);
     p.tmem_cols = pl.tmem_cols;
     p.up2 = up == 2; p.cout_real = Cout;
+    p.sp_x = sp_x; p.sp_mean = sp_mean; p.sp_rstd = sp_rstd; p.spade = sp_x != nullptr;
+    if (p.spade) PG_REQUIRE(pl.ntiles_n == 1 && pl.BN == Cout && (Cout / 2) % 16 == 0 && up == 1 && sp_mean && sp_rstd,
+                            "conv2d_igemm_spade: gamma and beta (2C <= 256 channels, C %% 16 == 0) must share one N tile");
     p.dbg = g_conv_dbg;
     p.pw_magic = (uint32_t)((0x100000000ull + (uint64_t)pl.PW - 1) / (uint64_t)pl.PW);
     const bool scale = styles != nullptr || in_act != PG_ACT_LINEAR || in_gain != 1.f;
@@ -561,6 +596,24 @@ extern "C" int pg_conv2d_igemm_run(const float* x, const void* wpack, const floa
     dim3 grid((unsigned)(N * pl.tiles_per_img), (unsigned)pl.ntiles_n);
     kern<<<grid, kConvThreads, pl.smem, s>>>(p);
     return launch_status("conv2d_igemm", 1);
+}
+
+extern "C" int pg_conv2d_igemm_run(const float* x, const void* wpack, const float* styles, const float* dcoefs,
+                                   const float* noise, int64_t noise_batch_stride, const float* bias, float* y,
+                                   int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t ksize, int32_t up,
+                                   int32_t in_act, float in_alpha, float in_gain,
+                                   int32_t act, float alpha, float gain, float clamp, int32_t operand_format, void* stream) {
+    return conv_run_impl(x, wpack, styles, dcoefs, noise, noise_batch_stride, bias, y, N, Cin, Cout, H, W, ksize, up, in_act, in_alpha, in_gain,
+                         act, alpha, gain, clamp, operand_format, stream, nullptr, nullptr, nullptr);
+}
+
+extern "C" int pg_conv2d_igemm_spade_run(const float* feat, const void* wpack_gamma_beta, const float* x, const float* mean, const float* rstd,
+                                         float* y, int32_t N, int32_t Cin, int32_t C, int32_t H, int32_t W, int32_t ksize,
+                                         int32_t act, float alpha, float gain, int32_t operand_format, void* stream) {
+    using namespace pg;
+    PG_REQUIRE(x && mean && rstd, "conv2d_igemm_spade: x, mean and rstd must be device pointers");
+    return conv_run_impl(feat, wpack_gamma_beta, nullptr, nullptr, nullptr, 0, nullptr, y, N, Cin, 2 * C, H, W, ksize, 1, PG_ACT_LINEAR, 0.f, 1.f,
+                         act, alpha, gain, -1.f, operand_format, stream, x, mean, rstd);
 }
 
 extern "C" int pg_conv2d_igemm_fwd(const float* x, const float* w, const float* fir, const float* styles, const float* dcoefs,

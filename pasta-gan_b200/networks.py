@@ -59,7 +59,7 @@ def cuda_ops():
             name='sm100a',
             setup_filter=U.setup_filter, upfirdn2d=U.upfirdn2d, filter2d=U.filter2d, upsample2d=U.upsample2d,
             downsample2d=U.downsample2d, bias_act=B.bias_act, conv2d_resample=C.conv2d_resample, fma=F.fma,
-            modulated_conv2d=modulated_conv2d, conv_layer=conv_layer, modconv_layer=modconv_layer, torgb_skip=_torgb_skip,
+            modulated_conv2d=modulated_conv2d, conv_layer=conv_layer, modconv_layer=modconv_layer, torgb_skip=_torgb_skip, spade_conv_norm=_spade_conv_norm,
             act_def_gain={k: float(v.def_gain) for k, v in B.activation_funcs.items()},
         )
     return _CUDA_OPS
@@ -207,6 +207,18 @@ def modconv_layer(x, weight, styles, noise=None, up=1, padding=0, resample_filte
     x = modulated_conv2d(x=x, weight=weight, styles=styles, noise=noise, up=up, padding=padding, resample_filter=resample_filter,
                          demodulate=demodulate, flip_weight=flip_weight, fused_modconv=fused_modconv)
     return B.bias_act(x, bias, act=act, gain=act_gain, clamp=clamp)
+
+
+def _spade_conv_norm(x, actv, w_gamma, w_beta, w_scale, post_act):
+    """Product SPADE normalisation: instance-norm + (1 + gamma) * . + beta (+ the consumer's pre-activation) inside the epilogue of the
+    merged gamma|beta convolution; None when the shape is not covered."""
+    from .torch_utils.ops import conv_igemm as K
+    if not K.spade_supported(x, actv, w_gamma, w_beta):
+        return None
+    act, gain = post_act if post_act is not None else ('linear', 1.0)
+    if act not in ('linear', 'relu', 'lrelu'):
+        return None
+    return K.spade_conv_norm(x, actv, w_gamma, w_beta, w_scale=w_scale, act=act, gain=gain)
 
 
 def _torgb_skip(x, weight, styles, bias, clamp, img, f):
@@ -511,11 +523,23 @@ class SpadeNormBlock(OpsModule):
         self.conv_beta = SpadeConv2dLayer(norm_channels, norm_channels, kernel_size=3, bias=False)
         self.param_free_norm = nn.InstanceNorm2d(norm_channels, affine=False)
 
-    def forward(self, x, denorm_feats):
+    def forward(self, x, denorm_feats, post_act=None):
+        """``post_act = (name, gain)``: apply the pre-activation of the Spade conv that consumes the result here (then call it with
+        ``no_act=True``); only honoured on the fused path, so callers must check ``fused_post_act``."""
+        fused = getattr(self.ops, 'spade_conv_norm', None)
+        if fused is not None:
+            actv = self.ops.conv_layer(denorm_feats, self.conv_mlp.weight, None, padding=1, act='relu', act_gain=1.0,
+                                       w_scale=float(self.conv_mlp.weight_gain), cache_weights=True)
+            y = fused(x, actv, self.conv_gamma.weight, self.conv_beta.weight, float(self.conv_gamma.weight_gain), post_act)
+            if y is not None:
+                return y
         actv = self.conv_mlp_act(self.conv_mlp(denorm_feats, no_act=True))
         gamma = self.conv_gamma(actv, no_act=True)
         beta = self.conv_beta(actv, no_act=True)
-        return self.param_free_norm(x) * (1 + gamma) + beta
+        y = self.param_free_norm(x) * (1 + gamma) + beta
+        if post_act is not None:
+            y = self.ops.bias_act(y, None, act=post_act[0], gain=post_act[1])
+        return y
 
 
 class SpadeResBlockV2(OpsModule):
@@ -534,9 +558,12 @@ class SpadeResBlockV2(OpsModule):
 
     def forward(self, x, denorm_feat):
         x = self.conv(x, no_act=True)
-        y = self.skip(self.spade_skip(x, denorm_feat), gain=np.sqrt(0.5))
-        x = self.conv0(self.spade0(x, denorm_feat))
-        x = self.conv1(self.spade1(x, denorm_feat), gain=np.sqrt(0.5))
+        # the pre-activation (relu * act_gain * gain) of each consuming Spade conv is handed to the norm block, which applies it in the
+        # same pass (fused: in the GEMM epilogue that produces gamma / beta); the convs then run bare
+        pre = lambda conv, gain: (conv.activation, float(conv.act_gain * gain))
+        y = self.skip(self.spade_skip(x, denorm_feat, post_act=pre(self.skip, np.sqrt(0.5))), no_act=True)
+        x = self.conv0(self.spade0(x, denorm_feat, post_act=pre(self.conv0, 1)), no_act=True)
+        x = self.conv1(self.spade1(x, denorm_feat, post_act=pre(self.conv1, np.sqrt(0.5))), no_act=True)
         return y.add_(x)
 
 

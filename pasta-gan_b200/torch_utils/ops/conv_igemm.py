@@ -112,3 +112,55 @@ def conv2d_igemm(x, w, f=None, up=1, flip_weight=True, styles=None, dcoefs=None,
         if sp:
             sp.close()
     return y
+
+
+_cat_cache = {}
+
+
+def _gamma_beta_weights(w_gamma, w_beta):
+    """[w_gamma ; w_beta] as one long-lived tensor (so the packed-weight cache can key on it), rebuilt when either parameter changes."""
+    key = (id(w_gamma), id(w_beta), w_gamma._version, w_beta._version, w_gamma.data_ptr(), w_beta.data_ptr())
+    hit = _cat_cache.get(key)
+    if hit is None or hit[0] is not w_gamma or hit[1] is not w_beta:
+        if len(_cat_cache) > 64:
+            _cat_cache.clear()
+        hit = (w_gamma, w_beta, torch.cat([w_gamma.detach(), w_beta.detach()], dim=0).contiguous())
+        _cat_cache[key] = hit
+    return hit[2]
+
+
+def spade_supported(x, feat, w_gamma, w_beta):
+    if not (enabled and x.is_cuda and x.dtype == torch.float32 and feat.dtype == torch.float32 and x.ndim == 4):
+        return False
+    if torch.is_grad_enabled() and (x.requires_grad or feat.requires_grad or w_gamma.requires_grad):
+        return False
+    c = int(x.shape[1])
+    k = int(w_gamma.shape[2])
+    return (w_gamma.shape == w_beta.shape and w_gamma.shape[0] == c and 2 * c <= 256 and c % 16 == 0 and k in (1, 3) and
+            w_gamma.shape[2] == w_gamma.shape[3] and feat.shape[2:] == x.shape[2:] and feat.shape[1] == w_gamma.shape[1] and x.numel() > 0)
+
+
+def spade_conv_norm(x, feat, w_gamma, w_beta, w_scale=1.0, act='linear', alpha=0.2, gain=1.0, eps=1e-5, fmt=None):
+    """act(instance_norm(x) * (1 + conv(feat, w_gamma)) + conv(feat, w_beta)) * gain  in one tcgen05 launch (gamma / beta stay in TMEM)."""
+    capi = _backend.capi()
+    n, c, h, wd = (int(v) for v in x.shape)
+    cin, k = int(feat.shape[1]), int(w_gamma.shape[2])
+    x = x.contiguous()
+    feat = feat.contiguous()
+    var, mean = torch.var_mean(x, dim=(2, 3), unbiased=False)
+    rstd = (var + eps).rsqrt().contiguous()
+    mean = mean.contiguous()
+    wcat = _gamma_beta_weights(w_gamma, w_beta)
+    fmt_code = _FMT[fmt or operand_format]
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        capi.require_device()
+        wpack = _packed_weights(capi, wcat, None, w_scale, 1, True, fmt_code, True)
+        sp = capi.span('conv_igemm', flops=2 * n * 2 * c * cin * k * k * h * wd, nbytes=4 * (2 * x.numel() + feat.numel() + wcat.numel()))
+        rc = capi.load().pg_conv2d_igemm_spade_run(capi.ptr(feat), capi.ptr(wpack), capi.ptr(x), capi.ptr(mean), capi.ptr(rstd), capi.ptr(y),
+                                                   n, cin, c, h, wd, k, _ACT[act], float(alpha), float(gain), fmt_code,
+                                                   capi.current_stream(x.device))
+        capi.check(rc, 'pg_conv2d_igemm_spade_run')
+        if sp:
+            sp.close()
+    return y

@@ -113,3 +113,21 @@ def test_torgb_skip_kernel(shape):
     ref = y + O.upsample2d(img.double(), f.double()) if with_img else y
     out = torgb.torgb_skip(x.to(DEV), wt.to(DEV), styles=s.to(DEV), bias=b.to(DEV), clamp=1.0, img=(img.to(DEV) if with_img else None), f=f.to(DEV))
     assert rel_err(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize('shape', [(2, 32, 48, 24, 24, 3), (1, 128, 128, 64, 64, 3), (2, 64, 16, 20, 28, 1)], ids=str)
+def test_spade_fused_epilogue(cv, shape):
+    """act(instance_norm(x) * (1 + conv(feat, Wg)) + conv(feat, Wb)) * gain with gamma / beta kept in TMEM (reference Spade_Norm_Block)."""
+    n, c, cin, h, w, k = shape
+    torch.manual_seed(sum(shape))
+    x = torch.randn(n, c, h, w) * 2 + 0.5
+    feat = torch.randn(n, cin, h, w)
+    wg = torch.randn(c, cin, k, k) / (cin * k * k) ** 0.5
+    wb = torch.randn(c, cin, k, k) / (cin * k * k) ** 0.5
+    xd = x.double()
+    norm = (xd - xd.mean(dim=(2, 3), keepdim=True)) / (xd.var(dim=(2, 3), unbiased=False, keepdim=True) + 1e-5).sqrt()
+    ref = norm * (1 + O._conv(feat.double(), wg.double(), padding=k // 2)) + O._conv(feat.double(), wb.double(), padding=k // 2)
+    ref = O.bias_act(ref, None, act='relu', gain=1.3)
+    assert cv.spade_supported(x.to(DEV), feat.to(DEV), wg.to(DEV), wb.to(DEV))
+    y = cv.spade_conv_norm(x.to(DEV), feat.to(DEV), wg.to(DEV), wb.to(DEV), act='relu', gain=1.3)
+    assert rel_err(y, ref) < 3e-3
