@@ -137,6 +137,10 @@ int pg_upfirdn2d_bias_act(const void* x, const float* f, const void* b, void* y,
  * workspace: device scratch of at least pg_conv2d_igemm_workspace_bytes(...) bytes (packed weights), caller-owned.
  * Forward only: gradients of convolutions stay on conv2d_gradfix in this release.
  */
+/* `up` selects the resampling fused into the convolution: 1 = none, 2 = up-2 (above), PG_CONV_DOWN2 = the down-2 form of
+ * conv2d_resample.py:119-122 (4x4 FIR with padding 2, then the 3x3 convolution at stride 2; y is [N,Cout,H/2,W/2]) evaluated as a
+ * 'same' 3x3 convolution over the four space-to-depth planes of x with the 6x6 composite kernel w (*) f — no filtered intermediate. */
+#define PG_CONV_DOWN2 (-2)
 int64_t pg_conv2d_igemm_workspace_bytes(int32_t Cin, int32_t Cout, int32_t ksize, int32_t up);
 /* Profiling aid: when non-NULL, every conv CTA writes 8 int64 clock64() phase stamps to buf[cta*8 ..] (tools/conv_timeline.py). */
 void    pg_debug_set_buffer(void* buf);

@@ -46,6 +46,7 @@ struct ConvParams {
     uint32_t idesc; uint32_t tmem_cols;
     // up-2 polyphase mode: BN virtual channels = phases x couts (see launch code); 0 = plain
     int up2; int cout_real;
+    int down2, cin_real, hin, win;   // down-2 mode: the A operand is the 4-plane space-to-depth view of x [N,cin_real,hin,win]
     const float* sp_x; const float* sp_mean; const float* sp_rstd; int spade;   // SPADE epilogue: y = act((x-mean)*rstd*(1+gamma)+beta)*gain
     long long* dbg;            // optional per-CTA phase timestamps (pg_debug_set_buffer), NULL in production
     uint32_t pw_magic;         // ceil(2^32 / PW): q / PW == umulhi(q, pw_magic) for the strip positions that occur
@@ -125,7 +126,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
 // up2 != 0: the 3x3 weights are first convolved with the 4x4 FIR (gain 4) into a 6x6 composite and split into the four
 // output-parity 3x3 kernels of the polyphase form; virtual channel v = phase * Cout + o.
 struct PackParams {
-    const float* w; const float* fir; void* out; int Cout, Cin, ks, BN, nchunks, ntaps, ntiles, flip_weight, fmt, up2; float w_scale;
+    const float* w; const float* fir; void* out; int Cout, Cin, ks, BN, nchunks, ntaps, ntiles, flip_weight, fmt, up2, down2; float w_scale;
 };
 
 __device__ float composite_tap(const PackParams& p, int o, int c, int a, int b, int th, int tw) {
@@ -144,6 +145,22 @@ __device__ float composite_tap(const PackParams& p, int o, int c, int a, int b, 
     return acc;
 }
 
+// down-2 (FIR pad 2 -> 3x3 stride 2, conv2d_resample.py:119-122) as a 'same' 3x3 stride-1 conv over the space-to-depth planes of x:
+//   Kd = w' (*) k (6x6 full convolution, k = f flipped, w' = w for correlation / w mirrored for true convolution)
+//   virtual channel (plane = 2a+b, c), tap (r, s)  ->  Kd[o, c, 2r+a, 2s+b]                  (checked against the oracle to 4e-15 in fp64)
+__device__ float down2_tap(const PackParams& p, int o, int c, int a, int b, int r, int s_) {
+    const int u = 2 * r + a, v = 2 * s_ + b;
+    float acc = 0.f;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            const int fp = u - i, fq = v - j;
+            if (fp < 0 || fp > 3 || fq < 0 || fq > 3) continue;
+            const int wi = p.flip_weight ? i : 2 - i, wj = p.flip_weight ? j : 2 - j;
+            acc += p.w[((size_t)(o * p.Cin + c) * 3 + wi) * 3 + wj] * p.fir[(3 - fp) * 4 + (3 - fq)];
+        }
+    return acc;
+}
+
 __global__ void conv_prepack_kernel(PackParams p) {
     const size_t total = (size_t)p.ntiles * p.nchunks * p.ntaps * 2 * p.BN * 8;
     const int nvirt = p.up2 ? 4 * p.Cout : p.Cout;
@@ -157,7 +174,13 @@ __global__ void conv_prepack_kernel(PackParams p) {
         const int jn = (int)r;
         const int v = jn * p.BN + nl, c = ci * kKC + j * 8 + e;
         float val = 0.f;
-        if (v < nvirt && c < p.Cin) {
+        if (p.down2) {
+            // c runs over the 4 * Cin virtual channels (plane-major); p.Cin is the real channel count
+            if (v < p.Cout && c < 4 * p.Cin) {
+                const int plane = c / p.Cin, cr = c - plane * p.Cin;
+                val = down2_tap(p, v, cr, plane >> 1, plane & 1, tap / 3, tap % 3);
+            }
+        } else if (v < nvirt && c < p.Cin) {
             const int kh = tap / p.ks, kw = tap % p.ks;
             if (p.up2) {
                 const int phase = v / p.Cout, o = v % p.Cout;
@@ -251,7 +274,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
     }
     // per-sample input scale: style * in_gain (1 * in_gain for plain convs); zero for padded channels
     for (int c = threadIdx.x; c < cin_pad; c += kConvThreads)
-        s_style[c] = (c < p.Cin) ? (p.styles ? p.styles[(size_t)n * p.Cin + c] : 1.f) * p.in_gain : 0.f;
+        s_style[c] = (c < p.Cin) ? (p.styles ? (p.down2 ? p.styles[(size_t)n * p.cin_real + c % p.cin_real] : p.styles[(size_t)n * p.Cin + c]) : 1.f) * p.in_gain : 0.f;
     // epilogue constants with the output gain folded in (relu / lrelu / linear are positively homogeneous, gain > 0)
     for (int j = threadIdx.x; j < p.BN; j += kConvThreads) {
         const int v = jn * p.BN + j;
@@ -300,7 +323,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
         const int ngroups = p.PA / 32;
         const int ntasks = ngroups * 2;                       // (position group, plane)
         const int halo = (p.ks == 3) ? p.PW + 1 : 0;
-        const float* xn = p.x + (size_t)n * p.Cin * HW;
+        const float* xn = p.down2 ? p.x + (size_t)n * p.cin_real * p.hin * p.win : p.x + (size_t)n * p.Cin * HW;
         const bool has_in_act = p.in_act != PG_ACT_LINEAR;
         const float in_slope = (p.in_act == PG_ACT_RELU) ? 0.f : p.in_alpha;
         int st = 0; uint32_t ph = 0;
@@ -318,16 +341,22 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
                     bool ok = tt < ntasks && q >= 0 && q < p.Lp;
                     if (ok) { h = (int)__umulhi((uint32_t)q, p.pw_magic); w = q - h * p.PW; ok = w < p.W; }
                     const int c0 = ci * kKC + (tt & 1) * 8;
-                    const float* src = xn + (size_t)c0 * HW + h * p.W + w;
+                    const float* src; int cs;
+                    if (!p.down2) { src = xn + (size_t)c0 * HW + h * p.W + w; cs = HW; }
+                    else {
+                        const int plane = c0 / p.cin_real, cr = c0 - plane * p.cin_real;     // 8-channel groups never straddle a plane
+                        cs = p.hin * p.win;
+                        src = xn + (size_t)cr * cs + (2 * h + (plane >> 1)) * p.win + 2 * w + (plane & 1);
+                    }
 #pragma unroll
                     for (int i = 0; i < 8; i++) v[u][i] = 0.f;
                     if (ok) {
                         if (c0 + 8 <= p.Cin) {
 #pragma unroll
-                            for (int i = 0; i < 8; i++) v[u][i] = __ldg(src + i * HW);
+                            for (int i = 0; i < 8; i++) v[u][i] = __ldg(src + i * cs);
                         } else {
 #pragma unroll
-                            for (int i = 0; i < 8; i++) if (c0 + i < p.Cin) v[u][i] = __ldg(src + i * HW);
+                            for (int i = 0; i < 8; i++) if (c0 + i < p.Cin) v[u][i] = __ldg(src + i * cs);
                         }
                     }
                 }
@@ -520,14 +549,15 @@ extern "C" void pg_debug_set_buffer(void* buf) { g_conv_dbg = (long long*)buf; }
 
 extern "C" int64_t pg_conv2d_igemm_workspace_bytes(int32_t Cin, int32_t Cout, int32_t ksize, int32_t up) {
     pg::ConvPlan pl;
-    if (pg::make_plan(pl, 1, Cin, Cout, 8, 8, ksize, up == 2) != PG_OK) return -1;
+    if (pg::make_plan(pl, 1, up == PG_CONV_DOWN2 ? 4 * Cin : Cin, Cout, 8, 8, ksize, up == 2) != PG_OK) return -1;
     return (int64_t)pl.ntiles_n * pl.nchunks * pl.b_stage;
 }
 
 static int conv_validate(int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t ksize, int32_t up, int32_t operand_format) {
     using namespace pg;
     PG_REQUIRE(ksize == 1 || ksize == 3, "conv2d_igemm: kernel size must be 1 or 3 (got %d)", ksize);
-    PG_REQUIRE(up == 1 || (up == 2 && ksize == 3), "conv2d_igemm: up must be 1, or 2 with a 3x3 kernel");
+    PG_REQUIRE(up == 1 || ((up == 2 || up == PG_CONV_DOWN2) && ksize == 3), "conv2d_igemm: resample must be 1, 2 (up) or PG_CONV_DOWN2, the latter two with a 3x3 kernel");
+    PG_REQUIRE(up != PG_CONV_DOWN2 || (Cin % 16 == 0 && H % 2 == 0 && W % 2 == 0), "conv2d_igemm: down-2 needs Cin %% 16 == 0 and even H, W");
     PG_REQUIRE(N >= 0 && Cin >= 1 && Cout >= 1 && H >= 1 && W >= 1, "conv2d_igemm: bad sizes");
     PG_REQUIRE(operand_format == 0 || operand_format == 1, "conv2d_igemm: operand_format must be 0 (fp16) or 1 (bf16)");
     PG_REQUIRE(up == 1 || Cout % 16 == 0, "conv2d_igemm: up=2 needs Cout to be a multiple of 16");
@@ -539,16 +569,17 @@ extern "C" int pg_conv2d_igemm_prepack(const float* w, const float* fir, float w
     using namespace pg;
     int rc = conv_validate(1, Cin, Cout, 8, 8, ksize, up, operand_format);
     if (rc != PG_OK) return rc;
-    PG_REQUIRE(up == 1 || fir != nullptr, "conv2d_igemm: up=2 needs the 4x4 FIR");
+    PG_REQUIRE(up == 1 || fir != nullptr, "conv2d_igemm: resampling needs the 4x4 FIR");
     PG_REQUIRE(w && workspace, "conv2d_igemm: w and workspace must be device pointers");
+    const bool down2 = up == PG_CONV_DOWN2;
     ConvPlan pl;
-    rc = make_plan(pl, 1, Cin, Cout, 8, 8, ksize, up == 2);
+    rc = make_plan(pl, 1, down2 ? 4 * Cin : Cin, Cout, 8, 8, ksize, up == 2);
     if (rc != PG_OK) return rc;
     const int64_t need = (int64_t)pl.ntiles_n * pl.nchunks * pl.b_stage;
     PG_REQUIRE(workspace_bytes >= need, "conv2d_igemm: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
     PackParams pp;
     pp.w = w; pp.fir = fir; pp.out = workspace; pp.Cout = Cout; pp.Cin = Cin; pp.ks = ksize; pp.BN = pl.BN; pp.nchunks = pl.nchunks;
-    pp.ntaps = pl.ntaps; pp.ntiles = pl.ntiles_n; pp.flip_weight = flip_weight ? 1 : 0; pp.fmt = operand_format; pp.up2 = up == 2; pp.w_scale = w_scale;
+    pp.ntaps = pl.ntaps; pp.ntiles = pl.ntiles_n; pp.flip_weight = flip_weight ? 1 : 0; pp.fmt = operand_format; pp.up2 = up == 2; pp.down2 = down2; pp.w_scale = w_scale;
     const size_t pack_total = (size_t)need / 2;
     int pblocks = (int)((pack_total + 255) / 256);
     if (pblocks > kNumSMs * 16) pblocks = kNumSMs * 16;
@@ -571,11 +602,15 @@ static int conv_run_impl(const float* x, const void* wpack, const float* styles,
     PG_REQUIRE(gain > 0.f && in_gain > 0.f, "conv2d_igemm: gains must be positive (they are folded through the activation)");
     if (N == 0) return PG_OK;
     PG_REQUIRE(x && wpack && y, "conv2d_igemm: x, packed weights and y must be device pointers");
+    const bool down2 = up == PG_CONV_DOWN2;
+    const int hin = H, win = W, cin_real = Cin;
+    if (down2) { H /= 2; W /= 2; Cin *= 4; }                      // the GEMM runs over the space-to-depth view at the output resolution
     ConvPlan pl;
     rc = make_plan(pl, N, Cin, Cout, H, W, ksize, up == 2);
     if (rc != PG_OK) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     ConvParams p;
+    p.down2 = down2; p.cin_real = cin_real; p.hin = hin; p.win = win;
     p.x = x; p.wpack = wpack; p.styles = styles; p.dcoefs = dcoefs; p.noise = noise; p.bias = bias; p.y = y;
     p.noise_bstride = noise_batch_stride;
     p.N = N; p.Cin = Cin; p.Cout = pl.nvirt; p.H = H; p.W = W; p.ks = ksize;

@@ -179,7 +179,7 @@ def conv_layer(x, w, b=None, f=None, up=1, down=1, padding=0, flip_weight=True, 
     pad4 = (padding,) * 4 if isinstance(padding, int) else None
     if act in ('linear', 'relu', 'lrelu') and in_act in (None, 'relu', 'lrelu') and \
             K.supported(x, w, up=up, down=down, f=f, padding=pad4):
-        return K.conv2d_igemm(x, w, f=f, up=up, flip_weight=flip_weight, bias=b, in_act=in_act or 'linear', in_gain=in_gain,
+        return K.conv2d_igemm(x, w, f=f, up=up, down=down, flip_weight=flip_weight, bias=b, in_act=in_act or 'linear', in_gain=in_gain,
                               act=act, gain=act_gain, clamp=clamp, w_scale=w_scale, cache_weights=cache_weights)
     if in_act is not None:
         x = B.bias_act(x, None, act=in_act, gain=in_gain)
@@ -290,7 +290,7 @@ class Conv2dLayer(OpsModule):
     def _fused(self, x, gain, pre_act):
         """One-launch layer when the operator table offers it (the CUDA product does; the oracle table does not)."""
         layer = getattr(self.ops, 'conv_layer', None)
-        if layer is None or self.down != 1:
+        if layer is None:
             return None
         w = self.weight                                   # raw parameter: weight_gain is applied when the GEMM tiles are packed
         b = self.bias.to(x.dtype) if self.bias is not None else None

@@ -25,6 +25,9 @@ def _conv2d_wrapper(x, w, stride=1, padding=0, groups=1, transpose=False, flip_w
     """``flip_weight=True`` is cross-correlation (what conv2d computes); ``False`` flips the taps first."""
     if not flip_weight:
         w = w.flip([2, 3])
+    py, px = (padding, padding) if isinstance(padding, int) else tuple(padding)
+    if not transpose and stride == 1 and conv_igemm.supported(x, w, groups=groups, padding=(px, px, py, py)):
+        return conv_igemm.conv2d_igemm(x, w, flip_weight=True)       # plain stride-1 'same' conv inside a lowering; w already carries the flip
     op = conv2d_gradfix.conv_transpose2d if transpose else conv2d_gradfix.conv2d
     sp = _backend.capi().span('library_conv(cudnn)') if x.is_cuda else None
     y = op(x, w, stride=stride, padding=padding, groups=groups)
@@ -66,7 +69,7 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
     # tcgen05 implicit-GEMM path (inference, dense fp32 NCHW): plain 'same' 1x1 / 3x3 convolutions, and the up-2 3x3 form
     # evaluated polyphase on the low-resolution input (no (2H+1)^2 intermediate, no separate FIR pass).
     if conv_igemm.supported(x, w, up=up, down=down, groups=groups, f=f, padding=_parse_padding(padding), flip_filter=flip_filter):
-        return conv_igemm.conv2d_igemm(x, w, f=f, up=up, flip_weight=flip_weight)
+        return conv_igemm.conv2d_igemm(x, w, f=f, up=up, down=down, flip_weight=flip_weight)
 
     pad = [px0, px1, py0, py1]
     pointwise = (kw == 1 and kh == 1)

@@ -24,9 +24,12 @@ def supported(x, w, up=1, down=1, groups=1, f=None, padding=None, flip_filter=Fa
         return False
     if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad):
         return False
-    if groups != 1 or down != 1 or up not in (1, 2) or w.shape[2] != w.shape[3] or w.shape[2] not in (1, 3):
+    if groups != 1 or down not in (1, 2) or up not in (1, 2) or w.shape[2] != w.shape[3] or w.shape[2] not in (1, 3):
         return False
     k = int(w.shape[2])
+    if down == 2 and (up != 1 or k != 3 or f is None or f.ndim != 2 or tuple(f.shape) != (4, 4) or flip_filter or
+                      x.shape[1] % 16 != 0 or x.shape[2] % 2 or x.shape[3] % 2):
+        return False
     if padding is not None and tuple(padding) != (k // 2,) * 4:
         return False
     if up == 2 and (k != 3 or f is None or f.ndim != 2 or tuple(f.shape) != (4, 4) or flip_filter or w.shape[0] % 16 != 0):
@@ -56,7 +59,7 @@ def _packed_weights(capi, w, f, w_scale, up, flip_weight, fmt_code, cache):
         capi.check(2, 'pg_conv2d_igemm_workspace_bytes')
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=w.device)
     wc = w.detach().contiguous()
-    rc = lib.pg_conv2d_igemm_prepack(capi.ptr(wc), capi.ptr(f) if up == 2 else None, float(w_scale), cin, cout, k, up,
+    rc = lib.pg_conv2d_igemm_prepack(capi.ptr(wc), capi.ptr(f) if up != 1 else None, float(w_scale), cin, cout, k, up,
                                      int(bool(flip_weight)), fmt_code, capi.ptr(ws), ws_bytes, capi.current_stream(w.device))
     capi.check(rc, 'pg_conv2d_igemm_prepack')
     if key is not None:
@@ -66,7 +69,7 @@ def _packed_weights(capi, w, f, w_scale, up, flip_weight, fmt_code, cache):
     return ws
 
 
-def conv2d_igemm(x, w, f=None, up=1, flip_weight=True, styles=None, dcoefs=None, noise=None, bias=None,
+def conv2d_igemm(x, w, f=None, up=1, down=1, flip_weight=True, styles=None, dcoefs=None, noise=None, bias=None,
                  in_act='linear', in_alpha=0.2, in_gain=1.0, act='linear', alpha=0.2, gain=1.0, clamp=None, fmt=None,
                  w_scale=1.0, cache_weights=False):
     """y = clamp(act(dcoefs * conv(styles * in_gain * in_act(x), w * w_scale) + noise + bias) * gain); see include/pasta_b200.h."""
@@ -76,14 +79,17 @@ def conv2d_igemm(x, w, f=None, up=1, flip_weight=True, styles=None, dcoefs=None,
     cout, cin_w, k, _ = (int(v) for v in w.shape)
     assert cin_w == cin, 'weight / input channel mismatch'
     x = x.contiguous()
-    y = torch.empty([n, cout, h * up, wd * up], dtype=torch.float32, device=x.device)
+    assert not (up == 2 and down == 2)
+    mode = -2 if down == 2 else up                       # PG_CONV_DOWN2 / 2 / 1
+    oh, ow = (h // 2, wd // 2) if down == 2 else (h * up, wd * up)
+    y = torch.empty([n, cout, oh, ow], dtype=torch.float32, device=x.device)
     nb_stride = 0
     if noise is not None:
         noise = noise.to(torch.float32).contiguous()
-        assert noise.shape[-2:] == (h * up, wd * up), 'noise must match the output resolution'
+        assert noise.shape[-2:] == (oh, ow), 'noise must match the output resolution'
         if noise.ndim == 4:
             assert noise.shape[1] == 1
-            nb_stride = 0 if noise.shape[0] == 1 else h * up * wd * up
+            nb_stride = 0 if noise.shape[0] == 1 else oh * ow
         else:
             assert noise.ndim == 2
     opt = lambda t: None if t is None else t.to(torch.float32).contiguous()
@@ -94,17 +100,17 @@ def conv2d_igemm(x, w, f=None, up=1, flip_weight=True, styles=None, dcoefs=None,
         assert tuple(dcoefs.shape) == (n, cout)
     if bias is not None:
         assert tuple(bias.shape) == (cout,)
-    if up == 2:
+    if mode != 1:
         f = f.to(torch.float32).contiguous()
     fmt_code = _FMT[fmt or operand_format]
     with torch.cuda.device(x.device):
         capi.require_device()
-        wpack = _packed_weights(capi, w, f, w_scale, up, flip_weight, fmt_code, cache_weights)
-        sp = capi.span('conv_igemm', flops=2 * n * cout * cin * k * k * h * wd * (4 if up == 2 else 1),
+        wpack = _packed_weights(capi, w, f, w_scale, mode, flip_weight, fmt_code, cache_weights)
+        sp = capi.span('conv_igemm', flops=2 * n * cout * cin * k * k * h * wd * (4 if mode != 1 and down != 2 else 1),
                        nbytes=4 * (x.numel() + y.numel() + w.numel()))
         rc = capi.load().pg_conv2d_igemm_run(capi.ptr(x), capi.ptr(wpack), capi.ptr(styles), capi.ptr(dcoefs),
                                              capi.ptr(noise), nb_stride, capi.ptr(bias), capi.ptr(y),
-                                             n, cin, cout, h, wd, k, up,
+                                             n, cin, cout, h, wd, k, mode,
                                              _ACT[in_act], float(in_alpha), float(in_gain),
                                              _ACT[act], float(alpha), float(gain), float(-1 if clamp is None else clamp),
                                              fmt_code, capi.current_stream(x.device))

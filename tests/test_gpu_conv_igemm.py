@@ -131,3 +131,25 @@ def test_spade_fused_epilogue(cv, shape):
     assert cv.spade_supported(x.to(DEV), feat.to(DEV), wg.to(DEV), wb.to(DEV))
     y = cv.spade_conv_norm(x.to(DEV), feat.to(DEV), wg.to(DEV), wb.to(DEV), act='relu', gain=1.3)
     assert rel_err(y, ref) < 3e-3
+
+
+DOWN2 = [(1, 16, 16, 8, 8), (2, 64, 128, 32, 32), (1, 128, 256, 64, 64), (2, 32, 48, 12, 20), (1, 64, 64, 256, 256)]
+
+
+@pytest.mark.parametrize('shape', DOWN2, ids=[str(s) for s in DOWN2])
+def test_down2_space_to_depth(cv, shape):
+    """conv2d_resample(down=2, k=3, padding=1) == FIR(pad 2) + 3x3 stride-2 conv, evaluated as one 'same' conv over the s2d planes of x."""
+    n, cin, cout, h, w = shape
+    torch.manual_seed(sum(shape))
+    f = O.setup_filter([1, 3, 3, 1])
+    x = torch.randn(n, cin, h, w)
+    wt = torch.randn(cout, cin, 3, 3) / (cin * 9) ** 0.5
+    b = torch.randn(cout) * 0.1
+    for flip_weight in (True, False):
+        ref = O.conv2d_resample(x.double(), wt.double(), f=f.double(), down=2, padding=1, flip_weight=flip_weight)
+        y = cv.conv2d_igemm(x.to(DEV), wt.to(DEV), f=f.to(DEV), down=2, flip_weight=flip_weight)
+        assert y.shape == ref.shape
+        assert rel_err(y, ref) < 3e-3, (shape, flip_weight)
+    y2 = cv.conv2d_igemm(x.to(DEV), wt.to(DEV), f=f.to(DEV), down=2, bias=b.to(DEV), act='lrelu', gain=2 ** 0.5, clamp=256)
+    ref2 = O.bias_act(O.conv2d_resample(x.double(), wt.double(), f=f.double(), down=2, padding=1), b.double(), act='lrelu', clamp=256)
+    assert rel_err(y2, ref2) < 3e-3
