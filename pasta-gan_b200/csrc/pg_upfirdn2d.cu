@@ -44,7 +44,7 @@ struct UpfirdnParams {
     int upx, upy, downx, downy, padx0, pady0, flip; float gain;
     Epilogue epi;
     // band kernel only
-    int band_rows, bands_per_plane, tile_rows, pitch;
+    int band_rows, bands_per_plane, tile_rows, pitch, rows_per_group;
 };
 
 // floor division / modulo for possibly negative numerators
@@ -89,6 +89,21 @@ __global__ void __launch_bounds__(256) upfirdn2d_generic_kernel(UpfirdnParams p)
     }
 }
 
+// epilogue + store of 4 adjacent outputs of one row
+template <class T, bool EPI>
+__device__ __forceinline__ void store_quad(const UpfirdnParams& p, T* dst, float (&out)[4], int x0, float bias, bool vec_store) {
+    if (EPI) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) out[c] = apply_epilogue<float>(p.epi, out[c], bias);
+    }
+    if (vec_store) {
+        *reinterpret_cast<float4*>(dst) = make_float4(out[0], out[1], out[2], out[3]);
+    } else {
+#pragma unroll
+        for (int c = 0; c < 4; c++) if (x0 + c < p.outW) dst[c] = from_acc<T, float>(out[c]);
+    }
+}
+
 // ------------------------------------------------------------------------------------ band (4x4, up=1)
 // grid.x = plane * bands_per_plane + band; 256 threads; dynamic smem = tile_rows * pitch floats.
 template <class T, int D, bool EPI>
@@ -113,65 +128,134 @@ __global__ void __launch_bounds__(256) upfirdn2d_band_kernel(UpfirdnParams p) {
         for (int j = 0; j < F; j++)
             k[i][j] = __ldg(p.f + (p.flip ? i : F - 1 - i) * p.fsh + (p.flip ? j : F - 1 - j) * p.fsw) * p.gain;
 
-    // stage: tile[r][c] = x[iy0 + r][c - padx0], zero outside the image
+    // stage: tile[r][c] = x[iy0 + r][c - padx0], zero outside the image.  One warp per row, 9 independent coalesced loads in flight per
+    // thread (288 columns) before any shared-memory store: with 4 resident CTAs that is ~36 KB of reads in flight per SM.
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int KC = 9;
     for (int r = warp; r < need; r += 8) {
         const int iy = iy0 + r;
         const bool row_ok = (iy >= 0) && (iy < p.inH);
         const T* src = xp + (ptrdiff_t)iy * p.inW - p.padx0;
         float* dst = tile + r * p.pitch;
-#pragma unroll 4
-        for (int c = lane; c < p.pitch; c += 32) {
-            const int ix = c - p.padx0;
-            float v = 0.f;
-            if (row_ok && ix >= 0 && ix < p.inW) v = (float)to_acc<T>(__ldg(src + c));
-            dst[c] = v;
+        for (int cb = 0; cb < p.pitch; cb += 32 * KC) {
+            float v[KC];
+#pragma unroll
+            for (int kk = 0; kk < KC; kk++) {
+                const int c = cb + lane + 32 * kk;
+                const int ix = c - p.padx0;
+                v[kk] = (row_ok && c < p.pitch && ix >= 0 && ix < p.inW) ? (float)to_acc<T>(__ldg(src + c)) : 0.f;
+            }
+#pragma unroll
+            for (int kk = 0; kk < KC; kk++) {
+                const int c = cb + lane + 32 * kk;
+                if (c < p.pitch) dst[c] = v[kk];
+            }
         }
     }
     __syncthreads();
 
-    // compute: work item = (row group g, column ox); each item slides a window down `rpg` rows
-    constexpr int RPG = 8;                                     // rows per group
-    const int groups = (rows + RPG - 1) / RPG;
-    const int items = groups * p.outW;
+    // compute: work item = (row group, quad of 4 adjacent output columns).  Rows are read from the tile as aligned float4 (the pitch is a
+    // multiple of 4 and output quad x0 starts at tile column x0 * D), horizontally filtered once per input row, and the four most recent
+    // filtered rows are kept in a register ring for the vertical pass: 8 FMAs and < 1 shared-memory load per output when the filter is an
+    // outer product (it always is for PASTA-GAN's [1,3,3,1]); a general 4x4 filter takes the 16-FMA path over the raw rows.
+    constexpr int NV4 = (3 * D + 4 + 3) / 4;                   // float4 loads per tile row per item: 2 (D = 1) or 3 (D = 2)
+    const int quads = (p.outW + 3) >> 2;
+    const int rpg = p.rows_per_group;
+    const int groups = (rows + rpg - 1) / rpg;
+    const int items = groups * quads;
     const int c_ch = plane % p.C;
     float bias = 0.f;
     if (EPI && p.epi.b) bias = (float)to_acc<T>(__ldg((const T*)p.epi.b + c_ch));
     T* yp = y + (size_t)plane * p.outH * p.outW;
+    const bool vec_store = sizeof(T) == 4 && (p.outW & 3) == 0 && ((((size_t)p.outH * p.outW) & 3) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+
+    // rank-1 test: k[i][j] == ky[i] * kx[j] with kx = k[0][:], ky = k[:][0] / k[0][0]
+    float kx[F], ky[F];
+    bool separable = k[0][0] != 0.f;
+    {
+        float kmax = 0.f;
+#pragma unroll
+        for (int i = 0; i < F; i++)
+#pragma unroll
+            for (int j = 0; j < F; j++) kmax = fmaxf(kmax, fabsf(k[i][j]));
+#pragma unroll
+        for (int i = 0; i < F; i++) { kx[i] = k[0][i]; ky[i] = separable ? k[i][0] / k[0][0] : 0.f; }
+#pragma unroll
+        for (int i = 0; i < F; i++)
+#pragma unroll
+            for (int j = 0; j < F; j++) separable = separable && fabsf(k[i][j] - ky[i] * kx[j]) <= 1e-6f * kmax;
+    }
+
     for (int item = threadIdx.x; item < items; item += 256) {
-        const int g = item / p.outW;
-        const int ox = item - g * p.outW;
-        const int r0 = g * RPG;
-        const int nr = min(RPG, rows - r0);
-        const float* col = tile + (r0 * D) * p.pitch + ox * D;
-        float w[F][F];                                         // register window: rows x taps
+        const int g = item / quads;
+        const int x0 = (item - g * quads) << 2;
+        const int r0 = g * rpg;
+        const int nr = min(rpg, rows - r0);
+        const float* rowp = tile + (r0 * D) * p.pitch + x0 * D;
+        float out[4];
+        if (separable) {
+            float h[F][4];                                     // ring of horizontally filtered rows
+            auto hfilter = [&](const float* rp, float (&hr)[4]) {
+                float v[NV4 * 4];
 #pragma unroll
-        for (int i = 0; i < F - D; i++)
+                for (int q = 0; q < NV4; q++) {
+                    const float4 t = reinterpret_cast<const float4*>(rp)[q];
+                    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+                }
 #pragma unroll
-            for (int j = 0; j < F; j++) w[i + D][j] = col[i * p.pitch + j];
-        col += (F - D) * p.pitch;
-        for (int r = 0; r < nr; r++) {
-            // shift the window up by D rows and load D new rows
+                for (int c = 0; c < 4; c++) {
+                    float a = kx[0] * v[c * D];
 #pragma unroll
-            for (int i = 0; i < F - D; i++)
+                    for (int j = 1; j < F; j++) a = fmaf(kx[j], v[c * D + j], a);
+                    hr[c] = a;
+                }
+            };
 #pragma unroll
-                for (int j = 0; j < F; j++) w[i][j] = w[i + D][j];
+            for (int i = 0; i < F - D; i++) hfilter(rowp + i * p.pitch, h[i + D]);
+            rowp += (F - D) * p.pitch;
+            for (int r = 0; r < nr; r++) {
 #pragma unroll
-            for (int i = F - D; i < F; i++)
+                for (int i = 0; i < F - D; i++)
 #pragma unroll
-                for (int j = 0; j < F; j++) w[i][j] = col[(i - (F - D)) * p.pitch + j];
-            col += D * p.pitch;
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                    for (int c = 0; c < 4; c++) h[i][c] = h[i + D][c];
 #pragma unroll
-            for (int j = 0; j < F; j++) {
-                a0 = fmaf(k[0][j], w[0][j], a0);
-                a1 = fmaf(k[1][j], w[1][j], a1);
-                a2 = fmaf(k[2][j], w[2][j], a2);
-                a3 = fmaf(k[3][j], w[3][j], a3);
+                for (int i = F - D; i < F; i++) hfilter(rowp + (i - (F - D)) * p.pitch, h[i]);
+                rowp += D * p.pitch;
+#pragma unroll
+                for (int c = 0; c < 4; c++) out[c] = fmaf(ky[3], h[3][c], fmaf(ky[2], h[2][c], fmaf(ky[1], h[1][c], ky[0] * h[0][c])));
+                store_quad<T, EPI>(p, yp + (size_t)(oy0 + r0 + r) * p.outW + x0, out, x0, bias, vec_store);
             }
-            float acc = (a0 + a1) + (a2 + a3);
-            if (EPI) acc = apply_epilogue<float>(p.epi, acc, bias);
-            yp[(size_t)(oy0 + r0 + r) * p.outW + ox] = from_acc<T, float>(acc);
+        } else {
+            float w[F][NV4 * 4];                               // raw rows
+            auto load = [&](const float* rp, float (&wr)[NV4 * 4]) {
+#pragma unroll
+                for (int q = 0; q < NV4; q++) {
+                    const float4 t = reinterpret_cast<const float4*>(rp)[q];
+                    wr[4 * q] = t.x; wr[4 * q + 1] = t.y; wr[4 * q + 2] = t.z; wr[4 * q + 3] = t.w;
+                }
+            };
+#pragma unroll
+            for (int i = 0; i < F - D; i++) load(rowp + i * p.pitch, w[i + D]);
+            rowp += (F - D) * p.pitch;
+            for (int r = 0; r < nr; r++) {
+#pragma unroll
+                for (int i = 0; i < F - D; i++)
+#pragma unroll
+                    for (int c = 0; c < NV4 * 4; c++) w[i][c] = w[i + D][c];
+#pragma unroll
+                for (int i = F - D; i < F; i++) load(rowp + (i - (F - D)) * p.pitch, w[i]);
+                rowp += D * p.pitch;
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    float a = 0.f;
+#pragma unroll
+                    for (int i = 0; i < F; i++)
+#pragma unroll
+                        for (int j = 0; j < F; j++) a = fmaf(k[i][j], w[i][c * D + j], a);
+                    out[c] = a;
+                }
+                store_quad<T, EPI>(p, yp + (size_t)(oy0 + r0 + r) * p.outW + x0, out, x0, bias, vec_store);
+            }
         }
     }
 }
@@ -185,12 +269,17 @@ template <class T, bool EPI>
 static int launch_upfirdn2d(UpfirdnParams p, bool band_ok, cudaStream_t stream) {
     if (band_ok) {
         const int D = p.downx;
-        // band height: keep the staged tile <= ~40 KB so >= 5 CTAs fit per SM
-        int band_rows = (D == 1) ? 16 : 8;
+        // band height: as tall as a ~40 KB tile allows (taller bands re-read fewer halo rows), at most 32 rows
+        int band_rows = 32;
         while (band_rows > 8 && (size_t)((band_rows - 1) * D + 4) * p.pitch * sizeof(float) > 40 * 1024) band_rows /= 2;
+        if (band_rows > p.outH) band_rows = p.outH;
         p.band_rows = band_rows;
         p.bands_per_plane = (p.outH + band_rows - 1) / band_rows;
         p.tile_rows = (band_rows - 1) * D + 4;
+        // rows per work item: aim for >= 256 items per CTA (one per thread) but at least 2 rows to amortise the window priming
+        const int quads = (p.outW + 3) / 4;
+        int rpg = band_rows * quads / 256;
+        p.rows_per_group = rpg < 2 ? 2 : (rpg > 8 ? 8 : rpg);
         const size_t smem = (size_t)p.tile_rows * p.pitch * sizeof(float);
         const int64_t blocks = (int64_t)p.N * p.C * p.bands_per_plane;
         if (smem <= 96 * 1024 && blocks <= INT32_MAX) {
@@ -243,9 +332,10 @@ static int upfirdn2d_entry(const void* x, const float* f, void* y,
     p.fh = fh; p.fw = fw; p.fsh = fsh; p.fsw = fsw;
     p.upx = upx; p.upy = upy; p.downx = downx; p.downy = downy; p.padx0 = padx0; p.pady0 = pady0; p.flip = flip ? 1 : 0; p.gain = gain;
     p.epi = epi;
-    p.band_rows = p.bands_per_plane = p.tile_rows = 0;
+    p.band_rows = p.bands_per_plane = p.tile_rows = p.rows_per_group = 0;
     // columns the band tile must hold: taps of the last output column reach (outW-1)*D + 3
-    p.pitch = ((outW - 1) * downx + 4) | 1;                     // odd pitch keeps row-to-row bank offsets distinct
+    // tile columns: the last quad of outputs starts at 4*(ceil(outW/4)-1)*D and reads 4*NV4 floats; multiple of 4 for aligned float4 reads
+    p.pitch = 4 * ((outW + 3) / 4 - 1) * downx + (downx == 1 ? 8 : 12);
 
     const bool band_ok = dtype != PG_F64 && fh == 4 && fw == 4 && upx == 1 && upy == 1 && downx == downy && (downx == 1 || downx == 2) &&
                          padx0 >= 0 && pady0 >= 0 && outW >= 32 &&
