@@ -188,6 +188,25 @@ def run_reference(args, world, rank):
 
 # ------------------------------------------------------------------------------------------------ B200 arm
 
+def ncu_traffic(kernel):
+    """dram__bytes_read + dram__bytes_write of one `ncu --set full` launch of this kernel family (profiles/r1_kernels_ncu_full.csv, captured
+    with tools/prof_ops.py at the kernel's largest generator shape); None if the capture is not in the tree."""
+    import csv
+    match = {'conv_igemm': 'conv_igemm_kernel', 'bias_act': 'bias_act_vec_kernel', 'upfirdn2d': 'upfirdn2d_band_kernel<float, 1, 0>',
+             'upfirdn2d_bias_act': 'upfirdn2d_band_kernel<float, 1, 1>', 'torgb_skip': 'torgb_skip_kernel'}.get(kernel)
+    shape = {'conv_igemm': '3x3 256->128 @128^2, N=16 (algorithmic 403 MB)', 'bias_act': '[16,64,256,256] lrelu (algorithmic 537 MB)',
+             'upfirdn2d': '[16,64,257,257]->256^2 (algorithmic 539 MB)', 'upfirdn2d_bias_act': '[16,64,257,257]->256^2 (algorithmic 539 MB)',
+             'torgb_skip': '[16,64,256,256]->3 ch (algorithmic 284 MB)'}.get(kernel)
+    try:
+        for r in csv.DictReader(open(os.path.join(ROOT, 'profiles', 'r1_kernels_ncu_full.csv'))):
+            if match and match in r['Kernel Name']:
+                tot = (float(r['dram__bytes_read.sum [Mbyte]']) + float(r['dram__bytes_write.sum [Mbyte]'])) * 1e6
+                return dict(traffic=tot, traffic_note=f'ncu --set full, one launch, {shape}; writes still resident in L2 at kernel end are not counted by ncu')
+    except Exception:
+        pass
+    return dict(traffic=None)
+
+
 def roofline_from(profile, pk):
     """Dominant hand-written kernel of one instrumented step -> the roofline object."""
     mine = {k: v for k, v in profile.items() if not k.startswith('library')}
@@ -199,11 +218,11 @@ def roofline_from(profile, pk):
     if name.startswith('conv_igemm'):
         ach = a['flops'] / a['launches'] / sec / 1e12
         roof = dict(kernel=name, bound='tensor', achieved=ach, peak=pk['tf_sustained'], unit='TFLOP/s', frac=ach / pk['tf_sustained'],
-                    traffic=None, peak_source=pk['src'] + ' (sustained bf16)')
+                    peak_source=pk['src'] + ' (sustained bf16: the kernel is timed inside a long step)')
     else:
         ach = a['bytes'] / a['launches'] / sec / 1e9
-        roof = dict(kernel=name, bound='hbm', achieved=ach, peak=pk['hbm'], unit='GB/s', frac=ach / pk['hbm'], traffic=None,
-                    peak_source=pk['src'])
+        roof = dict(kernel=name, bound='hbm', achieved=ach, peak=pk['hbm'], unit='GB/s', frac=ach / pk['hbm'], peak_source=pk['src'])
+    roof.update(ncu_traffic(name))
     roof['launches_per_step'] = a['launches']
     roof['avg_launch_us'] = sec * 1e6
     roof['measured'] = 'CUDA events around each launch, one instrumented eager step after the timed region'
@@ -248,6 +267,7 @@ def run_b200(args, world, rank, local):
             e0.record()
         for _ in range(args.steps):
             fn()
+        sess.join_streams()                                      # copies on the side streams are inside the timed region
         with torch.cuda.stream(sess.stream):
             e1.record()
         sess.synchronize()
@@ -283,7 +303,7 @@ def run_b200(args, world, rank, local):
         'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': wl,
                    'batch_per_gpu': args.batch, 'global_batch': world * args.batch, 'parallelism': f'replicas x{world} (batch-sharded, no collective)',
-                   'cuda_graph': not args.no_graph,
+                   'cuda_graph': not args.no_graph, 'e2e_pipeline': 'H2D / compute / D2H on three streams, 2 buffer sets',
                    'l2': f'no explicit flush: one step streams ~{act_bytes / 1e9:.1f} GB of activations through the operators (> 126 MB L2)',
                    'weights': 'procedural (name-keyed, tests/golden/procedural.py)', 'noise_mode': 'const'},
         'e2e': {'value': imgs / t_e2e, 'unit': UNIT, 'ms_per_step': 1e3 * t_e2e / args.steps,

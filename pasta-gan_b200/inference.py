@@ -10,27 +10,56 @@ INPUT_KEYS = ('c', 'retain', 'pose', 'denorm_upper_input', 'denorm_lower_input',
 
 
 class TryOnSession:
-    def __init__(self, generator, example_inputs, device, use_graph=True, warmup=3):
+    """``depth`` static input/output buffer sets (default 2), each with its own captured graph: ``step_from_host`` copies batch i+1 to the
+    device on a copy stream while batch i computes and batch i-1's images travel back on a third stream, so the end-to-end rate is
+    max(compute, PCIe) instead of their sum."""
+
+    def __init__(self, generator, example_inputs, device, use_graph=True, warmup=3, depth=2):
         self.G = generator.to(device).eval().requires_grad_(False)
         self.device = torch.device(device)
         self.batch = int(example_inputs['retain'].shape[0])
         self.keys = tuple(k for k in example_inputs if k != 'z')      # GeneratorFull: INPUT_KEYS; Generator512: c, retain, pose
-        self.static_in = {k: torch.empty_like(example_inputs[k], device=self.device) for k in self.keys}
-        self.static_in['z'] = torch.zeros(self.batch, self.G.z_dim, device=self.device)
+        self.depth = max(1, int(depth))
+        self.slots_in = []
+        for _ in range(self.depth):
+            d = {k: torch.empty_like(example_inputs[k], device=self.device) for k in self.keys}
+            d['z'] = torch.zeros(self.batch, self.G.z_dim, device=self.device)
+            self.slots_in.append(d)
+        self.static_in = self.slots_in[0]
         self.host_in = {k: torch.empty_like(example_inputs[k], device='cpu').pin_memory() for k in self.keys}
-        self.graph = None
-        self.out = None
-        self.stream = torch.cuda.Stream(self.device)
-        self.load(example_inputs)
+        self.stream = torch.cuda.Stream(self.device)               # compute
+        self.h2d_stream = torch.cuda.Stream(self.device)
+        self.d2h_stream = torch.cuda.Stream(self.device)
+        with torch.cuda.stream(self.stream):
+            for d in self.slots_in:
+                for k in self.keys:
+                    d[k].copy_(example_inputs[k], non_blocking=True)
         with torch.cuda.stream(self.stream), torch.no_grad():
             for _ in range(warmup):
                 self.out = self._forward()
         self.stream.synchronize()
-        if use_graph:
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.no_grad(), torch.cuda.graph(self.graph, stream=self.stream):
-                self.out = self._forward()
-        self.host_out = [torch.empty_like(o, device='cpu').pin_memory() for o in self.out[:2]]      # the image(s); parsing logits stay on device
+        self.graphs, self.slots_out = [], []
+        for i in range(self.depth):
+            self.static_in = self.slots_in[i]
+            if use_graph:
+                g = torch.cuda.CUDAGraph()
+                with torch.no_grad(), torch.cuda.graph(g, stream=self.stream):
+                    out = self._forward()
+                self.graphs.append(g)
+            else:
+                with torch.cuda.stream(self.stream), torch.no_grad():
+                    out = self._forward()
+                self.graphs.append(None)
+            self.slots_out.append(out)
+        self.static_in = self.slots_in[0]
+        self.graph = self.graphs[0]
+        self.out = self.slots_out[0]
+        self.host_outs = [[torch.empty_like(o, device='cpu').pin_memory() for o in out[:2]] for out in self.slots_out]
+        self.host_out = self.host_outs[0]                          # the image(s); parsing logits stay on device
+        self.ev_h2d = [torch.cuda.Event() for _ in range(self.depth)]
+        self.ev_comp = [torch.cuda.Event() for _ in range(self.depth)]
+        self.ev_d2h = [torch.cuda.Event() for _ in range(self.depth)]
+        self._turn = 0
         self.h2d_bytes = sum(self.host_in[k].numel() * self.host_in[k].element_size() for k in self.keys)
         self.d2h_bytes = sum(o.numel() * o.element_size() for o in self.host_out)
 
@@ -54,17 +83,42 @@ class TryOnSession:
         return self.out
 
     def step_from_host(self, host_inputs=None):
-        """End-to-end step: pinned host batch -> device, forward, images -> pinned host.  Asynchronous on the session stream;
-        call ``synchronize()`` before reading ``host_out``."""
+        """End-to-end step: pinned host batch -> device (copy stream), forward (compute stream), images -> pinned host (third stream).
+        Fully asynchronous and software-pipelined over ``depth`` buffer sets; returns the pinned output tensors of THIS step, valid after
+        ``synchronize()`` (or after ``depth`` further calls have been synchronised)."""
         src = self.host_in if host_inputs is None else host_inputs
-        with torch.cuda.stream(self.stream):
+        b = self._turn % self.depth
+        self._turn += 1
+        ins, outs, hosts = self.slots_in[b], self.slots_out[b], self.host_outs[b]
+        with torch.cuda.stream(self.h2d_stream):
+            self.h2d_stream.wait_event(self.ev_comp[b])            # the forward that last read this input slot has finished
             for k in self.keys:
-                self.static_in[k].copy_(src[k], non_blocking=True)
-        out = self.step()
-        with torch.cuda.stream(self.stream):
-            for h, o in zip(self.host_out, out[:2]):
+                ins[k].copy_(src[k], non_blocking=True)
+            self.ev_h2d[b].record(self.h2d_stream)
+        with torch.cuda.stream(self.stream), torch.no_grad():
+            self.stream.wait_event(self.ev_h2d[b])
+            self.stream.wait_event(self.ev_d2h[b])                 # the previous images of this slot have left the device
+            if self.graphs[b] is not None:
+                self.graphs[b].replay()
+            else:
+                self.static_in = ins
+                outs = self._forward()
+            self.ev_comp[b].record(self.stream)
+        with torch.cuda.stream(self.d2h_stream):
+            self.d2h_stream.wait_event(self.ev_comp[b])
+            for h, o in zip(hosts, outs[:2]):
                 h.copy_(o, non_blocking=True)
-        return self.host_out
+            self.ev_d2h[b].record(self.d2h_stream)
+        self.host_out = hosts
+        return hosts
+
+    def join_streams(self):
+        """Make the compute stream wait for every outstanding copy, so an event recorded on it afterwards closes the whole pipeline."""
+        for b in range(self.depth):
+            self.stream.wait_event(self.ev_h2d[b])
+            self.stream.wait_event(self.ev_d2h[b])
 
     def synchronize(self):
         self.stream.synchronize()
+        self.h2d_stream.synchronize()
+        self.d2h_stream.synchronize()

@@ -1,0 +1,26 @@
+#!/usr/bin/env python
+"""Driver for `ncu --set full`: two launches each of the hand-written kernels at their largest generator shapes (batch 16)."""
+import os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pasta_gan_b200.torch_utils.ops import upfirdn2d, bias_act, conv_igemm, torgb
+dev = torch.device('cuda:0')
+f = upfirdn2d.setup_filter([1, 3, 3, 1]).to(dev)
+with torch.no_grad():
+    x = torch.randn(16, 64, 256, 256, device=dev); b = torch.randn(64, device=dev)
+    x257 = torch.randn(16, 64, 257, 257, device=dev)
+    for _ in range(2):
+        bias_act.bias_act(x, b, act='lrelu', clamp=256)                                             # bias_act_vec_kernel
+        upfirdn2d.upfirdn2d(x257, f, padding=[1, 1, 1, 1], gain=4)                                  # upfirdn2d_band_kernel<1,0>
+        upfirdn2d.upfirdn2d_bias_act(x257, f, b, padding=[1, 1, 1, 1], gain=4, act='lrelu', clamp=256)   # <1,1> fused epilogue
+        upfirdn2d.downsample2d(x, f)                                                                # <2,0>
+    w3 = torch.randn(3, 64, 1, 1, device=dev); s = torch.randn(16, 64, device=dev) / 8; img = torch.randn(16, 3, 128, 128, device=dev)
+    for _ in range(2):
+        torgb.torgb_skip(x, w3, styles=s, bias=torch.zeros(3, device=dev), clamp=256, img=img, f=f)  # torgb_skip_kernel<3>
+    xa = torch.randn(16, 256, 128, 128, device=dev); wa = torch.randn(128, 256, 3, 3, device=dev) / 48
+    xb = torch.randn(16, 128, 128, 128, device=dev); wb = torch.randn(128, 128, 3, 3, device=dev) / 34
+    for _ in range(2):
+        conv_igemm.conv2d_igemm(xa, wa, bias=torch.zeros(128, device=dev), act='lrelu', gain=2 ** 0.5, clamp=256)   # 256->128 @128^2
+        conv_igemm.conv2d_igemm(xb, wb)                                                                            # 128->128 @128^2
+torch.cuda.synchronize()
+print('ok')
