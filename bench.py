@@ -250,10 +250,7 @@ def run_b200(args, world, rank, local):
         inp = procedural.synth_inputs(args.batch, seed=1234 + 100 * rank, device=dev)
         wl = 'GeneratorFull 256x192 (256x256 padded) full-body try-on inference, batch 16 per GPU (BASELINE configs[1])'
     procedural.fill_(G)
-    l0 = capi.launch_count()
     sess = TryOnSession(G, inp, dev, use_graph=not args.no_graph, warmup=max(3, args.warmup))
-    # launches of our kernels in ONE forward (eager count: warm-up forwards + the captured one all issue the same sequence)
-    per_fwd = (capi.launch_count() - l0) // (max(3, args.warmup) + (0 if args.no_graph else 1))
     sess.synchronize()
 
     def timed(fn):
@@ -284,7 +281,9 @@ def run_b200(args, world, rank, local):
 
     # one instrumented eager step (per-launch CUDA events) for the roofline of the dominant hand-written kernel
     with torch.cuda.stream(sess.stream), torch.no_grad():
+        l0 = capi.launch_count()
         sess.G(**sess.static_in, noise_mode='const')            # eager warm-up on the session stream (allocator pools, cuDNN plans)
+        per_fwd = capi.launch_count() - l0                      # launches of OUR kernels in one forward (what each graph replay re-issues)
         with capi.LaunchProfiler() as prof:
             sess.G(**sess.static_in, noise_mode='const')
     roof, profile = roofline_from(prof.summary(), pk)

@@ -41,7 +41,7 @@ struct ConvParams {
     long long noise_bstride;
     int N, Cin, Cout, H, W, ks;
     int PW, Lp, tiles_per_img, NACC, BN, nchunks, ntaps, PA;      // PA: staged strip positions (multiple of 32)
-    int SA, SB, tps; uint32_t a_stage_bytes, b_slot_bytes, b_tile_bytes;   // B ring: SB slots of `tps` taps each
+    int SA, SB, tps, cgroups; uint32_t a_stage_bytes, b_slot_bytes, b_tile_bytes;   // B ring: SB slots of `tps` taps each
     int in_act; float in_alpha, in_gain; int act; float alpha, gain, clamp; int fmt;
     uint32_t idesc; uint32_t tmem_cols;
     // up-2 polyphase mode: BN virtual channels = phases x couts (see launch code); 0 = plain
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
     if (warp == 0 && lane == 0) {
-        for (int i = 0; i < p.SA; i++) { mbar_init(smem_u32(&a_full[i]), kConvWarps); mbar_init(smem_u32(&a_empty[i]), 1); }
+        for (int i = 0; i < p.SA; i++) { mbar_init(smem_u32(&a_full[i]), kConvWarps / p.cgroups); mbar_init(smem_u32(&a_empty[i]), 1); }
         for (int i = 0; i < p.SB; i++) { mbar_init(smem_u32(&b_full[i]), 1); mbar_init(smem_u32(&b_empty[i]), 1); }
         mbar_init(smem_u32(acc_full), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -326,16 +326,21 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
         const float* xn = p.down2 ? p.x + (size_t)n * p.cin_real * p.hin * p.win : p.x + (size_t)n * p.Cin * HW;
         const bool has_in_act = p.in_act != PG_ACT_LINEAR;
         const float in_slope = (p.in_act == PG_ACT_RELU) ? 0.f : p.in_alpha;
-        int st = 0; uint32_t ph = 0;
-        for (int ci = 0; ci < p.nchunks; ci++) {
+        // Converter warps are split into `cgroups` groups that take alternate chunks, so that small tiles (a handful of tasks per chunk,
+        // i.e. one memory round trip per chunk) keep several chunks in flight instead of serialising on the L2/HBM latency.
+        const int wpg = kConvWarps / p.cgroups;                  // warps per group
+        const int grp = cw / wpg, gw = cw - grp * wpg;           // this warp's group and rank inside it
+        for (int ci = grp; ci < p.nchunks; ci += p.cgroups) {
+            const int st = ci % p.SA;
+            const uint32_t ph = (uint32_t)(ci / p.SA) & 1u;
             mbar_wait(smem_u32(&a_empty[st]), ph ^ 1);
             uint8_t* stage = a_base + (size_t)st * p.a_stage_bytes;
-            for (int t = cw; t < ntasks; t += kTaskBatch * kConvWarps) {
+            for (int t = gw; t < ntasks; t += kTaskBatch * wpg) {
                 // a whole batch of tasks is loaded before any is converted: 8 * kTaskBatch independent L2/HBM loads in flight per thread
                 float v[kTaskBatch][8];
 #pragma unroll
                 for (int u = 0; u < kTaskBatch; u++) {
-                    const int tt = t + u * kConvWarps;
+                    const int tt = t + u * wpg;
                     const int q = m0 - halo + (tt >> 1) * 32 + lane;          // strip position of this staged row
                     int h = 0, w = 0;
                     bool ok = tt < ntasks && q >= 0 && q < p.Lp;
@@ -362,7 +367,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
                 }
 #pragma unroll
                 for (int u = 0; u < kTaskBatch; u++) {
-                    const int tt = t + u * kConvWarps;
+                    const int tt = t + u * wpg;
                     if (tt >= ntasks) break;
                     const int plane = tt & 1, spos = (tt >> 1) * 32 + lane;
                     if (SCALE) {
@@ -383,7 +388,6 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
             fence_proxy_async();                               // generic-proxy stores -> visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&a_full[st]));
-            if (++st == p.SA) { st = 0; ph ^= 1; }
         }
         if (cw == 0 && lane == 0) PG_TS(6);
         // ===================== epilogue (same warps) =====================
@@ -484,7 +488,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
 
 // ---------------------------------------------------------------------------------------------- host side
 struct ConvPlan {
-    int BN, ntiles_n, nchunks, ntaps, NACC, PW, Lp, tiles_per_img, PA, SA, SB, tps;
+    int BN, ntiles_n, nchunks, ntaps, NACC, PW, Lp, tiles_per_img, PA, SA, SB, tps, cgroups;
     uint32_t a_stage, b_stage, b_slot, b_tile; size_t smem; uint32_t tmem_cols; int nvirt;
 };
 
@@ -524,6 +528,9 @@ static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int k
     pl.tps = (ks == 3) ? 3 : 1;
     pl.b_slot = pl.b_tile * pl.tps;
     size_t budget = pair ? 100 * 1024 : 200 * 1024;
+    // converter warp groups over alternate chunks (cgroups > 1) were measured to give nothing: small-spatial / wide-channel layers are bound by
+    // streaming the weight slab from L2 once per 128-position tile, not by the activation round trip.  Kept at 1; the code path stays.
+    pl.cgroups = 1;
     pl.SA = 3;
     if ((size_t)pl.SA * pl.a_stage > budget / 2) pl.SA = 2;
     if ((size_t)pl.SA * pl.a_stage + 2 * (size_t)pl.b_slot + fixed + 128 > budget) budget = 200 * 1024;   // large strips: one CTA per SM after all
@@ -615,7 +622,7 @@ static int conv_run_impl(const float* x, const void* wpack, const float* styles,
     p.noise_bstride = noise_batch_stride;
     p.N = N; p.Cin = Cin; p.Cout = pl.nvirt; p.H = H; p.W = W; p.ks = ksize;
     p.PW = pl.PW; p.Lp = pl.Lp; p.tiles_per_img = pl.tiles_per_img; p.NACC = pl.NACC; p.BN = pl.BN; p.nchunks = pl.nchunks; p.ntaps = pl.ntaps;
-    p.PA = pl.PA; p.SA = pl.SA; p.SB = pl.SB; p.tps = pl.tps; p.a_stage_bytes = pl.a_stage; p.b_slot_bytes = pl.b_slot; p.b_tile_bytes = pl.b_tile;
+    p.PA = pl.PA; p.SA = pl.SA; p.SB = pl.SB; p.tps = pl.tps; p.cgroups = pl.cgroups; p.a_stage_bytes = pl.a_stage; p.b_slot_bytes = pl.b_slot; p.b_tile_bytes = pl.b_tile;
     p.in_act = in_act; p.in_alpha = in_alpha; p.in_gain = in_gain; p.act = act; p.alpha = alpha; p.gain = gain; p.clamp = clamp; p.fmt = operand_format;
     p.idesc = (1u << 4) | ((uint32_t)operand_format << 7) | ((uint32_t)operand_format << 10) | ((uint32_t)(pl.BN >> 3) << 17) | (8u << 24);
     p.tmem_cols = pl.tmem_cols;

@@ -106,7 +106,8 @@ def conv2d_igemm(x, w, f=None, up=1, down=1, flip_weight=True, styles=None, dcoe
     with torch.cuda.device(x.device):
         capi.require_device()
         wpack = _packed_weights(capi, w, f, w_scale, mode, flip_weight, fmt_code, cache_weights)
-        sp = capi.span('conv_igemm', flops=2 * n * cout * cin * k * k * h * wd * (4 if mode != 1 and down != 2 else 1),
+        # algorithmic FLOPs: output pixels for stride-1 / down-2, INPUT pixels for up-2 (zero-inserted taps excluded)
+        sp = capi.span('conv_igemm', flops=2 * n * cout * cin * k * k * (oh * ow if up == 1 else h * wd),
                        nbytes=4 * (x.numel() + y.numel() + w.numel()))
         rc = capi.load().pg_conv2d_igemm_run(capi.ptr(x), capi.ptr(wpack), capi.ptr(styles), capi.ptr(dcoefs),
                                              capi.ptr(noise), nb_stride, capi.ptr(bias), capi.ptr(y),
