@@ -295,3 +295,35 @@ def test_conv2d_gradfix_double_backward_and_no_weight_gradients(ops):
         assert rel_err(ytg, ytr) < 1e-10
     finally:
         torch.backends.cudnn.allow_tf32, ops.cg.enabled = old_tf32, old_en
+
+
+# ----------------------------------------------------------------------------- edge cases
+def test_empty_and_degenerate_inputs(ops):
+    """Empty batches, 1x1 planes, single-channel tensors and the INT32_MAX guard behave like the reference launchers (no crash, right shapes)."""
+    f = O.setup_filter([1, 3, 3, 1]).to(DEV)
+    e = ops.up.upfirdn2d(torch.empty(0, 3, 8, 8, device=DEV), f, padding=[2, 1, 2, 1], up=2)
+    assert e.shape == (0, 3, 16, 16)
+    one = torch.randn(1, 1, 1, 1, device=DEV)
+    assert rel_err(ops.up.upfirdn2d(one, f, up=2, padding=[2, 1, 2, 1], gain=4), O.upfirdn2d(one.cpu(), f.cpu(), up=2, padding=[2, 1, 2, 1], gain=4)) < TOL
+    assert rel_err(ops.ba.bias_act(one, torch.ones(1, device=DEV), act='tanh'), O.bias_act(one.cpu(), torch.ones(1), act='tanh')) < TOL
+    x = torch.randn(2, 1, 37, 41, device=DEV)                       # single channel, odd sizes: band kernel with ragged quads
+    assert rel_err(ops.up.upfirdn2d(x, f, padding=[2, 2, 2, 2]), O.upfirdn2d(x.cpu(), f.cpu(), padding=[2, 2, 2, 2])) < TOL
+    assert rel_err(ops.up.downsample2d(x[:, :, :36, :40].contiguous(), f), O.downsample2d(x.cpu()[:, :, :36, :40], f.cpu())) < TOL
+    g = torch.randn(4, 4, device=DEV)                               # a general (rank-4) 4x4 filter takes the non-separable path of the band kernel
+    assert rel_err(ops.up.upfirdn2d(x, g, padding=[1, 2, 2, 1], flip_filter=True), O.upfirdn2d(x.cpu(), g.cpu(), padding=[1, 2, 2, 1], flip_filter=True)) < TOL
+    from pasta_gan_b200.torch_utils.ops import conv_igemm
+    y = conv_igemm.conv2d_igemm(torch.randn(1, 16, 1, 1, device=DEV), torch.randn(8, 16, 3, 3, device=DEV))    # 1x1 image, 3x3 kernel
+    assert y.shape == (1, 8, 1, 1)
+    assert not conv_igemm.supported(torch.empty(0, 16, 8, 8, device=DEV), torch.randn(8, 16, 3, 3, device=DEV))  # empty batch -> library path
+    with torch.no_grad():
+        z = ops.cr.conv2d_resample(torch.empty(0, 16, 8, 8, device=DEV), torch.randn(8, 16, 3, 3, device=DEV), padding=1)
+    assert z.shape == (0, 8, 8, 8)
+
+
+def test_conv_igemm_1x1_image_value(ops):
+    from pasta_gan_b200.torch_utils.ops import conv_igemm
+    torch.manual_seed(4)
+    x = torch.randn(3, 32, 1, 1)
+    w = torch.randn(16, 32, 3, 3) / 10
+    ref = O._conv(x.double(), w.double(), padding=1)
+    assert rel_err(conv_igemm.conv2d_igemm(x.to(DEV), w.to(DEV)), ref) < 2e-3
