@@ -54,7 +54,22 @@ def conv_transpose2d(input, weight, bias=None, stride=1, padding=0, output_paddi
                                                 output_padding=output_padding, groups=groups, dilation=dilation)
 
 
+# Opt-in: run the stride-1 'same' 1x1 / 3x3 convolutions of the custom op (forward AND the input-gradient conv) on the tcgen05 kernel.
+# Off by default: at the training batch (4 per GPU) it measured 2x slower than cuDNN (weights are re-packed every step, tiles under-fill the
+# GPU) and fp16 operands cost ~1.5e-4 on D's logits; the training path keeps fp32 library convolutions until dgrad/wgrad kernels exist.
+tensor_core_forward = False
+
+
 def _forward(input, weight, bias, transpose, stride, padding, output_padding, dilation, groups):
+    """Dense convolution of the custom autograd op.  Called with grad mode off (inside Function.forward), so the tensor-core kernel may be
+    used for the shapes it covers: a stride-1 'same' conv, and the stride-1 transposed conv that is its input gradient
+    (conv_transpose2d(x, w) == conv2d(x, w^T mirrored))."""
+    if tensor_core_forward and bias is None and groups == 1 and stride == (1, 1) and dilation == (1, 1) and output_padding == (0, 0) \
+            and input.dtype == torch.float32 and weight.shape[2] == weight.shape[3] and padding == (weight.shape[2] // 2,) * 2:
+        from . import conv_igemm
+        w = weight.transpose(0, 1) if transpose else weight
+        if conv_igemm.supported(input, w, padding=(padding[0],) * 4):
+            return conv_igemm.conv2d_igemm(input, w, flip_weight=not transpose)
     if not transpose:
         return torch.nn.functional.conv2d(input, weight, bias, stride, padding, dilation, groups)
     return torch.nn.functional.conv_transpose2d(input, weight, bias, stride, padding, output_padding, groups, dilation)
