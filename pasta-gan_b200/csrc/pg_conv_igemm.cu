@@ -27,6 +27,7 @@
 //     NCHW stores.  The convolution result never round-trips through HBM before bias_act.
 //   * mbarrier pipelines: A full/empty (converters <-> MMA), B full/empty (bulk copy <-> MMA), accumulator full.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include "pg_common.cuh"
 
 namespace pg {
@@ -34,14 +35,13 @@ namespace pg {
 constexpr int kConvWarps   = 8;                 // A converters, later the epilogue
 constexpr int kConvThreads = 64 + 32 * kConvWarps;
 constexpr int kKC          = 16;                // channels per pipeline chunk == one UMMA K step
-constexpr int kTaskBatch   = 4;                 // converter tasks (8 channels x 32 positions) loaded back to back per warp
 
 struct ConvParams {
     const float* x; const void* wpack; const float* styles; const float* dcoefs; const float* noise; const float* bias; float* y;
     long long noise_bstride;
     int N, Cin, Cout, H, W, ks;
     int PW, Lp, tiles_per_img, NACC, BN, nchunks, ntaps, PA;      // PA: staged strip positions (multiple of 32)
-    int SA, SB, tps, cgroups; uint32_t a_stage_bytes, b_slot_bytes, b_tile_bytes;   // B ring: SB slots of `tps` taps each
+    int SA, SB, tps; uint32_t a_stage_bytes, b_slot_bytes, b_tile_bytes;   // B ring: SB slots of `tps` taps each
     int in_act; float in_alpha, in_gain; int act; float alpha, gain, clamp; int fmt;
     uint32_t idesc; uint32_t tmem_cols;
     // up-2 polyphase mode: BN virtual channels = phases x couts (see launch code); 0 = plain
@@ -49,10 +49,13 @@ struct ConvParams {
     int down2, cin_real, hin, win;   // down-2 mode: the A operand is the 4-plane space-to-depth view of x [N,cin_real,hin,win]
     const float* sp_x; const float* sp_mean; const float* sp_rstd; int spade;   // SPADE epilogue: y = act((x-mean)*rstd*(1+gamma)+beta)*gain
     long long* dbg;            // optional per-CTA phase timestamps (pg_debug_set_buffer), NULL in production
+    int pipe, ldmode, dbgmode;          // converter knobs (tuning): register double-buffering on/off, L1::no_allocate loads
+    int vec2; uint32_t w_magic;   // aligned 8-byte loader (see the converter section); ceil(2^32 / W)
     uint32_t pw_magic;         // ceil(2^32 / PW): q / PW == umulhi(q, pw_magic) for the strip positions that occur
 };
 
-#define PG_TS(slot) do { if (p.dbg) p.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (slot)] = clock64(); } while (0)
+#define PG_TS(slot) do { if (p.dbg) p.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + (slot)] = clock64(); } while (0)
+#define PG_PUT(slot, v) do { if (p.dbg) p.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + (slot)] = (v); } while (0)
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -94,6 +97,14 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;                                        // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
 }
 
+// The whole MMA warp runs the issue loop in uniform control flow and the tcgen05 instructions sit in `if (elected)` regions, `elected` coming from
+// elect.sync: ptxas then knows a single lane is active and moves descriptors to uniform registers with plain R2URs.  Under `if (lane == 0)` it
+// emits an ELECT / R2UR / BRA.U.ANY waterfall loop before every MMA that costs more than the MMA itself (149 vs 64 cycles, tools/micro).
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred;
+}
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -196,45 +207,85 @@ __global__ void conv_prepack_kernel(PackParams p) {
     }
 }
 
-// MMA issue loop of one CTA (executed by a single thread).  KS = kernel size (1 or 3); B ring slots hold KS taps each.
-template <int KS>
-__device__ __forceinline__ void mma_issue_loop(const ConvParams& p, uint8_t* a_base, uint8_t* b_base, uint64_t* a_full, uint64_t* a_empty,
-                                               uint64_t* b_full, uint64_t* b_empty, uint64_t* acc_full, uint32_t tmem_base) {
+// MMA issue loop of one CTA, executed by ALL lanes of the MMA warp (uniform control flow); `issue` != 0 on the one lane that issues.
+// KS = kernel size (1 or 3); B ring slots hold KS taps each; NACC accumulators of BN columns.  Everything the tcgen05.mma needs is either a
+// kernel parameter, a compile-time constant or a warp-uniform loop counter, so one MMA costs two uniform adds.
+template <int KS, int NACC>
+__device__ __forceinline__ void mma_issue_loop(const ConvParams& p, uint32_t a_base, uint32_t b_base, uint32_t a_full, uint32_t a_empty,
+                                               uint32_t b_full, uint32_t b_empty, uint32_t acc_full, uint32_t tmem_base, uint32_t issue) {
     const uint32_t hi = (128u >> 4) | (1u << 14);                         // SBO = 128 B, descriptor version 1 (bits 32..47)
     const uint32_t a_lo_const = ((uint32_t)p.PA & 0x3FFF) << 16;          // LBO = PA * 16 B  (>> 4)
     const uint32_t b_lo_const = ((uint32_t)p.BN & 0x3FFF) << 16;          // LBO = BN * 16 B  (>> 4)
     const uint32_t b_tile16 = p.b_tile_bytes >> 4;
     const uint32_t bn = (uint32_t)p.BN;
-    const int nacc = p.NACC;
+    const uint32_t pw = (uint32_t)p.PW;
+    const uint32_t idesc = p.idesc;
+    const int nchunks = p.nchunks, SA = p.SA, SB = p.SB;
     int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-    for (int ci = 0; ci < p.nchunks; ci++) {
-        mbar_wait(smem_u32(&a_full[sa]), pa);
+    long long wait_a = 0, wait_b = 0;              // instrumentation (registers; written once at the end)
+    for (int ci = 0; ci < nchunks; ci++) {
+        long long t0 = p.dbg ? clock64() : 0;
+        mbar_wait(a_full + 8u * (uint32_t)sa, pa);
         tc_fence_after();
-        if (ci == 0) PG_TS(2);
-        const uint32_t a_lo = a_lo_const | (smem_u32(a_base + (size_t)sa * p.a_stage_bytes) >> 4);
+        if (p.dbg) { if (ci == 0) { if (issue) PG_TS(2); } else wait_a += clock64() - t0; }
+        const uint32_t a_lo = a_lo_const | ((a_base + (uint32_t)sa * p.a_stage_bytes) >> 4);
 #pragma unroll
         for (int kh = 0; kh < KS; kh++) {
-            mbar_wait(smem_u32(&b_full[sb]), pb);
+            t0 = p.dbg ? clock64() : 0;
+            mbar_wait(b_full + 8u * (uint32_t)sb, pb);
             tc_fence_after();
-            const uint32_t b_lo = b_lo_const | (smem_u32(b_base + (size_t)sb * p.b_slot_bytes) >> 4);
+            if (p.dbg) wait_b += clock64() - t0;
+            const uint32_t b_lo = b_lo_const | ((b_base + (uint32_t)sb * p.b_slot_bytes) >> 4);
+            if (issue) {
 #pragma unroll
-            for (int kw = 0; kw < KS; kw++) {
-                const uint32_t s0 = (KS == 3) ? (uint32_t)(kh * p.PW + kw) : 0u;     // tap shift in strip positions == 16-byte rows
-                const uint64_t bdesc = ((uint64_t)hi << 32) | (uint64_t)(b_lo + (uint32_t)kw * b_tile16);
-                const uint32_t acc_flag = (ci | kh | kw) ? 1u : 0u;
-                for (int a = 0; a < nacc; a++) {
-                    const uint64_t adesc = ((uint64_t)hi << 32) | (uint64_t)(a_lo + s0 + (uint32_t)a * 128u);
-                    umma_f16(tmem_base + (uint32_t)a * bn, adesc, bdesc, p.idesc, acc_flag);
+                for (int kw = 0; kw < KS; kw++) {
+                    const uint32_t s0 = (KS == 3) ? (uint32_t)kh * pw + (uint32_t)kw : 0u;     // tap shift in strip positions == 16-byte rows
+                    const uint64_t bdesc = ((uint64_t)hi << 32) | (uint64_t)(b_lo + (uint32_t)kw * b_tile16);
+                    const uint32_t acc_flag = (ci | kh | kw) ? 1u : 0u;
+#pragma unroll
+                    for (int a = 0; a < NACC; a++) {
+                        const uint64_t adesc = ((uint64_t)hi << 32) | (uint64_t)(a_lo + s0 + (uint32_t)a * 128u);
+                        umma_f16(tmem_base + (uint32_t)a * bn, adesc, bdesc, idesc, acc_flag);
+                    }
                 }
+                umma_commit(b_empty + 8u * (uint32_t)sb);
+                if (kh == KS - 1) umma_commit(a_empty + 8u * (uint32_t)sa);
             }
-            umma_commit(smem_u32(&b_empty[sb]));
-            if (++sb == p.SB) { sb = 0; pb ^= 1; }
+            __syncwarp();
+            if (++sb == SB) { sb = 0; pb ^= 1; }
         }
-        umma_commit(smem_u32(&a_empty[sa]));
-        if (++sa == p.SA) { sa = 0; pa ^= 1; }
+        if (++sa == SA) { sa = 0; pa ^= 1; }
     }
-    PG_TS(3);
-    umma_commit(smem_u32(acc_full));
+    if (issue) { PG_TS(3); PG_PUT(8, wait_a); PG_PUT(9, wait_b); }
+    if (issue) umma_commit(acc_full);
+}
+
+// Converter task stream of one warp: slots (chunk, idx), idx < tpw, in register batches of BATCH tasks of TREGS floats.  pipelined: the loads of
+// batch k + 1 are issued before batch k is converted and stored (two batches of registers); otherwise one batch per memory round trip.
+template <int TREGS, int BATCH, class Load, class Store>
+__device__ __forceinline__ void stream_tasks(Load&& load_task, Store&& store_task, const int tpw, const int nchunks, const bool pipelined) {
+    float va[BATCH][TREGS], vb[BATCH][TREGS];
+    int l_ci = 0, l_idx = 0, c_ci = 0, c_idx = 0;          // load cursor, convert/store cursor
+    auto advance = [&](int& ci, int& idx) { if (++idx == tpw) { idx = 0; ci++; } };
+#pragma unroll
+    for (int u = 0; u < BATCH; u++) { load_task(va[u], l_ci, l_idx); advance(l_ci, l_idx); }
+    while (!pipelined && c_ci < nchunks) {
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) { store_task(va[u], c_ci, c_idx); advance(c_ci, c_idx); }
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) { load_task(va[u], l_ci, l_idx); advance(l_ci, l_idx); }
+    }
+    while (c_ci < nchunks) {
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) { load_task(vb[u], l_ci, l_idx); advance(l_ci, l_idx); }
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) { store_task(va[u], c_ci, c_idx); advance(c_ci, c_idx); }
+        if (c_ci >= nchunks) break;
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) { load_task(va[u], l_ci, l_idx); advance(l_ci, l_idx); }
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) { store_task(vb[u], c_ci, c_idx); advance(c_ci, c_idx); }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------- main kernel
@@ -242,14 +293,20 @@ __device__ __forceinline__ void mma_issue_loop(const ConvParams& p, uint8_t* a_b
 template <bool SCALE>
 __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const int tile = blockIdx.x % p.tiles_per_img;
     const int n    = blockIdx.x / p.tiles_per_img;
     const int jn   = blockIdx.y;
     const int BM   = 128 * p.NACC;
     const int m0   = tile * BM;
     const int HW   = p.H * p.W;
-    if (threadIdx.x == 0) PG_TS(0);
+    if (threadIdx.x == 0 && p.dbg) {
+        PG_TS(0);
+        uint32_t smid; unsigned long long gt;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        PG_PUT(11, (long long)smid); PG_PUT(12, (long long)gt);
+    }
 
     uint8_t* a_base = smem;
     uint8_t* b_base = a_base + (size_t)p.SA * p.a_stage_bytes;
@@ -263,7 +320,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
     if (warp == 0 && lane == 0) {
-        for (int i = 0; i < p.SA; i++) { mbar_init(smem_u32(&a_full[i]), kConvWarps / p.cgroups); mbar_init(smem_u32(&a_empty[i]), 1); }
+        for (int i = 0; i < p.SA; i++) { mbar_init(smem_u32(&a_full[i]), kConvWarps); mbar_init(smem_u32(&a_empty[i]), 1); }
         for (int i = 0; i < p.SB; i++) { mbar_init(smem_u32(&b_full[i]), 1); mbar_init(smem_u32(&b_empty[i]), 1); }
         mbar_init(smem_u32(acc_full), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -290,6 +347,12 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
         s_scale[j] = live ? (p.dcoefs ? p.dcoefs[(size_t)n * p.cout_real + o] : 1.f) * p.gain : 0.f;
         s_shift[j] = live && p.bias ? p.bias[o] * p.gain : 0.f;
     }
+    if (p.vec2) {     // the vec2 loader never writes the padding slots of the strip: zero every A stage once
+        uint4* z = reinterpret_cast<uint4*>(a_base);
+        const int nz = (int)((size_t)p.SA * p.a_stage_bytes / 16);
+        for (int i = threadIdx.x; i < nz; i += kConvThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        fence_proxy_async();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -304,6 +367,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
             int st = 0; uint32_t ph = 0;
             for (int g = 0; g < nslots; g++) {
                 mbar_wait(smem_u32(&b_empty[st]), ph ^ 1);
+                if (p.dbgmode & 4) { mbar_arrive(smem_u32(&b_full[st])); if (++st == p.SB) { st = 0; ph ^= 1; } continue; }
                 mbar_expect_tx(smem_u32(&b_full[st]), p.b_slot_bytes);
                 bulk_g2s(smem_u32(b_base + (size_t)st * p.b_slot_bytes), src + (size_t)g * p.b_slot_bytes, p.b_slot_bytes, smem_u32(&b_full[st]));
                 if (++st == p.SB) { st = 0; ph ^= 1; }
@@ -313,83 +377,158 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
         // ===================== MMA issuer =====================
         // The issue loop must cost less than one MMA (64 cycles at N = 128): descriptors are a constant high word plus a
         // 14-bit start-address field, so each MMA is two integer adds and the tcgen05.mma itself; taps are fully unrolled.
-        if (lane == 0) {
-            if (p.ks == 3) mma_issue_loop<3>(p, a_base, b_base, a_full, a_empty, b_full, b_empty, acc_full, tmem_base);
-            else           mma_issue_loop<1>(p, a_base, b_base, a_full, a_empty, b_full, b_empty, acc_full, tmem_base);
-        }
+        const uint32_t issue = elect_one();
+        const uint32_t ab = smem_u32(a_base), bb = smem_u32(b_base), af = smem_u32(a_full), ae = smem_u32(a_empty), bf = smem_u32(b_full),
+                       be = smem_u32(b_empty), accf = smem_u32(acc_full);
+        const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+#define PG_ISSUE(KS_, NACC_) mma_issue_loop<KS_, NACC_>(p, ab, bb, af, ae, bf, be, accf, tb, issue)
+        if (p.ks == 3) { if (p.NACC == 4) PG_ISSUE(3, 4); else if (p.NACC == 3) PG_ISSUE(3, 3); else if (p.NACC == 2) PG_ISSUE(3, 2); else PG_ISSUE(3, 1); }
+        else           { if (p.NACC == 4) PG_ISSUE(1, 4); else if (p.NACC == 3) PG_ISSUE(1, 3); else if (p.NACC == 2) PG_ISSUE(1, 2); else PG_ISSUE(1, 1); }
+#undef PG_ISSUE
     } else {
         // ===================== A converters =====================
+        // Each warp owns the tasks t = cw, cw + 8, ... of every chunk and walks them as ONE stream that runs across chunk boundaries, in register
+        // batches (stream_tasks): the global loads of a batch never wait for the shared-memory stage, only the stores wait on a_empty.
+        //   * vec2 loader (W even, 8-byte aligned planes, not down-2): a task is 64 consecutive floats (one aligned 256-byte run) of 8 channels of
+        //     the flat NCHW plane, read with LDG.64: 2 L1 wavefronts per 256 B where the scalar loader (32 strip positions per task, unaligned
+        //     because the strip pitch is W + 1) needs 2 per 128 B.  Element e of row h lands on staged strip slot e + h * (PW - W) - q0; the
+        //     padding slots (zero column, rows outside the image) are never written and stay zero from the one-time fill in the prologue.
+        //   * scalar loader: any W, down-2 space-to-depth reads; writes every staged slot (zeros where out of range).
         const int cw = warp - 2;
-        const int ngroups = p.PA / 32;
-        const int ntasks = ngroups * 2;                       // (position group, plane)
         const int halo = (p.ks == 3) ? p.PW + 1 : 0;
         const float* xn = p.down2 ? p.x + (size_t)n * p.cin_real * p.hin * p.win : p.x + (size_t)n * p.Cin * HW;
         const bool has_in_act = p.in_act != PG_ACT_LINEAR;
         const float in_slope = (p.in_act == PG_ACT_RELU) ? 0.f : p.in_alpha;
-        // Converter warps are split into `cgroups` groups that take alternate chunks, so that small tiles (a handful of tasks per chunk,
-        // i.e. one memory round trip per chunk) keep several chunks in flight instead of serialising on the L2/HBM latency.
-        const int wpg = kConvWarps / p.cgroups;                  // warps per group
-        const int grp = cw / wpg, gw = cw - grp * wpg;           // this warp's group and rank inside it
-        for (int ci = grp; ci < p.nchunks; ci += p.cgroups) {
-            const int st = ci % p.SA;
-            const uint32_t ph = (uint32_t)(ci / p.SA) & 1u;
-            mbar_wait(smem_u32(&a_empty[st]), ph ^ 1);
-            uint8_t* stage = a_base + (size_t)st * p.a_stage_bytes;
-            for (int t = gw; t < ntasks; t += kTaskBatch * wpg) {
-                // a whole batch of tasks is loaded before any is converted: 8 * kTaskBatch independent L2/HBM loads in flight per thread
-                float v[kTaskBatch][8];
-#pragma unroll
-                for (int u = 0; u < kTaskBatch; u++) {
-                    const int tt = t + u * wpg;
-                    const int q = m0 - halo + (tt >> 1) * 32 + lane;          // strip position of this staged row
-                    int h = 0, w = 0;
-                    bool ok = tt < ntasks && q >= 0 && q < p.Lp;
-                    if (ok) { h = (int)__umulhi((uint32_t)q, p.pw_magic); w = q - h * p.PW; ok = w < p.W; }
-                    const int c0 = ci * kKC + (tt & 1) * 8;
-                    const float* src; int cs;
-                    if (!p.down2) { src = xn + (size_t)c0 * HW + h * p.W + w; cs = HW; }
-                    else {
-                        const int plane = c0 / p.cin_real, cr = c0 - plane * p.cin_real;     // 8-channel groups never straddle a plane
-                        cs = p.hin * p.win;
-                        src = xn + (size_t)cr * cs + (2 * h + (plane >> 1)) * p.win + 2 * w + (plane & 1);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; i++) v[u][i] = 0.f;
-                    if (ok) {
-                        if (c0 + 8 <= p.Cin) {
-#pragma unroll
-                            for (int i = 0; i < 8; i++) v[u][i] = __ldg(src + i * cs);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 8; i++) if (c0 + i < p.Cin) v[u][i] = __ldg(src + i * cs);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < kTaskBatch; u++) {
-                    const int tt = t + u * wpg;
-                    if (tt >= ntasks) break;
-                    const int plane = tt & 1, spos = (tt >> 1) * 32 + lane;
-                    if (SCALE) {
-                        const float* sc = s_style + ci * kKC + plane * 8;
-#pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            float a = v[u][i];
-                            if (has_in_act) a = fmaxf(a, 0.f) + in_slope * fminf(a, 0.f);
-                            v[u][i] = a * sc[i];
-                        }
-                    }
-                    uint4 pk;
-                    pk.x = pack2(v[u][0], v[u][1], p.fmt); pk.y = pack2(v[u][2], v[u][3], p.fmt);
-                    pk.z = pack2(v[u][4], v[u][5], p.fmt); pk.w = pack2(v[u][6], v[u][7], p.fmt);
-                    *reinterpret_cast<uint4*>(stage + (size_t)plane * p.PA * 16 + (size_t)spos * 16) = pk;
-                }
-            }
+        const int nchunks = p.nchunks;
+        const int q0 = m0 - halo;                              // strip position of staged slot 0
+        int s_st = 0; uint32_t s_ph = 0;                       // store cursor: stage / parity of the chunk being written
+        long long wait_e = 0;
+        auto stage_begin = [&]() {
+            const long long t0 = p.dbg ? clock64() : 0;
+            mbar_wait(smem_u32(&a_empty[s_st]), s_ph ^ 1);
+            if (p.dbg) wait_e += clock64() - t0;
+        };
+        auto stage_end = [&]() {
             fence_proxy_async();                               // generic-proxy stores -> visible to the tensor core (async proxy)
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&a_full[st]));
+            if (lane == 0) mbar_arrive(smem_u32(&a_full[s_st]));
+            if (++s_st == p.SA) { s_st = 0; s_ph ^= 1; }
+        };
+        auto scale8 = [&](float (&v)[8], int ci, int plane) {
+            const float* sc = s_style + ci * kKC + plane * 8;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                float a = v[i];
+                if (has_in_act) a = fmaxf(a, 0.f) + in_slope * fminf(a, 0.f);
+                v[i] = a * sc[i];
+            }
+        };
+        auto pack8 = [&](const float (&v)[8]) {
+            uint4 pk;
+            pk.x = pack2(v[0], v[1], p.fmt); pk.y = pack2(v[2], v[3], p.fmt);
+            pk.z = pack2(v[4], v[5], p.fmt); pk.w = pack2(v[6], v[7], p.fmt);
+            return pk;
+        };
+
+        if (p.vec2) {
+            // flat element range [e_lo, e_hi) of the plane that the staged strip slots [q0, q0 + PA) cover
+            const int qa = q0 < 0 ? 0 : q0, qb = (q0 + p.PA < p.Lp ? q0 + p.PA : p.Lp) - 1;     // first / last strip position inside the image
+            int ha = (int)__umulhi((uint32_t)qa, p.pw_magic), wa = qa - ha * p.PW;
+            int hb = (int)__umulhi((uint32_t)qb, p.pw_magic), wb = qb - hb * p.PW;
+            const int e_lo = wa >= p.W ? (ha + 1) * p.W : ha * p.W + wa;
+            const int e_hi = wb >= p.W ? (hb + 1) * p.W : hb * p.W + wb + 1;
+            const int g_lo = e_lo >> 1, g_hi = (e_hi + 1) >> 1;                 // pairs of floats
+            const int nseg = g_hi > g_lo ? (g_hi - g_lo + 31) >> 5 : 0;
+            const int ntasks = nseg * 2;                                        // (segment of 32 pairs, plane)
+            const int tpw = ntasks ? (ntasks + kConvWarps - 1) / kConvWarps : 1;
+            const int dpitch = p.PW - p.W;
+            auto load_task = [&](float (&v)[16], int ci, int idx) {
+                const int tt = cw + idx * kConvWarps;
+                const int g = g_lo + (tt >> 1) * 32 + lane;
+                const bool ok = ci < nchunks && tt < ntasks && g < g_hi && !(p.dbgmode & 1);
+                const int c0 = ci * kKC + (tt & 1) * 8;
+                const float* src = xn + (size_t)c0 * HW + 2 * g;
+#pragma unroll
+                for (int i = 0; i < 16; i++) v[i] = 0.f;
+                if (ok) {
+                    if (c0 + 8 <= p.Cin) {
+#pragma unroll
+                        for (int i = 0; i < 8; i++) { const float2 t = __ldg(reinterpret_cast<const float2*>(src + (size_t)i * HW)); v[i] = t.x; v[8 + i] = t.y; }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; i++) if (c0 + i < p.Cin) { const float2 t = __ldg(reinterpret_cast<const float2*>(src + (size_t)i * HW)); v[i] = t.x; v[8 + i] = t.y; }
+                    }
+                }
+            };
+            auto store_task = [&](float (&v)[16], int ci, int idx) {
+                if (ci >= nchunks) return;
+                if (idx == 0) stage_begin();
+                const int tt = cw + idx * kConvWarps;
+                const int g = g_lo + (tt >> 1) * 32 + lane;
+                if (tt < ntasks && g < g_hi && !(p.dbgmode & 2)) {
+                    const int plane = tt & 1;
+                    const int e = 2 * g;
+                    const int h = (int)__umulhi((uint32_t)e, p.w_magic);
+                    const int s0 = e + h * dpitch - q0;                          // staged slot of the first element; the second is s0 + 1 (same row)
+                    float lo[8], hi[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) { lo[i] = v[i]; hi[i] = v[8 + i]; }
+                    if (SCALE) { scale8(lo, ci, plane); scale8(hi, ci, plane); }
+                    const uint4 pl = pack8(lo), ph = pack8(hi);
+                    // lanes sit 32 B apart in the stage: quarter-warps store conflict-free when lanes 4..7 of each group of 8 write their second slot first
+                    const bool swap = (lane >> 2) & 1;
+                    uint8_t* base = a_base + (size_t)s_st * p.a_stage_bytes + (size_t)plane * p.PA * 16;
+                    const int sa_ = swap ? s0 + 1 : s0, sb_ = swap ? s0 : s0 + 1;
+                    const uint4 pa_ = swap ? ph : pl, pb_ = swap ? pl : ph;
+                    if (sa_ >= 0 && sa_ < p.PA) *reinterpret_cast<uint4*>(base + (size_t)sa_ * 16) = pa_;
+                    if (sb_ >= 0 && sb_ < p.PA) *reinterpret_cast<uint4*>(base + (size_t)sb_ * 16) = pb_;
+                }
+                if (idx == tpw - 1) stage_end();
+            };
+            stream_tasks<16, 2>(load_task, store_task, tpw, nchunks, p.pipe != 0);
+        } else {
+            const int ntasks = (p.PA / 32) * 2;                       // (group of 32 strip positions, plane)
+            const int tpw = (ntasks + kConvWarps - 1) / kConvWarps;   // stream slots per warp per chunk (trailing ones may be void)
+            auto load_task = [&](float (&v)[8], int ci, int idx) {
+                const int tt = cw + idx * kConvWarps;
+                const int q = q0 + (tt >> 1) * 32 + lane;                 // strip position of this staged row
+                int h = 0, w = 0;
+                bool ok = ci < nchunks && tt < ntasks && q >= 0 && q < p.Lp && !(p.dbgmode & 1);
+                if (ok) { h = (int)__umulhi((uint32_t)q, p.pw_magic); w = q - h * p.PW; ok = w < p.W; }
+                const int c0 = ci * kKC + (tt & 1) * 8;
+                const float* src; int cs;
+                if (!p.down2) { src = xn + (size_t)c0 * HW + h * p.W + w; cs = HW; }
+                else {
+                    const int plane = c0 / p.cin_real, cr = c0 - plane * p.cin_real;     // 8-channel groups never straddle a plane
+                    cs = p.hin * p.win;
+                    src = xn + (size_t)cr * cs + (2 * h + (plane >> 1)) * p.win + 2 * w + (plane & 1);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[i] = 0.f;
+                if (ok) {
+                    if (c0 + 8 <= p.Cin) {
+#pragma unroll
+                        for (int i = 0; i < 8; i++) v[i] = __ldg(src + i * cs);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; i++) if (c0 + i < p.Cin) v[i] = __ldg(src + i * cs);
+                    }
+                }
+            };
+            auto store_task = [&](float (&v)[8], int ci, int idx) {
+                if (ci >= nchunks) return;
+                if (idx == 0) stage_begin();
+                const int tt = cw + idx * kConvWarps;
+                if (tt < ntasks && !(p.dbgmode & 2)) {
+                    const int plane = tt & 1, spos = (tt >> 1) * 32 + lane;
+                    if (SCALE) scale8(v, ci, plane);
+                    *reinterpret_cast<uint4*>(a_base + (size_t)s_st * p.a_stage_bytes + (size_t)plane * p.PA * 16 + (size_t)spos * 16) = pack8(v);
+                }
+                if (idx == tpw - 1) stage_end();
+            };
+            stream_tasks<8, 4>(load_task, store_task, tpw, nchunks, p.pipe != 0);
         }
-        if (cw == 0 && lane == 0) PG_TS(6);
+        if (cw == 0 && lane == 0) { PG_TS(6); PG_PUT(10, wait_e); }
         // ===================== epilogue (same warps) =====================
         mbar_wait(smem_u32(acc_full), 0);
         tc_fence_after();
@@ -478,7 +617,12 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
             }
         }
     }
-    if (threadIdx.x == 64) PG_TS(5);
+    if (threadIdx.x == 64 && p.dbg) {
+        PG_TS(5);
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        PG_PUT(13, (long long)gt);
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -488,11 +632,13 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
 
 // ---------------------------------------------------------------------------------------------- host side
 struct ConvPlan {
-    int BN, ntiles_n, nchunks, ntaps, NACC, PW, Lp, tiles_per_img, PA, SA, SB, tps, cgroups;
+    int BN, ntiles_n, nchunks, ntaps, NACC, PW, Lp, tiles_per_img, PA, SA, SB, tps;
     uint32_t a_stage, b_stage, b_slot, b_tile; size_t smem; uint32_t tmem_cols; int nvirt;
 };
 
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
 
 static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int ks, int up2) {
     pl.nvirt = up2 ? 4 * Cout : Cout;
@@ -507,7 +653,9 @@ static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int k
     pl.Lp = H * pl.PW;
     // Two co-resident CTAs per SM when the N tile is narrow (BN <= 128): each gets half of TMEM (256 columns) and ~100 KB of shared
     // memory, so one CTA's prologue / pipeline fill / epilogue overlaps the other's main loop.  Wide tiles (BN = 256) keep the SM alone.
-    const bool pair = bn <= 128;
+    bool pair = bn <= 128;
+    const int force_nacc = env_int("PASTA_B200_CONV_NACC", 0);
+    if (env_int("PASTA_B200_CONV_PAIR", 1) == 0 || force_nacc * bn > 256) pair = false;
     const int tmem_budget = pair ? 256 : 512;
     const int max_acc = tmem_budget / bn;
     int nacc = 1;
@@ -515,6 +663,7 @@ static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int k
         const long long ctas = (long long)N * ((pl.Lp + 128 * cand - 1) / (128 * cand)) * pl.ntiles_n;
         if (ctas >= 2 * kNumSMs * (pair ? 2 : 1) || cand == 1) { nacc = cand; break; }
     }
+    if (force_nacc && force_nacc * bn <= 512) nacc = force_nacc;
     while (nacc > 1 && 128 * (nacc - 1) >= pl.Lp) nacc--;
     pl.NACC = nacc;
     const int BM = 128 * nacc;
@@ -528,9 +677,6 @@ static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int k
     pl.tps = (ks == 3) ? 3 : 1;
     pl.b_slot = pl.b_tile * pl.tps;
     size_t budget = pair ? 100 * 1024 : 200 * 1024;
-    // converter warp groups over alternate chunks (cgroups > 1) were measured to give nothing: small-spatial / wide-channel layers are bound by
-    // streaming the weight slab from L2 once per 128-position tile, not by the activation round trip.  Kept at 1; the code path stays.
-    pl.cgroups = 1;
     pl.SA = 3;
     if ((size_t)pl.SA * pl.a_stage > budget / 2) pl.SA = 2;
     if ((size_t)pl.SA * pl.a_stage + 2 * (size_t)pl.b_slot + fixed + 128 > budget) budget = 200 * 1024;   // large strips: one CTA per SM after all
@@ -622,7 +768,7 @@ static int conv_run_impl(const float* x, const void* wpack, const float* styles,
     p.noise_bstride = noise_batch_stride;
     p.N = N; p.Cin = Cin; p.Cout = pl.nvirt; p.H = H; p.W = W; p.ks = ksize;
     p.PW = pl.PW; p.Lp = pl.Lp; p.tiles_per_img = pl.tiles_per_img; p.NACC = pl.NACC; p.BN = pl.BN; p.nchunks = pl.nchunks; p.ntaps = pl.ntaps;
-    p.PA = pl.PA; p.SA = pl.SA; p.SB = pl.SB; p.tps = pl.tps; p.cgroups = pl.cgroups; p.a_stage_bytes = pl.a_stage; p.b_slot_bytes = pl.b_slot; p.b_tile_bytes = pl.b_tile;
+    p.PA = pl.PA; p.SA = pl.SA; p.SB = pl.SB; p.tps = pl.tps; p.a_stage_bytes = pl.a_stage; p.b_slot_bytes = pl.b_slot; p.b_tile_bytes = pl.b_tile;
     p.in_act = in_act; p.in_alpha = in_alpha; p.in_gain = in_gain; p.act = act; p.alpha = alpha; p.gain = gain; p.clamp = clamp; p.fmt = operand_format;
     p.idesc = (1u << 4) | ((uint32_t)operand_format << 7) | ((uint32_t)operand_format << 10) | ((uint32_t)(pl.BN >> 3) << 17) | (8u << 24);
     p.tmem_cols = pl.tmem_cols;
@@ -631,7 +777,10 @@ static int conv_run_impl(const float* x, const void* wpack, const float* styles,
     if (p.spade) PG_REQUIRE(pl.ntiles_n == 1 && pl.BN == Cout && (Cout / 2) % 16 == 0 && up == 1 && sp_mean && sp_rstd,
                             "conv2d_igemm_spade: gamma and beta (2C <= 256 channels, C %% 16 == 0) must share one N tile");
     p.dbg = g_conv_dbg;
+    p.pipe = env_int("PASTA_B200_CONV_PIPE", 0); p.ldmode = env_int("PASTA_B200_CONV_LDMODE", 0); p.dbgmode = env_int("PASTA_B200_CONV_DBGMODE", 0);
     p.pw_magic = (uint32_t)((0x100000000ull + (uint64_t)pl.PW - 1) / (uint64_t)pl.PW);
+    p.w_magic = (uint32_t)((0x100000000ull + (uint64_t)W - 1) / (uint64_t)W);
+    p.vec2 = (!down2 && W % 2 == 0 && ((uintptr_t)x & 7) == 0 && env_int("PASTA_B200_CONV_VEC2", 1)) ? 1 : 0;
     const bool scale = styles != nullptr || in_act != PG_ACT_LINEAR || in_gain != 1.f;
     auto kern = scale ? conv_igemm_kernel<true> : conv_igemm_kernel<false>;
     PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
