@@ -141,7 +141,7 @@ class LaunchProfiler:
         import torch
         torch.cuda.synchronize()
         agg = {}
-        for name, nbytes, flops, e0, e1 in self.records:
+        for name, nbytes, flops, e0, e1, _tag in self.records:
             a = agg.setdefault(name, dict(launches=0, ms=0.0, bytes=0, flops=0))
             a['launches'] += 1
             a['ms'] += e0.elapsed_time(e1)
@@ -151,11 +151,11 @@ class LaunchProfiler:
 
 
 class _Span:
-    __slots__ = ('name', 'nbytes', 'flops', 'e0')
+    __slots__ = ('name', 'nbytes', 'flops', 'e0', 'tag')
 
-    def __init__(self, name, nbytes, flops):
+    def __init__(self, name, nbytes, flops, tag=''):
         import torch
-        self.name, self.nbytes, self.flops = name, nbytes, flops
+        self.name, self.nbytes, self.flops, self.tag = name, nbytes, flops, tag
         self.e0 = torch.cuda.Event(enable_timing=True)
         self.e0.record()
 
@@ -164,11 +164,11 @@ class _Span:
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
         if _profiler is not None:
-            _profiler.records.append((self.name, self.nbytes, self.flops, self.e0, e1))
+            _profiler.records.append((self.name, self.nbytes, self.flops, self.e0, e1, self.tag))
 
 
-def span(name, nbytes=0, flops=0):
+def span(name, nbytes=0, flops=0, tag=''):
     """Open a timing span if a profiler is installed; returns None otherwise (callers do `if s: s.close()`)."""
     if _profiler is None:
         return None
-    return _Span(name, nbytes, flops)
+    return _Span(name, nbytes, flops, tag)

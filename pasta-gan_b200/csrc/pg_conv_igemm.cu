@@ -158,7 +158,7 @@ __device__ float composite_tap(const PackParams& p, int o, int c, int a, int b, 
 
 // down-2 (FIR pad 2 -> 3x3 stride 2, conv2d_resample.py:119-122) as a 'same' 3x3 stride-1 conv over the space-to-depth planes of x:
 //   Kd = w' (*) k (6x6 full convolution, k = f flipped, w' = w for correlation / w mirrored for true convolution)
-//   virtual channel (plane = 2a+b, c), tap (r, s)  ->  Kd[o, c, 2r+a, 2s+b]                  (checked against the oracle to 4e-15 in fp64)
+//   virtual channel (a, c, b), tap (r, s)  ->  Kd[o, c, 2r+a, 2s+b]                         (checked against the oracle to 4e-15 in fp64)
 __device__ float down2_tap(const PackParams& p, int o, int c, int a, int b, int r, int s_) {
     const int u = 2 * r + a, v = 2 * s_ + b;
     float acc = 0.f;
@@ -186,10 +186,11 @@ __global__ void conv_prepack_kernel(PackParams p) {
         const int v = jn * p.BN + nl, c = ci * kKC + j * 8 + e;
         float val = 0.f;
         if (p.down2) {
-            // c runs over the 4 * Cin virtual channels (plane-major); p.Cin is the real channel count
+            // c runs over the 4 * Cin virtual channels (row parity a, then real channel, then column parity b: the order in which the
+            // activation loader's 8-byte reads deliver them); p.Cin is the real channel count
             if (v < p.Cout && c < 4 * p.Cin) {
-                const int plane = c / p.Cin, cr = c - plane * p.Cin;
-                val = down2_tap(p, v, cr, plane >> 1, plane & 1, tap / 3, tap % 3);
+                const int a = c / (2 * p.Cin), rem = c - a * 2 * p.Cin;          // virtual channel = a * 2Cin + 2 * c_real + b
+                val = down2_tap(p, v, rem >> 1, a, rem & 1, tap / 3, tap % 3);
             }
         } else if (v < nvirt && c < p.Cin) {
             const int kh = tap / p.ks, kw = tap % p.ks;
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
     }
     // per-sample input scale: style * in_gain (1 * in_gain for plain convs); zero for padded channels
     for (int c = threadIdx.x; c < cin_pad; c += kConvThreads)
-        s_style[c] = (c < p.Cin) ? (p.styles ? (p.down2 ? p.styles[(size_t)n * p.cin_real + c % p.cin_real] : p.styles[(size_t)n * p.Cin + c]) : 1.f) * p.in_gain : 0.f;
+        s_style[c] = (c < p.Cin) ? (p.styles ? (p.down2 ? p.styles[(size_t)n * p.cin_real + ((c % (2 * p.cin_real)) >> 1)] : p.styles[(size_t)n * p.Cin + c]) : 1.f) * p.in_gain : 0.f;
     // epilogue constants with the output gain folded in (relu / lrelu / linear are positively homogeneous, gain > 0)
     for (int j = threadIdx.x; j < p.BN; j += kConvThreads) {
         const int v = jn * p.BN + j;
@@ -496,23 +497,27 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
                 bool ok = ci < nchunks && tt < ntasks && q >= 0 && q < p.Lp && !(p.dbgmode & 1);
                 if (ok) { h = (int)__umulhi((uint32_t)q, p.pw_magic); w = q - h * p.PW; ok = w < p.W; }
                 const int c0 = ci * kKC + (tt & 1) * 8;
-                const float* src; int cs;
-                if (!p.down2) { src = xn + (size_t)c0 * HW + h * p.W + w; cs = HW; }
-                else {
-                    const int plane = c0 / p.cin_real, cr = c0 - plane * p.cin_real;     // 8-channel groups never straddle a plane
-                    cs = p.hin * p.win;
-                    src = xn + (size_t)cr * cs + (2 * h + (plane >> 1)) * p.win + 2 * w + (plane & 1);
-                }
 #pragma unroll
                 for (int i = 0; i < 8; i++) v[i] = 0.f;
-                if (ok) {
-                    if (c0 + 8 <= p.Cin) {
+                if (!p.down2) {
+                    const float* src = xn + (size_t)c0 * HW + h * p.W + w;
+                    if (ok) {
+                        if (c0 + 8 <= p.Cin) {
 #pragma unroll
-                        for (int i = 0; i < 8; i++) v[i] = __ldg(src + i * cs);
-                    } else {
+                            for (int i = 0; i < 8; i++) v[i] = __ldg(src + (size_t)i * HW);
+                        } else {
 #pragma unroll
-                        for (int i = 0; i < 8; i++) if (c0 + i < p.Cin) v[i] = __ldg(src + i * cs);
+                            for (int i = 0; i < 8; i++) if (c0 + i < p.Cin) v[i] = __ldg(src + (size_t)i * HW);
+                        }
                     }
+                } else if (ok) {
+                    // down-2: the 8 virtual channels of this group are 4 real channels x both column parities of input row 2h + a: four aligned
+                    // 8-byte reads per lane, consecutive lanes read consecutive pairs (fully used sectors)
+                    const int a = c0 / (2 * p.cin_real), cr = (c0 - a * 2 * p.cin_real) >> 1;
+                    const size_t cs = (size_t)p.hin * p.win;
+                    const float* src = xn + (size_t)cr * cs + (size_t)(2 * h + a) * p.win + 2 * w;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { const float2 t = __ldg(reinterpret_cast<const float2*>(src + (size_t)i * cs)); v[2 * i] = t.x; v[2 * i + 1] = t.y; }
                 }
             };
             auto store_task = [&](float (&v)[8], int ci, int idx) {
@@ -756,6 +761,7 @@ static int conv_run_impl(const float* x, const void* wpack, const float* styles,
     if (N == 0) return PG_OK;
     PG_REQUIRE(x && wpack && y, "conv2d_igemm: x, packed weights and y must be device pointers");
     const bool down2 = up == PG_CONV_DOWN2;
+    PG_REQUIRE(!down2 || ((uintptr_t)x & 7) == 0, "conv2d_igemm: down-2 needs an 8-byte aligned input");
     const int hin = H, win = W, cin_real = Cin;
     if (down2) { H /= 2; W /= 2; Cin *= 4; }                      // the GEMM runs over the space-to-depth view at the output resolution
     ConvPlan pl;

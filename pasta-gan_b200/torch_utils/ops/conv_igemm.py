@@ -108,7 +108,8 @@ def conv2d_igemm(x, w, f=None, up=1, down=1, flip_weight=True, styles=None, dcoe
         wpack = _packed_weights(capi, w, f, w_scale, mode, flip_weight, fmt_code, cache_weights)
         # algorithmic FLOPs: output pixels for stride-1 / down-2, INPUT pixels for up-2 (zero-inserted taps excluded)
         sp = capi.span('conv_igemm', flops=2 * n * cout * cin * k * k * (oh * ow if up == 1 else h * wd),
-                       nbytes=4 * (x.numel() + y.numel() + w.numel()))
+                       nbytes=4 * (x.numel() + y.numel() + w.numel()),
+                       tag=f'{cin}->{cout} @{h}x{wd} k{k} mode{mode}' + (' mod' if styles is not None else '') + (f' in_{in_act}' if in_act != 'linear' else ''))
         rc = capi.load().pg_conv2d_igemm_run(capi.ptr(x), capi.ptr(wpack), capi.ptr(styles), capi.ptr(dcoefs),
                                              capi.ptr(noise), nb_stride, capi.ptr(bias), capi.ptr(y),
                                              n, cin, cout, h, wd, k, mode,
@@ -163,7 +164,8 @@ def spade_conv_norm(x, feat, w_gamma, w_beta, w_scale=1.0, act='linear', alpha=0
     with torch.cuda.device(x.device):
         capi.require_device()
         wpack = _packed_weights(capi, wcat, None, w_scale, 1, True, fmt_code, True)
-        sp = capi.span('conv_igemm', flops=2 * n * 2 * c * cin * k * k * h * wd, nbytes=4 * (2 * x.numel() + feat.numel() + wcat.numel()))
+        sp = capi.span('conv_igemm', flops=2 * n * 2 * c * cin * k * k * h * wd, nbytes=4 * (2 * x.numel() + feat.numel() + wcat.numel()),
+                       tag=f'{cin}->{2 * c} @{h}x{wd} k{k} spade')
         rc = capi.load().pg_conv2d_igemm_spade_run(capi.ptr(feat), capi.ptr(wpack), capi.ptr(x), capi.ptr(mean), capi.ptr(rstd), capi.ptr(y),
                                                    n, cin, c, h, wd, k, _ACT[act], float(alpha), float(gain), fmt_code,
                                                    capi.current_stream(x.device))
