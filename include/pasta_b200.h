@@ -154,6 +154,16 @@ int pg_conv2d_igemm_run(const float* x, const void* wpack, const float* styles, 
                         int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t ksize, int32_t up,
                         int32_t in_act, float in_alpha, float in_gain,
                         int32_t act, float alpha, float gain, float clamp, int32_t operand_format, void* stream);
+/* pg_conv2d_igemm_run with two more fusions around the same GEMM:
+ *   x2 != NULL: the input is the channel concatenation [x ; x2] without materialising it (x [N,Cin1,H,W], x2 [N,Cin-Cin1,H,W], Cin1 % 8 == 0;
+ *               replaces torch.cat + conv of SynthesisBlockFull's merge_conv, training/networks.py:5705-5706); not with PG_CONV_DOWN2.
+ *   residual != NULL: y += residual after activation, gain and clamp (the `y.add_(x)` that closes every residual block,
+ *               training/networks.py:986-990, :5268-5272). */
+int pg_conv2d_igemm_run2(const float* x, const float* x2, int32_t Cin1, const void* wpack, const float* styles, const float* dcoefs,
+                         const float* noise, int64_t noise_batch_stride, const float* bias, const float* residual, float* y,
+                         int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t ksize, int32_t up,
+                         int32_t in_act, float in_alpha, float in_gain,
+                         int32_t act, float alpha, float gain, float clamp, int32_t operand_format, void* stream);
 int pg_conv2d_igemm_fwd(const float* x, const float* w, const float* fir, const float* styles, const float* dcoefs,
                         const float* noise, int64_t noise_batch_stride, const float* bias, float* y,
                         int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t ksize, int32_t up,
@@ -172,6 +182,10 @@ int pg_conv2d_igemm_fwd(const float* x, const float* w, const float* fir, const 
 int pg_conv2d_igemm_spade_run(const float* feat, const void* wpack_gamma_beta, const float* x, const float* mean, const float* rstd,
                               float* y, int32_t N, int32_t Cin, int32_t C, int32_t H, int32_t W, int32_t ksize,
                               int32_t act, float alpha, float gain, int32_t operand_format, void* stream);
+
+/* Instance-norm statistics of x [planes = N*C, hw] (dense, fp32): mean and rstd = rsqrt(biased variance + eps), one streaming pass.
+ * Feeds pg_conv2d_igemm_spade_run; replaces nn.InstanceNorm2d(affine=False) inside Spade_Norm_Block (training/networks.py:4363, :4377). */
+int pg_instance_norm_stats(const float* x, float* mean, float* rstd, int64_t planes, int64_t hw, float eps, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * torgb_skip — the ToRGB skip path of a synthesis block in one streaming kernel (north_star kernel 3):

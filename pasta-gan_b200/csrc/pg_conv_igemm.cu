@@ -37,7 +37,8 @@ constexpr int kConvThreads = 64 + 32 * kConvWarps;
 constexpr int kKC          = 16;                // channels per pipeline chunk == one UMMA K step
 
 struct ConvParams {
-    const float* x; const void* wpack; const float* styles; const float* dcoefs; const float* noise; const float* bias; float* y;
+    const float* x; const float* x2; const float* residual; int cin1;   // channels [0, cin1) come from x, [cin1, Cin) from x2 (fused concat)
+    const void* wpack; const float* styles; const float* dcoefs; const float* noise; const float* bias; float* y;
     long long noise_bstride;
     int N, Cin, Cout, H, W, ks;
     int PW, Lp, tiles_per_img, NACC, BN, nchunks, ntaps, PA;      // PA: staged strip positions (multiple of 32)
@@ -397,7 +398,9 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
         //   * scalar loader: any W, down-2 space-to-depth reads; writes every staged slot (zeros where out of range).
         const int cw = warp - 2;
         const int halo = (p.ks == 3) ? p.PW + 1 : 0;
-        const float* xn = p.down2 ? p.x + (size_t)n * p.cin_real * p.hin * p.win : p.x + (size_t)n * p.Cin * HW;
+        const float* xn = p.down2 ? p.x + (size_t)n * p.cin_real * p.hin * p.win : p.x + (size_t)n * p.cin1 * HW;
+        const float* xn2 = p.x2 ? p.x2 + (size_t)n * (p.Cin - p.cin1) * HW - (size_t)p.cin1 * HW : xn;   // indexed with the global channel number
+        auto chan_base = [&](int c0) { return (c0 < p.cin1 ? xn : xn2) + (size_t)c0 * HW; };
         const bool has_in_act = p.in_act != PG_ACT_LINEAR;
         const float in_slope = (p.in_act == PG_ACT_RELU) ? 0.f : p.in_alpha;
         const int nchunks = p.nchunks;
@@ -448,7 +451,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
                 const int g = g_lo + (tt >> 1) * 32 + lane;
                 const bool ok = ci < nchunks && tt < ntasks && g < g_hi && !(p.dbgmode & 1);
                 const int c0 = ci * kKC + (tt & 1) * 8;
-                const float* src = xn + (size_t)c0 * HW + 2 * g;
+                const float* src = chan_base(c0) + 2 * g;
 #pragma unroll
                 for (int i = 0; i < 16; i++) v[i] = 0.f;
                 if (ok) {
@@ -500,7 +503,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
 #pragma unroll
                 for (int i = 0; i < 8; i++) v[i] = 0.f;
                 if (!p.down2) {
-                    const float* src = xn + (size_t)c0 * HW + h * p.W + w;
+                    const float* src = chan_base(c0) + h * p.W + w;
                     if (ok) {
                         if (c0 + 8 <= p.Cin) {
 #pragma unroll
@@ -574,36 +577,59 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
             }
             float nz0 = 0.f;
             if (ok && p.noise && !p.up2) nz0 = __ldg(p.noise + (size_t)n * p.noise_bstride + (size_t)h * p.W + w) * p.gain;
-            for (int cc = part; cc < ncol_chunks; cc += kConvWarps / 4) {
+            // output element offset / channel stride / valid channels of column chunk cc for this thread's position
+            auto chunk_out = [&](int cc, size_t& off, size_t& ystride, int& oy, int& ox) {
+                const int v0 = jn * p.BN + cc * 16;                  // first (virtual) output channel of this chunk
+                int nvalid = p.Cout - v0; nvalid = nvalid > 16 ? 16 : nvalid;
+                if (!p.up2) {
+                    off = ((size_t)n * p.Cout + v0) * HW + (size_t)h * p.W + w;
+                    ystride = (size_t)HW; oy = h; ox = w;
+                } else {
+                    // polyphase up-2: virtual channel = phase * Cout + o (Cout % 16 == 0, so a chunk has one phase); output is 2H x 2W
+                    const int phase = v0 / p.cout_real, o0 = v0 - phase * p.cout_real;
+                    oy = 2 * h + (phase >> 1); ox = 2 * w + (phase & 1);
+                    ystride = (size_t)4 * HW;
+                    off = ((size_t)n * p.cout_real + o0) * ystride + (size_t)oy * W2 + ox;
+                }
+                return nvalid;
+            };
+            // the residual of chunk cc + step is fetched while chunk cc is read from TMEM, transformed and stored (one memory round trip hidden)
+            const int step = kConvWarps / 4;
+            float res[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) res[i] = 0.f;
+            auto fetch_res = [&](int cc, float (&dst)[16]) {
+                if (!p.residual || !ok || cc >= ncol_chunks) return;
+                size_t off, ystride; int oy, ox;
+                const int nvalid = chunk_out(cc, off, ystride, oy, ox);
+#pragma unroll
+                for (int i = 0; i < 16; i++) if (i < nvalid) dst[i] = __ldg(p.residual + off + (size_t)i * ystride);
+            };
+            fetch_res(part, res);
+            for (int cc = part; cc < ncol_chunks; cc += step) {
+                float res_next[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) res_next[i] = 0.f;
+                fetch_res(cc + step, res_next);
                 uint32_t r[16];
                 tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.BN + cc * 16), r);
                 if (!ok) continue;
-                const int v0 = jn * p.BN + cc * 16;                  // first (virtual) output channel of this chunk
-                int nvalid = p.Cout - v0; nvalid = nvalid > 16 ? 16 : nvalid;
+                size_t off, ystride; int oy, ox;
+                const int nvalid = chunk_out(cc, off, ystride, oy, ox);
                 if (nvalid <= 0) continue;
-                float sc[16], sh[16];
+                float nz = nz0;
+                if (p.up2 && p.noise) nz = __ldg(p.noise + (size_t)n * p.noise_bstride + (size_t)oy * W2 + ox) * p.gain;
+                float* yp = p.y + off;
+                float v[16];
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     const float4 a4 = reinterpret_cast<const float4*>(s_scale + cc * 16)[i];
                     const float4 b4 = reinterpret_cast<const float4*>(s_shift + cc * 16)[i];
-                    sc[4 * i] = a4.x; sc[4 * i + 1] = a4.y; sc[4 * i + 2] = a4.z; sc[4 * i + 3] = a4.w;
-                    sh[4 * i] = b4.x; sh[4 * i + 1] = b4.y; sh[4 * i + 2] = b4.z; sh[4 * i + 3] = b4.w;
+                    v[4 * i]     = fmaf(__uint_as_float(r[4 * i]),     a4.x, b4.x + nz);
+                    v[4 * i + 1] = fmaf(__uint_as_float(r[4 * i + 1]), a4.y, b4.y + nz);
+                    v[4 * i + 2] = fmaf(__uint_as_float(r[4 * i + 2]), a4.z, b4.z + nz);
+                    v[4 * i + 3] = fmaf(__uint_as_float(r[4 * i + 3]), a4.w, b4.w + nz);
                 }
-                float nz = nz0; float* yp; size_t ystride;
-                if (!p.up2) {
-                    yp = p.y + ((size_t)n * p.Cout + v0) * HW + (size_t)h * p.W + w;
-                    ystride = (size_t)HW;
-                } else {
-                    // polyphase up-2: virtual channel = phase * Cout + o (Cout % 16 == 0, so a chunk has one phase); output is 2H x 2W
-                    const int phase = v0 / p.cout_real, o0 = v0 - phase * p.cout_real;
-                    const int oy = 2 * h + (phase >> 1), ox = 2 * w + (phase & 1);
-                    if (p.noise) nz = __ldg(p.noise + (size_t)n * p.noise_bstride + (size_t)oy * W2 + ox) * p.gain;
-                    ystride = (size_t)4 * HW;
-                    yp = p.y + ((size_t)n * p.cout_real + o0) * ystride + (size_t)oy * W2 + ox;
-                }
-                float v[16];
-#pragma unroll
-                for (int i = 0; i < 16; i++) v[i] = fmaf(__uint_as_float(r[i]), sc[i], sh[i] + nz);
                 if (do_act) {
 #pragma unroll
                     for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i], 0.f) + slope * fminf(v[i], 0.f);
@@ -612,6 +638,8 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
 #pragma unroll
                     for (int i = 0; i < 16; i++) v[i] = fminf(fmaxf(v[i], -cl), cl);
                 }
+#pragma unroll
+                for (int i = 0; i < 16; i++) v[i] += res[i];
                 if (nvalid == 16) {
 #pragma unroll
                     for (int i = 0; i < 16; i++) yp[(size_t)i * ystride] = v[i];
@@ -619,6 +647,8 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
 #pragma unroll
                     for (int i = 0; i < 16; i++) if (i < nvalid) yp[(size_t)i * ystride] = v[i];
                 }
+#pragma unroll
+                for (int i = 0; i < 16; i++) res[i] = res_next[i];
             }
         }
     }
@@ -750,7 +780,8 @@ static int conv_run_impl(const float* x, const void* wpack, const float* styles,
                          int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t ksize, int32_t up,
                          int32_t in_act, float in_alpha, float in_gain,
                          int32_t act, float alpha, float gain, float clamp, int32_t operand_format, void* stream,
-                         const float* sp_x, const float* sp_mean, const float* sp_rstd) {
+                         const float* sp_x, const float* sp_mean, const float* sp_rstd,
+                         const float* x2 = nullptr, int32_t Cin1 = 0, const float* residual = nullptr) {
     using namespace pg;
     int rc = conv_validate(N, Cin, Cout, H, W, ksize, up, operand_format);
     if (rc != PG_OK) return rc;
@@ -770,6 +801,8 @@ static int conv_run_impl(const float* x, const void* wpack, const float* styles,
     cudaStream_t s = (cudaStream_t)stream;
     ConvParams p;
     p.down2 = down2; p.cin_real = cin_real; p.hin = hin; p.win = win;
+    PG_REQUIRE(!x2 || (!down2 && Cin1 > 0 && Cin1 < Cin && Cin1 % 8 == 0), "conv2d_igemm: the split input needs 0 < Cin1 < Cin, Cin1 %% 8 == 0 and no down-sampling");
+    p.x2 = x2; p.cin1 = x2 ? Cin1 : Cin; p.residual = residual;
     p.x = x; p.wpack = wpack; p.styles = styles; p.dcoefs = dcoefs; p.noise = noise; p.bias = bias; p.y = y;
     p.noise_bstride = noise_batch_stride;
     p.N = N; p.Cin = Cin; p.Cout = pl.nvirt; p.H = H; p.W = W; p.ks = ksize;
@@ -786,7 +819,7 @@ static int conv_run_impl(const float* x, const void* wpack, const float* styles,
     p.pipe = env_int("PASTA_B200_CONV_PIPE", 0); p.ldmode = env_int("PASTA_B200_CONV_LDMODE", 0); p.dbgmode = env_int("PASTA_B200_CONV_DBGMODE", 0);
     p.pw_magic = (uint32_t)((0x100000000ull + (uint64_t)pl.PW - 1) / (uint64_t)pl.PW);
     p.w_magic = (uint32_t)((0x100000000ull + (uint64_t)W - 1) / (uint64_t)W);
-    p.vec2 = (!down2 && W % 2 == 0 && ((uintptr_t)x & 7) == 0 && env_int("PASTA_B200_CONV_VEC2", 1)) ? 1 : 0;
+    p.vec2 = (!down2 && W % 2 == 0 && ((uintptr_t)x & 7) == 0 && ((uintptr_t)x2 & 7) == 0 && env_int("PASTA_B200_CONV_VEC2", 1)) ? 1 : 0;
     const bool scale = styles != nullptr || in_act != PG_ACT_LINEAR || in_gain != 1.f;
     auto kern = scale ? conv_igemm_kernel<true> : conv_igemm_kernel<false>;
     PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
@@ -802,6 +835,15 @@ extern "C" int pg_conv2d_igemm_run(const float* x, const void* wpack, const floa
                                    int32_t act, float alpha, float gain, float clamp, int32_t operand_format, void* stream) {
     return conv_run_impl(x, wpack, styles, dcoefs, noise, noise_batch_stride, bias, y, N, Cin, Cout, H, W, ksize, up, in_act, in_alpha, in_gain,
                          act, alpha, gain, clamp, operand_format, stream, nullptr, nullptr, nullptr);
+}
+
+extern "C" int pg_conv2d_igemm_run2(const float* x, const float* x2, int32_t Cin1, const void* wpack, const float* styles, const float* dcoefs,
+                                    const float* noise, int64_t noise_batch_stride, const float* bias, const float* residual, float* y,
+                                    int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t ksize, int32_t up,
+                                    int32_t in_act, float in_alpha, float in_gain,
+                                    int32_t act, float alpha, float gain, float clamp, int32_t operand_format, void* stream) {
+    return conv_run_impl(x, wpack, styles, dcoefs, noise, noise_batch_stride, bias, y, N, Cin, Cout, H, W, ksize, up, in_act, in_alpha, in_gain,
+                         act, alpha, gain, clamp, operand_format, stream, nullptr, nullptr, nullptr, x2, Cin1, residual);
 }
 
 extern "C" int pg_conv2d_igemm_spade_run(const float* feat, const void* wpack_gamma_beta, const float* x, const float* mean, const float* rstd,

@@ -54,12 +54,13 @@ def cuda_ops():
     """The product operator table: every entry lands in libpasta_b200.so (dense convs: see conv2d_gradfix)."""
     global _CUDA_OPS
     if _CUDA_OPS is None:
-        from .torch_utils.ops import upfirdn2d as U, bias_act as B, conv2d_resample as C, fma as F
+        from .torch_utils.ops import upfirdn2d as U, bias_act as B, conv2d_resample as C, fma as F, conv_igemm as K
         _CUDA_OPS = types.SimpleNamespace(
             name='sm100a',
             setup_filter=U.setup_filter, upfirdn2d=U.upfirdn2d, filter2d=U.filter2d, upsample2d=U.upsample2d,
             downsample2d=U.downsample2d, bias_act=B.bias_act, conv2d_resample=C.conv2d_resample, fma=F.fma,
             modulated_conv2d=modulated_conv2d, conv_layer=conv_layer, modconv_layer=modconv_layer, torgb_skip=_torgb_skip, spade_conv_norm=_spade_conv_norm,
+            instance_stats=lambda x: K.instance_stats(x) if (K.enabled and x.is_cuda and x.dtype == torch.float32) else None,
             act_def_gain={k: float(v.def_gain) for k, v in B.activation_funcs.items()},
         )
     return _CUDA_OPS
@@ -171,24 +172,27 @@ def _weight_sq_sums(weight):
 
 
 def conv_layer(x, w, b=None, f=None, up=1, down=1, padding=0, flip_weight=True, act='linear', act_gain=1.0, clamp=None,
-               in_act=None, in_gain=1.0, w_scale=1.0, cache_weights=False):
-    """Product form of one plain conv layer: [in_act(x) * in_gain ->] conv2d_resample -> bias_act.  When the tcgen05 kernel covers
-    the shape the whole layer is ONE launch (bias, activation, gain and clamp live in the GEMM epilogue; the SPADE pre-activation
-    lives in the operand prologue); otherwise it is composed from the same operators the reference calls."""
+               in_act=None, in_gain=1.0, w_scale=1.0, cache_weights=False, x2=None, residual=None):
+    """Product form of one plain conv layer: [in_act([x ; x2]) * in_gain ->] conv2d_resample -> bias_act [-> + residual].  When the tcgen05
+    kernel covers the shape the whole layer is ONE launch (bias, activation, gain, clamp and the residual add live in the GEMM epilogue; the
+    SPADE pre-activation and the channel concatenation live in the operand prologue); otherwise it is composed from the same operators
+    the reference calls."""
     from .torch_utils.ops import conv_igemm as K, conv2d_resample as C, bias_act as B
     pad4 = (padding,) * 4 if isinstance(padding, int) else None
     if act in ('linear', 'relu', 'lrelu') and in_act in (None, 'relu', 'lrelu') and \
-            K.supported(x, w, up=up, down=down, f=f, padding=pad4):
+            K.supported(x, w, up=up, down=down, f=f, padding=pad4, x2=x2, residual=residual):
         return K.conv2d_igemm(x, w, f=f, up=up, down=down, flip_weight=flip_weight, bias=b, in_act=in_act or 'linear', in_gain=in_gain,
-                              act=act, gain=act_gain, clamp=clamp, w_scale=w_scale, cache_weights=cache_weights)
+                              act=act, gain=act_gain, clamp=clamp, w_scale=w_scale, cache_weights=cache_weights, x2=x2, residual=residual)
+    if x2 is not None:
+        x = torch.cat([x, x2.to(x.dtype)], dim=1)
     if in_act is not None:
         x = B.bias_act(x, None, act=in_act, gain=in_gain)
     if w_scale != 1.0:
         w = w * w_scale
     x = C.conv2d_resample(x=x, w=w.to(x.dtype), f=f, up=up, down=down, padding=padding, flip_weight=flip_weight)
-    if b is None and act == 'linear' and act_gain == 1 and clamp is None:
-        return x
-    return B.bias_act(x, b, act=act, gain=act_gain, clamp=clamp)
+    if not (b is None and act == 'linear' and act_gain == 1 and clamp is None):
+        x = B.bias_act(x, b, act=act, gain=act_gain, clamp=clamp)
+    return x if residual is None else residual.add_(x)
 
 
 def modconv_layer(x, weight, styles, noise=None, up=1, padding=0, resample_filter=None, demodulate=True, flip_weight=True,
@@ -209,7 +213,7 @@ def modconv_layer(x, weight, styles, noise=None, up=1, padding=0, resample_filte
     return B.bias_act(x, bias, act=act, gain=act_gain, clamp=clamp)
 
 
-def _spade_conv_norm(x, actv, w_gamma, w_beta, w_scale, post_act):
+def _spade_conv_norm(x, actv, w_gamma, w_beta, w_scale, post_act, stats=None):
     """Product SPADE normalisation: instance-norm + (1 + gamma) * . + beta (+ the consumer's pre-activation) inside the epilogue of the
     merged gamma|beta convolution; None when the shape is not covered."""
     from .torch_utils.ops import conv_igemm as K
@@ -218,7 +222,7 @@ def _spade_conv_norm(x, actv, w_gamma, w_beta, w_scale, post_act):
     act, gain = post_act if post_act is not None else ('linear', 1.0)
     if act not in ('linear', 'relu', 'lrelu'):
         return None
-    return K.spade_conv_norm(x, actv, w_gamma, w_beta, w_scale=w_scale, act=act, gain=gain)
+    return K.spade_conv_norm(x, actv, w_gamma, w_beta, w_scale=w_scale, act=act, gain=gain, stats=stats)
 
 
 def _torgb_skip(x, weight, styles, bias, clamp, img, f):
@@ -287,7 +291,7 @@ class Conv2dLayer(OpsModule):
         clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
         return self.ops.bias_act(x, b, act=self.activation, gain=self.act_gain * gain, clamp=clamp)
 
-    def _fused(self, x, gain, pre_act):
+    def _fused(self, x, gain, pre_act, x2=None, residual=None):
         """One-launch layer when the operator table offers it (the CUDA product does; the oracle table does not)."""
         layer = getattr(self.ops, 'conv_layer', None)
         if layer is None:
@@ -296,7 +300,7 @@ class Conv2dLayer(OpsModule):
         b = self.bias.to(x.dtype) if self.bias is not None else None
         clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
         kw = dict(f=self.resample_filter, up=self.up, down=self.down, padding=self.padding, flip_weight=(self.up == 1),
-                  w_scale=float(self.weight_gain), cache_weights=True)
+                  w_scale=float(self.weight_gain), cache_weights=True, x2=x2, residual=residual)
         if pre_act is None:
             return layer(x, w, b, act=self.activation, act_gain=self.act_gain * gain, clamp=clamp, **kw)
         if not pre_act:                                   # SPADE layer called with no_act=True: bare convolution
@@ -305,22 +309,30 @@ class Conv2dLayer(OpsModule):
             return None
         return layer(x, w, None, in_act=self.activation, in_gain=self.act_gain * gain, **kw)
 
-    def forward(self, x, gain=1):
-        y = self._fused(x, gain, None)
-        return y if y is not None else self._act(self._conv(x), gain)
+    def forward(self, x, gain=1, x2=None, residual=None):
+        """``x2``: second input concatenated along channels (reference: torch.cat before the call, :5705); ``residual``: added to the
+        result (reference: ``y.add_(x)`` after the call, :990)."""
+        y = self._fused(x, gain, None, x2, residual)
+        if y is not None:
+            return y
+        if x2 is not None:
+            x = torch.cat([x, x2.to(x.dtype)], dim=1)
+        y = self._act(self._conv(x), gain)
+        return y if residual is None else residual.add_(y)
 
 
 class SpadeConv2dLayer(Conv2dLayer):
     def __init__(self, in_channels, out_channels, kernel_size, bias=True, activation='relu', **kw):
         super().__init__(in_channels, out_channels, kernel_size, bias=bias, activation=activation, **kw)
 
-    def forward(self, x, gain=1, no_act=False):
-        y = self._fused(x, gain, not no_act)
+    def forward(self, x, gain=1, no_act=False, residual=None):
+        y = self._fused(x, gain, not no_act, None, residual)
         if y is not None:
             return y
         if not no_act:
             x = self._act(x, gain)
-        return self._conv(x)
+        y = self._conv(x)
+        return y if residual is None else residual.add_(y)
 
 
 class MappingNetwork(OpsModule):
@@ -455,8 +467,7 @@ class ResBlock(OpsModule):
 
     def forward(self, x):
         y = self.skip(x, gain=np.sqrt(0.5))
-        x = self.conv1(self.conv0(x), gain=np.sqrt(0.5))
-        return y.add_(x)
+        return self.conv1(self.conv0(x), gain=np.sqrt(0.5), residual=y)          # y + conv1(...): the add rides in conv1's epilogue
 
 
 class ConstEncoderNetwork(OpsModule):
@@ -523,14 +534,15 @@ class SpadeNormBlock(OpsModule):
         self.conv_beta = SpadeConv2dLayer(norm_channels, norm_channels, kernel_size=3, bias=False)
         self.param_free_norm = nn.InstanceNorm2d(norm_channels, affine=False)
 
-    def forward(self, x, denorm_feats, post_act=None):
+    def forward(self, x, denorm_feats, post_act=None, stats=None):
         """``post_act = (name, gain)``: apply the pre-activation of the Spade conv that consumes the result here (then call it with
-        ``no_act=True``); only honoured on the fused path, so callers must check ``fused_post_act``."""
+        ``no_act=True``).  ``stats``: (mean, rstd) of ``x`` when the caller already has them (two norm blocks of a SPADE res-block
+        normalise the same tensor); only used on the fused path."""
         fused = getattr(self.ops, 'spade_conv_norm', None)
         if fused is not None:
             actv = self.ops.conv_layer(denorm_feats, self.conv_mlp.weight, None, padding=1, act='relu', act_gain=1.0,
                                        w_scale=float(self.conv_mlp.weight_gain), cache_weights=True)
-            y = fused(x, actv, self.conv_gamma.weight, self.conv_beta.weight, float(self.conv_gamma.weight_gain), post_act)
+            y = fused(x, actv, self.conv_gamma.weight, self.conv_beta.weight, float(self.conv_gamma.weight_gain), post_act, stats)
             if y is not None:
                 return y
         actv = self.conv_mlp_act(self.conv_mlp(denorm_feats, no_act=True))
@@ -561,10 +573,11 @@ class SpadeResBlockV2(OpsModule):
         # the pre-activation (relu * act_gain * gain) of each consuming Spade conv is handed to the norm block, which applies it in the
         # same pass (fused: in the GEMM epilogue that produces gamma / beta); the convs then run bare
         pre = lambda conv, gain: (conv.activation, float(conv.act_gain * gain))
-        y = self.skip(self.spade_skip(x, denorm_feat, post_act=pre(self.skip, np.sqrt(0.5))), no_act=True)
-        x = self.conv0(self.spade0(x, denorm_feat, post_act=pre(self.conv0, 1)), no_act=True)
-        x = self.conv1(self.spade1(x, denorm_feat, post_act=pre(self.conv1, np.sqrt(0.5))), no_act=True)
-        return y.add_(x)
+        stats_fn = getattr(self.ops, 'instance_stats', None)
+        stats = stats_fn(x) if stats_fn is not None and not (torch.is_grad_enabled() and x.requires_grad) else None   # shared by spade_skip / spade0
+        y = self.skip(self.spade_skip(x, denorm_feat, post_act=pre(self.skip, np.sqrt(0.5)), stats=stats), no_act=True)
+        x = self.conv0(self.spade0(x, denorm_feat, post_act=pre(self.conv0, 1), stats=stats), no_act=True)
+        return self.conv1(self.spade1(x, denorm_feat, post_act=pre(self.conv1, np.sqrt(0.5))), no_act=True, residual=y)
 
 
 class SynthesisBlockFull(OpsModule):
@@ -610,7 +623,7 @@ class SynthesisBlockFull(OpsModule):
             x = self.conv0(x.to(torch.float32), next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
             x = self.conv1(x, next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
             if x.shape[2] > 16:                          # merge the warped retain-person features
-                x = self.merge_conv(torch.cat([x, cat_feat[str(x.shape[2])].to(torch.float32)], dim=1))
+                x = self.merge_conv(x, x2=cat_feat[str(x.shape[2])].to(torch.float32))     # concat fused into the 1x1 conv's operand loader
         if img is not None:
             misc.assert_shape(img, [None, self.img_channels, self.resolution // 2, self.resolution // 2])
         parsing = None
@@ -776,7 +789,7 @@ class SynthesisBlock512(OpsModule):
             x = self.conv0(x.to(torch.float32), next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
             x = self.conv1(x, next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
             if x.shape[2] > 32:
-                x = self.merge_conv(torch.cat([x, cat_feat[str(x.shape[2])].to(torch.float32)], dim=1))
+                x = self.merge_conv(x, x2=cat_feat[str(x.shape[2])].to(torch.float32))     # concat fused into the 1x1 conv's operand loader
         w_rgb = next(w_iter)
         fused = self.torgb.forward_skip(x, w_rgb, img, self.resample_filter)
         if fused is not None:
@@ -904,8 +917,7 @@ class DiscriminatorBlock(OpsModule):
             img = self.ops.downsample2d(img, self.resample_filter) if self.architecture == 'skip' else None
         if self.architecture == 'resnet':
             y = self.skip(x, gain=np.sqrt(0.5))
-            x = self.conv1(self.conv0(x), gain=np.sqrt(0.5))
-            x = y.add_(x)
+            x = self.conv1(self.conv0(x), gain=np.sqrt(0.5), residual=y)
         else:
             x = self.conv1(self.conv0(x))
         assert x.dtype == dtype

@@ -18,7 +18,7 @@ enabled = os.environ.get('PASTA_B200_CONV', '1') != '0'
 operand_format = os.environ.get('PASTA_B200_CONV_FMT', 'fp16')
 
 
-def supported(x, w, up=1, down=1, groups=1, f=None, padding=None, flip_filter=False):
+def supported(x, w, up=1, down=1, groups=1, f=None, padding=None, flip_filter=False, x2=None, residual=None):
     """Shapes the kernel covers: dense fp32 NCHW on CUDA, 1x1 / 3x3, stride 1, 'same' padding, optional polyphase up-2."""
     if not (enabled and x.is_cuda and x.dtype == torch.float32 and w.dtype == torch.float32 and x.ndim == 4):
         return False
@@ -35,6 +35,13 @@ def supported(x, w, up=1, down=1, groups=1, f=None, padding=None, flip_filter=Fa
     if up == 2 and (k != 3 or f is None or f.ndim != 2 or tuple(f.shape) != (4, 4) or flip_filter or w.shape[0] % 16 != 0):
         return False
     if x.numel() == 0 or x.numel() > 2 ** 31 - 1:
+        return False
+    if x2 is not None and (down != 1 or x2.dtype != torch.float32 or x.shape[1] % 8 or x2.shape[0] != x.shape[0] or x2.shape[2:] != x.shape[2:] or
+                           (torch.is_grad_enabled() and x2.requires_grad)):
+        return False
+    if residual is not None and (residual.dtype != torch.float32 or (torch.is_grad_enabled() and residual.requires_grad)):
+        return False
+    if down == 2 and x.data_ptr() % 8:
         return False
     return True
 
@@ -71,14 +78,19 @@ def _packed_weights(capi, w, f, w_scale, up, flip_weight, fmt_code, cache):
 
 def conv2d_igemm(x, w, f=None, up=1, down=1, flip_weight=True, styles=None, dcoefs=None, noise=None, bias=None,
                  in_act='linear', in_alpha=0.2, in_gain=1.0, act='linear', alpha=0.2, gain=1.0, clamp=None, fmt=None,
-                 w_scale=1.0, cache_weights=False):
-    """y = clamp(act(dcoefs * conv(styles * in_gain * in_act(x), w * w_scale) + noise + bias) * gain); see include/pasta_b200.h."""
+                 w_scale=1.0, cache_weights=False, x2=None, residual=None):
+    """y = clamp(act(dcoefs * conv(styles * in_gain * in_act([x ; x2]), w * w_scale) + noise + bias) * gain) + residual; see include/pasta_b200.h.
+    ``x2``: second part of the input along channels (fused torch.cat); ``residual``: tensor of the output's shape added last."""
     capi = _backend.capi()
     _backend.require_cuda(x, 'conv2d_igemm')
-    n, cin, h, wd = (int(v) for v in x.shape)
+    n, cin1, h, wd = (int(v) for v in x.shape)
+    cin = cin1 + (int(x2.shape[1]) if x2 is not None else 0)
     cout, cin_w, k, _ = (int(v) for v in w.shape)
     assert cin_w == cin, 'weight / input channel mismatch'
     x = x.contiguous()
+    if x2 is not None:
+        assert x2.dtype == torch.float32 and tuple(x2.shape[2:]) == (h, wd) and int(x2.shape[0]) == n and down == 1 and cin1 % 8 == 0
+        x2 = x2.contiguous()
     assert not (up == 2 and down == 2)
     mode = -2 if down == 2 else up                       # PG_CONV_DOWN2 / 2 / 1
     oh, ow = (h // 2, wd // 2) if down == 2 else (h * up, wd * up)
@@ -102,21 +114,24 @@ def conv2d_igemm(x, w, f=None, up=1, down=1, flip_weight=True, styles=None, dcoe
         assert tuple(bias.shape) == (cout,)
     if mode != 1:
         f = f.to(torch.float32).contiguous()
+    if residual is not None:
+        assert residual.dtype == torch.float32 and residual.shape == y.shape
+        residual = residual.contiguous()
     fmt_code = _FMT[fmt or operand_format]
     with torch.cuda.device(x.device):
         capi.require_device()
         wpack = _packed_weights(capi, w, f, w_scale, mode, flip_weight, fmt_code, cache_weights)
         # algorithmic FLOPs: output pixels for stride-1 / down-2, INPUT pixels for up-2 (zero-inserted taps excluded)
         sp = capi.span('conv_igemm', flops=2 * n * cout * cin * k * k * (oh * ow if up == 1 else h * wd),
-                       nbytes=4 * (x.numel() + y.numel() + w.numel()),
-                       tag=f'{cin}->{cout} @{h}x{wd} k{k} mode{mode}' + (' mod' if styles is not None else '') + (f' in_{in_act}' if in_act != 'linear' else ''))
-        rc = capi.load().pg_conv2d_igemm_run(capi.ptr(x), capi.ptr(wpack), capi.ptr(styles), capi.ptr(dcoefs),
-                                             capi.ptr(noise), nb_stride, capi.ptr(bias), capi.ptr(y),
-                                             n, cin, cout, h, wd, k, mode,
-                                             _ACT[in_act], float(in_alpha), float(in_gain),
-                                             _ACT[act], float(alpha), float(gain), float(-1 if clamp is None else clamp),
-                                             fmt_code, capi.current_stream(x.device))
-        capi.check(rc, 'pg_conv2d_igemm_run')
+                       nbytes=4 * (x.numel() + (x2.numel() if x2 is not None else 0) + y.numel() * (2 if residual is not None else 1) + w.numel()),
+                       tag=f'{cin}->{cout} @{h}x{wd} k{k} mode{mode}' + (' mod' if styles is not None else '') + (' cat' if x2 is not None else '') + (' res' if residual is not None else '') + (f' in_{in_act}' if in_act != 'linear' else ''))
+        rc = capi.load().pg_conv2d_igemm_run2(capi.ptr(x), capi.ptr(x2), cin1, capi.ptr(wpack), capi.ptr(styles), capi.ptr(dcoefs),
+                                              capi.ptr(noise), nb_stride, capi.ptr(bias), capi.ptr(residual), capi.ptr(y),
+                                              n, cin, cout, h, wd, k, mode,
+                                              _ACT[in_act], float(in_alpha), float(in_gain),
+                                              _ACT[act], float(alpha), float(gain), float(-1 if clamp is None else clamp),
+                                              fmt_code, capi.current_stream(x.device))
+        capi.check(rc, 'pg_conv2d_igemm_run2')
         if sp:
             sp.close()
     return y
@@ -148,16 +163,32 @@ def spade_supported(x, feat, w_gamma, w_beta):
             w_gamma.shape[2] == w_gamma.shape[3] and feat.shape[2:] == x.shape[2:] and feat.shape[1] == w_gamma.shape[1] and x.numel() > 0)
 
 
-def spade_conv_norm(x, feat, w_gamma, w_beta, w_scale=1.0, act='linear', alpha=0.2, gain=1.0, eps=1e-5, fmt=None):
+def instance_stats(x, eps=1e-5):
+    """(mean, rstd) [N, C] of nn.InstanceNorm2d(affine=False) for x [N, C, H, W] fp32, one streaming pass (pg_instance_norm_stats)."""
+    capi = _backend.capi()
+    _backend.require_cuda(x, 'instance_stats')
+    x = x.contiguous()
+    n, c, h, wd = (int(v) for v in x.shape)
+    mean = torch.empty([n, c], dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    with torch.cuda.device(x.device):
+        capi.require_device()
+        sp = capi.span('instance_stats', nbytes=4 * x.numel(), tag=f'{n * c} x {h * wd}')
+        rc = capi.load().pg_instance_norm_stats(capi.ptr(x), capi.ptr(mean), capi.ptr(rstd), n * c, h * wd, float(eps), capi.current_stream(x.device))
+        capi.check(rc, 'pg_instance_norm_stats')
+        if sp:
+            sp.close()
+    return mean, rstd
+
+
+def spade_conv_norm(x, feat, w_gamma, w_beta, w_scale=1.0, act='linear', alpha=0.2, gain=1.0, eps=1e-5, fmt=None, stats=None):
     """act(instance_norm(x) * (1 + conv(feat, w_gamma)) + conv(feat, w_beta)) * gain  in one tcgen05 launch (gamma / beta stay in TMEM)."""
     capi = _backend.capi()
     n, c, h, wd = (int(v) for v in x.shape)
     cin, k = int(feat.shape[1]), int(w_gamma.shape[2])
     x = x.contiguous()
     feat = feat.contiguous()
-    var, mean = torch.var_mean(x, dim=(2, 3), unbiased=False)
-    rstd = (var + eps).rsqrt().contiguous()
-    mean = mean.contiguous()
+    mean, rstd = stats if stats is not None else instance_stats(x, eps)      # `stats`: reuse when several norm blocks share x
     wcat = _gamma_beta_weights(w_gamma, w_beta)
     fmt_code = _FMT[fmt or operand_format]
     y = torch.empty_like(x)

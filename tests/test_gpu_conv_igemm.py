@@ -153,3 +153,57 @@ def test_down2_space_to_depth(cv, shape):
     y2 = cv.conv2d_igemm(x.to(DEV), wt.to(DEV), f=f.to(DEV), down=2, bias=b.to(DEV), act='lrelu', gain=2 ** 0.5, clamp=256)
     ref2 = O.bias_act(O.conv2d_resample(x.double(), wt.double(), f=f.double(), down=2, padding=1), b.double(), act='lrelu', clamp=256)
     assert rel_err(y2, ref2) < 3e-3
+
+
+SPLIT = [(2, 64, 64, 32, 20, 28, 1), (1, 128, 64, 128, 33, 31, 1), (2, 16, 24, 48, 16, 16, 3), (1, 512, 64, 512, 32, 32, 1), (2, 8, 42, 64, 10, 12, 3)]
+
+
+@pytest.mark.parametrize('shape', SPLIT, ids=[str(s) for s in SPLIT])
+def test_split_input_and_residual(cv, shape):
+    """conv([x ; x2]) without the concatenation (merge_conv, reference :5705-5706) and the residual add in the epilogue (`y.add_(x)`, :990)."""
+    n, c1, c2, cout, h, w, k = shape
+    torch.manual_seed(sum(shape))
+    x, x2 = torch.randn(n, c1, h, w), torch.randn(n, c2, h, w)
+    wt = torch.randn(cout, c1 + c2, k, k) / ((c1 + c2) * k * k) ** 0.5
+    b = torch.randn(cout) * 0.2
+    res = torch.randn(n, cout, h, w)
+    ref = O.bias_act(O._conv(torch.cat([x, x2], 1).double(), wt.double(), padding=k // 2), b.double(), act='lrelu', gain=0.7, clamp=0.9) + res.double()
+    y = cv.conv2d_igemm(x.to(DEV), wt.to(DEV), x2=x2.to(DEV), bias=b.to(DEV), act='lrelu', gain=0.7, clamp=0.9, residual=res.to(DEV))
+    assert rel_err(y, ref) < 2e-3
+    # residual with the polyphase up-2 output mapping
+    if k == 3 and cout % 16 == 0:
+        f = O.setup_filter([1, 3, 3, 1])
+        res2 = torch.randn(n, cout, 2 * h, 2 * w)
+        xx = torch.cat([x, x2], 1)
+        ref2 = O.conv2d_resample(xx.double(), wt.double(), f.double(), up=2, padding=1, flip_weight=False) + res2.double()
+        y2 = cv.conv2d_igemm(xx.to(DEV), wt.to(DEV), f=f.to(DEV), up=2, flip_weight=False, residual=res2.to(DEV))
+        assert rel_err(y2, ref2) < 2e-3
+
+
+def test_residual_blocks_match_unfused(cv):
+    """ResBlock / SpadeResBlockV2 with the fused residual equal the same modules with the tcgen05 path disabled (library convs + add_)."""
+    from pasta_gan_b200 import networks as N
+    torch.manual_seed(5)
+    blk = N.ResBlock(32, 64, kernel_size=3, activation='relu', down=2).to(DEV).eval().requires_grad_(False)
+    x = torch.randn(2, 32, 32, 32, device=DEV)
+    with torch.no_grad():
+        y = blk(x)
+        cv.enabled = False
+        try:
+            ref = blk(x)
+        finally:
+            cv.enabled = True
+    assert rel_err(y, ref) < 3e-3
+
+
+@pytest.mark.parametrize('shape', [(2, 16, 128, 128), (3, 5, 33, 31), (1, 128, 16, 16), (2, 3, 4, 4), (1, 2, 256, 256)])
+def test_instance_stats(cv, shape):
+    """pg_instance_norm_stats == nn.InstanceNorm2d's statistics (biased variance, eps 1e-5), also with a large common offset."""
+    torch.manual_seed(sum(shape))
+    for offset in (0.0, 100.0):
+        x = (torch.randn(*shape) * 1.7 + offset)
+        mean, rstd = cv.instance_stats(x.to(DEV))
+        xd = x.double()
+        m_ref = xd.mean(dim=(2, 3)); r_ref = (xd.var(dim=(2, 3), unbiased=False) + 1e-5).rsqrt()
+        assert float((mean.double().cpu() - m_ref).abs().max()) < 1e-6 * max(1.7, offset)      # mean error relative to the data scale
+        assert rel_err(rstd, r_ref) < (1e-5 if offset == 0 else 2e-4)
