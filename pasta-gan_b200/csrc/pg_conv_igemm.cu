@@ -51,6 +51,7 @@ struct ConvParams {
     const float* sp_x; const float* sp_mean; const float* sp_rstd; int spade;   // SPADE epilogue: y = act((x-mean)*rstd*(1+gamma)+beta)*gain
     long long* dbg;            // optional per-CTA phase timestamps (pg_debug_set_buffer), NULL in production
     int pipe, ldmode, dbgmode;          // converter knobs (tuning): register double-buffering on/off, L1::no_allocate loads
+    int im2col; uint32_t kk_magic, ks_magic;   // im2col mode: real kernel size (0 = off); ceil(2^32 / k^2), ceil(2^32 / k)
     int vec2; uint32_t w_magic;   // aligned 8-byte loader (see the converter section); ceil(2^32 / W)
     uint32_t pw_magic;         // ceil(2^32 / PW): q / PW == umulhi(q, pw_magic) for the strip positions that occur
 };
@@ -138,7 +139,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
 // up2 != 0: the 3x3 weights are first convolved with the 4x4 FIR (gain 4) into a 6x6 composite and split into the four
 // output-parity 3x3 kernels of the polyphase form; virtual channel v = phase * Cout + o.
 struct PackParams {
-    const float* w; const float* fir; void* out; int Cout, Cin, ks, BN, nchunks, ntaps, ntiles, flip_weight, fmt, up2, down2; float w_scale;
+    const float* w; const float* fir; void* out; int Cout, Cin, ks, BN, nchunks, ntaps, ntiles, flip_weight, fmt, up2, down2, im2col; float w_scale;
 };
 
 __device__ float composite_tap(const PackParams& p, int o, int c, int a, int b, int th, int tw) {
@@ -192,6 +193,13 @@ __global__ void conv_prepack_kernel(PackParams p) {
             if (v < p.Cout && c < 4 * p.Cin) {
                 const int a = c / (2 * p.Cin), rem = c - a * 2 * p.Cin;          // virtual channel = a * 2Cin + 2 * c_real + b
                 val = down2_tap(p, v, rem >> 1, a, rem & 1, tap / 3, tap % 3);
+            }
+        } else if (p.im2col) {
+            // one "tap", Cin * ks * ks virtual channels in the weight tensor's memory order; a true convolution mirrors the taps
+            const int kk = p.ks * p.ks;
+            if (v < p.Cout && c < p.Cin * kk) {
+                const int cr = c / kk, r2 = c - cr * kk;
+                val = p.w[(size_t)(v * p.Cin + cr) * kk + (p.flip_weight ? r2 : kk - 1 - r2)];
             }
         } else if (v < nvirt && c < p.Cin) {
             const int kh = tap / p.ks, kw = tap % p.ks;
@@ -320,6 +328,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
     uint64_t* a_full = bars, *a_empty = bars + p.SA, *b_full = bars + 2 * p.SA, *b_empty = bars + 2 * p.SA + p.SB;
     uint64_t* acc_full = bars + 2 * p.SA + 2 * p.SB;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+    int2* s_tab = reinterpret_cast<int2*>(acc_full + 2);    // folded-tap mode: per virtual channel (element offset, (dh << 16) | (dw & 0xffff))
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < p.SA; i++) { mbar_init(smem_u32(&a_full[i]), kConvWarps); mbar_init(smem_u32(&a_empty[i]), 1); }
@@ -333,7 +342,15 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
     }
     // per-sample input scale: style * in_gain (1 * in_gain for plain convs); zero for padded channels
     for (int c = threadIdx.x; c < cin_pad; c += kConvThreads)
-        s_style[c] = (c < p.Cin) ? (p.styles ? (p.down2 ? p.styles[(size_t)n * p.cin_real + ((c % (2 * p.cin_real)) >> 1)] : p.styles[(size_t)n * p.Cin + c]) : 1.f) * p.in_gain : 0.f;
+        s_style[c] = (c < p.Cin) ? (p.styles ? (p.down2 ? p.styles[(size_t)n * p.cin_real + ((c % (2 * p.cin_real)) >> 1)] : p.im2col ? p.styles[(size_t)n * p.cin_real + c / (p.im2col * p.im2col)] : p.styles[(size_t)n * p.Cin + c]) : 1.f) * p.in_gain : 0.f;
+    if (p.im2col) {
+        const int ks = p.im2col, kk = ks * ks, pad = ks >> 1;
+        for (int c = threadIdx.x; c < cin_pad; c += kConvThreads) {
+            const int cr = c / kk, r2 = c - cr * kk, kh = r2 / ks, kw = r2 - kh * ks;
+            s_tab[c] = c < p.Cin ? make_int2(cr * HW + (kh - pad) * p.W + (kw - pad), ((kh - pad) << 16) | ((kw - pad) & 0xffff))
+                                 : make_int2(0, 0x7fff0000);                                    // padding channel: row offset out of range
+        }
+    }
     // epilogue constants with the output gain folded in (relu / lrelu / linear are positively homogeneous, gain > 0)
     for (int j = threadIdx.x; j < p.BN; j += kConvThreads) {
         const int v = jn * p.BN + j;
@@ -502,7 +519,18 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
                 const int c0 = ci * kKC + (tt & 1) * 8;
 #pragma unroll
                 for (int i = 0; i < 8; i++) v[i] = 0.f;
-                if (!p.down2) {
+                if (p.im2col) {
+                    if (ok) {
+                        const int2* tab = s_tab + c0;
+                        const float* src = xn + h * p.W + w;
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const int2 t = tab[i];
+                            const int hh = h + (t.y >> 16), ww = w + (int)(short)(t.y & 0xffff);
+                            if ((unsigned)hh < (unsigned)p.H && (unsigned)ww < (unsigned)p.W) v[i] = __ldg(src + t.x);
+                        }
+                    }
+                } else if (!p.down2) {
                     const float* src = chan_base(c0) + h * p.W + w;
                     if (ok) {
                         if (c0 + 8 <= p.Cin) {
@@ -708,7 +736,7 @@ static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int k
     pl.a_stage = (uint32_t)pl.PA * 32u;                        // 2 planes x 16 B per position
     pl.b_tile = (uint32_t)bn * 32u;
     pl.b_stage = pl.b_tile * pl.ntaps;
-    const size_t fixed = (size_t)pl.nchunks * kKC * 4 + (size_t)bn * 8 + 96 * 8;
+    const size_t fixed = (size_t)pl.nchunks * kKC * 4 + (size_t)bn * 8 + 96 * 8 + ((ks == 1 && Cin <= 160) ? 160 * 8 : 0);   // last term: folded-tap offset table
     pl.tps = (ks == 3) ? 3 : 1;
     pl.b_slot = pl.b_tile * pl.tps;
     size_t budget = pair ? 100 * 1024 : 200 * 1024;
@@ -735,15 +763,22 @@ static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int k
 static long long* g_conv_dbg = nullptr;
 extern "C" void pg_debug_set_buffer(void* buf) { g_conv_dbg = (long long*)buf; }
 
+// Small-K layers (first layers: 3 -> 64 channels, 7x7 or 3x3): the k x k taps are folded into the GEMM K dimension ("im2col" virtual channels
+// v = c * k * k + kh * k + kw, i.e. the weight tensor's own memory order) and the layer runs as a 1x1 convolution over Cin * k * k channels,
+// instead of k * k shifted MMAs over a 16-channel chunk that is mostly padding.
+static bool use_im2col(int Cin, int ksize, int up) { return up == 1 && ksize > 1 && Cin * ksize * ksize <= 160; }
+
 extern "C" int64_t pg_conv2d_igemm_workspace_bytes(int32_t Cin, int32_t Cout, int32_t ksize, int32_t up) {
     pg::ConvPlan pl;
-    if (pg::make_plan(pl, 1, up == PG_CONV_DOWN2 ? 4 * Cin : Cin, Cout, 8, 8, ksize, up == 2) != PG_OK) return -1;
+    const bool im2col = use_im2col(Cin, ksize, up);
+    if (pg::make_plan(pl, 1, up == PG_CONV_DOWN2 ? 4 * Cin : (im2col ? Cin * ksize * ksize : Cin), Cout, 8, 8, im2col ? 1 : ksize, up == 2) != PG_OK) return -1;
     return (int64_t)pl.ntiles_n * pl.nchunks * pl.b_stage;
 }
 
 static int conv_validate(int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t ksize, int32_t up, int32_t operand_format) {
     using namespace pg;
-    PG_REQUIRE(ksize == 1 || ksize == 3, "conv2d_igemm: kernel size must be 1 or 3 (got %d)", ksize);
+    PG_REQUIRE(ksize == 1 || ksize == 3 || (ksize % 2 == 1 && ksize <= 7 && use_im2col(Cin, ksize, up)),
+               "conv2d_igemm: kernel size must be 1 or 3, or odd <= 7 with Cin * k * k <= 160 (got k = %d, Cin = %d)", ksize, Cin);
     PG_REQUIRE(up == 1 || ((up == 2 || up == PG_CONV_DOWN2) && ksize == 3), "conv2d_igemm: resample must be 1, 2 (up) or PG_CONV_DOWN2, the latter two with a 3x3 kernel");
     PG_REQUIRE(up != PG_CONV_DOWN2 || (Cin % 16 == 0 && H % 2 == 0 && W % 2 == 0), "conv2d_igemm: down-2 needs Cin %% 16 == 0 and even H, W");
     PG_REQUIRE(N >= 0 && Cin >= 1 && Cout >= 1 && H >= 1 && W >= 1, "conv2d_igemm: bad sizes");
@@ -761,13 +796,14 @@ extern "C" int pg_conv2d_igemm_prepack(const float* w, const float* fir, float w
     PG_REQUIRE(w && workspace, "conv2d_igemm: w and workspace must be device pointers");
     const bool down2 = up == PG_CONV_DOWN2;
     ConvPlan pl;
-    rc = make_plan(pl, 1, down2 ? 4 * Cin : Cin, Cout, 8, 8, ksize, up == 2);
+    const bool im2col = use_im2col(Cin, ksize, up);
+    rc = make_plan(pl, 1, down2 ? 4 * Cin : (im2col ? Cin * ksize * ksize : Cin), Cout, 8, 8, im2col ? 1 : ksize, up == 2);
     if (rc != PG_OK) return rc;
     const int64_t need = (int64_t)pl.ntiles_n * pl.nchunks * pl.b_stage;
     PG_REQUIRE(workspace_bytes >= need, "conv2d_igemm: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
     PackParams pp;
     pp.w = w; pp.fir = fir; pp.out = workspace; pp.Cout = Cout; pp.Cin = Cin; pp.ks = ksize; pp.BN = pl.BN; pp.nchunks = pl.nchunks;
-    pp.ntaps = pl.ntaps; pp.ntiles = pl.ntiles_n; pp.flip_weight = flip_weight ? 1 : 0; pp.fmt = operand_format; pp.up2 = up == 2; pp.down2 = down2; pp.w_scale = w_scale;
+    pp.ntaps = pl.ntaps; pp.ntiles = pl.ntiles_n; pp.flip_weight = flip_weight ? 1 : 0; pp.fmt = operand_format; pp.up2 = up == 2; pp.down2 = down2; pp.w_scale = w_scale; pp.im2col = im2col;
     const size_t pack_total = (size_t)need / 2;
     int pblocks = (int)((pack_total + 255) / 256);
     if (pblocks > kNumSMs * 16) pblocks = kNumSMs * 16;
@@ -795,6 +831,9 @@ static int conv_run_impl(const float* x, const void* wpack, const float* styles,
     PG_REQUIRE(!down2 || ((uintptr_t)x & 7) == 0, "conv2d_igemm: down-2 needs an 8-byte aligned input");
     const int hin = H, win = W, cin_real = Cin;
     if (down2) { H /= 2; W /= 2; Cin *= 4; }                      // the GEMM runs over the space-to-depth view at the output resolution
+    const bool im2col = use_im2col(Cin, ksize, up);
+    const int ks_real = ksize;
+    if (im2col) { Cin *= ksize * ksize; ksize = 1; }              // taps folded into K: a 1x1 convolution over Cin * k * k virtual channels
     ConvPlan pl;
     rc = make_plan(pl, N, Cin, Cout, H, W, ksize, up == 2);
     if (rc != PG_OK) return rc;
@@ -802,7 +841,11 @@ static int conv_run_impl(const float* x, const void* wpack, const float* styles,
     ConvParams p;
     p.down2 = down2; p.cin_real = cin_real; p.hin = hin; p.win = win;
     PG_REQUIRE(!x2 || (!down2 && Cin1 > 0 && Cin1 < Cin && Cin1 % 8 == 0), "conv2d_igemm: the split input needs 0 < Cin1 < Cin, Cin1 %% 8 == 0 and no down-sampling");
-    p.x2 = x2; p.cin1 = x2 ? Cin1 : Cin; p.residual = residual;
+    PG_REQUIRE(!(im2col && x2), "conv2d_igemm: the split input is not available for folded-tap (small Cin) layers");
+    p.x2 = x2; p.cin1 = x2 ? Cin1 : (im2col ? cin_real : Cin); p.residual = residual;
+    p.im2col = im2col ? ks_real : 0;
+    p.kk_magic = (uint32_t)((0x100000000ull + (uint64_t)(ks_real * ks_real) - 1) / (uint64_t)(ks_real * ks_real));
+    p.ks_magic = (uint32_t)((0x100000000ull + (uint64_t)ks_real - 1) / (uint64_t)ks_real);
     p.x = x; p.wpack = wpack; p.styles = styles; p.dcoefs = dcoefs; p.noise = noise; p.bias = bias; p.y = y;
     p.noise_bstride = noise_batch_stride;
     p.N = N; p.Cin = Cin; p.Cout = pl.nvirt; p.H = H; p.W = W; p.ks = ksize;
@@ -819,7 +862,7 @@ static int conv_run_impl(const float* x, const void* wpack, const float* styles,
     p.pipe = env_int("PASTA_B200_CONV_PIPE", 0); p.ldmode = env_int("PASTA_B200_CONV_LDMODE", 0); p.dbgmode = env_int("PASTA_B200_CONV_DBGMODE", 0);
     p.pw_magic = (uint32_t)((0x100000000ull + (uint64_t)pl.PW - 1) / (uint64_t)pl.PW);
     p.w_magic = (uint32_t)((0x100000000ull + (uint64_t)W - 1) / (uint64_t)W);
-    p.vec2 = (!down2 && W % 2 == 0 && ((uintptr_t)x & 7) == 0 && ((uintptr_t)x2 & 7) == 0 && env_int("PASTA_B200_CONV_VEC2", 1)) ? 1 : 0;
+    p.vec2 = (!down2 && !im2col && W % 2 == 0 && ((uintptr_t)x & 7) == 0 && ((uintptr_t)x2 & 7) == 0 && env_int("PASTA_B200_CONV_VEC2", 1)) ? 1 : 0;
     const bool scale = styles != nullptr || in_act != PG_ACT_LINEAR || in_gain != 1.f;
     auto kern = scale ? conv_igemm_kernel<true> : conv_igemm_kernel<false>;
     PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));

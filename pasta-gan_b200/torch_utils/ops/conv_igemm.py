@@ -24,9 +24,10 @@ def supported(x, w, up=1, down=1, groups=1, f=None, padding=None, flip_filter=Fa
         return False
     if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad):
         return False
-    if groups != 1 or down not in (1, 2) or up not in (1, 2) or w.shape[2] != w.shape[3] or w.shape[2] not in (1, 3):
-        return False
     k = int(w.shape[2])
+    folded = up == 1 and down == 1 and k in (3, 5, 7) and int(w.shape[1]) * k * k <= 160     # small-Cin layers: taps folded into the GEMM K dimension
+    if groups != 1 or down not in (1, 2) or up not in (1, 2) or w.shape[2] != w.shape[3] or (k not in (1, 3) and not folded):
+        return False
     if down == 2 and (up != 1 or k != 3 or f is None or f.ndim != 2 or tuple(f.shape) != (4, 4) or flip_filter or
                       x.shape[1] % 16 != 0 or x.shape[2] % 2 or x.shape[3] % 2):
         return False

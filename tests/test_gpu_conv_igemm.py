@@ -26,6 +26,8 @@ PLAIN = [
     (1, 64, 64, 64, 64, 1), (2, 48, 24, 20, 28, 3), (1, 3, 64, 33, 31, 3), (2, 42, 64, 16, 16, 1),
     (1, 512, 512, 4, 4, 3), (1, 512, 512, 16, 16, 3), (1, 256, 128, 64, 64, 3), (2, 64, 3, 32, 32, 1),
     (1, 192, 128, 40, 40, 1), (1, 64, 64, 128, 128, 3), (3, 20, 300, 12, 12, 3),
+    # small Cin: taps folded into the GEMM K dimension (7x7 / 5x5 / 3x3)
+    (2, 3, 64, 40, 36, 7), (1, 3, 64, 256, 256, 7), (2, 6, 32, 17, 19, 5), (1, 2, 16, 8, 8, 7), (2, 17, 48, 24, 24, 3),
 ]
 
 
