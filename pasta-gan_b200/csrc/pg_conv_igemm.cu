@@ -50,7 +50,7 @@ struct ConvParams {
     int down2, cin_real, hin, win;   // down-2 mode: the A operand is the 4-plane space-to-depth view of x [N,cin_real,hin,win]
     const float* sp_x; const float* sp_mean; const float* sp_rstd; int spade;   // SPADE epilogue: y = act((x-mean)*rstd*(1+gamma)+beta)*gain
     long long* dbg;            // optional per-CTA phase timestamps (pg_debug_set_buffer), NULL in production
-    int pipe, ldmode, dbgmode;          // converter knobs (tuning): register double-buffering on/off, L1::no_allocate loads
+    int pipe, ldmode, dbgmode, prefetch;          // converter knobs (tuning): register double-buffering on/off, L1::no_allocate loads
     int im2col; uint32_t kk_magic, ks_magic;   // im2col mode: real kernel size (0 = off); ceil(2^32 / k^2), ceil(2^32 / k)
     int vec2; uint32_t w_magic;   // aligned 8-byte loader (see the converter section); ceil(2^32 / W)
     uint32_t pw_magic;         // ceil(2^32 / PW): q / PW == umulhi(q, pw_magic) for the strip positions that occur
@@ -273,17 +273,21 @@ __device__ __forceinline__ void mma_issue_loop(const ConvParams& p, uint32_t a_b
 // Converter task stream of one warp: slots (chunk, idx), idx < tpw, in register batches of BATCH tasks of TREGS floats.  pipelined: the loads of
 // batch k + 1 are issued before batch k is converted and stored (two batches of registers); otherwise one batch per memory round trip.
 template <int TREGS, int BATCH, class Load, class Store>
-__device__ __forceinline__ void stream_tasks(Load&& load_task, Store&& store_task, const int tpw, const int nchunks, const bool pipelined) {
+__device__ __forceinline__ void stream_tasks(Load&& load_task, Store&& store_task, const int tpw, const int nchunks, const bool pipelined,
+                                             const bool timed, long long& t_issue, long long& t_store) {
     float va[BATCH][TREGS], vb[BATCH][TREGS];
     int l_ci = 0, l_idx = 0, c_ci = 0, c_idx = 0;          // load cursor, convert/store cursor
     auto advance = [&](int& ci, int& idx) { if (++idx == tpw) { idx = 0; ci++; } };
 #pragma unroll
     for (int u = 0; u < BATCH; u++) { load_task(va[u], l_ci, l_idx); advance(l_ci, l_idx); }
     while (!pipelined && c_ci < nchunks) {
+        const long long t0 = timed ? clock64() : 0;
 #pragma unroll
         for (int u = 0; u < BATCH; u++) { store_task(va[u], c_ci, c_idx); advance(c_ci, c_idx); }
+        const long long t1 = timed ? clock64() : 0;
 #pragma unroll
         for (int u = 0; u < BATCH; u++) { load_task(va[u], l_ci, l_idx); advance(l_ci, l_idx); }
+        if (timed) { t_store += t1 - t0; t_issue += clock64() - t1; }
     }
     while (c_ci < nchunks) {
 #pragma unroll
@@ -423,7 +427,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
         const int nchunks = p.nchunks;
         const int q0 = m0 - halo;                              // strip position of staged slot 0
         int s_st = 0; uint32_t s_ph = 0;                       // store cursor: stage / parity of the chunk being written
-        long long wait_e = 0;
+        long long wait_e = 0, t_issue = 0, t_store = 0;
         auto stage_begin = [&]() {
             const long long t0 = p.dbg ? clock64() : 0;
             mbar_wait(smem_u32(&a_empty[s_st]), s_ph ^ 1);
@@ -463,7 +467,23 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
             const int ntasks = nseg * 2;                                        // (segment of 32 pairs, plane)
             const int tpw = ntasks ? (ntasks + kConvWarps - 1) / kConvWarps : 1;
             const int dpitch = p.PW - p.W;
+            // L2 prefetch of the activation rows of a later chunk (one bulk prefetch per channel, lanes 0..15 of converter warp 0): the LSU can keep
+            // only a limited number of L1 misses in flight per SM, so what bounds the converters is (misses in flight) / latency -- with the
+            // lines already in L2 the same window moves ~3x the bytes that it does at DRAM latency.
+            const int pf_dist = p.prefetch;
+            auto prefetch_chunk = [&](int ci) {
+                const int c = ci * kKC + lane;
+                if (ci < nchunks && lane < kKC && c < p.Cin && e_hi > e_lo) {
+                    const uintptr_t a0 = (uintptr_t)(chan_base(c) + e_lo) & ~(uintptr_t)15;
+                    const uintptr_t a1 = ((uintptr_t)(chan_base(c) + e_hi) + 15) & ~(uintptr_t)15;
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((uint32_t)(a1 - a0)) : "memory");
+                }
+            };
             auto load_task = [&](float (&v)[16], int ci, int idx) {
+                if (cw == 0 && idx == 0 && pf_dist > 0) {
+                    if (ci == 0) for (int d = 1; d < pf_dist; d++) prefetch_chunk(d);
+                    prefetch_chunk(ci + pf_dist);
+                }
                 const int tt = cw + idx * kConvWarps;
                 const int g = g_lo + (tt >> 1) * 32 + lane;
                 const bool ok = ci < nchunks && tt < ntasks && g < g_hi && !(p.dbgmode & 1);
@@ -506,7 +526,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
                 }
                 if (idx == tpw - 1) stage_end();
             };
-            stream_tasks<16, 2>(load_task, store_task, tpw, nchunks, p.pipe != 0);
+            stream_tasks<16, 2>(load_task, store_task, tpw, nchunks, p.pipe != 0, p.dbg != nullptr, t_issue, t_store);
         } else {
             const int ntasks = (p.PA / 32) * 2;                       // (group of 32 strip positions, plane)
             const int tpw = (ntasks + kConvWarps - 1) / kConvWarps;   // stream slots per warp per chunk (trailing ones may be void)
@@ -562,9 +582,9 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
                 }
                 if (idx == tpw - 1) stage_end();
             };
-            stream_tasks<8, 4>(load_task, store_task, tpw, nchunks, p.pipe != 0);
+            stream_tasks<8, 4>(load_task, store_task, tpw, nchunks, p.pipe != 0, p.dbg != nullptr, t_issue, t_store);
         }
-        if (cw == 0 && lane == 0) { PG_TS(6); PG_PUT(10, wait_e); }
+        if (cw == 0 && lane == 0) { PG_TS(6); PG_PUT(10, wait_e); PG_PUT(14, t_issue); PG_PUT(15, t_store); }
         // ===================== epilogue (same warps) =====================
         mbar_wait(smem_u32(acc_full), 0);
         tc_fence_after();
@@ -726,6 +746,17 @@ static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int k
         const long long ctas = (long long)N * ((pl.Lp + 128 * cand - 1) / (128 * cand)) * pl.ntiles_n;
         if (ctas >= 2 * kNumSMs * (pair ? 2 : 1) || cand == 1) { nacc = cand; break; }
     }
+    if (!pair && max_acc >= 2 && ks == 3) {
+        // wide tiles (one CTA per SM): pick the strip length by (fill of the last wave) x (useful fraction of the staged strip); measured on
+        // 256->256 @64^2 (2 accumulators: 80 us vs 103), 512->512 @32^2 (1: 84 vs 125) and 512->256 up-2 @32^2 (1: 189 vs 230)
+        double best = -1.0;
+        for (int cand = 1; cand <= (max_acc < 4 ? max_acc : 4); cand <<= 1) {
+            const long long ctas = (long long)N * ((pl.Lp + 128 * cand - 1) / (128 * cand)) * pl.ntiles_n;
+            const double wave_fill = (double)ctas / (double)(((ctas + kNumSMs - 1) / kNumSMs) * kNumSMs);
+            const double useful = 128.0 * cand / (128.0 * cand + 2.0 * pl.PW + 2.0);
+            if (wave_fill * useful > best) { best = wave_fill * useful; nacc = cand; }
+        }
+    }
     if (force_nacc && force_nacc * bn <= 512) nacc = force_nacc;
     while (nacc > 1 && 128 * (nacc - 1) >= pl.Lp) nacc--;
     pl.NACC = nacc;
@@ -859,7 +890,7 @@ static int conv_run_impl(const float* x, const void* wpack, const float* styles,
     if (p.spade) PG_REQUIRE(pl.ntiles_n == 1 && pl.BN == Cout && (Cout / 2) % 16 == 0 && up == 1 && sp_mean && sp_rstd,
                             "conv2d_igemm_spade: gamma and beta (2C <= 256 channels, C %% 16 == 0) must share one N tile");
     p.dbg = g_conv_dbg;
-    p.pipe = env_int("PASTA_B200_CONV_PIPE", 0); p.ldmode = env_int("PASTA_B200_CONV_LDMODE", 0); p.dbgmode = env_int("PASTA_B200_CONV_DBGMODE", 0);
+    p.pipe = env_int("PASTA_B200_CONV_PIPE", 0); p.ldmode = env_int("PASTA_B200_CONV_LDMODE", 0); p.dbgmode = env_int("PASTA_B200_CONV_DBGMODE", 0); p.prefetch = env_int("PASTA_B200_CONV_PREFETCH", 0);
     p.pw_magic = (uint32_t)((0x100000000ull + (uint64_t)pl.PW - 1) / (uint64_t)pl.PW);
     p.w_magic = (uint32_t)((0x100000000ull + (uint64_t)W - 1) / (uint64_t)W);
     p.vec2 = (!down2 && !im2col && W % 2 == 0 && ((uintptr_t)x & 7) == 0 && ((uintptr_t)x2 & 7) == 0 && env_int("PASTA_B200_CONV_VEC2", 1)) ? 1 : 0;

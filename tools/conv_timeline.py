@@ -27,8 +27,9 @@ t = buf.view(-1, 16).cpu()
 t = t[t[:, 0] != 0].double()
 names = ['prologue (start -> setup sync)', 'fill (setup -> first A stage ready at the MMA thread)', 'main loop (first A ready -> last MMA issued)',
          'converters done (setup -> last stage stored)', 'accumulator ready seen by epilogue (setup -> acc_full)', 'epilogue (acc_full -> stores done)', 'total',
-         'MMA thread: cycles waiting on A stages', 'MMA thread: cycles waiting on B slots', 'converter warp 0: cycles waiting on free A stages']
-vals = [t[:, 1] - t[:, 0], t[:, 2] - t[:, 1], t[:, 3] - t[:, 2], t[:, 6] - t[:, 1], t[:, 4] - t[:, 1], t[:, 5] - t[:, 4], t[:, 5] - t[:, 0], t[:, 8], t[:, 9], t[:, 10]]
+         'MMA thread: cycles waiting on A stages', 'MMA thread: cycles waiting on B slots', 'converter warp 0: cycles waiting on free A stages',
+         'converter warp 0: cycles issuing loads (non-pipelined mode)', 'converter warp 0: cycles converting + storing incl. waiting for the loaded data and free stages']
+vals = [t[:, 1] - t[:, 0], t[:, 2] - t[:, 1], t[:, 3] - t[:, 2], t[:, 6] - t[:, 1], t[:, 4] - t[:, 1], t[:, 5] - t[:, 4], t[:, 5] - t[:, 0], t[:, 8], t[:, 9], t[:, 10], t[:, 14], t[:, 15]]
 print(f'{t.shape[0]} CTAs; cycles (median / p10 / p90)')
 for nme, v in zip(names, vals):
     q = torch.quantile(v, torch.tensor([0.5, 0.1, 0.9], dtype=torch.float64))
