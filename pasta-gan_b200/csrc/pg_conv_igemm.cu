@@ -50,7 +50,7 @@ struct ConvParams {
     int down2, cin_real, hin, win;   // down-2 mode: the A operand is the 4-plane space-to-depth view of x [N,cin_real,hin,win]
     const float* sp_x; const float* sp_mean; const float* sp_rstd; int spade;   // SPADE epilogue: y = act((x-mean)*rstd*(1+gamma)+beta)*gain
     long long* dbg;            // optional per-CTA phase timestamps (pg_debug_set_buffer), NULL in production
-    int pipe, ldmode, dbgmode, prefetch;          // converter knobs (tuning): register double-buffering on/off, L1::no_allocate loads
+    int pipe, ldmode, dbgmode, lean;          // converter knobs (tuning): register double-buffering on/off, L1::no_allocate loads
     int im2col; uint32_t kk_magic, ks_magic;   // im2col mode: real kernel size (0 = off); ceil(2^32 / k^2), ceil(2^32 / k)
     int vec2; uint32_t w_magic;   // aligned 8-byte loader (see the converter section); ceil(2^32 / W)
     uint32_t pw_magic;         // ceil(2^32 / PW): q / PW == umulhi(q, pw_magic) for the strip positions that occur
@@ -302,6 +302,90 @@ __device__ __forceinline__ void stream_tasks(Load&& load_task, Store&& store_tas
     }
 }
 
+// Lean A converter for the aligned 8-byte loader.  Everything that depends only on (warp, lane, task slot) -- the element offset of the lane's
+// pair inside a channel plane and the two shared-memory slots it lands on -- is computed once per CTA; per chunk only the channel base moves.
+// A warp owns task slots idx = r * PER + u (task = cw + 8 * idx: 32 pairs of one 8-channel plane; all of a warp's tasks share the plane cw & 1),
+// processed in ROUNDS register batches of PER tasks: the loads of a batch are issued before the stage is waited for.
+template <bool SCALE, int PER, int ROUNDS>
+__device__ __forceinline__ void convert_vec2(const ConvParams& p, const float* xn, const float* xn2, const int HW, const int cw, const int lane,
+                                             const int g_lo, const int g_hi, const int ntasks, const int q0, uint8_t* a_base, const float* s_style,
+                                             uint64_t* a_full, uint64_t* a_empty, long long& wait_e) {
+    constexpr int NS = PER * ROUNDS;
+    const int plane = cw & 1;
+    const bool swap = (lane >> 2) & 1;          // lanes sit 32 B apart in the stage: lanes 4..7 of each group of 8 write their second slot first
+    const int dpitch = p.PW - p.W;
+    int goff[NS]; uint32_t sA[NS], sB[NS];
+#pragma unroll
+    for (int idx = 0; idx < NS; idx++) {
+        const int tt = cw + idx * kConvWarps;
+        const int g = g_lo + (tt >> 1) * 32 + lane;
+        const bool ok = tt < ntasks && g < g_hi;
+        const int e = 2 * g;
+        const int h = (int)__umulhi((uint32_t)e, p.w_magic);
+        const int s0 = e + h * dpitch - q0;                          // staged slot of the first element; the second is s0 + 1 (same row)
+        const int s1st = swap ? s0 + 1 : s0, s2nd = swap ? s0 : s0 + 1;
+        goff[idx] = (ok && !(p.dbgmode & 1)) ? e : -1;
+        const bool st_ok = ok && !(p.dbgmode & 2);
+        sA[idx] = (st_ok && s1st >= 0 && s1st < p.PA) ? (uint32_t)((plane * p.PA + s1st) * 16) : 0xffffffffu;
+        sB[idx] = (st_ok && s2nd >= 0 && s2nd < p.PA) ? (uint32_t)((plane * p.PA + s2nd) * 16) : 0xffffffffu;
+    }
+    const bool has_in_act = p.in_act != PG_ACT_LINEAR;
+    const float in_slope = (p.in_act == PG_ACT_RELU) ? 0.f : p.in_alpha;
+    const int nchunks = p.nchunks;
+    int st = 0; uint32_t ph = 0;
+    for (int ci = 0; ci < nchunks; ci++) {
+        const int c0 = ci * kKC + plane * 8;
+        const int nval = p.Cin - c0;                                  // channels of this group that exist (>= 8: all)
+        const float* cb = (c0 < p.cin1 ? xn : xn2) + (size_t)c0 * HW;
+        uint8_t* stage = a_base + (size_t)st * p.a_stage_bytes;
+#pragma unroll
+        for (int r = 0; r < ROUNDS; r++) {
+            float v[PER][16];
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                const int off = goff[r * PER + u];
+#pragma unroll
+                for (int i = 0; i < 16; i++) v[u][i] = 0.f;
+                if (off >= 0) {
+                    const float* src = cb + off;
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+                        if (i < nval) { const float2 t = __ldg(reinterpret_cast<const float2*>(src + (size_t)i * HW)); v[u][i] = t.x; v[u][8 + i] = t.y; }
+                }
+            }
+            if (r == 0) {
+                const long long t0 = p.dbg ? clock64() : 0;
+                mbar_wait(smem_u32(&a_empty[st]), ph ^ 1);
+                if (p.dbg) wait_e += clock64() - t0;
+            }
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                const uint32_t a1 = sA[r * PER + u], a2 = sB[r * PER + u];
+                if ((a1 & a2) == 0xffffffffu) continue;
+                if (SCALE) {
+                    const float* sc = s_style + c0;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        float a = v[u][i], b = v[u][8 + i];
+                        if (has_in_act) { a = fmaxf(a, 0.f) + in_slope * fminf(a, 0.f); b = fmaxf(b, 0.f) + in_slope * fminf(b, 0.f); }
+                        v[u][i] = a * sc[i]; v[u][8 + i] = b * sc[i];
+                    }
+                }
+                uint4 lo, hi;
+                lo.x = pack2(v[u][0], v[u][1], p.fmt); lo.y = pack2(v[u][2], v[u][3], p.fmt); lo.z = pack2(v[u][4], v[u][5], p.fmt); lo.w = pack2(v[u][6], v[u][7], p.fmt);
+                hi.x = pack2(v[u][8], v[u][9], p.fmt); hi.y = pack2(v[u][10], v[u][11], p.fmt); hi.z = pack2(v[u][12], v[u][13], p.fmt); hi.w = pack2(v[u][14], v[u][15], p.fmt);
+                const uint4 d1 = swap ? hi : lo, d2 = swap ? lo : hi;
+                if (a1 != 0xffffffffu) *reinterpret_cast<uint4*>(stage + a1) = d1;
+                if (a2 != 0xffffffffu) *reinterpret_cast<uint4*>(stage + a2) = d2;
+            }
+        }
+        fence_proxy_async();                               // generic-proxy stores -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&a_full[st]));
+        if (++st == p.SA) { st = 0; ph ^= 1; }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- main kernel
 // SCALE: the A operand needs a per-channel scale and/or an input activation (modulated / SPADE layers); plain layers skip both.
 template <bool SCALE>
@@ -467,23 +551,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
             const int ntasks = nseg * 2;                                        // (segment of 32 pairs, plane)
             const int tpw = ntasks ? (ntasks + kConvWarps - 1) / kConvWarps : 1;
             const int dpitch = p.PW - p.W;
-            // L2 prefetch of the activation rows of a later chunk (one bulk prefetch per channel, lanes 0..15 of converter warp 0): the LSU can keep
-            // only a limited number of L1 misses in flight per SM, so what bounds the converters is (misses in flight) / latency -- with the
-            // lines already in L2 the same window moves ~3x the bytes that it does at DRAM latency.
-            const int pf_dist = p.prefetch;
-            auto prefetch_chunk = [&](int ci) {
-                const int c = ci * kKC + lane;
-                if (ci < nchunks && lane < kKC && c < p.Cin && e_hi > e_lo) {
-                    const uintptr_t a0 = (uintptr_t)(chan_base(c) + e_lo) & ~(uintptr_t)15;
-                    const uintptr_t a1 = ((uintptr_t)(chan_base(c) + e_hi) + 15) & ~(uintptr_t)15;
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((uint32_t)(a1 - a0)) : "memory");
-                }
-            };
             auto load_task = [&](float (&v)[16], int ci, int idx) {
-                if (cw == 0 && idx == 0 && pf_dist > 0) {
-                    if (ci == 0) for (int d = 1; d < pf_dist; d++) prefetch_chunk(d);
-                    prefetch_chunk(ci + pf_dist);
-                }
                 const int tt = cw + idx * kConvWarps;
                 const int g = g_lo + (tt >> 1) * 32 + lane;
                 const bool ok = ci < nchunks && tt < ntasks && g < g_hi && !(p.dbgmode & 1);
@@ -526,7 +594,14 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
                 }
                 if (idx == tpw - 1) stage_end();
             };
-            stream_tasks<16, 2>(load_task, store_task, tpw, nchunks, p.pipe != 0, p.dbg != nullptr, t_issue, t_store);
+#define PG_CONVERT(PER_, ROUNDS_) convert_vec2<SCALE, PER_, ROUNDS_>(p, xn, xn2, HW, cw, lane, g_lo, g_hi, ntasks, q0, a_base, s_style, a_full, a_empty, wait_e)
+            if (p.lean && tpw <= 6) {
+                if (tpw <= 1) PG_CONVERT(1, 1); else if (tpw == 2) PG_CONVERT(2, 1); else if (tpw == 3) PG_CONVERT(3, 1);
+                else if (tpw == 4) PG_CONVERT(2, 2); else PG_CONVERT(3, 2);
+            } else {
+                stream_tasks<16, 2>(load_task, store_task, tpw, nchunks, p.pipe != 0, p.dbg != nullptr, t_issue, t_store);
+            }
+#undef PG_CONVERT
         } else {
             const int ntasks = (p.PA / 32) * 2;                       // (group of 32 strip positions, plane)
             const int tpw = (ntasks + kConvWarps - 1) / kConvWarps;   // stream slots per warp per chunk (trailing ones may be void)
@@ -890,7 +965,7 @@ static int conv_run_impl(const float* x, const void* wpack, const float* styles,
     if (p.spade) PG_REQUIRE(pl.ntiles_n == 1 && pl.BN == Cout && (Cout / 2) % 16 == 0 && up == 1 && sp_mean && sp_rstd,
                             "conv2d_igemm_spade: gamma and beta (2C <= 256 channels, C %% 16 == 0) must share one N tile");
     p.dbg = g_conv_dbg;
-    p.pipe = env_int("PASTA_B200_CONV_PIPE", 0); p.ldmode = env_int("PASTA_B200_CONV_LDMODE", 0); p.dbgmode = env_int("PASTA_B200_CONV_DBGMODE", 0); p.prefetch = env_int("PASTA_B200_CONV_PREFETCH", 0);
+    p.pipe = env_int("PASTA_B200_CONV_PIPE", 0); p.ldmode = env_int("PASTA_B200_CONV_LDMODE", 0); p.dbgmode = env_int("PASTA_B200_CONV_DBGMODE", 0); p.lean = env_int("PASTA_B200_CONV_LEAN", 1);
     p.pw_magic = (uint32_t)((0x100000000ull + (uint64_t)pl.PW - 1) / (uint64_t)pl.PW);
     p.w_magic = (uint32_t)((0x100000000ull + (uint64_t)W - 1) / (uint64_t)W);
     p.vec2 = (!down2 && !im2col && W % 2 == 0 && ((uintptr_t)x & 7) == 0 && ((uintptr_t)x2 & 7) == 0 && env_int("PASTA_B200_CONV_VEC2", 1)) ? 1 : 0;
