@@ -287,6 +287,17 @@ def run_b200(args, world, rank, local):
         with capi.LaunchProfiler() as prof:
             sess.G(**sess.static_in, noise_mode='const')
     roof, profile = roofline_from(prof.summary(), pk)
+    if roof is not None:
+        # the dominant kernel family by layer shape: algorithmic TFLOP/s and GB/s per shape (the family mixes tensor-bound 128^2 layers with
+        # HBM-bound 64-channel 256^2 layers and latency-bound 4^2..16^2 layers, so the family-wide fraction understates the big shapes)
+        by = {}
+        for name, nbytes, flops, e0, e1, tag in prof.records:
+            if name == roof['kernel']:
+                a = by.setdefault(tag, [0, 0.0, 0, 0])
+                a[0] += 1; a[1] += e0.elapsed_time(e1); a[2] += nbytes; a[3] += flops
+        roof['by_shape'] = [dict(shape=t, launches=n, ms=round(ms, 3), tflops=round(fl / ms / 1e9, 1), gbs=round(nb / ms / 1e6),
+                                 frac_tensor=round(fl / ms / 1e9 / pk['tf_sustained'], 3), frac_hbm=round(nb / ms / 1e6 / pk['hbm'], 3))
+                            for t, (n, ms, nb, fl) in sorted(by.items(), key=lambda kv: -kv[1][1])[:8] if ms > 0]
 
     if rank != 0:
         return
