@@ -39,6 +39,8 @@ table with ``use_ops(module, table)``.  The product never imports the oracle.
 """
 import types
 
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -196,15 +198,16 @@ def conv_layer(x, w, b=None, f=None, up=1, down=1, padding=0, flip_weight=True, 
 
 
 def modconv_layer(x, weight, styles, noise=None, up=1, padding=0, resample_filter=None, demodulate=True, flip_weight=True,
-                  fused_modconv=True, bias=None, act='linear', act_gain=1.0, clamp=None):
+                  fused_modconv=True, bias=None, act='linear', act_gain=1.0, clamp=None, dcoefs=None):
     """Product form of modulated_conv2d + bias_act (SynthesisLayer / ToRGB): one tcgen05 launch with the style folded into the
     activation operand, demodulation / noise / bias / activation / clamp in the epilogue."""
     from .torch_utils.ops import conv_igemm as K, bias_act as B
     k = int(weight.shape[2])
     if act in ('linear', 'relu', 'lrelu') and padding == k // 2 and \
             K.supported(x, weight, up=up, f=resample_filter, padding=(padding,) * 4) and not styles.requires_grad:
-        dcoefs = None
-        if demodulate:
+        if not demodulate:
+            dcoefs = None
+        elif dcoefs is None:                              # (a StyleBank hands precomputed coefficients in)
             dcoefs = torch.addmm(_EPS.get(x.device), styles.square(), _weight_sq_sums(weight).t()).rsqrt()
         return K.conv2d_igemm(x, weight, f=resample_filter, up=up, flip_weight=flip_weight, styles=styles, dcoefs=dcoefs, noise=noise,
                               bias=bias, act=act, gain=act_gain, clamp=clamp, cache_weights=isinstance(weight, nn.Parameter))
@@ -231,6 +234,75 @@ def _torgb_skip(x, weight, styles, bias, clamp, img, f):
     if not T.supported(x, weight, img, f) or styles.requires_grad:
         return None
     return T.torgb_skip(x, weight, styles=styles, bias=bias, clamp=clamp, img=img, f=f)
+
+
+class StyleBank:
+    """All per-layer styles (affine(w), reference :296-299 / :5602) and demodulation coefficients (:65-68, in the GEMV form of SURVEY appendix A, I8)
+    of a synthesis network in TWO batched GEMMs instead of ~6 tiny kernels per layer (weight * gain, addmm + split-K reduce, square, addmm,
+    rsqrt): they depend only on ``ws``, which is known before the first block runs.  Inference only (no autograd); the packed affine
+    weights are cached and rebuilt when any source parameter changes.  Layers pick their rows up through ``layer._pre``."""
+
+    def __init__(self):
+        self.key = None
+
+    def _pack(self, layers):
+        key = tuple((id(l), l.affine.weight._version, l.affine.bias._version, l.weight._version, l.weight.data_ptr()) for l in layers)
+        if key == self.key:
+            return
+        dev = layers[0].weight.device
+        L, wd = len(layers), int(layers[0].affine.weight.shape[1])
+        cmax = max(int(l.affine.weight.shape[0]) for l in layers)
+        self.demod = [i for i, l in enumerate(layers) if isinstance(l, SynthesisLayer)]
+        omax = max([int(layers[i].weight.shape[0]) for i in self.demod] or [1])
+        W = torch.zeros([L, wd, cmax], device=dev); B = torch.zeros([L, 1, cmax], device=dev)
+        Q = torch.zeros([max(len(self.demod), 1), cmax, omax], device=dev)
+        with torch.no_grad():
+            for i, l in enumerate(layers):
+                c = int(l.affine.weight.shape[0])
+                g = 1.0 if isinstance(l, SynthesisLayer) else float(l.weight_gain)          # ToRGB: styles * weight_gain (:5602)
+                W[i, :, :c] = (l.affine.weight * (l.affine.weight_gain * g)).t()
+                B[i, 0, :c] = l.affine.bias * (l.affine.bias_gain * g)
+            for j, i in enumerate(self.demod):
+                w = layers[i].weight
+                Q[j, :w.shape[1], :w.shape[0]] = w.square().sum(dim=[2, 3]).t()
+        self.W, self.B, self.Q, self.key = W, B, Q, key
+        self.demod_idx = torch.tensor(self.demod, device=dev, dtype=torch.long)
+
+    def fill(self, entries):
+        """entries: [(layer, w [N, w_dim])] in any order; sets layer._pre = (styles [N, Cin], dcoefs [N, Cout] or None)."""
+        layers = [l for l, _ in entries]
+        self._pack(layers)
+        X = torch.stack([w for _, w in entries], dim=0).to(torch.float32)                    # [L, N, w_dim]
+        S = torch.baddbmm(self.B, X, self.W)                                                 # [L, N, Cmax]
+        D = None
+        if self.demod:
+            D = torch.baddbmm(_EPS.get(X.device).reshape(1, 1, 1), S.index_select(0, self.demod_idx).square(), self.Q).rsqrt()
+        pos = {i: j for j, i in enumerate(self.demod)}
+        for i, l in enumerate(layers):
+            c = int(l.affine.weight.shape[0])
+            d = D[pos[i], :, :int(l.weight.shape[0])] if i in pos else None
+            l._pre = (S[i, :, :c], d)
+
+    @staticmethod
+    def clear(entries):
+        for l, _ in entries:
+            l._pre = None
+
+
+def _block_style_entries(blk, cur):
+    """(layer, w) pairs of one synthesis block in the order its forward consumes ``cur`` (conv0 if present, conv1, torgb)."""
+    out, it = [], 0
+    if hasattr(blk, 'conv0'):
+        out.append((blk.conv0, cur[:, it])); it += 1
+    out.append((blk.conv1, cur[:, it])); it += 1
+    if hasattr(blk, 'torgb'):
+        out.append((blk.torgb, cur[:, it]))
+    return out
+
+
+def _style_bank_usable(module, ws):
+    return (not torch.is_grad_enabled()) and ws.is_cuda and getattr(module.ops, 'modconv_layer', None) is not None and \
+        os.environ.get('PASTA_B200_STYLE_BANK', '1') != '0'
 
 
 # ----------------------------------------------------------------------------- layers
@@ -394,7 +466,8 @@ class SynthesisLayer(OpsModule):
     def forward(self, x, w, noise_mode='random', fused_modconv=True, gain=1):
         assert noise_mode in ['random', 'const', 'none']
         misc.assert_shape(x, [None, self.weight.shape[1], self.resolution // self.up, self.resolution // self.up])
-        styles = self.affine(w)
+        pre = getattr(self, '_pre', None)
+        styles, dcoefs = pre if pre is not None else (self.affine(w), None)
         noise = None
         if self.use_noise and noise_mode == 'random':
             noise = torch.randn([x.shape[0], 1, self.resolution, self.resolution], device=x.device) * self.noise_strength
@@ -405,7 +478,7 @@ class SynthesisLayer(OpsModule):
         if layer is not None:
             return layer(x, self.weight, styles, noise=noise, up=self.up, padding=self.padding, resample_filter=self.resample_filter,
                          flip_weight=(self.up == 1), fused_modconv=fused_modconv, bias=self.bias.to(x.dtype), act=self.activation,
-                         act_gain=self.act_gain * gain, clamp=clamp)
+                         act_gain=self.act_gain * gain, clamp=clamp, dcoefs=dcoefs)
         x = self.ops.modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=noise, up=self.up, padding=self.padding,
                                       resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv)
         return self.ops.bias_act(x, self.bias.to(x.dtype), act=self.activation, gain=self.act_gain * gain, clamp=clamp)
@@ -432,7 +505,8 @@ class ToRGBLayerFull(OpsModule):
         fused = getattr(self.ops, 'torgb_skip', None)
         if fused is None:
             return None
-        styles = self.affine(w) * self.weight_gain
+        pre = getattr(self, '_pre', None)
+        styles = pre[0] if pre is not None else self.affine(w) * self.weight_gain
         rgb = fused(x, self.weight, styles, self.bias, self.conv_clamp, img, resample_filter)
         if rgb is None:
             return None
@@ -440,7 +514,8 @@ class ToRGBLayerFull(OpsModule):
         return rgb, parsing
 
     def forward(self, x, w, fused_modconv=True):
-        styles = self.affine(w) * self.weight_gain
+        pre = getattr(self, '_pre', None)
+        styles = pre[0] if pre is not None else self.affine(w) * self.weight_gain
         layer = getattr(self.ops, 'modconv_layer', None)
 
         def head(weight, bias):
@@ -692,6 +767,20 @@ class SynthesisNetworkFull(OpsModule):
             block = getattr(self, f'b{res}')
             block_ws.append(ws.narrow(1, idx, block.num_conv + block.num_torgb))
             idx += block.num_conv
+        entries = []
+        if _style_bank_usable(self, ws):
+            for blk, cur in list(zip([getattr(self, f'b{res}') for res in self.block_resolutions], block_ws)) + [(self.texture_b256, block_ws[-1])]:
+                entries += _block_style_entries(blk, cur)
+            if not hasattr(self, '_bank'):
+                object.__setattr__(self, '_bank', StyleBank())
+            self._bank.fill(entries)
+        try:
+            return self._forward_blocks(block_ws, pose_feat, cat_feat, denorm_upper_input, denorm_lower_input, denorm_upper_mask, denorm_lower_mask,
+                                        **block_kwargs)
+        finally:
+            StyleBank.clear(entries)
+
+    def _forward_blocks(self, block_ws, pose_feat, cat_feat, denorm_upper_input, denorm_lower_input, denorm_upper_mask, denorm_lower_mask, **block_kwargs):
         x = img = parsing = None
         for res, cur in zip(self.block_resolutions, block_ws):
             x, img, parsing = getattr(self, f'b{res}')(x, img, cur, pose_feat, cat_feat, force_fp32=True, **block_kwargs)
@@ -748,7 +837,8 @@ class ToRGBLayer(OpsModule):
     forward_skip = ToRGBLayerFull.forward_skip
 
     def forward(self, x, w, fused_modconv=True):
-        styles = self.affine(w) * self.weight_gain
+        pre = getattr(self, '_pre', None)
+        styles = pre[0] if pre is not None else self.affine(w) * self.weight_gain
         layer = getattr(self.ops, 'modconv_layer', None)
         if layer is not None:
             return layer(x, self.weight, styles, demodulate=False, fused_modconv=fused_modconv, bias=self.bias.to(x.dtype), clamp=self.conv_clamp)
@@ -820,11 +910,23 @@ class SynthesisNetwork512(OpsModule):
         misc.assert_shape(ws, [None, self.num_ws, self.w_dim])
         ws = ws.to(torch.float32)
         x = img = None
-        idx = 0
+        idx, plan = 0, []
         for res in self.block_resolutions:
             block = getattr(self, f'b{res}')
-            x, img = block(x, img, ws.narrow(1, idx, block.num_conv + block.num_torgb), pose_feat, cat_feat, **block_kwargs)
+            plan.append((block, ws.narrow(1, idx, block.num_conv + block.num_torgb)))
             idx += block.num_conv
+        entries = []
+        if _style_bank_usable(self, ws):
+            for block, cur in plan:
+                entries += _block_style_entries(block, cur)
+            if not hasattr(self, '_bank'):
+                object.__setattr__(self, '_bank', StyleBank())
+            self._bank.fill(entries)
+        try:
+            for block, cur in plan:
+                x, img = block(x, img, cur, pose_feat, cat_feat, **block_kwargs)
+        finally:
+            StyleBank.clear(entries)
         return img
 
 
