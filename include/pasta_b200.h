@@ -187,6 +187,14 @@ int pg_conv2d_igemm_spade_run(const float* feat, const void* wpack_gamma_beta, c
  * Feeds pg_conv2d_igemm_spade_run; replaces nn.InstanceNorm2d(affine=False) inside Spade_Norm_Block (training/networks.py:4363, :4377). */
 int pg_instance_norm_stats(const float* x, float* mean, float* rstd, int64_t planes, int64_t hw, float eps, void* stream);
 
+/* Garment-feature completion of SynthesisNetworkFull.get_spade_feat (training/networks.py:5777-5800), the two passes over the feature map:
+ *   pg_masked_plane_sum: out[n,c] = sum_hw feat[n,c,hw] * mask[n,hw]                      feat [N,C,hw], mask [N,hw], out [N,C]
+ *   pg_masked_fill:      out[n,c,hw] = feat[n,c,hw] * (1 - rest[n,hw]) + fill[n,c] * rest[n,hw], out addressed with a batch stride in elements
+ *                        (>= C*hw) so that it can be a channel slice of the concatenated upper|lower tensor (replaces torch.cat, :5831). */
+int pg_masked_plane_sum(const float* feat, const float* mask, float* out, int64_t N, int64_t C, int64_t hw, void* stream);
+int pg_masked_fill(const float* feat, const float* rest, const float* fill, float* out, int64_t N, int64_t C, int64_t hw,
+                   int64_t out_batch_stride, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * torgb_skip — the ToRGB skip path of a synthesis block in one streaming kernel (north_star kernel 3):
  *

@@ -61,7 +61,7 @@ def cuda_ops():
             name='sm100a',
             setup_filter=U.setup_filter, upfirdn2d=U.upfirdn2d, filter2d=U.filter2d, upsample2d=U.upsample2d,
             downsample2d=U.downsample2d, bias_act=B.bias_act, conv2d_resample=C.conv2d_resample, fma=F.fma,
-            modulated_conv2d=modulated_conv2d, conv_layer=conv_layer, modconv_layer=modconv_layer, torgb_skip=_torgb_skip, spade_conv_norm=_spade_conv_norm,
+            modulated_conv2d=modulated_conv2d, conv_layer=conv_layer, modconv_layer=modconv_layer, torgb_skip=_torgb_skip, spade_conv_norm=_spade_conv_norm, masked_mean_fill=_masked_mean_fill,
             instance_stats=lambda x: K.instance_stats(x) if (K.enabled and x.is_cuda and x.dtype == torch.float32) else None,
             act_def_gain={k: float(v.def_gain) for k, v in B.activation_funcs.items()},
         )
@@ -226,6 +226,14 @@ def _spade_conv_norm(x, actv, w_gamma, w_beta, w_scale, post_act, stats=None):
     if act not in ('linear', 'relu', 'lrelu'):
         return None
     return K.spade_conv_norm(x, actv, w_gamma, w_beta, w_scale=w_scale, act=act, gain=gain, stats=stats)
+
+
+def _masked_mean_fill(feat, valid, rest, out):
+    """Product get_spade_feat tail (two streaming kernels); None when the tensors are not covered."""
+    from .torch_utils.ops import spade_feat as S
+    if not S.supported(feat, valid, rest, out):
+        return None
+    return S.masked_mean_fill(feat, valid, rest, out)
 
 
 def _torgb_skip(x, weight, styles, bias, clamp, img, f):
@@ -742,9 +750,10 @@ class SynthesisNetworkFull(OpsModule):
                                            ResBlock(ngf, ngf, kernel_size=4, activation='relu'),
                                            ResBlock(ngf, ngf * 2, kernel_size=4, activation='relu', down=2))
 
-    def get_spade_feat(self, mask_256, denorm_mask, denorm_input):
+    def get_spade_feat(self, mask_256, denorm_mask, denorm_input, out=None):
         """Garment features at 128 px; pixels the predicted mask covers but the source garment does not are filled with the
-        garment's mean feature (reference :5777-5800)."""
+        garment's mean feature (reference :5777-5800).  ``out``: channel slice of the concatenated upper|lower tensor to write into
+        (fused path: two streaming kernels instead of five elementwise passes and the torch.cat)."""
         half = lambda t: torch.nn.functional.interpolate(t, scale_factor=0.5)
         binar = lambda t: (t > 0.9).to(mask_256.dtype)
         mask_256 = binar(mask_256)
@@ -753,11 +762,20 @@ class SynthesisNetworkFull(OpsModule):
         valid = ((mask_128 + denorm_mask_128) == 2.0).to(mask_256.dtype)
         rest = mask_128 - valid
         feat = self.spade_encoder(denorm_input * mask_256 - (1 - mask_256))
+        fused = getattr(self.ops, 'masked_mean_fill', None)
+        if fused is not None and out is not None:
+            y = fused(feat, valid, rest, out)
+            if y is not None:
+                return y
         feat_sum = (feat * valid).sum(dim=(2, 3), keepdim=True)
         count = valid.sum(dim=(2, 3), keepdim=True)
         enough = (count > 10).to(mask_256.dtype)
         count = count * enough + (128 * 128) * (1 - enough)
-        return feat * (1 - rest) + (feat_sum / count) * rest
+        y = feat * (1 - rest) + (feat_sum / count) * rest
+        if out is not None:
+            out.copy_(y)
+            return out
+        return y
 
     def forward(self, ws, pose_feat, cat_feat, denorm_upper_input, denorm_lower_input, denorm_upper_mask, denorm_lower_mask, **block_kwargs):
         misc.assert_shape(ws, [None, self.num_ws, self.w_dim])
@@ -787,9 +805,10 @@ class SynthesisNetworkFull(OpsModule):
             if res == 128:
                 x_128, img_128 = x.clone(), img.clone()
         label = torch.argmax(torch.softmax(parsing.detach(), dim=1), dim=1)[:, None].float()
-        upper = self.get_spade_feat((label == 1).float(), denorm_upper_mask, denorm_upper_input)
-        lower = self.get_spade_feat((label == 2).float(), denorm_lower_mask, denorm_lower_input)
-        spade_feat = torch.cat([upper, lower], dim=1)
+        cf = self.spade_encoder[-1].conv1.weight.shape[0]                 # channels of one garment's feature map (128)
+        spade_feat = torch.empty([label.shape[0], 2 * cf, label.shape[2] // 2, label.shape[3] // 2], dtype=torch.float32, device=label.device)
+        self.get_spade_feat((label == 1).float(), denorm_upper_mask, denorm_upper_input, out=spade_feat[:, :cf])      # upper | lower (:5831)
+        self.get_spade_feat((label == 2).float(), denorm_lower_mask, denorm_lower_input, out=spade_feat[:, cf:])
         x = x_128
         for k in (1, 2, 3):
             x = getattr(self, f'spade_b128_{k}')(x, spade_feat)

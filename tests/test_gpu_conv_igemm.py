@@ -209,3 +209,24 @@ def test_instance_stats(cv, shape):
         m_ref = xd.mean(dim=(2, 3)); r_ref = (xd.var(dim=(2, 3), unbiased=False) + 1e-5).rsqrt()
         assert float((mean.double().cpu() - m_ref).abs().max()) < 1e-6 * max(1.7, offset)      # mean error relative to the data scale
         assert rel_err(rstd, r_ref) < (1e-5 if offset == 0 else 2e-4)
+
+
+@pytest.mark.parametrize('shape', [(2, 16, 32, 32), (3, 5, 9, 7), (1, 128, 128, 128)])
+def test_masked_mean_fill(shape):
+    """pg_masked_plane_sum + pg_masked_fill == the tail of get_spade_feat (reference :5791-5800), written into a channel slice."""
+    from pasta_gan_b200.torch_utils.ops import spade_feat as S
+    n, c, h, w = shape
+    torch.manual_seed(sum(shape))
+    feat = torch.randn(n, c, h, w)
+    m1 = (torch.rand(n, 1, h, w) > 0.5).float(); m2 = (torch.rand(n, 1, h, w) > 0.4).float()
+    if n > 1:
+        m2[0] = 0                                                   # a sample without enough valid pixels: count falls back to H*W
+    valid = ((m1 + m2) == 2.0).float(); rest = m1 - valid
+    fs = (feat.double() * valid.double()).sum(dim=(2, 3), keepdim=True)
+    cnt = valid.double().sum(dim=(2, 3), keepdim=True); en = (cnt > 10).double(); cnt = cnt * en + (h * w) * (1 - en)
+    ref = feat.double() * (1 - rest.double()) + (fs / cnt) * rest.double()
+    buf = torch.full([n, 2 * c + 3, h, w], float('nan'), device=DEV)
+    out = S.masked_mean_fill(feat.to(DEV), valid.to(DEV), rest.to(DEV), buf[:, 2:2 + c])
+    assert out.data_ptr() == buf[:, 2:2 + c].data_ptr()
+    assert rel_err(buf[:, 2:2 + c], ref) < 1e-5
+    assert torch.isnan(buf[:, :2]).all() and torch.isnan(buf[:, 2 + c:]).all()          # neighbours of the slice untouched
