@@ -158,12 +158,17 @@ int pg_conv2d_igemm_run(const float* x, const void* wpack, const float* styles, 
  *   x2 != NULL: the input is the channel concatenation [x ; x2] without materialising it (x [N,Cin1,H,W], x2 [N,Cin-Cin1,H,W], Cin1 % 8 == 0;
  *               replaces torch.cat + conv of SynthesisBlockFull's merge_conv, training/networks.py:5705-5706); not with PG_CONV_DOWN2.
  *   residual != NULL: y += residual after activation, gain and clamp (the `y.add_(x)` that closes every residual block,
- *               training/networks.py:986-990, :5268-5272). */
+ *               training/networks.py:986-990, :5268-5272).
+ *   x_dtype / y_dtype = PG_F16: x and / or y are dense NCHW float16 (pass the pointers cast to float*).  For tensors that only travel between two
+ *               of these convolutions (the SPADE blocks' `actv` and normalised maps, training/networks.py:4371-4379): the consumer would round
+ *               the fp32 value to an fp16 operand anyway, so results are bit-identical while the tensor costs half the bytes.  A float16 input
+ *               needs a plain layer (styles == NULL, in_act linear, in_gain 1, no x2 / down-2), operand_format 0 and even W; a float16 output
+ *               excludes `residual`. */
 int pg_conv2d_igemm_run2(const float* x, const float* x2, int32_t Cin1, const void* wpack, const float* styles, const float* dcoefs,
                          const float* noise, int64_t noise_batch_stride, const float* bias, const float* residual, float* y,
                          int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t ksize, int32_t up,
                          int32_t in_act, float in_alpha, float in_gain,
-                         int32_t act, float alpha, float gain, float clamp, int32_t operand_format, void* stream);
+                         int32_t act, float alpha, float gain, float clamp, int32_t operand_format, int32_t x_dtype, int32_t y_dtype, void* stream);
 int pg_conv2d_igemm_fwd(const float* x, const float* w, const float* fir, const float* styles, const float* dcoefs,
                         const float* noise, int64_t noise_batch_stride, const float* bias, float* y,
                         int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t ksize, int32_t up,
@@ -178,10 +183,11 @@ int pg_conv2d_igemm_fwd(const float* x, const float* w, const float* fir, const 
  *   y[n,c]         = act( (x[n,c] - mean[n,c]) * rstd[n,c] * (1 + gamma[n,c]) + beta[n,c] ) * gain
  *
  * feat [N,Cin,H,W]; wpack_gamma_beta = pg_conv2d_igemm_prepack of the [2C,Cin,k,k] concatenation; x, y [N,C,H,W]; mean, rstd [N,C]
- * (instance-norm statistics of x); 2C <= 256, C % 16 == 0.  gamma and beta never reach HBM. */
+ * (instance-norm statistics of x); 2C <= 256, C % 16 == 0.  gamma and beta never reach HBM.  feat_dtype / y_dtype: PG_F32 or PG_F16 as in
+ * pg_conv2d_igemm_run2 (x, mean, rstd are always float32). */
 int pg_conv2d_igemm_spade_run(const float* feat, const void* wpack_gamma_beta, const float* x, const float* mean, const float* rstd,
                               float* y, int32_t N, int32_t Cin, int32_t C, int32_t H, int32_t W, int32_t ksize,
-                              int32_t act, float alpha, float gain, int32_t operand_format, void* stream);
+                              int32_t act, float alpha, float gain, int32_t operand_format, int32_t feat_dtype, int32_t y_dtype, void* stream);
 
 /* Instance-norm statistics of x [planes = N*C, hw] (dense, fp32): mean and rstd = rsqrt(biased variance + eps), one streaming pass.
  * Feeds pg_conv2d_igemm_spade_run; replaces nn.InstanceNorm2d(affine=False) inside Spade_Norm_Block (training/networks.py:4363, :4377). */
@@ -193,7 +199,7 @@ int pg_instance_norm_stats(const float* x, float* mean, float* rstd, int64_t pla
  *                        (>= C*hw) so that it can be a channel slice of the concatenated upper|lower tensor (replaces torch.cat, :5831). */
 int pg_masked_plane_sum(const float* feat, const float* mask, float* out, int64_t N, int64_t C, int64_t hw, void* stream);
 int pg_masked_fill(const float* feat, const float* rest, const float* fill, float* out, int64_t N, int64_t C, int64_t hw,
-                   int64_t out_batch_stride, void* stream);
+                   int64_t out_batch_stride, int32_t out_dtype, void* stream);   /* out_dtype: PG_F32 or PG_F16 (out cast to float*) */
 
 /* ---------------------------------------------------------------------------------------------
  * torgb_skip — the ToRGB skip path of a synthesis block in one streaming kernel (north_star kernel 3):

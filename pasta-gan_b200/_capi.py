@@ -34,11 +34,11 @@ SIGNATURES = {
     'pg_debug_set_buffer': [c_ptr],
     'pg_conv2d_igemm_prepack': [c_ptr, c_ptr, c_f32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr, c_i64, c_ptr],
     'pg_conv2d_igemm_run': [c_ptr] * 5 + [c_i64, c_ptr, c_ptr] + [c_i32] * 7 + [c_i32, c_f32, c_f32, c_i32, c_f32, c_f32, c_f32, c_i32, c_ptr],
-    'pg_conv2d_igemm_run2': [c_ptr, c_ptr, c_i32] + [c_ptr] * 4 + [c_i64, c_ptr, c_ptr, c_ptr] + [c_i32] * 7 + [c_i32, c_f32, c_f32, c_i32, c_f32, c_f32, c_f32, c_i32, c_ptr],
+    'pg_conv2d_igemm_run2': [c_ptr, c_ptr, c_i32] + [c_ptr] * 4 + [c_i64, c_ptr, c_ptr, c_ptr] + [c_i32] * 7 + [c_i32, c_f32, c_f32, c_i32, c_f32, c_f32, c_f32, c_i32, c_i32, c_i32, c_ptr],
     'pg_masked_plane_sum': [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr],
-    'pg_masked_fill': [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr],
+    'pg_masked_fill': [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i32, c_ptr],
     'pg_instance_norm_stats': [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_f32, c_ptr],
-    'pg_conv2d_igemm_spade_run': [c_ptr] * 6 + [c_i32] * 6 + [c_i32, c_f32, c_f32, c_i32, c_ptr],
+    'pg_conv2d_igemm_spade_run': [c_ptr] * 6 + [c_i32] * 6 + [c_i32, c_f32, c_f32, c_i32, c_i32, c_i32, c_ptr],
     'pg_conv2d_igemm_fwd': [c_ptr] * 6 + [c_i64, c_ptr, c_ptr] + [c_i32] * 7 + [c_i32, c_i32, c_f32, c_f32, c_i32, c_f32, c_f32, c_f32, c_i32,
                             c_ptr, c_i64, c_ptr],
     'pg_torgb_skip': [c_ptr] * 7 + [c_i32] * 5 + [c_f32, c_ptr],

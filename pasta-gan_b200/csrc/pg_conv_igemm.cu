@@ -50,6 +50,8 @@ struct ConvParams {
     int down2, cin_real, hin, win;   // down-2 mode: the A operand is the 4-plane space-to-depth view of x [N,cin_real,hin,win]
     const float* sp_x; const float* sp_mean; const float* sp_rstd; int spade;   // SPADE epilogue: y = act((x-mean)*rstd*(1+gamma)+beta)*gain
     long long* dbg;            // optional per-CTA phase timestamps (pg_debug_set_buffer), NULL in production
+    int in_half, out_half;     // x / y are fp16 NCHW (intermediates between our own layers); everything else stays fp32
+    int cgroups;               // converter warp groups that take alternate chunks (lean loader): several chunks' load round trips in flight
     int pipe, ldmode, dbgmode, lean;          // converter knobs (tuning): register double-buffering on/off, L1::no_allocate loads
     int im2col; uint32_t kk_magic, ks_magic;   // im2col mode: real kernel size (0 = off); ceil(2^32 / k^2), ceil(2^32 / k)
     int vec2; uint32_t w_magic;   // aligned 8-byte loader (see the converter section); ceil(2^32 / W)
@@ -123,6 +125,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                  : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// fp16 output element: the same round-to-nearest / saturate-to-finite conversion the consuming layer's loader would apply to the fp32 value
+__device__ __forceinline__ void store_half(float* y, size_t off, float v) {
+    unsigned short h;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+    reinterpret_cast<unsigned short*>(y)[off] = h;
 }
 
 // two fp32 -> packed fp16x2 / bf16x2 (a in the low half), round-to-nearest, saturating to the largest finite value
@@ -306,18 +315,20 @@ __device__ __forceinline__ void stream_tasks(Load&& load_task, Store&& store_tas
 // pair inside a channel plane and the two shared-memory slots it lands on -- is computed once per CTA; per chunk only the channel base moves.
 // A warp owns task slots idx = r * PER + u (task = cw + 8 * idx: 32 pairs of one 8-channel plane; all of a warp's tasks share the plane cw & 1),
 // processed in ROUNDS register batches of PER tasks: the loads of a batch are issued before the stage is waited for.
-template <bool SCALE, int PER, int ROUNDS>
+template <bool SCALE, bool IN_HALF, int PER, int ROUNDS>
 __device__ __forceinline__ void convert_vec2(const ConvParams& p, const float* xn, const float* xn2, const int HW, const int cw, const int lane,
                                              const int g_lo, const int g_hi, const int ntasks, const int q0, uint8_t* a_base, const float* s_style,
                                              uint64_t* a_full, uint64_t* a_empty, long long& wait_e) {
     constexpr int NS = PER * ROUNDS;
+    const int wpg = kConvWarps / p.cgroups;     // warps per group; group g converts chunks g, g + cgroups, ...
+    const int grp = cw / wpg, gw = cw - grp * wpg;
     const int plane = cw & 1;
     const bool swap = (lane >> 2) & 1;          // lanes sit 32 B apart in the stage: lanes 4..7 of each group of 8 write their second slot first
     const int dpitch = p.PW - p.W;
     int goff[NS]; uint32_t sA[NS], sB[NS];
 #pragma unroll
     for (int idx = 0; idx < NS; idx++) {
-        const int tt = cw + idx * kConvWarps;
+        const int tt = gw + idx * wpg;                               // wpg is even: every task of a warp has the plane cw & 1
         const int g = g_lo + (tt >> 1) * 32 + lane;
         const bool ok = tt < ntasks && g < g_hi;
         const int e = 2 * g;
@@ -332,25 +343,44 @@ __device__ __forceinline__ void convert_vec2(const ConvParams& p, const float* x
     const bool has_in_act = p.in_act != PG_ACT_LINEAR;
     const float in_slope = (p.in_act == PG_ACT_RELU) ? 0.f : p.in_alpha;
     const int nchunks = p.nchunks;
-    int st = 0; uint32_t ph = 0;
-    for (int ci = 0; ci < nchunks; ci++) {
+    for (int ci = grp; ci < nchunks; ci += p.cgroups) {
+        const int st = ci % p.SA; const uint32_t ph = (uint32_t)(ci / p.SA) & 1u;
         const int c0 = ci * kKC + plane * 8;
         const int nval = p.Cin - c0;                                  // channels of this group that exist (>= 8: all)
         const float* cb = (c0 < p.cin1 ? xn : xn2) + (size_t)c0 * HW;
+        const __half* cbh = reinterpret_cast<const __half*>(xn) + (size_t)c0 * HW;      // IN_HALF: x is fp16, one sample's planes start at xn
         uint8_t* stage = a_base + (size_t)st * p.a_stage_bytes;
 #pragma unroll
         for (int r = 0; r < ROUNDS; r++) {
-            float v[PER][16];
+            float v[PER][IN_HALF ? 8 : 16];                      // IN_HALF: v[u][i] holds the half2 (positions e, e + 1) of channel i as raw bits
 #pragma unroll
             for (int u = 0; u < PER; u++) {
                 const int off = goff[r * PER + u];
 #pragma unroll
-                for (int i = 0; i < 16; i++) v[u][i] = 0.f;
+                for (int i = 0; i < (IN_HALF ? 8 : 16); i++) v[u][i] = 0.f;
                 if (off >= 0) {
-                    const float* src = cb + off;
+                    if (IN_HALF) {
+                        const __half* src = cbh + off;
 #pragma unroll
-                    for (int i = 0; i < 8; i++)
-                        if (i < nval) { const float2 t = __ldg(reinterpret_cast<const float2*>(src + (size_t)i * HW)); v[u][i] = t.x; v[u][8 + i] = t.y; }
+                        for (int i = 0; i < 8; i++)
+                            if (i < nval) v[u][i] = __uint_as_float(__ldg(reinterpret_cast<const unsigned int*>(src + (size_t)i * HW)));
+                    } else {
+                        const float* src = cb + off;
+#pragma unroll
+                        if (p.ldmode == 1) {
+#pragma unroll
+                            for (int i = 0; i < 8; i++)
+                                if (i < nval) asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v[u][i]), "=f"(v[u][8 + i]) : "l"(src + (size_t)i * HW));
+                        } else if (p.ldmode == 2) {
+#pragma unroll
+                            for (int i = 0; i < 8; i++)
+                                if (i < nval) asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(v[u][i]), "=f"(v[u][8 + i]) : "l"(src + (size_t)i * HW));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; i++)
+                                if (i < nval) { const float2 t = __ldg(reinterpret_cast<const float2*>(src + (size_t)i * HW)); v[u][i] = t.x; v[u][8 + i] = t.y; }
+                        }
+                    }
                 }
             }
             if (r == 0) {
@@ -362,18 +392,28 @@ __device__ __forceinline__ void convert_vec2(const ConvParams& p, const float* x
             for (int u = 0; u < PER; u++) {
                 const uint32_t a1 = sA[r * PER + u], a2 = sB[r * PER + u];
                 if ((a1 & a2) == 0xffffffffu) continue;
-                if (SCALE) {
-                    const float* sc = s_style + c0;
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        float a = v[u][i], b = v[u][8 + i];
-                        if (has_in_act) { a = fmaxf(a, 0.f) + in_slope * fminf(a, 0.f); b = fmaxf(b, 0.f) + in_slope * fminf(b, 0.f); }
-                        v[u][i] = a * sc[i]; v[u][8 + i] = b * sc[i];
-                    }
-                }
                 uint4 lo, hi;
-                lo.x = pack2(v[u][0], v[u][1], p.fmt); lo.y = pack2(v[u][2], v[u][3], p.fmt); lo.z = pack2(v[u][4], v[u][5], p.fmt); lo.w = pack2(v[u][6], v[u][7], p.fmt);
-                hi.x = pack2(v[u][8], v[u][9], p.fmt); hi.y = pack2(v[u][10], v[u][11], p.fmt); hi.z = pack2(v[u][12], v[u][13], p.fmt); hi.w = pack2(v[u][14], v[u][15], p.fmt);
+                if (IN_HALF) {
+                    // already fp16: gather the low (position e) / high (position e + 1) halves of channel pairs into the two 16-byte rows
+                    const unsigned int b0 = __float_as_uint(v[u][0]), b1 = __float_as_uint(v[u][1]), b2 = __float_as_uint(v[u][2]), b3 = __float_as_uint(v[u][3]),
+                                       b4 = __float_as_uint(v[u][4]), b5 = __float_as_uint(v[u][5]), b6 = __float_as_uint(v[u][6]), b7 = __float_as_uint(v[u][7]);
+                    lo.x = __byte_perm(b0, b1, 0x5410); lo.y = __byte_perm(b2, b3, 0x5410); lo.z = __byte_perm(b4, b5, 0x5410); lo.w = __byte_perm(b6, b7, 0x5410);
+                    hi.x = __byte_perm(b0, b1, 0x7632); hi.y = __byte_perm(b2, b3, 0x7632); hi.z = __byte_perm(b4, b5, 0x7632); hi.w = __byte_perm(b6, b7, 0x7632);
+                } else {
+                    if (SCALE) {
+                        const float* sc = s_style + c0;
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            float a = v[u][i], b = v[u][(IN_HALF ? 0 : 8) + i];
+                            if (has_in_act) { a = fmaxf(a, 0.f) + in_slope * fminf(a, 0.f); b = fmaxf(b, 0.f) + in_slope * fminf(b, 0.f); }
+                            v[u][i] = a * sc[i]; v[u][(IN_HALF ? 0 : 8) + i] = b * sc[i];
+                        }
+                    }
+                    constexpr int H8 = IN_HALF ? 0 : 8;
+                    lo.x = pack2(v[u][0], v[u][1], p.fmt); lo.y = pack2(v[u][2], v[u][3], p.fmt); lo.z = pack2(v[u][4], v[u][5], p.fmt); lo.w = pack2(v[u][6], v[u][7], p.fmt);
+                    hi.x = pack2(v[u][H8 + 0], v[u][H8 + 1], p.fmt); hi.y = pack2(v[u][H8 + 2], v[u][H8 + 3], p.fmt);
+                    hi.z = pack2(v[u][H8 + 4], v[u][H8 + 5], p.fmt); hi.w = pack2(v[u][H8 + 6], v[u][H8 + 7], p.fmt);
+                }
                 const uint4 d1 = swap ? hi : lo, d2 = swap ? lo : hi;
                 if (a1 != 0xffffffffu) *reinterpret_cast<uint4*>(stage + a1) = d1;
                 if (a2 != 0xffffffffu) *reinterpret_cast<uint4*>(stage + a2) = d2;
@@ -382,7 +422,6 @@ __device__ __forceinline__ void convert_vec2(const ConvParams& p, const float* x
         fence_proxy_async();                               // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&a_full[st]));
-        if (++st == p.SA) { st = 0; ph ^= 1; }
     }
 }
 
@@ -419,7 +458,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
     int2* s_tab = reinterpret_cast<int2*>(acc_full + 2);    // folded-tap mode: per virtual channel (element offset, (dh << 16) | (dw & 0xffff))
 
     if (warp == 0 && lane == 0) {
-        for (int i = 0; i < p.SA; i++) { mbar_init(smem_u32(&a_full[i]), kConvWarps); mbar_init(smem_u32(&a_empty[i]), 1); }
+        for (int i = 0; i < p.SA; i++) { mbar_init(smem_u32(&a_full[i]), (uint32_t)(kConvWarps / p.cgroups)); mbar_init(smem_u32(&a_empty[i]), 1); }
         for (int i = 0; i < p.SB; i++) { mbar_init(smem_u32(&b_full[i]), 1); mbar_init(smem_u32(&b_empty[i]), 1); }
         mbar_init(smem_u32(acc_full), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -503,7 +542,10 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
         //   * scalar loader: any W, down-2 space-to-depth reads; writes every staged slot (zeros where out of range).
         const int cw = warp - 2;
         const int halo = (p.ks == 3) ? p.PW + 1 : 0;
-        const float* xn = p.down2 ? p.x + (size_t)n * p.cin_real * p.hin * p.win : p.x + (size_t)n * p.cin1 * HW;
+        const int n_in = (p.dbgmode & 8) ? 0 : n;      // tuning: every sample reads sample 0 (input stays L2-resident)
+        const float* xn = p.down2 ? p.x + (size_t)n_in * p.cin_real * p.hin * p.win
+                        : p.in_half ? reinterpret_cast<const float*>(reinterpret_cast<const __half*>(p.x) + (size_t)n_in * p.cin1 * HW)
+                                    : p.x + (size_t)n_in * p.cin1 * HW;
         const float* xn2 = p.x2 ? p.x2 + (size_t)n * (p.Cin - p.cin1) * HW - (size_t)p.cin1 * HW : xn;   // indexed with the global channel number
         auto chan_base = [&](int c0) { return (c0 < p.cin1 ? xn : xn2) + (size_t)c0 * HW; };
         const bool has_in_act = p.in_act != PG_ACT_LINEAR;
@@ -549,7 +591,8 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
             const int g_lo = e_lo >> 1, g_hi = (e_hi + 1) >> 1;                 // pairs of floats
             const int nseg = g_hi > g_lo ? (g_hi - g_lo + 31) >> 5 : 0;
             const int ntasks = nseg * 2;                                        // (segment of 32 pairs, plane)
-            const int tpw = ntasks ? (ntasks + kConvWarps - 1) / kConvWarps : 1;
+            const int wpg_ = p.lean || p.in_half ? kConvWarps / p.cgroups : kConvWarps;
+            const int tpw = ntasks ? (ntasks + wpg_ - 1) / wpg_ : 1;
             const int dpitch = p.PW - p.W;
             auto load_task = [&](float (&v)[16], int ci, int idx) {
                 const int tt = cw + idx * kConvWarps;
@@ -594,14 +637,18 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
                 }
                 if (idx == tpw - 1) stage_end();
             };
-#define PG_CONVERT(PER_, ROUNDS_) convert_vec2<SCALE, PER_, ROUNDS_>(p, xn, xn2, HW, cw, lane, g_lo, g_hi, ntasks, q0, a_base, s_style, a_full, a_empty, wait_e)
-            if (p.lean && tpw <= 6) {
+#define PG_CONVERT(PER_, ROUNDS_) convert_vec2<SCALE, false, PER_, ROUNDS_>(p, xn, xn2, HW, cw, lane, g_lo, g_hi, ntasks, q0, a_base, s_style, a_full, a_empty, wait_e)
+#define PG_CONVERT_H(PER_, ROUNDS_) convert_vec2<false, true, PER_, ROUNDS_>(p, xn, xn2, HW, cw, lane, g_lo, g_hi, ntasks, q0, a_base, s_style, a_full, a_empty, wait_e)
+            if (p.in_half) {                              // fp16 input (host side guarantees tpw <= 6, no input scale / activation)
+                if (tpw <= 2) PG_CONVERT_H(2, 1); else if (tpw <= 4) PG_CONVERT_H(2, 2); else PG_CONVERT_H(3, 2);
+            } else if (p.lean && tpw <= 6) {
                 if (tpw <= 1) PG_CONVERT(1, 1); else if (tpw == 2) PG_CONVERT(2, 1); else if (tpw == 3) PG_CONVERT(3, 1);
                 else if (tpw == 4) PG_CONVERT(2, 2); else PG_CONVERT(3, 2);
             } else {
                 stream_tasks<16, 2>(load_task, store_task, tpw, nchunks, p.pipe != 0, p.dbg != nullptr, t_issue, t_store);
             }
 #undef PG_CONVERT
+#undef PG_CONVERT_H
         } else {
             const int ntasks = (p.PA / 32) * 2;                       // (group of 32 strip positions, plane)
             const int tpw = (ntasks + kConvWarps - 1) / kConvWarps;   // stream slots per warp per chunk (trailing ones may be void)
@@ -679,7 +726,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
                 // gamma = columns [0, C), beta = columns [C, 2C) of the same accumulator row; normalise x with the staged statistics
                 const int C = p.cout_real >> 1;
                 const float* xp = p.sp_x + (size_t)n * C * HW + (size_t)h * p.W + w;
-                float* yp = p.y + (size_t)n * C * HW + (size_t)h * p.W + w;
+                const size_t yoff = (size_t)n * C * HW + (size_t)h * p.W + w;
                 for (int cc = part; cc < C / 16; cc += kConvWarps / 4) {
                     uint32_t rg[16], rb[16];
                     tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.BN + cc * 16), rg);
@@ -688,12 +735,23 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
                     float xv[16];
 #pragma unroll
                     for (int i = 0; i < 16; i++) xv[i] = __ldg(xp + (size_t)(cc * 16 + i) * HW);
+                    if (p.out_half) {
 #pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        const float xn_ = fmaf(xv[i], s_scale[cc * 16 + i], s_shift[cc * 16 + i]);
-                        float v = fmaf(xn_, 1.f + __uint_as_float(rg[i]), __uint_as_float(rb[i]));
-                        v = (fmaxf(v, 0.f) + slope * fminf(v, 0.f)) * p.gain;
-                        yp[(size_t)(cc * 16 + i) * HW] = v;
+                        for (int i = 0; i < 16; i++) {
+                            const float xn_ = fmaf(xv[i], s_scale[cc * 16 + i], s_shift[cc * 16 + i]);
+                            float v = fmaf(xn_, 1.f + __uint_as_float(rg[i]), __uint_as_float(rb[i]));
+                            v = (fmaxf(v, 0.f) + slope * fminf(v, 0.f)) * p.gain;
+                            store_half(p.y, yoff + (size_t)(cc * 16 + i) * HW, v);
+                        }
+                    } else {
+                        float* yp = p.y + yoff;
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            const float xn_ = fmaf(xv[i], s_scale[cc * 16 + i], s_shift[cc * 16 + i]);
+                            float v = fmaf(xn_, 1.f + __uint_as_float(rg[i]), __uint_as_float(rb[i]));
+                            v = (fmaxf(v, 0.f) + slope * fminf(v, 0.f)) * p.gain;
+                            yp[(size_t)(cc * 16 + i) * HW] = v;
+                        }
                     }
                 }
                 continue;
@@ -742,7 +800,6 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
                 if (nvalid <= 0) continue;
                 float nz = nz0;
                 if (p.up2 && p.noise) nz = __ldg(p.noise + (size_t)n * p.noise_bstride + (size_t)oy * W2 + ox) * p.gain;
-                float* yp = p.y + off;
                 float v[16];
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
@@ -763,7 +820,11 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
                 }
 #pragma unroll
                 for (int i = 0; i < 16; i++) v[i] += res[i];
-                if (nvalid == 16) {
+                float* yp = p.y + off;
+                if (p.out_half) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) if (i < nvalid) store_half(p.y, off + (size_t)i * ystride, v[i]);
+                } else if (nvalid == 16) {
 #pragma unroll
                     for (int i = 0; i < 16; i++) yp[(size_t)i * ystride] = v[i];
                 } else {
@@ -923,7 +984,7 @@ static int conv_run_impl(const float* x, const void* wpack, const float* styles,
                          int32_t in_act, float in_alpha, float in_gain,
                          int32_t act, float alpha, float gain, float clamp, int32_t operand_format, void* stream,
                          const float* sp_x, const float* sp_mean, const float* sp_rstd,
-                         const float* x2 = nullptr, int32_t Cin1 = 0, const float* residual = nullptr) {
+                         const float* x2 = nullptr, int32_t Cin1 = 0, const float* residual = nullptr, int32_t x_dtype = PG_F32, int32_t y_dtype = PG_F32) {
     using namespace pg;
     int rc = conv_validate(N, Cin, Cout, H, W, ksize, up, operand_format);
     if (rc != PG_OK) return rc;
@@ -966,10 +1027,27 @@ static int conv_run_impl(const float* x, const void* wpack, const float* styles,
                             "conv2d_igemm_spade: gamma and beta (2C <= 256 channels, C %% 16 == 0) must share one N tile");
     p.dbg = g_conv_dbg;
     p.pipe = env_int("PASTA_B200_CONV_PIPE", 0); p.ldmode = env_int("PASTA_B200_CONV_LDMODE", 0); p.dbgmode = env_int("PASTA_B200_CONV_DBGMODE", 0); p.lean = env_int("PASTA_B200_CONV_LEAN", 1);
+    p.cgroups = 1;
     p.pw_magic = (uint32_t)((0x100000000ull + (uint64_t)pl.PW - 1) / (uint64_t)pl.PW);
     p.w_magic = (uint32_t)((0x100000000ull + (uint64_t)W - 1) / (uint64_t)W);
     p.vec2 = (!down2 && !im2col && W % 2 == 0 && ((uintptr_t)x & 7) == 0 && ((uintptr_t)x2 & 7) == 0 && env_int("PASTA_B200_CONV_VEC2", 1)) ? 1 : 0;
     const bool scale = styles != nullptr || in_act != PG_ACT_LINEAR || in_gain != 1.f;
+    PG_REQUIRE((x_dtype == PG_F32 || x_dtype == PG_F16) && (y_dtype == PG_F32 || y_dtype == PG_F16), "conv2d_igemm: x / y must be float32 or float16");
+    p.in_half = x_dtype == PG_F16; p.out_half = y_dtype == PG_F16;
+    if (p.in_half) {
+        // fp16 NCHW input: taken as the operand bits (no conversion), so no input scale / activation, fp16 operand format, the aligned pair loader
+        const int pairs = (pl.PA + 3) / 2, tpw = (2 * ((pairs + 31) / 32) + kConvWarps - 1) / kConvWarps;
+        PG_REQUIRE(!scale && !x2 && !down2 && !im2col && operand_format == 0 && W % 2 == 0 && ((uintptr_t)x & 3) == 0 && tpw <= 6,
+                   "conv2d_igemm: a float16 input needs a plain (unmodulated, no input activation) stride-1 layer, fp16 operands, even W");
+        p.vec2 = 1;
+    }
+    {   // converter warp groups: only with the lean / fp16 loaders, and only while the doubled per-warp task count stays in the register batches
+        const int cg = env_int("PASTA_B200_CONV_CGROUPS", 1);      // measured neutral (profiles/r1 notes in DESIGN.md): off by default
+        const int pairs = (pl.PA + 3) / 2, nt = 2 * ((pairs + 31) / 32);
+        if (p.vec2 && (p.lean || p.in_half) && cg == 2 && (nt + kConvWarps / 2 - 1) / (kConvWarps / 2) <= 6) p.cgroups = 2;
+        if (p.vec2 && p.lean && !p.in_half && p.cgroups == 1 && (nt + kConvWarps - 1) / kConvWarps > 6) p.lean = 0;
+    }
+    PG_REQUIRE(!(p.out_half && residual), "conv2d_igemm: the residual add is not available with a float16 output");
     auto kern = scale ? conv_igemm_kernel<true> : conv_igemm_kernel<false>;
     PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     dim3 grid((unsigned)(N * pl.tiles_per_img), (unsigned)pl.ntiles_n);
@@ -990,18 +1068,18 @@ extern "C" int pg_conv2d_igemm_run2(const float* x, const float* x2, int32_t Cin
                                     const float* noise, int64_t noise_batch_stride, const float* bias, const float* residual, float* y,
                                     int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t ksize, int32_t up,
                                     int32_t in_act, float in_alpha, float in_gain,
-                                    int32_t act, float alpha, float gain, float clamp, int32_t operand_format, void* stream) {
+                                    int32_t act, float alpha, float gain, float clamp, int32_t operand_format, int32_t x_dtype, int32_t y_dtype, void* stream) {
     return conv_run_impl(x, wpack, styles, dcoefs, noise, noise_batch_stride, bias, y, N, Cin, Cout, H, W, ksize, up, in_act, in_alpha, in_gain,
-                         act, alpha, gain, clamp, operand_format, stream, nullptr, nullptr, nullptr, x2, Cin1, residual);
+                         act, alpha, gain, clamp, operand_format, stream, nullptr, nullptr, nullptr, x2, Cin1, residual, x_dtype, y_dtype);
 }
 
 extern "C" int pg_conv2d_igemm_spade_run(const float* feat, const void* wpack_gamma_beta, const float* x, const float* mean, const float* rstd,
                                          float* y, int32_t N, int32_t Cin, int32_t C, int32_t H, int32_t W, int32_t ksize,
-                                         int32_t act, float alpha, float gain, int32_t operand_format, void* stream) {
+                                         int32_t act, float alpha, float gain, int32_t operand_format, int32_t feat_dtype, int32_t y_dtype, void* stream) {
     using namespace pg;
     PG_REQUIRE(x && mean && rstd, "conv2d_igemm_spade: x, mean and rstd must be device pointers");
     return conv_run_impl(feat, wpack_gamma_beta, nullptr, nullptr, nullptr, 0, nullptr, y, N, Cin, 2 * C, H, W, ksize, 1, PG_ACT_LINEAR, 0.f, 1.f,
-                         act, alpha, gain, -1.f, operand_format, stream, x, mean, rstd);
+                         act, alpha, gain, -1.f, operand_format, stream, x, mean, rstd, nullptr, 0, nullptr, feat_dtype, y_dtype);
 }
 
 extern "C" int pg_conv2d_igemm_fwd(const float* x, const float* w, const float* fir, const float* styles, const float* dcoefs,

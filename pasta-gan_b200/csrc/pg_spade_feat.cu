@@ -46,13 +46,16 @@ __global__ void __launch_bounds__(kSfThreads) masked_plane_sum_kernel(const floa
     }
 }
 
+template <bool HALF>
 __global__ void __launch_bounds__(kSfThreads) masked_fill_kernel(const float* __restrict__ feat, const float* __restrict__ rest, const float* __restrict__ fill,
                                                                  float* __restrict__ out, int C, long long hw, long long out_batch_stride, int vec) {
     const long long plane = blockIdx.y;                       // n * C + c
     const int n = (int)(plane / C), c = (int)(plane - (long long)n * C);
     const float* fp = feat + (size_t)plane * hw;
     const float* rp = rest + (size_t)n * hw;
-    float* op = out + (size_t)n * out_batch_stride + (size_t)c * hw;
+    float* op = HALF ? nullptr : out + (size_t)n * out_batch_stride + (size_t)c * hw;
+    __half* oh = HALF ? reinterpret_cast<__half*>(out) + (size_t)n * out_batch_stride + (size_t)c * hw : nullptr;
+    auto h2 = [](float a, float b) { unsigned int r; asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a)); return r; };
     const float m = __ldg(fill + plane);
     if (vec) {
         const long long n4 = hw >> 2;
@@ -61,12 +64,15 @@ __global__ void __launch_bounds__(kSfThreads) masked_fill_kernel(const float* __
             float4 y;
             y.x = a.x * (1.f - r.x) + m * r.x; y.y = a.y * (1.f - r.y) + m * r.y;
             y.z = a.z * (1.f - r.z) + m * r.z; y.w = a.w * (1.f - r.w) + m * r.w;
-            reinterpret_cast<float4*>(op)[i] = y;
+            if (HALF) reinterpret_cast<uint2*>(oh)[i] = make_uint2(h2(y.x, y.y), h2(y.z, y.w));
+            else      reinterpret_cast<float4*>(op)[i] = y;
         }
     } else {
         for (long long i = (long long)blockIdx.x * kSfThreads + threadIdx.x; i < hw; i += (long long)gridDim.x * kSfThreads) {
             const float r = __ldg(rp + i);
-            op[i] = __ldg(fp + i) * (1.f - r) + m * r;
+            const float y = __ldg(fp + i) * (1.f - r) + m * r;
+            if (HALF) reinterpret_cast<unsigned short*>(oh)[i] = (unsigned short)(h2(y, 0.f) & 0xffffu);
+            else      op[i] = y;
         }
     }
 }
@@ -84,17 +90,20 @@ extern "C" int pg_masked_plane_sum(const float* feat, const float* mask, float* 
 }
 
 extern "C" int pg_masked_fill(const float* feat, const float* rest, const float* fill, float* out, int64_t N, int64_t C, int64_t hw,
-                              int64_t out_batch_stride, void* stream) {
+                              int64_t out_batch_stride, int32_t out_dtype, void* stream) {
     using namespace pg;
     PG_REQUIRE(N >= 0 && C >= 1 && hw >= 1 && N * C <= 65535 * 64LL && out_batch_stride >= C * hw, "masked_fill: bad sizes");
     if (N == 0) return PG_OK;
     PG_REQUIRE(feat && rest && fill && out, "masked_fill: feat, rest, fill and out must be device pointers");
     PG_REQUIRE(N * C <= 65535, "masked_fill: N * C must fit gridDim.y");
-    const int vec = (hw % 4 == 0) && (out_batch_stride % 4 == 0) && aligned16(feat) && aligned16(rest) && aligned16(out);
+    PG_REQUIRE(out_dtype == PG_F32 || out_dtype == PG_F16, "masked_fill: out must be float32 or float16");
+    const bool half = out_dtype == PG_F16;
+    const int vec = (hw % 4 == 0) && (out_batch_stride % 4 == 0) && aligned16(feat) && aligned16(rest) && (half ? ((uintptr_t)out & 7) == 0 : aligned16(out));
     const long long per = vec ? hw / 4 : hw;
     unsigned gx = (unsigned)((per + kSfThreads * 4 - 1) / (kSfThreads * 4));
     if (gx < 1) gx = 1;
     dim3 grid(gx, (unsigned)(N * C));
-    masked_fill_kernel<<<grid, kSfThreads, 0, (cudaStream_t)stream>>>(feat, rest, fill, out, (int)C, (long long)hw, (long long)out_batch_stride, vec);
+    if (half) masked_fill_kernel<true><<<grid, kSfThreads, 0, (cudaStream_t)stream>>>(feat, rest, fill, out, (int)C, (long long)hw, (long long)out_batch_stride, vec);
+    else      masked_fill_kernel<false><<<grid, kSfThreads, 0, (cudaStream_t)stream>>>(feat, rest, fill, out, (int)C, (long long)hw, (long long)out_batch_stride, vec);
     return launch_status("masked_fill", 1);
 }

@@ -61,7 +61,7 @@ def cuda_ops():
             name='sm100a',
             setup_filter=U.setup_filter, upfirdn2d=U.upfirdn2d, filter2d=U.filter2d, upsample2d=U.upsample2d,
             downsample2d=U.downsample2d, bias_act=B.bias_act, conv2d_resample=C.conv2d_resample, fma=F.fma,
-            modulated_conv2d=modulated_conv2d, conv_layer=conv_layer, modconv_layer=modconv_layer, torgb_skip=_torgb_skip, spade_conv_norm=_spade_conv_norm, masked_mean_fill=_masked_mean_fill,
+            modulated_conv2d=modulated_conv2d, conv_layer=conv_layer, modconv_layer=modconv_layer, torgb_skip=_torgb_skip, spade_conv_norm=_spade_conv_norm, masked_mean_fill=_masked_mean_fill, half_intermediates=_half_intermediates,
             instance_stats=lambda x: K.instance_stats(x) if (K.enabled and x.is_cuda and x.dtype == torch.float32) else None,
             act_def_gain={k: float(v.def_gain) for k, v in B.activation_funcs.items()},
         )
@@ -174,7 +174,7 @@ def _weight_sq_sums(weight):
 
 
 def conv_layer(x, w, b=None, f=None, up=1, down=1, padding=0, flip_weight=True, act='linear', act_gain=1.0, clamp=None,
-               in_act=None, in_gain=1.0, w_scale=1.0, cache_weights=False, x2=None, residual=None):
+               in_act=None, in_gain=1.0, w_scale=1.0, cache_weights=False, x2=None, residual=None, out_dtype=None, half_ok=False):
     """Product form of one plain conv layer: [in_act([x ; x2]) * in_gain ->] conv2d_resample -> bias_act [-> + residual].  When the tcgen05
     kernel covers the shape the whole layer is ONE launch (bias, activation, gain, clamp and the residual add live in the GEMM epilogue; the
     SPADE pre-activation and the channel concatenation live in the operand prologue); otherwise it is composed from the same operators
@@ -182,9 +182,12 @@ def conv_layer(x, w, b=None, f=None, up=1, down=1, padding=0, flip_weight=True, 
     from .torch_utils.ops import conv_igemm as K, conv2d_resample as C, bias_act as B
     pad4 = (padding,) * 4 if isinstance(padding, int) else None
     if act in ('linear', 'relu', 'lrelu') and in_act in (None, 'relu', 'lrelu') and \
-            K.supported(x, w, up=up, down=down, f=f, padding=pad4, x2=x2, residual=residual):
+            K.supported(x, w, up=up, down=down, f=f, padding=pad4, x2=x2, residual=residual, allow_half=half_ok):
         return K.conv2d_igemm(x, w, f=f, up=up, down=down, flip_weight=flip_weight, bias=b, in_act=in_act or 'linear', in_gain=in_gain,
-                              act=act, gain=act_gain, clamp=clamp, w_scale=w_scale, cache_weights=cache_weights, x2=x2, residual=residual)
+                              act=act, gain=act_gain, clamp=clamp, w_scale=w_scale, cache_weights=cache_weights, x2=x2, residual=residual,
+                              out_dtype=out_dtype or torch.float32)
+    if half_ok and x.dtype == torch.float16:
+        x = x.float()                                     # an fp16 intermediate of ours reached a layer the tcgen05 kernel does not cover
     if x2 is not None:
         x = torch.cat([x, x2.to(x.dtype)], dim=1)
     if in_act is not None:
@@ -194,7 +197,8 @@ def conv_layer(x, w, b=None, f=None, up=1, down=1, padding=0, flip_weight=True, 
     x = C.conv2d_resample(x=x, w=w.to(x.dtype), f=f, up=up, down=down, padding=padding, flip_weight=flip_weight)
     if not (b is None and act == 'linear' and act_gain == 1 and clamp is None):
         x = B.bias_act(x, b, act=act, gain=act_gain, clamp=clamp)
-    return x if residual is None else residual.add_(x)
+    x = x if residual is None else residual.add_(x)
+    return x if out_dtype is None else x.to(out_dtype)
 
 
 def modconv_layer(x, weight, styles, noise=None, up=1, padding=0, resample_filter=None, demodulate=True, flip_weight=True,
@@ -216,7 +220,7 @@ def modconv_layer(x, weight, styles, noise=None, up=1, padding=0, resample_filte
     return B.bias_act(x, bias, act=act, gain=act_gain, clamp=clamp)
 
 
-def _spade_conv_norm(x, actv, w_gamma, w_beta, w_scale, post_act, stats=None):
+def _spade_conv_norm(x, actv, w_gamma, w_beta, w_scale, post_act, stats=None, out_dtype=None):
     """Product SPADE normalisation: instance-norm + (1 + gamma) * . + beta (+ the consumer's pre-activation) inside the epilogue of the
     merged gamma|beta convolution; None when the shape is not covered."""
     from .torch_utils.ops import conv_igemm as K
@@ -225,7 +229,15 @@ def _spade_conv_norm(x, actv, w_gamma, w_beta, w_scale, post_act, stats=None):
     act, gain = post_act if post_act is not None else ('linear', 1.0)
     if act not in ('linear', 'relu', 'lrelu'):
         return None
-    return K.spade_conv_norm(x, actv, w_gamma, w_beta, w_scale=w_scale, act=act, gain=gain, stats=stats)
+    return K.spade_conv_norm(x, actv, w_gamma, w_beta, w_scale=w_scale, act=act, gain=gain, stats=stats, out_dtype=out_dtype or torch.float32)
+
+
+def _half_intermediates(x):
+    """fp16 for tensors that only travel between two tcgen05 convolutions (SPADE `actv`, the normalised maps, the garment features): the
+    consumer rounds to fp16 operands anyway, so the values it multiplies are the same bits at half the traffic."""
+    from .torch_utils.ops import conv_igemm as K
+    return (K.enabled and K.operand_format == 'fp16' and os.environ.get('PASTA_B200_HALF_INTERMEDIATES', '1') != '0' and x.is_cuda and
+            not torch.is_grad_enabled() and x.shape[3] % 2 == 0 and x.shape[3] <= 256)
 
 
 def _masked_mean_fill(feat, valid, rest, out):
@@ -381,6 +393,8 @@ class Conv2dLayer(OpsModule):
         clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
         kw = dict(f=self.resample_filter, up=self.up, down=self.down, padding=self.padding, flip_weight=(self.up == 1),
                   w_scale=float(self.weight_gain), cache_weights=True, x2=x2, residual=residual)
+        if isinstance(self, SpadeConv2dLayer):
+            kw['half_ok'] = True                          # SPADE convs may be fed the fp16 intermediates of the norm blocks
         if pre_act is None:
             return layer(x, w, b, act=self.activation, act_gain=self.act_gain * gain, clamp=clamp, **kw)
         if not pre_act:                                   # SPADE layer called with no_act=True: bare convolution
@@ -617,18 +631,23 @@ class SpadeNormBlock(OpsModule):
         self.conv_beta = SpadeConv2dLayer(norm_channels, norm_channels, kernel_size=3, bias=False)
         self.param_free_norm = nn.InstanceNorm2d(norm_channels, affine=False)
 
-    def forward(self, x, denorm_feats, post_act=None, stats=None):
+    def forward(self, x, denorm_feats, post_act=None, stats=None, out_half=False):
         """``post_act = (name, gain)``: apply the pre-activation of the Spade conv that consumes the result here (then call it with
         ``no_act=True``).  ``stats``: (mean, rstd) of ``x`` when the caller already has them (two norm blocks of a SPADE res-block
-        normalise the same tensor); only used on the fused path."""
+        normalise the same tensor); only used on the fused path.  ``out_half``: the caller feeds the result straight into a bare Spade
+        conv, so it may be an fp16 tensor when the operator table keeps fp16 intermediates."""
         fused = getattr(self.ops, 'spade_conv_norm', None)
         if fused is not None:
+            half = getattr(self.ops, 'half_intermediates', None)
+            half = torch.float16 if (half is not None and half(x)) else None
             actv = self.ops.conv_layer(denorm_feats, self.conv_mlp.weight, None, padding=1, act='relu', act_gain=1.0,
-                                       w_scale=float(self.conv_mlp.weight_gain), cache_weights=True)
-            y = fused(x, actv, self.conv_gamma.weight, self.conv_beta.weight, float(self.conv_gamma.weight_gain), post_act, stats)
+                                       w_scale=float(self.conv_mlp.weight_gain), cache_weights=True, out_dtype=half, half_ok=True)   # consumed by the next launch only
+            y = fused(x, actv, self.conv_gamma.weight, self.conv_beta.weight, float(self.conv_gamma.weight_gain), post_act, stats,
+                      half if (post_act is not None and out_half) else None)
             if y is not None:
                 return y
-        actv = self.conv_mlp_act(self.conv_mlp(denorm_feats, no_act=True))
+            actv = actv.float()
+        actv = self.conv_mlp_act(self.conv_mlp(denorm_feats.to(x.dtype), no_act=True))
         gamma = self.conv_gamma(actv, no_act=True)
         beta = self.conv_beta(actv, no_act=True)
         y = self.param_free_norm(x) * (1 + gamma) + beta
@@ -658,9 +677,9 @@ class SpadeResBlockV2(OpsModule):
         pre = lambda conv, gain: (conv.activation, float(conv.act_gain * gain))
         stats_fn = getattr(self.ops, 'instance_stats', None)
         stats = stats_fn(x) if stats_fn is not None and not (torch.is_grad_enabled() and x.requires_grad) else None   # shared by spade_skip / spade0
-        y = self.skip(self.spade_skip(x, denorm_feat, post_act=pre(self.skip, np.sqrt(0.5)), stats=stats), no_act=True)
-        x = self.conv0(self.spade0(x, denorm_feat, post_act=pre(self.conv0, 1), stats=stats), no_act=True)
-        return self.conv1(self.spade1(x, denorm_feat, post_act=pre(self.conv1, np.sqrt(0.5))), no_act=True, residual=y)
+        y = self.skip(self.spade_skip(x, denorm_feat, post_act=pre(self.skip, np.sqrt(0.5)), stats=stats, out_half=True), no_act=True)
+        x = self.conv0(self.spade0(x, denorm_feat, post_act=pre(self.conv0, 1), stats=stats, out_half=True), no_act=True)
+        return self.conv1(self.spade1(x, denorm_feat, post_act=pre(self.conv1, np.sqrt(0.5)), out_half=True), no_act=True, residual=y)
 
 
 class SynthesisBlockFull(OpsModule):
@@ -806,7 +825,9 @@ class SynthesisNetworkFull(OpsModule):
                 x_128, img_128 = x.clone(), img.clone()
         label = torch.argmax(torch.softmax(parsing.detach(), dim=1), dim=1)[:, None].float()
         cf = self.spade_encoder[-1].conv1.weight.shape[0]                 # channels of one garment's feature map (128)
-        spade_feat = torch.empty([label.shape[0], 2 * cf, label.shape[2] // 2, label.shape[3] // 2], dtype=torch.float32, device=label.device)
+        half = getattr(self.ops, 'half_intermediates', None)
+        feat_dtype = torch.float16 if (half is not None and label.is_cuda and half(label[:, :, ::2, ::2])) else torch.float32   # read by conv_mlp only
+        spade_feat = torch.empty([label.shape[0], 2 * cf, label.shape[2] // 2, label.shape[3] // 2], dtype=feat_dtype, device=label.device)
         self.get_spade_feat((label == 1).float(), denorm_upper_mask, denorm_upper_input, out=spade_feat[:, :cf])      # upper | lower (:5831)
         self.get_spade_feat((label == 2).float(), denorm_lower_mask, denorm_lower_input, out=spade_feat[:, cf:])
         x = x_128

@@ -18,10 +18,12 @@ enabled = os.environ.get('PASTA_B200_CONV', '1') != '0'
 operand_format = os.environ.get('PASTA_B200_CONV_FMT', 'fp16')
 
 
-def supported(x, w, up=1, down=1, groups=1, f=None, padding=None, flip_filter=False, x2=None, residual=None):
+def supported(x, w, up=1, down=1, groups=1, f=None, padding=None, flip_filter=False, x2=None, residual=None, allow_half=False):
     """Shapes the kernel covers: dense fp32 NCHW on CUDA, 1x1 / 3x3, stride 1, 'same' padding, optional polyphase up-2."""
-    if not (enabled and x.is_cuda and x.dtype == torch.float32 and w.dtype == torch.float32 and x.ndim == 4):
+    if not (enabled and x.is_cuda and x.dtype in (torch.float32, torch.float16) and w.dtype == torch.float32 and x.ndim == 4):
         return False
+    if x.dtype == torch.float16 and not (allow_half and half_input_ok(x, w, up, down, x2)):
+        return False                                     # fp16 activations of the reference's own fp16 blocks (discriminator) keep their path
     if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad):
         return False
     k = int(w.shape[2])
@@ -45,6 +47,14 @@ def supported(x, w, up=1, down=1, groups=1, f=None, padding=None, flip_filter=Fa
     if down == 2 and x.data_ptr() % 8:
         return False
     return True
+
+
+def half_input_ok(x, w, up=1, down=1, x2=None):
+    """fp16 NCHW activations are accepted as operand bits by plain stride-1 1x1 / 3x3 layers with even W (include/pasta_b200.h); W <= 256 keeps the
+    converter's task count inside the register-batched loader."""
+    k = int(w.shape[2])
+    return (operand_format == 'fp16' and up == 1 and down == 1 and x2 is None and k in (1, 3) and (k == 1 or int(w.shape[1]) * k * k > 160) and
+            x.shape[3] % 2 == 0 and x.shape[3] <= 256 and x.data_ptr() % 4 == 0)
 
 
 _pack_cache = {}          # (id(param), version, ...) -> (param, packed weights): inference packs each parameter once
@@ -79,7 +89,7 @@ def _packed_weights(capi, w, f, w_scale, up, flip_weight, fmt_code, cache):
 
 def conv2d_igemm(x, w, f=None, up=1, down=1, flip_weight=True, styles=None, dcoefs=None, noise=None, bias=None,
                  in_act='linear', in_alpha=0.2, in_gain=1.0, act='linear', alpha=0.2, gain=1.0, clamp=None, fmt=None,
-                 w_scale=1.0, cache_weights=False, x2=None, residual=None):
+                 w_scale=1.0, cache_weights=False, x2=None, residual=None, out_dtype=torch.float32):
     """y = clamp(act(dcoefs * conv(styles * in_gain * in_act([x ; x2]), w * w_scale) + noise + bias) * gain) + residual; see include/pasta_b200.h.
     ``x2``: second part of the input along channels (fused torch.cat); ``residual``: tensor of the output's shape added last."""
     capi = _backend.capi()
@@ -95,7 +105,10 @@ def conv2d_igemm(x, w, f=None, up=1, down=1, flip_weight=True, styles=None, dcoe
     assert not (up == 2 and down == 2)
     mode = -2 if down == 2 else up                       # PG_CONV_DOWN2 / 2 / 1
     oh, ow = (h // 2, wd // 2) if down == 2 else (h * up, wd * up)
-    y = torch.empty([n, cout, oh, ow], dtype=torch.float32, device=x.device)
+    assert out_dtype in (torch.float32, torch.float16) and x.dtype in (torch.float32, torch.float16)
+    if x.dtype == torch.float16:
+        assert styles is None and in_act == 'linear' and in_gain == 1.0 and half_input_ok(x, w, up, down, x2), 'float16 input: plain stride-1 layer only'
+    y = torch.empty([n, cout, oh, ow], dtype=out_dtype, device=x.device)
     nb_stride = 0
     if noise is not None:
         noise = noise.to(torch.float32).contiguous()
@@ -124,14 +137,14 @@ def conv2d_igemm(x, w, f=None, up=1, down=1, flip_weight=True, styles=None, dcoe
         wpack = _packed_weights(capi, w, f, w_scale, mode, flip_weight, fmt_code, cache_weights)
         # algorithmic FLOPs: output pixels for stride-1 / down-2, INPUT pixels for up-2 (zero-inserted taps excluded)
         sp = capi.span('conv_igemm', flops=2 * n * cout * cin * k * k * (oh * ow if up == 1 else h * wd),
-                       nbytes=4 * (x.numel() + (x2.numel() if x2 is not None else 0) + y.numel() * (2 if residual is not None else 1) + w.numel()),
+                       nbytes=x.element_size() * x.numel() + 4 * ((x2.numel() if x2 is not None else 0) + (y.numel() if residual is not None else 0) + w.numel()) + y.element_size() * y.numel(),
                        tag=f'{cin}->{cout} @{h}x{wd} k{k} mode{mode}' + (' mod' if styles is not None else '') + (' cat' if x2 is not None else '') + (' res' if residual is not None else '') + (f' in_{in_act}' if in_act != 'linear' else ''))
         rc = capi.load().pg_conv2d_igemm_run2(capi.ptr(x), capi.ptr(x2), cin1, capi.ptr(wpack), capi.ptr(styles), capi.ptr(dcoefs),
                                               capi.ptr(noise), nb_stride, capi.ptr(bias), capi.ptr(residual), capi.ptr(y),
                                               n, cin, cout, h, wd, k, mode,
                                               _ACT[in_act], float(in_alpha), float(in_gain),
                                               _ACT[act], float(alpha), float(gain), float(-1 if clamp is None else clamp),
-                                              fmt_code, capi.current_stream(x.device))
+                                              fmt_code, capi.dtype_code(x.dtype), capi.dtype_code(out_dtype), capi.current_stream(x.device))
         capi.check(rc, 'pg_conv2d_igemm_run2')
         if sp:
             sp.close()
@@ -154,12 +167,14 @@ def _gamma_beta_weights(w_gamma, w_beta):
 
 
 def spade_supported(x, feat, w_gamma, w_beta):
-    if not (enabled and x.is_cuda and x.dtype == torch.float32 and feat.dtype == torch.float32 and x.ndim == 4):
+    if not (enabled and x.is_cuda and x.dtype == torch.float32 and feat.dtype in (torch.float32, torch.float16) and x.ndim == 4):
         return False
     if torch.is_grad_enabled() and (x.requires_grad or feat.requires_grad or w_gamma.requires_grad):
         return False
     c = int(x.shape[1])
     k = int(w_gamma.shape[2])
+    if feat.dtype == torch.float16 and not half_input_ok(feat, w_gamma):
+        return False
     return (w_gamma.shape == w_beta.shape and w_gamma.shape[0] == c and 2 * c <= 256 and c % 16 == 0 and k in (1, 3) and
             w_gamma.shape[2] == w_gamma.shape[3] and feat.shape[2:] == x.shape[2:] and feat.shape[1] == w_gamma.shape[1] and x.numel() > 0)
 
@@ -182,7 +197,7 @@ def instance_stats(x, eps=1e-5):
     return mean, rstd
 
 
-def spade_conv_norm(x, feat, w_gamma, w_beta, w_scale=1.0, act='linear', alpha=0.2, gain=1.0, eps=1e-5, fmt=None, stats=None):
+def spade_conv_norm(x, feat, w_gamma, w_beta, w_scale=1.0, act='linear', alpha=0.2, gain=1.0, eps=1e-5, fmt=None, stats=None, out_dtype=torch.float32):
     """act(instance_norm(x) * (1 + conv(feat, w_gamma)) + conv(feat, w_beta)) * gain  in one tcgen05 launch (gamma / beta stay in TMEM)."""
     capi = _backend.capi()
     n, c, h, wd = (int(v) for v in x.shape)
@@ -192,15 +207,15 @@ def spade_conv_norm(x, feat, w_gamma, w_beta, w_scale=1.0, act='linear', alpha=0
     mean, rstd = stats if stats is not None else instance_stats(x, eps)      # `stats`: reuse when several norm blocks share x
     wcat = _gamma_beta_weights(w_gamma, w_beta)
     fmt_code = _FMT[fmt or operand_format]
-    y = torch.empty_like(x)
+    y = torch.empty_like(x, dtype=out_dtype)
     with torch.cuda.device(x.device):
         capi.require_device()
         wpack = _packed_weights(capi, wcat, None, w_scale, 1, True, fmt_code, True)
-        sp = capi.span('conv_igemm', flops=2 * n * 2 * c * cin * k * k * h * wd, nbytes=4 * (2 * x.numel() + feat.numel() + wcat.numel()),
-                       tag=f'{cin}->{2 * c} @{h}x{wd} k{k} spade')
+        sp = capi.span('conv_igemm', flops=2 * n * 2 * c * cin * k * k * h * wd, nbytes=4 * (x.numel() + wcat.numel()) + feat.element_size() * feat.numel() + y.element_size() * y.numel(),
+                       tag=f'{cin}->{2 * c} @{h}x{wd} k{k} spade' + (' in16' if feat.dtype == torch.float16 else '') + (' out16' if out_dtype == torch.float16 else ''))
         rc = capi.load().pg_conv2d_igemm_spade_run(capi.ptr(feat), capi.ptr(wpack), capi.ptr(x), capi.ptr(mean), capi.ptr(rstd), capi.ptr(y),
                                                    n, cin, c, h, wd, k, _ACT[act], float(alpha), float(gain), fmt_code,
-                                                   capi.current_stream(x.device))
+                                                   capi.dtype_code(feat.dtype), capi.dtype_code(out_dtype), capi.current_stream(x.device))
         capi.check(rc, 'pg_conv2d_igemm_spade_run')
         if sp:
             sp.close()

@@ -8,7 +8,7 @@ from . import _backend
 
 def supported(feat, valid, rest, out):
     return (feat.is_cuda and feat.dtype == torch.float32 and feat.ndim == 4 and valid.dtype == torch.float32 and rest.dtype == torch.float32 and
-            out.dtype == torch.float32 and not (torch.is_grad_enabled() and feat.requires_grad) and feat.shape[0] * feat.shape[1] <= 65535)
+            out.dtype in (torch.float32, torch.float16) and not (torch.is_grad_enabled() and feat.requires_grad) and feat.shape[0] * feat.shape[1] <= 65535)
 
 
 def masked_mean_fill(feat, valid, rest, out, min_count=10):
@@ -34,8 +34,8 @@ def masked_mean_fill(feat, valid, rest, out, min_count=10):
         enough = (count > min_count).to(feat.dtype)
         count = count * enough + (h * w) * (1 - enough)
         fill = (sums / count).contiguous()
-        sp = capi.span('spade_feat', nbytes=8 * feat.numel(), tag='masked fill')
-        capi.check(lib.pg_masked_fill(capi.ptr(feat), capi.ptr(rest), capi.ptr(fill), capi.ptr(out), n, c, h * w, int(out.stride(0)), stream),
+        sp = capi.span('spade_feat', nbytes=(4 + out.element_size()) * feat.numel(), tag='masked fill')
+        capi.check(lib.pg_masked_fill(capi.ptr(feat), capi.ptr(rest), capi.ptr(fill), capi.ptr(out), n, c, h * w, int(out.stride(0)), capi.dtype_code(out.dtype), stream),
                    'pg_masked_fill')
         if sp:
             sp.close()

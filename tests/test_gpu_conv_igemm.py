@@ -230,3 +230,27 @@ def test_masked_mean_fill(shape):
     assert out.data_ptr() == buf[:, 2:2 + c].data_ptr()
     assert rel_err(buf[:, 2:2 + c], ref) < 1e-5
     assert torch.isnan(buf[:, :2]).all() and torch.isnan(buf[:, 2 + c:]).all()          # neighbours of the slice untouched
+
+
+@pytest.mark.parametrize('shape', [(2, 128, 64, 32, 32, 3), (1, 256, 128, 128, 128, 3), (2, 64, 48, 20, 28, 1), (1, 24, 32, 16, 16, 3), (1, 128, 128, 64, 256, 3)])
+def test_half_intermediates_are_bit_identical(cv, shape):
+    """An fp16 NCHW input is taken as the operand bits and an fp16 output is the fp32 result rounded like the consumer's loader would round it:
+    conv(x.half()) == conv(x.half().float()) exactly, and conv(..., out_dtype=half) == conv(...).half() (same kernel, same accumulation order)."""
+    n, cin, cout, h, w, k = shape
+    torch.manual_seed(sum(shape))
+    x = (torch.randn(n, cin, h, w) * 3).to(DEV)
+    wt = (torch.randn(cout, cin, k, k) / (cin * k * k) ** 0.5).to(DEV)
+    b = torch.randn(cout, device=DEV)
+    xh = x.half()
+    y32 = cv.conv2d_igemm(xh.float(), wt, bias=b, act='relu', gain=1.3)
+    y_in16 = cv.conv2d_igemm(xh, wt, bias=b, act='relu', gain=1.3)
+    assert torch.equal(y_in16, y32)
+    y_out16 = cv.conv2d_igemm(xh, wt, bias=b, act='relu', gain=1.3, out_dtype=torch.float16)
+    assert y_out16.dtype == torch.float16 and torch.equal(y_out16, y32.half())
+    # SPADE epilogue with fp16 feature input and fp16 output
+    if k == 3 and cout % 16 == 0 and 2 * cout <= 256 and cin * 9 > 160:
+        xs = torch.randn(n, cout, h, w, device=DEV)
+        wg = torch.randn(cout, cin, 3, 3, device=DEV) / (cin * 9) ** 0.5; wb = torch.randn(cout, cin, 3, 3, device=DEV) / (cin * 9) ** 0.5
+        r32 = cv.spade_conv_norm(xs, xh.float(), wg, wb, act='relu', gain=1.1)
+        r16 = cv.spade_conv_norm(xs, xh, wg, wb, act='relu', gain=1.1, out_dtype=torch.float16)
+        assert torch.equal(r16, r32.half())
