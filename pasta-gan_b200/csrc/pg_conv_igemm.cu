@@ -41,6 +41,7 @@ struct ConvParams {
     const void* wpack; const float* styles; const float* dcoefs; const float* noise; const float* bias; float* y;
     long long noise_bstride;
     int N, Cin, Cout, H, W, ks;
+    int ntiles_n;              // N tiles (persistent kernel: tile list = n-tile major)
     int PW, Lp, tiles_per_img, NACC, BN, nchunks, ntaps, PA;      // PA: staged strip positions (multiple of 32)
     int SA, SB, tps; uint32_t a_stage_bytes, b_slot_bytes, b_tile_bytes;   // B ring: SB slots of `tps` taps each
     int in_act; float in_alpha, in_gain; int act; float alpha, gain, clamp; int fmt;
@@ -226,12 +227,14 @@ __global__ void conv_prepack_kernel(PackParams p) {
     }
 }
 
+struct MmaRing { int sa, sb; uint32_t pa, pb; };
+
 // MMA issue loop of one CTA, executed by ALL lanes of the MMA warp (uniform control flow); `issue` != 0 on the one lane that issues.
 // KS = kernel size (1 or 3); B ring slots hold KS taps each; NACC accumulators of BN columns.  Everything the tcgen05.mma needs is either a
 // kernel parameter, a compile-time constant or a warp-uniform loop counter, so one MMA costs two uniform adds.
 template <int KS, int NACC>
 __device__ __forceinline__ void mma_issue_loop(const ConvParams& p, uint32_t a_base, uint32_t b_base, uint32_t a_full, uint32_t a_empty,
-                                               uint32_t b_full, uint32_t b_empty, uint32_t acc_full, uint32_t tmem_base, uint32_t issue) {
+                                               uint32_t b_full, uint32_t b_empty, uint32_t acc_full, uint32_t tmem_base, uint32_t issue, MmaRing& ring) {
     const uint32_t hi = (128u >> 4) | (1u << 14);                         // SBO = 128 B, descriptor version 1 (bits 32..47)
     const uint32_t a_lo_const = ((uint32_t)p.PA & 0x3FFF) << 16;          // LBO = PA * 16 B  (>> 4)
     const uint32_t b_lo_const = ((uint32_t)p.BN & 0x3FFF) << 16;          // LBO = BN * 16 B  (>> 4)
@@ -240,7 +243,7 @@ __device__ __forceinline__ void mma_issue_loop(const ConvParams& p, uint32_t a_b
     const uint32_t pw = (uint32_t)p.PW;
     const uint32_t idesc = p.idesc;
     const int nchunks = p.nchunks, SA = p.SA, SB = p.SB;
-    int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+    int sa = ring.sa, sb = ring.sb; uint32_t pa = ring.pa, pb = ring.pb;   // stage / slot cursors continue across the tiles of a persistent CTA
     long long wait_a = 0, wait_b = 0;              // instrumentation (registers; written once at the end)
     for (int ci = 0; ci < nchunks; ci++) {
         long long t0 = p.dbg ? clock64() : 0;
@@ -277,6 +280,7 @@ __device__ __forceinline__ void mma_issue_loop(const ConvParams& p, uint32_t a_b
     }
     if (issue) { PG_TS(3); PG_PUT(8, wait_a); PG_PUT(9, wait_b); }
     if (issue) umma_commit(acc_full);
+    ring.sa = sa; ring.sb = sb; ring.pa = pa; ring.pb = pb;
 }
 
 // Converter task stream of one warp: slots (chunk, idx), idx < tpw, in register batches of BATCH tasks of TREGS floats.  pipelined: the loads of
@@ -318,9 +322,12 @@ __device__ __forceinline__ void stream_tasks(Load&& load_task, Store&& store_tas
 template <bool SCALE, bool IN_HALF, int PER, int ROUNDS>
 __device__ __forceinline__ void convert_vec2(const ConvParams& p, const float* xn, const float* xn2, const int HW, const int cw, const int lane,
                                              const int g_lo, const int g_hi, const int ntasks, const int q0, uint8_t* a_base, const float* s_style,
-                                             uint64_t* a_full, uint64_t* a_empty, long long& wait_e) {
+                                             uint64_t* a_full, uint64_t* a_empty, long long& wait_e,
+                                             const int nwarps = kConvWarps, const int chunk_base = 0, const bool zero_pads = false) {
+    // nwarps: converter warps of the CTA; chunk_base: chunks converted by this CTA before this tile (persistent CTAs: the stage ring continues);
+    // zero_pads: the padding slots of the strip move from tile to tile, so the first use of every stage in a tile re-zeroes them
     constexpr int NS = PER * ROUNDS;
-    const int wpg = kConvWarps / p.cgroups;     // warps per group; group g converts chunks g, g + cgroups, ...
+    const int wpg = nwarps / p.cgroups;         // warps per group; group g converts chunks g, g + cgroups, ...
     const int grp = cw / wpg, gw = cw - grp * wpg;
     const int plane = cw & 1;
     const bool swap = (lane >> 2) & 1;          // lanes sit 32 B apart in the stage: lanes 4..7 of each group of 8 write their second slot first
@@ -344,7 +351,8 @@ __device__ __forceinline__ void convert_vec2(const ConvParams& p, const float* x
     const float in_slope = (p.in_act == PG_ACT_RELU) ? 0.f : p.in_alpha;
     const int nchunks = p.nchunks;
     for (int ci = grp; ci < nchunks; ci += p.cgroups) {
-        const int st = ci % p.SA; const uint32_t ph = (uint32_t)(ci / p.SA) & 1u;
+        const int gci = chunk_base + ci;
+        const int st = gci % p.SA; const uint32_t ph = (uint32_t)(gci / p.SA) & 1u;
         const int c0 = ci * kKC + plane * 8;
         const int nval = p.Cin - c0;                                  // channels of this group that exist (>= 8: all)
         const float* cb = (c0 < p.cin1 ? xn : xn2) + (size_t)c0 * HW;
@@ -387,6 +395,17 @@ __device__ __forceinline__ void convert_vec2(const ConvParams& p, const float* x
                 const long long t0 = p.dbg ? clock64() : 0;
                 mbar_wait(smem_u32(&a_empty[st]), ph ^ 1);
                 if (p.dbg) wait_e += clock64() - t0;
+                if (zero_pads && ci < p.SA) {
+                    for (int sl = gw * 32 + lane; sl < p.PA; sl += wpg * 32) {
+                        const int q = q0 + sl;
+                        bool pad = q < 0 || q >= p.Lp;
+                        if (!pad) { const int hq = (int)__umulhi((uint32_t)q, p.pw_magic); pad = q - hq * p.PW >= p.W; }
+                        if (pad) {
+                            *reinterpret_cast<uint4*>(stage + (size_t)sl * 16) = make_uint4(0u, 0u, 0u, 0u);
+                            *reinterpret_cast<uint4*>(stage + ((size_t)p.PA + sl) * 16) = make_uint4(0u, 0u, 0u, 0u);
+                        }
+                    }
+                }
             }
 #pragma unroll
             for (int u = 0; u < PER; u++) {
@@ -422,6 +441,156 @@ __device__ __forceinline__ void convert_vec2(const ConvParams& p, const float* x
         fence_proxy_async();                               // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&a_full[st]));
+    }
+}
+
+// Epilogue of one output tile for one warp: TMEM lane quarter `quarter`, 16-column chunks part, part + step, ... of every accumulator.
+__device__ __forceinline__ void epilogue_tile(const ConvParams& p, const int n, const int jn, const int m0, const int HW, const uint32_t tmem_base,
+                                              const float* s_scale, const float* s_shift, const int quarter, const int part, const int step, const int lane) {
+    const int ncol_chunks = p.BN / 16;
+    const float slope = (p.act == PG_ACT_LINEAR) ? 1.f : (p.act == PG_ACT_RELU ? 0.f : p.alpha);   // act(v) = max(v,0) + slope*min(v,0)
+    const float cl = p.clamp >= 0.f ? p.clamp : __int_as_float(0x7f800000);
+    const bool do_act = p.act != PG_ACT_LINEAR, do_clamp = p.clamp >= 0.f;
+    const int W2 = 2 * p.W;
+    for (int a = 0; a < p.NACC; a++) {
+        const int q = m0 + a * 128 + quarter * 32 + lane;
+        const int h = (int)__umulhi((uint32_t)q, p.pw_magic), w = q - h * p.PW;
+        const bool ok = q < p.Lp && w < p.W;
+        if (p.spade) {
+            // gamma = columns [0, C), beta = columns [C, 2C) of the same accumulator row; normalise x with the staged statistics
+            const int C = p.cout_real >> 1;
+            const float* xp = p.sp_x + (size_t)n * C * HW + (size_t)h * p.W + w;
+            const size_t yoff = (size_t)n * C * HW + (size_t)h * p.W + w;
+            for (int cc = part; cc < C / 16; cc += step) {
+                uint32_t rg[16], rb[16];
+                tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.BN + cc * 16), rg);
+                tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.BN + C + cc * 16), rb);
+                if (!ok) continue;
+                float xv[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) xv[i] = __ldg(xp + (size_t)(cc * 16 + i) * HW);
+                if (p.out_half) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const float xn_ = fmaf(xv[i], s_scale[cc * 16 + i], s_shift[cc * 16 + i]);
+                        float v = fmaf(xn_, 1.f + __uint_as_float(rg[i]), __uint_as_float(rb[i]));
+                        v = (fmaxf(v, 0.f) + slope * fminf(v, 0.f)) * p.gain;
+                        store_half(p.y, yoff + (size_t)(cc * 16 + i) * HW, v);
+                    }
+                } else {
+                    float* yp = p.y + yoff;
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const float xn_ = fmaf(xv[i], s_scale[cc * 16 + i], s_shift[cc * 16 + i]);
+                        float v = fmaf(xn_, 1.f + __uint_as_float(rg[i]), __uint_as_float(rb[i]));
+                        v = (fmaxf(v, 0.f) + slope * fminf(v, 0.f)) * p.gain;
+                        yp[(size_t)(cc * 16 + i) * HW] = v;
+                    }
+                }
+            }
+            continue;
+        }
+        float nz0 = 0.f;
+        if (ok && p.noise && !p.up2) nz0 = __ldg(p.noise + (size_t)n * p.noise_bstride + (size_t)h * p.W + w) * p.gain;
+        // output element offset / channel stride / valid channels of column chunk cc for this thread's position
+        auto chunk_out = [&](int cc, size_t& off, size_t& ystride, int& oy, int& ox) {
+            const int v0 = jn * p.BN + cc * 16;                  // first (virtual) output channel of this chunk
+            int nvalid = p.Cout - v0; nvalid = nvalid > 16 ? 16 : nvalid;
+            if (!p.up2) {
+                off = ((size_t)n * p.Cout + v0) * HW + (size_t)h * p.W + w;
+                ystride = (size_t)HW; oy = h; ox = w;
+            } else {
+                // polyphase up-2: virtual channel = phase * Cout + o (Cout % 16 == 0, so a chunk has one phase); output is 2H x 2W
+                const int phase = v0 / p.cout_real, o0 = v0 - phase * p.cout_real;
+                oy = 2 * h + (phase >> 1); ox = 2 * w + (phase & 1);
+                ystride = (size_t)4 * HW;
+                off = ((size_t)n * p.cout_real + o0) * ystride + (size_t)oy * W2 + ox;
+            }
+            return nvalid;
+        };
+        // the residual of chunk cc + step is fetched while chunk cc is read from TMEM, transformed and stored (one memory round trip hidden)
+                    float res[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) res[i] = 0.f;
+        auto fetch_res = [&](int cc, float (&dst)[16]) {
+            if (!p.residual || !ok || cc >= ncol_chunks) return;
+            size_t off, ystride; int oy, ox;
+            const int nvalid = chunk_out(cc, off, ystride, oy, ox);
+#pragma unroll
+            for (int i = 0; i < 16; i++) if (i < nvalid) dst[i] = __ldg(p.residual + off + (size_t)i * ystride);
+        };
+        fetch_res(part, res);
+        for (int cc = part; cc < ncol_chunks; cc += step) {
+            float res_next[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) res_next[i] = 0.f;
+            fetch_res(cc + step, res_next);
+            uint32_t r[16];
+            tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.BN + cc * 16), r);
+            if (!ok) continue;
+            size_t off, ystride; int oy, ox;
+            const int nvalid = chunk_out(cc, off, ystride, oy, ox);
+            if (nvalid <= 0) continue;
+            float nz = nz0;
+            if (p.up2 && p.noise) nz = __ldg(p.noise + (size_t)n * p.noise_bstride + (size_t)oy * W2 + ox) * p.gain;
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const float4 a4 = reinterpret_cast<const float4*>(s_scale + cc * 16)[i];
+                const float4 b4 = reinterpret_cast<const float4*>(s_shift + cc * 16)[i];
+                v[4 * i]     = fmaf(__uint_as_float(r[4 * i]),     a4.x, b4.x + nz);
+                v[4 * i + 1] = fmaf(__uint_as_float(r[4 * i + 1]), a4.y, b4.y + nz);
+                v[4 * i + 2] = fmaf(__uint_as_float(r[4 * i + 2]), a4.z, b4.z + nz);
+                v[4 * i + 3] = fmaf(__uint_as_float(r[4 * i + 3]), a4.w, b4.w + nz);
+            }
+            if (do_act) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i], 0.f) + slope * fminf(v[i], 0.f);
+            }
+            if (do_clamp) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) v[i] = fminf(fmaxf(v[i], -cl), cl);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; i++) v[i] += res[i];
+            float* yp = p.y + off;
+            if (p.out_half) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) if (i < nvalid) store_half(p.y, off + (size_t)i * ystride, v[i]);
+            } else if (nvalid == 16) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) yp[(size_t)i * ystride] = v[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; i++) if (i < nvalid) yp[(size_t)i * ystride] = v[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 16; i++) res[i] = res_next[i];
+        }
+    }
+}
+
+// per-sample input scale: style * in_gain (1 * in_gain for plain convs); zero for padded channels
+__device__ __forceinline__ void stage_styles(const ConvParams& p, const int n, float* s_style, const int cin_pad, const int tid, const int nthreads) {
+    for (int c = tid; c < cin_pad; c += nthreads)
+        s_style[c] = (c < p.Cin) ? (p.styles ? (p.down2 ? p.styles[(size_t)n * p.cin_real + ((c % (2 * p.cin_real)) >> 1)] : p.im2col ? p.styles[(size_t)n * p.cin_real + c / (p.im2col * p.im2col)] : p.styles[(size_t)n * p.Cin + c]) : 1.f) * p.in_gain : 0.f;
+}
+
+// epilogue constants with the output gain folded in (relu / lrelu / linear are positively homogeneous, gain > 0)
+__device__ __forceinline__ void stage_epilogue_constants(const ConvParams& p, const int n, const int jn, float* s_scale, float* s_shift, const int tid, const int nthreads) {
+    for (int j = tid; j < p.BN; j += nthreads) {
+        const int v = jn * p.BN + j;
+        const int o = p.up2 ? v % p.cout_real : v;
+        const bool live = v < p.Cout;
+        if (p.spade) {
+            const int C = p.cout_real >> 1;
+            const float r = j < C ? p.sp_rstd[(size_t)n * C + j] : 0.f;
+            s_scale[j] = r;
+            s_shift[j] = j < C ? -p.sp_mean[(size_t)n * C + j] * r : 0.f;
+            continue;
+        }
+        s_scale[j] = live ? (p.dcoefs ? p.dcoefs[(size_t)n * p.cout_real + o] : 1.f) * p.gain : 0.f;
+        s_shift[j] = live && p.bias ? p.bias[o] * p.gain : 0.f;
     }
 }
 
@@ -467,9 +636,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // per-sample input scale: style * in_gain (1 * in_gain for plain convs); zero for padded channels
-    for (int c = threadIdx.x; c < cin_pad; c += kConvThreads)
-        s_style[c] = (c < p.Cin) ? (p.styles ? (p.down2 ? p.styles[(size_t)n * p.cin_real + ((c % (2 * p.cin_real)) >> 1)] : p.im2col ? p.styles[(size_t)n * p.cin_real + c / (p.im2col * p.im2col)] : p.styles[(size_t)n * p.Cin + c]) : 1.f) * p.in_gain : 0.f;
+    stage_styles(p, n, s_style, cin_pad, threadIdx.x, kConvThreads);
     if (p.im2col) {
         const int ks = p.im2col, kk = ks * ks, pad = ks >> 1;
         for (int c = threadIdx.x; c < cin_pad; c += kConvThreads) {
@@ -478,21 +645,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
                                  : make_int2(0, 0x7fff0000);                                    // padding channel: row offset out of range
         }
     }
-    // epilogue constants with the output gain folded in (relu / lrelu / linear are positively homogeneous, gain > 0)
-    for (int j = threadIdx.x; j < p.BN; j += kConvThreads) {
-        const int v = jn * p.BN + j;
-        const int o = p.up2 ? v % p.cout_real : v;
-        const bool live = v < p.Cout;
-        if (p.spade) {
-            const int C = p.cout_real >> 1;
-            const float r = j < C ? p.sp_rstd[(size_t)n * C + j] : 0.f;
-            s_scale[j] = r;
-            s_shift[j] = j < C ? -p.sp_mean[(size_t)n * C + j] * r : 0.f;
-            continue;
-        }
-        s_scale[j] = live ? (p.dcoefs ? p.dcoefs[(size_t)n * p.cout_real + o] : 1.f) * p.gain : 0.f;
-        s_shift[j] = live && p.bias ? p.bias[o] * p.gain : 0.f;
-    }
+    stage_epilogue_constants(p, n, jn, s_scale, s_shift, threadIdx.x, kConvThreads);
     if (p.vec2) {     // the vec2 loader never writes the padding slots of the strip: zero every A stage once
         uint4* z = reinterpret_cast<uint4*>(a_base);
         const int nz = (int)((size_t)p.SA * p.a_stage_bytes / 16);
@@ -527,7 +680,8 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
         const uint32_t ab = smem_u32(a_base), bb = smem_u32(b_base), af = smem_u32(a_full), ae = smem_u32(a_empty), bf = smem_u32(b_full),
                        be = smem_u32(b_empty), accf = smem_u32(acc_full);
         const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
-#define PG_ISSUE(KS_, NACC_) mma_issue_loop<KS_, NACC_>(p, ab, bb, af, ae, bf, be, accf, tb, issue)
+        MmaRing ring = {0, 0, 0u, 0u};
+#define PG_ISSUE(KS_, NACC_) mma_issue_loop<KS_, NACC_>(p, ab, bb, af, ae, bf, be, accf, tb, issue, ring)
         if (p.ks == 3) { if (p.NACC == 4) PG_ISSUE(3, 4); else if (p.NACC == 3) PG_ISSUE(3, 3); else if (p.NACC == 2) PG_ISSUE(3, 2); else PG_ISSUE(3, 1); }
         else           { if (p.NACC == 4) PG_ISSUE(1, 4); else if (p.NACC == 3) PG_ISSUE(1, 3); else if (p.NACC == 2) PG_ISSUE(1, 2); else PG_ISSUE(1, 1); }
 #undef PG_ISSUE
@@ -711,130 +865,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
         mbar_wait(smem_u32(acc_full), 0);
         tc_fence_after();
         if (cw == 0 && lane == 0) PG_TS(4);
-        const int quarter = warp & 3;                          // TMEM lane quarter this warp may read
-        const int part = cw >> 2;                              // the kConvWarps/4 warps of a quarter take 16-column chunks round-robin
-        const int ncol_chunks = p.BN / 16;
-        const float slope = (p.act == PG_ACT_LINEAR) ? 1.f : (p.act == PG_ACT_RELU ? 0.f : p.alpha);   // act(v) = max(v,0) + slope*min(v,0)
-        const float cl = p.clamp >= 0.f ? p.clamp : __int_as_float(0x7f800000);
-        const bool do_act = p.act != PG_ACT_LINEAR, do_clamp = p.clamp >= 0.f;
-        const int W2 = 2 * p.W;
-        for (int a = 0; a < p.NACC; a++) {
-            const int q = m0 + a * 128 + quarter * 32 + lane;
-            const int h = (int)__umulhi((uint32_t)q, p.pw_magic), w = q - h * p.PW;
-            const bool ok = q < p.Lp && w < p.W;
-            if (p.spade) {
-                // gamma = columns [0, C), beta = columns [C, 2C) of the same accumulator row; normalise x with the staged statistics
-                const int C = p.cout_real >> 1;
-                const float* xp = p.sp_x + (size_t)n * C * HW + (size_t)h * p.W + w;
-                const size_t yoff = (size_t)n * C * HW + (size_t)h * p.W + w;
-                for (int cc = part; cc < C / 16; cc += kConvWarps / 4) {
-                    uint32_t rg[16], rb[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.BN + cc * 16), rg);
-                    tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.BN + C + cc * 16), rb);
-                    if (!ok) continue;
-                    float xv[16];
-#pragma unroll
-                    for (int i = 0; i < 16; i++) xv[i] = __ldg(xp + (size_t)(cc * 16 + i) * HW);
-                    if (p.out_half) {
-#pragma unroll
-                        for (int i = 0; i < 16; i++) {
-                            const float xn_ = fmaf(xv[i], s_scale[cc * 16 + i], s_shift[cc * 16 + i]);
-                            float v = fmaf(xn_, 1.f + __uint_as_float(rg[i]), __uint_as_float(rb[i]));
-                            v = (fmaxf(v, 0.f) + slope * fminf(v, 0.f)) * p.gain;
-                            store_half(p.y, yoff + (size_t)(cc * 16 + i) * HW, v);
-                        }
-                    } else {
-                        float* yp = p.y + yoff;
-#pragma unroll
-                        for (int i = 0; i < 16; i++) {
-                            const float xn_ = fmaf(xv[i], s_scale[cc * 16 + i], s_shift[cc * 16 + i]);
-                            float v = fmaf(xn_, 1.f + __uint_as_float(rg[i]), __uint_as_float(rb[i]));
-                            v = (fmaxf(v, 0.f) + slope * fminf(v, 0.f)) * p.gain;
-                            yp[(size_t)(cc * 16 + i) * HW] = v;
-                        }
-                    }
-                }
-                continue;
-            }
-            float nz0 = 0.f;
-            if (ok && p.noise && !p.up2) nz0 = __ldg(p.noise + (size_t)n * p.noise_bstride + (size_t)h * p.W + w) * p.gain;
-            // output element offset / channel stride / valid channels of column chunk cc for this thread's position
-            auto chunk_out = [&](int cc, size_t& off, size_t& ystride, int& oy, int& ox) {
-                const int v0 = jn * p.BN + cc * 16;                  // first (virtual) output channel of this chunk
-                int nvalid = p.Cout - v0; nvalid = nvalid > 16 ? 16 : nvalid;
-                if (!p.up2) {
-                    off = ((size_t)n * p.Cout + v0) * HW + (size_t)h * p.W + w;
-                    ystride = (size_t)HW; oy = h; ox = w;
-                } else {
-                    // polyphase up-2: virtual channel = phase * Cout + o (Cout % 16 == 0, so a chunk has one phase); output is 2H x 2W
-                    const int phase = v0 / p.cout_real, o0 = v0 - phase * p.cout_real;
-                    oy = 2 * h + (phase >> 1); ox = 2 * w + (phase & 1);
-                    ystride = (size_t)4 * HW;
-                    off = ((size_t)n * p.cout_real + o0) * ystride + (size_t)oy * W2 + ox;
-                }
-                return nvalid;
-            };
-            // the residual of chunk cc + step is fetched while chunk cc is read from TMEM, transformed and stored (one memory round trip hidden)
-            const int step = kConvWarps / 4;
-            float res[16];
-#pragma unroll
-            for (int i = 0; i < 16; i++) res[i] = 0.f;
-            auto fetch_res = [&](int cc, float (&dst)[16]) {
-                if (!p.residual || !ok || cc >= ncol_chunks) return;
-                size_t off, ystride; int oy, ox;
-                const int nvalid = chunk_out(cc, off, ystride, oy, ox);
-#pragma unroll
-                for (int i = 0; i < 16; i++) if (i < nvalid) dst[i] = __ldg(p.residual + off + (size_t)i * ystride);
-            };
-            fetch_res(part, res);
-            for (int cc = part; cc < ncol_chunks; cc += step) {
-                float res_next[16];
-#pragma unroll
-                for (int i = 0; i < 16; i++) res_next[i] = 0.f;
-                fetch_res(cc + step, res_next);
-                uint32_t r[16];
-                tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.BN + cc * 16), r);
-                if (!ok) continue;
-                size_t off, ystride; int oy, ox;
-                const int nvalid = chunk_out(cc, off, ystride, oy, ox);
-                if (nvalid <= 0) continue;
-                float nz = nz0;
-                if (p.up2 && p.noise) nz = __ldg(p.noise + (size_t)n * p.noise_bstride + (size_t)oy * W2 + ox) * p.gain;
-                float v[16];
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const float4 a4 = reinterpret_cast<const float4*>(s_scale + cc * 16)[i];
-                    const float4 b4 = reinterpret_cast<const float4*>(s_shift + cc * 16)[i];
-                    v[4 * i]     = fmaf(__uint_as_float(r[4 * i]),     a4.x, b4.x + nz);
-                    v[4 * i + 1] = fmaf(__uint_as_float(r[4 * i + 1]), a4.y, b4.y + nz);
-                    v[4 * i + 2] = fmaf(__uint_as_float(r[4 * i + 2]), a4.z, b4.z + nz);
-                    v[4 * i + 3] = fmaf(__uint_as_float(r[4 * i + 3]), a4.w, b4.w + nz);
-                }
-                if (do_act) {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i], 0.f) + slope * fminf(v[i], 0.f);
-                }
-                if (do_clamp) {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) v[i] = fminf(fmaxf(v[i], -cl), cl);
-                }
-#pragma unroll
-                for (int i = 0; i < 16; i++) v[i] += res[i];
-                float* yp = p.y + off;
-                if (p.out_half) {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) if (i < nvalid) store_half(p.y, off + (size_t)i * ystride, v[i]);
-                } else if (nvalid == 16) {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) yp[(size_t)i * ystride] = v[i];
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) if (i < nvalid) yp[(size_t)i * ystride] = v[i];
-                }
-#pragma unroll
-                for (int i = 0; i < 16; i++) res[i] = res_next[i];
-            }
-        }
+        epilogue_tile(p, n, jn, m0, HW, tmem_base, s_scale, s_shift, warp & 3, cw >> 2, kConvWarps / 4, lane);   // 2 warps per TMEM lane quarter
     }
     if (threadIdx.x == 64 && p.dbg) {
         PG_TS(5);
@@ -846,6 +877,153 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- persistent kernel
+// One CTA per SM walks a static list of output tiles (tile = blockIdx.x, + gridDim.x, ...).  Roles: warp 0 streams the weights, warp 1 issues the
+// MMAs, 12 converter warps (two groups on alternate chunks) stage the A operand, 4 epilogue warps drain TMEM.  TMEM holds TWO accumulator
+// buffers of NACC x BN <= 256 columns: while the epilogue warps read buffer i & 1 the MMA warp is already filling the other one, and the
+// converters / weight stream never stop at a tile boundary (their stage rings run on), so the prologue, pipeline fill and epilogue that cost a
+// quarter of a one-tile CTA's life are off the critical path.  Covers the aligned pair loader (plain / modulated / split input / residual /
+// fp16 in / fp16 out), 1x1 and 3x3, stride 1; everything else keeps conv_igemm_kernel.
+constexpr int kPConvWarps = 12;
+constexpr int kPEpiWarps  = 4;
+constexpr int kPThreads   = 64 + 32 * (kPConvWarps + kPEpiWarps);
+
+template <bool SCALE>
+__global__ void __launch_bounds__(kPThreads, 1) conv_igemm_persistent_kernel(const __grid_constant__ ConvParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const int BM = 128 * p.NACC;
+    const int HW = p.H * p.W;
+    const int tiles_n = p.N * p.tiles_per_img;               // tiles of one n-tile (jn)
+    const int total = tiles_n * p.ntiles_n;
+    const int cin_pad = p.nchunks * kKC;
+
+    uint8_t* a_base = smem;
+    uint8_t* b_base = a_base + (size_t)p.SA * p.a_stage_bytes;
+    float*   s_style = reinterpret_cast<float*>(b_base + (size_t)p.SB * p.b_slot_bytes);      // [2][cin_pad]
+    float*   s_scale = s_style + 2 * cin_pad;                                                  // [2][BN]
+    float*   s_shift = s_scale + 2 * p.BN;                                                     // [2][BN]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 2 * p.BN);
+    uint64_t* a_full = bars, *a_empty = bars + p.SA, *b_full = bars + 2 * p.SA, *b_empty = bars + 2 * p.SA + p.SB;
+    uint64_t* acc_full = bars + 2 * p.SA + 2 * p.SB, *acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < p.SA; i++) { mbar_init(smem_u32(&a_full[i]), (uint32_t)(kPConvWarps / p.cgroups)); mbar_init(smem_u32(&a_empty[i]), 1); }
+        for (int i = 0; i < p.SB; i++) { mbar_init(smem_u32(&b_full[i]), 1); mbar_init(smem_u32(&b_empty[i]), 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), kPEpiWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    {   // padding slots are re-zeroed per tile by the converters; start from a clean slate anyway
+        uint4* z = reinterpret_cast<uint4*>(a_base);
+        const int nz = (int)((size_t)p.SA * p.a_stage_bytes / 16);
+        for (int i = threadIdx.x; i < nz; i += kPThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== B producer =====================
+        if (lane == 0) {
+            const int nslots = p.nchunks * (p.ntaps / p.tps);
+            int st = 0; uint32_t ph = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                const int jn = t / tiles_n;
+                const uint8_t* src = (const uint8_t*)p.wpack + (size_t)jn * p.nchunks * p.ntaps * p.b_tile_bytes;
+                for (int g = 0; g < nslots; g++) {
+                    mbar_wait(smem_u32(&b_empty[st]), ph ^ 1);
+                    mbar_expect_tx(smem_u32(&b_full[st]), p.b_slot_bytes);
+                    bulk_g2s(smem_u32(b_base + (size_t)st * p.b_slot_bytes), src + (size_t)g * p.b_slot_bytes, p.b_slot_bytes, smem_u32(&b_full[st]));
+                    if (++st == p.SB) { st = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t issue = elect_one();
+        const uint32_t ab = smem_u32(a_base), bb = smem_u32(b_base), af = smem_u32(a_full), ae = smem_u32(a_empty), bf = smem_u32(b_full),
+                       be = smem_u32(b_empty);
+        const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+        MmaRing ring = {0, 0, 0u, 0u};
+        int it = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, it++) {
+            const int buf = it & 1;
+            mbar_wait(smem_u32(&acc_empty[buf]), (((uint32_t)it >> 1) & 1u) ^ 1u);       // the epilogue has drained this buffer (tile it - 2)
+            tc_fence_after();
+            const uint32_t accf = smem_u32(&acc_full[buf]), tacc = tb + (uint32_t)buf * 256u;
+#define PG_ISSUE(KS_, NACC_) mma_issue_loop<KS_, NACC_>(p, ab, bb, af, ae, bf, be, accf, tacc, issue, ring)
+            if (p.ks == 3) { if (p.NACC == 4) PG_ISSUE(3, 4); else if (p.NACC == 3) PG_ISSUE(3, 3); else if (p.NACC == 2) PG_ISSUE(3, 2); else PG_ISSUE(3, 1); }
+            else           { if (p.NACC == 4) PG_ISSUE(1, 4); else if (p.NACC == 3) PG_ISSUE(1, 3); else if (p.NACC == 2) PG_ISSUE(1, 2); else PG_ISSUE(1, 1); }
+#undef PG_ISSUE
+        }
+    } else if (warp < 2 + kPConvWarps) {
+        // ===================== A converters =====================
+        const int cw = warp - 2;
+        const int halo = (p.ks == 3) ? p.PW + 1 : 0;
+        long long wait_e = 0;
+        int it = 0, chunk_base = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, it++, chunk_base += p.nchunks) {
+            const int r = t % tiles_n, n = r / p.tiles_per_img, tile = r - n * p.tiles_per_img;
+            const int m0 = tile * BM, q0 = m0 - halo;
+            float* sty = s_style + (it & 1) * cin_pad;
+            if (SCALE) {
+                // this tile's per-sample input scales; buffer it & 1 was last read for tile it - 2, which every converter warp finished before it
+                // passed the named barrier of tile it - 1
+                stage_styles(p, n, sty, cin_pad, (int)threadIdx.x - 64, 32 * kPConvWarps);
+                asm volatile("bar.sync 1, %0;" ::"r"(32 * kPConvWarps) : "memory");
+            }
+            const float* xn = p.in_half ? reinterpret_cast<const float*>(reinterpret_cast<const __half*>(p.x) + (size_t)n * p.cin1 * HW) : p.x + (size_t)n * p.cin1 * HW;
+            const float* xn2 = p.x2 ? p.x2 + (size_t)n * (p.Cin - p.cin1) * HW - (size_t)p.cin1 * HW : xn;
+            const int qa = q0 < 0 ? 0 : q0, qb = (q0 + p.PA < p.Lp ? q0 + p.PA : p.Lp) - 1;
+            const int ha = (int)__umulhi((uint32_t)qa, p.pw_magic), wa = qa - ha * p.PW;
+            const int hb = (int)__umulhi((uint32_t)qb, p.pw_magic), wb = qb - hb * p.PW;
+            const int e_lo = wa >= p.W ? (ha + 1) * p.W : ha * p.W + wa;
+            const int e_hi = wb >= p.W ? (hb + 1) * p.W : hb * p.W + wb + 1;
+            const int g_lo = e_lo >> 1, g_hi = (e_hi + 1) >> 1;
+            const int nseg = g_hi > g_lo ? (g_hi - g_lo + 31) >> 5 : 0;
+            const int ntasks = nseg * 2;
+            const int wpg = kPConvWarps / p.cgroups;
+            const int tpw = ntasks ? (ntasks + wpg - 1) / wpg : 1;
+#define PG_CONVERT(PER_, ROUNDS_) convert_vec2<SCALE, false, PER_, ROUNDS_>(p, xn, xn2, HW, cw, lane, g_lo, g_hi, ntasks, q0, a_base, sty, a_full, a_empty, wait_e, kPConvWarps, chunk_base, true)
+#define PG_CONVERT_H(PER_, ROUNDS_) convert_vec2<false, true, PER_, ROUNDS_>(p, xn, xn2, HW, cw, lane, g_lo, g_hi, ntasks, q0, a_base, sty, a_full, a_empty, wait_e, kPConvWarps, chunk_base, true)
+            if (p.in_half) { if (tpw <= 2) PG_CONVERT_H(2, 1); else if (tpw <= 4) PG_CONVERT_H(2, 2); else PG_CONVERT_H(3, 2); }
+            else if (tpw <= 1) PG_CONVERT(1, 1); else if (tpw == 2) PG_CONVERT(2, 1); else if (tpw == 3) PG_CONVERT(3, 1);
+            else if (tpw == 4) PG_CONVERT(2, 2); else PG_CONVERT(3, 2);                   // host side guarantees tpw <= 6
+#undef PG_CONVERT
+#undef PG_CONVERT_H
+        }
+    } else {
+        // ===================== epilogue warps =====================
+        const int et = (int)threadIdx.x - 32 * (2 + kPConvWarps);     // 0..127
+        int it = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, it++) {
+            const int jn = t / tiles_n, r = t - jn * tiles_n, n = r / p.tiles_per_img, tile = r - n * p.tiles_per_img;
+            const int buf = it & 1;
+            float* sc = s_scale + buf * p.BN; float* sh = s_shift + buf * p.BN;
+            stage_epilogue_constants(p, n, jn, sc, sh, et, 32 * kPEpiWarps);
+            asm volatile("bar.sync 2, %0;" ::"r"(32 * kPEpiWarps) : "memory");
+            mbar_wait(smem_u32(&acc_full[buf]), ((uint32_t)it >> 1) & 1u);
+            tc_fence_after();
+            epilogue_tile(p, n, jn, tile * BM, HW, tmem_base + (uint32_t)buf * 256u, sc, sh, warp & 3, 0, 1, lane);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -1048,6 +1226,32 @@ static int conv_run_impl(const float* x, const void* wpack, const float* styles,
         if (p.vec2 && p.lean && !p.in_half && p.cgroups == 1 && (nt + kConvWarps - 1) / kConvWarps > 6) p.lean = 0;
     }
     PG_REQUIRE(!(p.out_half && residual), "conv2d_igemm: the residual add is not available with a float16 output");
+    p.ntiles_n = pl.ntiles_n;
+    {   // persistent variant (one CTA per SM, double-buffered TMEM, dedicated epilogue warps) where it applies and there is more than one wave of tiles
+        const long long total_tiles = (long long)N * pl.tiles_per_img * pl.ntiles_n;
+        const int pairs = (pl.PA + 3) / 2, nt = 2 * ((pairs + 31) / 32), tpw_p = (nt + kPConvWarps / 2 - 1) / (kPConvWarps / 2);
+        const bool ok = env_int("PASTA_B200_CONV_PERSIST", 0) != 0 &&      // opt-in: measured slower than two co-resident one-tile CTAs
+                        p.vec2 && (p.lean || p.in_half) && up == 1 && !down2 && !im2col && !p.spade &&
+                        pl.BN <= 128 && pl.BN * pl.NACC <= 256 && tpw_p <= 6 && total_tiles > 2 * kNumSMs && total_tiles < (1ll << 30);
+        if (ok) {
+            const size_t fixed_p = (size_t)2 * pl.nchunks * kKC * 4 + (size_t)2 * pl.BN * 8 + (size_t)(2 * 4 + 2 * 24 + 4) * 8 + 64;
+            const size_t budget = 200 * 1024;
+            int SA = 4;
+            while (SA > 2 && (size_t)SA * pl.a_stage + 2 * (size_t)pl.b_slot + fixed_p + 128 > budget) SA--;
+            const size_t used = (size_t)SA * pl.a_stage + fixed_p + 128;
+            int SB = used < budget ? (int)((budget - used) / pl.b_slot) : 0;
+            if (SB > 24) SB = 24;
+            if (SB >= 2) {
+                p.SA = SA; p.SB = SB; p.cgroups = 2;
+                const size_t smem_p = (size_t)SA * pl.a_stage + (size_t)SB * pl.b_slot + fixed_p + 128;
+                auto pk = scale ? conv_igemm_persistent_kernel<true> : conv_igemm_persistent_kernel<false>;
+                PG_CUDA(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+                const unsigned gridp = (unsigned)(total_tiles < kNumSMs ? total_tiles : kNumSMs);
+                pk<<<gridp, kPThreads, smem_p, s>>>(p);
+                return launch_status("conv2d_igemm(persistent)", 1);
+            }
+        }
+    }
     auto kern = scale ? conv_igemm_kernel<true> : conv_igemm_kernel<false>;
     PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     dim3 grid((unsigned)(N * pl.tiles_per_img), (unsigned)pl.ntiles_n);

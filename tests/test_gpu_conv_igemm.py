@@ -254,3 +254,22 @@ def test_half_intermediates_are_bit_identical(cv, shape):
         r32 = cv.spade_conv_norm(xs, xh.float(), wg, wb, act='relu', gain=1.1)
         r16 = cv.spade_conv_norm(xs, xh, wg, wb, act='relu', gain=1.1, out_dtype=torch.float16)
         assert torch.equal(r16, r32.half())
+
+
+def test_persistent_variant_matches(cv, monkeypatch):
+    """The opt-in persistent kernel (one CTA per SM, double-buffered TMEM, dedicated epilogue warps; PASTA_B200_CONV_PERSIST=1) computes the same
+    tiles with the same accumulation order as the default one-tile kernel: identical bits."""
+    torch.manual_seed(11)
+    for (n, cin, cout, h, w, k, mod) in [(16, 128, 128, 64, 64, 3, False), (16, 64, 64, 128, 128, 3, True), (16, 96, 64, 64, 96, 1, False)]:
+        x = torch.randn(n, cin, h, w, device=DEV)
+        wt = torch.randn(cout, cin, k, k, device=DEV) / (cin * k * k) ** 0.5
+        b = torch.randn(cout, device=DEV)
+        st = (1 + 0.3 * torch.randn(n, cin, device=DEV)) if mod else None
+        dc = (torch.rand(n, cout, device=DEV) + 0.5) if mod else None
+        res = torch.randn(n, cout, h, w, device=DEV)
+        monkeypatch.setenv('PASTA_B200_CONV_PERSIST', '0')
+        y0 = cv.conv2d_igemm(x, wt, styles=st, dcoefs=dc, bias=b, act='lrelu', gain=1.2, clamp=3.0, residual=res)
+        monkeypatch.setenv('PASTA_B200_CONV_PERSIST', '1')
+        y1 = cv.conv2d_igemm(x, wt, styles=st, dcoefs=dc, bias=b, act='lrelu', gain=1.2, clamp=3.0, residual=res)
+        monkeypatch.setenv('PASTA_B200_CONV_PERSIST', '0')
+        assert torch.equal(y0, y1), (n, cin, cout, h, w, k, mod)
