@@ -45,6 +45,7 @@ struct UpfirdnParams {
     Epilogue epi;
     // band kernel only
     int band_rows, bands_per_plane, tile_rows, pitch, rows_per_group;
+    int flat_stage; uint32_t inw_magic;      // narrow planes: stage the band's (contiguous) input span as one flat stream; ceil(2^32 / inW)
 };
 
 // floor division / modulo for possibly negative numerators
@@ -132,6 +133,31 @@ __global__ void __launch_bounds__(256) upfirdn2d_band_kernel(UpfirdnParams p) {
     // thread (288 columns) before any shared-memory store: with 4 resident CTAs that is ~36 KB of reads in flight per SM.
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int KC = 9;
+    if (p.flat_stage) {
+        // Narrow planes (row shorter than the 288 columns one warp keeps in flight): the band is full width, so the input rows it needs are ONE
+        // contiguous span of the plane.  Zero the tile (padding columns / rows outside the image), then stream the span with every lane busy
+        // and 9 independent loads in flight per thread, scattering element i to tile[row][padx0 + col] with a magic-number division.
+        for (int i = threadIdx.x; i < need * p.pitch; i += 256) tile[i] = 0.f;
+        __syncthreads();
+        const int r_lo = iy0 < 0 ? -iy0 : 0;
+        const int r_hi = min(need, p.inH - iy0);
+        const int total = (r_hi - r_lo) * p.inW;
+        const T* src = xp + (ptrdiff_t)(iy0 + r_lo) * p.inW;
+        for (int base = 0; base < total; base += 256 * KC) {
+            float v[KC];
+#pragma unroll
+            for (int kk = 0; kk < KC; kk++) {
+                const int i = base + (int)threadIdx.x + 256 * kk;
+                v[kk] = i < total ? (float)to_acc<T>(__ldg(src + i)) : 0.f;
+            }
+#pragma unroll
+            for (int kk = 0; kk < KC; kk++) {
+                const int i = base + (int)threadIdx.x + 256 * kk;
+                const int r = (int)__umulhi((uint32_t)i, p.inw_magic), c = i - r * p.inW + p.padx0;
+                if (i < total && c < p.pitch) tile[(r_lo + r) * p.pitch + c] = v[kk];
+            }
+        }
+    } else
     for (int r = warp; r < need; r += 8) {
         const int iy = iy0 + r;
         const bool row_ok = (iy >= 0) && (iy < p.inH);
@@ -280,6 +306,8 @@ static int launch_upfirdn2d(UpfirdnParams p, bool band_ok, cudaStream_t stream) 
         const int quads = (p.outW + 3) / 4;
         int rpg = band_rows * quads / 256;
         p.rows_per_group = rpg < 2 ? 2 : (rpg > 8 ? 8 : rpg);
+        p.flat_stage = p.pitch <= 192 ? 1 : 0;
+        p.inw_magic = (uint32_t)((0x100000000ull + (uint64_t)p.inW - 1) / (uint64_t)p.inW);
         const size_t smem = (size_t)p.tile_rows * p.pitch * sizeof(float);
         const int64_t blocks = (int64_t)p.N * p.C * p.bands_per_plane;
         if (smem <= 96 * 1024 && blocks <= INT32_MAX) {
@@ -332,7 +360,7 @@ static int upfirdn2d_entry(const void* x, const float* f, void* y,
     p.fh = fh; p.fw = fw; p.fsh = fsh; p.fsw = fsw;
     p.upx = upx; p.upy = upy; p.downx = downx; p.downy = downy; p.padx0 = padx0; p.pady0 = pady0; p.flip = flip ? 1 : 0; p.gain = gain;
     p.epi = epi;
-    p.band_rows = p.bands_per_plane = p.tile_rows = p.rows_per_group = 0;
+    p.band_rows = p.bands_per_plane = p.tile_rows = p.rows_per_group = 0; p.flat_stage = 0; p.inw_magic = 0;
     // columns the band tile must hold: taps of the last output column reach (outW-1)*D + 3
     // tile columns: the last quad of outputs starts at 4*(ceil(outW/4)-1)*D and reads 4*NV4 floats; multiple of 4 for aligned float4 reads
     p.pitch = 4 * ((outW + 3) / 4 - 1) * downx + (downx == 1 ? 8 : 12);
