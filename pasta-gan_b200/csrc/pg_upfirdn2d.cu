@@ -53,35 +53,51 @@ __device__ __forceinline__ int floordiv(int a, int b) { int q = a / b; return (a
 __device__ __forceinline__ int posmod(int a, int b)   { int m = a % b; return m < 0 ? m + b : m; }
 
 // ------------------------------------------------------------------------------------ generic
-template <class T, bool EPI>
+// UP1: up == 1 in both directions (every tap lands on a sample: no divisions in the tap loops).  Index arithmetic is 32-bit: the entry point
+// rejects tensors with more than INT32_MAX elements (as the reference does, upfirdn2d.cpp:22-23,36).
+template <class T, bool EPI, bool UP1>
 __global__ void __launch_bounds__(256) upfirdn2d_generic_kernel(UpfirdnParams p) {
     typedef typename Acc<T>::type S;
     const T* __restrict__ x = (const T*)p.x;
     T* __restrict__ y = (T*)p.y;
-    const int64_t total = (int64_t)p.N * p.C * p.outH * p.outW;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int ox = (int)(idx % p.outW);
-        int64_t r = idx / p.outW;
-        const int oy = (int)(r % p.outH); r /= p.outH;
-        const int c = (int)(r % p.C);
-        const int n = (int)(r / p.C);
+    const unsigned total = (unsigned)((int64_t)p.N * p.C * p.outH * p.outW);
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int ox = (int)(idx % (unsigned)p.outW);
+        unsigned r = idx / (unsigned)p.outW;
+        const int oy = (int)(r % (unsigned)p.outH); r /= (unsigned)p.outH;
+        const int c = (int)(r % (unsigned)p.C);
+        const int n = (int)(r / (unsigned)p.C);
         // position of tap (0,0) in the zero-inserted (un-padded) image
         const int ux0 = ox * p.downx - p.padx0;
         const int uy0 = oy * p.downy - p.pady0;
-        // first tap that lands on a real sample: (u0 + j) % up == 0
-        const int j0 = posmod(-ux0, p.upx);
-        const int i0 = posmod(-uy0, p.upy);
         const T* xp = x + n * p.xs[0] + c * p.xs[1];
         S acc = (S)0;
-        for (int i = i0; i < p.fh; i += p.upy) {
-            const int iy = (uy0 + i) / p.upy;            // exact: numerator is a multiple of upy
-            if (iy < 0 || iy >= p.inH) continue;
-            const int fi = p.flip ? i : p.fh - 1 - i;
-            for (int j = j0; j < p.fw; j += p.upx) {
-                const int ix = (ux0 + j) / p.upx;
-                if (ix < 0 || ix >= p.inW) continue;
-                const int fj = p.flip ? j : p.fw - 1 - j;
-                acc += (S)__ldg(p.f + fi * p.fsh + fj * p.fsw) * to_acc<T>(__ldg(xp + iy * p.xs[2] + ix * p.xs[3]));
+        if (UP1) {
+            for (int i = 0; i < p.fh; i++) {
+                const int iy = uy0 + i;
+                if (iy < 0 || iy >= p.inH) continue;
+                const float* frow = p.f + (p.flip ? i : p.fh - 1 - i) * p.fsh;
+                const T* xrow = xp + iy * p.xs[2];
+                for (int j = 0; j < p.fw; j++) {
+                    const int ix = ux0 + j;
+                    if (ix < 0 || ix >= p.inW) continue;
+                    acc += (S)__ldg(frow + (p.flip ? j : p.fw - 1 - j) * p.fsw) * to_acc<T>(__ldg(xrow + ix * p.xs[3]));
+                }
+            }
+        } else {
+            // first tap that lands on a real sample: (u0 + j) % up == 0
+            const int j0 = posmod(-ux0, p.upx);
+            const int i0 = posmod(-uy0, p.upy);
+            for (int i = i0; i < p.fh; i += p.upy) {
+                const int iy = (uy0 + i) / p.upy;            // exact: numerator is a multiple of upy
+                if (iy < 0 || iy >= p.inH) continue;
+                const int fi = p.flip ? i : p.fh - 1 - i;
+                for (int j = j0; j < p.fw; j += p.upx) {
+                    const int ix = (ux0 + j) / p.upx;
+                    if (ix < 0 || ix >= p.inW) continue;
+                    const int fj = p.flip ? j : p.fw - 1 - j;
+                    acc += (S)__ldg(p.f + fi * p.fsh + fj * p.fsw) * to_acc<T>(__ldg(xp + iy * p.xs[2] + ix * p.xs[3]));
+                }
             }
         }
         acc *= (S)p.gain;
@@ -299,8 +315,11 @@ static int launch_upfirdn2d(UpfirdnParams p, bool band_ok, cudaStream_t stream) 
         int band_rows = 32;
         while (band_rows > 8 && (size_t)((band_rows - 1) * D + 4) * p.pitch * sizeof(float) > 40 * 1024) band_rows /= 2;
         if (band_rows > p.outH) band_rows = p.outH;
-        p.band_rows = band_rows;
+        // balanced bands (a 33-row plane is 17 + 16 rows, not 32 + 1); a plane a few rows taller than one band stays one band
+        if (p.outH <= band_rows + 8 && (size_t)((p.outH - 1) * D + 4) * p.pitch * sizeof(float) <= 48 * 1024) band_rows = p.outH;
         p.bands_per_plane = (p.outH + band_rows - 1) / band_rows;
+        band_rows = (p.outH + p.bands_per_plane - 1) / p.bands_per_plane;
+        p.band_rows = band_rows;
         p.tile_rows = (band_rows - 1) * D + 4;
         // rows per work item: aim for >= 256 items per CTA (one per thread) but at least 2 rows to amortise the window priming
         const int quads = (p.outW + 3) / 4;
@@ -321,7 +340,8 @@ static int launch_upfirdn2d(UpfirdnParams p, bool band_ok, cudaStream_t stream) 
     int64_t blocks = (total + 255) / 256;
     const int64_t cap = (int64_t)kNumSMs * 64;
     if (blocks > cap) blocks = cap;
-    upfirdn2d_generic_kernel<T, EPI><<<(unsigned)blocks, 256, 0, stream>>>(p);
+    if (p.upx == 1 && p.upy == 1) upfirdn2d_generic_kernel<T, EPI, true><<<(unsigned)blocks, 256, 0, stream>>>(p);
+    else                          upfirdn2d_generic_kernel<T, EPI, false><<<(unsigned)blocks, 256, 0, stream>>>(p);
     return launch_status("upfirdn2d(generic)");
 }
 
@@ -366,7 +386,8 @@ static int upfirdn2d_entry(const void* x, const float* f, void* y,
     p.pitch = 4 * ((outW + 3) / 4 - 1) * downx + (downx == 1 ? 8 : 12);
 
     const bool band_ok = dtype != PG_F64 && fh == 4 && fw == 4 && upx == 1 && upy == 1 && downx == downy && (downx == 1 || downx == 2) &&
-                         padx0 >= 0 && pady0 >= 0 && outW >= 32 &&
+                         padx0 >= 0 && pady0 >= 0 && outW >= 8 && (int64_t)outH * outW >= 256 &&      // smaller planes: per-CTA setup costs more than the generic kernel
+                        
                          contiguous_nchw(in_size, in_stride) && contiguous_nchw(out_size, out_stride);
     cudaStream_t s = (cudaStream_t)stream;
     const bool e = epi.enabled != 0;
