@@ -53,9 +53,9 @@ __device__ __forceinline__ int floordiv(int a, int b) { int q = a / b; return (a
 __device__ __forceinline__ int posmod(int a, int b)   { int m = a % b; return m < 0 ? m + b : m; }
 
 // ------------------------------------------------------------------------------------ generic
-// UP1: up == 1 in both directions (every tap lands on a sample: no divisions in the tap loops).  Index arithmetic is 32-bit: the entry point
+// UP == 1: every tap lands on a sample (no divisions in the tap loops); UP == 2: divisions become shifts.  Index arithmetic is 32-bit: the entry point
 // rejects tensors with more than INT32_MAX elements (as the reference does, upfirdn2d.cpp:22-23,36).
-template <class T, bool EPI, bool UP1>
+template <class T, bool EPI, int UP>      // UP: 1, 2 = compile-time up factor (both directions), 0 = run-time
 __global__ void __launch_bounds__(256) upfirdn2d_generic_kernel(UpfirdnParams p) {
     typedef typename Acc<T>::type S;
     const T* __restrict__ x = (const T*)p.x;
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) upfirdn2d_generic_kernel(UpfirdnParams p)
         const int uy0 = oy * p.downy - p.pady0;
         const T* xp = x + n * p.xs[0] + c * p.xs[1];
         S acc = (S)0;
-        if (UP1) {
+        if (UP == 1) {
             for (int i = 0; i < p.fh; i++) {
                 const int iy = uy0 + i;
                 if (iy < 0 || iy >= p.inH) continue;
@@ -86,14 +86,15 @@ __global__ void __launch_bounds__(256) upfirdn2d_generic_kernel(UpfirdnParams p)
             }
         } else {
             // first tap that lands on a real sample: (u0 + j) % up == 0
-            const int j0 = posmod(-ux0, p.upx);
-            const int i0 = posmod(-uy0, p.upy);
-            for (int i = i0; i < p.fh; i += p.upy) {
-                const int iy = (uy0 + i) / p.upy;            // exact: numerator is a multiple of upy
+            const int upx = UP ? UP : p.upx, upy = UP ? UP : p.upy;
+            const int j0 = posmod(-ux0, upx);
+            const int i0 = posmod(-uy0, upy);
+            for (int i = i0; i < p.fh; i += upy) {
+                const int iy = (uy0 + i) / upy;              // exact: numerator is a multiple of upy
                 if (iy < 0 || iy >= p.inH) continue;
                 const int fi = p.flip ? i : p.fh - 1 - i;
-                for (int j = j0; j < p.fw; j += p.upx) {
-                    const int ix = (ux0 + j) / p.upx;
+                for (int j = j0; j < p.fw; j += upx) {
+                    const int ix = (ux0 + j) / upx;
                     if (ix < 0 || ix >= p.inW) continue;
                     const int fj = p.flip ? j : p.fw - 1 - j;
                     acc += (S)__ldg(p.f + fi * p.fsh + fj * p.fsw) * to_acc<T>(__ldg(xp + iy * p.xs[2] + ix * p.xs[3]));
@@ -340,8 +341,9 @@ static int launch_upfirdn2d(UpfirdnParams p, bool band_ok, cudaStream_t stream) 
     int64_t blocks = (total + 255) / 256;
     const int64_t cap = (int64_t)kNumSMs * 64;
     if (blocks > cap) blocks = cap;
-    if (p.upx == 1 && p.upy == 1) upfirdn2d_generic_kernel<T, EPI, true><<<(unsigned)blocks, 256, 0, stream>>>(p);
-    else                          upfirdn2d_generic_kernel<T, EPI, false><<<(unsigned)blocks, 256, 0, stream>>>(p);
+    if (p.upx == 1 && p.upy == 1)      upfirdn2d_generic_kernel<T, EPI, 1><<<(unsigned)blocks, 256, 0, stream>>>(p);
+    else if (p.upx == 2 && p.upy == 2) upfirdn2d_generic_kernel<T, EPI, 2><<<(unsigned)blocks, 256, 0, stream>>>(p);
+    else                               upfirdn2d_generic_kernel<T, EPI, 0><<<(unsigned)blocks, 256, 0, stream>>>(p);
     return launch_status("upfirdn2d(generic)");
 }
 

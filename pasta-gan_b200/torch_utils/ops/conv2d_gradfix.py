@@ -13,6 +13,8 @@ for the shapes they cover.
 """
 import contextlib
 
+import os
+
 import torch
 
 enabled = False                     # the reference's training loop sets this to True (training_loop...py:255)
@@ -57,7 +59,7 @@ def conv_transpose2d(input, weight, bias=None, stride=1, padding=0, output_paddi
 # Opt-in: run the stride-1 'same' 1x1 / 3x3 convolutions of the custom op (forward AND the input-gradient conv) on the tcgen05 kernel.
 # Off by default: at the training batch (4 per GPU) it measured 2x slower than cuDNN (weights are re-packed every step, tiles under-fill the
 # GPU) and fp16 operands cost ~1.5e-4 on D's logits; the training path keeps fp32 library convolutions until dgrad/wgrad kernels exist.
-tensor_core_forward = False
+tensor_core_forward = os.environ.get('PASTA_B200_TC_TRAIN', '0') == '1'
 
 
 def _forward(input, weight, bias, transpose, stride, padding, output_padding, dilation, groups):

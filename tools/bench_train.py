@@ -13,7 +13,7 @@ from pasta_gan_b200 import networks as N, data_parallel as dp
 from pasta_gan_b200.training import TryOnTrainer, synth_training_batch
 
 ap = argparse.ArgumentParser()
-ap.add_argument('--steps', type=int, default=16); ap.add_argument('--warmup', type=int, default=2); ap.add_argument('--batch-gpu', type=int, default=4)
+ap.add_argument('--steps', type=int, default=16); ap.add_argument('--warmup', type=int, default=17); ap.add_argument('--batch-gpu', type=int, default=4)
 a = ap.parse_args()
 world, rank, local = int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('RANK', 0)), int(os.environ.get('LOCAL_RANK', 0))
 dev = torch.device('cuda', local); torch.cuda.set_device(dev)
