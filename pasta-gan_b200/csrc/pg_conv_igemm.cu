@@ -438,7 +438,7 @@ __device__ __forceinline__ void convert_vec2(const ConvParams& p, const float* x
                 if (a2 != 0xffffffffu) *reinterpret_cast<uint4*>(stage + a2) = d2;
             }
         }
-        fence_proxy_async();                               // generic-proxy stores -> visible to the tensor core (async proxy)
+        if (!(p.dbgmode & 16)) fence_proxy_async();        // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&a_full[st]));
     }
