@@ -822,7 +822,9 @@ class SynthesisNetworkFull(OpsModule):
         for res, cur in zip(self.block_resolutions, block_ws):
             x, img, parsing = getattr(self, f'b{res}')(x, img, cur, pose_feat, cat_feat, force_fp32=True, **block_kwargs)
             if res == 128:
-                x_128, img_128 = x.clone(), img.clone()
+                # reference :5820 clones both; none of the layers of this mirror writes into its input (every conv / ToRGB result is a fresh tensor),
+                # so inference keeps the aliases and saves a 134 MB copy
+                x_128, img_128 = (x, img) if not torch.is_grad_enabled() else (x.clone(), img.clone())
         label = torch.argmax(torch.softmax(parsing.detach(), dim=1), dim=1)[:, None].float()
         cf = self.spade_encoder[-1].conv1.weight.shape[0]                 # channels of one garment's feature map (128)
         half = getattr(self.ops, 'half_intermediates', None)
