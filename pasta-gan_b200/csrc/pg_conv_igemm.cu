@@ -558,8 +558,13 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const int n, 
 #pragma unroll
                 for (int i = 0; i < 16; i++) if (i < nvalid) store_half(p.y, off + (size_t)i * ystride, v[i]);
             } else if (nvalid == 16) {
+                if (p.ldmode == 3) {                              // tuning: streaming (evict-first) stores
 #pragma unroll
-                for (int i = 0; i < 16; i++) yp[(size_t)i * ystride] = v[i];
+                    for (int i = 0; i < 16; i++) __stcs(yp + (size_t)i * ystride, v[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) yp[(size_t)i * ystride] = v[i];
+                }
             } else {
 #pragma unroll
                 for (int i = 0; i < 16; i++) if (i < nvalid) yp[(size_t)i * ystride] = v[i];
