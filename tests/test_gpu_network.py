@@ -113,6 +113,29 @@ def test_fused_inference_paths_are_equivalent(cuda_generator, monkeypatch):
     no_half = run(PASTA_B200_HALF_INTERMEDIATES='0')
     for a, b in zip(base, no_half):
         assert torch.equal(a, b)
+    # StyleBank: the batched styles / demodulation coefficients themselves agree with the per-layer path to fp32 GEMM rounding ...
+    syn = G.synthesis
+    ws = torch.randn(2, syn.num_ws, syn.w_dim, device=DEV)
+    entries = []
+    idx = 0
+    for res in syn.block_resolutions:
+        blk = getattr(syn, f'b{res}')
+        entries += N._block_style_entries(blk, ws.narrow(1, idx, blk.num_conv + blk.num_torgb))
+        idx += blk.num_conv
+    bank = N.StyleBank()
+    with torch.no_grad():
+        bank.fill(entries)
+        for layer, w in entries:
+            styles, dcoefs = layer._pre
+            ref_s = layer.affine(w) * (1.0 if isinstance(layer, N.SynthesisLayer) else layer.weight_gain)
+            assert rel_err(styles, ref_s) < 1e-5
+            if isinstance(layer, N.SynthesisLayer):
+                ref_d = (ref_s.square() @ layer.weight.square().sum(dim=[2, 3]).t() + 1e-8).rsqrt()
+                assert rel_err(dcoefs, ref_d) < 1e-5
+            else:
+                assert dcoefs is None
+    N.StyleBank.clear(entries)
+    # ... and the network outputs to the noise of re-rounding fp16 operands (a 1e-7 change of a style can move an operand by one fp16 ulp)
     no_bank = run(PASTA_B200_STYLE_BANK='0')
-    assert rel_err(base[0], no_bank[0]) < 1e-4 and rel_err(base[2], no_bank[2]) < 1e-4          # coarse image, parsing logits
-    assert float((base[1] - no_bank[1]).norm() / no_bank[1].norm()) < 1e-3                      # fine image (argmax-dependent)
+    assert rel_err(base[0], no_bank[0]) < 2e-3 and rel_err(base[2], no_bank[2]) < 2e-3          # coarse image, parsing logits
+    assert float((base[1] - no_bank[1]).norm() / no_bank[1].norm()) < 1e-2                      # fine image: argmax(parsing) flips at near-ties, as in test_generator_cuda_vs_reference
