@@ -42,6 +42,8 @@ struct ConvParams {
     long long noise_bstride;
     int N, Cin, Cout, H, W, ks;
     int ntiles_n;              // N tiles (persistent kernel: tile list = n-tile major)
+    int band_tw, nbands, Wimg; // column bands (wide images): band_tw output columns per band (0 = off), bands per image, real image width.
+                               // In band mode W = band_tw + 4 (two halo columns each side, real data) and PW = W: a tile then covers several rows
     int PW, Lp, tiles_per_img, NACC, BN, nchunks, ntaps, PA;      // PA: staged strip positions (multiple of 32)
     int SA, SB, tps; uint32_t a_stage_bytes, b_slot_bytes, b_tile_bytes;   // B ring: SB slots of `tps` taps each
     int in_act; float in_alpha, in_gain; int act; float alpha, gain, clamp; int fmt;
@@ -323,7 +325,7 @@ template <bool SCALE, bool IN_HALF, int PER, int ROUNDS>
 __device__ __forceinline__ void convert_vec2(const ConvParams& p, const float* xn, const float* xn2, const int HW, const int cw, const int lane,
                                              const int g_lo, const int g_hi, const int ntasks, const int q0, uint8_t* a_base, const float* s_style,
                                              uint64_t* a_full, uint64_t* a_empty, long long& wait_e,
-                                             const int nwarps = kConvWarps, const int chunk_base = 0, const bool zero_pads = false) {
+                                             const int nwarps = kConvWarps, const int chunk_base = 0, const bool zero_pads = false, const int band = 0) {
     // nwarps: converter warps of the CTA; chunk_base: chunks converted by this CTA before this tile (persistent CTAs: the stage ring continues);
     // zero_pads: the padding slots of the strip move from tile to tile, so the first use of every stage in a tile re-zeroes them
     constexpr int NS = PER * ROUNDS;
@@ -337,12 +339,20 @@ __device__ __forceinline__ void convert_vec2(const ConvParams& p, const float* x
     for (int idx = 0; idx < NS; idx++) {
         const int tt = gw + idx * wpg;                               // wpg is even: every task of a warp has the plane cw & 1
         const int g = g_lo + (tt >> 1) * 32 + lane;
-        const bool ok = tt < ntasks && g < g_hi;
+        bool ok = tt < ntasks && g < g_hi;
         const int e = 2 * g;
         const int h = (int)__umulhi((uint32_t)e, p.w_magic);
         const int s0 = e + h * dpitch - q0;                          // staged slot of the first element; the second is s0 + 1 (same row)
         const int s1st = swap ? s0 + 1 : s0, s2nd = swap ? s0 : s0 + 1;
-        goff[idx] = (ok && !(p.dbgmode & 1)) ? e : -1;
+        int eoff = e;                                                // element offset inside the channel plane
+        if (p.band_tw) {
+            // band mode: e indexes the band's own strip (rows of W = band_tw + 4 columns); column 0 of the band is image column band * band_tw - 2
+            // (even, so pairs are whole); pairs outside the image stay zero
+            const int wimg = band * p.band_tw - 2 + (e - h * p.W);
+            ok = ok && wimg >= 0 && wimg < p.Wimg;
+            eoff = h * p.Wimg + wimg;
+        }
+        goff[idx] = (ok && !(p.dbgmode & 1)) ? eoff : -1;
         const bool st_ok = ok && !(p.dbgmode & 2);
         sA[idx] = (st_ok && s1st >= 0 && s1st < p.PA) ? (uint32_t)((plane * p.PA + s1st) * 16) : 0xffffffffu;
         sB[idx] = (st_ok && s2nd >= 0 && s2nd < p.PA) ? (uint32_t)((plane * p.PA + s2nd) * 16) : 0xffffffffu;
@@ -446,21 +456,23 @@ __device__ __forceinline__ void convert_vec2(const ConvParams& p, const float* x
 
 // Epilogue of one output tile for one warp: TMEM lane quarter `quarter`, 16-column chunks part, part + step, ... of every accumulator.
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const int n, const int jn, const int m0, const int HW, const uint32_t tmem_base,
-                                              const float* s_scale, const float* s_shift, const int quarter, const int part, const int step, const int lane) {
+                                              const float* s_scale, const float* s_shift, const int quarter, const int part, const int step, const int lane,
+                                              const int band = 0) {
     const int ncol_chunks = p.BN / 16;
     const float slope = (p.act == PG_ACT_LINEAR) ? 1.f : (p.act == PG_ACT_RELU ? 0.f : p.alpha);   // act(v) = max(v,0) + slope*min(v,0)
     const float cl = p.clamp >= 0.f ? p.clamp : __int_as_float(0x7f800000);
     const bool do_act = p.act != PG_ACT_LINEAR, do_clamp = p.clamp >= 0.f;
-    const int W2 = 2 * p.W;
+    const int W2 = 2 * p.Wimg;
     for (int a = 0; a < p.NACC; a++) {
         const int q = m0 + a * 128 + quarter * 32 + lane;
-        const int h = (int)__umulhi((uint32_t)q, p.pw_magic), w = q - h * p.PW;
-        const bool ok = q < p.Lp && w < p.W;
+        const int h = (int)__umulhi((uint32_t)q, p.pw_magic), ws = q - h * p.PW;      // row, column inside the strip
+        const int w = p.band_tw ? band * p.band_tw + ws - 2 : ws;                      // image column
+        const bool ok = q < p.Lp && (p.band_tw ? (ws >= 2 && ws < p.band_tw + 2 && w < p.Wimg) : ws < p.W);
         if (p.spade) {
             // gamma = columns [0, C), beta = columns [C, 2C) of the same accumulator row; normalise x with the staged statistics
             const int C = p.cout_real >> 1;
-            const float* xp = p.sp_x + (size_t)n * C * HW + (size_t)h * p.W + w;
-            const size_t yoff = (size_t)n * C * HW + (size_t)h * p.W + w;
+            const float* xp = p.sp_x + (size_t)n * C * HW + (size_t)h * p.Wimg + w;
+            const size_t yoff = (size_t)n * C * HW + (size_t)h * p.Wimg + w;
             for (int cc = part; cc < C / 16; cc += step) {
                 uint32_t rg[16], rb[16];
                 tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.BN + cc * 16), rg);
@@ -491,13 +503,13 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const int n, 
             continue;
         }
         float nz0 = 0.f;
-        if (ok && p.noise && !p.up2) nz0 = __ldg(p.noise + (size_t)n * p.noise_bstride + (size_t)h * p.W + w) * p.gain;
+        if (ok && p.noise && !p.up2) nz0 = __ldg(p.noise + (size_t)n * p.noise_bstride + (size_t)h * p.Wimg + w) * p.gain;
         // output element offset / channel stride / valid channels of column chunk cc for this thread's position
         auto chunk_out = [&](int cc, size_t& off, size_t& ystride, int& oy, int& ox) {
             const int v0 = jn * p.BN + cc * 16;                  // first (virtual) output channel of this chunk
             int nvalid = p.Cout - v0; nvalid = nvalid > 16 ? 16 : nvalid;
             if (!p.up2) {
-                off = ((size_t)n * p.Cout + v0) * HW + (size_t)h * p.W + w;
+                off = ((size_t)n * p.Cout + v0) * HW + (size_t)h * p.Wimg + w;
                 ystride = (size_t)HW; oy = h; ox = w;
             } else {
                 // polyphase up-2: virtual channel = phase * Cout + o (Cout % 16 == 0, so a chunk has one phase); output is 2H x 2W
@@ -606,11 +618,13 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const int tile = blockIdx.x % p.tiles_per_img;
-    const int n    = blockIdx.x / p.tiles_per_img;
+    const int nb_  = blockIdx.x / p.tiles_per_img;
+    const int band = p.band_tw ? nb_ % p.nbands : 0;
+    const int n    = p.band_tw ? nb_ / p.nbands : nb_;
     const int jn   = blockIdx.y;
     const int BM   = 128 * p.NACC;
     const int m0   = tile * BM;
-    const int HW   = p.H * p.W;
+    const int HW   = p.H * p.Wimg;
     if (threadIdx.x == 0 && p.dbg) {
         PG_TS(0);
         uint32_t smid; unsigned long long gt;
@@ -796,8 +810,8 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
                 }
                 if (idx == tpw - 1) stage_end();
             };
-#define PG_CONVERT(PER_, ROUNDS_) convert_vec2<SCALE, false, PER_, ROUNDS_>(p, xn, xn2, HW, cw, lane, g_lo, g_hi, ntasks, q0, a_base, s_style, a_full, a_empty, wait_e)
-#define PG_CONVERT_H(PER_, ROUNDS_) convert_vec2<false, true, PER_, ROUNDS_>(p, xn, xn2, HW, cw, lane, g_lo, g_hi, ntasks, q0, a_base, s_style, a_full, a_empty, wait_e)
+#define PG_CONVERT(PER_, ROUNDS_) convert_vec2<SCALE, false, PER_, ROUNDS_>(p, xn, xn2, HW, cw, lane, g_lo, g_hi, ntasks, q0, a_base, s_style, a_full, a_empty, wait_e, kConvWarps, 0, false, band)
+#define PG_CONVERT_H(PER_, ROUNDS_) convert_vec2<false, true, PER_, ROUNDS_>(p, xn, xn2, HW, cw, lane, g_lo, g_hi, ntasks, q0, a_base, s_style, a_full, a_empty, wait_e, kConvWarps, 0, false, band)
             if (p.in_half) {                              // fp16 input (host side guarantees tpw <= 6, no input scale / activation)
                 if (tpw <= 2) PG_CONVERT_H(2, 1); else if (tpw <= 4) PG_CONVERT_H(2, 2); else PG_CONVERT_H(3, 2);
             } else if (p.lean && tpw <= 6) {
@@ -870,7 +884,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
         mbar_wait(smem_u32(acc_full), 0);
         tc_fence_after();
         if (cw == 0 && lane == 0) PG_TS(4);
-        epilogue_tile(p, n, jn, m0, HW, tmem_base, s_scale, s_shift, warp & 3, cw >> 2, kConvWarps / 4, lane);   // 2 warps per TMEM lane quarter
+        epilogue_tile(p, n, jn, m0, HW, tmem_base, s_scale, s_shift, warp & 3, cw >> 2, kConvWarps / 4, lane, band);   // 2 warps per TMEM lane quarter
     }
     if (threadIdx.x == 64 && p.dbg) {
         PG_TS(5);
@@ -901,7 +915,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_igemm_persistent_kernel(con
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int BM = 128 * p.NACC;
-    const int HW = p.H * p.W;
+    const int HW = p.H * p.Wimg;
     const int tiles_n = p.N * p.tiles_per_img;               // tiles of one n-tile (jn)
     const int total = tiles_n * p.ntiles_n;
     const int cin_pad = p.nchunks * kKC;
@@ -1042,7 +1056,7 @@ static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
 
-static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int ks, int up2) {
+static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int ks, int up2, bool band = false) {
     pl.nvirt = up2 ? 4 * Cout : Cout;
     pl.ntaps = ks * ks;
     pl.nchunks = (Cin + kKC - 1) / kKC;
@@ -1051,7 +1065,7 @@ static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int k
     if (up2 && pl.nvirt > 256) bn = (2 * Cout <= 256 && (2 * Cout) % 16 == 0) ? 2 * Cout : 256;   // keep both x-phases of a row parity together
     pl.BN = bn;
     pl.ntiles_n = (pl.nvirt + bn - 1) / bn;
-    pl.PW = (ks == 3) ? W + 1 : W;
+    pl.PW = (ks == 3 && !band) ? W + 1 : W;          // band mode: the halo columns of the band are its own padding
     pl.Lp = H * pl.PW;
     // Two co-resident CTAs per SM when the N tile is narrow (BN <= 128): each gets half of TMEM (256 columns) and ~100 KB of shared
     // memory, so one CTA's prologue / pipeline fill / epilogue overlaps the other's main loop.  Wide tiles (BN = 256) keep the SM alone.
@@ -1185,10 +1199,27 @@ static int conv_run_impl(const float* x, const void* wpack, const float* styles,
     const int ks_real = ksize;
     if (im2col) { Cin *= ksize * ksize; ksize = 1; }              // taps folded into K: a 1x1 convolution over Cin * k * k virtual channels
     ConvPlan pl;
-    rc = make_plan(pl, N, Cin, Cout, H, W, ksize, up == 2);
-    if (rc != PG_OK) return rc;
+    // Column bands for wide images (W >= 256): with the full-width strip a 256..512-position tile is 1..2 rows and stages 2..3x what it outputs
+    // (one halo row above and below); bands of 64 columns (+ 2 halo columns each side, real data) make the same tile 4..8 rows tall: 1.3x.
+    const int kBandTW = 64;
+    int band_tw = 0, nbands = 1;
+    const int Wimg = W;
+    if (env_int("PASTA_B200_CONV_BANDS", 1) && ksize == 3 && up == 1 && !im2col && !sp_x && W >= 256 && W % 2 == 0 &&
+        ((uintptr_t)x & 7) == 0 && ((uintptr_t)x2 & 7) == 0 && env_int("PASTA_B200_CONV_VEC2", 1) && env_int("PASTA_B200_CONV_LEAN", 1)) {
+        ConvPlan pb;
+        const int nb = (W + kBandTW - 1) / kBandTW;
+        if (make_plan(pb, N * nb, Cin, Cout, H, kBandTW + 4, ksize, false, true) == PG_OK) {
+            const int pairs = (pb.PA + 3) / 2, nt = 2 * ((pairs + 31) / 32);
+            if ((nt + kConvWarps - 1) / kConvWarps <= 6) { pl = pb; band_tw = kBandTW; nbands = nb; W = kBandTW + 4; }
+        }
+    }
+    if (!band_tw) {
+        rc = make_plan(pl, N, Cin, Cout, H, W, ksize, up == 2);
+        if (rc != PG_OK) return rc;
+    }
     cudaStream_t s = (cudaStream_t)stream;
     ConvParams p;
+    p.band_tw = band_tw; p.nbands = nbands; p.Wimg = Wimg;
     p.down2 = down2; p.cin_real = cin_real; p.hin = hin; p.win = win;
     PG_REQUIRE(!x2 || (!down2 && Cin1 > 0 && Cin1 < Cin && Cin1 % 8 == 0), "conv2d_igemm: the split input needs 0 < Cin1 < Cin, Cin1 %% 8 == 0 and no down-sampling");
     PG_REQUIRE(!(im2col && x2), "conv2d_igemm: the split input is not available for folded-tap (small Cin) layers");
@@ -1235,7 +1266,7 @@ static int conv_run_impl(const float* x, const void* wpack, const float* styles,
     {   // persistent variant (one CTA per SM, double-buffered TMEM, dedicated epilogue warps) where it applies and there is more than one wave of tiles
         const long long total_tiles = (long long)N * pl.tiles_per_img * pl.ntiles_n;
         const int pairs = (pl.PA + 3) / 2, nt = 2 * ((pairs + 31) / 32), tpw_p = (nt + kPConvWarps / 2 - 1) / (kPConvWarps / 2);
-        const bool ok = env_int("PASTA_B200_CONV_PERSIST", 0) != 0 &&      // opt-in: measured slower than two co-resident one-tile CTAs
+        const bool ok = env_int("PASTA_B200_CONV_PERSIST", 0) != 0 && !band_tw &&      // opt-in: measured slower than two co-resident one-tile CTAs
                         p.vec2 && (p.lean || p.in_half) && up == 1 && !down2 && !im2col && !p.spade &&
                         pl.BN <= 128 && pl.BN * pl.NACC <= 256 && tpw_p <= 6 && total_tiles > 2 * kNumSMs && total_tiles < (1ll << 30);
         if (ok) {
@@ -1259,7 +1290,7 @@ static int conv_run_impl(const float* x, const void* wpack, const float* styles,
     }
     auto kern = scale ? conv_igemm_kernel<true> : conv_igemm_kernel<false>;
     PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    dim3 grid((unsigned)(N * pl.tiles_per_img), (unsigned)pl.ntiles_n);
+    dim3 grid((unsigned)(N * nbands * pl.tiles_per_img), (unsigned)pl.ntiles_n);
     kern<<<grid, kConvThreads, pl.smem, s>>>(p);
     return launch_status("conv2d_igemm", 1);
 }

@@ -273,3 +273,35 @@ def test_persistent_variant_matches(cv, monkeypatch):
         y1 = cv.conv2d_igemm(x, wt, styles=st, dcoefs=dc, bias=b, act='lrelu', gain=1.2, clamp=3.0, residual=res)
         monkeypatch.setenv('PASTA_B200_CONV_PERSIST', '0')
         assert torch.equal(y0, y1), (n, cin, cout, h, w, k, mod)
+
+
+BANDS = [(1, 64, 64, 256, 256), (1, 32, 48, 40, 320), (2, 16, 16, 24, 258), (1, 24, 32, 130, 512), (2, 64, 32, 9, 256)]
+
+
+@pytest.mark.parametrize('shape', BANDS, ids=[str(s) for s in BANDS])
+def test_column_band_mode(cv, shape, monkeypatch):
+    """W >= 256: the image is processed in 64-column bands with real halo columns (strip pitch 68) instead of one full-width strip.  Same GEMM,
+    different tiling: parity against the oracle with styles / demodulation / noise / bias / lrelu / clamp / residual, and bit-equality with
+    the full-width tiling (PASTA_B200_CONV_BANDS=0) -- every output is the same sum of the same fp16 products in the same chunk order."""
+    n, cin, cout, h, w = shape
+    torch.manual_seed(sum(shape))
+    x = torch.randn(n, cin, h, w)
+    wt = torch.randn(cout, cin, 3, 3)
+    s = 1 + 0.5 * torch.randn(n, cin)
+    noise = torch.randn(h, w) * 0.3
+    b = torch.randn(cout) * 0.2
+    res = torch.randn(n, cout, h, w)
+    ref = O.bias_act(O.modulated_conv2d(x.double(), wt.double(), s.double(), noise=noise.double(), padding=1), b.double(), act='lrelu', gain=1.2, clamp=1.5) + res.double()
+    d = (s.square() @ wt.square().sum(dim=[2, 3]).t() + 1e-8).rsqrt()
+    args = dict(styles=s.to(DEV), dcoefs=d.to(DEV), noise=noise.to(DEV), bias=b.to(DEV), act='lrelu', gain=1.2, clamp=1.5, residual=res.to(DEV))
+    y = cv.conv2d_igemm(x.to(DEV), wt.to(DEV), **args)
+    assert rel_err(y, ref) < 3e-3
+    monkeypatch.setenv('PASTA_B200_CONV_BANDS', '0')
+    y0 = cv.conv2d_igemm(x.to(DEV), wt.to(DEV), **args)
+    monkeypatch.delenv('PASTA_B200_CONV_BANDS')
+    assert torch.equal(y, y0)
+    # plain layer, fp16 input and output
+    wp = (wt / (cin * 9) ** 0.5).to(DEV)
+    xh = x.to(DEV).half()
+    if w <= 256 and cin * 9 > 160:
+        assert torch.equal(cv.conv2d_igemm(xh, wp, out_dtype=torch.float16), cv.conv2d_igemm(xh.float(), wp).half())

@@ -24,7 +24,10 @@ def timeit(fn, iters=10):
     return ts[len(ts) // 2] * 1e3
 
 
-shapes = [(256, 128, 128, 3, 1), (128, 128, 128, 3, 1), (128, 256, 128, 3, 1), (64, 64, 256, 3, 1), (128, 64, 256, 3, 1), (256, 256, 64, 3, 1),
+if __name__ != "__main__":
+    shapes = []
+else:
+  shapes = [(256, 128, 128, 3, 1), (128, 128, 128, 3, 1), (128, 256, 128, 3, 1), (64, 64, 256, 3, 1), (128, 64, 256, 3, 1), (256, 256, 64, 3, 1),
           (512, 512, 32, 3, 1), (512, 512, 16, 3, 1), (192, 128, 128, 1, 1), (128, 64, 256, 1, 1), (256, 128, 64, 3, 2), (128, 64, 128, 3, 2), (512, 256, 32, 3, 2)]
 knobs = [dict(PIPE=p, NACC=n, PAIR=pr) for p, n, pr in
          [(0, 0, 1), (1, 0, 1), (0, 1, 1), (0, 2, 1), (0, 4, 1), (0, 1, 0), (0, 2, 0), (0, 4, 0), (1, 4, 0)]]
