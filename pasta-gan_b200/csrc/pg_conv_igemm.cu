@@ -831,6 +831,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
                 int h = 0, w = 0;
                 bool ok = ci < nchunks && tt < ntasks && q >= 0 && q < p.Lp && !(p.dbgmode & 1);
                 if (ok) { h = (int)__umulhi((uint32_t)q, p.pw_magic); w = q - h * p.PW; ok = w < p.W; }
+                if (p.band_tw) { w = band * p.band_tw - 2 + w; ok = ok && w >= 0 && w < p.Wimg; }     // band mode (down-2 layers): image column of this slot
                 const int c0 = ci * kKC + (tt & 1) * 8;
 #pragma unroll
                 for (int i = 0; i < 8; i++) v[i] = 0.f;
@@ -1204,13 +1205,17 @@ static int conv_run_impl(const float* x, const void* wpack, const float* styles,
     const int kBandTW = 64;
     int band_tw = 0, nbands = 1;
     const int Wimg = W;
-    if (env_int("PASTA_B200_CONV_BANDS", 1) && ksize == 3 && up == 1 && !im2col && !sp_x && W >= 256 && W % 2 == 0 &&
+    // (W is the GEMM's width here: the output width for down-2, the input width for up-2.)
+    if (env_int("PASTA_B200_CONV_BANDS", 1) && ksize == 3 && !im2col && !sp_x && W >= 256 && W % 2 == 0 &&
         ((uintptr_t)x & 7) == 0 && ((uintptr_t)x2 & 7) == 0 && env_int("PASTA_B200_CONV_VEC2", 1) && env_int("PASTA_B200_CONV_LEAN", 1)) {
-        ConvPlan pb;
+        ConvPlan pb, pf;
         const int nb = (W + kBandTW - 1) / kBandTW;
-        if (make_plan(pb, N * nb, Cin, Cout, H, kBandTW + 4, ksize, false, true) == PG_OK) {
+        // only where the full-width strip stages >= 2.5x what it outputs (a tile of one row: W >= 512, or W >= 256 with a wide N tile); at 2x the
+        // bands' 6 % of wasted MMA rows and narrower rows cancel the saving (measured: 64->64 @256^2 neutral, 64->64 down-2 @512^2 7 % slower)
+        const bool worth = make_plan(pf, N, Cin, Cout, H, W, ksize, up == 2) == PG_OK && 2 * pf.PA >= 5 * 128 * pf.NACC;
+        if (worth && make_plan(pb, N * nb, Cin, Cout, H, kBandTW + 4, ksize, up == 2, true) == PG_OK) {
             const int pairs = (pb.PA + 3) / 2, nt = 2 * ((pairs + 31) / 32);
-            if ((nt + kConvWarps - 1) / kConvWarps <= 6) { pl = pb; band_tw = kBandTW; nbands = nb; W = kBandTW + 4; }
+            if (down2 || (nt + kConvWarps - 1) / kConvWarps <= 6) { pl = pb; band_tw = kBandTW; nbands = nb; W = kBandTW + 4; }   // down-2: generic task stream, any count
         }
     }
     if (!band_tw) {

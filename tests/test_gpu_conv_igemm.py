@@ -305,3 +305,27 @@ def test_column_band_mode(cv, shape, monkeypatch):
     xh = x.to(DEV).half()
     if w <= 256 and cin * 9 > 160:
         assert torch.equal(cv.conv2d_igemm(xh, wp, out_dtype=torch.float16), cv.conv2d_igemm(xh.float(), wp).half())
+
+
+@pytest.mark.parametrize('shape', [(1, 32, 32, 16, 512, 'down'), (2, 16, 48, 40, 520, 'down'), (1, 32, 16, 24, 256, 'up'), (2, 16, 32, 10, 322, 'up')])
+def test_column_band_mode_resampling(cv, shape, monkeypatch):
+    """Band tiling under the fused resampling forms: down-2 (bands over the OUTPUT columns of the space-to-depth GEMM) and polyphase up-2 (bands over
+    the INPUT columns).  Parity against conv2d_resample's definition and bit-equality with the full-width tiling."""
+    n, cin, cout, h, w, mode = shape
+    torch.manual_seed(sum(shape[:5]))
+    f = O.setup_filter([1, 3, 3, 1])
+    x = torch.randn(n, cin, h, w)
+    wt = torch.randn(cout, cin, 3, 3) / (cin * 9) ** 0.5
+    b = torch.randn(cout) * 0.2
+    if mode == 'down':
+        ref = O.bias_act(O.conv2d_resample(x.double(), wt.double(), f.double(), down=2, padding=1), b.double(), act='lrelu')
+        run = lambda: cv.conv2d_igemm(x.to(DEV), wt.to(DEV), f=f.to(DEV), down=2, bias=b.to(DEV), act='lrelu', gain=2 ** 0.5)
+    else:
+        ref = O.bias_act(O.conv2d_resample(x.double(), wt.double(), f.double(), up=2, padding=1, flip_weight=False), b.double(), act='lrelu')
+        run = lambda: cv.conv2d_igemm(x.to(DEV), wt.to(DEV), f=f.to(DEV), up=2, flip_weight=False, bias=b.to(DEV), act='lrelu', gain=2 ** 0.5)
+    y = run()
+    assert y.shape == ref.shape and rel_err(y, ref) < 3e-3
+    monkeypatch.setenv('PASTA_B200_CONV_BANDS', '0')
+    y0 = run()
+    monkeypatch.delenv('PASTA_B200_CONV_BANDS')
+    assert torch.equal(y, y0)
