@@ -1206,13 +1206,19 @@ static int conv_run_impl(const float* x, const void* wpack, const float* styles,
     int band_tw = 0, nbands = 1;
     const int Wimg = W;
     // (W is the GEMM's width here: the output width for down-2, the input width for up-2.)
-    if (env_int("PASTA_B200_CONV_BANDS", 1) && ksize == 3 && !im2col && !sp_x && W >= 256 && W % 2 == 0 &&
+    if (env_int("PASTA_B200_CONV_BANDS", 1) && ksize == 3 && !im2col && W >= env_int("PASTA_B200_CONV_BAND_MINW", 128) && W % 2 == 0 &&
         ((uintptr_t)x & 7) == 0 && ((uintptr_t)x2 & 7) == 0 && env_int("PASTA_B200_CONV_VEC2", 1) && env_int("PASTA_B200_CONV_LEAN", 1)) {
         ConvPlan pb, pf;
         const int nb = (W + kBandTW - 1) / kBandTW;
-        // only where the full-width strip stages >= 2.5x what it outputs (a tile of one row: W >= 512, or W >= 256 with a wide N tile); at 2x the
-        // bands' 6 % of wasted MMA rows and narrower rows cancel the saving (measured: 64->64 @256^2 neutral, 64->64 down-2 @512^2 7 % slower)
-        const bool worth = make_plan(pf, N, Cin, Cout, H, W, ksize, up == 2) == PG_OK && 2 * pf.PA >= 5 * 128 * pf.NACC;
+        // only where the full-width strip stages >= 2.5x what it outputs (a tile of one row), or >= 2x with an N tile of >= 128 columns (measured:
+        // 256->128 @128^2 -8 %, 128->128 @128^2 -6 %); narrow N tiles at 2x lose more to the bands' 6 % of unused MMA rows than they gain
+        // (64->64 @256^2 +4 %, 64->64 down-2 @512^2 +7 %)
+        const int ratio10 = env_int("PASTA_B200_CONV_BAND_RATIO10", 0);
+        bool worth = make_plan(pf, N, Cin, Cout, H, W, ksize, up == 2) == PG_OK;
+        if (worth) {
+            const int staged10 = 10 * pf.PA / (128 * pf.NACC);
+            worth = ratio10 ? staged10 >= ratio10 : (staged10 >= 25 || (staged10 >= 20 && pf.BN >= 128));
+        }
         if (worth && make_plan(pb, N * nb, Cin, Cout, H, kBandTW + 4, ksize, up == 2, true) == PG_OK) {
             const int pairs = (pb.PA + 3) / 2, nt = 2 * ((pairs + 31) / 32);
             if (down2 || (nt + kConvWarps - 1) / kConvWarps <= 6) { pl = pb; band_tw = kBandTW; nbands = nb; W = kBandTW + 4; }   // down-2: generic task stream, any count
