@@ -1202,7 +1202,7 @@ static int conv_run_impl(const float* x, const void* wpack, const float* styles,
     ConvPlan pl;
     // Column bands for wide images (W >= 256): with the full-width strip a 256..512-position tile is 1..2 rows and stages 2..3x what it outputs
     // (one halo row above and below); bands of 64 columns (+ 2 halo columns each side, real data) make the same tile 4..8 rows tall: 1.3x.
-    const int kBandTW = 64;
+    const int kBandTW = env_int("PASTA_B200_CONV_BAND_TW", 64);     // even
     int band_tw = 0, nbands = 1;
     const int Wimg = W;
     // (W is the GEMM's width here: the output width for down-2, the input width for up-2.)
