@@ -94,15 +94,8 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-// shared-memory matrix descriptor: K-major, SWIZZLE_NONE, rows 16 B apart (SBO = 128 B), K chunks `lbo_bytes` apart
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((128u >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;                          // descriptor version (sm_100)
-    return d;                                        // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
-}
+// Shared-memory matrix descriptors (K-major, SWIZZLE_NONE, rows 16 B apart: SBO = 128 B, K chunks LBO bytes apart, descriptor version 1) are
+// assembled inline in mma_issue_loop: constant high word, low word = (LBO >> 4) << 16 | (start address >> 4).
 
 // The whole MMA warp runs the issue loop in uniform control flow and the tcgen05 instructions sit in `if (elected)` regions, `elected` coming from
 // elect.sync: ptxas then knows a single lane is active and moves descriptors to uniform registers with plain R2URs.  Under `if (lane == 0)` it

@@ -24,25 +24,27 @@ def timeit(fn, iters=10):
     return ts[len(ts) // 2] * 1e3
 
 
-if __name__ != "__main__":
-    shapes = []
-else:
-  shapes = [(256, 128, 128, 3, 1), (128, 128, 128, 3, 1), (128, 256, 128, 3, 1), (64, 64, 256, 3, 1), (128, 64, 256, 3, 1), (256, 256, 64, 3, 1),
-          (512, 512, 32, 3, 1), (512, 512, 16, 3, 1), (192, 128, 128, 1, 1), (128, 64, 256, 1, 1), (256, 128, 64, 3, 2), (128, 64, 128, 3, 2), (512, 256, 32, 3, 2)]
-knobs = [dict(PIPE=p, NACC=n, PAIR=pr) for p, n, pr in
-         [(0, 0, 1), (1, 0, 1), (0, 1, 1), (0, 2, 1), (0, 4, 1), (0, 1, 0), (0, 2, 0), (0, 4, 0), (1, 4, 0)]]
-with torch.no_grad():
-    for cin, cout, res, k, up in shapes:
-        x = torch.randn(16, cin, res, res, device=dev)
-        w = torch.randn(cout, cin, k, k, device=dev) / (cin * k * k) ** 0.5
-        out = []
-        for kn in knobs:
-            for key, v in kn.items():
-                os.environ['PASTA_B200_CONV_' + key] = str(v)
-            conv_igemm._pack_cache.clear() if hasattr(conv_igemm, '_pack_cache') else None
-            try:
-                t = timeit(lambda: conv_igemm.conv2d_igemm(x, w, f=f if up == 2 else None, up=up, flip_weight=(up == 1)))
-            except Exception as e:
-                t = float('nan')
-            out.append(f"p{kn['PIPE']}n{kn['NACC']}c{kn['PAIR']}={t:.0f}")
-        print(f'{cin}->{cout} @{res} k{k} up{up}: ' + '  '.join(out), flush=True)
+def main():
+    shapes = [(256, 128, 128, 3, 1), (128, 128, 128, 3, 1), (128, 256, 128, 3, 1), (64, 64, 256, 3, 1), (128, 64, 256, 3, 1), (256, 256, 64, 3, 1),
+              (512, 512, 32, 3, 1), (512, 512, 16, 3, 1), (192, 128, 128, 1, 1), (128, 64, 256, 1, 1), (256, 128, 64, 3, 2), (128, 64, 128, 3, 2), (512, 256, 32, 3, 2)]
+    knobs = [dict(PIPE=p, NACC=n, PAIR=pr) for p, n, pr in
+             [(0, 0, 1), (1, 0, 1), (0, 1, 1), (0, 2, 1), (0, 4, 1), (0, 1, 0), (0, 2, 0), (0, 4, 0), (1, 4, 0)]]
+    with torch.no_grad():
+        for cin, cout, res, k, up in shapes:
+            x = torch.randn(16, cin, res, res, device=dev)
+            w = torch.randn(cout, cin, k, k, device=dev) / (cin * k * k) ** 0.5
+            out = []
+            for kn in knobs:
+                for key, v in kn.items():
+                    os.environ['PASTA_B200_CONV_' + key] = str(v)
+                conv_igemm._pack_cache.clear() if hasattr(conv_igemm, '_pack_cache') else None
+                try:
+                    t = timeit(lambda: conv_igemm.conv2d_igemm(x, w, f=f if up == 2 else None, up=up, flip_weight=(up == 1)))
+                except Exception as e:
+                    t = float('nan')
+                out.append(f"p{kn['PIPE']}n{kn['NACC']}c{kn['PAIR']}={t:.0f}")
+            print(f'{cin}->{cout} @{res} k{k} up{up}: ' + '  '.join(out), flush=True)
+
+
+if __name__ == '__main__':
+    main()
