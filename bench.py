@@ -11,7 +11,7 @@ batch of 16 synthetic 256x192 (padded to 256x256) person / garment / pose / pars
 Prints ONE JSON line on rank 0:
   value      whole-job img/s, inputs resident in HBM when the timed region starts (CUDA events, max over ranks)
   e2e        same metric through the public API (TryOnSession.step_from_host): pinned-host H2D of the batch and D2H of the images
-             inside the timed region
+             inside the timed region; e2e_u8: the uint8-in / uint8-out form of the same call (device-side normalise and photo conversion)
   roofline   dominant hand-written kernel: algorithmic bytes (or flops) per launch / CUDA-event time per launch vs
              MEASURED_PEAKS.json; measured in one instrumented eager step right after the timed region (per-launch events cannot
              be recorded inside a replayed CUDA graph)
@@ -278,6 +278,14 @@ def run_b200(args, world, rank, local):
     t_dev = timed(sess.step)
     clk = clocks.stop() if rank == 0 else None
     t_e2e = timed(sess.step_from_host)
+    # the same call with the loader's uint8 tensors in and the uint8 BGR photo out (device-side normalise / concat / crop / BGR kernels, test.py:105-135)
+    if args.workload == 'gen512':
+        u8 = procedural.synth_inputs_u8(args.batch, res=512, parts_ch=48, parts_res=128, seed=4321 + 100 * rank, full_body=False)
+        sess.enable_u8_io(u8, crop=(96, 416))
+    else:
+        u8 = procedural.synth_inputs_u8(args.batch, seed=1234 + 100 * rank)
+        sess.enable_u8_io(u8)
+    t_u8 = timed(sess.step_from_host_u8)
 
     # one instrumented eager step (per-launch CUDA events) for the roofline of the dominant hand-written kernel
     with torch.cuda.stream(sess.stream), torch.no_grad():
@@ -318,6 +326,8 @@ def run_b200(args, world, rank, local):
                    'weights': 'procedural (name-keyed, tests/golden/procedural.py)', 'noise_mode': 'const'},
         'e2e': {'value': imgs / t_e2e, 'unit': UNIT, 'ms_per_step': 1e3 * t_e2e / args.steps,
                 'h2d_bytes_per_step': sess.h2d_bytes, 'd2h_bytes_per_step': sess.d2h_bytes},
+        'e2e_u8': {'value': imgs / t_u8, 'unit': UNIT, 'ms_per_step': 1e3 * t_u8 / args.steps, 'h2d_bytes_per_step': sess.h2d_bytes_u8,
+                   'd2h_bytes_per_step': sess.d2h_bytes_u8, 'note': 'uint8 loader tensors in, uint8 BGR photo out (TryOnSession.step_from_host_u8)'},
         'gpu_launches': per_fwd * args.steps,
         'gpu_launches_per_step': per_fwd,
         'clocks': clk,

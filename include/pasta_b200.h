@@ -201,6 +201,15 @@ int pg_masked_plane_sum(const float* feat, const float* mask, float* out, int64_
 int pg_masked_fill(const float* feat, const float* rest, const float* fill, float* out, int64_t N, int64_t C, int64_t hw,
                    int64_t out_batch_stride, int32_t out_dtype, void* stream);   /* out_dtype: PG_F32 or PG_F16 (out cast to float*) */
 
+/* Device-side input / output pipeline around the generator (reference test.py:105-115, :131-135).
+ *   pg_u8_normalize: njobs (<= 8) tensors in one launch; job i converts rows[i] rows of row_len[i] uint8 elements (row r at src[i] + r*src_stride[i])
+ *                    to float32 rows at dst[i] + r*dst_stride[i] (strides in elements): x / 127.5 - 1 when normalize[i] != 0, else x.  A destination
+ *                    stride larger than the row writes a channel slice of a wider tensor (`pose || retain`, test.py:115).  The job arrays are HOST arrays.
+ *   pg_image_to_u8_bgr: img [N,3,H,W] float32 -> out [N,H,x1-x0,3] uint8 = uint8(clip((img[:, ::-1, :, x0:x1] + 1) * 127.5, 0, 255)), channel-last. */
+int pg_u8_normalize(const void* const* src, void* const* dst, const int64_t* rows, const int64_t* row_len, const int64_t* src_stride,
+                    const int64_t* dst_stride, const int32_t* normalize, int32_t njobs, void* stream);
+int pg_image_to_u8_bgr(const float* img, void* out, int32_t N, int32_t H, int32_t W, int32_t x0, int32_t x1, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * torgb_skip — the ToRGB skip path of a synthesis block in one streaming kernel (north_star kernel 3):
  *

@@ -35,6 +35,8 @@ SIGNATURES = {
     'pg_conv2d_igemm_prepack': [c_ptr, c_ptr, c_f32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr, c_i64, c_ptr],
     'pg_conv2d_igemm_run': [c_ptr] * 5 + [c_i64, c_ptr, c_ptr] + [c_i32] * 7 + [c_i32, c_f32, c_f32, c_i32, c_f32, c_f32, c_f32, c_i32, c_ptr],
     'pg_conv2d_igemm_run2': [c_ptr, c_ptr, c_i32] + [c_ptr] * 4 + [c_i64, c_ptr, c_ptr, c_ptr] + [c_i32] * 7 + [c_i32, c_f32, c_f32, c_i32, c_f32, c_f32, c_f32, c_i32, c_i32, c_i32, c_ptr],
+    'pg_u8_normalize': [c_ptr] * 7 + [c_i32, c_ptr],
+    'pg_image_to_u8_bgr': [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr],
     'pg_masked_plane_sum': [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr],
     'pg_masked_fill': [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i32, c_ptr],
     'pg_instance_norm_stats': [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_f32, c_ptr],

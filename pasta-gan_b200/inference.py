@@ -112,6 +112,52 @@ class TryOnSession:
         self.host_out = hosts
         return hosts
 
+    # ---- uint8 in / uint8 out (the loader's tensors in, the images test.py writes out) ---------------------------------------------------
+    def enable_u8_io(self, example_u8, crop=None):
+        """Allocate the uint8 side of the pipeline: pinned host + device buffers shaped like ``example_u8`` (io_pipeline.U8_KEYS), and uint8
+        BGR output buffers for the final image.  After this, ``step_from_host_u8`` is the end-to-end call."""
+        from . import io_pipeline
+        self._io = io_pipeline
+        self.u8_keys = tuple(k for k in io_pipeline.U8_KEYS if k in example_u8)
+        self.u8_host = {k: example_u8[k].clone().contiguous().pin_memory() for k in self.u8_keys}
+        self.u8_dev = [{k: torch.empty_like(example_u8[k], device=self.device) for k in self.u8_keys} for _ in range(self.depth)]
+        self.u8_crop = crop
+        with torch.cuda.stream(self.stream):
+            self.u8_out_dev = [io_pipeline.images_to_u8(out[1] if len(out) > 1 else out[0], crop) for out in self.slots_out]
+        self.stream.synchronize()
+        self.u8_out_host = [torch.empty_like(o, device='cpu').pin_memory() for o in self.u8_out_dev]
+        self.h2d_bytes_u8 = sum(t.numel() for t in self.u8_host.values())
+        self.d2h_bytes_u8 = self.u8_out_host[0].numel()
+
+    def step_from_host_u8(self, host_u8=None):
+        """uint8 loader tensors (pinned host) -> device -> normalise / concatenate (one kernel) -> generator -> uint8 BGR photo (one kernel) -> pinned
+        host.  Same three-stream software pipeline as ``step_from_host``; returns this step's pinned uint8 images [N, H, Wcrop, 3]."""
+        src = self.u8_host if host_u8 is None else host_u8
+        b = self._turn % self.depth
+        self._turn += 1
+        ins, outs = self.slots_in[b], self.slots_out[b]
+        with torch.cuda.stream(self.h2d_stream):
+            self.h2d_stream.wait_event(self.ev_comp[b])
+            for k in self.u8_keys:
+                self.u8_dev[b][k].copy_(src[k], non_blocking=True)
+            self.ev_h2d[b].record(self.h2d_stream)
+        with torch.cuda.stream(self.stream), torch.no_grad():
+            self.stream.wait_event(self.ev_h2d[b])
+            self.stream.wait_event(self.ev_d2h[b])
+            self._io.normalize_u8_batch(self.u8_dev[b], out=ins)
+            if self.graphs[b] is not None:
+                self.graphs[b].replay()
+            else:
+                self.static_in = ins
+                outs = self._forward()
+            self._io.images_to_u8(outs[1] if len(outs) > 1 else outs[0], self.u8_crop, out=self.u8_out_dev[b])
+            self.ev_comp[b].record(self.stream)
+        with torch.cuda.stream(self.d2h_stream):
+            self.d2h_stream.wait_event(self.ev_comp[b])
+            self.u8_out_host[b].copy_(self.u8_out_dev[b], non_blocking=True)
+            self.ev_d2h[b].record(self.d2h_stream)
+        return self.u8_out_host[b]
+
     def join_streams(self):
         """Make the compute stream wait for every outstanding copy, so an event recorded on it afterwards closes the whole pipeline."""
         for b in range(self.depth):

@@ -105,3 +105,15 @@ def synth_inputs_512(batch, seed=4321, device='cpu'):
     """Inputs of the 512 x 512 generator (reference test_512.py:104-118 shapes): 48-channel 128 px garment patches, retain, pose."""
     d = synth_inputs(batch, res=512, parts_ch=48, parts_res=128, seed=seed, content_w=320, device=device)
     return {k: d[k] for k in ('z', 'c', 'retain', 'pose')}
+
+
+def synth_inputs_u8(batch, res=256, parts_ch=42, parts_res=64, seed=1234, full_body=True, device='cpu'):
+    """uint8 loader tensors as test.py:103 receives them (image, pose skeleton, garment patches, de-normalised clothes and masks)."""
+    def u8(idx, ch, r, hi=256):
+        g = torch.Generator(device='cpu')
+        g.manual_seed(seed + idx)
+        return torch.randint(0, hi, (batch, ch, r, r), generator=g, dtype=torch.uint8)
+    d = dict(image=u8(1, 3, res), pose=u8(2, 3, res), norm_img=u8(0, parts_ch, parts_res))
+    if full_body:
+        d.update(denorm_upper_clothes=u8(3, 3, res), denorm_lower_clothes=u8(4, 3, res), denorm_upper_mask=u8(5, 1, res, 2), denorm_lower_mask=u8(6, 1, res, 2))
+    return {k: v.to(device) for k, v in d.items()}

@@ -139,3 +139,40 @@ def test_fused_inference_paths_are_equivalent(cuda_generator, monkeypatch):
     no_bank = run(PASTA_B200_STYLE_BANK='0')
     assert rel_err(base[0], no_bank[0]) < 2e-3 and rel_err(base[2], no_bank[2]) < 2e-3          # coarse image, parsing logits
     assert float((base[1] - no_bank[1]).norm() / no_bank[1].norm()) < 1e-2                      # fine image: argmax(parsing) flips at near-ties, as in test_generator_cuda_vs_reference
+
+
+def test_u8_io_pipeline_bit_exact(cuda_generator):
+    """pg_u8_normalize / pg_image_to_u8_bgr against the reference's expressions (test.py:105-115, :131-135), and the uint8 session call against the
+    float session call on the same data."""
+    import numpy as np
+    from pasta_gan_b200 import io_pipeline
+    from pasta_gan_b200.inference import TryOnSession
+    u8 = procedural.synth_inputs_u8(2, device=DEV)
+    got = io_pipeline.normalize_u8_batch(u8)
+    norm = lambda t: t.to(torch.float32) / 127.5 - 1
+    ref = dict(retain=norm(u8['image']), pose=torch.cat([norm(u8['pose']), norm(u8['image'])], dim=1), c=norm(u8['norm_img']),
+               denorm_upper_input=norm(u8['denorm_upper_clothes']), denorm_lower_input=norm(u8['denorm_lower_clothes']),
+               denorm_upper_mask=u8['denorm_upper_mask'].to(torch.float32), denorm_lower_mask=u8['denorm_lower_mask'].to(torch.float32))
+    for k in ref:
+        assert torch.equal(got[k], ref[k]), k
+    img = torch.randn(2, 3, 256, 256, device=DEV) * 0.8
+    img[0, 0, 0, 40] = float('inf'); img[0, 1, 3, 50] = -7.0
+    out = io_pipeline.images_to_u8(img)
+    g = img.cpu().numpy()
+    exp = np.stack([np.clip(((g[i].transpose(1, 2, 0) + 1.0) * 127.5)[:, 32:224, [2, 1, 0]], 0, 255).astype(np.uint8) for i in range(2)])
+    assert out.shape == (2, 256, 192, 3) and np.array_equal(out.cpu().numpy(), exp)
+    # unaligned / odd sizes take the scalar path
+    odd = torch.randint(0, 256, (3, 5, 7, 9), dtype=torch.uint8, device=DEV)
+    dst = torch.empty(3, 5, 7, 9, device=DEV)
+    io_pipeline.capi.load()
+    tmp = io_pipeline.normalize_u8_batch(dict(image=odd[:, :3].contiguous(), pose=odd[:, :3].contiguous(), norm_img=odd))
+    assert torch.equal(tmp['c'], norm(odd))
+    # session: uint8 in -> uint8 out equals the float session followed by the output conversion
+    sess = TryOnSession(cuda_generator, ref | dict(z=torch.zeros(2, 0, device=DEV)), DEV, use_graph=True, warmup=1)
+    sess.enable_u8_io({k: v.cpu() for k, v in u8.items()})
+    photo = sess.step_from_host_u8()
+    sess.synchronize()
+    sess.load(ref)
+    fimg = sess.step()[1]
+    sess.synchronize()
+    assert torch.equal(photo, io_pipeline.images_to_u8(fimg).cpu())
