@@ -447,6 +447,83 @@ __device__ __forceinline__ void convert_vec2(const ConvParams& p, const float* x
     }
 }
 
+// Lean A converter for the down-2 form (space-to-depth view, virtual channels ordered (row parity a, real channel, column parity b)): a task is
+// 32 strip positions x 8 virtual channels = 4 real channels x both column parities of input row 2h + a, read as four aligned 8-byte loads per lane.
+// As in convert_vec2 the per-(warp, lane, slot) geometry -- input element offset of the lane's output position, its shared-memory slot -- is
+// computed once per CTA; per chunk only the channel / row-parity base moves.  Every staged slot is written (zeros where out of range).
+template <bool SCALE, int PER, int ROUNDS>
+__device__ __forceinline__ void convert_down2(const ConvParams& p, const float* xn, const int cw, const int lane, const int ntasks, const int q0, const int band,
+                                              uint8_t* a_base, const float* s_style, uint64_t* a_full, uint64_t* a_empty, long long& wait_e) {
+    constexpr int NS = PER * ROUNDS;
+    const int plane = cw & 1;                   // kConvWarps is even: every task cw + 8 * idx of a warp has the same plane
+    int soff[NS]; uint32_t slot[NS];
+#pragma unroll
+    for (int idx = 0; idx < NS; idx++) {
+        const int tt = cw + idx * kConvWarps;
+        const int spos = (tt >> 1) * 32 + lane;
+        const int q = q0 + spos;
+        bool ok = tt < ntasks && q >= 0 && q < p.Lp && !(p.dbgmode & 1);
+        int h = 0, w = 0;
+        if (ok) { h = (int)__umulhi((uint32_t)q, p.pw_magic); w = q - h * p.PW; ok = w < p.W; }
+        if (p.band_tw) { w = band * p.band_tw - 2 + w; ok = ok && w >= 0 && w < p.Wimg; }
+        soff[idx] = ok ? 2 * h * p.win + 2 * w : -1;                                  // input element of (row 2h, column 2w); + a * win per chunk
+        slot[idx] = (tt < ntasks && !(p.dbgmode & 2)) ? (uint32_t)((plane * p.PA + spos) * 16) : 0xffffffffu;
+    }
+    const bool has_in_act = p.in_act != PG_ACT_LINEAR;
+    const float in_slope = (p.in_act == PG_ACT_RELU) ? 0.f : p.in_alpha;
+    const size_t cs = (size_t)p.hin * p.win;
+    const int nchunks = p.nchunks;
+    int st = 0; uint32_t ph = 0;
+    for (int ci = 0; ci < nchunks; ci++) {
+        const int c0 = ci * kKC + plane * 8;
+        const int a = c0 / (2 * p.cin_real), cr = (c0 - a * 2 * p.cin_real) >> 1;
+        const float* cb = xn + (size_t)cr * cs + (size_t)a * p.win;
+        uint8_t* stage = a_base + (size_t)st * p.a_stage_bytes;
+#pragma unroll
+        for (int r = 0; r < ROUNDS; r++) {
+            float v[PER][8];
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                const int off = soff[r * PER + u];
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[u][i] = 0.f;
+                if (off >= 0) {
+                    const float* src = cb + off;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { const float2 t = __ldg(reinterpret_cast<const float2*>(src + (size_t)i * cs)); v[u][2 * i] = t.x; v[u][2 * i + 1] = t.y; }
+                }
+            }
+            if (r == 0) {
+                const long long t0 = p.dbg ? clock64() : 0;
+                mbar_wait(smem_u32(&a_empty[st]), ph ^ 1);
+                if (p.dbg) wait_e += clock64() - t0;
+            }
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                const uint32_t sl = slot[r * PER + u];
+                if (sl == 0xffffffffu) continue;
+                if (SCALE) {
+                    const float* sc = s_style + c0;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        float x = v[u][i];
+                        if (has_in_act) x = fmaxf(x, 0.f) + in_slope * fminf(x, 0.f);
+                        v[u][i] = x * sc[i];
+                    }
+                }
+                uint4 pk;
+                pk.x = pack2(v[u][0], v[u][1], p.fmt); pk.y = pack2(v[u][2], v[u][3], p.fmt);
+                pk.z = pack2(v[u][4], v[u][5], p.fmt); pk.w = pack2(v[u][6], v[u][7], p.fmt);
+                *reinterpret_cast<uint4*>(stage + sl) = pk;
+            }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&a_full[st]));
+        if (++st == p.SA) { st = 0; ph ^= 1; }
+    }
+}
+
 // Epilogue of one output tile for one warp: TMEM lane quarter `quarter`, 16-column chunks part, part + step, ... of every accumulator.
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const int n, const int jn, const int m0, const int HW, const uint32_t tmem_base,
                                               const float* s_scale, const float* s_shift, const int quarter, const int part, const int step, const int lane,
@@ -871,7 +948,13 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
                 }
                 if (idx == tpw - 1) stage_end();
             };
-            stream_tasks<8, 4>(load_task, store_task, tpw, nchunks, p.pipe != 0, p.dbg != nullptr, t_issue, t_store);
+#define PG_CONVERT_D(PER_, ROUNDS_) convert_down2<SCALE, PER_, ROUNDS_>(p, xn, cw, lane, ntasks, q0, band, a_base, s_style, a_full, a_empty, wait_e)
+            if (p.down2 && p.lean && tpw <= 6) {
+                if (tpw <= 2) PG_CONVERT_D(2, 1); else if (tpw <= 4) PG_CONVERT_D(4, 1); else PG_CONVERT_D(3, 2);
+            } else {
+                stream_tasks<8, 4>(load_task, store_task, tpw, nchunks, p.pipe != 0, p.dbg != nullptr, t_issue, t_store);
+            }
+#undef PG_CONVERT_D
         }
         if (cw == 0 && lane == 0) { PG_TS(6); PG_PUT(10, wait_e); PG_PUT(14, t_issue); PG_PUT(15, t_store); }
         // ===================== epilogue (same warps) =====================
@@ -1050,7 +1133,7 @@ static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
 
-static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int ks, int up2, bool band = false) {
+static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int ks, int up2, bool band = false, int max_nacc = 4) {
     pl.nvirt = up2 ? 4 * Cout : Cout;
     pl.ntaps = ks * ks;
     pl.nchunks = (Cin + kKC - 1) / kKC;
@@ -1067,7 +1150,7 @@ static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int k
     const int force_nacc = env_int("PASTA_B200_CONV_NACC", 0);
     if (env_int("PASTA_B200_CONV_PAIR", 1) == 0 || force_nacc * bn > 256) pair = false;
     const int tmem_budget = pair ? 256 : 512;
-    const int max_acc = tmem_budget / bn;
+    const int max_acc = tmem_budget / bn < max_nacc ? tmem_budget / bn : max_nacc;
     int nacc = 1;
     for (int cand = (max_acc < 4 ? max_acc : 4); cand >= 1; cand >>= 1) {
         const long long ctas = (long long)N * ((pl.Lp + 128 * cand - 1) / (128 * cand)) * pl.ntiles_n;
@@ -1195,6 +1278,13 @@ static int conv_run_impl(const float* x, const void* wpack, const float* styles,
     ConvPlan pl;
     // Column bands for wide images (W >= 256): with the full-width strip a 256..512-position tile is 1..2 rows and stages 2..3x what it outputs
     // (one halo row above and below); bands of 64 columns (+ 2 halo columns each side, real data) make the same tile 4..8 rows tall: 1.3x.
+    // down-2: the register-batched loader covers at most 6 tasks per warp per chunk; a 4-accumulator strip of a wide image exceeds that and would
+    // fall back to the generic task stream (64->64 down-2 @512^2: 827 us vs 503 us with 2 accumulators + bands)
+    int max_nacc = 4;
+    if (down2) {
+        ConvPlan pt;
+        if (make_plan(pt, N, Cin, Cout, H, W, ksize, false) == PG_OK && (2 * (pt.PA / 32) + kConvWarps - 1) / kConvWarps > 6) max_nacc = 2;
+    }
     const int kBandTW = env_int("PASTA_B200_CONV_BAND_TW", 64);     // even
     int band_tw = 0, nbands = 1;
     const int Wimg = W;
@@ -1207,18 +1297,18 @@ static int conv_run_impl(const float* x, const void* wpack, const float* styles,
         // 256->128 @128^2 -8 %, 128->128 @128^2 -6 %); narrow N tiles at 2x lose more to the bands' 6 % of unused MMA rows than they gain
         // (64->64 @256^2 +4 %, 64->64 down-2 @512^2 +7 %)
         const int ratio10 = env_int("PASTA_B200_CONV_BAND_RATIO10", 0);
-        bool worth = make_plan(pf, N, Cin, Cout, H, W, ksize, up == 2) == PG_OK;
+        bool worth = make_plan(pf, N, Cin, Cout, H, W, ksize, up == 2, false, max_nacc) == PG_OK;
         if (worth) {
             const int staged10 = 10 * pf.PA / (128 * pf.NACC);
             worth = ratio10 ? staged10 >= ratio10 : (staged10 >= 25 || (staged10 >= 20 && pf.BN >= 128));
         }
-        if (worth && make_plan(pb, N * nb, Cin, Cout, H, kBandTW + 4, ksize, up == 2, true) == PG_OK) {
+        if (worth && make_plan(pb, N * nb, Cin, Cout, H, kBandTW + 4, ksize, up == 2, true, max_nacc) == PG_OK) {
             const int pairs = (pb.PA + 3) / 2, nt = 2 * ((pairs + 31) / 32);
             if (down2 || (nt + kConvWarps - 1) / kConvWarps <= 6) { pl = pb; band_tw = kBandTW; nbands = nb; W = kBandTW + 4; }   // down-2: generic task stream, any count
         }
     }
     if (!band_tw) {
-        rc = make_plan(pl, N, Cin, Cout, H, W, ksize, up == 2);
+        rc = make_plan(pl, N, Cin, Cout, H, W, ksize, up == 2, false, max_nacc);
         if (rc != PG_OK) return rc;
     }
     cudaStream_t s = (cudaStream_t)stream;
