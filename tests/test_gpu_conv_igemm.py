@@ -26,6 +26,8 @@ PLAIN = [
     (1, 64, 64, 64, 64, 1), (2, 48, 24, 20, 28, 3), (1, 3, 64, 33, 31, 3), (2, 42, 64, 16, 16, 1),
     (1, 512, 512, 4, 4, 3), (1, 512, 512, 16, 16, 3), (1, 256, 128, 64, 64, 3), (2, 64, 3, 32, 32, 1),
     (1, 192, 128, 40, 40, 1), (1, 64, 64, 128, 128, 3), (3, 20, 300, 12, 12, 3),
+    # W = 128 with N tiles of >= 128 columns: column bands at a staged / useful ratio of 2
+    (1, 128, 128, 24, 128, 3), (1, 64, 256, 16, 128, 3), (2, 32, 144, 130, 128, 3),
     # small Cin: taps folded into the GEMM K dimension (7x7 / 5x5 / 3x3)
     (2, 3, 64, 40, 36, 7), (1, 3, 64, 256, 256, 7), (2, 6, 32, 17, 19, 5), (1, 2, 16, 8, 8, 7), (2, 17, 48, 24, 24, 3),
 ]
@@ -329,3 +331,30 @@ def test_column_band_mode_resampling(cv, shape, monkeypatch):
     y0 = run()
     monkeypatch.delenv('PASTA_B200_CONV_BANDS')
     assert torch.equal(y, y0)
+
+
+def test_band_mode_with_split_input_spade_and_modulated_down2(cv, monkeypatch):
+    """Remaining combinations of the band tiling and the lean down-2 loader: 3x3 over a split input, the SPADE epilogue (bands vs full width,
+    bit-equal), and a style-modulated down-2 layer against the oracle."""
+    torch.manual_seed(3)
+    # split input, 3x3, W = 128, 128 output channels -> banded
+    x, x2 = torch.randn(1, 64, 20, 128), torch.randn(1, 64, 20, 128)
+    wt = torch.randn(128, 128, 3, 3) / (128 * 9) ** 0.5
+    ref = O._conv(torch.cat([x, x2], 1).double(), wt.double(), padding=1)
+    y = cv.conv2d_igemm(x.to(DEV), wt.to(DEV), x2=x2.to(DEV))
+    assert rel_err(y, ref) < 2e-3
+    # SPADE epilogue: bands on / off
+    xs = torch.randn(2, 128, 24, 128, device=DEV); feat = torch.randn(2, 64, 24, 128, device=DEV)
+    wg = torch.randn(128, 64, 3, 3, device=DEV) / 24; wb = torch.randn(128, 64, 3, 3, device=DEV) / 24
+    r1 = cv.spade_conv_norm(xs, feat, wg, wb, act='relu', gain=1.1)
+    monkeypatch.setenv('PASTA_B200_CONV_BANDS', '0')
+    r0 = cv.spade_conv_norm(xs, feat, wg, wb, act='relu', gain=1.1)
+    monkeypatch.delenv('PASTA_B200_CONV_BANDS')
+    assert torch.equal(r0, r1)
+    # modulated down-2 (styles in the lean down-2 loader's prologue)
+    f = O.setup_filter([1, 3, 3, 1])
+    xd = torch.randn(2, 32, 24, 40); wd = torch.randn(48, 32, 3, 3); st = 1 + 0.4 * torch.randn(2, 32)
+    refd = O.modulated_conv2d(xd.double(), wd.double(), st.double(), down=2, padding=1, resample_filter=f.double())
+    dco = (st.square() @ wd.square().sum(dim=[2, 3]).t() + 1e-8).rsqrt()
+    yd = cv.conv2d_igemm(xd.to(DEV), wd.to(DEV), f=f.to(DEV), down=2, styles=st.to(DEV), dcoefs=dco.to(DEV))
+    assert yd.shape == refd.shape and rel_err(yd, refd) < 3e-3
