@@ -52,60 +52,52 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
     assert isinstance(down, int) and down >= 1
     assert isinstance(groups, int) and groups >= 1
     cout, cin_g, kh, kw = _get_weight_shape(w)
-    fw, fh = _get_filter_size(f)
-    px0, px1, py0, py1 = _parse_padding(padding)
+    taps = _get_filter_size(f)                                   # (fw, fh)
+    pad = list(_parse_padding(padding))                          # [x0, x1, y0, y1], relative to the up-sampled image
 
-    # Padding owed to the resampling filters, so that sizes come out as H*up/down.
-    if up > 1:
-        px0 += (fw + up - 1) // 2
-        px1 += (fw - up) // 2
-        py0 += (fh + up - 1) // 2
-        py1 += (fh - up) // 2
-    if down > 1:
-        px0 += (fw - down + 1) // 2
-        px1 += (fw - down) // 2
-        py0 += (fh - down + 1) // 2
-        py1 += (fh - down) // 2
+    # Padding owed to the resampling filters, so that sizes come out as H * up / down (reference :94-104): per axis, an up-sampling FIR of
+    # t taps needs ((t + up - 1) // 2, (t - up) // 2) more, a down-sampling one ((t - down + 1) // 2, (t - down) // 2).
+    for axis, t in enumerate(taps):
+        lo, hi = 2 * axis, 2 * axis + 1
+        if up > 1:
+            pad[lo] += (t + up - 1) // 2
+            pad[hi] += (t - up) // 2
+        if down > 1:
+            pad[lo] += (t - down + 1) // 2
+            pad[hi] += (t - down) // 2
     # tcgen05 implicit-GEMM path (inference, dense fp32 NCHW): plain 'same' 1x1 / 3x3 convolutions, and the up-2 3x3 form
     # evaluated polyphase on the low-resolution input (no (2H+1)^2 intermediate, no separate FIR pass).
     if conv_igemm.supported(x, w, up=up, down=down, groups=groups, f=f, padding=_parse_padding(padding), flip_filter=flip_filter):
         return conv_igemm.conv2d_igemm(x, w, f=f, up=up, down=down, flip_weight=flip_weight)
 
-    pad = [px0, px1, py0, py1]
     pointwise = (kw == 1 and kh == 1)
+    fir = dict(f=f, flip_filter=flip_filter)
+    conv = dict(groups=groups, flip_weight=flip_weight)
 
     if pointwise and down > 1 and up == 1:          # decimate first: 4x fewer pixels through the GEMM
-        x = upfirdn2d.upfirdn2d(x=x, f=f, down=down, padding=pad, flip_filter=flip_filter)
-        return _conv2d_wrapper(x=x, w=w, groups=groups, flip_weight=flip_weight)
+        return _conv2d_wrapper(x=upfirdn2d.upfirdn2d(x=x, down=down, padding=pad, **fir), w=w, **conv)
 
     if pointwise and up > 1 and down == 1:          # conv at low resolution, then upsample
-        x = _conv2d_wrapper(x=x, w=w, groups=groups, flip_weight=flip_weight)
-        return upfirdn2d.upfirdn2d(x=x, f=f, up=up, padding=pad, gain=up ** 2, flip_filter=flip_filter)
+        return upfirdn2d.upfirdn2d(x=_conv2d_wrapper(x=x, w=w, **conv), up=up, padding=pad, gain=up ** 2, **fir)
 
     if down > 1 and up == 1:                        # low-pass at full resolution, strided conv
-        x = upfirdn2d.upfirdn2d(x=x, f=f, padding=pad, flip_filter=flip_filter)
-        return _conv2d_wrapper(x=x, w=w, stride=down, groups=groups, flip_weight=flip_weight)
+        return _conv2d_wrapper(x=upfirdn2d.upfirdn2d(x=x, padding=pad, **fir), w=w, stride=down, **conv)
 
-    if up > 1:                                      # transposed strided conv, then low-pass (gain up^2)
+    if up > 1:                                      # transposed strided conv, then low-pass (gain up^2), then the optional decimation
         if groups == 1:
             wt = w.transpose(0, 1)
-        else:
+        else:                                       # swap (out, in) inside every group
             wt = w.reshape(groups, cout // groups, cin_g, kh, kw).transpose(1, 2).reshape(groups * cin_g, cout // groups, kh, kw)
-        px0 -= kw - 1
-        px1 -= kw - up
-        py0 -= kh - 1
-        py1 -= kh - up
-        pxt = max(min(-px0, -px1), 0)
-        pyt = max(min(-py0, -py1), 0)
-        x = _conv2d_wrapper(x=x, w=wt, stride=up, padding=[pyt, pxt], groups=groups, transpose=True, flip_weight=(not flip_weight))
-        x = upfirdn2d.upfirdn2d(x=x, f=f, padding=[px0 + pxt, px1 + pxt, py0 + pyt, py1 + pyt], gain=up ** 2, flip_filter=flip_filter)
-        if down > 1:
-            x = upfirdn2d.upfirdn2d(x=x, f=f, down=down, flip_filter=flip_filter)
-        return x
+        # the transposed conv grows each axis by k - 1 on the left and k - up on the right; whatever part of that the FIR padding does not
+        # want back is cropped by the transposed conv's own (symmetric) padding, the rest by the FIR stage
+        rest = [pad[0] - (kw - 1), pad[1] - (kw - up), pad[2] - (kh - 1), pad[3] - (kh - up)]
+        crop = [max(min(-rest[0], -rest[1]), 0), max(min(-rest[2], -rest[3]), 0)]          # (x, y)
+        x = _conv2d_wrapper(x=x, w=wt, stride=up, padding=[crop[1], crop[0]], groups=groups, transpose=True, flip_weight=(not flip_weight))
+        x = upfirdn2d.upfirdn2d(x=x, padding=[rest[0] + crop[0], rest[1] + crop[0], rest[2] + crop[1], rest[3] + crop[1]], gain=up ** 2, **fir)
+        return upfirdn2d.upfirdn2d(x=x, down=down, **fir) if down > 1 else x
 
-    if px0 == px1 and py0 == py1 and px0 >= 0 and py0 >= 0:      # plain convolution
-        return _conv2d_wrapper(x=x, w=w, padding=[py0, px0], groups=groups, flip_weight=flip_weight)
+    if pad[0] == pad[1] and pad[2] == pad[3] and pad[0] >= 0 and pad[2] >= 0:               # plain convolution, symmetric padding
+        return _conv2d_wrapper(x=x, w=w, padding=[pad[2], pad[0]], **conv)
 
     # Anything else (asymmetric / negative padding without resampling): explicit pad-or-crop, then conv.
-    x = upfirdn2d.upfirdn2d(x=x, f=None, padding=pad, flip_filter=flip_filter)
-    return _conv2d_wrapper(x=x, w=w, groups=groups, flip_weight=flip_weight)
+    return _conv2d_wrapper(x=upfirdn2d.upfirdn2d(x=x, f=None, padding=pad, flip_filter=flip_filter), w=w, **conv)
