@@ -23,6 +23,10 @@ Reference lines each function follows (paths relative to the reference root):
 * ``conv2d_resample``  torch_utils/ops/conv2d_resample.py:59-154
 * ``fma``              torch_utils/ops/fma.py:15-38
 * ``modulated_conv2d`` training/networks.py:37-94
+* ``instance_norm_stats``  training/networks.py:4363,4377 (nn.InstanceNorm2d(affine=False) inside Spade_Norm_Block)
+* ``spade_norm``       training/networks.py:4371-4379 (Spade_Norm_Block.forward) + the consumer's pre-activation :4345-4349
+* ``masked_mean_fill`` training/networks.py:5791-5800 (tail of SynthesisNetworkFull.get_spade_feat)
+* ``u8_normalize`` / ``image_to_u8_bgr``  test.py:105-115 / :131-135 (device-side input normalisation, CPU-side photo conversion)
 
 The restatements deliberately use a different decomposition from the reference
 (tap-loop FIR instead of a depthwise conv2d; the *definitional* zero-insert →
@@ -414,6 +418,50 @@ def modulated_conv2d_fast(x, weight, styles, noise=None, up=1, down=1, padding=0
 
 # The operator table handed to the host-side network mirror when tests / the CPU
 # baseline want the whole generator evaluated by the oracle.
+# ----------------------------------------------------------------------------- helpers of the SPADE / IO rows
+
+def instance_norm_stats(x, eps=1e-5):
+    """(mean, rstd) per (n, c) plane: biased variance, as nn.InstanceNorm2d(affine=False) (networks.py:4363)."""
+    mean = x.mean(dim=(2, 3))
+    var = (x - mean[:, :, None, None]).square().mean(dim=(2, 3))
+    return mean, (var + eps).rsqrt()
+
+
+def spade_norm(x, gamma, beta, act=None, gain=1.0, eps=1e-5):
+    """normalized * (1 + gamma) + beta (networks.py:4377-4379), optionally followed by the consuming Spade conv's pre-activation
+    (relu / lrelu with gain, :4345-4349)."""
+    mean, rstd = instance_norm_stats(x, eps)
+    y = (x - mean[:, :, None, None]) * rstd[:, :, None, None] * (1 + gamma) + beta
+    return y if act is None else bias_act(y, None, act=act, gain=gain)
+
+
+def masked_mean_fill(feat, valid, rest, min_count=10):
+    """feat * (1 - rest) + mean * rest with mean = sum(feat * valid) / count and count falling back to H * W when at most ``min_count``
+    pixels are valid (networks.py:5791-5800)."""
+    h, w = feat.shape[2:]
+    total = (feat * valid).sum(dim=(2, 3), keepdim=True)
+    count = valid.sum(dim=(2, 3), keepdim=True)
+    enough = (count > min_count).to(feat.dtype)
+    count = count * enough + (h * w) * (1 - enough)
+    return feat * (1 - rest) + (total / count) * rest
+
+
+def u8_normalize(x_u8, normalize=True):
+    """x.to(float32) / 127.5 - 1 (test.py:105-111); masks are plain casts (:109, :112).  float32 arithmetic, true division."""
+    x = x_u8.to(torch.float32)
+    return x / 127.5 - 1 if normalize else x
+
+
+def image_to_u8_bgr(img, crop=None):
+    """uint8(clip((img.transpose(1, 2, 0) + 1) * 127.5, 0, 255)) with the columns cropped to the photo and RGB -> BGR (test.py:131-135);
+    img [N,3,H,W] float32 -> [N,H,x1-x0,3] uint8."""
+    import numpy as np
+    g = img.detach().cpu().numpy().astype(np.float32)
+    x0, x1 = crop if crop is not None else (g.shape[3] // 8, g.shape[3] - g.shape[3] // 8)
+    out = [np.clip(((g[i].transpose(1, 2, 0) + np.float32(1.0)) * np.float32(127.5))[:, x0:x1, [2, 1, 0]], 0, 255).astype(np.uint8) for i in range(g.shape[0])]
+    return torch.from_numpy(np.stack(out))
+
+
 class _Namespace:
     def __init__(self, **kw):
         self.__dict__.update(kw)

@@ -207,8 +207,7 @@ def test_instance_stats(cv, shape):
     for offset in (0.0, 100.0):
         x = (torch.randn(*shape) * 1.7 + offset)
         mean, rstd = cv.instance_stats(x.to(DEV))
-        xd = x.double()
-        m_ref = xd.mean(dim=(2, 3)); r_ref = (xd.var(dim=(2, 3), unbiased=False) + 1e-5).rsqrt()
+        m_ref, r_ref = O.instance_norm_stats(x.double())
         assert float((mean.double().cpu() - m_ref).abs().max()) < 1e-6 * max(1.7, offset)      # mean error relative to the data scale
         assert rel_err(rstd, r_ref) < (1e-5 if offset == 0 else 2e-4)
 
@@ -224,9 +223,7 @@ def test_masked_mean_fill(shape):
     if n > 1:
         m2[0] = 0                                                   # a sample without enough valid pixels: count falls back to H*W
     valid = ((m1 + m2) == 2.0).float(); rest = m1 - valid
-    fs = (feat.double() * valid.double()).sum(dim=(2, 3), keepdim=True)
-    cnt = valid.double().sum(dim=(2, 3), keepdim=True); en = (cnt > 10).double(); cnt = cnt * en + (h * w) * (1 - en)
-    ref = feat.double() * (1 - rest.double()) + (fs / cnt) * rest.double()
+    ref = O.masked_mean_fill(feat.double(), valid.double(), rest.double())
     buf = torch.full([n, 2 * c + 3, h, w], float('nan'), device=DEV)
     out = S.masked_mean_fill(feat.to(DEV), valid.to(DEV), rest.to(DEV), buf[:, 2:2 + c])
     assert out.data_ptr() == buf[:, 2:2 + c].data_ptr()

@@ -155,3 +155,33 @@ def test_fast_port_modulated_conv2d(golden, i):
     y = O.modulated_conv2d_fast(g.t(f'{i}/x'), g.t(f'{i}/w'), g.t(f'{i}/s'), noise=noise, up=m['up'], padding=m['k'] // 2,
                                 resample_filter=g.t('f4'), demodulate=m['demod'], flip_weight=m['flip_weight'])
     assert rel_err(y, g.t(f'{i}/y')) < TOL_CONV
+
+
+def test_oracle_helpers_of_the_spade_and_io_rows():
+    """The oracle's restatements of the SPADE / IO helpers against the library modules and literal expressions the reference uses
+    (nn.InstanceNorm2d: networks.py:4363; get_spade_feat tail :5791-5800; test.py:105-115, :131-135)."""
+    import numpy as np
+    from oracle import ops_oracle as O
+    torch.manual_seed(0)
+    x = torch.randn(2, 6, 9, 11, dtype=torch.float64) * 3 + 2
+    mean, rstd = O.instance_norm_stats(x)
+    ref = torch.nn.InstanceNorm2d(6, affine=False)(x)
+    assert torch.allclose((x - mean[:, :, None, None]) * rstd[:, :, None, None], ref, atol=1e-12)
+    gamma, beta = torch.randn_like(x), torch.randn_like(x)
+    assert torch.allclose(O.spade_norm(x, gamma, beta), ref * (1 + gamma) + beta, atol=1e-12)
+    assert torch.allclose(O.spade_norm(x, gamma, beta, act='relu', gain=2 ** 0.5), torch.relu(ref * (1 + gamma) + beta) * 2 ** 0.5, atol=1e-12)
+    # get_spade_feat tail, including the "not enough valid pixels" fallback
+    feat = torch.randn(3, 4, 8, 8, dtype=torch.float64)
+    m1 = (torch.rand(3, 1, 8, 8) > 0.5).double(); m2 = (torch.rand(3, 1, 8, 8) > 0.3).double(); m2[0] = 0
+    valid = ((m1 + m2) == 2.0).double(); rest = m1 - valid
+    fs = (feat * valid).sum(dim=(2, 3), keepdim=True); cnt = valid.sum(dim=(2, 3), keepdim=True)
+    en = (cnt > 10).double(); cnt = cnt * en + (8 * 8) * (1 - en)
+    assert torch.equal(O.masked_mean_fill(feat, valid, rest), feat * (1 - rest) + (fs / cnt) * rest)
+    # IO expressions
+    u8 = torch.arange(256, dtype=torch.uint8).reshape(1, 1, 16, 16)
+    assert torch.equal(O.u8_normalize(u8), u8.to(torch.float32) / 127.5 - 1) and torch.equal(O.u8_normalize(u8, False), u8.float())
+    img = torch.linspace(-1.3, 1.3, 3 * 8 * 16).reshape(1, 3, 8, 16)
+    out = O.image_to_u8_bgr(img, crop=(2, 14))
+    g = img.numpy()
+    exp = np.clip(((g[0].transpose(1, 2, 0) + 1.0) * 127.5)[:, 2:14, [2, 1, 0]], 0, 255).astype(np.uint8)
+    assert out.shape == (1, 8, 12, 3) and np.array_equal(out[0].numpy(), exp)
