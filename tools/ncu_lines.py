@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Aggregate an ncu report's per-SASS stall samples by CUDA source line (needs -lineinfo and the matching .so).
-usage: tools/ncu_lines.py <report.ncu-rep> <kernel-substring> <source.cu> [top]"""
+usage: tools/ncu_lines.py <report.ncu-rep> <kernel-substring> <source.cu> [top]
+The substring must select ONE kernel of the library (e.g. conv_igemm_kernelILb0 for conv_igemm_kernel<false>, not conv_igemm_kernel, which
+also matches the <true> and persistent variants), and the .so must be the build the report was captured with."""
 import csv, io, os, re, subprocess, sys, tempfile
 
 rep, kname, srcfile = sys.argv[1:4]
