@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define PG_ABI_VERSION 1
+#define PG_ABI_VERSION 2
 
 enum {
     PG_OK = 0,
@@ -142,8 +142,6 @@ int pg_upfirdn2d_bias_act(const void* x, const float* f, const void* b, void* y,
  * 'same' 3x3 convolution over the four space-to-depth planes of x with the 6x6 composite kernel w (*) f — no filtered intermediate. */
 #define PG_CONV_DOWN2 (-2)
 int64_t pg_conv2d_igemm_workspace_bytes(int32_t Cin, int32_t Cout, int32_t ksize, int32_t up);
-/* Profiling aid: when non-NULL, every conv CTA writes 8 int64 clock64() phase stamps to buf[cta*8 ..] (tools/conv_timeline.py). */
-void    pg_debug_set_buffer(void* buf);
 /* The same operation in two steps, so that inference can pack the weights once per parameter version:
  *   prepack: w * w_scale (the layer's weight_gain, training/networks.py:171) -> fp16/bf16 GEMM tiles in `workspace`
  *   run:     the convolution proper on packed weights.  pg_conv2d_igemm_fwd == prepack(w_scale = 1) + run. */
@@ -169,6 +167,49 @@ int pg_conv2d_igemm_run2(const float* x, const float* x2, int32_t Cin1, const vo
                          int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t ksize, int32_t up,
                          int32_t in_act, float in_alpha, float in_gain,
                          int32_t act, float alpha, float gain, float clamp, int32_t operand_format, int32_t x_dtype, int32_t y_dtype, void* stream);
+/* Batched weight packing: `batch` weight sets in one launch, set i written at workspace + i * pg_conv2d_igemm_workspace_bytes(...).
+ *   w_batch_stride > 0: set i is read from w + i * w_batch_stride elements — the per-sample weights [N*O, I, k, k] that the reference's FUSED
+ *                       modulated convolution hands to conv2d_resample with groups = N (training/networks.py:84-94);
+ *   w_batch_stride == 0 with styles [batch, Cin]: set i = w * styles[i, c] — the modulation of networks.py:64-66 applied while packing, for layers
+ *                       whose activations are read by TMA and therefore cannot be scaled on the way in. */
+int pg_conv2d_igemm_prepack_batched(const float* w, int64_t w_batch_stride, const float* styles, int32_t batch, const float* fir, float w_scale,
+                                    int32_t Cin, int32_t Cout, int32_t ksize, int32_t up, int32_t flip_weight, int32_t operand_format,
+                                    void* workspace, int64_t workspace_bytes, void* stream);
+
+/* The general entry point (everything pg_conv2d_igemm_run2 / _spade_run do, plus):
+ *   wpack_sample_stride > 0: sample n multiplies with the packed weight set at wpack + n * wpack_sample_stride bytes.  This is the
+ *               `groups = N` convolution of the reference's fused modulated conv (x [1, N*I, H, W] x w [N*O, I, k, k], conv2d_resample.py:59 with
+ *               groups = N called from networks.py:88-90) with x viewed as [N, I, H, W] and y as [N, O, H', W'], including its up-2 form.
+ *   x_layout / y_layout = PG_LAYOUT_C8: the tensor is float16 in the channel-blocked layout [N][C/8][H][W][8] (C % 16 == 0).  Such an input is
+ *               loaded by the Tensor Memory Accelerator straight into the tensor-core operand layout (a 3-D box of rows x strip positions x 2
+ *               channel blocks per 16-channel chunk; halo and padding are the tensor map's out-of-bounds zero fill) — no conversion pass at all.
+ *               It must be a plain layer (no styles, input activation, x2 or down-2; fold a modulation into the weights with
+ *               pg_conv2d_igemm_prepack_batched).  Such an output is written 16 bytes per (pixel, 8 channels) by the epilogue.
+ *   spade_x != NULL: the SPADE epilogue of pg_conv2d_igemm_spade_run (Cout = 2C, wpack = [gamma ; beta]).
+ * struct_bytes must be sizeof(pg_conv_args) (guards against a binding built for another header). */
+enum { PG_LAYOUT_NCHW = 0, PG_LAYOUT_C8 = 1 };
+typedef struct pg_conv_args {
+    uint32_t struct_bytes;
+    int32_t  N, Cin, Cout, H, W, ksize, up;
+    const void* x;  int32_t x_dtype, x_layout;
+    const void* x2; int32_t cin1, reserved0;
+    const void* wpack; int64_t wpack_sample_stride;
+    const float* styles; const float* dcoefs; const float* noise; int64_t noise_batch_stride; const float* bias; const float* residual;
+    void* y; int32_t y_dtype, y_layout;
+    int32_t in_act; float in_alpha, in_gain;
+    int32_t act; float alpha, gain, clamp;
+    int32_t operand_format, reserved1;
+    const float* spade_x; const float* spade_mean; const float* spade_rstd;
+    void* stream;
+} pg_conv_args;
+int pg_conv2d_igemm_launch(const pg_conv_args* args);
+
+/* Plan / loader choices that were measured against each other (column bands, strip length, loader variants, TMA on / off ...).  Defaults are the
+ * measured best; the PASTA_B200_CONV_* environment variables are read once at first use and this call overrides a value for the rest of the
+ * process.  Keys: conv_bands, conv_band_tw, conv_band_minw, conv_band_ratio10, conv_persist, conv_nacc, conv_pair, conv_vec2, conv_lean,
+ * conv_cgroups, conv_tma.  Every setting computes the same result (bit-identical for a fixed operand format). */
+int pg_set_tuning(const char* key, int32_t value);
+
 int pg_conv2d_igemm_fwd(const float* x, const float* w, const float* fir, const float* styles, const float* dcoefs,
                         const float* noise, int64_t noise_batch_stride, const float* bias, float* y,
                         int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t ksize, int32_t up,
@@ -200,6 +241,16 @@ int pg_instance_norm_stats(const float* x, float* mean, float* rstd, int64_t pla
 int pg_masked_plane_sum(const float* feat, const float* mask, float* out, int64_t N, int64_t C, int64_t hw, void* stream);
 int pg_masked_fill(const float* feat, const float* rest, const float* fill, float* out, int64_t N, int64_t C, int64_t hw,
                    int64_t out_batch_stride, int32_t out_dtype, void* stream);   /* out_dtype: PG_F32 or PG_F16 (out cast to float*) */
+
+/* pg_masked_fill writing channel-blocked fp16 (PG_LAYOUT_C8): channels land in blocks [cb_offset, cb_offset + C/8) of out [N][cb_total][hw][8]
+ * (C % 8 == 0) — the concatenated upper|lower garment feature map in the layout the SPADE convolutions load by TMA. */
+int pg_masked_fill_c8(const float* feat, const float* rest, const float* fill, void* out, int64_t N, int64_t C, int64_t hw,
+                      int64_t cb_total, int64_t cb_offset, void* stream);
+
+/* Boundary of a chain of channel-blocked layers: dense NCHW (float32 or float16) [N, C, hw] <-> float16 C8 [N][ceil(C/8)][hw][8] (channels past C are
+ * zero).  Tensors from other code enter through pg_nchw_to_c8; results leave through pg_c8_to_nchw.  Both HBM-bound, one pass. */
+int pg_nchw_to_c8(const void* x, void* y, int64_t N, int64_t C, int64_t hw, int32_t x_dtype, void* stream);
+int pg_c8_to_nchw(const void* x, void* y, int64_t N, int64_t C, int64_t hw, int32_t y_dtype, void* stream);
 
 /* Device-side input / output pipeline around the generator (reference test.py:105-115, :131-135).
  *   pg_u8_normalize: njobs (<= 8) tensors in one launch; job i converts rows[i] rows of row_len[i] uint8 elements (row r at src[i] + r*src_stride[i])

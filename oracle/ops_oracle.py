@@ -7,7 +7,7 @@ only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
 ``--impl reference`` legs may import it.  The product package
 (``pasta-gan_b200/``) never imports anything from ``oracle/``.
 
-Parity status: PINNED.  ``oracle/gen_golden.py`` imports the unmodified
+Parity status: PINNED.  ``tests/golden/gen_golden.py`` imports the unmodified
 reference from ``/root/reference`` (CPU, ``impl='ref'`` semantics) and writes
 seeded input/output/gradient vectors to ``tests/golden/*.npz``;
 ``tests/test_oracle_golden.py`` checks every function below against them.

@@ -7,7 +7,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, 'lib', 'libpasta_b200.so')
+_LIB_PATH = os.environ.get('PASTA_B200_LIB') or os.path.join(_HERE, 'lib', 'libpasta_b200.so')   # override: the -DPG_DEBUG build of tools/
 
 _lib = None
 _lock = threading.Lock()
@@ -31,7 +31,6 @@ SIGNATURES = {
     'pg_upfirdn2d': [c_ptr, c_ptr, c_ptr, I32x4, I64x4, I32x4, I64x4, c_i32, c_i32, c_i64, c_i64] + [c_i32] * 8 +
                     [c_i32, c_f32, c_i32, c_ptr],
     'pg_conv2d_igemm_workspace_bytes': [c_i32, c_i32, c_i32, c_i32],
-    'pg_debug_set_buffer': [c_ptr],
     'pg_conv2d_igemm_prepack': [c_ptr, c_ptr, c_f32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr, c_i64, c_ptr],
     'pg_conv2d_igemm_run': [c_ptr] * 5 + [c_i64, c_ptr, c_ptr] + [c_i32] * 7 + [c_i32, c_f32, c_f32, c_i32, c_f32, c_f32, c_f32, c_i32, c_ptr],
     'pg_conv2d_igemm_run2': [c_ptr, c_ptr, c_i32] + [c_ptr] * 4 + [c_i64, c_ptr, c_ptr, c_ptr] + [c_i32] * 7 + [c_i32, c_f32, c_f32, c_i32, c_f32, c_f32, c_f32, c_i32, c_i32, c_i32, c_ptr],
@@ -44,9 +43,36 @@ SIGNATURES = {
     'pg_conv2d_igemm_fwd': [c_ptr] * 6 + [c_i64, c_ptr, c_ptr] + [c_i32] * 7 + [c_i32, c_i32, c_f32, c_f32, c_i32, c_f32, c_f32, c_f32, c_i32,
                             c_ptr, c_i64, c_ptr],
     'pg_torgb_skip': [c_ptr] * 7 + [c_i32] * 5 + [c_f32, c_ptr],
+    'pg_conv2d_igemm_prepack_batched': [c_ptr, c_i64, c_ptr, c_i32, c_ptr, c_f32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr, c_i64, c_ptr],
+    'pg_conv2d_igemm_launch': [c_ptr],
+    'pg_set_tuning': [ctypes.c_char_p, c_i32],
+    'pg_masked_fill_c8': [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_ptr],
+    'pg_nchw_to_c8': [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i32, c_ptr],
+    'pg_c8_to_nchw': [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i32, c_ptr],
     'pg_upfirdn2d_bias_act': [c_ptr, c_ptr, c_ptr, c_ptr, I32x4, I64x4, I32x4, I64x4, c_i32, c_i32, c_i64, c_i64] + [c_i32] * 8 +
                              [c_i32, c_f32, c_i32, c_f32, c_f32, c_f32, c_i32, c_ptr],
 }
+
+
+class ConvArgs(ctypes.Structure):
+    """pg_conv_args of include/pasta_b200.h (field order and types must match the header)."""
+    _fields_ = [
+        ('struct_bytes', ctypes.c_uint32),
+        ('N', c_i32), ('Cin', c_i32), ('Cout', c_i32), ('H', c_i32), ('W', c_i32), ('ksize', c_i32), ('up', c_i32),
+        ('x', c_ptr), ('x_dtype', c_i32), ('x_layout', c_i32),
+        ('x2', c_ptr), ('cin1', c_i32), ('reserved0', c_i32),
+        ('wpack', c_ptr), ('wpack_sample_stride', c_i64),
+        ('styles', c_ptr), ('dcoefs', c_ptr), ('noise', c_ptr), ('noise_batch_stride', c_i64), ('bias', c_ptr), ('residual', c_ptr),
+        ('y', c_ptr), ('y_dtype', c_i32), ('y_layout', c_i32),
+        ('in_act', c_i32), ('in_alpha', c_f32), ('in_gain', c_f32),
+        ('act', c_i32), ('alpha', c_f32), ('gain', c_f32), ('clamp', c_f32),
+        ('operand_format', c_i32), ('reserved1', c_i32),
+        ('spade_x', c_ptr), ('spade_mean', c_ptr), ('spade_rstd', c_ptr),
+        ('stream', c_ptr),
+    ]
+
+
+LAYOUT_NCHW, LAYOUT_C8 = 0, 1
 
 
 class PastaB200Error(RuntimeError):
@@ -73,9 +99,11 @@ def load():
         for name, argtypes in SIGNATURES.items():
             fn = getattr(lib, name)                     # AttributeError if the symbol is not exported
             fn.argtypes = argtypes
-            fn.restype = {'pg_debug_set_buffer': None, 'pg_last_error': ctypes.c_char_p, 'pg_launch_count': c_i64, 'pg_conv2d_igemm_workspace_bytes': c_i64}.get(name, c_int)
-        if lib.pg_abi_version() != 1:
-            raise PastaB200Error(f'ABI mismatch: library reports {lib.pg_abi_version()}, binding expects 1')
+            fn.restype = {'pg_last_error': ctypes.c_char_p, 'pg_launch_count': c_i64, 'pg_conv2d_igemm_workspace_bytes': c_i64}.get(name, c_int)
+        if lib.pg_abi_version() != 2:
+            raise PastaB200Error(f'ABI mismatch: library reports {lib.pg_abi_version()}, binding expects 2')
+        if hasattr(lib, 'pg_debug_set_buffer'):                      # -DPG_DEBUG builds only (tools/conv_timeline.py)
+            lib.pg_debug_set_buffer.argtypes, lib.pg_debug_set_buffer.restype = [c_ptr], None
         _lib = lib
     return _lib
 
@@ -84,6 +112,11 @@ def check(rc, what):
     if rc != 0:
         msg = load().pg_last_error()
         raise PastaB200Error(f'{what}: {msg.decode() if msg else "error"} (code {rc})')
+
+
+def set_tuning(key, value):
+    """pg_set_tuning: override one of the conv plan / loader choices for the rest of the process (tests and tools compare variants)."""
+    check(load().pg_set_tuning(key.encode(), int(value)), 'pg_set_tuning')
 
 
 def require_device():

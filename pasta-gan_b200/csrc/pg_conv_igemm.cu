@@ -26,8 +26,10 @@
 //   * Epilogue: tcgen05.ld 32x32b.x16 -> demodulate, add noise and bias, activation, gain, clamp -> coalesced fp32
 //     NCHW stores.  The convolution result never round-trips through HBM before bias_act.
 //   * mbarrier pipelines: A full/empty (converters <-> MMA), B full/empty (bulk copy <-> MMA), accumulator full.
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
+#include <string.h>
 #include "pg_common.cuh"
 
 namespace pg {
@@ -57,12 +59,33 @@ struct ConvParams {
     int cgroups;               // converter warp groups that take alternate chunks (lean loader): several chunks' load round trips in flight
     int pipe, ldmode, dbgmode, lean;          // converter knobs (tuning): register double-buffering on/off, L1::no_allocate loads
     int im2col; uint32_t kk_magic, ks_magic;   // im2col mode: real kernel size (0 = off); ceil(2^32 / k^2), ceil(2^32 / k)
+    long long wpack_sample_stride;             // bytes between the packed weight sets of consecutive samples (groups = N form, networks.py:84-94); 0 = shared weights
+    // TMA A operand (x is fp16 in the channel-blocked layout [N][C/8][H][W][8], see include/pasta_b200.h PG_LAYOUT_C8): the staged strip is a
+    // tensor-map box of tma_rows image rows x PW positions x 2 channel blocks, written by cp.async.bulk.tensor; no converter warps
+    int tma_a, tma_rows, tma_cb;               // on/off, rows per box, channel blocks per sample (Cin / 8)
+    uint32_t a_lbo16;                          // A descriptor leading-dimension byte offset >> 4 (distance between the two 8-channel planes of a stage)
+    int y_c8, cb_out;                          // y is fp16 channel-blocked [N][cb_out][H][W][8]
     int vec2; uint32_t w_magic;   // aligned 8-byte loader (see the converter section); ceil(2^32 / W)
     uint32_t pw_magic;         // ceil(2^32 / PW): q / PW == umulhi(q, pw_magic) for the strip positions that occur
 };
 
-#define PG_TS(slot) do { if (p.dbg) p.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + (slot)] = clock64(); } while (0)
-#define PG_PUT(slot, v) do { if (p.dbg) p.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + (slot)] = (v); } while (0)
+// Phase timestamps, load / store / fence suppression and the loader experiments exist only in -DPG_DEBUG builds (tools/conv_timeline.py builds its
+// own library); in the release library PG_DBG / PG_DBGMODE / PG_LDMODE / PG_PIPE are compile-time constants and the code behind them is removed.
+#ifdef PG_DEBUG
+#define PG_DBG(p)     ((p).dbg != nullptr)
+#define PG_DBGMODE(p) ((p).dbgmode)
+#define PG_LDMODE(p)  ((p).ldmode)
+#define PG_PIPE(p)    ((p).pipe)
+#define PG_TS(slot) do { if (PG_DBG(p)) p.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + (slot)] = clock64(); } while (0)
+#define PG_PUT(slot, v) do { if (PG_DBG(p)) p.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + (slot)] = (v); } while (0)
+#else
+#define PG_DBG(p)     false
+#define PG_DBGMODE(p) 0
+#define PG_LDMODE(p)  0
+#define PG_PIPE(p)    0
+#define PG_TS(slot) do { } while (0)
+#define PG_PUT(slot, v) do { } while (0)
+#endif
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -92,6 +115,12 @@ __device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// 3-D tensor-map tile load (TMA): box -> shared memory, completion counted in bytes on `bar`; out-of-bounds elements arrive as zeros
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
 
 // Shared-memory matrix descriptors (K-major, SWIZZLE_NONE, rows 16 B apart: SBO = 128 B, K chunks LBO bytes apart, descriptor version 1) are
@@ -130,6 +159,16 @@ __device__ __forceinline__ void store_half(float* y, size_t off, float v) {
     reinterpret_cast<unsigned short*>(y)[off] = h;
 }
 
+// eight fp32 -> one 16-byte row of the channel-blocked fp16 layout (the conversion the consuming layer's loader would apply)
+__device__ __forceinline__ uint4 pack_half8(const float* v) {
+    uint4 r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r.x) : "f"(v[1]), "f"(v[0]));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r.y) : "f"(v[3]), "f"(v[2]));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r.z) : "f"(v[5]), "f"(v[4]));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r.w) : "f"(v[7]), "f"(v[6]));
+    return r;
+}
+
 // two fp32 -> packed fp16x2 / bf16x2 (a in the low half), round-to-nearest, saturating to the largest finite value
 __device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
     uint32_t r;
@@ -145,6 +184,9 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
 // output-parity 3x3 kernels of the polyphase form; virtual channel v = phase * Cout + o.
 struct PackParams {
     const float* w; const float* fir; void* out; int Cout, Cin, ks, BN, nchunks, ntaps, ntiles, flip_weight, fmt, up2, down2, im2col; float w_scale;
+    // batched form (blockIdx.y = sample): per-sample weight sets `w_bstride` elements apart (0: one shared set) and / or per-sample input-channel
+    // scales styles[sample, Cin] folded into the weights (the modulation of networks.py:64-66 applied while packing)
+    long long w_bstride; const float* styles;
 };
 
 __device__ float composite_tap(const PackParams& p, int o, int c, int a, int b, int th, int tw) {
@@ -182,6 +224,10 @@ __device__ float down2_tap(const PackParams& p, int o, int c, int a, int b, int 
 __global__ void conv_prepack_kernel(PackParams p) {
     const size_t total = (size_t)p.ntiles * p.nchunks * p.ntaps * 2 * p.BN * 8;
     const int nvirt = p.up2 ? 4 * p.Cout : p.Cout;
+    const int sample = blockIdx.y;
+    p.w += (size_t)sample * p.w_bstride;
+    p.out = (void*)((uint16_t*)p.out + (size_t)sample * total);
+    const float* sty = p.styles ? p.styles + (size_t)sample * p.Cin : nullptr;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         size_t r = idx;
         const int e = r % 8; r /= 8;
@@ -217,6 +263,11 @@ __global__ void conv_prepack_kernel(PackParams p) {
             }
         }
         val *= p.w_scale;
+        if (sty && val != 0.f) {
+            // real input channel of GEMM channel c (down-2: (row parity, channel, column parity) order; folded taps: channel-major)
+            const int cr = p.down2 ? ((c % (2 * p.Cin)) >> 1) : (p.im2col ? c / (p.ks * p.ks) : c);
+            val *= sty[cr];
+        }
         if (p.fmt == 0) ((__half*)p.out)[idx] = __float2half_rn(fminf(fmaxf(val, -65504.f), 65504.f));
         else            ((__nv_bfloat16*)p.out)[idx] = __float2bfloat16_rn(val);
     }
@@ -229,9 +280,11 @@ struct MmaRing { int sa, sb; uint32_t pa, pb; };
 // kernel parameter, a compile-time constant or a warp-uniform loop counter, so one MMA costs two uniform adds.
 template <int KS, int NACC>
 __device__ __forceinline__ void mma_issue_loop(const ConvParams& p, uint32_t a_base, uint32_t b_base, uint32_t a_full, uint32_t a_empty,
-                                               uint32_t b_full, uint32_t b_empty, uint32_t acc_full, uint32_t tmem_base, uint32_t issue, MmaRing& ring) {
+                                               uint32_t b_full, uint32_t b_empty, uint32_t acc_full, uint32_t tmem_base, uint32_t issue, MmaRing& ring,
+                                               const uint32_t a_off16 = 0u) {
+    // a_off16: first staged 16-byte row of this tile inside a stage (TMA mode: the box starts at a row boundary of the image, the tile does not)
     const uint32_t hi = (128u >> 4) | (1u << 14);                         // SBO = 128 B, descriptor version 1 (bits 32..47)
-    const uint32_t a_lo_const = ((uint32_t)p.PA & 0x3FFF) << 16;          // LBO = PA * 16 B  (>> 4)
+    const uint32_t a_lo_const = (p.a_lbo16 & 0x3FFF) << 16;               // LBO = distance between the two 8-channel planes of a stage (>> 4)
     const uint32_t b_lo_const = ((uint32_t)p.BN & 0x3FFF) << 16;          // LBO = BN * 16 B  (>> 4)
     const uint32_t b_tile16 = p.b_tile_bytes >> 4;
     const uint32_t bn = (uint32_t)p.BN;
@@ -241,17 +294,17 @@ __device__ __forceinline__ void mma_issue_loop(const ConvParams& p, uint32_t a_b
     int sa = ring.sa, sb = ring.sb; uint32_t pa = ring.pa, pb = ring.pb;   // stage / slot cursors continue across the tiles of a persistent CTA
     long long wait_a = 0, wait_b = 0;              // instrumentation (registers; written once at the end)
     for (int ci = 0; ci < nchunks; ci++) {
-        long long t0 = p.dbg ? clock64() : 0;
+        long long t0 = PG_DBG(p) ? clock64() : 0;
         mbar_wait(a_full + 8u * (uint32_t)sa, pa);
         tc_fence_after();
-        if (p.dbg) { if (ci == 0) { if (issue) PG_TS(2); } else wait_a += clock64() - t0; }
-        const uint32_t a_lo = a_lo_const | ((a_base + (uint32_t)sa * p.a_stage_bytes) >> 4);
+        if (PG_DBG(p)) { if (ci == 0) { if (issue) PG_TS(2); } else wait_a += clock64() - t0; }
+        const uint32_t a_lo = (a_lo_const | ((a_base + (uint32_t)sa * p.a_stage_bytes) >> 4)) + a_off16;
 #pragma unroll
         for (int kh = 0; kh < KS; kh++) {
-            t0 = p.dbg ? clock64() : 0;
+            t0 = PG_DBG(p) ? clock64() : 0;
             mbar_wait(b_full + 8u * (uint32_t)sb, pb);
             tc_fence_after();
-            if (p.dbg) wait_b += clock64() - t0;
+            if (PG_DBG(p)) wait_b += clock64() - t0;
             const uint32_t b_lo = b_lo_const | ((b_base + (uint32_t)sb * p.b_slot_bytes) >> 4);
             if (issue) {
 #pragma unroll
@@ -345,8 +398,8 @@ __device__ __forceinline__ void convert_vec2(const ConvParams& p, const float* x
             ok = ok && wimg >= 0 && wimg < p.Wimg;
             eoff = h * p.Wimg + wimg;
         }
-        goff[idx] = (ok && !(p.dbgmode & 1)) ? eoff : -1;
-        const bool st_ok = ok && !(p.dbgmode & 2);
+        goff[idx] = (ok && !(PG_DBGMODE(p) & 1)) ? eoff : -1;
+        const bool st_ok = ok && !(PG_DBGMODE(p) & 2);
         sA[idx] = (st_ok && s1st >= 0 && s1st < p.PA) ? (uint32_t)((plane * p.PA + s1st) * 16) : 0xffffffffu;
         sB[idx] = (st_ok && s2nd >= 0 && s2nd < p.PA) ? (uint32_t)((plane * p.PA + s2nd) * 16) : 0xffffffffu;
     }
@@ -378,11 +431,11 @@ __device__ __forceinline__ void convert_vec2(const ConvParams& p, const float* x
                     } else {
                         const float* src = cb + off;
 #pragma unroll
-                        if (p.ldmode == 1) {
+                        if (PG_LDMODE(p) == 1) {
 #pragma unroll
                             for (int i = 0; i < 8; i++)
                                 if (i < nval) asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v[u][i]), "=f"(v[u][8 + i]) : "l"(src + (size_t)i * HW));
-                        } else if (p.ldmode == 2) {
+                        } else if (PG_LDMODE(p) == 2) {
 #pragma unroll
                             for (int i = 0; i < 8; i++)
                                 if (i < nval) asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(v[u][i]), "=f"(v[u][8 + i]) : "l"(src + (size_t)i * HW));
@@ -395,9 +448,9 @@ __device__ __forceinline__ void convert_vec2(const ConvParams& p, const float* x
                 }
             }
             if (r == 0) {
-                const long long t0 = p.dbg ? clock64() : 0;
+                const long long t0 = PG_DBG(p) ? clock64() : 0;
                 mbar_wait(smem_u32(&a_empty[st]), ph ^ 1);
-                if (p.dbg) wait_e += clock64() - t0;
+                if (PG_DBG(p)) wait_e += clock64() - t0;
                 if (zero_pads && ci < p.SA) {
                     for (int sl = gw * 32 + lane; sl < p.PA; sl += wpg * 32) {
                         const int q = q0 + sl;
@@ -441,7 +494,7 @@ __device__ __forceinline__ void convert_vec2(const ConvParams& p, const float* x
                 if (a2 != 0xffffffffu) *reinterpret_cast<uint4*>(stage + a2) = d2;
             }
         }
-        if (!(p.dbgmode & 16)) fence_proxy_async();        // generic-proxy stores -> visible to the tensor core (async proxy)
+        if (!(PG_DBGMODE(p) & 16)) fence_proxy_async();        // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&a_full[st]));
     }
@@ -462,12 +515,12 @@ __device__ __forceinline__ void convert_down2(const ConvParams& p, const float* 
         const int tt = cw + idx * kConvWarps;
         const int spos = (tt >> 1) * 32 + lane;
         const int q = q0 + spos;
-        bool ok = tt < ntasks && q >= 0 && q < p.Lp && !(p.dbgmode & 1);
+        bool ok = tt < ntasks && q >= 0 && q < p.Lp && !(PG_DBGMODE(p) & 1);
         int h = 0, w = 0;
         if (ok) { h = (int)__umulhi((uint32_t)q, p.pw_magic); w = q - h * p.PW; ok = w < p.W; }
         if (p.band_tw) { w = band * p.band_tw - 2 + w; ok = ok && w >= 0 && w < p.Wimg; }
         soff[idx] = ok ? 2 * h * p.win + 2 * w : -1;                                  // input element of (row 2h, column 2w); + a * win per chunk
-        slot[idx] = (tt < ntasks && !(p.dbgmode & 2)) ? (uint32_t)((plane * p.PA + spos) * 16) : 0xffffffffu;
+        slot[idx] = (tt < ntasks && !(PG_DBGMODE(p) & 2)) ? (uint32_t)((plane * p.PA + spos) * 16) : 0xffffffffu;
     }
     const bool has_in_act = p.in_act != PG_ACT_LINEAR;
     const float in_slope = (p.in_act == PG_ACT_RELU) ? 0.f : p.in_alpha;
@@ -494,9 +547,9 @@ __device__ __forceinline__ void convert_down2(const ConvParams& p, const float* 
                 }
             }
             if (r == 0) {
-                const long long t0 = p.dbg ? clock64() : 0;
+                const long long t0 = PG_DBG(p) ? clock64() : 0;
                 mbar_wait(smem_u32(&a_empty[st]), ph ^ 1);
-                if (p.dbg) wait_e += clock64() - t0;
+                if (PG_DBG(p)) wait_e += clock64() - t0;
             }
 #pragma unroll
             for (int u = 0; u < PER; u++) {
@@ -551,7 +604,17 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const int n, 
                 float xv[16];
 #pragma unroll
                 for (int i = 0; i < 16; i++) xv[i] = __ldg(xp + (size_t)(cc * 16 + i) * HW);
-                if (p.out_half) {
+                if (p.y_c8) {
+                    float v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const float xn_ = fmaf(xv[i], s_scale[cc * 16 + i], s_shift[cc * 16 + i]);
+                        v[i] = fmaf(xn_, 1.f + __uint_as_float(rg[i]), __uint_as_float(rb[i]));
+                        v[i] = (fmaxf(v[i], 0.f) + slope * fminf(v[i], 0.f)) * p.gain;
+                    }
+                    uint4* yb = reinterpret_cast<uint4*>(p.y) + ((size_t)n * p.cb_out + 2 * cc) * HW + (size_t)h * p.Wimg + w;
+                    yb[0] = pack_half8(v); yb[HW] = pack_half8(v + 8);
+                } else if (p.out_half) {
 #pragma unroll
                     for (int i = 0; i < 16; i++) {
                         const float xn_ = fmaf(xv[i], s_scale[cc * 16 + i], s_shift[cc * 16 + i]);
@@ -636,11 +699,16 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const int n, 
 #pragma unroll
             for (int i = 0; i < 16; i++) v[i] += res[i];
             float* yp = p.y + off;
-            if (p.out_half) {
+            if (p.y_c8) {
+                // channel-blocked fp16: the 16 channels of this chunk are two 16-byte rows, consecutive lanes write consecutive rows (host side
+                // guarantees Cout % 16 == 0 and no up-2)
+                uint4* yb = reinterpret_cast<uint4*>(p.y) + ((size_t)n * p.cb_out + (size_t)(jn * p.BN + cc * 16) / 8) * HW + (size_t)h * p.Wimg + w;
+                yb[0] = pack_half8(v); yb[HW] = pack_half8(v + 8);
+            } else if (p.out_half) {
 #pragma unroll
                 for (int i = 0; i < 16; i++) if (i < nvalid) store_half(p.y, off + (size_t)i * ystride, v[i]);
             } else if (nvalid == 16) {
-                if (p.ldmode == 3) {                              // tuning: streaming (evict-first) stores
+                if (PG_LDMODE(p) == 3) {                              // tuning: streaming (evict-first) stores
 #pragma unroll
                     for (int i = 0; i < 16; i++) __stcs(yp + (size_t)i * ystride, v[i]);
                 } else {
@@ -684,7 +752,7 @@ __device__ __forceinline__ void stage_epilogue_constants(const ConvParams& p, co
 // ---------------------------------------------------------------------------------------------- main kernel
 // SCALE: the A operand needs a per-channel scale and/or an input activation (modulated / SPADE layers); plain layers skip both.
 template <bool SCALE>
-__global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ CUtensorMap tmap_a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const int tile = blockIdx.x % p.tiles_per_img;
@@ -695,7 +763,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
     const int BM   = 128 * p.NACC;
     const int m0   = tile * BM;
     const int HW   = p.H * p.Wimg;
-    if (threadIdx.x == 0 && p.dbg) {
+    if (threadIdx.x == 0 && PG_DBG(p)) {
         PG_TS(0);
         uint32_t smid; unsigned long long gt;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -716,10 +784,11 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
     int2* s_tab = reinterpret_cast<int2*>(acc_full + 2);    // folded-tap mode: per virtual channel (element offset, (dh << 16) | (dw & 0xffff))
 
     if (warp == 0 && lane == 0) {
-        for (int i = 0; i < p.SA; i++) { mbar_init(smem_u32(&a_full[i]), (uint32_t)(kConvWarps / p.cgroups)); mbar_init(smem_u32(&a_empty[i]), 1); }
+        for (int i = 0; i < p.SA; i++) { mbar_init(smem_u32(&a_full[i]), p.tma_a ? 1u : (uint32_t)(kConvWarps / p.cgroups)); mbar_init(smem_u32(&a_empty[i]), 1); }
         for (int i = 0; i < p.SB; i++) { mbar_init(smem_u32(&b_full[i]), 1); mbar_init(smem_u32(&b_empty[i]), 1); }
         mbar_init(smem_u32(acc_full), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (p.tma_a) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
@@ -735,7 +804,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
         }
     }
     stage_epilogue_constants(p, n, jn, s_scale, s_shift, threadIdx.x, kConvThreads);
-    if (p.vec2) {     // the vec2 loader never writes the padding slots of the strip: zero every A stage once
+    if (p.vec2 && !p.tma_a) {     // the vec2 loader never writes the padding slots of the strip: zero every A stage once
         uint4* z = reinterpret_cast<uint4*>(a_base);
         const int nz = (int)((size_t)p.SA * p.a_stage_bytes / 16);
         for (int i = threadIdx.x; i < nz; i += kConvThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -747,15 +816,31 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) PG_TS(1);
 
+    // TMA A operand: the staged box starts at image row r0 = floor(q0 / PW) (q0 = first staged strip position of this tile, may be negative);
+    // the tile's first GEMM row sits a_off rows into the stage
+    const int tma_halo = (p.ks == 3) ? p.PW + 1 : 0;
+    const int tma_q0 = m0 - tma_halo;
+    const int tma_r0 = tma_q0 >= 0 ? tma_q0 / p.PW : -((-tma_q0 + p.PW - 1) / p.PW);
+    const uint32_t a_off16 = p.tma_a ? (uint32_t)(tma_q0 - tma_r0 * p.PW) : 0u;
     if (warp == 0) {
         // ===================== B producer: a ring of small bulk copies (`tps` taps each) keeps many copies in flight =====================
+        // (TMA mode: the same thread also issues the A boxes, one per 16-channel chunk, in chunk order ahead of that chunk's weight slots)
         if (lane == 0) {
-            const uint8_t* src = (const uint8_t*)p.wpack + (size_t)jn * p.nchunks * p.ntaps * p.b_tile_bytes;
+            const uint8_t* src = (const uint8_t*)p.wpack + (size_t)n * p.wpack_sample_stride + (size_t)jn * p.nchunks * p.ntaps * p.b_tile_bytes;
             const int nslots = p.nchunks * (p.ntaps / p.tps);
+            const int spc = p.ntaps / p.tps;                   // weight slots per chunk
+            const int col0 = p.band_tw ? 2 * (band * p.band_tw - 2) : 0;       // box start along the row, in 8-byte units (two per position)
             int st = 0; uint32_t ph = 0;
+            int sa = 0; uint32_t pa = 0;
             for (int g = 0; g < nslots; g++) {
+                if (p.tma_a && g % spc == 0) {
+                    mbar_wait(smem_u32(&a_empty[sa]), pa ^ 1);
+                    mbar_expect_tx(smem_u32(&a_full[sa]), p.a_stage_bytes);
+                    tma_load_3d(smem_u32(a_base + (size_t)sa * p.a_stage_bytes), &tmap_a, col0, tma_r0, n * p.tma_cb + 2 * (g / spc), smem_u32(&a_full[sa]));
+                    if (++sa == p.SA) { sa = 0; pa ^= 1; }
+                }
                 mbar_wait(smem_u32(&b_empty[st]), ph ^ 1);
-                if (p.dbgmode & 4) { mbar_arrive(smem_u32(&b_full[st])); if (++st == p.SB) { st = 0; ph ^= 1; } continue; }
+                if (PG_DBGMODE(p) & 4) { mbar_arrive(smem_u32(&b_full[st])); if (++st == p.SB) { st = 0; ph ^= 1; } continue; }
                 mbar_expect_tx(smem_u32(&b_full[st]), p.b_slot_bytes);
                 bulk_g2s(smem_u32(b_base + (size_t)st * p.b_slot_bytes), src + (size_t)g * p.b_slot_bytes, p.b_slot_bytes, smem_u32(&b_full[st]));
                 if (++st == p.SB) { st = 0; ph ^= 1; }
@@ -770,12 +855,12 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
                        be = smem_u32(b_empty), accf = smem_u32(acc_full);
         const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
         MmaRing ring = {0, 0, 0u, 0u};
-#define PG_ISSUE(KS_, NACC_) mma_issue_loop<KS_, NACC_>(p, ab, bb, af, ae, bf, be, accf, tb, issue, ring)
+#define PG_ISSUE(KS_, NACC_) mma_issue_loop<KS_, NACC_>(p, ab, bb, af, ae, bf, be, accf, tb, issue, ring, a_off16)
         if (p.ks == 3) { if (p.NACC == 4) PG_ISSUE(3, 4); else if (p.NACC == 3) PG_ISSUE(3, 3); else if (p.NACC == 2) PG_ISSUE(3, 2); else PG_ISSUE(3, 1); }
         else           { if (p.NACC == 4) PG_ISSUE(1, 4); else if (p.NACC == 3) PG_ISSUE(1, 3); else if (p.NACC == 2) PG_ISSUE(1, 2); else PG_ISSUE(1, 1); }
 #undef PG_ISSUE
     } else {
-        // ===================== A converters =====================
+        // ===================== A converters (none in TMA mode: these warps are the epilogue only) =====================
         // Each warp owns the tasks t = cw, cw + 8, ... of every chunk and walks them as ONE stream that runs across chunk boundaries, in register
         // batches (stream_tasks): the global loads of a batch never wait for the shared-memory stage, only the stores wait on a_empty.
         //   * vec2 loader (W even, 8-byte aligned planes, not down-2): a task is 64 consecutive floats (one aligned 256-byte run) of 8 channels of
@@ -785,7 +870,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
         //   * scalar loader: any W, down-2 space-to-depth reads; writes every staged slot (zeros where out of range).
         const int cw = warp - 2;
         const int halo = (p.ks == 3) ? p.PW + 1 : 0;
-        const int n_in = (p.dbgmode & 8) ? 0 : n;      // tuning: every sample reads sample 0 (input stays L2-resident)
+        const int n_in = (PG_DBGMODE(p) & 8) ? 0 : n;      // tuning: every sample reads sample 0 (input stays L2-resident)
         const float* xn = p.down2 ? p.x + (size_t)n_in * p.cin_real * p.hin * p.win
                         : p.in_half ? reinterpret_cast<const float*>(reinterpret_cast<const __half*>(p.x) + (size_t)n_in * p.cin1 * HW)
                                     : p.x + (size_t)n_in * p.cin1 * HW;
@@ -798,9 +883,9 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
         int s_st = 0; uint32_t s_ph = 0;                       // store cursor: stage / parity of the chunk being written
         long long wait_e = 0, t_issue = 0, t_store = 0;
         auto stage_begin = [&]() {
-            const long long t0 = p.dbg ? clock64() : 0;
+            const long long t0 = PG_DBG(p) ? clock64() : 0;
             mbar_wait(smem_u32(&a_empty[s_st]), s_ph ^ 1);
-            if (p.dbg) wait_e += clock64() - t0;
+            if (PG_DBG(p)) wait_e += clock64() - t0;
         };
         auto stage_end = [&]() {
             fence_proxy_async();                               // generic-proxy stores -> visible to the tensor core (async proxy)
@@ -824,7 +909,9 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
             return pk;
         };
 
-        if (p.vec2) {
+        if (p.tma_a) {
+            // nothing to stage: the A boxes arrive by TMA (warp 0)
+        } else if (p.vec2) {
             // flat element range [e_lo, e_hi) of the plane that the staged strip slots [q0, q0 + PA) cover
             const int qa = q0 < 0 ? 0 : q0, qb = (q0 + p.PA < p.Lp ? q0 + p.PA : p.Lp) - 1;     // first / last strip position inside the image
             int ha = (int)__umulhi((uint32_t)qa, p.pw_magic), wa = qa - ha * p.PW;
@@ -840,7 +927,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
             auto load_task = [&](float (&v)[16], int ci, int idx) {
                 const int tt = cw + idx * kConvWarps;
                 const int g = g_lo + (tt >> 1) * 32 + lane;
-                const bool ok = ci < nchunks && tt < ntasks && g < g_hi && !(p.dbgmode & 1);
+                const bool ok = ci < nchunks && tt < ntasks && g < g_hi && !(PG_DBGMODE(p) & 1);
                 const int c0 = ci * kKC + (tt & 1) * 8;
                 const float* src = chan_base(c0) + 2 * g;
 #pragma unroll
@@ -860,7 +947,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
                 if (idx == 0) stage_begin();
                 const int tt = cw + idx * kConvWarps;
                 const int g = g_lo + (tt >> 1) * 32 + lane;
-                if (tt < ntasks && g < g_hi && !(p.dbgmode & 2)) {
+                if (tt < ntasks && g < g_hi && !(PG_DBGMODE(p) & 2)) {
                     const int plane = tt & 1;
                     const int e = 2 * g;
                     const int h = (int)__umulhi((uint32_t)e, p.w_magic);
@@ -888,7 +975,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
                 if (tpw <= 1) PG_CONVERT(1, 1); else if (tpw == 2) PG_CONVERT(2, 1); else if (tpw == 3) PG_CONVERT(3, 1);
                 else if (tpw == 4) PG_CONVERT(2, 2); else PG_CONVERT(3, 2);
             } else {
-                stream_tasks<16, 2>(load_task, store_task, tpw, nchunks, p.pipe != 0, p.dbg != nullptr, t_issue, t_store);
+                stream_tasks<16, 2>(load_task, store_task, tpw, nchunks, PG_PIPE(p) != 0, PG_DBG(p), t_issue, t_store);
             }
 #undef PG_CONVERT
 #undef PG_CONVERT_H
@@ -899,7 +986,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
                 const int tt = cw + idx * kConvWarps;
                 const int q = q0 + (tt >> 1) * 32 + lane;                 // strip position of this staged row
                 int h = 0, w = 0;
-                bool ok = ci < nchunks && tt < ntasks && q >= 0 && q < p.Lp && !(p.dbgmode & 1);
+                bool ok = ci < nchunks && tt < ntasks && q >= 0 && q < p.Lp && !(PG_DBGMODE(p) & 1);
                 if (ok) { h = (int)__umulhi((uint32_t)q, p.pw_magic); w = q - h * p.PW; ok = w < p.W; }
                 if (p.band_tw) { w = band * p.band_tw - 2 + w; ok = ok && w >= 0 && w < p.Wimg; }     // band mode (down-2 layers): image column of this slot
                 const int c0 = ci * kKC + (tt & 1) * 8;
@@ -941,7 +1028,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
                 if (ci >= nchunks) return;
                 if (idx == 0) stage_begin();
                 const int tt = cw + idx * kConvWarps;
-                if (tt < ntasks && !(p.dbgmode & 2)) {
+                if (tt < ntasks && !(PG_DBGMODE(p) & 2)) {
                     const int plane = tt & 1, spos = (tt >> 1) * 32 + lane;
                     if (SCALE) scale8(v, ci, plane);
                     *reinterpret_cast<uint4*>(a_base + (size_t)s_st * p.a_stage_bytes + (size_t)plane * p.PA * 16 + (size_t)spos * 16) = pack8(v);
@@ -952,7 +1039,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
             if (p.down2 && p.lean && tpw <= 6) {
                 if (tpw <= 2) PG_CONVERT_D(2, 1); else if (tpw <= 4) PG_CONVERT_D(4, 1); else PG_CONVERT_D(3, 2);
             } else {
-                stream_tasks<8, 4>(load_task, store_task, tpw, nchunks, p.pipe != 0, p.dbg != nullptr, t_issue, t_store);
+                stream_tasks<8, 4>(load_task, store_task, tpw, nchunks, PG_PIPE(p) != 0, PG_DBG(p), t_issue, t_store);
             }
 #undef PG_CONVERT_D
         }
@@ -963,7 +1050,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
         if (cw == 0 && lane == 0) PG_TS(4);
         epilogue_tile(p, n, jn, m0, HW, tmem_base, s_scale, s_shift, warp & 3, cw >> 2, kConvWarps / 4, lane, band);   // 2 warps per TMEM lane quarter
     }
-    if (threadIdx.x == 64 && p.dbg) {
+    if (threadIdx.x == 64 && PG_DBG(p)) {
         PG_TS(5);
         unsigned long long gt;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -1034,8 +1121,8 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_igemm_persistent_kernel(con
             const int nslots = p.nchunks * (p.ntaps / p.tps);
             int st = 0; uint32_t ph = 0;
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
-                const int jn = t / tiles_n;
-                const uint8_t* src = (const uint8_t*)p.wpack + (size_t)jn * p.nchunks * p.ntaps * p.b_tile_bytes;
+                const int jn = t / tiles_n, n_t = (t - jn * tiles_n) / p.tiles_per_img;
+                const uint8_t* src = (const uint8_t*)p.wpack + (size_t)n_t * p.wpack_sample_stride + (size_t)jn * p.nchunks * p.ntaps * p.b_tile_bytes;
                 for (int g = 0; g < nslots; g++) {
                     mbar_wait(smem_u32(&b_empty[st]), ph ^ 1);
                     mbar_expect_tx(smem_u32(&b_full[st]), p.b_slot_bytes);
@@ -1123,17 +1210,48 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_igemm_persistent_kernel(con
     }
 }
 
+
 // ---------------------------------------------------------------------------------------------- host side
 struct ConvPlan {
     int BN, ntiles_n, nchunks, ntaps, NACC, PW, Lp, tiles_per_img, PA, SA, SB, tps;
     uint32_t a_stage, b_stage, b_slot, b_tile; size_t smem; uint32_t tmem_cols; int nvirt;
+    int tma_rows; uint32_t a_lbo16;
 };
 
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
-static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
+// Plan / loader choices that were measured against each other.  Defaults are the measured best; the environment is read ONCE, when
+// the library is first used, and pg_set_tuning() changes a value for the rest of the process (tests and tools/ compare variants through it).
+struct Tuning {
+    int bands = 1, band_tw = 64, band_minw = 128, band_ratio10 = 0, persist = 0, nacc = 0, pair = 1, vec2 = 1, lean = 1, cgroups = 1, tma = 1;
+#ifdef PG_DEBUG
+    int pipe = 0, ldmode = 0, dbgmode = 0;
+#endif
+};
+struct TuningKey { const char* key; const char* env; int Tuning::*field; };
+static const TuningKey kTuningKeys[] = {
+    {"conv_bands", "PASTA_B200_CONV_BANDS", &Tuning::bands}, {"conv_band_tw", "PASTA_B200_CONV_BAND_TW", &Tuning::band_tw},
+    {"conv_band_minw", "PASTA_B200_CONV_BAND_MINW", &Tuning::band_minw}, {"conv_band_ratio10", "PASTA_B200_CONV_BAND_RATIO10", &Tuning::band_ratio10},
+    {"conv_persist", "PASTA_B200_CONV_PERSIST", &Tuning::persist}, {"conv_nacc", "PASTA_B200_CONV_NACC", &Tuning::nacc},
+    {"conv_pair", "PASTA_B200_CONV_PAIR", &Tuning::pair}, {"conv_vec2", "PASTA_B200_CONV_VEC2", &Tuning::vec2},
+    {"conv_lean", "PASTA_B200_CONV_LEAN", &Tuning::lean}, {"conv_cgroups", "PASTA_B200_CONV_CGROUPS", &Tuning::cgroups},
+    {"conv_tma", "PASTA_B200_CONV_TMA", &Tuning::tma},
+#ifdef PG_DEBUG
+    {"conv_pipe", "PASTA_B200_CONV_PIPE", &Tuning::pipe}, {"conv_ldmode", "PASTA_B200_CONV_LDMODE", &Tuning::ldmode},
+    {"conv_dbgmode", "PASTA_B200_CONV_DBGMODE", &Tuning::dbgmode},
+#endif
+};
+static Tuning& tuning() {
+    static Tuning t = [] {
+        Tuning v;
+        for (const TuningKey& k : kTuningKeys) { const char* e = getenv(k.env); if (e && *e) v.*(k.field) = atoi(e); }
+        return v;
+    }();
+    return t;
+}
 
-static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int ks, int up2, bool band = false, int max_nacc = 4) {
+static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int ks, int up2, bool band = false, int max_nacc = 4, bool tma = false) {
+    const Tuning& tn = tuning();
     pl.nvirt = up2 ? 4 * Cout : Cout;
     pl.ntaps = ks * ks;
     pl.nchunks = (Cin + kKC - 1) / kKC;
@@ -1147,8 +1265,8 @@ static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int k
     // Two co-resident CTAs per SM when the N tile is narrow (BN <= 128): each gets half of TMEM (256 columns) and ~100 KB of shared
     // memory, so one CTA's prologue / pipeline fill / epilogue overlaps the other's main loop.  Wide tiles (BN = 256) keep the SM alone.
     bool pair = bn <= 128;
-    const int force_nacc = env_int("PASTA_B200_CONV_NACC", 0);
-    if (env_int("PASTA_B200_CONV_PAIR", 1) == 0 || force_nacc * bn > 256) pair = false;
+    const int force_nacc = tn.nacc;
+    if (tn.pair == 0 || force_nacc * bn > 256) pair = false;
     const int tmem_budget = pair ? 256 : 512;
     const int max_acc = tmem_budget / bn < max_nacc ? tmem_budget / bn : max_nacc;
     int nacc = 1;
@@ -1175,6 +1293,13 @@ static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int k
     const int halo = (ks == 3) ? 2 * pl.PW + 2 : 0;
     pl.PA = round_up(BM + halo, 32);
     pl.a_stage = (uint32_t)pl.PA * 32u;                        // 2 planes x 16 B per position
+    pl.tma_rows = 0; pl.a_lbo16 = (uint32_t)pl.PA;
+    if (tma) {
+        // the box starts at the image row that holds the tile's first staged position: up to PW - 1 positions before it, BM + halo after
+        pl.tma_rows = (pl.PW - 1 + BM + halo + pl.PW - 1) / pl.PW;
+        pl.a_lbo16 = (uint32_t)(pl.tma_rows * pl.PW);
+        pl.a_stage = (uint32_t)round_up(2 * pl.tma_rows * pl.PW * 16, 128);
+    }
     pl.b_tile = (uint32_t)bn * 32u;
     pl.b_stage = pl.b_tile * pl.ntaps;
     const size_t fixed = (size_t)pl.nchunks * kKC * 4 + (size_t)bn * 8 + 96 * 8 + ((ks == 1 && Cin <= 160) ? 160 * 8 : 0);   // last term: folded-tap offset table
@@ -1199,10 +1324,49 @@ static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int k
     return PG_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point query (the library links cudart only)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); f = nullptr; }
+        return (EncodeTiledFn)f;
+    }();
+    return fn;
+}
+
+// Tensor map of a channel-blocked fp16 activation [N][CB][H][W][8] for the A operand: a row of one channel block is W x 16 contiguous bytes, described as
+// 2 W eight-byte elements so that a box row of up to 128 strip positions is ONE contiguous run; box = {2 PW, rows, 2 channel blocks}.  Positions
+// outside the image (the strip's zero column, halo rows above / below, band halos beyond the edges) are the map's zero fill.
+static int make_a_tensor_map(CUtensorMap& tm, const void* x, int N, int CB, int H, int W, int PW, int rows) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return fail(PG_ERR_CUDA, "conv2d_igemm: cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[3] = {(cuuint64_t)2 * W, (cuuint64_t)H, (cuuint64_t)N * CB};
+    const cuuint64_t strides[2] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+    const cuuint32_t box[3] = {(cuuint32_t)2 * PW, (cuuint32_t)rows, 2u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(PG_ERR_CUDA, "conv2d_igemm: cuTensorMapEncodeTiled failed (%d) for W=%d H=%d PW=%d rows=%d", (int)r, W, H, PW, rows);
+    return PG_OK;
+}
+
 }  // namespace pg
 
+extern "C" int pg_set_tuning(const char* key, int32_t value) {
+    using namespace pg;
+    PG_REQUIRE(key != nullptr, "pg_set_tuning: key must not be NULL");
+    for (const TuningKey& k : kTuningKeys)
+        if (strcmp(k.key, key) == 0) { tuning().*(k.field) = value; return PG_OK; }
+    return fail(PG_ERR_INVALID_ARGUMENT, "pg_set_tuning: unknown key '%s'", key);
+}
+
+#ifdef PG_DEBUG
 static long long* g_conv_dbg = nullptr;
 extern "C" void pg_debug_set_buffer(void* buf) { g_conv_dbg = (long long*)buf; }
+#endif
 
 // Small-K layers (first layers: 3 -> 64 channels, 7x7 or 3x3): the k x k taps are folded into the GEMM K dimension ("im2col" virtual channels
 // v = c * k * k + kh * k + kw, i.e. the weight tensor's own memory order) and the layer runs as a 1x1 convolution over Cin * k * k channels,
@@ -1228,49 +1392,69 @@ static int conv_validate(int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_
     return PG_OK;
 }
 
-extern "C" int pg_conv2d_igemm_prepack(const float* w, const float* fir, float w_scale, int32_t Cin, int32_t Cout, int32_t ksize, int32_t up,
-                                       int32_t flip_weight, int32_t operand_format, void* workspace, int64_t workspace_bytes, void* stream) {
+extern "C" int pg_conv2d_igemm_prepack_batched(const float* w, int64_t w_batch_stride, const float* styles, int32_t batch, const float* fir, float w_scale,
+                                               int32_t Cin, int32_t Cout, int32_t ksize, int32_t up, int32_t flip_weight, int32_t operand_format,
+                                               void* workspace, int64_t workspace_bytes, void* stream) {
     using namespace pg;
     int rc = conv_validate(1, Cin, Cout, 8, 8, ksize, up, operand_format);
     if (rc != PG_OK) return rc;
     PG_REQUIRE(up == 1 || fir != nullptr, "conv2d_igemm: resampling needs the 4x4 FIR");
     PG_REQUIRE(w && workspace, "conv2d_igemm: w and workspace must be device pointers");
+    PG_REQUIRE(batch >= 1 && batch <= 65535 && w_batch_stride >= 0, "conv2d_igemm: batch must be in [1, 65535]");
     const bool down2 = up == PG_CONV_DOWN2;
     ConvPlan pl;
     const bool im2col = use_im2col(Cin, ksize, up);
     rc = make_plan(pl, 1, down2 ? 4 * Cin : (im2col ? Cin * ksize * ksize : Cin), Cout, 8, 8, im2col ? 1 : ksize, up == 2);
     if (rc != PG_OK) return rc;
     const int64_t need = (int64_t)pl.ntiles_n * pl.nchunks * pl.b_stage;
-    PG_REQUIRE(workspace_bytes >= need, "conv2d_igemm: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
+    PG_REQUIRE(workspace_bytes >= need * batch, "conv2d_igemm: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)(need * batch));
     PackParams pp;
     pp.w = w; pp.fir = fir; pp.out = workspace; pp.Cout = Cout; pp.Cin = Cin; pp.ks = ksize; pp.BN = pl.BN; pp.nchunks = pl.nchunks;
     pp.ntaps = pl.ntaps; pp.ntiles = pl.ntiles_n; pp.flip_weight = flip_weight ? 1 : 0; pp.fmt = operand_format; pp.up2 = up == 2; pp.down2 = down2; pp.w_scale = w_scale; pp.im2col = im2col;
+    pp.w_bstride = w_batch_stride; pp.styles = styles;
     const size_t pack_total = (size_t)need / 2;
     int pblocks = (int)((pack_total + 255) / 256);
-    if (pblocks > kNumSMs * 16) pblocks = kNumSMs * 16;
-    conv_prepack_kernel<<<pblocks, 256, 0, (cudaStream_t)stream>>>(pp);
+    const int cap = kNumSMs * 16 / (batch < 16 ? batch : 16);
+    if (pblocks > cap) pblocks = cap < 1 ? 1 : cap;
+    conv_prepack_kernel<<<dim3((unsigned)pblocks, (unsigned)batch), 256, 0, (cudaStream_t)stream>>>(pp);
     return launch_status("conv2d_igemm_prepack", 1);
 }
 
-static int conv_run_impl(const float* x, const void* wpack, const float* styles, const float* dcoefs,
-                         const float* noise, int64_t noise_batch_stride, const float* bias, float* y,
-                         int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t ksize, int32_t up,
-                         int32_t in_act, float in_alpha, float in_gain,
-                         int32_t act, float alpha, float gain, float clamp, int32_t operand_format, void* stream,
-                         const float* sp_x, const float* sp_mean, const float* sp_rstd,
-                         const float* x2 = nullptr, int32_t Cin1 = 0, const float* residual = nullptr, int32_t x_dtype = PG_F32, int32_t y_dtype = PG_F32) {
+extern "C" int pg_conv2d_igemm_prepack(const float* w, const float* fir, float w_scale, int32_t Cin, int32_t Cout, int32_t ksize, int32_t up,
+                                       int32_t flip_weight, int32_t operand_format, void* workspace, int64_t workspace_bytes, void* stream) {
+    return pg_conv2d_igemm_prepack_batched(w, 0, nullptr, 1, fir, w_scale, Cin, Cout, ksize, up, flip_weight, operand_format, workspace, workspace_bytes, stream);
+}
+
+static int conv_run_impl(const pg_conv_args& a) {
     using namespace pg;
+    const Tuning& tn = tuning();
+    int32_t N = a.N, Cin = a.Cin, Cout = a.Cout, H = a.H, W = a.W, ksize = a.ksize;
+    const int32_t up = a.up, operand_format = a.operand_format;
     int rc = conv_validate(N, Cin, Cout, H, W, ksize, up, operand_format);
     if (rc != PG_OK) return rc;
-    PG_REQUIRE(act == PG_ACT_LINEAR || act == PG_ACT_RELU || act == PG_ACT_LRELU, "conv2d_igemm: epilogue act must be linear/relu/lrelu");
-    PG_REQUIRE(in_act == PG_ACT_LINEAR || in_act == PG_ACT_RELU || in_act == PG_ACT_LRELU, "conv2d_igemm: input act must be linear/relu/lrelu");
+    PG_REQUIRE(a.act == PG_ACT_LINEAR || a.act == PG_ACT_RELU || a.act == PG_ACT_LRELU, "conv2d_igemm: epilogue act must be linear/relu/lrelu");
+    PG_REQUIRE(a.in_act == PG_ACT_LINEAR || a.in_act == PG_ACT_RELU || a.in_act == PG_ACT_LRELU, "conv2d_igemm: input act must be linear/relu/lrelu");
     PG_REQUIRE((int64_t)N * Cin * H * W <= INT32_MAX && (int64_t)N * Cout * H * W * (up == 2 ? 4 : 1) <= INT32_MAX, "conv2d_igemm: tensor too large");
-    PG_REQUIRE(gain > 0.f && in_gain > 0.f, "conv2d_igemm: gains must be positive (they are folded through the activation)");
+    PG_REQUIRE(a.gain > 0.f && a.in_gain > 0.f, "conv2d_igemm: gains must be positive (they are folded through the activation)");
     if (N == 0) return PG_OK;
-    PG_REQUIRE(x && wpack && y, "conv2d_igemm: x, packed weights and y must be device pointers");
+    const float* x = (const float*)a.x; const float* x2 = (const float*)a.x2;
+    PG_REQUIRE(x && a.wpack && a.y, "conv2d_igemm: x, packed weights and y must be device pointers");
+    PG_REQUIRE(a.wpack_sample_stride >= 0 && a.wpack_sample_stride % 16 == 0, "conv2d_igemm: the per-sample weight stride must be a multiple of 16 bytes");
     const bool down2 = up == PG_CONV_DOWN2;
     PG_REQUIRE(!down2 || ((uintptr_t)x & 7) == 0, "conv2d_igemm: down-2 needs an 8-byte aligned input");
     const int hin = H, win = W, cin_real = Cin;
+    const bool scale = a.styles != nullptr || a.in_act != PG_ACT_LINEAR || a.in_gain != 1.f;
+    PG_REQUIRE((a.x_dtype == PG_F32 || a.x_dtype == PG_F16) && (a.y_dtype == PG_F32 || a.y_dtype == PG_F16), "conv2d_igemm: x / y must be float32 or float16");
+    PG_REQUIRE((a.x_layout == PG_LAYOUT_NCHW || a.x_layout == PG_LAYOUT_C8) && (a.y_layout == PG_LAYOUT_NCHW || a.y_layout == PG_LAYOUT_C8), "conv2d_igemm: unknown tensor layout");
+    const bool tma = a.x_layout == PG_LAYOUT_C8;
+    if (tma) {
+        // channel-blocked fp16 input: taken as the operand bits by TMA, so no input scale / activation / concat, fp16 operands, whole 16-channel chunks
+        PG_REQUIRE(a.x_dtype == PG_F16 && !scale && !x2 && !down2 && operand_format == 0 && Cin % 16 == 0 && !use_im2col(Cin, ksize, up) && ((uintptr_t)x & 15) == 0,
+                   "conv2d_igemm: a channel-blocked input needs float16, a plain (unmodulated, no input activation, no concat) stride-1 or up-2 layer, fp16 operands and Cin %% 16 == 0");
+    }
+    if (a.y_layout == PG_LAYOUT_C8)
+        PG_REQUIRE(a.y_dtype == PG_F16 && up != 2 && !a.residual && (a.spade_x ? (Cout / 2) % 16 == 0 : Cout % 16 == 0) && ((uintptr_t)a.y & 15) == 0,
+                   "conv2d_igemm: a channel-blocked output needs float16, no up-sampling, no residual and Cout %% 16 == 0");
     if (down2) { H /= 2; W /= 2; Cin *= 4; }                      // the GEMM runs over the space-to-depth view at the output resolution
     const bool im2col = use_im2col(Cin, ksize, up);
     const int ks_real = ksize;
@@ -1285,83 +1469,98 @@ static int conv_run_impl(const float* x, const void* wpack, const float* styles,
         ConvPlan pt;
         if (make_plan(pt, N, Cin, Cout, H, W, ksize, false) == PG_OK && (2 * (pt.PA / 32) + kConvWarps - 1) / kConvWarps > 6) max_nacc = 2;
     }
-    const int kBandTW = env_int("PASTA_B200_CONV_BAND_TW", 64);     // even
+    const int kBandTW = tn.band_tw;     // even
     int band_tw = 0, nbands = 1;
     const int Wimg = W;
     // (W is the GEMM's width here: the output width for down-2, the input width for up-2.)
-    if (env_int("PASTA_B200_CONV_BANDS", 1) && ksize == 3 && !im2col && W >= env_int("PASTA_B200_CONV_BAND_MINW", 128) && W % 2 == 0 &&
-        ((uintptr_t)x & 7) == 0 && ((uintptr_t)x2 & 7) == 0 && env_int("PASTA_B200_CONV_VEC2", 1) && env_int("PASTA_B200_CONV_LEAN", 1)) {
+    // TMA boxes hold at most 128 strip positions per row, so a channel-blocked input wider than 127 columns (3x3) is always processed in bands.
+    const bool tma_needs_bands = tma && ksize == 3 && W + 1 > 128;
+    PG_REQUIRE(!tma || ksize == 3 || W <= 128, "conv2d_igemm: a channel-blocked input of a 1x1 layer must be at most 128 columns wide");
+    if ((tn.bands || tma_needs_bands) && ksize == 3 && !im2col && W >= (tma_needs_bands ? 1 : tn.band_minw) && W % 2 == 0 &&
+        (tma || (((uintptr_t)x & 7) == 0 && ((uintptr_t)x2 & 7) == 0 && tn.vec2 && tn.lean))) {
         ConvPlan pb, pf;
         const int nb = (W + kBandTW - 1) / kBandTW;
         // only where the full-width strip stages >= 2.5x what it outputs (a tile of one row), or >= 2x with an N tile of >= 128 columns (measured:
         // 256->128 @128^2 -8 %, 128->128 @128^2 -6 %); narrow N tiles at 2x lose more to the bands' 6 % of unused MMA rows than they gain
         // (64->64 @256^2 +4 %, 64->64 down-2 @512^2 +7 %)
-        const int ratio10 = env_int("PASTA_B200_CONV_BAND_RATIO10", 0);
+        const int ratio10 = tn.band_ratio10;
         bool worth = make_plan(pf, N, Cin, Cout, H, W, ksize, up == 2, false, max_nacc) == PG_OK;
         if (worth) {
             const int staged10 = 10 * pf.PA / (128 * pf.NACC);
             worth = ratio10 ? staged10 >= ratio10 : (staged10 >= 25 || (staged10 >= 20 && pf.BN >= 128));
         }
-        if (worth && make_plan(pb, N * nb, Cin, Cout, H, kBandTW + 4, ksize, up == 2, true, max_nacc) == PG_OK) {
+        if ((worth || tma_needs_bands) && make_plan(pb, N * nb, Cin, Cout, H, kBandTW + 4, ksize, up == 2, true, max_nacc, tma) == PG_OK) {
             const int pairs = (pb.PA + 3) / 2, nt = 2 * ((pairs + 31) / 32);
-            if (down2 || (nt + kConvWarps - 1) / kConvWarps <= 6) { pl = pb; band_tw = kBandTW; nbands = nb; W = kBandTW + 4; }   // down-2: generic task stream, any count
+            if (tma || down2 || (nt + kConvWarps - 1) / kConvWarps <= 6) { pl = pb; band_tw = kBandTW; nbands = nb; W = kBandTW + 4; }   // down-2: generic task stream, any count
         }
     }
+    PG_REQUIRE(!tma_needs_bands || band_tw, "conv2d_igemm: no band plan for a channel-blocked input of width %d", Wimg);
     if (!band_tw) {
-        rc = make_plan(pl, N, Cin, Cout, H, W, ksize, up == 2, false, max_nacc);
+        rc = make_plan(pl, N, Cin, Cout, H, W, ksize, up == 2, false, max_nacc, tma);
         if (rc != PG_OK) return rc;
     }
-    cudaStream_t s = (cudaStream_t)stream;
+    PG_REQUIRE(!tma || (2 * pl.PW <= 256 && pl.tma_rows <= 256), "conv2d_igemm: TMA box out of range (PW=%d rows=%d)", pl.PW, pl.tma_rows);
+    cudaStream_t s = (cudaStream_t)a.stream;
     ConvParams p;
+    memset(&p, 0, sizeof(p));
     p.band_tw = band_tw; p.nbands = nbands; p.Wimg = Wimg;
     p.down2 = down2; p.cin_real = cin_real; p.hin = hin; p.win = win;
-    PG_REQUIRE(!x2 || (!down2 && Cin1 > 0 && Cin1 < Cin && Cin1 % 8 == 0), "conv2d_igemm: the split input needs 0 < Cin1 < Cin, Cin1 %% 8 == 0 and no down-sampling");
+    PG_REQUIRE(!x2 || (!down2 && a.cin1 > 0 && a.cin1 < Cin && a.cin1 % 8 == 0), "conv2d_igemm: the split input needs 0 < Cin1 < Cin, Cin1 %% 8 == 0 and no down-sampling");
     PG_REQUIRE(!(im2col && x2), "conv2d_igemm: the split input is not available for folded-tap (small Cin) layers");
-    p.x2 = x2; p.cin1 = x2 ? Cin1 : (im2col ? cin_real : Cin); p.residual = residual;
+    p.x2 = x2; p.cin1 = x2 ? a.cin1 : (im2col ? cin_real : Cin); p.residual = a.residual;
     p.im2col = im2col ? ks_real : 0;
     p.kk_magic = (uint32_t)((0x100000000ull + (uint64_t)(ks_real * ks_real) - 1) / (uint64_t)(ks_real * ks_real));
     p.ks_magic = (uint32_t)((0x100000000ull + (uint64_t)ks_real - 1) / (uint64_t)ks_real);
-    p.x = x; p.wpack = wpack; p.styles = styles; p.dcoefs = dcoefs; p.noise = noise; p.bias = bias; p.y = y;
-    p.noise_bstride = noise_batch_stride;
+    p.x = x; p.wpack = a.wpack; p.wpack_sample_stride = a.wpack_sample_stride;
+    p.styles = a.styles; p.dcoefs = a.dcoefs; p.noise = a.noise; p.bias = a.bias; p.y = (float*)a.y;
+    p.noise_bstride = a.noise_batch_stride;
     p.N = N; p.Cin = Cin; p.Cout = pl.nvirt; p.H = H; p.W = W; p.ks = ksize;
     p.PW = pl.PW; p.Lp = pl.Lp; p.tiles_per_img = pl.tiles_per_img; p.NACC = pl.NACC; p.BN = pl.BN; p.nchunks = pl.nchunks; p.ntaps = pl.ntaps;
     p.PA = pl.PA; p.SA = pl.SA; p.SB = pl.SB; p.tps = pl.tps; p.a_stage_bytes = pl.a_stage; p.b_slot_bytes = pl.b_slot; p.b_tile_bytes = pl.b_tile;
-    p.in_act = in_act; p.in_alpha = in_alpha; p.in_gain = in_gain; p.act = act; p.alpha = alpha; p.gain = gain; p.clamp = clamp; p.fmt = operand_format;
+    p.in_act = a.in_act; p.in_alpha = a.in_alpha; p.in_gain = a.in_gain; p.act = a.act; p.alpha = a.alpha; p.gain = a.gain; p.clamp = a.clamp; p.fmt = operand_format;
     p.idesc = (1u << 4) | ((uint32_t)operand_format << 7) | ((uint32_t)operand_format << 10) | ((uint32_t)(pl.BN >> 3) << 17) | (8u << 24);
     p.tmem_cols = pl.tmem_cols;
     p.up2 = up == 2; p.cout_real = Cout;
-    p.sp_x = sp_x; p.sp_mean = sp_mean; p.sp_rstd = sp_rstd; p.spade = sp_x != nullptr;
-    if (p.spade) PG_REQUIRE(pl.ntiles_n == 1 && pl.BN == Cout && (Cout / 2) % 16 == 0 && up == 1 && sp_mean && sp_rstd,
+    p.sp_x = a.spade_x; p.sp_mean = a.spade_mean; p.sp_rstd = a.spade_rstd; p.spade = a.spade_x != nullptr;
+    if (p.spade) PG_REQUIRE(pl.ntiles_n == 1 && pl.BN == Cout && (Cout / 2) % 16 == 0 && up == 1 && a.spade_mean && a.spade_rstd && !a.wpack_sample_stride,
                             "conv2d_igemm_spade: gamma and beta (2C <= 256 channels, C %% 16 == 0) must share one N tile");
-    p.dbg = g_conv_dbg;
-    p.pipe = env_int("PASTA_B200_CONV_PIPE", 0); p.ldmode = env_int("PASTA_B200_CONV_LDMODE", 0); p.dbgmode = env_int("PASTA_B200_CONV_DBGMODE", 0); p.lean = env_int("PASTA_B200_CONV_LEAN", 1);
+    p.tma_a = tma; p.tma_rows = pl.tma_rows; p.tma_cb = cin_real / 8; p.a_lbo16 = pl.a_lbo16;
+    p.y_c8 = a.y_layout == PG_LAYOUT_C8; p.cb_out = (p.spade ? Cout / 2 : Cout) / 8;
+#ifdef PG_DEBUG
+    p.dbg = g_conv_dbg; p.pipe = tn.pipe; p.ldmode = tn.ldmode; p.dbgmode = tn.dbgmode;
+#endif
+    p.lean = tn.lean;
     p.cgroups = 1;
     p.pw_magic = (uint32_t)((0x100000000ull + (uint64_t)pl.PW - 1) / (uint64_t)pl.PW);
     p.w_magic = (uint32_t)((0x100000000ull + (uint64_t)W - 1) / (uint64_t)W);
-    p.vec2 = (!down2 && !im2col && W % 2 == 0 && ((uintptr_t)x & 7) == 0 && ((uintptr_t)x2 & 7) == 0 && env_int("PASTA_B200_CONV_VEC2", 1)) ? 1 : 0;
-    const bool scale = styles != nullptr || in_act != PG_ACT_LINEAR || in_gain != 1.f;
-    PG_REQUIRE((x_dtype == PG_F32 || x_dtype == PG_F16) && (y_dtype == PG_F32 || y_dtype == PG_F16), "conv2d_igemm: x / y must be float32 or float16");
-    p.in_half = x_dtype == PG_F16; p.out_half = y_dtype == PG_F16;
-    if (p.in_half) {
+    p.vec2 = (!tma && !down2 && !im2col && W % 2 == 0 && ((uintptr_t)x & 7) == 0 && ((uintptr_t)x2 & 7) == 0 && tn.vec2) ? 1 : 0;
+    p.in_half = a.x_dtype == PG_F16; p.out_half = a.y_dtype == PG_F16;
+    if (p.in_half && !tma) {
         // fp16 NCHW input: taken as the operand bits (no conversion), so no input scale / activation, fp16 operand format, the aligned pair loader
         const int pairs = (pl.PA + 3) / 2, tpw = (2 * ((pairs + 31) / 32) + kConvWarps - 1) / kConvWarps;
         PG_REQUIRE(!scale && !x2 && !down2 && !im2col && operand_format == 0 && W % 2 == 0 && ((uintptr_t)x & 3) == 0 && tpw <= 6,
                    "conv2d_igemm: a float16 input needs a plain (unmodulated, no input activation) stride-1 layer, fp16 operands, even W");
         p.vec2 = 1;
     }
-    {   // converter warp groups: only with the lean / fp16 loaders, and only while the doubled per-warp task count stays in the register batches
-        const int cg = env_int("PASTA_B200_CONV_CGROUPS", 1);      // measured neutral (profiles/r1 notes in DESIGN.md): off by default
+    if (!tma) {   // converter warp groups: only with the lean / fp16 loaders, and only while the doubled per-warp task count stays in the register batches
+        const int cg = tn.cgroups;      // measured neutral (profiles/r1 notes in DESIGN.md): off by default
         const int pairs = (pl.PA + 3) / 2, nt = 2 * ((pairs + 31) / 32);
         if (p.vec2 && (p.lean || p.in_half) && cg == 2 && (nt + kConvWarps / 2 - 1) / (kConvWarps / 2) <= 6) p.cgroups = 2;
         if (p.vec2 && p.lean && !p.in_half && p.cgroups == 1 && (nt + kConvWarps - 1) / kConvWarps > 6) p.lean = 0;
     }
-    PG_REQUIRE(!(p.out_half && residual), "conv2d_igemm: the residual add is not available with a float16 output");
+    PG_REQUIRE(!(p.out_half && a.residual), "conv2d_igemm: the residual add is not available with a float16 output");
     p.ntiles_n = pl.ntiles_n;
-    {   // persistent variant (one CTA per SM, double-buffered TMEM, dedicated epilogue warps) where it applies and there is more than one wave of tiles
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (tma) {
+        rc = make_a_tensor_map(tmap, x, N, cin_real / 8, H, Wimg, pl.PW, pl.tma_rows);
+        if (rc != PG_OK) return rc;
+    }
+    if (!tma) {   // persistent variant (one CTA per SM, double-buffered TMEM, dedicated epilogue warps) where it applies and there is more than one wave of tiles
         const long long total_tiles = (long long)N * pl.tiles_per_img * pl.ntiles_n;
         const int pairs = (pl.PA + 3) / 2, nt = 2 * ((pairs + 31) / 32), tpw_p = (nt + kPConvWarps / 2 - 1) / (kPConvWarps / 2);
-        const bool ok = env_int("PASTA_B200_CONV_PERSIST", 0) != 0 && !band_tw &&      // opt-in: measured slower than two co-resident one-tile CTAs
-                        p.vec2 && (p.lean || p.in_half) && up == 1 && !down2 && !im2col && !p.spade &&
+        const bool ok = tn.persist != 0 && !band_tw &&      // opt-in: measured slower than two co-resident one-tile CTAs
+                        p.vec2 && (p.lean || p.in_half) && up == 1 && !down2 && !im2col && !p.spade && !p.y_c8 &&
                         pl.BN <= 128 && pl.BN * pl.NACC <= 256 && tpw_p <= 6 && total_tiles > 2 * kNumSMs && total_tiles < (1ll << 30);
         if (ok) {
             const size_t fixed_p = (size_t)2 * pl.nchunks * kKC * 4 + (size_t)2 * pl.BN * 8 + (size_t)(2 * 4 + 2 * 24 + 4) * 8 + 64;
@@ -1385,8 +1584,28 @@ static int conv_run_impl(const float* x, const void* wpack, const float* styles,
     auto kern = scale ? conv_igemm_kernel<true> : conv_igemm_kernel<false>;
     PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     dim3 grid((unsigned)(N * nbands * pl.tiles_per_img), (unsigned)pl.ntiles_n);
-    kern<<<grid, kConvThreads, pl.smem, s>>>(p);
+    kern<<<grid, kConvThreads, pl.smem, s>>>(p, tmap);
     return launch_status("conv2d_igemm", 1);
+}
+
+extern "C" int pg_conv2d_igemm_launch(const pg_conv_args* a) {
+    using namespace pg;
+    PG_REQUIRE(a != nullptr && a->struct_bytes == sizeof(pg_conv_args), "conv2d_igemm_launch: pg_conv_args.struct_bytes does not match this library (%u vs %u)",
+               a ? a->struct_bytes : 0u, (unsigned)sizeof(pg_conv_args));
+    return conv_run_impl(*a);
+}
+
+static pg_conv_args base_args(const float* x, const void* wpack, const float* styles, const float* dcoefs, const float* noise, int64_t noise_batch_stride,
+                              const float* bias, float* y, int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t ksize, int32_t up,
+                              int32_t in_act, float in_alpha, float in_gain, int32_t act, float alpha, float gain, float clamp, int32_t operand_format, void* stream) {
+    pg_conv_args a;
+    memset(&a, 0, sizeof(a));
+    a.struct_bytes = sizeof(a);
+    a.N = N; a.Cin = Cin; a.Cout = Cout; a.H = H; a.W = W; a.ksize = ksize; a.up = up;
+    a.x = x; a.wpack = wpack; a.styles = styles; a.dcoefs = dcoefs; a.noise = noise; a.noise_batch_stride = noise_batch_stride; a.bias = bias; a.y = y;
+    a.in_act = in_act; a.in_alpha = in_alpha; a.in_gain = in_gain; a.act = act; a.alpha = alpha; a.gain = gain; a.clamp = clamp;
+    a.operand_format = operand_format; a.stream = stream;
+    return a;
 }
 
 extern "C" int pg_conv2d_igemm_run(const float* x, const void* wpack, const float* styles, const float* dcoefs,
@@ -1394,8 +1613,8 @@ extern "C" int pg_conv2d_igemm_run(const float* x, const void* wpack, const floa
                                    int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t ksize, int32_t up,
                                    int32_t in_act, float in_alpha, float in_gain,
                                    int32_t act, float alpha, float gain, float clamp, int32_t operand_format, void* stream) {
-    return conv_run_impl(x, wpack, styles, dcoefs, noise, noise_batch_stride, bias, y, N, Cin, Cout, H, W, ksize, up, in_act, in_alpha, in_gain,
-                         act, alpha, gain, clamp, operand_format, stream, nullptr, nullptr, nullptr);
+    return conv_run_impl(base_args(x, wpack, styles, dcoefs, noise, noise_batch_stride, bias, y, N, Cin, Cout, H, W, ksize, up, in_act, in_alpha, in_gain,
+                                   act, alpha, gain, clamp, operand_format, stream));
 }
 
 extern "C" int pg_conv2d_igemm_run2(const float* x, const float* x2, int32_t Cin1, const void* wpack, const float* styles, const float* dcoefs,
@@ -1403,8 +1622,10 @@ extern "C" int pg_conv2d_igemm_run2(const float* x, const float* x2, int32_t Cin
                                     int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t ksize, int32_t up,
                                     int32_t in_act, float in_alpha, float in_gain,
                                     int32_t act, float alpha, float gain, float clamp, int32_t operand_format, int32_t x_dtype, int32_t y_dtype, void* stream) {
-    return conv_run_impl(x, wpack, styles, dcoefs, noise, noise_batch_stride, bias, y, N, Cin, Cout, H, W, ksize, up, in_act, in_alpha, in_gain,
-                         act, alpha, gain, clamp, operand_format, stream, nullptr, nullptr, nullptr, x2, Cin1, residual, x_dtype, y_dtype);
+    pg_conv_args a = base_args(x, wpack, styles, dcoefs, noise, noise_batch_stride, bias, y, N, Cin, Cout, H, W, ksize, up, in_act, in_alpha, in_gain,
+                               act, alpha, gain, clamp, operand_format, stream);
+    a.x2 = x2; a.cin1 = Cin1; a.residual = residual; a.x_dtype = x_dtype; a.y_dtype = y_dtype;
+    return conv_run_impl(a);
 }
 
 extern "C" int pg_conv2d_igemm_spade_run(const float* feat, const void* wpack_gamma_beta, const float* x, const float* mean, const float* rstd,
@@ -1412,8 +1633,10 @@ extern "C" int pg_conv2d_igemm_spade_run(const float* feat, const void* wpack_ga
                                          int32_t act, float alpha, float gain, int32_t operand_format, int32_t feat_dtype, int32_t y_dtype, void* stream) {
     using namespace pg;
     PG_REQUIRE(x && mean && rstd, "conv2d_igemm_spade: x, mean and rstd must be device pointers");
-    return conv_run_impl(feat, wpack_gamma_beta, nullptr, nullptr, nullptr, 0, nullptr, y, N, Cin, 2 * C, H, W, ksize, 1, PG_ACT_LINEAR, 0.f, 1.f,
-                         act, alpha, gain, -1.f, operand_format, stream, x, mean, rstd, nullptr, 0, nullptr, feat_dtype, y_dtype);
+    pg_conv_args a = base_args(feat, wpack_gamma_beta, nullptr, nullptr, nullptr, 0, nullptr, y, N, Cin, 2 * C, H, W, ksize, 1, PG_ACT_LINEAR, 0.f, 1.f,
+                               act, alpha, gain, -1.f, operand_format, stream);
+    a.spade_x = x; a.spade_mean = mean; a.spade_rstd = rstd; a.x_dtype = feat_dtype; a.y_dtype = y_dtype;
+    return conv_run_impl(a);
 }
 
 extern "C" int pg_conv2d_igemm_fwd(const float* x, const float* w, const float* fir, const float* styles, const float* dcoefs,

@@ -77,7 +77,44 @@ __global__ void __launch_bounds__(kSfThreads) masked_fill_kernel(const float* __
     }
 }
 
+// The same fill written as channel-blocked fp16 (C8): one thread per (pixel, 8-channel block), eight coalesced plane reads, one 16-byte store into
+// blocks [cb_offset, cb_offset + C / 8) of out [N][cb_total][hw][8].
+__global__ void __launch_bounds__(kSfThreads) masked_fill_c8_kernel(const float* __restrict__ feat, const float* __restrict__ rest, const float* __restrict__ fill,
+                                                                    uint4* __restrict__ out, int C, long long hw, int cb_total, int cb_offset) {
+    const int CB = C / 8;
+    const long long blk = blockIdx.y;                       // n * CB + cb
+    const int n = (int)(blk / CB), cb = (int)(blk - (long long)n * CB);
+    const float* fp = feat + ((size_t)n * C + (size_t)cb * 8) * hw;
+    const float* rp = rest + (size_t)n * hw;
+    uint4* op = out + ((size_t)n * cb_total + cb_offset + cb) * hw;
+    auto h2 = [](float a, float b) { unsigned int r; asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a)); return r; };
+    float m[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) m[c] = __ldg(fill + (size_t)n * C + cb * 8 + c);
+    for (long long i = (long long)blockIdx.x * kSfThreads + threadIdx.x; i < hw; i += (long long)gridDim.x * kSfThreads) {
+        const float r = __ldg(rp + i);
+        float y[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) y[c] = __ldg(fp + (size_t)c * hw + i) * (1.f - r) + m[c] * r;
+        op[i] = make_uint4(h2(y[0], y[1]), h2(y[2], y[3]), h2(y[4], y[5]), h2(y[6], y[7]));
+    }
+}
+
 }  // namespace pg
+
+extern "C" int pg_masked_fill_c8(const float* feat, const float* rest, const float* fill, void* out, int64_t N, int64_t C, int64_t hw,
+                                 int64_t cb_total, int64_t cb_offset, void* stream) {
+    using namespace pg;
+    PG_REQUIRE(N >= 0 && C >= 8 && C % 8 == 0 && hw >= 1 && cb_offset >= 0 && cb_offset + C / 8 <= cb_total, "masked_fill_c8: bad sizes (C %% 8 == 0)");
+    if (N == 0) return PG_OK;
+    PG_REQUIRE(feat && rest && fill && out && aligned16(out), "masked_fill_c8: feat, rest, fill and out must be device pointers, out 16-byte aligned");
+    PG_REQUIRE(N * (C / 8) <= 65535, "masked_fill_c8: N * C / 8 must fit gridDim.y");
+    long long gx = (hw + kSfThreads * 2 - 1) / (kSfThreads * 2);
+    if (gx < 1) gx = 1;
+    dim3 grid((unsigned)gx, (unsigned)(N * (C / 8)));
+    masked_fill_c8_kernel<<<grid, kSfThreads, 0, (cudaStream_t)stream>>>(feat, rest, fill, (uint4*)out, (int)C, (long long)hw, (int)cb_total, (int)cb_offset);
+    return launch_status("masked_fill_c8", 1);
+}
 
 extern "C" int pg_masked_plane_sum(const float* feat, const float* mask, float* out, int64_t N, int64_t C, int64_t hw, void* stream) {
     using namespace pg;

@@ -63,6 +63,19 @@ class TryOnSession:
         self.h2d_bytes = sum(self.host_in[k].numel() * self.host_in[k].element_size() for k in self.keys)
         self.d2h_bytes = sum(o.numel() * o.element_size() for o in self.host_out)
 
+    def refresh_weights(self):
+        """Call after changing the generator's parameters (load_state_dict, EMA update): every buffer derived from them -- packed tcgen05 weight tiles,
+        gamma|beta concatenations, per-parameter squared sums, the StyleBank matrices -- is rebuilt IN PLACE on the session stream, so the captured
+        graphs (which hold those addresses) replay with the new weights.  No re-capture."""
+        from . import networks
+        from .torch_utils.ops import conv_igemm
+        self.synchronize()
+        with torch.cuda.stream(self.stream), torch.no_grad():
+            networks.refresh_weight_caches(self.G)
+            n = conv_igemm.refresh_packed_weights(self.device)
+        self.stream.synchronize()
+        return n
+
     def _forward(self):
         out = self.G(**self.static_in, noise_mode='const')
         return out if isinstance(out, (tuple, list)) else (out,)

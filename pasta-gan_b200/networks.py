@@ -38,6 +38,7 @@ The default operator table is the CUDA product (``cuda_ops()``); tests and the C
 table with ``use_ops(module, table)``.  The product never imports the oracle.
 """
 import types
+import weakref
 
 import os
 
@@ -61,7 +62,7 @@ def cuda_ops():
             name='sm100a',
             setup_filter=U.setup_filter, upfirdn2d=U.upfirdn2d, filter2d=U.filter2d, upsample2d=U.upsample2d,
             downsample2d=U.downsample2d, bias_act=B.bias_act, conv2d_resample=C.conv2d_resample, fma=F.fma,
-            modulated_conv2d=modulated_conv2d, conv_layer=conv_layer, modconv_layer=modconv_layer, torgb_skip=_torgb_skip, spade_conv_norm=_spade_conv_norm, masked_mean_fill=_masked_mean_fill, half_intermediates=_half_intermediates,
+            modulated_conv2d=modulated_conv2d, conv_layer=conv_layer, modconv_layer=modconv_layer, torgb_skip=_torgb_skip, spade_conv_norm=_spade_conv_norm, masked_mean_fill=_masked_mean_fill, half_intermediates=_half_intermediates, c8_ok=_c8_ok,
             instance_stats=lambda x: K.instance_stats(x) if (K.enabled and x.is_cuda and x.dtype == torch.float32) else None,
             act_def_gain={k: float(v.def_gain) for k, v in B.activation_funcs.items()},
         )
@@ -163,29 +164,57 @@ def _weight_sq_sums(weight):
     """sum_k W[o,i,k]^2  ([O, I]); cached per Parameter version (it only changes when the optimizer steps)."""
     if not isinstance(weight, nn.Parameter) or torch.is_grad_enabled():
         return weight.square().sum(dim=[2, 3])
-    key = (id(weight), weight._version, weight.data_ptr())
+    key = id(weight)
     hit = _WSQ_CACHE.get(key)
-    if hit is None or hit[0] is not weight:
-        if len(_WSQ_CACHE) > 256:
-            _WSQ_CACHE.clear()
-        hit = (weight, weight.detach().square().sum(dim=[2, 3]))
+    if hit is not None and hit['w']() is not weight:
+        _WSQ_CACHE.pop(key, None)
+        hit = None
+    ver = (weight._version, weight.data_ptr())
+    if hit is None:
+        hit = dict(w=weakref.ref(weight, lambda _r, key=key: _WSQ_CACHE.pop(key, None)), ver=ver, sq=weight.detach().square().sum(dim=[2, 3]))
         _WSQ_CACHE[key] = hit
-    return hit[1]
+    elif hit['ver'] != ver:
+        hit['sq'].copy_(weight.detach().square().sum(dim=[2, 3]))      # in place: one buffer per parameter, valid for captured graphs
+        hit['ver'] = ver
+    return hit['sq']
+
+
+def refresh_weight_caches(module=None):
+    """After load_state_dict / an optimizer step under a captured session: bring every derived buffer (per-parameter squared sums, StyleBanks)
+    up to date in place.  The packed GEMM tiles are handled by conv_igemm.refresh_packed_weights()."""
+    for hit in list(_WSQ_CACHE.values()):
+        w = hit['w']()
+        if w is not None and hit['ver'] != (w._version, w.data_ptr()):
+            hit['sq'].copy_(w.detach().square().sum(dim=[2, 3]))
+            hit['ver'] = (w._version, w.data_ptr())
+    if module is not None:
+        for m in module.modules():
+            bank = getattr(m, '_bank', None)
+            if bank is not None:
+                with torch.no_grad():
+                    bank.refresh()
 
 
 def conv_layer(x, w, b=None, f=None, up=1, down=1, padding=0, flip_weight=True, act='linear', act_gain=1.0, clamp=None,
-               in_act=None, in_gain=1.0, w_scale=1.0, cache_weights=False, x2=None, residual=None, out_dtype=None, half_ok=False):
+               in_act=None, in_gain=1.0, w_scale=1.0, cache_weights=False, x2=None, residual=None, out_dtype=None, half_ok=False, out_c8=False):
     """Product form of one plain conv layer: [in_act([x ; x2]) * in_gain ->] conv2d_resample -> bias_act [-> + residual].  When the tcgen05
     kernel covers the shape the whole layer is ONE launch (bias, activation, gain, clamp and the residual add live in the GEMM epilogue; the
     SPADE pre-activation and the channel concatenation live in the operand prologue); otherwise it is composed from the same operators
     the reference calls."""
     from .torch_utils.ops import conv_igemm as K, conv2d_resample as C, bias_act as B
     pad4 = (padding,) * 4 if isinstance(padding, int) else None
+    if K.is_c8(x):
+        # channel-blocked fp16 from one of our own epilogues: TMA operand path.  The producer only emits this layout for consumers it has checked
+        # (K.c8_input_ok), so there is nothing to fall back to here.
+        assert in_act is None and x2 is None and act in ('linear', 'relu', 'lrelu') and padding == int(w.shape[2]) // 2 and down == 1
+        return K.conv2d_igemm(x, w, f=f, up=up, flip_weight=flip_weight, bias=b, act=act, gain=act_gain, clamp=clamp, w_scale=w_scale,
+                              cache_weights=cache_weights, residual=residual, out_dtype=out_dtype or torch.float32, out_c8=out_c8)
     if act in ('linear', 'relu', 'lrelu') and in_act in (None, 'relu', 'lrelu') and \
             K.supported(x, w, up=up, down=down, f=f, padding=pad4, x2=x2, residual=residual, allow_half=half_ok):
         return K.conv2d_igemm(x, w, f=f, up=up, down=down, flip_weight=flip_weight, bias=b, in_act=in_act or 'linear', in_gain=in_gain,
                               act=act, gain=act_gain, clamp=clamp, w_scale=w_scale, cache_weights=cache_weights, x2=x2, residual=residual,
-                              out_dtype=out_dtype or torch.float32)
+                              out_dtype=out_dtype or torch.float32, out_c8=out_c8)
+    assert not out_c8, 'a channel-blocked output was requested from a layer the tcgen05 kernel does not cover'
     if half_ok and x.dtype == torch.float16:
         x = x.float()                                     # an fp16 intermediate of ours reached a layer the tcgen05 kernel does not cover
     if x2 is not None:
@@ -202,7 +231,7 @@ def conv_layer(x, w, b=None, f=None, up=1, down=1, padding=0, flip_weight=True, 
 
 
 def modconv_layer(x, weight, styles, noise=None, up=1, padding=0, resample_filter=None, demodulate=True, flip_weight=True,
-                  fused_modconv=True, bias=None, act='linear', act_gain=1.0, clamp=None, dcoefs=None):
+                  fused_modconv=True, bias=None, act='linear', act_gain=1.0, clamp=None, dcoefs=None, styles_normalized=False):
     """Product form of modulated_conv2d + bias_act (SynthesisLayer / ToRGB): one tcgen05 launch with the style folded into the
     activation operand, demodulation / noise / bias / activation / clamp in the epilogue."""
     from .torch_utils.ops import conv_igemm as K, bias_act as B
@@ -214,13 +243,15 @@ def modconv_layer(x, weight, styles, noise=None, up=1, padding=0, resample_filte
         elif dcoefs is None:                              # (a StyleBank hands precomputed coefficients in)
             dcoefs = torch.addmm(_EPS.get(x.device), styles.square(), _weight_sq_sums(weight).t()).rsqrt()
         return K.conv2d_igemm(x, weight, f=resample_filter, up=up, flip_weight=flip_weight, styles=styles, dcoefs=dcoefs, noise=noise,
-                              bias=bias, act=act, gain=act_gain, clamp=clamp, cache_weights=isinstance(weight, nn.Parameter))
+                              bias=bias, act=act, gain=act_gain, clamp=clamp, cache_weights=isinstance(weight, nn.Parameter),
+                              styles_normalized=styles_normalized)
+    assert not styles_normalized, 'normalised styles are only produced for the tcgen05 path'
     x = modulated_conv2d(x=x, weight=weight, styles=styles, noise=noise, up=up, padding=padding, resample_filter=resample_filter,
                          demodulate=demodulate, flip_weight=flip_weight, fused_modconv=fused_modconv)
     return B.bias_act(x, bias, act=act, gain=act_gain, clamp=clamp)
 
 
-def _spade_conv_norm(x, actv, w_gamma, w_beta, w_scale, post_act, stats=None, out_dtype=None):
+def _spade_conv_norm(x, actv, w_gamma, w_beta, w_scale, post_act, stats=None, out_dtype=None, out_c8=False):
     """Product SPADE normalisation: instance-norm + (1 + gamma) * . + beta (+ the consumer's pre-activation) inside the epilogue of the
     merged gamma|beta convolution; None when the shape is not covered."""
     from .torch_utils.ops import conv_igemm as K
@@ -229,7 +260,7 @@ def _spade_conv_norm(x, actv, w_gamma, w_beta, w_scale, post_act, stats=None, ou
     act, gain = post_act if post_act is not None else ('linear', 1.0)
     if act not in ('linear', 'relu', 'lrelu'):
         return None
-    return K.spade_conv_norm(x, actv, w_gamma, w_beta, w_scale=w_scale, act=act, gain=gain, stats=stats, out_dtype=out_dtype or torch.float32)
+    return K.spade_conv_norm(x, actv, w_gamma, w_beta, w_scale=w_scale, act=act, gain=gain, stats=stats, out_dtype=out_dtype or torch.float32, out_c8=out_c8)
 
 
 def _half_intermediates(x):
@@ -238,6 +269,12 @@ def _half_intermediates(x):
     from .torch_utils.ops import conv_igemm as K
     return (K.enabled and K.operand_format == 'fp16' and os.environ.get('PASTA_B200_HALF_INTERMEDIATES', '1') != '0' and x.is_cuda and
             not torch.is_grad_enabled() and x.shape[3] % 2 == 0 and x.shape[3] <= 256)
+
+
+def _c8_ok(channels, h, w, k):
+    """May a tensor [N, channels, h, w] consumed only by a plain k x k tcgen05 convolution travel as channel-blocked fp16 (TMA operand path)?"""
+    from .torch_utils.ops import conv_igemm as K
+    return (not torch.is_grad_enabled()) and os.environ.get('PASTA_B200_HALF_INTERMEDIATES', '1') != '0' and K.c8_input_ok(int(channels), int(h), int(w), int(k))
 
 
 def _masked_mean_fill(feat, valid, rest, out):
@@ -274,8 +311,13 @@ class StyleBank:
         cmax = max(int(l.affine.weight.shape[0]) for l in layers)
         self.demod = [i for i, l in enumerate(layers) if isinstance(l, SynthesisLayer)]
         omax = max([int(layers[i].weight.shape[0]) for i in self.demod] or [1])
-        W = torch.zeros([L, wd, cmax], device=dev); B = torch.zeros([L, 1, cmax], device=dev)
-        Q = torch.zeros([max(len(self.demod), 1), cmax, omax], device=dev)
+        same = self.key is not None and len(self.key) == len(key) and all(a[0] == b[0] for a, b in zip(self.key, key)) and self.W.device == dev
+        if same:
+            # same layers, new parameter values: rebuild IN PLACE (captured CUDA graphs hold the addresses of W / B / Q)
+            W, B, Q = self.W.zero_(), self.B.zero_(), self.Q.zero_()
+        else:
+            W = torch.zeros([L, wd, cmax], device=dev); B = torch.zeros([L, 1, cmax], device=dev)
+            Q = torch.zeros([max(len(self.demod), 1), cmax, omax], device=dev)
         with torch.no_grad():
             for i, l in enumerate(layers):
                 c = int(l.affine.weight.shape[0])
@@ -286,7 +328,15 @@ class StyleBank:
                 w = layers[i].weight
                 Q[j, :w.shape[1], :w.shape[0]] = w.square().sum(dim=[2, 3]).t()
         self.W, self.B, self.Q, self.key = W, B, Q, key
-        self.demod_idx = torch.tensor(self.demod, device=dev, dtype=torch.long)
+        if not same:
+            self.demod_idx = torch.tensor(self.demod, device=dev, dtype=torch.long)
+        self._layers = [weakref.ref(l) for l in layers]
+
+    def refresh(self):
+        """Rebuild the packed affine / demodulation matrices in place if any source parameter changed (TryOnSession.refresh_weights)."""
+        layers = [r() for r in getattr(self, '_layers', [])]
+        if layers and all(l is not None for l in layers):
+            self._pack(layers)
 
     def fill(self, entries):
         """entries: [(layer, w [N, w_dim])] in any order; sets layer._pre = (styles [N, Cin], dcoefs [N, Cout] or None)."""
@@ -294,14 +344,21 @@ class StyleBank:
         self._pack(layers)
         X = torch.stack([w for _, w in entries], dim=0).to(torch.float32)                    # [L, N, w_dim]
         S = torch.baddbmm(self.B, X, self.W)                                                 # [L, N, Cmax]
-        D = None
+        D = Sn = None
         if self.demod:
-            D = torch.baddbmm(_EPS.get(X.device).reshape(1, 1, 1), S.index_select(0, self.demod_idx).square(), self.Q).rsqrt()
+            Sd = S.index_select(0, self.demod_idx)
+            D = torch.baddbmm(_EPS.get(X.device).reshape(1, 1, 1), Sd.square(), self.Q).rsqrt()
+            # fp16 operand range: each sample's styles go to the kernel with unit inf-norm, the factor rides in the demodulation coefficient
+            # (what conv2d_igemm does per call; batched here).  ToRGB layers keep raw styles: their fused kernel is fp32 arithmetic.
+            smax = Sd.abs().amax(dim=2, keepdim=True).clamp_min(1e-20)
+            Sn, D = Sd / smax, D * smax
         pos = {i: j for j, i in enumerate(self.demod)}
         for i, l in enumerate(layers):
             c = int(l.affine.weight.shape[0])
-            d = D[pos[i], :, :int(l.weight.shape[0])] if i in pos else None
-            l._pre = (S[i, :, :c], d)
+            if i in pos:
+                l._pre = (Sn[pos[i], :, :c], D[pos[i], :, :int(l.weight.shape[0])], True)
+            else:
+                l._pre = (S[i, :, :c], None, False)
 
     @staticmethod
     def clear(entries):
@@ -489,7 +546,7 @@ class SynthesisLayer(OpsModule):
         assert noise_mode in ['random', 'const', 'none']
         misc.assert_shape(x, [None, self.weight.shape[1], self.resolution // self.up, self.resolution // self.up])
         pre = getattr(self, '_pre', None)
-        styles, dcoefs = pre if pre is not None else (self.affine(w), None)
+        styles, dcoefs, normalized = pre if pre is not None else (self.affine(w), None, False)
         noise = None
         if self.use_noise and noise_mode == 'random':
             noise = torch.randn([x.shape[0], 1, self.resolution, self.resolution], device=x.device) * self.noise_strength
@@ -500,7 +557,7 @@ class SynthesisLayer(OpsModule):
         if layer is not None:
             return layer(x, self.weight, styles, noise=noise, up=self.up, padding=self.padding, resample_filter=self.resample_filter,
                          flip_weight=(self.up == 1), fused_modconv=fused_modconv, bias=self.bias.to(x.dtype), act=self.activation,
-                         act_gain=self.act_gain * gain, clamp=clamp, dcoefs=dcoefs)
+                         act_gain=self.act_gain * gain, clamp=clamp, dcoefs=dcoefs, styles_normalized=normalized)
         x = self.ops.modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=noise, up=self.up, padding=self.padding,
                                       resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv)
         return self.ops.bias_act(x, self.bias.to(x.dtype), act=self.activation, gain=self.act_gain * gain, clamp=clamp)
@@ -631,29 +688,45 @@ class SpadeNormBlock(OpsModule):
         self.conv_beta = SpadeConv2dLayer(norm_channels, norm_channels, kernel_size=3, bias=False)
         self.param_free_norm = nn.InstanceNorm2d(norm_channels, affine=False)
 
-    def forward(self, x, denorm_feats, post_act=None, stats=None, out_half=False):
+    def forward(self, x, denorm_feats, post_act=None, stats=None, out_half=False, out_k=None):
         """``post_act = (name, gain)``: apply the pre-activation of the Spade conv that consumes the result here (then call it with
         ``no_act=True``).  ``stats``: (mean, rstd) of ``x`` when the caller already has them (two norm blocks of a SPADE res-block
         normalise the same tensor); only used on the fused path.  ``out_half``: the caller feeds the result straight into a bare Spade
-        conv, so it may be an fp16 tensor when the operator table keeps fp16 intermediates."""
+        conv, so it may be an fp16 tensor when the operator table keeps fp16 intermediates; ``out_k``: that conv's kernel size -- when the table's
+        ``c8_ok`` agrees, the result (and ``actv`` in between) travel channel-blocked and are loaded by TMA."""
         fused = getattr(self.ops, 'spade_conv_norm', None)
         if fused is not None:
             half = getattr(self.ops, 'half_intermediates', None)
             half = torch.float16 if (half is not None and half(x)) else None
+            c8_ok = getattr(self.ops, 'c8_ok', None)
+            h, w = int(x.shape[2]), int(x.shape[3])
+            actv_c8 = c8_ok is not None and c8_ok(self.conv_gamma.weight.shape[1], h, w, self.conv_gamma.weight.shape[2])
+            out_c8 = bool(c8_ok is not None and post_act is not None and out_half and out_k is not None and c8_ok(x.shape[1], h, w, out_k))
             actv = self.ops.conv_layer(denorm_feats, self.conv_mlp.weight, None, padding=1, act='relu', act_gain=1.0,
-                                       w_scale=float(self.conv_mlp.weight_gain), cache_weights=True, out_dtype=half, half_ok=True)   # consumed by the next launch only
+                                       w_scale=float(self.conv_mlp.weight_gain), cache_weights=True, out_dtype=half, half_ok=True, out_c8=actv_c8)   # consumed by the next launch only
             y = fused(x, actv, self.conv_gamma.weight, self.conv_beta.weight, float(self.conv_gamma.weight_gain), post_act, stats,
-                      half if (post_act is not None and out_half) else None)
+                      half if (post_act is not None and out_half) else None, out_c8)
             if y is not None:
                 return y
-            actv = actv.float()
-        actv = self.conv_mlp_act(self.conv_mlp(denorm_feats.to(x.dtype), no_act=True))
+            actv = self._to_nchw(actv).float()
+            denorm_feats = self._to_nchw(denorm_feats)
+        actv = self.conv_mlp_act(self.conv_mlp(self._to_nchw(denorm_feats).to(x.dtype), no_act=True))
         gamma = self.conv_gamma(actv, no_act=True)
         beta = self.conv_beta(actv, no_act=True)
         y = self.param_free_norm(x) * (1 + gamma) + beta
         if post_act is not None:
             y = self.ops.bias_act(y, None, act=post_act[0], gain=post_act[1])
         return y
+
+
+def _spade_to_nchw(t):
+    if t.ndim == 5:
+        from .torch_utils.ops import conv_igemm as K
+        return K.from_c8(t, dtype=torch.float16)
+    return t
+
+
+SpadeNormBlock._to_nchw = staticmethod(_spade_to_nchw)
 
 
 class SpadeResBlockV2(OpsModule):
@@ -677,9 +750,9 @@ class SpadeResBlockV2(OpsModule):
         pre = lambda conv, gain: (conv.activation, float(conv.act_gain * gain))
         stats_fn = getattr(self.ops, 'instance_stats', None)
         stats = stats_fn(x) if stats_fn is not None and not (torch.is_grad_enabled() and x.requires_grad) else None   # shared by spade_skip / spade0
-        y = self.skip(self.spade_skip(x, denorm_feat, post_act=pre(self.skip, np.sqrt(0.5)), stats=stats, out_half=True), no_act=True)
-        x = self.conv0(self.spade0(x, denorm_feat, post_act=pre(self.conv0, 1), stats=stats, out_half=True), no_act=True)
-        return self.conv1(self.spade1(x, denorm_feat, post_act=pre(self.conv1, np.sqrt(0.5)), out_half=True), no_act=True, residual=y)
+        y = self.skip(self.spade_skip(x, denorm_feat, post_act=pre(self.skip, np.sqrt(0.5)), stats=stats, out_half=True, out_k=1), no_act=True)
+        x = self.conv0(self.spade0(x, denorm_feat, post_act=pre(self.conv0, 1), stats=stats, out_half=True, out_k=3), no_act=True)
+        return self.conv1(self.spade1(x, denorm_feat, post_act=pre(self.conv1, np.sqrt(0.5)), out_half=True, out_k=3), no_act=True, residual=y)
 
 
 class SynthesisBlockFull(OpsModule):
@@ -786,6 +859,8 @@ class SynthesisNetworkFull(OpsModule):
             y = fused(feat, valid, rest, out)
             if y is not None:
                 return y
+        assert not isinstance(out, tuple), 'channel-blocked garment features need the fused fill'
+
         feat_sum = (feat * valid).sum(dim=(2, 3), keepdim=True)
         count = valid.sum(dim=(2, 3), keepdim=True)
         enough = (count > 10).to(mask_256.dtype)
@@ -796,7 +871,10 @@ class SynthesisNetworkFull(OpsModule):
             return out
         return y
 
-    def forward(self, ws, pose_feat, cat_feat, denorm_upper_input, denorm_lower_input, denorm_upper_mask, denorm_lower_mask, **block_kwargs):
+    def forward(self, ws, pose_feat, cat_feat, denorm_upper_input, denorm_lower_input, denorm_upper_mask, denorm_lower_mask, label_override=None,
+                **block_kwargs):
+        """``label_override`` ([N, H, W] integer class map): use these labels instead of argmax(pred_parsing) for the garment masks of the fine stage
+        (a test hook: the fine image is a discontinuous function of the logits, reference :5823-5826, so parity tests pin the labels)."""
         misc.assert_shape(ws, [None, self.num_ws, self.w_dim])
         ws = ws.to(torch.float32)
         block_ws, idx = [], 0
@@ -813,11 +891,12 @@ class SynthesisNetworkFull(OpsModule):
             self._bank.fill(entries)
         try:
             return self._forward_blocks(block_ws, pose_feat, cat_feat, denorm_upper_input, denorm_lower_input, denorm_upper_mask, denorm_lower_mask,
-                                        **block_kwargs)
+                                        label_override=label_override, **block_kwargs)
         finally:
             StyleBank.clear(entries)
 
-    def _forward_blocks(self, block_ws, pose_feat, cat_feat, denorm_upper_input, denorm_lower_input, denorm_upper_mask, denorm_lower_mask, **block_kwargs):
+    def _forward_blocks(self, block_ws, pose_feat, cat_feat, denorm_upper_input, denorm_lower_input, denorm_upper_mask, denorm_lower_mask,
+                        label_override=None, **block_kwargs):
         x = img = parsing = None
         for res, cur in zip(self.block_resolutions, block_ws):
             x, img, parsing = getattr(self, f'b{res}')(x, img, cur, pose_feat, cat_feat, force_fp32=True, **block_kwargs)
@@ -826,12 +905,22 @@ class SynthesisNetworkFull(OpsModule):
                 # so inference keeps the aliases and saves a 134 MB copy
                 x_128, img_128 = (x, img) if not torch.is_grad_enabled() else (x.clone(), img.clone())
         label = torch.argmax(torch.softmax(parsing.detach(), dim=1), dim=1)[:, None].float()
+        if label_override is not None:
+            label = label_override.to(parsing.device)[:, None].float()
         cf = self.spade_encoder[-1].conv1.weight.shape[0]                 # channels of one garment's feature map (128)
         half = getattr(self.ops, 'half_intermediates', None)
         feat_dtype = torch.float16 if (half is not None and label.is_cuda and half(label[:, :, ::2, ::2])) else torch.float32   # read by conv_mlp only
-        spade_feat = torch.empty([label.shape[0], 2 * cf, label.shape[2] // 2, label.shape[3] // 2], dtype=feat_dtype, device=label.device)
-        self.get_spade_feat((label == 1).float(), denorm_upper_mask, denorm_upper_input, out=spade_feat[:, :cf])      # upper | lower (:5831)
-        self.get_spade_feat((label == 2).float(), denorm_lower_mask, denorm_lower_input, out=spade_feat[:, cf:])
+        fh, fw = label.shape[2] // 2, label.shape[3] // 2
+        c8_ok = getattr(self.ops, 'c8_ok', None)
+        if c8_ok is not None and label.is_cuda and feat_dtype == torch.float16 and cf % 8 == 0 and c8_ok(2 * cf, fh, fw, 3):
+            # channel-blocked fp16: the nine conv_mlp convolutions that read this tensor load it by TMA
+            spade_feat = torch.empty([label.shape[0], 2 * cf // 8, fh, fw, 8], dtype=torch.float16, device=label.device)
+            self.get_spade_feat((label == 1).float(), denorm_upper_mask, denorm_upper_input, out=(spade_feat, 0))
+            self.get_spade_feat((label == 2).float(), denorm_lower_mask, denorm_lower_input, out=(spade_feat, cf // 8))
+        else:
+            spade_feat = torch.empty([label.shape[0], 2 * cf, fh, fw], dtype=feat_dtype, device=label.device)
+            self.get_spade_feat((label == 1).float(), denorm_upper_mask, denorm_upper_input, out=spade_feat[:, :cf])      # upper | lower (:5831)
+            self.get_spade_feat((label == 2).float(), denorm_lower_mask, denorm_lower_input, out=spade_feat[:, cf:])
         x = x_128
         for k in (1, 2, 3):
             x = getattr(self, f'spade_b128_{k}')(x, spade_feat)

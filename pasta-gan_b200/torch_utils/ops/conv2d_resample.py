@@ -27,7 +27,7 @@ def _conv2d_wrapper(x, w, stride=1, padding=0, groups=1, transpose=False, flip_w
         w = w.flip([2, 3])
     py, px = (padding, padding) if isinstance(padding, int) else tuple(padding)
     if not transpose and stride == 1 and conv_igemm.supported(x, w, groups=groups, padding=(px, px, py, py)):
-        return conv_igemm.conv2d_igemm(x, w, flip_weight=True)       # plain stride-1 'same' conv inside a lowering; w already carries the flip
+        return _igemm(x, w, groups, flip_weight=True)                # plain stride-1 'same' conv inside a lowering; w already carries the flip
     op = conv2d_gradfix.conv_transpose2d if transpose else conv2d_gradfix.conv2d
     sp = _backend.capi().span('library_conv(cudnn)') if x.is_cuda else None
     y = op(x, w, stride=stride, padding=padding, groups=groups)
@@ -39,6 +39,16 @@ def _conv2d_wrapper(x, w, stride=1, padding=0, groups=1, transpose=False, flip_w
         sp.nbytes = (x.numel() + y.numel() + w.numel()) * x.element_size()
         sp.close()
     return y
+
+
+def _igemm(x, w, groups, **kw):
+    """tcgen05 kernel call; ``groups = N`` is the reference's fused modulated convolution (x [1, N*I, H, W], w [N*O, I, k, k],
+    training/networks.py:88-90): the same GEMM with one weight set per sample, x viewed as [N, I, H, W]."""
+    if groups == 1:
+        return conv_igemm.conv2d_igemm(x, w, **kw)
+    cout, cin_g, kh, kwid = (int(v) for v in w.shape)
+    y = conv_igemm.conv2d_igemm(x.reshape(groups, cin_g, *x.shape[2:]), w.reshape(groups, cout // groups, cin_g, kh, kwid), per_sample_weights=True, **kw)
+    return y.reshape(1, cout, *y.shape[2:])
 
 
 @misc.profiled_function
@@ -68,7 +78,7 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
     # tcgen05 implicit-GEMM path (inference, dense fp32 NCHW): plain 'same' 1x1 / 3x3 convolutions, and the up-2 3x3 form
     # evaluated polyphase on the low-resolution input (no (2H+1)^2 intermediate, no separate FIR pass).
     if conv_igemm.supported(x, w, up=up, down=down, groups=groups, f=f, padding=_parse_padding(padding), flip_filter=flip_filter):
-        return conv_igemm.conv2d_igemm(x, w, f=f, up=up, down=down, flip_weight=flip_weight)
+        return _igemm(x, w, groups, f=f, up=up, down=down, flip_weight=flip_weight)
 
     pointwise = (kw == 1 and kh == 1)
     fir = dict(f=f, flip_filter=flip_filter)

@@ -1,11 +1,14 @@
-"""tcgen05 / TMEM implicit-GEMM convolution (``pg_conv2d_igemm_fwd``) — the B200 replacement for the cuDNN calls behind
+"""tcgen05 / TMEM implicit-GEMM convolution (``pg_conv2d_igemm_launch``) — the B200 replacement for the cuDNN calls behind
 ``conv2d_gradfix`` plus the modulation / demodulation / noise / bias_act passes the reference runs around them
 (training/networks.py:37-94, :170-179, :296-315, :4342-4354).
 
 Forward only: it is used when no gradient is required (inference); under autograd the callers keep the
-``conv2d_gradfix`` route.  fp32 NCHW in / out, fp16 (default) or bf16 operands, fp32 accumulation in TMEM.
+``conv2d_gradfix`` route.  Activations: fp32 NCHW at the API boundary; between two of our own layers they may travel as fp16 NCHW or as
+channel-blocked fp16 ("C8", a 5-D tensor ``[N, C/8, H, W, 8]``) which the kernel loads by TMA.  fp16 (default) or bf16 operands, fp32
+accumulation in TMEM.
 """
 import os
+import weakref
 
 import torch
 
@@ -18,8 +21,14 @@ enabled = os.environ.get('PASTA_B200_CONV', '1') != '0'
 operand_format = os.environ.get('PASTA_B200_CONV_FMT', 'fp16')
 
 
+def is_c8(x):
+    """Channel-blocked fp16 activation: [N, C/8, H, W, 8]."""
+    return x.ndim == 5 and x.dtype == torch.float16 and x.shape[4] == 8
+
+
 def supported(x, w, up=1, down=1, groups=1, f=None, padding=None, flip_filter=False, x2=None, residual=None, allow_half=False):
-    """Shapes the kernel covers: dense fp32 NCHW on CUDA, 1x1 / 3x3, stride 1, 'same' padding, optional polyphase up-2."""
+    """Shapes the kernel covers: dense fp32 NCHW on CUDA, 1x1 / 3x3, stride 1, 'same' padding, optional polyphase up-2 / fused down-2; with
+    ``groups = N`` the reference's fused modulated convolution x [1, N*I, H, W] * w [N*O, I, k, k] (training/networks.py:88-90)."""
     if not (enabled and x.is_cuda and x.dtype in (torch.float32, torch.float16) and w.dtype == torch.float32 and x.ndim == 4):
         return False
     if x.dtype == torch.float16 and not (allow_half and half_input_ok(x, w, up, down, x2)):
@@ -27,15 +36,22 @@ def supported(x, w, up=1, down=1, groups=1, f=None, padding=None, flip_filter=Fa
     if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad):
         return False
     k = int(w.shape[2])
-    folded = up == 1 and down == 1 and k in (3, 5, 7) and int(w.shape[1]) * k * k <= 160     # small-Cin layers: taps folded into the GEMM K dimension
-    if groups != 1 or down not in (1, 2) or up not in (1, 2) or w.shape[2] != w.shape[3] or (k not in (1, 3) and not folded):
+    cin_g, cout = int(w.shape[1]), int(w.shape[0])
+    if groups != 1:
+        # per-sample weights: one "sample" per group
+        if not (x.shape[0] == 1 and x.shape[1] == groups * cin_g and cout % groups == 0 and x2 is None and residual is None and down == 1 and
+                groups <= 65535 and x.dtype == torch.float32):
+            return False
+        cout //= groups
+    folded = up == 1 and down == 1 and k in (3, 5, 7) and cin_g * k * k <= 160     # small-Cin layers: taps folded into the GEMM K dimension
+    if down not in (1, 2) or up not in (1, 2) or w.shape[2] != w.shape[3] or (k not in (1, 3) and not folded):
         return False
     if down == 2 and (up != 1 or k != 3 or f is None or f.ndim != 2 or tuple(f.shape) != (4, 4) or flip_filter or
                       x.shape[1] % 16 != 0 or x.shape[2] % 2 or x.shape[3] % 2):
         return False
     if padding is not None and tuple(padding) != (k // 2,) * 4:
         return False
-    if up == 2 and (k != 3 or f is None or f.ndim != 2 or tuple(f.shape) != (4, 4) or flip_filter or w.shape[0] % 16 != 0):
+    if up == 2 and (k != 3 or f is None or f.ndim != 2 or tuple(f.shape) != (4, 4) or flip_filter or cout % 16 != 0):
         return False
     if x.numel() == 0 or x.numel() > 2 ** 31 - 1:
         return False
@@ -57,46 +73,180 @@ def half_input_ok(x, w, up=1, down=1, x2=None):
             x.shape[3] % 2 == 0 and x.shape[3] <= 256 and x.data_ptr() % 4 == 0)
 
 
-_pack_cache = {}          # (id(param), version, ...) -> (param, packed weights): inference packs each parameter once
-_PACK_CACHE_MAX = 512
+def c8_input_ok(c, h, wd, k, up=1, down=1):
+    """A channel-blocked input is loaded by TMA: plain stride-1 (or up-2) 1x1 / 3x3 layer, fp16 operands, whole 16-channel chunks; 3x3 layers wider than
+    127 columns run in 64-column bands (even W), 1x1 layers take at most 128 columns."""
+    return (enabled and operand_format == 'fp16' and down == 1 and up in (1, 2) and k in (1, 3) and c % 16 == 0 and (k == 1 or c * k * k > 160) and
+            (wd <= 128 if k == 1 else (wd <= 127 or wd % 2 == 0)) and
+            os.environ.get('PASTA_B200_CONV_TMA', '1') != '0')
 
 
-def _packed_weights(capi, w, f, w_scale, up, flip_weight, fmt_code, cache):
-    """fp16/bf16 GEMM tiles of ``w * w_scale`` (pg_conv2d_igemm_prepack).  With ``cache=True`` the caller promises that ``w`` is a
-    long-lived tensor (a Parameter / buffer): the packed copy is reused until the tensor's version counter changes."""
-    cout, cin, k, _ = (int(v) for v in w.shape)
-    key = None
-    if cache:
-        key = (id(w), w._version, w.data_ptr(), float(w_scale), up, bool(flip_weight), fmt_code)
-        hit = _pack_cache.get(key)
-        if hit is not None and hit[0] is w:
-            return hit[1]
-    lib = capi.load()
-    ws_bytes = int(lib.pg_conv2d_igemm_workspace_bytes(cin, cout, k, up))
-    if ws_bytes < 0:
-        capi.check(2, 'pg_conv2d_igemm_workspace_bytes')
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=w.device)
+def to_c8(x):
+    """dense NCHW fp32 / fp16 -> channel-blocked fp16 [N, ceil(C/8), H, W, 8] (pg_nchw_to_c8)."""
+    capi = _backend.capi()
+    _backend.require_cuda(x, 'to_c8')
+    x = x.contiguous()
+    n, c, h, wd = (int(v) for v in x.shape)
+    y = torch.empty([n, (c + 7) // 8, h, wd, 8], dtype=torch.float16, device=x.device)
+    with torch.cuda.device(x.device):
+        capi.require_device()
+        sp = capi.span('layout', nbytes=x.element_size() * x.numel() + 2 * y.numel(), tag='nchw->c8')
+        capi.check(capi.load().pg_nchw_to_c8(capi.ptr(x), capi.ptr(y), n, c, h * wd, capi.dtype_code(x.dtype), capi.current_stream(x.device)), 'pg_nchw_to_c8')
+        if sp:
+            sp.close()
+    return y
+
+
+def from_c8(x, channels=None, dtype=torch.float32):
+    """channel-blocked fp16 -> dense NCHW (pg_c8_to_nchw); ``channels``: the logical channel count (default: all stored)."""
+    capi = _backend.capi()
+    assert is_c8(x)
+    x = x.contiguous()
+    n, cb, h, wd, _ = (int(v) for v in x.shape)
+    c = cb * 8 if channels is None else int(channels)
+    assert (c + 7) // 8 == cb
+    y = torch.empty([n, c, h, wd], dtype=dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        capi.require_device()
+        sp = capi.span('layout', nbytes=2 * x.numel() + y.element_size() * y.numel(), tag='c8->nchw')
+        capi.check(capi.load().pg_c8_to_nchw(capi.ptr(x), capi.ptr(y), n, c, h * wd, capi.dtype_code(dtype), capi.current_stream(x.device)), 'pg_c8_to_nchw')
+        if sp:
+            sp.close()
+    return y
+
+
+# ---------------------------------------------------------------------------------------------------------------- packed-weight store
+# One entry per (parameter, packing configuration).  An entry owns ONE workspace buffer for its whole life: when the parameter's version counter
+# moves (optimizer step, EMA update, load_state_dict) the new values are packed INTO THE SAME STORAGE, so
+#   * stale versions never accumulate (the round-1 cache kept every version until a FIFO eviction),
+#   * a CUDA graph that baked the buffer's address keeps reading live weights after `refresh()` (TryOnSession.refresh_weights),
+#   * nothing a captured graph points to is ever freed while the parameter lives: entries die with their parameter (weakref finalizer).
+# The key carries the FIR tensor's identity for the resampling composites, and consumers on another stream wait on the pack's event.
+
+
+class _PackEntry:
+    __slots__ = ('wref', 'version', 'ptr', 'f', 'f_version', 'ws', 'event', 'stream', 'cfg')
+
+
+_pack_store = {}          # (id(w), cfg) -> _PackEntry
+
+
+def _pack_cfg(w_scale, mode, flip_weight, fmt_code):
+    return (float(w_scale), int(mode), bool(flip_weight), int(fmt_code))
+
+
+def _drop_entries(wid):
+    for key in [k for k in _pack_store if k[0] == wid]:
+        _pack_store.pop(key, None)
+
+
+def _run_prepack(capi, w, f, w_scale, mode, flip_weight, fmt_code, ws, batch=1, w_batch_stride=0, styles=None):
+    cout, cin, k = int(w.shape[-4]), int(w.shape[-3]), int(w.shape[-1])
     wc = w.detach().contiguous()
-    rc = lib.pg_conv2d_igemm_prepack(capi.ptr(wc), capi.ptr(f) if up != 1 else None, float(w_scale), cin, cout, k, up,
-                                     int(bool(flip_weight)), fmt_code, capi.ptr(ws), ws_bytes, capi.current_stream(w.device))
+    rc = capi.load().pg_conv2d_igemm_prepack_batched(capi.ptr(wc), int(w_batch_stride), capi.ptr(styles), int(batch),
+                                                     capi.ptr(f) if mode != 1 else None, float(w_scale), cin, cout, k, mode,
+                                                     int(bool(flip_weight)), fmt_code, capi.ptr(ws), int(ws.numel()), capi.current_stream(w.device))
     capi.check(rc, 'pg_conv2d_igemm_prepack')
-    if key is not None:
-        if len(_pack_cache) >= _PACK_CACHE_MAX:
-            _pack_cache.pop(next(iter(_pack_cache)))
-        _pack_cache[key] = (w, ws)
-    return ws
+
+
+def _workspace_bytes(capi, cin, cout, k, mode):
+    n = int(capi.load().pg_conv2d_igemm_workspace_bytes(cin, cout, k, mode))
+    if n < 0:
+        capi.check(2, 'pg_conv2d_igemm_workspace_bytes')
+    return n
+
+
+def _packed_weights(capi, w, f, w_scale, mode, flip_weight, fmt_code, cache):
+    """fp16/bf16 GEMM tiles of ``w * w_scale`` (pg_conv2d_igemm_prepack).  With ``cache=True`` the caller promises that ``w`` is a
+    long-lived tensor (a Parameter / buffer): the packed copy lives in the store above and is refreshed in place when ``w`` changes."""
+    cout, cin, k, _ = (int(v) for v in w.shape)
+    if not cache:
+        ws = torch.empty(_workspace_bytes(capi, cin, cout, k, mode), dtype=torch.uint8, device=w.device)
+        _run_prepack(capi, w, f, w_scale, mode, flip_weight, fmt_code, ws)
+        return ws
+    key = (id(w), _pack_cfg(w_scale, mode, flip_weight, fmt_code))
+    e = _pack_store.get(key)
+    if e is not None and e.wref() is not w:               # id() reuse after the old tensor died without its finalizer having run yet
+        _pack_store.pop(key, None)
+        e = None
+    cur = torch.cuda.current_stream(w.device)
+    fresh = e is None
+    if fresh:
+        e = _PackEntry()
+        wid = id(w)
+        e.wref = weakref.ref(w, lambda _r, wid=wid: _drop_entries(wid))
+        e.ws = torch.empty(_workspace_bytes(capi, cin, cout, k, mode), dtype=torch.uint8, device=w.device)
+        e.cfg = (mode, flip_weight, fmt_code, w_scale)
+        e.version = None
+        _pack_store[key] = e
+    f_ver = None if mode == 1 else (f.data_ptr(), f._version)
+    if fresh or e.version != w._version or e.ptr != w.data_ptr() or (mode != 1 and (e.f is not f or e.f_version != f_ver)):
+        _run_prepack(capi, w, f, w_scale, mode, flip_weight, fmt_code, e.ws)
+        e.version, e.ptr = w._version, w.data_ptr()
+        e.f, e.f_version = (None, None) if mode == 1 else (f, f_ver)
+        e.stream = cur
+        if not torch.cuda.is_current_stream_capturing():
+            e.event = torch.cuda.Event()
+            e.event.record(cur)
+        else:
+            e.event = None
+    elif e.stream != cur and e.event is not None:
+        cur.wait_event(e.event)                           # packed on another stream: order this consumer after the pack
+    return e.ws
+
+
+def refresh_packed_weights(device=None):
+    """Re-pack, in place, every stored parameter whose version moved (after load_state_dict / an optimizer step).  Buffers keep their addresses, so
+    CUDA graphs captured earlier read the new weights on their next replay.  Returns the number of re-packed entries."""
+    capi = _backend.capi()
+    done = 0
+    for (wid, _cfg), e in list(_pack_store.items()):
+        w = e.wref()
+        if w is None or (device is not None and w.device != torch.device(device)):
+            continue
+        if e.version != w._version or e.ptr != w.data_ptr():
+            mode, flip_weight, fmt_code, w_scale = e.cfg
+            with torch.cuda.device(w.device):
+                _run_prepack(capi, w, e.f, w_scale, mode, flip_weight, fmt_code, e.ws)
+            e.version, e.ptr = w._version, w.data_ptr()
+            e.stream = torch.cuda.current_stream(w.device)
+            e.event = torch.cuda.Event()
+            e.event.record(e.stream)
+            done += 1
+    for hit in _cat_cache.values():                       # [gamma ; beta] concatenations: rebuild in place, then their packed copy
+        done += _refresh_cat(hit)
+    return done
+
+
+def packed_weight_buffers():
+    """Every live packed-weight buffer (for owners of captured CUDA graphs that want to hold strong references)."""
+    return [e.ws for e in _pack_store.values()] + [h['cat'] for h in _cat_cache.values()]
 
 
 def conv2d_igemm(x, w, f=None, up=1, down=1, flip_weight=True, styles=None, dcoefs=None, noise=None, bias=None,
                  in_act='linear', in_alpha=0.2, in_gain=1.0, act='linear', alpha=0.2, gain=1.0, clamp=None, fmt=None,
-                 w_scale=1.0, cache_weights=False, x2=None, residual=None, out_dtype=torch.float32):
+                 w_scale=1.0, cache_weights=False, x2=None, residual=None, out_dtype=torch.float32, out_c8=False,
+                 per_sample_weights=False, fold_styles=False, styles_normalized=False):
     """y = clamp(act(dcoefs * conv(styles * in_gain * in_act([x ; x2]), w * w_scale) + noise + bias) * gain) + residual; see include/pasta_b200.h.
-    ``x2``: second part of the input along channels (fused torch.cat); ``residual``: tensor of the output's shape added last."""
+    ``x2``: second part of the input along channels (fused torch.cat); ``residual``: tensor of the output's shape added last.
+    ``x`` may be channel-blocked fp16 (``is_c8``): TMA operand path; ``out_c8``: write the result channel-blocked.
+    ``per_sample_weights``: ``w`` is [N, O, I, k, k] — the groups = N form of the reference's fused modulated conv.
+    ``fold_styles``: multiply the styles into per-sample packed weights instead of the activations (needed when x is channel-blocked)."""
     capi = _backend.capi()
     _backend.require_cuda(x, 'conv2d_igemm')
-    n, cin1, h, wd = (int(v) for v in x.shape)
+    x_c8 = is_c8(x)
+    if x_c8:
+        n, cb_in, h, wd, _ = (int(v) for v in x.shape)
+        cin1 = cb_in * 8
+        assert x2 is None
+    else:
+        n, cin1, h, wd = (int(v) for v in x.shape)
     cin = cin1 + (int(x2.shape[1]) if x2 is not None else 0)
-    cout, cin_w, k, _ = (int(v) for v in w.shape)
+    if per_sample_weights:
+        assert w.ndim == 5 and int(w.shape[0]) == n and not cache_weights and styles is None
+        cout, cin_w, k = int(w.shape[1]), int(w.shape[2]), int(w.shape[4])
+    else:
+        cout, cin_w, k, _ = (int(v) for v in w.shape)
     assert cin_w == cin, 'weight / input channel mismatch'
     x = x.contiguous()
     if x2 is not None:
@@ -106,9 +256,16 @@ def conv2d_igemm(x, w, f=None, up=1, down=1, flip_weight=True, styles=None, dcoe
     mode = -2 if down == 2 else up                       # PG_CONV_DOWN2 / 2 / 1
     oh, ow = (h // 2, wd // 2) if down == 2 else (h * up, wd * up)
     assert out_dtype in (torch.float32, torch.float16) and x.dtype in (torch.float32, torch.float16)
-    if x.dtype == torch.float16:
+    if x_c8:
+        assert in_act == 'linear' and in_gain == 1.0 and (styles is None or fold_styles) and c8_input_ok(cin, h, wd, k, up, down), \
+            'channel-blocked input: plain (or style-folded) stride-1 / up-2 layer only'
+    elif x.dtype == torch.float16:
         assert styles is None and in_act == 'linear' and in_gain == 1.0 and half_input_ok(x, w, up, down, x2), 'float16 input: plain stride-1 layer only'
-    y = torch.empty([n, cout, oh, ow], dtype=out_dtype, device=x.device)
+    if out_c8:
+        assert cout % 16 == 0 and up == 1 and residual is None
+        y = torch.empty([n, cout // 8, oh, ow, 8], dtype=torch.float16, device=x.device)
+    else:
+        y = torch.empty([n, cout, oh, ow], dtype=out_dtype, device=x.device)
     nb_stride = 0
     if noise is not None:
         noise = noise.to(torch.float32).contiguous()
@@ -122,6 +279,12 @@ def conv2d_igemm(x, w, f=None, up=1, down=1, flip_weight=True, styles=None, dcoe
     styles, dcoefs, bias = opt(styles), opt(dcoefs), opt(bias)
     if styles is not None:
         assert tuple(styles.shape) == (n, cin)
+        if not styles_normalized:
+            # fp16 operands: keep x * s inside the fp16 range whatever the style magnitude (the reference pre-normalises its own fp16 path the same
+            # way, training/networks.py:57-59): scale each sample's styles to unit inf-norm and hand the factor to the epilogue's per-sample coefficient
+            smax = styles.abs().amax(dim=1, keepdim=True).clamp_min(1e-20)
+            styles = styles / smax
+            dcoefs = smax.expand(n, cout).contiguous() if dcoefs is None else dcoefs * smax
     if dcoefs is not None:
         assert tuple(dcoefs.shape) == (n, cout)
     if bias is not None:
@@ -134,36 +297,80 @@ def conv2d_igemm(x, w, f=None, up=1, down=1, flip_weight=True, styles=None, dcoe
     fmt_code = _FMT[fmt or operand_format]
     with torch.cuda.device(x.device):
         capi.require_device()
-        wpack = _packed_weights(capi, w, f, w_scale, mode, flip_weight, fmt_code, cache_weights)
+        sample_stride = 0
+        if per_sample_weights or (fold_styles and styles is not None):
+            # one packed weight set per sample, built per call (the weights are a function of this batch's styles)
+            per = _workspace_bytes(capi, cin, cout, k, mode)
+            wpack = torch.empty(per * n, dtype=torch.uint8, device=x.device)
+            if per_sample_weights:
+                _run_prepack(capi, w, f, w_scale, mode, flip_weight, fmt_code, wpack, batch=n, w_batch_stride=cout * cin * k * k)
+            else:
+                _run_prepack(capi, w, f, w_scale, mode, flip_weight, fmt_code, wpack, batch=n, w_batch_stride=0, styles=styles)
+                styles = None
+            sample_stride = per
+        else:
+            wpack = _packed_weights(capi, w, f, w_scale, mode, flip_weight, fmt_code, cache_weights)
         # algorithmic FLOPs (SURVEY.md §8d): output pixels for stride-1 / down-2, INPUT pixels for up-2 (zero-inserted taps excluded)
         sp = capi.span('conv_igemm', flops=2 * n * cout * cin * k * k * (oh * ow if up == 1 else h * wd),
                        nbytes=x.element_size() * x.numel() + 4 * ((x2.numel() if x2 is not None else 0) + (y.numel() if residual is not None else 0) + w.numel()) + y.element_size() * y.numel(),
-                       tag=f'{cin}->{cout} @{h}x{wd} k{k} mode{mode}' + (' mod' if styles is not None else '') + (' cat' if x2 is not None else '') + (' res' if residual is not None else '') + (f' in_{in_act}' if in_act != 'linear' else ''))
-        rc = capi.load().pg_conv2d_igemm_run2(capi.ptr(x), capi.ptr(x2), cin1, capi.ptr(wpack), capi.ptr(styles), capi.ptr(dcoefs),
-                                              capi.ptr(noise), nb_stride, capi.ptr(bias), capi.ptr(residual), capi.ptr(y),
-                                              n, cin, cout, h, wd, k, mode,
-                                              _ACT[in_act], float(in_alpha), float(in_gain),
-                                              _ACT[act], float(alpha), float(gain), float(-1 if clamp is None else clamp),
-                                              fmt_code, capi.dtype_code(x.dtype), capi.dtype_code(out_dtype), capi.current_stream(x.device))
-        capi.check(rc, 'pg_conv2d_igemm_run2')
+                       tag=f'{cin}->{cout} @{h}x{wd} k{k} mode{mode}' + (' mod' if styles is not None else '') + (' cat' if x2 is not None else '') + (' res' if residual is not None else '') +
+                           (f' in_{in_act}' if in_act != 'linear' else '') + (' tma' if x_c8 else '') + (' psw' if sample_stride else '') + (' oc8' if out_c8 else ''))
+        a = capi.ConvArgs()
+        a.struct_bytes = _ARGS_BYTES
+        a.N, a.Cin, a.Cout, a.H, a.W, a.ksize, a.up = n, cin, cout, h, wd, k, mode
+        a.x, a.x_dtype, a.x_layout = capi.ptr(x), capi.dtype_code(x.dtype), capi.LAYOUT_C8 if x_c8 else capi.LAYOUT_NCHW
+        a.x2, a.cin1 = capi.ptr(x2), cin1
+        a.wpack, a.wpack_sample_stride = capi.ptr(wpack), sample_stride
+        a.styles, a.dcoefs, a.noise, a.noise_batch_stride, a.bias, a.residual = capi.ptr(styles), capi.ptr(dcoefs), capi.ptr(noise), nb_stride, capi.ptr(bias), capi.ptr(residual)
+        a.y, a.y_dtype, a.y_layout = capi.ptr(y), capi.dtype_code(y.dtype), capi.LAYOUT_C8 if out_c8 else capi.LAYOUT_NCHW
+        a.in_act, a.in_alpha, a.in_gain = _ACT[in_act], float(in_alpha), float(in_gain)
+        a.act, a.alpha, a.gain, a.clamp = _ACT[act], float(alpha), float(gain), float(-1 if clamp is None else clamp)
+        a.operand_format = fmt_code
+        a.stream = capi.current_stream(x.device)
+        rc = capi.load().pg_conv2d_igemm_launch(_byref(a))
+        capi.check(rc, 'pg_conv2d_igemm_launch')
         if sp:
             sp.close()
     return y
 
 
-_cat_cache = {}
+import ctypes as _ctypes  # noqa: E402
+
+_byref = _ctypes.byref
+_ARGS_BYTES = _ctypes.sizeof(_backend.capi().ConvArgs)
+
+_cat_cache = {}           # (id(w_gamma), id(w_beta)) -> dict(refs, versions, cat)
+
+
+def _refresh_cat(hit):
+    wg, wb = hit['g'](), hit['b']()
+    if wg is None or wb is None:
+        return 0
+    ver = (wg._version, wb._version, wg.data_ptr(), wb.data_ptr())
+    if ver == hit['ver']:
+        return 0
+    with torch.no_grad():
+        c = int(wg.shape[0])
+        hit['cat'][:c].copy_(wg.detach())
+        hit['cat'][c:].copy_(wb.detach())                # in place: the tensor (and its packed copy's storage) keep their addresses
+    hit['ver'] = ver
+    return 1
 
 
 def _gamma_beta_weights(w_gamma, w_beta):
-    """[w_gamma ; w_beta] as one long-lived tensor (so the packed-weight cache can key on it), rebuilt when either parameter changes."""
-    key = (id(w_gamma), id(w_beta), w_gamma._version, w_beta._version, w_gamma.data_ptr(), w_beta.data_ptr())
+    """[w_gamma ; w_beta] as one long-lived tensor (so the packed-weight store can key on it), rebuilt IN PLACE when either parameter changes."""
+    key = (id(w_gamma), id(w_beta))
     hit = _cat_cache.get(key)
-    if hit is None or hit[0] is not w_gamma or hit[1] is not w_beta:
-        if len(_cat_cache) > 64:
-            _cat_cache.clear()
-        hit = (w_gamma, w_beta, torch.cat([w_gamma.detach(), w_beta.detach()], dim=0).contiguous())
+    if hit is not None and (hit['g']() is not w_gamma or hit['b']() is not w_beta):
+        _cat_cache.pop(key, None)
+        hit = None
+    if hit is None:
+        drop = lambda _r, key=key: _cat_cache.pop(key, None)
+        hit = dict(g=weakref.ref(w_gamma, drop), b=weakref.ref(w_beta, drop), ver=None,
+                   cat=torch.empty([2 * int(w_gamma.shape[0])] + list(w_gamma.shape[1:]), dtype=torch.float32, device=w_gamma.device))
         _cat_cache[key] = hit
-    return hit[2]
+    _refresh_cat(hit)
+    return hit['cat']
 
 
 def spade_supported(x, feat, w_gamma, w_beta):
@@ -173,10 +380,17 @@ def spade_supported(x, feat, w_gamma, w_beta):
         return False
     c = int(x.shape[1])
     k = int(w_gamma.shape[2])
-    if feat.dtype == torch.float16 and not half_input_ok(feat, w_gamma):
-        return False
+    if is_c8(feat):
+        if not (c8_input_ok(int(feat.shape[1]) * 8, int(feat.shape[2]), int(feat.shape[3]), k) and tuple(feat.shape[2:4]) == tuple(x.shape[2:]) and
+                int(feat.shape[1]) * 8 == int(w_gamma.shape[1])):
+            return False
+    else:
+        if feat.ndim != 4 or (feat.dtype == torch.float16 and not half_input_ok(feat, w_gamma)):
+            return False
+        if not (feat.shape[2:] == x.shape[2:] and feat.shape[1] == w_gamma.shape[1]):
+            return False
     return (w_gamma.shape == w_beta.shape and w_gamma.shape[0] == c and 2 * c <= 256 and c % 16 == 0 and k in (1, 3) and
-            w_gamma.shape[2] == w_gamma.shape[3] and feat.shape[2:] == x.shape[2:] and feat.shape[1] == w_gamma.shape[1] and x.numel() > 0)
+            w_gamma.shape[2] == w_gamma.shape[3] and x.numel() > 0)
 
 
 def instance_stats(x, eps=1e-5):
@@ -197,26 +411,39 @@ def instance_stats(x, eps=1e-5):
     return mean, rstd
 
 
-def spade_conv_norm(x, feat, w_gamma, w_beta, w_scale=1.0, act='linear', alpha=0.2, gain=1.0, eps=1e-5, fmt=None, stats=None, out_dtype=torch.float32):
-    """act(instance_norm(x) * (1 + conv(feat, w_gamma)) + conv(feat, w_beta)) * gain  in one tcgen05 launch (gamma / beta stay in TMEM)."""
+def spade_conv_norm(x, feat, w_gamma, w_beta, w_scale=1.0, act='linear', alpha=0.2, gain=1.0, eps=1e-5, fmt=None, stats=None, out_dtype=torch.float32,
+                    out_c8=False):
+    """act(instance_norm(x) * (1 + conv(feat, w_gamma)) + conv(feat, w_beta)) * gain  in one tcgen05 launch (gamma / beta stay in TMEM).
+    ``feat`` may be channel-blocked fp16 (TMA operand path); ``out_c8``: channel-blocked fp16 result."""
     capi = _backend.capi()
     n, c, h, wd = (int(v) for v in x.shape)
-    cin, k = int(feat.shape[1]), int(w_gamma.shape[2])
+    f_c8 = is_c8(feat)
+    cin, k = (int(feat.shape[1]) * 8 if f_c8 else int(feat.shape[1])), int(w_gamma.shape[2])
     x = x.contiguous()
     feat = feat.contiguous()
     mean, rstd = stats if stats is not None else instance_stats(x, eps)      # `stats`: reuse when several norm blocks share x
     wcat = _gamma_beta_weights(w_gamma, w_beta)
     fmt_code = _FMT[fmt or operand_format]
-    y = torch.empty_like(x, dtype=out_dtype)
+    y = torch.empty([n, c // 8, h, wd, 8], dtype=torch.float16, device=x.device) if out_c8 else torch.empty_like(x, dtype=out_dtype)
     with torch.cuda.device(x.device):
         capi.require_device()
         wpack = _packed_weights(capi, wcat, None, w_scale, 1, True, fmt_code, True)
         sp = capi.span('conv_igemm', flops=2 * n * 2 * c * cin * k * k * h * wd, nbytes=4 * (x.numel() + wcat.numel()) + feat.element_size() * feat.numel() + y.element_size() * y.numel(),
-                       tag=f'{cin}->{2 * c} @{h}x{wd} k{k} spade' + (' in16' if feat.dtype == torch.float16 else '') + (' out16' if out_dtype == torch.float16 else ''))
-        rc = capi.load().pg_conv2d_igemm_spade_run(capi.ptr(feat), capi.ptr(wpack), capi.ptr(x), capi.ptr(mean), capi.ptr(rstd), capi.ptr(y),
-                                                   n, cin, c, h, wd, k, _ACT[act], float(alpha), float(gain), fmt_code,
-                                                   capi.dtype_code(feat.dtype), capi.dtype_code(out_dtype), capi.current_stream(x.device))
-        capi.check(rc, 'pg_conv2d_igemm_spade_run')
+                       tag=f'{cin}->{2 * c} @{h}x{wd} k{k} spade' + (' tma' if f_c8 else (' in16' if feat.dtype == torch.float16 else '')) +
+                           (' oc8' if out_c8 else (' out16' if out_dtype == torch.float16 else '')))
+        a = capi.ConvArgs()
+        a.struct_bytes = _ARGS_BYTES
+        a.N, a.Cin, a.Cout, a.H, a.W, a.ksize, a.up = n, cin, 2 * c, h, wd, k, 1
+        a.x, a.x_dtype, a.x_layout = capi.ptr(feat), capi.dtype_code(feat.dtype), capi.LAYOUT_C8 if f_c8 else capi.LAYOUT_NCHW
+        a.wpack = capi.ptr(wpack)
+        a.y, a.y_dtype, a.y_layout = capi.ptr(y), capi.dtype_code(y.dtype), capi.LAYOUT_C8 if out_c8 else capi.LAYOUT_NCHW
+        a.in_act, a.in_alpha, a.in_gain = _ACT['linear'], 0.0, 1.0
+        a.act, a.alpha, a.gain, a.clamp = _ACT[act], float(alpha), float(gain), -1.0
+        a.operand_format = fmt_code
+        a.spade_x, a.spade_mean, a.spade_rstd = capi.ptr(x), capi.ptr(mean), capi.ptr(rstd)
+        a.stream = capi.current_stream(x.device)
+        rc = capi.load().pg_conv2d_igemm_launch(_byref(a))
+        capi.check(rc, 'pg_conv2d_igemm_launch(spade)')
         if sp:
             sp.close()
     return y

@@ -7,6 +7,11 @@ from . import _backend
 
 
 def supported(feat, valid, rest, out):
+    if isinstance(out, tuple):                            # (channel-blocked fp16 tensor [N, CB, H, W, 8], first channel block)
+        buf, cb0 = out
+        return (feat.is_cuda and feat.dtype == torch.float32 and feat.ndim == 4 and valid.dtype == torch.float32 and rest.dtype == torch.float32 and
+                buf.dtype == torch.float16 and buf.ndim == 5 and buf.is_contiguous() and feat.shape[1] % 8 == 0 and
+                not (torch.is_grad_enabled() and feat.requires_grad) and feat.shape[0] * feat.shape[1] // 8 <= 65535)
     return (feat.is_cuda and feat.dtype == torch.float32 and feat.ndim == 4 and valid.dtype == torch.float32 and rest.dtype == torch.float32 and
             out.dtype in (torch.float32, torch.float16) and not (torch.is_grad_enabled() and feat.requires_grad) and feat.shape[0] * feat.shape[1] <= 65535)
 
@@ -20,7 +25,12 @@ def masked_mean_fill(feat, valid, rest, out, min_count=10):
     feat = feat.contiguous()
     valid = valid.reshape(n, h * w).contiguous()
     rest = rest.reshape(n, h * w).contiguous()
-    assert tuple(out.shape) == (n, c, h, w) and out.stride(3) == 1 and out.stride(2) == w and out.stride(1) == h * w
+    c8 = isinstance(out, tuple)
+    if c8:
+        buf, cb0 = out
+        assert tuple(buf.shape[2:]) == (h, w, 8) and int(buf.shape[0]) == n and cb0 + c // 8 <= int(buf.shape[1])
+    else:
+        assert tuple(out.shape) == (n, c, h, w) and out.stride(3) == 1 and out.stride(2) == w and out.stride(1) == h * w
     sums = torch.empty([n, c], dtype=torch.float32, device=feat.device)
     lib = capi.load()
     with torch.cuda.device(feat.device):
@@ -34,6 +44,13 @@ def masked_mean_fill(feat, valid, rest, out, min_count=10):
         enough = (count > min_count).to(feat.dtype)
         count = count * enough + (h * w) * (1 - enough)
         fill = (sums / count).contiguous()
+        if c8:
+            sp = capi.span('spade_feat', nbytes=(4 + 2) * feat.numel(), tag='masked fill c8')
+            capi.check(lib.pg_masked_fill_c8(capi.ptr(feat), capi.ptr(rest), capi.ptr(fill), capi.ptr(buf), n, c, h * w, int(buf.shape[1]), int(cb0), stream),
+                       'pg_masked_fill_c8')
+            if sp:
+                sp.close()
+            return buf
         sp = capi.span('spade_feat', nbytes=(4 + out.element_size()) * feat.numel(), tag='masked fill')
         capi.check(lib.pg_masked_fill(capi.ptr(feat), capi.ptr(rest), capi.ptr(fill), capi.ptr(out), n, c, h * w, int(out.stride(0)), capi.dtype_code(out.dtype), stream),
                    'pg_masked_fill')

@@ -97,13 +97,9 @@ class TryOnTrainer:
 
 
 def synth_training_batch(batch, seed=1234, device='cpu'):
-    """Generator inputs (tests/golden/procedural.synth_inputs layout) + a real image and a 6-class parsing map."""
-    import sys, os
-    here = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
-    if here not in sys.path:
-        sys.path.insert(0, here)
-    import procedural
-    b = procedural.synth_inputs(batch, seed=seed, device=device)
+    """Generator inputs (synthetic.synth_inputs layout) + a real image and a 6-class parsing map."""
+    from . import synthetic
+    b = synthetic.synth_inputs(batch, seed=seed, device=device)
     g = torch.Generator().manual_seed(seed + 99)
     b['real_img'] = (torch.randint(0, 256, (batch, 3, 256, 256), generator=g).float() / 127.5 - 1).to(device)
     b['gt_parsing'] = torch.randint(0, 6, (batch, 1, 256, 256), generator=g).float().to(device)

@@ -309,6 +309,41 @@ def gen_generator():
     save('generator_full', arrays, [meta])
 
 
+def gen_generator_n16():
+    """GeneratorFull at the BASELINE config AND the BASELINE batch (N = 16, configs[1]): tile counts, strip lengths and band choices of the CUDA
+    kernels depend on N * H * W, so parity is pinned at the measured batch as well.  To keep the fixture small the three outputs are stored
+    float16 and spatially subsampled (images stride 2, parsing logits stride 4); the reference's argmax label map is stored in full (uint8) so
+    that a test can feed BOTH sides the same labels and hold the fine-tuned image to a max-abs bound (networks.py:5823-5826 makes it a
+    discontinuous function of the logits)."""
+    G = R_net.GeneratorFull(z_dim=0, c_dim=512, w_dim=512, img_resolution=256, img_channels=3,
+                            mapping_kwargs=dict(num_layers=1),
+                            synthesis_kwargs=dict(channel_base=16384, channel_max=512, num_fp16_res=3, conv_clamp=256, use_noise=True)).eval()
+    procedural.fill_(G)
+    inp = procedural.synth_inputs(16, seed=2468)
+    with torch.no_grad():
+        img, fimg, parsing = G(**inp, noise_mode='const')
+    label = torch.argmax(torch.softmax(parsing, dim=1), dim=1).to(torch.uint8)
+    arrays = {'img': img[:, :, ::2, ::2].half(), 'finetune_img': fimg[:, :, ::2, ::2].half(), 'pred_parsing': parsing[:, :, ::4, ::4].half(),
+              'label': label}
+    meta = dict(seed=2468, batch=16, stats=dict(img_absmax=float(img.abs().max()), fimg_absmax=float(fimg.abs().max()),
+                                                parsing_absmax=float(parsing.abs().max())))
+    save('generator_full_n16', arrays, [meta])
+
+
+def gen_generator_labels():
+    """The reference's argmax label map for the N = 2 case of generator_full.npz (same weights, same inputs), so the fine-tuned image of that
+    fixture can be compared with the labels pinned (see gen_generator_n16)."""
+    G = R_net.GeneratorFull(z_dim=0, c_dim=512, w_dim=512, img_resolution=256, img_channels=3,
+                            mapping_kwargs=dict(num_layers=1),
+                            synthesis_kwargs=dict(channel_base=16384, channel_max=512, num_fp16_res=3, conv_clamp=256, use_noise=True)).eval()
+    procedural.fill_(G)
+    inp = procedural.synth_inputs(2)
+    with torch.no_grad():
+        img, fimg, parsing = G(**inp, noise_mode='const')
+    label = torch.argmax(torch.softmax(parsing, dim=1), dim=1).to(torch.uint8)
+    save('generator_full_labels', {'label': label, 'finetune_img': fimg.half()}, [dict(batch=2)])
+
+
 def gen_generator_512():
     """Generator_512 (the only 512-px network in the tree) at channel_base 16384, N = 1, eval, const noise; fp16-stored output."""
     G = R_net.Generator_512(z_dim=0, c_dim=512, w_dim=512, img_resolution=512, img_channels=3, mapping_kwargs=dict(num_layers=1),
@@ -350,6 +385,7 @@ def gen_discriminator():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['upfirdn2d', 'bias_act', 'conv2d_resample', 'modulated_conv2d', 'layers', 'generator', 'discriminator', 'generator_512']
+    which = sys.argv[1:] or ['upfirdn2d', 'bias_act', 'conv2d_resample', 'modulated_conv2d', 'layers', 'generator', 'discriminator', 'generator_512',
+                             'generator_labels', 'generator_n16']
     for w in which:
         globals()['gen_' + w]()

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f'{n} declared in include/pasta_b200.h but not exported'
         assert n in capi.SIGNATURES, f'{n} has no ctypes signature in _capi.py'
     assert sorted(capi.SIGNATURES) == names
-    assert capi.load().pg_abi_version() == 1
+    assert capi.load().pg_abi_version() == 2
 
 
 def test_argument_errors_are_reported_not_crashed():

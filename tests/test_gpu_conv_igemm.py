@@ -20,6 +20,11 @@ def cv():
     return conv_igemm
 
 
+import pasta_gan_b200  # noqa: E402
+
+capi = pasta_gan_b200.capi
+
+
 PLAIN = [
     # (N, Cin, Cout, H, W, k)
     (1, 16, 16, 8, 8, 3), (2, 32, 16, 16, 16, 3), (1, 64, 64, 32, 32, 3), (2, 128, 128, 32, 32, 3),
@@ -256,7 +261,7 @@ def test_half_intermediates_are_bit_identical(cv, shape):
 
 
 def test_persistent_variant_matches(cv, monkeypatch):
-    """The opt-in persistent kernel (one CTA per SM, double-buffered TMEM, dedicated epilogue warps; PASTA_B200_CONV_PERSIST=1) computes the same
+    """The opt-in persistent kernel (one CTA per SM, double-buffered TMEM, dedicated epilogue warps; pg_set_tuning('conv_persist', 1)) computes the same
     tiles with the same accumulation order as the default one-tile kernel: identical bits."""
     torch.manual_seed(11)
     for (n, cin, cout, h, w, k, mod) in [(16, 128, 128, 64, 64, 3, False), (16, 64, 64, 128, 128, 3, True), (16, 96, 64, 64, 96, 1, False)]:
@@ -266,11 +271,11 @@ def test_persistent_variant_matches(cv, monkeypatch):
         st = (1 + 0.3 * torch.randn(n, cin, device=DEV)) if mod else None
         dc = (torch.rand(n, cout, device=DEV) + 0.5) if mod else None
         res = torch.randn(n, cout, h, w, device=DEV)
-        monkeypatch.setenv('PASTA_B200_CONV_PERSIST', '0')
+        capi.set_tuning('conv_persist', 0)
         y0 = cv.conv2d_igemm(x, wt, styles=st, dcoefs=dc, bias=b, act='lrelu', gain=1.2, clamp=3.0, residual=res)
-        monkeypatch.setenv('PASTA_B200_CONV_PERSIST', '1')
+        capi.set_tuning('conv_persist', 1)
         y1 = cv.conv2d_igemm(x, wt, styles=st, dcoefs=dc, bias=b, act='lrelu', gain=1.2, clamp=3.0, residual=res)
-        monkeypatch.setenv('PASTA_B200_CONV_PERSIST', '0')
+        capi.set_tuning('conv_persist', 0)
         assert torch.equal(y0, y1), (n, cin, cout, h, w, k, mod)
 
 
@@ -281,7 +286,7 @@ BANDS = [(1, 64, 64, 256, 256), (1, 32, 48, 40, 320), (2, 16, 16, 24, 258), (1, 
 def test_column_band_mode(cv, shape, monkeypatch):
     """W >= 256: the image is processed in 64-column bands with real halo columns (strip pitch 68) instead of one full-width strip.  Same GEMM,
     different tiling: parity against the oracle with styles / demodulation / noise / bias / lrelu / clamp / residual, and bit-equality with
-    the full-width tiling (PASTA_B200_CONV_BANDS=0) -- every output is the same sum of the same fp16 products in the same chunk order."""
+    the full-width tiling (pg_set_tuning('conv_bands', 0)) -- every output is the same sum of the same fp16 products in the same chunk order."""
     n, cin, cout, h, w = shape
     torch.manual_seed(sum(shape))
     x = torch.randn(n, cin, h, w)
@@ -295,9 +300,9 @@ def test_column_band_mode(cv, shape, monkeypatch):
     args = dict(styles=s.to(DEV), dcoefs=d.to(DEV), noise=noise.to(DEV), bias=b.to(DEV), act='lrelu', gain=1.2, clamp=1.5, residual=res.to(DEV))
     y = cv.conv2d_igemm(x.to(DEV), wt.to(DEV), **args)
     assert rel_err(y, ref) < 3e-3
-    monkeypatch.setenv('PASTA_B200_CONV_BANDS', '0')
+    capi.set_tuning('conv_bands', 0)
     y0 = cv.conv2d_igemm(x.to(DEV), wt.to(DEV), **args)
-    monkeypatch.delenv('PASTA_B200_CONV_BANDS')
+    capi.set_tuning('conv_bands', 1)
     assert torch.equal(y, y0)
     # plain layer, fp16 input and output
     wp = (wt / (cin * 9) ** 0.5).to(DEV)
@@ -324,9 +329,9 @@ def test_column_band_mode_resampling(cv, shape, monkeypatch):
         run = lambda: cv.conv2d_igemm(x.to(DEV), wt.to(DEV), f=f.to(DEV), up=2, flip_weight=False, bias=b.to(DEV), act='lrelu', gain=2 ** 0.5)
     y = run()
     assert y.shape == ref.shape and rel_err(y, ref) < 3e-3
-    monkeypatch.setenv('PASTA_B200_CONV_BANDS', '0')
+    capi.set_tuning('conv_bands', 0)
     y0 = run()
-    monkeypatch.delenv('PASTA_B200_CONV_BANDS')
+    capi.set_tuning('conv_bands', 1)
     assert torch.equal(y, y0)
 
 
@@ -344,9 +349,9 @@ def test_band_mode_with_split_input_spade_and_modulated_down2(cv, monkeypatch):
     xs = torch.randn(2, 128, 24, 128, device=DEV); feat = torch.randn(2, 64, 24, 128, device=DEV)
     wg = torch.randn(128, 64, 3, 3, device=DEV) / 24; wb = torch.randn(128, 64, 3, 3, device=DEV) / 24
     r1 = cv.spade_conv_norm(xs, feat, wg, wb, act='relu', gain=1.1)
-    monkeypatch.setenv('PASTA_B200_CONV_BANDS', '0')
+    capi.set_tuning('conv_bands', 0)
     r0 = cv.spade_conv_norm(xs, feat, wg, wb, act='relu', gain=1.1)
-    monkeypatch.delenv('PASTA_B200_CONV_BANDS')
+    capi.set_tuning('conv_bands', 1)
     assert torch.equal(r0, r1)
     # modulated down-2 (styles in the lean down-2 loader's prologue)
     f = O.setup_filter([1, 3, 3, 1])
@@ -355,3 +360,175 @@ def test_band_mode_with_split_input_spade_and_modulated_down2(cv, monkeypatch):
     dco = (st.square() @ wd.square().sum(dim=[2, 3]).t() + 1e-8).rsqrt()
     yd = cv.conv2d_igemm(xd.to(DEV), wd.to(DEV), f=f.to(DEV), down=2, styles=st.to(DEV), dcoefs=dco.to(DEV))
     assert yd.shape == refd.shape and rel_err(yd, refd) < 3e-3
+
+
+# ------------------------------------------------------------------------------------------------ groups = N (the reference's fused modulated conv)
+
+def test_groups_n_matches_modulated_goldens(golden):
+    """The fused cases of tests/golden/modulated_conv2d.npz through the reference's own arithmetic (networks.py:64-94): per-sample weights
+    w * s * d built with torch, then conv2d_resample(x [1, N*I, H, W], w [N*O, I, k, k], groups = N) -- which must land on the tcgen05 kernel
+    (no library convolution) for every case the kernel covers, including the up-2 form."""
+    from pasta_gan_b200.torch_utils.ops import conv2d_resample as C
+    g = golden('modulated_conv2d')
+    f4 = g.t('f4', device=DEV)
+    ran = 0
+    for idx, c in enumerate(g.meta):
+        if not c['fused']:
+            continue
+        x, w, s = g.t(f'{idx}/x', device=DEV), g.t(f'{idx}/w', device=DEV), g.t(f'{idx}/s', device=DEV)
+        n, o, i, k = c['n'], c['o'], c['i'], c['k']
+        wn = w.unsqueeze(0) * s.reshape(n, 1, -1, 1, 1)
+        if c['demod']:
+            wn = wn * (wn.square().sum(dim=[2, 3, 4]) + 1e-8).rsqrt().reshape(n, -1, 1, 1, 1)
+        l0 = capi.launch_count()
+        with torch.no_grad():
+            y = C.conv2d_resample(x=x.reshape(1, -1, *x.shape[2:]), w=wn.reshape(-1, i, k, k), f=f4, up=c['up'], padding=k // 2, groups=n,
+                                  flip_weight=c['flip_weight'])
+        y = y.reshape(n, -1, *y.shape[2:])
+        if g.has(f'{idx}/noise'):
+            y = y + g.t(f'{idx}/noise', device=DEV)
+        assert rel_err(y, g.t(f'{idx}/y')) < 3e-3, c
+        if c['up'] == 1 or o % 16 == 0:
+            assert capi.launch_count() - l0 == 2, 'expected exactly: batched weight pack + one tcgen05 launch'
+            ran += 1
+    assert ran >= 2
+
+
+@pytest.mark.parametrize('shape', [(16, 64, 64, 32, 32, 3, 1), (4, 128, 64, 16, 16, 3, 2), (3, 32, 3, 24, 24, 1, 1), (2, 512, 512, 8, 8, 3, 1), (5, 48, 32, 20, 36, 3, 2)])
+def test_groups_n_vs_oracle(cv, shape):
+    """groups = N at generator-like shapes against the oracle's grouped conv2d_resample (fp64), stride 1 and up-2."""
+    from pasta_gan_b200.torch_utils.ops import conv2d_resample as C
+    n, cin, cout, h, w, k, up = shape
+    torch.manual_seed(sum(shape))
+    f = O.setup_filter([1, 3, 3, 1])
+    x = torch.randn(1, n * cin, h, w)
+    wt = torch.randn(n * cout, cin, k, k) / (cin * k * k) ** 0.5
+    ref = O.conv2d_resample(x.double(), wt.double(), f.double(), up=up, padding=k // 2, groups=n, flip_weight=(up == 1))
+    with torch.no_grad():
+        y = C.conv2d_resample(x.to(DEV), wt.to(DEV), f.to(DEV), up=up, padding=k // 2, groups=n, flip_weight=(up == 1))
+    assert y.shape == ref.shape and rel_err(y, ref) < TOL['fp16']
+
+
+# ------------------------------------------------------------------------------------------------ channel-blocked fp16 (TMA operand path)
+
+def test_c8_layout_round_trip(cv):
+    torch.manual_seed(5)
+    for shape in [(2, 16, 8, 8), (1, 20, 5, 7), (3, 64, 33, 31)]:
+        x = torch.randn(*shape, device=DEV)
+        y = cv.to_c8(x)
+        assert y.shape == (shape[0], (shape[1] + 7) // 8, shape[2], shape[3], 8)
+        ref = torch.zeros(shape[0], y.shape[1] * 8, shape[2], shape[3], device=DEV, dtype=torch.float16)
+        ref[:, :shape[1]] = x.half()
+        assert torch.equal(y, ref.reshape(shape[0], -1, 8, shape[2], shape[3]).permute(0, 1, 3, 4, 2))
+        assert torch.equal(cv.from_c8(y, shape[1], dtype=torch.float16), x.half())
+        assert torch.equal(cv.to_c8(x.half()), y)
+
+
+C8 = [
+    # (N, Cin, Cout, H, W, k): full-width strips (W <= 127), 64-column bands (W >= 128), 1x1, ragged heights / band counts
+    (2, 32, 32, 16, 16, 3), (1, 64, 48, 33, 31, 3), (2, 128, 128, 64, 64, 3), (1, 256, 128, 24, 128, 3), (2, 64, 64, 40, 256, 3),
+    (1, 32, 16, 9, 130, 3), (2, 128, 128, 32, 128, 1), (1, 64, 32, 50, 50, 1), (1, 16, 16, 4, 4, 3), (3, 48, 272, 20, 20, 3), (1, 32, 32, 130, 126, 3),
+]
+
+
+@pytest.mark.parametrize('shape', C8, ids=[str(s) for s in C8])
+def test_c8_tma_path_bit_identical(cv, shape):
+    """A channel-blocked fp16 input is the same operand bits the fp16-NCHW loader stages, multiplied in the same chunk order: results must be
+    bit-identical to the converter path; a channel-blocked output holds the same fp16 values as the fp16-NCHW output."""
+    n, cin, cout, h, w, k = shape
+    torch.manual_seed(sum(shape))
+    xh = torch.randn(n, cin, h, w, device=DEV).half()
+    wt = torch.randn(cout, cin, k, k, device=DEV) / (cin * k * k) ** 0.5
+    b = torch.randn(cout, device=DEV) * 0.2
+    ref = cv.conv2d_igemm(xh.float(), wt, bias=b, act='lrelu', gain=1.3, clamp=2.0)
+    assert rel_err(ref, O.bias_act(O._conv(xh.double().cpu(), wt.double().cpu(), padding=k // 2), b.double().cpu(), act='lrelu', gain=1.3, clamp=2.0)) < TOL['fp16']
+    xc = cv.to_c8(xh)
+    y = cv.conv2d_igemm(xc, wt, bias=b, act='lrelu', gain=1.3, clamp=2.0)
+    assert torch.equal(y, ref)
+    res = torch.randn_like(ref)
+    assert torch.equal(cv.conv2d_igemm(xc, wt, bias=b, residual=res), cv.conv2d_igemm(xh.float(), wt, bias=b, residual=res))
+    if cout % 16 == 0:
+        yc = cv.conv2d_igemm(xc, wt, bias=b, act='lrelu', gain=1.3, clamp=2.0, out_c8=True)
+        assert torch.equal(cv.from_c8(yc, cout, dtype=torch.float16), ref.half())
+        y2 = cv.conv2d_igemm(xh.float(), wt, bias=b, act='lrelu', gain=1.3, clamp=2.0, out_c8=True)      # converter path in, blocked out
+        assert torch.equal(y2, yc)
+
+
+def test_c8_tma_up2_spade_and_folded_styles(cv):
+    """TMA operand path under the other epilogues: polyphase up-2, the SPADE epilogue (blocked in, blocked out), and a modulated layer whose styles
+    are folded into per-sample packed weights (the activations cannot be scaled on the way in)."""
+    torch.manual_seed(17)
+    f = O.setup_filter([1, 3, 3, 1]).to(DEV)
+    xh = torch.randn(2, 64, 24, 24, device=DEV).half()
+    wt = torch.randn(32, 64, 3, 3, device=DEV) / 24
+    up_ref = cv.conv2d_igemm(xh.float(), wt, f=f, up=2, flip_weight=False, act='lrelu', gain=2 ** 0.5)
+    assert torch.equal(cv.conv2d_igemm(cv.to_c8(xh), wt, f=f, up=2, flip_weight=False, act='lrelu', gain=2 ** 0.5), up_ref)
+    # SPADE
+    xs = torch.randn(2, 64, 24, 128, device=DEV); feat = torch.randn(2, 32, 24, 128, device=DEV).half()
+    wg = torch.randn(64, 32, 3, 3, device=DEV) / 17; wb = torch.randn(64, 32, 3, 3, device=DEV) / 17
+    r = cv.spade_conv_norm(xs, feat, wg, wb, act='relu', gain=1.1, out_dtype=torch.float16)
+    rc = cv.spade_conv_norm(xs, cv.to_c8(feat), wg, wb, act='relu', gain=1.1, out_c8=True)
+    assert torch.equal(cv.from_c8(rc, 64, dtype=torch.float16), r)
+    # styles folded into the weights vs styles on the activations: same math, different fp16 roundings -> oracle tolerance
+    x = torch.randn(3, 64, 40, 40); wm = torch.randn(48, 64, 3, 3); st = 1 + 0.5 * torch.randn(3, 64); nz = torch.randn(40, 40) * 0.3; b = torch.randn(48) * 0.1
+    ref = O.bias_act(O.modulated_conv2d(x.double(), wm.double(), st.double(), noise=nz.double(), padding=1), b.double(), act='lrelu', clamp=256)
+    dco = (st.square() @ wm.square().sum(dim=[2, 3]).t() + 1e-8).rsqrt()
+    y = cv.conv2d_igemm(cv.to_c8(x.to(DEV)), wm.to(DEV), styles=st.to(DEV), dcoefs=dco.to(DEV), noise=nz.to(DEV), bias=b.to(DEV), act='lrelu',
+                        gain=2 ** 0.5, clamp=256, fold_styles=True)
+    assert rel_err(y, ref) < 3e-3
+
+
+# ------------------------------------------------------------------------------------------------ dynamic range / weight store
+
+@pytest.mark.parametrize('fmt', ['fp16', 'bf16'])
+def test_trained_like_dynamic_range(cv, fmt):
+    """Unit-variance inputs never reach the edges of the fp16 range.  Here: activations at the conv_clamp (+-256), styles in the tens to hundreds
+    (x * s would overflow fp16's 65504 un-normalised), weights x 100, plus a block of tiny (1e-6) activations.  The per-sample style
+    normalisation (reference networks.py:57-59, folded into the demodulation coefficient) keeps the operands finite; the result must match the
+    fp64 oracle to the operand format's tolerance with no inf / nan."""
+    torch.manual_seed(23)
+    n, cin, cout, h = 4, 64, 48, 24
+    x = (torch.randn(n, cin, h, h) * 200).clamp(-256, 256)
+    x[:, :8] = torch.randn(n, 8, h, h) * 1e-6
+    wt = torch.randn(cout, cin, 3, 3) * 100
+    st = torch.randn(n, cin) * 150 + 40 * torch.sign(torch.randn(n, cin))
+    dco = (st.double().square() @ wt.double().square().sum(dim=[2, 3]).t() + 1e-8).rsqrt().float()
+    ref = O.bias_act(O.modulated_conv2d(x.double(), wt.double(), st.double(), padding=1), None, act='lrelu', clamp=256)
+    y = cv.conv2d_igemm(x.to(DEV), wt.to(DEV), styles=st.to(DEV), dcoefs=dco.to(DEV), act='lrelu', gain=2 ** 0.5, clamp=256, fmt=fmt)
+    assert torch.isfinite(y).all()
+    assert rel_err(y, ref) < TOL[fmt]
+    # without demodulation (ToRGB form): outputs in the 1e7 range, still finite and accurate
+    ref2 = O.modulated_conv2d(x.double(), wt.double()[:3, :, :1, :1], st.double(), demodulate=False)
+    y2 = cv.conv2d_igemm(x.to(DEV), wt[:3, :, :1, :1].contiguous().to(DEV), styles=st.to(DEV), fmt=fmt)
+    assert torch.isfinite(y2).all() and rel_err(y2, ref2) < TOL[fmt]
+    # plain layer, activations +-1e4 (no clamp in the encoders): inside fp16 range, must not saturate
+    xe = torch.randn(2, 32, 20, 20) * 1e4
+    we = torch.randn(32, 32, 3, 3) / 17
+    assert rel_err(cv.conv2d_igemm(xe.to(DEV), we.to(DEV), fmt=fmt), O._conv(xe.double(), we.double(), padding=1)) < TOL[fmt]
+
+
+def test_packed_weight_store_refreshes_in_place(cv):
+    """The packed copy of a parameter lives in ONE buffer: an in-place parameter update re-packs into the same storage (no stale versions pile up,
+    addresses baked into CUDA graphs stay valid), and entries disappear with their parameter."""
+    torch.manual_seed(29)
+    w = torch.nn.Parameter(torch.randn(32, 32, 3, 3, device=DEV) / 17)
+    x = torch.randn(2, 32, 16, 16, device=DEV)
+    n0 = len(cv._pack_store)
+    with torch.no_grad():
+        y0 = cv.conv2d_igemm(x, w, cache_weights=True)
+        key = [k for k in cv._pack_store if k[0] == id(w)]
+        assert len(key) == 1 and len(cv._pack_store) == n0 + 1
+        ptr = cv._pack_store[key[0]].ws.data_ptr()
+        l0 = capi.launch_count()
+        assert torch.equal(cv.conv2d_igemm(x, w, cache_weights=True), y0) and capi.launch_count() - l0 == 1       # cached: no second pack
+        w.mul_(2.0)
+        y1 = cv.conv2d_igemm(x, w, cache_weights=True)
+        assert len(cv._pack_store) == n0 + 1 and cv._pack_store[key[0]].ws.data_ptr() == ptr
+        assert rel_err(y1, 2 * y0) < 1e-6
+        w.mul_(0.5)
+        assert cv.refresh_packed_weights() >= 1 and cv._pack_store[key[0]].ws.data_ptr() == ptr
+        assert torch.equal(cv.conv2d_igemm(x, w, cache_weights=True), y0)
+    del w
+    import gc
+    gc.collect()
+    assert len(cv._pack_store) == n0
