@@ -1,0 +1,248 @@
+#!/usr/bin/env python
+"""Runs the UNMODIFIED reference tree in this process, in one of several arrangements, and prints ONE JSON line.
+
+The tree is ``baseline/_ref`` — a plain file copy of the reference checkout made by ``__graft_entry__.build()`` in the authoring container
+(git-ignored, so never part of the history; it travels to the GPU box with the gpurun snapshot).  Nothing of it is modified: the harness only
+supplies what the reference expects from its environment: a stub ``matplotlib``, cwd = tree root for ``./human_colormap.mat``,
+and ``torch.version.cuda == '11.0'`` while ``training.networks`` is imported (its lines 1206-1222 otherwise try to JIT a second upfirdn2d op from
+files that do not exist).
+
+    --mode cpu       reference networks + reference ops, CPU tensors => every op takes impl='ref' (upfirdn2d.py:162-164, bias_act.py:87-89).
+                     This is the reference's own CPU implementation of the hot path: bench.py's --impl reference arm and cpu_baseline.
+    --mode gpu       reference networks + reference ops on the GPU: its own CUDA plugins (upfirdn2d.cu / bias_act.cu JIT-built for sm_100 through
+                     torch_utils/custom_ops.py) and cuDNN fp32 convolutions (allow_tf32 = False, training_loop...py:243,253).  The GPU code to beat.
+    --mode overlay   reference networks (unmodified training/networks.py: GeneratorFull :5844) over OUR torch_utils/ops/*.py — the drop-in of
+                     INTEGRATION.md §2, built as an overlay copy in a temp dir.  Eval mode, so modulated convs arrive as groups = N.
+    --mode overlay_hook   the same after a pickle round trip through legacy.load_network_pkl with the persistence.import_hook recipe of
+                     INTEGRATION.md §2 that re-routes the pickled modulated_conv2d to the one-launch kernel.
+    --mode ops       per-op timings of the reference's CUDA plugins and cuDNN fp32 on the op-microbenchmark grid (BASELINE configs[4]).
+
+Parity (``--check``): outputs at batch 2 against tests/golden/generator_full.npz (written from this same reference on CPU).
+"""
+import argparse
+import json
+import os
+import shutil
+import sys
+import tempfile
+import time
+import types
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get('PASTA_REFERENCE_TREE', os.path.join(ROOT, 'baseline', '_ref'))
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--mode', required=True, choices=['cpu', 'gpu', 'overlay', 'overlay_hook', 'ops'])
+    ap.add_argument('--batch', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=1)
+    ap.add_argument('--check', action='store_true', help='also run batch 2 and compare with tests/golden/generator_full.npz')
+    ap.add_argument('--threads', type=int, default=0)
+    return ap.parse_args()
+
+
+def make_overlay_tree():
+    """Copy of the reference tree with our torch_utils/ops/*.py laid over its own (exactly the `cp` of INTEGRATION.md §2)."""
+    tree = os.path.join(tempfile.mkdtemp(prefix='pasta_overlay_'), 'ref')
+    shutil.copytree(REF, tree, ignore=shutil.ignore_patterns('__pycache__', '*.pyc', '.git'))
+    ops_src = os.path.join(ROOT, 'pasta-gan_b200', 'torch_utils', 'ops')
+    for fn in os.listdir(ops_src):
+        if fn.endswith('.py') and fn != '__init__.py':
+            shutil.copy(os.path.join(ops_src, fn), os.path.join(tree, 'torch_utils', 'ops', fn))
+    os.environ['PASTA_B200_HOME'] = os.path.join(ROOT, 'pasta-gan_b200')
+    return tree
+
+
+def import_reference(tree):
+    os.environ.setdefault('PYTHONDONTWRITEBYTECODE', '1')
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, tree)
+    sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
+    for m in ('matplotlib', 'matplotlib.pyplot'):
+        sys.modules.setdefault(m, types.ModuleType(m))
+    sys.modules['matplotlib'].pyplot = sys.modules['matplotlib.pyplot']
+    import torch
+    os.chdir(tree)
+    real = torch.version.cuda
+    torch.version.cuda = '11.0'
+    try:
+        import training.networks as R_net
+        import legacy
+    finally:
+        torch.version.cuda = real
+    return R_net, legacy
+
+
+def build_generator(R_net):
+    return R_net.GeneratorFull(z_dim=0, c_dim=512, w_dim=512, img_resolution=256, img_channels=3, mapping_kwargs=dict(num_layers=1),
+                               synthesis_kwargs=dict(channel_base=16384, channel_max=512, num_fp16_res=3, conv_clamp=256, use_noise=True)).eval().requires_grad_(False)
+
+
+def golden_check(G, device):
+    """batch-2 outputs against the committed fixture: max-abs relative error of the coarse image and parsing logits, relative L2 of all three."""
+    import numpy as np
+    import torch
+    import procedural
+    z = np.load(os.path.join(ROOT, 'tests', 'golden', 'generator_full.npz'))
+    inp = procedural.synth_inputs(2, device=device)
+    with torch.no_grad():
+        img, fimg, parsing = G(**inp, noise_mode='const')
+    out = dict(img=img, finetune_img=fimg, pred_parsing=parsing)
+    res = {}
+    for k, v in out.items():
+        ref = torch.from_numpy(z[k].astype(np.float32)).double()
+        got = v.detach().cpu().double()
+        res[k] = dict(max_rel=float((got - ref).abs().max() / ref.abs().max()), l2_rel=float((got - ref).norm() / ref.norm()))
+    return res
+
+
+def time_generator(G, batch, steps, warmup, device):
+    import torch
+    import procedural
+    inp = procedural.synth_inputs(batch, seed=1234, device=device)
+    cuda = torch.device(device).type == 'cuda'
+    with torch.no_grad():
+        for _ in range(warmup):
+            G(**inp, noise_mode='const')
+        if cuda:
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            G(**inp, noise_mode='const')
+        if cuda:
+            e1.record()
+            torch.cuda.synchronize()
+            dt = e0.elapsed_time(e1) * 1e-3
+        else:
+            dt = time.perf_counter() - t0
+    return dict(img_s=batch * steps / dt, ms_per_step=1e3 * dt / steps, batch=batch, steps=steps, warmup=warmup)
+
+
+def run_ops(out):
+    """Reference CUDA plugins + cuDNN fp32 on the op grid of BASELINE configs[4] (N = 16): microseconds per call, CUDA events, inputs cycled through a
+    pool larger than L2."""
+    import torch
+    from torch_utils.ops import upfirdn2d, bias_act
+    dev = 'cuda'
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    f = upfirdn2d.setup_filter([1, 3, 3, 1], device=dev)
+    rows = []
+
+    def bench(fn, make, nbytes, reps=10):
+        pool = [make() for _ in range(max(2, int(400e6 // max(nbytes, 1)) + 1))][:8]
+        for p in pool[:2]:
+            fn(*p)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            fn(*pool[i % len(pool)])
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e3 / reps
+
+    n = 16
+    for res, c in [(512, 32), (256, 64), (128, 128), (64, 256), (32, 512)]:
+        numel = n * c * res * res
+        with torch.no_grad():
+            us = bench(lambda x, b: bias_act.bias_act(x, b, act='lrelu', clamp=256), lambda: (torch.randn(n, c, res, res, device=dev), torch.randn(c, device=dev)), 8 * numel)
+            rows.append(dict(op='bias_act lrelu+clamp', res=res, c=c, us=us, gbs=8 * numel / us / 1e3))
+            us = bench(lambda x: upfirdn2d.upfirdn2d(x, f, padding=[1, 1, 1, 1], gain=4), lambda: (torch.randn(n, c, res + 1, res + 1, device=dev),), 8 * numel)
+            rows.append(dict(op='upfirdn2d filter pad1 gain4', res=res, c=c, us=us, gbs=4 * (numel + n * c * (res + 1) ** 2) / us / 1e3))
+            us = bench(lambda x: upfirdn2d.upfirdn2d(x, f, down=2, padding=[1, 1, 1, 1]), lambda: (torch.randn(n, c, res, res, device=dev),), 5 * numel)
+            rows.append(dict(op='upfirdn2d down2', res=res, c=c, us=us, gbs=5 * numel / us / 1e3))
+            if res <= 256:
+                us = bench(lambda x: upfirdn2d.upsample2d(x, f), lambda: (torch.randn(n, c, res // 2, res // 2, device=dev),), 5 * numel)
+                rows.append(dict(op='upfirdn2d up2 (upsample2d)', res=res, c=c, us=us, gbs=5 * numel / us / 1e3))
+            us = bench(lambda x: upfirdn2d.upsample2d(x, f), lambda: (torch.randn(n, 3, res // 2, res // 2, device=dev),), 5 * n * 3 * res * res)
+            rows.append(dict(op='upfirdn2d up2 rgb', res=res, c=3, us=us, gbs=5 * n * 3 * res * res / us / 1e3))
+            w = torch.randn(c, c, 3, 3, device=dev) / (c * 9) ** 0.5
+            us = bench(lambda x: torch.nn.functional.conv2d(x, w, padding=1), lambda: (torch.randn(n, c, res, res, device=dev),), 8 * numel, reps=6)
+            rows.append(dict(op='cudnn fp32 conv3x3', res=res, c=c, us=us, tflops=2 * numel * c * 9 / us / 1e6))
+    out['ops'] = rows
+    out['plugins'] = dict(upfirdn2d=upfirdn2d._plugin is not None, bias_act=bias_act._plugin is not None)
+
+
+def main():
+    args = parse()
+    out = dict(mode=args.mode, ref_tree=os.path.relpath(REF, ROOT))
+    if not os.path.isdir(os.path.join(REF, 'torch_utils')):
+        out['unavailable'] = f'{REF} is missing (it is copied from the reference checkout by __graft_entry__.build())'
+        print(json.dumps(out), flush=True)
+        return
+    import torch
+    if args.threads:
+        torch.set_num_threads(args.threads)
+    overlay = args.mode.startswith('overlay')
+    tree = make_overlay_tree() if overlay else REF
+    if args.mode in ('gpu', 'ops'):
+        os.environ.setdefault('TORCH_CUDA_ARCH_LIST', '10.0')
+        os.environ.setdefault('TORCH_EXTENSIONS_DIR', os.path.join(tempfile.gettempdir(), 'pasta_ref_plugins'))
+    R_net, legacy = import_reference(tree)
+    import procedural
+    device = 'cpu' if args.mode == 'cpu' else 'cuda'
+    if device == 'cuda':
+        torch.backends.cudnn.benchmark = True                  # training_loop_wo_flow_fullbody.py:242
+        torch.backends.cudnn.allow_tf32 = False                # :243, :253 — the reference's own GPU convolutions are full fp32
+        torch.backends.cuda.matmul.allow_tf32 = False
+    if args.mode == 'ops':
+        run_ops(out)
+        print(json.dumps(out), flush=True)
+        return
+    if args.mode == 'cpu':
+        try:    # keep freed activation buffers in the heap instead of re-faulting fresh mmap pages on every op (glibc mallopt)
+            import ctypes
+            libc = ctypes.CDLL('libc.so.6')
+            libc.mallopt(-3, 32 * 1024 * 1024)
+            libc.mallopt(-1, 2 ** 31 - 1)
+        except Exception:
+            pass
+        out['cores'] = os.cpu_count() or 1
+        out['threads'] = torch.get_num_threads()
+    G = build_generator(R_net)
+    procedural.fill_(G)
+    if args.mode == 'overlay_hook':
+        # pickle with the reference's persistence, re-load through legacy.load_network_pkl with an import hook that swaps the
+        # pickled module's modulated_conv2d for the one-launch kernel entry point
+        import io
+        import pickle
+        from torch_utils import persistence
+        sys.path.insert(0, ROOT)
+
+        @persistence.import_hook
+        def _use_b200_modconv(meta):
+            if meta.type == 'class' and 'def modulated_conv2d(' in meta.module_src:
+                meta.module_src = meta.module_src.replace('def modulated_conv2d(', 'def _modulated_conv2d_ref(') + \
+                    '\nfrom pasta_gan_b200.networks import modulated_conv2d\n'
+            return meta
+        buf = io.BytesIO()
+        pickle.dump(dict(G_ema=G), buf)
+        buf.seek(0)
+        G = legacy.load_network_pkl(buf)['G_ema'].eval().requires_grad_(False)
+        out['hooked'] = 'pasta_gan_b200' in sys.modules
+    G = G.to(device)
+    if overlay:
+        from torch_utils.ops import upfirdn2d
+        out['overlay_in_effect'] = 'pg_upfirdn2d' in open(upfirdn2d.__file__).read()
+    if args.check:
+        out['golden'] = golden_check(G, device)
+    if device == 'cuda':
+        capi = sys.modules.get('pasta_b200_capi')              # our C-ABI binding, if the overlay loaded it into this process
+        l0 = capi.launch_count() if capi is not None else 0
+    out.update(time_generator(G, args.batch, args.steps, args.warmup, device))
+    if device == 'cuda':
+        out['our_kernel_launches'] = (capi.launch_count() - l0) if capi is not None else 0
+        if args.mode == 'gpu':
+            from torch_utils.ops import upfirdn2d, bias_act
+            out['plugins'] = dict(upfirdn2d=upfirdn2d._plugin is not None, bias_act=bias_act._plugin is not None)
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == '__main__':
+    main()

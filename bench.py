@@ -15,8 +15,13 @@ Prints ONE JSON line on rank 0:
   roofline   dominant hand-written kernel: algorithmic bytes (or flops) per launch / CUDA-event time per launch vs
              MEASURED_PEAKS.json; measured in one instrumented eager step right after the timed region (per-launch events cannot
              be recorded inside a replayed CUDA graph)
-  cpu_baseline   the CPU oracle port of the reference impl='ref' path on this box's host cores, bounded sample (rank 0, N = 1)
-  --impl reference   times that CPU port alone (the reference's own CPU implementation cannot travel to the GPU box).
+  cpu_baseline   the reference's own impl='ref' CPU path on this box's host cores, bounded sample (rank 0, N = 1): the UNMODIFIED reference tree
+             (baseline/_ref, shipped copy) through baseline/run_reference.py when it is present (kind "reference"), else the oracle port (kind "port")
+  --impl reference   times that CPU arm alone
+  extra      dropin: the unmodified reference networks.py over OUR ops on this GPU (INTEGRATION.md section 2), eager, img/s;
+             reference_gpu: the unmodified reference with its OWN CUDA plugins (JIT) + cuDNN fp32 on this GPU — the GPU code to beat;
+             gen512: the same bench line for BASELINE configs[2] (Generator_512, 512x320)
+  gpu_library_baseline   our module tree with every convolution routed to cuDNN fp32 (the reference's library path), eager, same batch
 """
 import argparse
 import json
@@ -46,6 +51,7 @@ def parse():
     ap.add_argument('--workload', default='gen256', choices=['gen256', 'gen512'], help='gen256 = BASELINE configs[1] (default); gen512 = configs[2]')
     ap.add_argument('--no-graph', action='store_true', help='eager launches instead of CUDA-graph replay')
     ap.add_argument('--skip-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip the drop-in / reference-GPU / gen512 / library-baseline legs')
     return ap.parse_args()
 
 
@@ -132,6 +138,43 @@ def barrier(world):
         dist.barrier()
 
 
+# ------------------------------------------------------------------------------------------------ reference tree (baseline/_ref) legs
+
+HARNESS = os.path.join(ROOT, 'baseline', 'run_reference.py')
+HAVE_REF = os.path.isdir(os.path.join(ROOT, 'baseline', '_ref', 'torch_utils'))
+DTYPE = 'f16 tensor-core operands, f32 accumulate (TMEM), f32 I/O at the API boundary'
+
+
+def run_harness(mode, batch, steps, warmup, timeout, check=False, env=None):
+    """One arrangement of the unmodified reference in its own process -> its JSON dict (or {'unavailable': why})."""
+    if not HAVE_REF:
+        return dict(unavailable='baseline/_ref not present')
+    cmd = [sys.executable, HARNESS, '--mode', mode, '--batch', str(batch), '--steps', str(steps), '--warmup', str(warmup)] + (['--check'] if check else [])
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=dict(os.environ, **(env or {})))
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith('{')]
+        if r.returncode != 0 or not lines:
+            return dict(unavailable=f'rc {r.returncode}: {(r.stderr or r.stdout)[-300:]}')
+        return json.loads(lines[-1])
+    except subprocess.TimeoutExpired:
+        return dict(unavailable=f'timed out after {timeout} s')
+    except Exception as e:  # noqa: BLE001
+        return dict(unavailable=repr(e)[:300])
+
+
+def time_cpu_reference(steps, warmup, batch=1):
+    """The reference's own CPU implementation (impl='ref' ops, unmodified networks.py) on the host cores; falls back to the oracle port only where the
+    shipped copy of the reference tree is absent."""
+    if HAVE_REF:
+        r = run_harness('cpu', batch, steps, warmup, timeout=1200)
+        if 'unavailable' not in r:
+            return dict(value=r['img_s'], unit=UNIT, cores=r['cores'], threads=r['threads'], kind='reference',
+                        sample=f'{steps} forward(s) of batch {batch}: UNMODIFIED reference GeneratorFull 256x256 (training/networks.py:5844) with its impl=ref ops '
+                               f'on torch-CPU, {r["threads"]} threads (baseline/_ref via baseline/run_reference.py --mode cpu)',
+                        seconds=steps * r['ms_per_step'] * 1e-3, ms_per_step=r['ms_per_step'])
+    return time_cpu_oracle(steps, warmup, batch)
+
+
 # ------------------------------------------------------------------------------------------------ CPU oracle arm
 
 def cpu_generator():
@@ -172,12 +215,13 @@ def time_cpu_oracle(steps, warmup, batch=1):
 def run_reference(args, world, rank):
     if rank != 0:
         return
-    r = time_cpu_oracle(args.steps, args.warmup, batch=1)
+    r = time_cpu_reference(args.steps, args.warmup, batch=1)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'GeneratorFull 256x192 (256x256 padded) inference, CPU oracle port of impl=ref; each step = 1 image',
+        'config': {'workload': 'GeneratorFull 256x192 (256x256 padded) inference on the host cores: ' +
+                               ('the unmodified reference (impl=ref ops)' if r['kind'] == 'reference' else 'CPU oracle port of impl=ref') + '; each step = 1 image',
                    'batch_per_step': 1, 'l2': 'n/a (CPU)'},
         'cpu_baseline': {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
         'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -307,18 +351,63 @@ def run_b200(args, world, rank, local):
                                  frac_tensor=round(fl / ms / 1e9 / pk['tf_sustained'], 3), frac_hbm=round(nb / ms / 1e6 / pk['hbm'], 3))
                             for t, (n, ms, nb, fl) in sorted(by.items(), key=lambda kv: -kv[1][1])[:8] if ms > 0]
 
+    # library baseline: the same module tree with every convolution on cuDNN fp32 (what the reference's conv2d_gradfix calls; allow_tf32 = False as in
+    # training_loop_wo_flow_fullbody.py:243,253), FIR / bias_act on our kernels; eager, same batch, CUDA events
+    lib_base = None
+    extras = world == 1 and not args.no_extras
+    if extras:
+        from pasta_gan_b200.torch_utils.ops import conv_igemm as K
+        old = (K.enabled, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        K.enabled, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = False, False, False
+        try:
+            with torch.cuda.stream(sess.stream), torch.no_grad():
+                for _ in range(2):
+                    sess.G(**sess.static_in, noise_mode='const')
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3):
+                    sess.G(**sess.static_in, noise_mode='const')
+                e1.record()
+            sess.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            lib_base = dict(value=args.batch / (ms * 1e-3), unit=UNIT, ms_per_step=ms,
+                            what='same module tree, convolutions on cuDNN fp32 (conv_igemm disabled, allow_tf32=False), eager, 3 steps')
+        finally:
+            K.enabled, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
     if rank != 0:
         return
     imgs = world * args.batch * args.steps
     cpu = None
     if world == 1 and not args.skip_cpu_baseline:
-        cpu = time_cpu_oracle(steps=2, warmup=1, batch=1)
+        cpu = time_cpu_reference(steps=4, warmup=1, batch=1)
         cpu = {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+    extra = {}
+    if extras:
+        t_x = time.perf_counter()
+        del sess
+        torch.cuda.empty_cache()
+        # the real drop-in: unmodified reference networks.py over OUR ops on this GPU (eager; every modulated conv arrives as groups = N)
+        d = run_harness('overlay', args.batch, 5, 2, timeout=300)
+        extra['dropin'] = d if 'unavailable' in d else dict(value=d['img_s'], unit=UNIT, ms_per_step=d['ms_per_step'], our_kernel_launches=d['our_kernel_launches'],
+                                                              what='UNMODIFIED reference training/networks.py GeneratorFull over our torch_utils/ops overlay, eager, batch %d' % args.batch)
+        if time.perf_counter() - t_x < 240:
+            d = run_harness('gpu', args.batch, 5, 2, timeout=420)
+            extra['reference_gpu'] = d if 'unavailable' in d else dict(value=d['img_s'], unit=UNIT, ms_per_step=d['ms_per_step'], plugins=d.get('plugins'),
+                                                                         what='UNMODIFIED reference with its own CUDA plugins (JIT, sm_100) + cuDNN fp32, eager, batch %d' % args.batch)
+        if args.workload == 'gen256' and time.perf_counter() - t_x < 480:
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), '--workload', 'gen512', '--steps', str(args.steps), '--warmup', str(args.warmup),
+                                    '--batch', str(args.batch), '--skip-cpu-baseline', '--no-extras'], capture_output=True, text=True, timeout=300, cwd=ROOT)
+                g = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith('{')][-1])
+                extra['gen512'] = {k: g[k] for k in ('metric', 'value', 'unit', 'ms_per_step', 'e2e', 'e2e_u8', 'roofline', 'gpu_launches_per_step', 'config')}
+            except Exception as e:  # noqa: BLE001
+                extra['gen512'] = dict(unavailable=repr(e)[:300])
     act_bytes = sum(v['bytes'] for v in profile.values())
     line = {
         'metric': METRIC if args.workload == 'gen256' else METRIC.replace('256x192 padded to 256x256', '512x320 padded to 512x512'), 'value': imgs / t_dev, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * t_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32', 'data': 'synthetic',
+        'dtype': DTYPE, 'data': 'synthetic',
         'config': {'workload': wl,
                    'batch_per_gpu': args.batch, 'global_batch': world * args.batch, 'parallelism': f'replicas x{world} (batch-sharded, no collective)',
                    'cuda_graph': not args.no_graph, 'e2e_pipeline': 'H2D / compute / D2H on three streams, 2 buffer sets',
@@ -333,6 +422,8 @@ def run_b200(args, world, rank, local):
         'clocks': clk,
         'roofline': roof,
         'cpu_baseline': cpu,
+        'gpu_library_baseline': lib_base,
+        'extra': extra,
         'kernel_breakdown_ms_per_step': {k: round(v['ms'], 3) for k, v in sorted(profile.items(), key=lambda kv: -kv[1]['ms'])},
         'kernel_launches_per_step': {k: v['launches'] for k, v in profile.items()},
     }

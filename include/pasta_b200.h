@@ -171,9 +171,12 @@ int pg_conv2d_igemm_run2(const float* x, const float* x2, int32_t Cin1, const vo
  *   w_batch_stride > 0: set i is read from w + i * w_batch_stride elements — the per-sample weights [N*O, I, k, k] that the reference's FUSED
  *                       modulated convolution hands to conv2d_resample with groups = N (training/networks.py:84-94);
  *   w_batch_stride == 0 with styles [batch, Cin]: set i = w * styles[i, c] — the modulation of networks.py:64-66 applied while packing, for layers
- *                       whose activations are read by TMA and therefore cannot be scaled on the way in. */
+ *                       whose activations are read by TMA and therefore cannot be scaled on the way in.
+ *   n_tile: 0 = the library's default N tile (min(Cout rounded to 16, 256)); otherwise the GEMM's N-tile width (multiple of 16 dividing Cout).  The
+ *           same value must be passed in pg_conv_args.n_tile.  Used by the SPADE layer: with rows ordered [gamma_t ; beta_t] per 64-channel tile t
+ *           and n_tile = 128, two CTAs share an SM and one's epilogue overlaps the other's main loop. */
 int pg_conv2d_igemm_prepack_batched(const float* w, int64_t w_batch_stride, const float* styles, int32_t batch, const float* fir, float w_scale,
-                                    int32_t Cin, int32_t Cout, int32_t ksize, int32_t up, int32_t flip_weight, int32_t operand_format,
+                                    int32_t Cin, int32_t Cout, int32_t ksize, int32_t up, int32_t flip_weight, int32_t operand_format, int32_t n_tile,
                                     void* workspace, int64_t workspace_bytes, void* stream);
 
 /* The general entry point (everything pg_conv2d_igemm_run2 / _spade_run do, plus):
@@ -183,9 +186,10 @@ int pg_conv2d_igemm_prepack_batched(const float* w, int64_t w_batch_stride, cons
  *   x_layout / y_layout = PG_LAYOUT_C8: the tensor is float16 in the channel-blocked layout [N][C/8][H][W][8] (C % 16 == 0).  Such an input is
  *               loaded by the Tensor Memory Accelerator straight into the tensor-core operand layout (a 3-D box of rows x strip positions x 2
  *               channel blocks per 16-channel chunk; halo and padding are the tensor map's out-of-bounds zero fill) — no conversion pass at all.
- *               It must be a plain layer (no styles, input activation, x2 or down-2; fold a modulation into the weights with
- *               pg_conv2d_igemm_prepack_batched).  Such an output is written 16 bytes per (pixel, 8 channels) by the epilogue.
- *   spade_x != NULL: the SPADE epilogue of pg_conv2d_igemm_spade_run (Cout = 2C, wpack = [gamma ; beta]).
+ *               It must be a plain layer (no styles, input activation or down-2; fold a modulation into the weights with
+ *               pg_conv2d_igemm_prepack_batched).  x2 (the fused concat) must then be channel-blocked too, with Cin1 % 16 == 0.  Such an output is written 16 bytes per (pixel, 8 channels) by the epilogue.
+ *   spade_x != NULL: the SPADE epilogue of pg_conv2d_igemm_spade_run (Cout = 2C).  wpack = [gamma ; beta], or with n_tile = 2 Ct < 2C the rows
+ *               ordered tile by tile: [gamma[0:Ct] ; beta[0:Ct] ; gamma[Ct:2Ct] ; beta[Ct:2Ct] ; ...].
  * struct_bytes must be sizeof(pg_conv_args) (guards against a binding built for another header). */
 enum { PG_LAYOUT_NCHW = 0, PG_LAYOUT_C8 = 1 };
 typedef struct pg_conv_args {
@@ -198,7 +202,7 @@ typedef struct pg_conv_args {
     void* y; int32_t y_dtype, y_layout;
     int32_t in_act; float in_alpha, in_gain;
     int32_t act; float alpha, gain, clamp;
-    int32_t operand_format, reserved1;
+    int32_t operand_format, n_tile;      /* n_tile: N-tile width the weights were packed with (0 = the library's default) */
     const float* spade_x; const float* spade_mean; const float* spade_rstd;
     void* stream;
 } pg_conv_args;
@@ -273,6 +277,9 @@ int pg_image_to_u8_bgr(const float* img, void* out, int32_t N, int32_t H, int32_
  * fir: the [4,4] float32 resample filter (needed with img_in); clamp < 0: none; out [N,O,H,W].  Forward only. */
 int pg_torgb_skip(const float* x, const float* w, const float* styles, const float* bias, const float* img_in, const float* fir,
                   float* out, int32_t N, int32_t C, int32_t O, int32_t H, int32_t W, float clamp, void* stream);
+/* The same with x as channel-blocked float16 (PG_LAYOUT_C8, [N][C/8][H*W][8], C % 8 == 0): half the bytes of the feature-map read. */
+int pg_torgb_skip_c8(const void* x_c8, const float* w, const float* styles, const float* bias, const float* img_in, const float* fir,
+                     float* out, int32_t N, int32_t C, int32_t O, int32_t H, int32_t W, float clamp, void* stream);
 
 #ifdef __cplusplus
 }

@@ -43,7 +43,8 @@ SIGNATURES = {
     'pg_conv2d_igemm_fwd': [c_ptr] * 6 + [c_i64, c_ptr, c_ptr] + [c_i32] * 7 + [c_i32, c_i32, c_f32, c_f32, c_i32, c_f32, c_f32, c_f32, c_i32,
                             c_ptr, c_i64, c_ptr],
     'pg_torgb_skip': [c_ptr] * 7 + [c_i32] * 5 + [c_f32, c_ptr],
-    'pg_conv2d_igemm_prepack_batched': [c_ptr, c_i64, c_ptr, c_i32, c_ptr, c_f32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr, c_i64, c_ptr],
+    'pg_torgb_skip_c8': [c_ptr] * 7 + [c_i32] * 5 + [c_f32, c_ptr],
+    'pg_conv2d_igemm_prepack_batched': [c_ptr, c_i64, c_ptr, c_i32, c_ptr, c_f32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr, c_i64, c_ptr],
     'pg_conv2d_igemm_launch': [c_ptr],
     'pg_set_tuning': [ctypes.c_char_p, c_i32],
     'pg_masked_fill_c8': [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_ptr],
@@ -66,7 +67,7 @@ class ConvArgs(ctypes.Structure):
         ('y', c_ptr), ('y_dtype', c_i32), ('y_layout', c_i32),
         ('in_act', c_i32), ('in_alpha', c_f32), ('in_gain', c_f32),
         ('act', c_i32), ('alpha', c_f32), ('gain', c_f32), ('clamp', c_f32),
-        ('operand_format', c_i32), ('reserved1', c_i32),
+        ('operand_format', c_i32), ('n_tile', c_i32),
         ('spade_x', c_ptr), ('spade_mean', c_ptr), ('spade_rstd', c_ptr),
         ('stream', c_ptr),
     ]

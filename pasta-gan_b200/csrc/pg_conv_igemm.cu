@@ -51,7 +51,7 @@ struct ConvParams {
     int in_act; float in_alpha, in_gain; int act; float alpha, gain, clamp; int fmt;
     uint32_t idesc; uint32_t tmem_cols;
     // up-2 polyphase mode: BN virtual channels = phases x couts (see launch code); 0 = plain
-    int up2; int cout_real;
+    int up2; int cout_real; int up2_pair;      // up2_pair: paired-phase epilogue (see epilogue_tile_up2_pair)
     int down2, cin_real, hin, win;   // down-2 mode: the A operand is the 4-plane space-to-depth view of x [N,cin_real,hin,win]
     const float* sp_x; const float* sp_mean; const float* sp_rstd; int spade;   // SPADE epilogue: y = act((x-mean)*rstd*(1+gamma)+beta)*gain
     long long* dbg;            // optional per-CTA phase timestamps (pg_debug_set_buffer), NULL in production
@@ -62,7 +62,8 @@ struct ConvParams {
     long long wpack_sample_stride;             // bytes between the packed weight sets of consecutive samples (groups = N form, networks.py:84-94); 0 = shared weights
     // TMA A operand (x is fp16 in the channel-blocked layout [N][C/8][H][W][8], see include/pasta_b200.h PG_LAYOUT_C8): the staged strip is a
     // tensor-map box of tma_rows image rows x PW positions x 2 channel blocks, written by cp.async.bulk.tensor; no converter warps
-    int tma_a, tma_rows, tma_cb;               // on/off, rows per box, channel blocks per sample (Cin / 8)
+    int tma_a, tma_rows, tma_cb, tma_cb2;      // on/off, rows per box, channel blocks per sample of x (Cin1 / 8) and of x2 (0: no second input)
+    uint32_t a_tx_bytes;                       // bytes one A box delivers (the stage itself is rounded up to 128 B)
     uint32_t a_lbo16;                          // A descriptor leading-dimension byte offset >> 4 (distance between the two 8-channel planes of a stage)
     int y_c8, cb_out;                          // y is fp16 channel-blocked [N][cb_out][H][W][8]
     int vec2; uint32_t w_magic;   // aligned 8-byte loader (see the converter section); ceil(2^32 / W)
@@ -592,45 +593,36 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const int n, 
         const int w = p.band_tw ? band * p.band_tw + ws - 2 : ws;                      // image column
         const bool ok = q < p.Lp && (p.band_tw ? (ws >= 2 && ws < p.band_tw + 2 && w < p.Wimg) : ws < p.W);
         if (p.spade) {
-            // gamma = columns [0, C), beta = columns [C, 2C) of the same accumulator row; normalise x with the staged statistics
-            const int C = p.cout_real >> 1;
-            const float* xp = p.sp_x + (size_t)n * C * HW + (size_t)h * p.Wimg + w;
-            const size_t yoff = (size_t)n * C * HW + (size_t)h * p.Wimg + w;
-            for (int cc = part; cc < C / 16; cc += step) {
+            // N tile jn holds gamma of channels [jn * Ct, (jn + 1) * Ct) in columns [0, Ct) and their beta in columns [Ct, 2 Ct) of the same accumulator
+            // row (Ct = BN / 2; one tile when 2C <= BN); normalise x with the staged statistics
+            const int C = p.cout_real >> 1, Ct = p.BN >> 1, cbase = jn * Ct;
+            const float* xp = p.sp_x + ((size_t)n * C + cbase) * HW + (size_t)h * p.Wimg + w;
+            const size_t yoff = ((size_t)n * C + cbase) * HW + (size_t)h * p.Wimg + w;
+            for (int cc = part; cc < Ct / 16; cc += step) {
                 uint32_t rg[16], rb[16];
                 tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.BN + cc * 16), rg);
-                tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.BN + C + cc * 16), rb);
+                tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.BN + Ct + cc * 16), rb);
                 if (!ok) continue;
                 float xv[16];
 #pragma unroll
                 for (int i = 0; i < 16; i++) xv[i] = __ldg(xp + (size_t)(cc * 16 + i) * HW);
-                if (p.y_c8) {
-                    float v[16];
+                float v[16];
 #pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        const float xn_ = fmaf(xv[i], s_scale[cc * 16 + i], s_shift[cc * 16 + i]);
-                        v[i] = fmaf(xn_, 1.f + __uint_as_float(rg[i]), __uint_as_float(rb[i]));
-                        v[i] = (fmaxf(v[i], 0.f) + slope * fminf(v[i], 0.f)) * p.gain;
-                    }
-                    uint4* yb = reinterpret_cast<uint4*>(p.y) + ((size_t)n * p.cb_out + 2 * cc) * HW + (size_t)h * p.Wimg + w;
+                for (int i = 0; i < 16; i++) {
+                    const float xn_ = fmaf(xv[i], s_scale[cc * 16 + i], s_shift[cc * 16 + i]);
+                    v[i] = fmaf(xn_, 1.f + __uint_as_float(rg[i]), __uint_as_float(rb[i]));
+                    v[i] = (fmaxf(v[i], 0.f) + slope * fminf(v[i], 0.f)) * p.gain;
+                }
+                if (p.y_c8) {
+                    uint4* yb = reinterpret_cast<uint4*>(p.y) + ((size_t)n * p.cb_out + (size_t)(cbase + cc * 16) / 8) * HW + (size_t)h * p.Wimg + w;
                     yb[0] = pack_half8(v); yb[HW] = pack_half8(v + 8);
                 } else if (p.out_half) {
 #pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        const float xn_ = fmaf(xv[i], s_scale[cc * 16 + i], s_shift[cc * 16 + i]);
-                        float v = fmaf(xn_, 1.f + __uint_as_float(rg[i]), __uint_as_float(rb[i]));
-                        v = (fmaxf(v, 0.f) + slope * fminf(v, 0.f)) * p.gain;
-                        store_half(p.y, yoff + (size_t)(cc * 16 + i) * HW, v);
-                    }
+                    for (int i = 0; i < 16; i++) store_half(p.y, yoff + (size_t)(cc * 16 + i) * HW, v[i]);
                 } else {
                     float* yp = p.y + yoff;
 #pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        const float xn_ = fmaf(xv[i], s_scale[cc * 16 + i], s_shift[cc * 16 + i]);
-                        float v = fmaf(xn_, 1.f + __uint_as_float(rg[i]), __uint_as_float(rb[i]));
-                        v = (fmaxf(v, 0.f) + slope * fminf(v, 0.f)) * p.gain;
-                        yp[(size_t)(cc * 16 + i) * HW] = v;
-                    }
+                    for (int i = 0; i < 16; i++) yp[(size_t)(cc * 16 + i) * HW] = v[i];
                 }
             }
             continue;
@@ -725,6 +717,74 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const int n, 
     }
 }
 
+// Polyphase up-2 epilogue when an N tile holds both x-phases of a row parity (BN % (2 Cout) == 0: Cout <= 128): a thread reads the two accumulator
+// chunks (phase 2py, phase 2py + 1) of 16 output channels and writes the two horizontally adjacent output pixels (2h + py, 2w), (2h + py, 2w + 1)
+// together -- 8 contiguous bytes per channel in fp32 NCHW, 32 contiguous bytes per 8-channel block in the channel-blocked fp16 layout -- where the
+// one-phase-at-a-time path writes every other element (half-used sectors).
+__device__ __forceinline__ void epilogue_tile_up2_pair(const ConvParams& p, const int n, const int jn, const int m0, const int HW, const uint32_t tmem_base,
+                                                       const float* s_scale, const float* s_shift, const int quarter, const int part, const int step,
+                                                       const int lane, const int band) {
+    const float slope = (p.act == PG_ACT_LINEAR) ? 1.f : (p.act == PG_ACT_RELU ? 0.f : p.alpha);
+    const float cl = p.clamp >= 0.f ? p.clamp : __int_as_float(0x7f800000);
+    const bool do_act = p.act != PG_ACT_LINEAR, do_clamp = p.clamp >= 0.f;
+    const int W2 = 2 * p.Wimg, H2W2 = 4 * HW;
+    const int co = p.cout_real, ocs = co / 16;                 // 16-channel chunks per phase
+    const int ph_per_tile = p.BN / co, npairs = ph_per_tile >> 1;
+    for (int a = 0; a < p.NACC; a++) {
+        const int q = m0 + a * 128 + quarter * 32 + lane;
+        const int h = (int)__umulhi((uint32_t)q, p.pw_magic), ws = q - h * p.PW;
+        const int w = p.band_tw ? band * p.band_tw + ws - 2 : ws;
+        const bool ok = q < p.Lp && (p.band_tw ? (ws >= 2 && ws < p.band_tw + 2 && w < p.Wimg) : ws < p.W);
+        for (int pc = part; pc < npairs * ocs; pc += step) {
+            const int lp = 2 * (pc / ocs), ob = pc - (pc / ocs) * ocs;          // local phase of the pair's first member, channel chunk
+            const int col0 = lp * co + ob * 16, col1 = col0 + co;
+            uint32_t r0[16], r1[16];
+            tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.BN + col0), r0);
+            tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.BN + col1), r1);
+            if (!ok) continue;
+            const int py = (jn * ph_per_tile + lp) >> 1;
+            const int oy = 2 * h + py, ox = 2 * w;
+            float nz0 = 0.f, nz1 = 0.f;
+            if (p.noise) {
+                const float2 t = __ldg(reinterpret_cast<const float2*>(p.noise + (size_t)n * p.noise_bstride + (size_t)oy * W2 + ox));
+                nz0 = t.x * p.gain; nz1 = t.y * p.gain;
+            }
+            float v0[16], v1[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                v0[i] = fmaf(__uint_as_float(r0[i]), s_scale[col0 + i], s_shift[col0 + i] + nz0);
+                v1[i] = fmaf(__uint_as_float(r1[i]), s_scale[col1 + i], s_shift[col1 + i] + nz1);
+            }
+            if (do_act) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) { v0[i] = fmaxf(v0[i], 0.f) + slope * fminf(v0[i], 0.f); v1[i] = fmaxf(v1[i], 0.f) + slope * fminf(v1[i], 0.f); }
+            }
+            if (do_clamp) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) { v0[i] = fminf(fmaxf(v0[i], -cl), cl); v1[i] = fminf(fmaxf(v1[i], -cl), cl); }
+            }
+            const int o0 = ob * 16;
+            if (p.y_c8) {
+                uint4* yb = reinterpret_cast<uint4*>(p.y) + ((size_t)n * p.cb_out + (size_t)o0 / 8) * H2W2 + (size_t)oy * W2 + ox;
+                yb[0] = pack_half8(v0); yb[1] = pack_half8(v1);
+                yb[H2W2] = pack_half8(v0 + 8); yb[H2W2 + 1] = pack_half8(v1 + 8);
+            } else if (p.out_half) {
+                __half2* yh = reinterpret_cast<__half2*>(reinterpret_cast<__half*>(p.y) + ((size_t)n * co + o0) * H2W2 + (size_t)oy * W2 + ox);
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    uint32_t hh;
+                    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hh) : "f"(v1[i]), "f"(v0[i]));
+                    *reinterpret_cast<uint32_t*>(yh + (size_t)i * (H2W2 / 2)) = hh;
+                }
+            } else {
+                float2* yp = reinterpret_cast<float2*>(p.y + ((size_t)n * co + o0) * H2W2 + (size_t)oy * W2 + ox);
+#pragma unroll
+                for (int i = 0; i < 16; i++) yp[(size_t)i * (H2W2 / 2)] = make_float2(v0[i], v1[i]);
+            }
+        }
+    }
+}
+
 // per-sample input scale: style * in_gain (1 * in_gain for plain convs); zero for padded channels
 __device__ __forceinline__ void stage_styles(const ConvParams& p, const int n, float* s_style, const int cin_pad, const int tid, const int nthreads) {
     for (int c = tid; c < cin_pad; c += nthreads)
@@ -738,10 +798,10 @@ __device__ __forceinline__ void stage_epilogue_constants(const ConvParams& p, co
         const int o = p.up2 ? v % p.cout_real : v;
         const bool live = v < p.Cout;
         if (p.spade) {
-            const int C = p.cout_real >> 1;
-            const float r = j < C ? p.sp_rstd[(size_t)n * C + j] : 0.f;
+            const int C = p.cout_real >> 1, Ct = p.BN >> 1, ch = jn * Ct + j;
+            const float r = j < Ct ? p.sp_rstd[(size_t)n * C + ch] : 0.f;
             s_scale[j] = r;
-            s_shift[j] = j < C ? -p.sp_mean[(size_t)n * C + j] * r : 0.f;
+            s_shift[j] = j < Ct ? -p.sp_mean[(size_t)n * C + ch] * r : 0.f;
             continue;
         }
         s_scale[j] = live ? (p.dcoefs ? p.dcoefs[(size_t)n * p.cout_real + o] : 1.f) * p.gain : 0.f;
@@ -752,7 +812,7 @@ __device__ __forceinline__ void stage_epilogue_constants(const ConvParams& p, co
 // ---------------------------------------------------------------------------------------------- main kernel
 // SCALE: the A operand needs a per-channel scale and/or an input activation (modulated / SPADE layers); plain layers skip both.
 template <bool SCALE>
-__global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ CUtensorMap tmap_a) {
+__global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const int tile = blockIdx.x % p.tiles_per_img;
@@ -789,6 +849,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
         mbar_init(smem_u32(acc_full), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (p.tma_a) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+        if (p.tma_a && p.tma_cb2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a2) : "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
@@ -835,8 +896,10 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
             for (int g = 0; g < nslots; g++) {
                 if (p.tma_a && g % spc == 0) {
                     mbar_wait(smem_u32(&a_empty[sa]), pa ^ 1);
-                    mbar_expect_tx(smem_u32(&a_full[sa]), p.a_stage_bytes);
-                    tma_load_3d(smem_u32(a_base + (size_t)sa * p.a_stage_bytes), &tmap_a, col0, tma_r0, n * p.tma_cb + 2 * (g / spc), smem_u32(&a_full[sa]));
+                    mbar_expect_tx(smem_u32(&a_full[sa]), p.a_tx_bytes);
+                    const int cb = 2 * (g / spc);                // first channel block of this chunk; blocks >= tma_cb come from the second input (fused concat)
+                    if (cb < p.tma_cb) tma_load_3d(smem_u32(a_base + (size_t)sa * p.a_stage_bytes), &tmap_a, col0, tma_r0, n * p.tma_cb + cb, smem_u32(&a_full[sa]));
+                    else               tma_load_3d(smem_u32(a_base + (size_t)sa * p.a_stage_bytes), &tmap_a2, col0, tma_r0, n * p.tma_cb2 + cb - p.tma_cb, smem_u32(&a_full[sa]));
                     if (++sa == p.SA) { sa = 0; pa ^= 1; }
                 }
                 mbar_wait(smem_u32(&b_empty[st]), ph ^ 1);
@@ -1048,7 +1111,8 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
         mbar_wait(smem_u32(acc_full), 0);
         tc_fence_after();
         if (cw == 0 && lane == 0) PG_TS(4);
-        epilogue_tile(p, n, jn, m0, HW, tmem_base, s_scale, s_shift, warp & 3, cw >> 2, kConvWarps / 4, lane, band);   // 2 warps per TMEM lane quarter
+        if (p.up2_pair) epilogue_tile_up2_pair(p, n, jn, m0, HW, tmem_base, s_scale, s_shift, warp & 3, cw >> 2, kConvWarps / 4, lane, band);
+        else epilogue_tile(p, n, jn, m0, HW, tmem_base, s_scale, s_shift, warp & 3, cw >> 2, kConvWarps / 4, lane, band);   // 2 warps per TMEM lane quarter
     }
     if (threadIdx.x == 64 && PG_DBG(p)) {
         PG_TS(5);
@@ -1250,7 +1314,7 @@ static Tuning& tuning() {
     return t;
 }
 
-static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int ks, int up2, bool band = false, int max_nacc = 4, bool tma = false) {
+static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int ks, int up2, bool band = false, int max_nacc = 4, bool tma = false, int n_tile = 0) {
     const Tuning& tn = tuning();
     pl.nvirt = up2 ? 4 * Cout : Cout;
     pl.ntaps = ks * ks;
@@ -1258,6 +1322,7 @@ static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int k
     int bn = round_up(pl.nvirt, 16);
     if (bn > 256) bn = 256;
     if (up2 && pl.nvirt > 256) bn = (2 * Cout <= 256 && (2 * Cout) % 16 == 0) ? 2 * Cout : 256;   // keep both x-phases of a row parity together
+    if (n_tile > 0 && n_tile % 16 == 0 && n_tile < bn && !up2) bn = n_tile;                        // caller-chosen N tile (must match the packed weights)
     pl.BN = bn;
     pl.ntiles_n = (pl.nvirt + bn - 1) / bn;
     pl.PW = (ks == 3 && !band) ? W + 1 : W;          // band mode: the halo columns of the band are its own padding
@@ -1393,7 +1458,7 @@ static int conv_validate(int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_
 }
 
 extern "C" int pg_conv2d_igemm_prepack_batched(const float* w, int64_t w_batch_stride, const float* styles, int32_t batch, const float* fir, float w_scale,
-                                               int32_t Cin, int32_t Cout, int32_t ksize, int32_t up, int32_t flip_weight, int32_t operand_format,
+                                               int32_t Cin, int32_t Cout, int32_t ksize, int32_t up, int32_t flip_weight, int32_t operand_format, int32_t n_tile,
                                                void* workspace, int64_t workspace_bytes, void* stream) {
     using namespace pg;
     int rc = conv_validate(1, Cin, Cout, 8, 8, ksize, up, operand_format);
@@ -1404,8 +1469,9 @@ extern "C" int pg_conv2d_igemm_prepack_batched(const float* w, int64_t w_batch_s
     const bool down2 = up == PG_CONV_DOWN2;
     ConvPlan pl;
     const bool im2col = use_im2col(Cin, ksize, up);
-    rc = make_plan(pl, 1, down2 ? 4 * Cin : (im2col ? Cin * ksize * ksize : Cin), Cout, 8, 8, im2col ? 1 : ksize, up == 2);
+    rc = make_plan(pl, 1, down2 ? 4 * Cin : (im2col ? Cin * ksize * ksize : Cin), Cout, 8, 8, im2col ? 1 : ksize, up == 2, false, 4, false, n_tile);
     if (rc != PG_OK) return rc;
+    PG_REQUIRE(n_tile == 0 || (n_tile % 16 == 0 && Cout % n_tile == 0 && up != 2), "conv2d_igemm: n_tile must be a multiple of 16 that divides Cout (no up-2)");
     const int64_t need = (int64_t)pl.ntiles_n * pl.nchunks * pl.b_stage;
     PG_REQUIRE(workspace_bytes >= need * batch, "conv2d_igemm: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)(need * batch));
     PackParams pp;
@@ -1422,7 +1488,7 @@ extern "C" int pg_conv2d_igemm_prepack_batched(const float* w, int64_t w_batch_s
 
 extern "C" int pg_conv2d_igemm_prepack(const float* w, const float* fir, float w_scale, int32_t Cin, int32_t Cout, int32_t ksize, int32_t up,
                                        int32_t flip_weight, int32_t operand_format, void* workspace, int64_t workspace_bytes, void* stream) {
-    return pg_conv2d_igemm_prepack_batched(w, 0, nullptr, 1, fir, w_scale, Cin, Cout, ksize, up, flip_weight, operand_format, workspace, workspace_bytes, stream);
+    return pg_conv2d_igemm_prepack_batched(w, 0, nullptr, 1, fir, w_scale, Cin, Cout, ksize, up, flip_weight, operand_format, 0, workspace, workspace_bytes, stream);
 }
 
 static int conv_run_impl(const pg_conv_args& a) {
@@ -1447,14 +1513,22 @@ static int conv_run_impl(const pg_conv_args& a) {
     PG_REQUIRE((a.x_dtype == PG_F32 || a.x_dtype == PG_F16) && (a.y_dtype == PG_F32 || a.y_dtype == PG_F16), "conv2d_igemm: x / y must be float32 or float16");
     PG_REQUIRE((a.x_layout == PG_LAYOUT_NCHW || a.x_layout == PG_LAYOUT_C8) && (a.y_layout == PG_LAYOUT_NCHW || a.y_layout == PG_LAYOUT_C8), "conv2d_igemm: unknown tensor layout");
     const bool tma = a.x_layout == PG_LAYOUT_C8;
+    const int n_tile = a.n_tile;
+    PG_REQUIRE(n_tile == 0 || (n_tile % 16 == 0 && Cout % n_tile == 0 && up != 2), "conv2d_igemm: n_tile must be a multiple of 16 that divides Cout (no up-2)");
     if (tma) {
         // channel-blocked fp16 input: taken as the operand bits by TMA, so no input scale / activation / concat, fp16 operands, whole 16-channel chunks
-        PG_REQUIRE(a.x_dtype == PG_F16 && !scale && !x2 && !down2 && operand_format == 0 && Cin % 16 == 0 && !use_im2col(Cin, ksize, up) && ((uintptr_t)x & 15) == 0,
-                   "conv2d_igemm: a channel-blocked input needs float16, a plain (unmodulated, no input activation, no concat) stride-1 or up-2 layer, fp16 operands and Cin %% 16 == 0");
+        PG_REQUIRE(a.x_dtype == PG_F16 && !scale && !down2 && operand_format == 0 && Cin % 16 == 0 && !use_im2col(Cin, ksize, up) && ((uintptr_t)x & 15) == 0,
+                   "conv2d_igemm: a channel-blocked input needs float16, a plain (unmodulated, no input activation) stride-1 or up-2 layer, fp16 operands and Cin %% 16 == 0");
+        PG_REQUIRE(!x2 || (a.cin1 % 16 == 0 && ((uintptr_t)x2 & 15) == 0), "conv2d_igemm: a channel-blocked split input needs Cin1 %% 16 == 0 (x2 is channel-blocked float16 too)");
     }
     if (a.y_layout == PG_LAYOUT_C8)
-        PG_REQUIRE(a.y_dtype == PG_F16 && up != 2 && !a.residual && (a.spade_x ? (Cout / 2) % 16 == 0 : Cout % 16 == 0) && ((uintptr_t)a.y & 15) == 0,
-                   "conv2d_igemm: a channel-blocked output needs float16, no up-sampling, no residual and Cout %% 16 == 0");
+        PG_REQUIRE(a.y_dtype == PG_F16 && (up != 2 || Cout <= 128) && !a.residual && (a.spade_x ? (Cout / 2) % 16 == 0 : Cout % 16 == 0) && ((uintptr_t)a.y & 15) == 0,
+                   "conv2d_igemm: a channel-blocked output needs float16, no residual, Cout %% 16 == 0 (and Cout <= 128 with up-2)");
+    if (tma && ksize == 1 && W > 128) {
+        // a 1x1 convolution does not care how H * W pixels are cut into rows: view a wide image as rows of 128 pixels so that a row fits one TMA box
+        PG_REQUIRE(W % 128 == 0, "conv2d_igemm: a channel-blocked input of a 1x1 layer wider than 128 columns needs W %% 128 == 0");
+        H *= W / 128; W = 128;
+    }
     if (down2) { H /= 2; W /= 2; Cin *= 4; }                      // the GEMM runs over the space-to-depth view at the output resolution
     const bool im2col = use_im2col(Cin, ksize, up);
     const int ks_real = ksize;
@@ -1475,7 +1549,6 @@ static int conv_run_impl(const pg_conv_args& a) {
     // (W is the GEMM's width here: the output width for down-2, the input width for up-2.)
     // TMA boxes hold at most 128 strip positions per row, so a channel-blocked input wider than 127 columns (3x3) is always processed in bands.
     const bool tma_needs_bands = tma && ksize == 3 && W + 1 > 128;
-    PG_REQUIRE(!tma || ksize == 3 || W <= 128, "conv2d_igemm: a channel-blocked input of a 1x1 layer must be at most 128 columns wide");
     if ((tn.bands || tma_needs_bands) && ksize == 3 && !im2col && W >= (tma_needs_bands ? 1 : tn.band_minw) && W % 2 == 0 &&
         (tma || (((uintptr_t)x & 7) == 0 && ((uintptr_t)x2 & 7) == 0 && tn.vec2 && tn.lean))) {
         ConvPlan pb, pf;
@@ -1484,19 +1557,19 @@ static int conv_run_impl(const pg_conv_args& a) {
         // 256->128 @128^2 -8 %, 128->128 @128^2 -6 %); narrow N tiles at 2x lose more to the bands' 6 % of unused MMA rows than they gain
         // (64->64 @256^2 +4 %, 64->64 down-2 @512^2 +7 %)
         const int ratio10 = tn.band_ratio10;
-        bool worth = make_plan(pf, N, Cin, Cout, H, W, ksize, up == 2, false, max_nacc) == PG_OK;
+        bool worth = make_plan(pf, N, Cin, Cout, H, W, ksize, up == 2, false, max_nacc, false, n_tile) == PG_OK;
         if (worth) {
             const int staged10 = 10 * pf.PA / (128 * pf.NACC);
             worth = ratio10 ? staged10 >= ratio10 : (staged10 >= 25 || (staged10 >= 20 && pf.BN >= 128));
         }
-        if ((worth || tma_needs_bands) && make_plan(pb, N * nb, Cin, Cout, H, kBandTW + 4, ksize, up == 2, true, max_nacc, tma) == PG_OK) {
+        if ((worth || tma_needs_bands) && make_plan(pb, N * nb, Cin, Cout, H, kBandTW + 4, ksize, up == 2, true, max_nacc, tma, n_tile) == PG_OK) {
             const int pairs = (pb.PA + 3) / 2, nt = 2 * ((pairs + 31) / 32);
             if (tma || down2 || (nt + kConvWarps - 1) / kConvWarps <= 6) { pl = pb; band_tw = kBandTW; nbands = nb; W = kBandTW + 4; }   // down-2: generic task stream, any count
         }
     }
     PG_REQUIRE(!tma_needs_bands || band_tw, "conv2d_igemm: no band plan for a channel-blocked input of width %d", Wimg);
     if (!band_tw) {
-        rc = make_plan(pl, N, Cin, Cout, H, W, ksize, up == 2, false, max_nacc, tma);
+        rc = make_plan(pl, N, Cin, Cout, H, W, ksize, up == 2, false, max_nacc, tma, n_tile);
         if (rc != PG_OK) return rc;
     }
     PG_REQUIRE(!tma || (2 * pl.PW <= 256 && pl.tma_rows <= 256), "conv2d_igemm: TMA box out of range (PW=%d rows=%d)", pl.PW, pl.tma_rows);
@@ -1521,10 +1594,12 @@ static int conv_run_impl(const pg_conv_args& a) {
     p.idesc = (1u << 4) | ((uint32_t)operand_format << 7) | ((uint32_t)operand_format << 10) | ((uint32_t)(pl.BN >> 3) << 17) | (8u << 24);
     p.tmem_cols = pl.tmem_cols;
     p.up2 = up == 2; p.cout_real = Cout;
+    p.up2_pair = (up == 2 && pl.BN % (2 * Cout) == 0 && !a.residual && ((uintptr_t)a.y & 15) == 0 && ((uintptr_t)a.noise & 7) == 0 && (a.noise_batch_stride % 2) == 0) ? 1 : 0;
+    PG_REQUIRE(!(p.up2 && a.y_layout == PG_LAYOUT_C8) || p.up2_pair, "conv2d_igemm: up-2 with a channel-blocked output needs the paired-phase epilogue (Cout <= 128, aligned noise)");
     p.sp_x = a.spade_x; p.sp_mean = a.spade_mean; p.sp_rstd = a.spade_rstd; p.spade = a.spade_x != nullptr;
-    if (p.spade) PG_REQUIRE(pl.ntiles_n == 1 && pl.BN == Cout && (Cout / 2) % 16 == 0 && up == 1 && a.spade_mean && a.spade_rstd && !a.wpack_sample_stride,
-                            "conv2d_igemm_spade: gamma and beta (2C <= 256 channels, C %% 16 == 0) must share one N tile");
-    p.tma_a = tma; p.tma_rows = pl.tma_rows; p.tma_cb = cin_real / 8; p.a_lbo16 = pl.a_lbo16;
+    if (p.spade) PG_REQUIRE(pl.ntiles_n * pl.BN == Cout && (pl.BN / 2) % 16 == 0 && up == 1 && a.spade_mean && a.spade_rstd && !a.wpack_sample_stride,
+                            "conv2d_igemm_spade: every N tile must hold [gamma_t | beta_t] of whole 16-channel groups (2C = %d, tile %d)", Cout, pl.BN);
+    p.tma_a = tma; p.tma_rows = pl.tma_rows; p.tma_cb = (x2 ? a.cin1 : cin_real) / 8; p.tma_cb2 = (tma && x2) ? (cin_real - a.cin1) / 8 : 0; p.a_lbo16 = pl.a_lbo16; p.a_tx_bytes = (uint32_t)(2 * pl.tma_rows * pl.PW * 16);
     p.y_c8 = a.y_layout == PG_LAYOUT_C8; p.cb_out = (p.spade ? Cout / 2 : Cout) / 8;
 #ifdef PG_DEBUG
     p.dbg = g_conv_dbg; p.pipe = tn.pipe; p.ldmode = tn.ldmode; p.dbgmode = tn.dbgmode;
@@ -1550,11 +1625,16 @@ static int conv_run_impl(const pg_conv_args& a) {
     }
     PG_REQUIRE(!(p.out_half && a.residual), "conv2d_igemm: the residual add is not available with a float16 output");
     p.ntiles_n = pl.ntiles_n;
-    CUtensorMap tmap;
+    CUtensorMap tmap, tmap2;
     memset(&tmap, 0, sizeof(tmap));
+    memset(&tmap2, 0, sizeof(tmap2));
     if (tma) {
-        rc = make_a_tensor_map(tmap, x, N, cin_real / 8, H, Wimg, pl.PW, pl.tma_rows);
+        rc = make_a_tensor_map(tmap, x, N, p.tma_cb, H, Wimg, pl.PW, pl.tma_rows);
         if (rc != PG_OK) return rc;
+        if (x2) {
+            rc = make_a_tensor_map(tmap2, x2, N, p.tma_cb2, H, Wimg, pl.PW, pl.tma_rows);
+            if (rc != PG_OK) return rc;
+        }
     }
     if (!tma) {   // persistent variant (one CTA per SM, double-buffered TMEM, dedicated epilogue warps) where it applies and there is more than one wave of tiles
         const long long total_tiles = (long long)N * pl.tiles_per_img * pl.ntiles_n;
@@ -1584,7 +1664,7 @@ static int conv_run_impl(const pg_conv_args& a) {
     auto kern = scale ? conv_igemm_kernel<true> : conv_igemm_kernel<false>;
     PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     dim3 grid((unsigned)(N * nbands * pl.tiles_per_img), (unsigned)pl.ntiles_n);
-    kern<<<grid, kConvThreads, pl.smem, s>>>(p, tmap);
+    kern<<<grid, kConvThreads, pl.smem, s>>>(p, tmap, tmap2);
     return launch_status("conv2d_igemm", 1);
 }
 

@@ -16,7 +16,7 @@ constexpr int kRgbMaxO = 8;
 
 struct ToRgbParams {
     const float* x; const float* w; const float* styles; const float* bias; const float* img_in; const float* fir; float* out;
-    int N, C, O, H, W; float clamp; int has_img;
+    int N, C, O, H, W; float clamp; int has_img; int x_c8;
 };
 
 template <int O>
@@ -101,8 +101,84 @@ __global__ void __launch_bounds__(256) torgb_skip_kernel(ToRgbParams p) {
     }
 }
 
+// The same operation over a channel-blocked fp16 feature map (PG_LAYOUT_C8, [N][C/8][H*W][8]): one thread = one pixel, a 16-byte load per channel
+// block (a warp reads 512 contiguous bytes), four blocks in flight; half the bytes of the fp32 form.
+template <int O>
+__global__ void __launch_bounds__(256) torgb_skip_c8_kernel(ToRgbParams p) {
+    extern __shared__ float wmod[];                         // [C][O] for this sample
+    const int n = blockIdx.y;
+    const int HW = p.H * p.W;
+    for (int i = threadIdx.x; i < p.C * O; i += blockDim.x) {
+        const int c = i / O, o = i - c * O;
+        wmod[i] = p.w[o * p.C + c] * (p.styles ? p.styles[(size_t)n * p.C + c] : 1.f);
+    }
+    __syncthreads();
+    const int CB = p.C >> 3;
+    const uint4* xn = reinterpret_cast<const uint4*>(p.x) + (size_t)n * CB * HW;
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
+        float acc[O];
+#pragma unroll
+        for (int o = 0; o < O; o++) acc[o] = 0.f;
+        auto fma8 = [&](const uint4& q, int cb) {
+            const unsigned int wds[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&wds[j]));
+                const float* w0 = wmod + (cb * 8 + 2 * j) * O;
+#pragma unroll
+                for (int o = 0; o < O; o++) acc[o] = fmaf(w0[O + o], f.y, fmaf(w0[o], f.x, acc[o]));
+            }
+        };
+        int cb = 0;
+        for (; cb + 4 <= CB; cb += 4) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[u] = __ldg(xn + (size_t)(cb + u) * HW + pix);
+#pragma unroll
+            for (int u = 0; u < 4; u++) fma8(v[u], cb + u);
+        }
+        for (; cb < CB; cb++) fma8(__ldg(xn + (size_t)cb * HW + pix), cb);
+        const int Y = pix / p.W, X = pix - Y * p.W;
+#pragma unroll
+        for (int o = 0; o < O; o++) {
+            float v = acc[o] + (p.bias ? __ldg(p.bias + o) : 0.f);
+            if (p.clamp >= 0.f) v = fminf(fmaxf(v, -p.clamp), p.clamp);
+            if (p.has_img) {
+                const int h2 = p.H >> 1, w2 = p.W >> 1;
+                const float* im = p.img_in + ((size_t)n * O + o) * h2 * w2;
+                const int uy0 = Y - 2, ux0 = X - 2;
+                float s = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if ((uy0 + i) & 1) continue;
+                    const int iy = (uy0 + i) >> 1;
+                    if (iy < 0 || iy >= h2) continue;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if ((ux0 + j) & 1) continue;
+                        const int ix = (ux0 + j) >> 1;
+                        if (ix < 0 || ix >= w2) continue;
+                        s = fmaf(__ldg(p.fir + (3 - i) * 4 + (3 - j)), __ldg(im + iy * w2 + ix), s);
+                    }
+                }
+                v += 4.f * s;
+            }
+            p.out[((size_t)n * O + o) * HW + pix] = v;
+        }
+    }
+}
+
 template <int O>
 static int launch_torgb(const ToRgbParams& p, cudaStream_t s) {
+    if (p.x_c8) {
+        const size_t smem = (size_t)p.C * O * sizeof(float);
+        const int HW = p.H * p.W;
+        int bx = (HW + 255) / 256;
+        if (bx > kNumSMs * 8) bx = kNumSMs * 8;
+        if (smem > 48 * 1024) PG_CUDA(cudaFuncSetAttribute(torgb_skip_c8_kernel<O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        torgb_skip_c8_kernel<O><<<dim3(bx, p.N), 256, smem, s>>>(p);
+        return launch_status("torgb_skip(c8)");
+    }
     const size_t smem = (size_t)p.C * O * sizeof(float);
     const int quads = p.H * p.W / 4;
     int bx = (quads + 255) / 256;
@@ -114,9 +190,10 @@ static int launch_torgb(const ToRgbParams& p, cudaStream_t s) {
 
 }  // namespace pg
 
-extern "C" int pg_torgb_skip(const float* x, const float* w, const float* styles, const float* bias, const float* img_in, const float* fir,
-                             float* out, int32_t N, int32_t C, int32_t O, int32_t H, int32_t W, float clamp, void* stream) {
+static int torgb_entry(const float* x, const float* w, const float* styles, const float* bias, const float* img_in, const float* fir,
+                       float* out, int32_t N, int32_t C, int32_t O, int32_t H, int32_t W, float clamp, int x_c8, void* stream) {
     using namespace pg;
+    PG_REQUIRE(!x_c8 || C % 8 == 0, "torgb_skip: a channel-blocked input needs C %% 8 == 0");
     PG_REQUIRE(N >= 0 && C >= 1 && H >= 1 && W >= 1, "torgb_skip: bad sizes");
     PG_REQUIRE(O >= 1 && O <= kRgbMaxO, "torgb_skip: 1..%d output channels supported (got %d)", kRgbMaxO, O);
     PG_REQUIRE((H * W) % 4 == 0 && W % 4 == 0, "torgb_skip: W must be a multiple of 4");
@@ -127,7 +204,7 @@ extern "C" int pg_torgb_skip(const float* x, const float* w, const float* styles
     PG_REQUIRE(aligned16(x) && aligned16(out), "torgb_skip: x and out must be 16-byte aligned");
     ToRgbParams p;
     p.x = x; p.w = w; p.styles = styles; p.bias = bias; p.img_in = img_in; p.fir = fir; p.out = out;
-    p.N = N; p.C = C; p.O = O; p.H = H; p.W = W; p.clamp = clamp; p.has_img = img_in != nullptr;
+    p.N = N; p.C = C; p.O = O; p.H = H; p.W = W; p.clamp = clamp; p.has_img = img_in != nullptr; p.x_c8 = x_c8;
     cudaStream_t s = (cudaStream_t)stream;
     switch (O) {
         case 1: return launch_torgb<1>(p, s); case 2: return launch_torgb<2>(p, s); case 3: return launch_torgb<3>(p, s);
@@ -135,4 +212,14 @@ extern "C" int pg_torgb_skip(const float* x, const float* w, const float* styles
         case 7: return launch_torgb<7>(p, s); case 8: return launch_torgb<8>(p, s);
     }
     return fail(PG_ERR_UNSUPPORTED, "torgb_skip: O=%d", O);
+}
+
+extern "C" int pg_torgb_skip(const float* x, const float* w, const float* styles, const float* bias, const float* img_in, const float* fir,
+                             float* out, int32_t N, int32_t C, int32_t O, int32_t H, int32_t W, float clamp, void* stream) {
+    return torgb_entry(x, w, styles, bias, img_in, fir, out, N, C, O, H, W, clamp, 0, stream);
+}
+
+extern "C" int pg_torgb_skip_c8(const void* x_c8, const float* w, const float* styles, const float* bias, const float* img_in, const float* fir,
+                                float* out, int32_t N, int32_t C, int32_t O, int32_t H, int32_t W, float clamp, void* stream) {
+    return torgb_entry((const float*)x_c8, w, styles, bias, img_in, fir, out, N, C, O, H, W, clamp, 1, stream);
 }

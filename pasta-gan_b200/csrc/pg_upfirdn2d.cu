@@ -18,6 +18,7 @@
 //                   (channels_last included): one thread per output element gathers its taps through
 //                   the read-only path.  Serves AugmentPipe-style filters, the 3-channel RGB up-2 and
 //                   every tiny plane (< 32 px wide) where launch latency, not bandwidth, is the cost.
+#include <limits.h>
 #include "pg_common.cuh"
 
 namespace pg {
@@ -303,13 +304,150 @@ __global__ void __launch_bounds__(256) upfirdn2d_band_kernel(UpfirdnParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------ band (4x4, up=2): polyphase
+// Zero-insert up-2 + 4x4 FIR (reference tile kernel upfirdn2d.cu:252 <2,2,1,1,4,4,64,16,1>): the RGB skip image of every synthesis block
+// (networks.py:5711 -> upfirdn2d.py:308-343, pad (2,1,2,1), gain 4) and the backward of every down-2 (upfirdn2d.py:251-261).  Only the taps that land
+// on a sample are evaluated: output (oy, ox) with b = ox - padx0 reads input columns ceil(b/2), ceil(b/2)+1 with taps (b&1), (b&1)+2 -- 4 FMAs per
+// output instead of 16 tests.  One CTA owns a full-width band of output rows of one plane; the input rows it needs (a quarter of the output's bytes)
+// are staged in shared memory with a zero border, each thread walks a quad of 4 adjacent output columns down the band holding the two live input
+// rows (4 columns each) in registers, and stores aligned float4.  grid.x = plane * bands_per_plane + band; smem = tile_rows * pitch floats.
+template <int PR, int PODD>
+__device__ __forceinline__ void up2_quad(const float (&k)[4][4], const float (&a)[4], const float (&b)[4], float (&out)[4]) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const int pc = (c + PODD) & 1;                          // horizontal tap parity of this output column
+        const int q = (c + PODD + pc) >> 1;                     // register column of its first tap
+        out[c] = fmaf(k[PR][pc], a[q], fmaf(k[PR][pc + 2], a[q + 1], fmaf(k[PR + 2][pc], b[q], k[PR + 2][pc + 2] * b[q + 1])));
+    }
+}
+
+template <class T, bool EPI>
+__global__ void __launch_bounds__(256) upfirdn2d_up2_band_kernel(UpfirdnParams p) {
+    constexpr int F = 4;
+    extern __shared__ float tile[];
+    const T* __restrict__ x = (const T*)p.x;
+    T* __restrict__ y = (T*)p.y;
+    const int plane = blockIdx.x / p.bands_per_plane;
+    const int band  = blockIdx.x - plane * p.bands_per_plane;
+    const int oy0   = band * p.band_rows;
+    const int rows  = min(p.band_rows, p.outH - oy0);
+    const int padl  = (p.padx0 + 1) >> 1;                       // tile column of input column 0
+    // input rows of the band: first = ceil((oy0 - pady0) / 2), last = ceil((oy0 + rows - 1 - pady0) / 2) + 1
+    const int by0 = oy0 - p.pady0;
+    const int iy0 = (by0 + (by0 & 1)) >> 1;                     // arithmetic shift: exact, numerator even
+    const int byl = oy0 + rows - 1 - p.pady0;
+    const int need = ((byl + (byl & 1)) >> 1) + 2 - iy0;        // staged rows
+    const T* xp = x + (size_t)plane * p.inH * p.inW;
+
+    float k[F][F];
+#pragma unroll
+    for (int i = 0; i < F; i++)
+#pragma unroll
+        for (int j = 0; j < F; j++)
+            k[i][j] = __ldg(p.f + (p.flip ? i : F - 1 - i) * p.fsh + (p.flip ? j : F - 1 - j) * p.fsw) * p.gain;
+
+    // stage: zero the tile, then stream the (contiguous) span of input rows with 8 independent loads in flight per thread
+    for (int i = threadIdx.x; i < need * p.pitch; i += 256) tile[i] = 0.f;
+    __syncthreads();
+    {
+        const int r_lo = iy0 < 0 ? -iy0 : 0;
+        const int r_hi = min(need, p.inH - iy0);
+        const int total = (r_hi - r_lo) * p.inW;
+        const T* src = xp + (ptrdiff_t)(iy0 + r_lo) * p.inW;
+        constexpr int KC = 8;
+        for (int base = 0; base < total; base += 256 * KC) {
+            float v[KC];
+#pragma unroll
+            for (int kk = 0; kk < KC; kk++) {
+                const int i = base + (int)threadIdx.x + 256 * kk;
+                v[kk] = i < total ? (float)to_acc<T>(__ldg(src + i)) : 0.f;
+            }
+#pragma unroll
+            for (int kk = 0; kk < KC; kk++) {
+                const int i = base + (int)threadIdx.x + 256 * kk;
+                const int r = (int)__umulhi((uint32_t)i, p.inw_magic), c = i - r * p.inW + padl;
+                if (i < total) tile[(r_lo + r) * p.pitch + c] = v[kk];
+            }
+        }
+    }
+    __syncthreads();
+
+    const int quads = (p.outW + 3) >> 2;
+    const int rpg = p.rows_per_group;
+    const int groups = (rows + rpg - 1) / rpg;
+    const int items = groups * quads;
+    float bias = 0.f;
+    if (EPI && p.epi.b) bias = (float)to_acc<T>(__ldg((const T*)p.epi.b + plane % p.C));
+    T* yp = y + (size_t)plane * p.outH * p.outW;
+    const bool vec_store = sizeof(T) == 4 && (p.outW & 3) == 0 && ((((size_t)p.outH * p.outW) & 3) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+    const int podd = p.padx0 & 1;                               // parity of (x0 - padx0) for every quad (x0 is a multiple of 4)
+    // horizontal tap pairs and register columns of the quad's 4 outputs (see header comment): even base: (0,1) (1,2) (1,2) (2,3); odd: (1,2) (1,2) (2,3) (2,3)
+    for (int item = threadIdx.x; item < items; item += 256) {
+        const int g = item / quads;
+        const int x0 = (item - g * quads) << 2;
+        const int r0 = g * rpg;
+        const int nr = min(rpg, rows - r0);
+        // tile column of register column 0: floor((x0 - padx0) / 2) + padl == x0 / 2 for either parity of padx0
+        const float* colp = tile + (x0 >> 1);
+        float a[4], b[4];                                       // input rows ra, ra + 1
+        int ra = INT_MIN;
+        for (int r = 0; r < nr; r++) {
+            const int oy = oy0 + r0 + r;
+            const int by = oy - p.pady0;
+            const int pr = by & 1;
+            const int rn = ((by + pr) >> 1) - iy0;              // staged row of the first vertical tap
+            if (rn != ra) {
+                if (rn == ra + 1) {
+#pragma unroll
+                    for (int c = 0; c < 4; c++) a[c] = b[c];
+                } else {
+                    const float2 t0 = *reinterpret_cast<const float2*>(colp + rn * p.pitch), t1 = *reinterpret_cast<const float2*>(colp + rn * p.pitch + 2);
+                    a[0] = t0.x; a[1] = t0.y; a[2] = t1.x; a[3] = t1.y;
+                }
+                const float2 u0 = *reinterpret_cast<const float2*>(colp + (rn + 1) * p.pitch), u1 = *reinterpret_cast<const float2*>(colp + (rn + 1) * p.pitch + 2);
+                b[0] = u0.x; b[1] = u0.y; b[2] = u1.x; b[3] = u1.y;
+                ra = rn;
+            }
+            float out[4];
+            // pr and podd are uniform over the CTA (even rows_per_group), so the four variants are branches with compile-time tap indices
+            if (pr) { if (podd) up2_quad<1, 1>(k, a, b, out); else up2_quad<1, 0>(k, a, b, out); }
+            else    { if (podd) up2_quad<0, 1>(k, a, b, out); else up2_quad<0, 0>(k, a, b, out); }
+            store_quad<T, EPI>(p, yp + (size_t)oy * p.outW + x0, out, x0, bias, vec_store);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------ host side
 static bool contiguous_nchw(const int32_t sz[4], const int64_t st[4]) {
     return st[3] == 1 && st[2] == sz[3] && st[1] == (int64_t)sz[2] * sz[3] && (st[0] == (int64_t)sz[1] * sz[2] * sz[3] || sz[0] == 1);
 }
 
 template <class T, bool EPI>
-static int launch_upfirdn2d(UpfirdnParams p, bool band_ok, cudaStream_t stream) {
+static int launch_upfirdn2d(UpfirdnParams p, bool band_ok, bool up2_ok, cudaStream_t stream) {
+    if (up2_ok) {
+        int band_rows = 32;
+        if (band_rows > p.outH) band_rows = p.outH;
+        p.bands_per_plane = (p.outH + band_rows - 1) / band_rows;
+        // few planes (the 3-channel RGB skip): shorter bands so that the grid still covers the SMs
+        while (band_rows > 8 && (int64_t)p.N * p.C * p.bands_per_plane < 2 * kNumSMs) { band_rows /= 2; p.bands_per_plane = (p.outH + band_rows - 1) / band_rows; }
+        band_rows = (p.outH + p.bands_per_plane - 1) / p.bands_per_plane;
+        p.band_rows = band_rows;
+        p.tile_rows = band_rows / 2 + 3;
+        p.pitch = ((p.outW + 3) / 4) * 2 + 4;                    // register column 3 of the last quad: (outW/4 - 1) * 2 + 3, even pitch for float2 reads
+        if (p.pitch < p.inW + ((p.padx0 + 1) >> 1) + 1) p.pitch = (p.inW + ((p.padx0 + 1) >> 1) + 2) & ~1;
+        const int quads = (p.outW + 3) / 4;
+        int rpg = band_rows * quads / 256;
+        p.rows_per_group = (rpg < 4 ? 4 : (rpg > 16 ? 16 : rpg)) & ~1;      // even: the row parity of step r is then uniform over the CTA
+        p.inw_magic = (uint32_t)((0x100000000ull + (uint64_t)p.inW - 1) / (uint64_t)p.inW);
+        const size_t smem = (size_t)p.tile_rows * p.pitch * sizeof(float);
+        const int64_t blocks = (int64_t)p.N * p.C * p.bands_per_plane;
+        if (smem <= 96 * 1024 && blocks <= INT32_MAX) {
+            auto kern = upfirdn2d_up2_band_kernel<T, EPI>;
+            if (smem > 48 * 1024) PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<(unsigned)blocks, 256, smem, stream>>>(p);
+            return launch_status("upfirdn2d(up2 band)");
+        }
+    }
     if (band_ok) {
         const int D = p.downx;
         // band height: as tall as a ~40 KB tile allows (taller bands re-read fewer halo rows), at most 32 rows
@@ -391,12 +529,16 @@ static int upfirdn2d_entry(const void* x, const float* f, void* y,
                          padx0 >= 0 && pady0 >= 0 && outW >= 8 && (int64_t)outH * outW >= 256 &&      // smaller planes: per-CTA setup costs more than the generic kernel
                         
                          contiguous_nchw(in_size, in_stride) && contiguous_nchw(out_size, out_stride);
+    // polyphase up-2 band kernel: 4x4 filter, up 2 in both directions, no decimation, non-negative left / top padding, every tap row / column the
+    // band touches inside the staged tile (right / bottom padding may be anything: samples past the image are the tile's zero border)
+    const bool up2_ok = dtype != PG_F64 && fh == 4 && fw == 4 && upx == 2 && upy == 2 && downx == 1 && downy == 1 && padx0 >= 0 && pady0 >= 0 &&
+                        outW >= 8 && (int64_t)outH * outW >= 256 && contiguous_nchw(in_size, in_stride) && contiguous_nchw(out_size, out_stride);
     cudaStream_t s = (cudaStream_t)stream;
     const bool e = epi.enabled != 0;
     switch (dtype) {
-        case PG_F32: return e ? launch_upfirdn2d<float, true>(p, band_ok, s)  : launch_upfirdn2d<float, false>(p, band_ok, s);
-        case PG_F16: return e ? launch_upfirdn2d<__half, true>(p, band_ok, s) : launch_upfirdn2d<__half, false>(p, band_ok, s);
-        case PG_F64: return e ? launch_upfirdn2d<double, true>(p, false, s)   : launch_upfirdn2d<double, false>(p, false, s);
+        case PG_F32: return e ? launch_upfirdn2d<float, true>(p, band_ok, up2_ok, s)  : launch_upfirdn2d<float, false>(p, band_ok, up2_ok, s);
+        case PG_F16: return e ? launch_upfirdn2d<__half, true>(p, band_ok, up2_ok, s) : launch_upfirdn2d<__half, false>(p, band_ok, up2_ok, s);
+        case PG_F64: return e ? launch_upfirdn2d<double, true>(p, false, false, s)    : launch_upfirdn2d<double, false>(p, false, false, s);
     }
     return fail(PG_ERR_INVALID_ARGUMENT, "unsupported dtype %d", dtype);
 }

@@ -206,9 +206,9 @@ def conv_layer(x, w, b=None, f=None, up=1, down=1, padding=0, flip_weight=True, 
     if K.is_c8(x):
         # channel-blocked fp16 from one of our own epilogues: TMA operand path.  The producer only emits this layout for consumers it has checked
         # (K.c8_input_ok), so there is nothing to fall back to here.
-        assert in_act is None and x2 is None and act in ('linear', 'relu', 'lrelu') and padding == int(w.shape[2]) // 2 and down == 1
+        assert in_act is None and act in ('linear', 'relu', 'lrelu') and padding == int(w.shape[2]) // 2 and down == 1
         return K.conv2d_igemm(x, w, f=f, up=up, flip_weight=flip_weight, bias=b, act=act, gain=act_gain, clamp=clamp, w_scale=w_scale,
-                              cache_weights=cache_weights, residual=residual, out_dtype=out_dtype or torch.float32, out_c8=out_c8)
+                              cache_weights=cache_weights, x2=x2, residual=residual, out_dtype=out_dtype or torch.float32, out_c8=out_c8)
     if act in ('linear', 'relu', 'lrelu') and in_act in (None, 'relu', 'lrelu') and \
             K.supported(x, w, up=up, down=down, f=f, padding=pad4, x2=x2, residual=residual, allow_half=half_ok):
         return K.conv2d_igemm(x, w, f=f, up=up, down=down, flip_weight=flip_weight, bias=b, in_act=in_act or 'linear', in_gain=in_gain,
@@ -231,11 +231,20 @@ def conv_layer(x, w, b=None, f=None, up=1, down=1, padding=0, flip_weight=True, 
 
 
 def modconv_layer(x, weight, styles, noise=None, up=1, padding=0, resample_filter=None, demodulate=True, flip_weight=True,
-                  fused_modconv=True, bias=None, act='linear', act_gain=1.0, clamp=None, dcoefs=None, styles_normalized=False):
+                  fused_modconv=True, bias=None, act='linear', act_gain=1.0, clamp=None, dcoefs=None, styles_normalized=False, out_c8=False):
     """Product form of modulated_conv2d + bias_act (SynthesisLayer / ToRGB): one tcgen05 launch with the style folded into the
-    activation operand, demodulation / noise / bias / activation / clamp in the epilogue."""
+    activation operand, demodulation / noise / bias / activation / clamp in the epilogue.  A channel-blocked fp16 ``x`` is loaded by TMA and cannot be
+    scaled on the way in: the styles are then folded into per-sample packed weights (the reference's own formulation, networks.py:64-66)."""
     from .torch_utils.ops import conv_igemm as K, bias_act as B
     k = int(weight.shape[2])
+    if K.is_c8(x):
+        assert act in ('linear', 'relu', 'lrelu') and padding == k // 2
+        if not demodulate:
+            dcoefs = None
+        elif dcoefs is None:
+            dcoefs = torch.addmm(_EPS.get(x.device), styles.square(), _weight_sq_sums(weight).t()).rsqrt()
+        return K.conv2d_igemm(x, weight, f=resample_filter, up=up, flip_weight=flip_weight, styles=styles, dcoefs=dcoefs, noise=noise,
+                              bias=bias, act=act, gain=act_gain, clamp=clamp, fold_styles=True, styles_normalized=True, out_c8=out_c8)
     if act in ('linear', 'relu', 'lrelu') and padding == k // 2 and \
             K.supported(x, weight, up=up, f=resample_filter, padding=(padding,) * 4) and not styles.requires_grad:
         if not demodulate:
@@ -244,8 +253,8 @@ def modconv_layer(x, weight, styles, noise=None, up=1, padding=0, resample_filte
             dcoefs = torch.addmm(_EPS.get(x.device), styles.square(), _weight_sq_sums(weight).t()).rsqrt()
         return K.conv2d_igemm(x, weight, f=resample_filter, up=up, flip_weight=flip_weight, styles=styles, dcoefs=dcoefs, noise=noise,
                               bias=bias, act=act, gain=act_gain, clamp=clamp, cache_weights=isinstance(weight, nn.Parameter),
-                              styles_normalized=styles_normalized)
-    assert not styles_normalized, 'normalised styles are only produced for the tcgen05 path'
+                              styles_normalized=styles_normalized, out_c8=out_c8)
+    assert not styles_normalized and not out_c8, 'normalised styles / channel-blocked outputs are only produced for the tcgen05 path'
     x = modulated_conv2d(x=x, weight=weight, styles=styles, noise=noise, up=up, padding=padding, resample_filter=resample_filter,
                          demodulate=demodulate, flip_weight=flip_weight, fused_modconv=fused_modconv)
     return B.bias_act(x, bias, act=act, gain=act_gain, clamp=clamp)
@@ -271,10 +280,10 @@ def _half_intermediates(x):
             not torch.is_grad_enabled() and x.shape[3] % 2 == 0 and x.shape[3] <= 256)
 
 
-def _c8_ok(channels, h, w, k):
+def _c8_ok(channels, h, w, k, up=1):
     """May a tensor [N, channels, h, w] consumed only by a plain k x k tcgen05 convolution travel as channel-blocked fp16 (TMA operand path)?"""
     from .torch_utils.ops import conv_igemm as K
-    return (not torch.is_grad_enabled()) and os.environ.get('PASTA_B200_HALF_INTERMEDIATES', '1') != '0' and K.c8_input_ok(int(channels), int(h), int(w), int(k))
+    return (not torch.is_grad_enabled()) and os.environ.get('PASTA_B200_HALF_INTERMEDIATES', '1') != '0' and K.c8_input_ok(int(channels), int(h), int(w), int(k), up)
 
 
 def _masked_mean_fill(feat, valid, rest, out):
@@ -440,16 +449,18 @@ class Conv2dLayer(OpsModule):
         clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
         return self.ops.bias_act(x, b, act=self.activation, gain=self.act_gain * gain, clamp=clamp)
 
-    def _fused(self, x, gain, pre_act, x2=None, residual=None):
+    def _fused(self, x, gain, pre_act, x2=None, residual=None, out_c8=False):
         """One-launch layer when the operator table offers it (the CUDA product does; the oracle table does not)."""
         layer = getattr(self.ops, 'conv_layer', None)
         if layer is None:
             return None
         w = self.weight                                   # raw parameter: weight_gain is applied when the GEMM tiles are packed
-        b = self.bias.to(x.dtype) if self.bias is not None else None
+        b = self.bias.float() if self.bias is not None else None
         clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
         kw = dict(f=self.resample_filter, up=self.up, down=self.down, padding=self.padding, flip_weight=(self.up == 1),
                   w_scale=float(self.weight_gain), cache_weights=True, x2=x2, residual=residual)
+        if out_c8:
+            kw['out_c8'] = True
         if isinstance(self, SpadeConv2dLayer):
             kw['half_ok'] = True                          # SPADE convs may be fed the fp16 intermediates of the norm blocks
         if pre_act is None:
@@ -460,12 +471,13 @@ class Conv2dLayer(OpsModule):
             return None
         return layer(x, w, None, in_act=self.activation, in_gain=self.act_gain * gain, **kw)
 
-    def forward(self, x, gain=1, x2=None, residual=None):
+    def forward(self, x, gain=1, x2=None, residual=None, out_c8=False):
         """``x2``: second input concatenated along channels (reference: torch.cat before the call, :5705); ``residual``: added to the
-        result (reference: ``y.add_(x)`` after the call, :990)."""
-        y = self._fused(x, gain, None, x2, residual)
+        result (reference: ``y.add_(x)`` after the call, :990); ``out_c8``: channel-blocked fp16 result for a consumer that loads it by TMA."""
+        y = self._fused(x, gain, None, x2, residual, out_c8)
         if y is not None:
             return y
+        assert not out_c8 and x.ndim == 4
         if x2 is not None:
             x = torch.cat([x, x2.to(x.dtype)], dim=1)
         y = self._act(self._conv(x), gain)
@@ -542,9 +554,12 @@ class SynthesisLayer(OpsModule):
             self.noise_strength = nn.Parameter(torch.zeros([]))
         self.bias = nn.Parameter(torch.zeros([out_channels]))
 
-    def forward(self, x, w, noise_mode='random', fused_modconv=True, gain=1):
+    def forward(self, x, w, noise_mode='random', fused_modconv=True, gain=1, out_c8=False):
         assert noise_mode in ['random', 'const', 'none']
-        misc.assert_shape(x, [None, self.weight.shape[1], self.resolution // self.up, self.resolution // self.up])
+        if x.ndim == 5:                                   # channel-blocked fp16 [N, C/8, H, W, 8] from one of our own epilogues
+            misc.assert_shape(x, [None, self.weight.shape[1] // 8, self.resolution // self.up, self.resolution // self.up, 8])
+        else:
+            misc.assert_shape(x, [None, self.weight.shape[1], self.resolution // self.up, self.resolution // self.up])
         pre = getattr(self, '_pre', None)
         styles, dcoefs, normalized = pre if pre is not None else (self.affine(w), None, False)
         noise = None
@@ -556,8 +571,8 @@ class SynthesisLayer(OpsModule):
         layer = getattr(self.ops, 'modconv_layer', None)
         if layer is not None:
             return layer(x, self.weight, styles, noise=noise, up=self.up, padding=self.padding, resample_filter=self.resample_filter,
-                         flip_weight=(self.up == 1), fused_modconv=fused_modconv, bias=self.bias.to(x.dtype), act=self.activation,
-                         act_gain=self.act_gain * gain, clamp=clamp, dcoefs=dcoefs, styles_normalized=normalized)
+                         flip_weight=(self.up == 1), fused_modconv=fused_modconv, bias=self.bias.float(), act=self.activation,
+                         act_gain=self.act_gain * gain, clamp=clamp, dcoefs=dcoefs, styles_normalized=normalized, **(dict(out_c8=True) if out_c8 else {}))
         x = self.ops.modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=noise, up=self.up, padding=self.padding,
                                       resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv)
         return self.ops.bias_act(x, self.bias.to(x.dtype), act=self.activation, gain=self.act_gain * gain, clamp=clamp)
@@ -755,6 +770,32 @@ class SpadeResBlockV2(OpsModule):
         return self.conv1(self.spade1(x, denorm_feat, post_act=pre(self.conv1, np.sqrt(0.5)), out_half=True, out_k=3), no_act=True, residual=y)
 
 
+def _c8_chain_ok(block, x, cat_feat):
+    """Channel-blocked chain through a synthesis block: only under inference on the CUDA operator table, at >= 128 px with <= 128 output channels, when
+    the caller provided the channel-blocked retain-person features and every layer's shape is TMA-loadable."""
+    c8_ok = getattr(block.ops, 'c8_ok', None)
+    res, cout = block.resolution, int(block.conv1.weight.shape[0])
+    if c8_ok is None or torch.is_grad_enabled() or not x.is_cuda or res < 128 or cout > 128 or cout % 16 or f'{res}_c8' not in cat_feat:
+        return False
+    if os.environ.get('PASTA_B200_C8_CHAIN', '1') == '0' or getattr(block.ops, 'torgb_skip', None) is None:
+        return False
+    return bool(c8_ok(cout, res, res, 3) and c8_ok(cout, res, res, 1) and (x.ndim == 4 or c8_ok(int(x.shape[1]) * 8, res // 2, res // 2, 3, 2)))
+
+
+def _with_c8_cat_feats(module, cat_feat):
+    """Channel-blocked copies ('<res>_c8') of the retain-person feature maps at >= 128 px, read by the merge convs of the channel-blocked blocks."""
+    c8_ok = getattr(module.ops, 'c8_ok', None)
+    if c8_ok is None or torch.is_grad_enabled() or os.environ.get('PASTA_B200_C8_CHAIN', '1') == '0':
+        return cat_feat
+    from .torch_utils.ops import conv_igemm as K
+    cat_feat = dict(cat_feat)
+    for key in [k for k in cat_feat if k.isdigit() and int(k) >= 128]:
+        t = cat_feat[key]
+        if t.is_cuda and t.ndim == 4 and t.shape[1] % 16 == 0 and c8_ok(t.shape[1], t.shape[2], t.shape[3], 1):
+            cat_feat[key + '_c8'] = K.to_c8(t)
+    return cat_feat
+
+
 class SynthesisBlockFull(OpsModule):
     def __init__(self, in_channels, out_channels, w_dim, resolution, img_channels, is_last, is_style=False, architecture='skip',
                  resample_filter=_FIR, conv_clamp=None, use_fp16=False, fp16_channels_last=False, **layer_kwargs):
@@ -794,11 +835,20 @@ class SynthesisBlockFull(OpsModule):
             x = self.conv1(x, next(w_iter), fused_modconv=fused_modconv, gain=np.sqrt(0.5), **layer_kwargs)
             x = y.add_(x)
         else:
-            misc.assert_shape(x, [None, self.in_channels, self.resolution // 2, self.resolution // 2])
-            x = self.conv0(x.to(torch.float32), next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
-            x = self.conv1(x, next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
+            # high-resolution blocks (>= 128 px, <= 128 channels) under inference: activations travel between conv0 / conv1 / merge_conv / ToRGB as
+            # channel-blocked fp16 -- half the HBM bytes, TMA operand loads, styles folded into per-sample weights (a few MB at these widths)
+            chain = _c8_chain_ok(self, x, cat_feat)
+            if x.ndim == 4:
+                misc.assert_shape(x, [None, self.in_channels, self.resolution // 2, self.resolution // 2])
+                x = x.to(torch.float32)
+            c8kw = dict(out_c8=True) if chain else {}
+            x = self.conv0(x, next(w_iter), fused_modconv=fused_modconv, **layer_kwargs, **c8kw)
+            x = self.conv1(x, next(w_iter), fused_modconv=fused_modconv, **layer_kwargs, **c8kw)
             if x.shape[2] > 16:                          # merge the warped retain-person features
-                x = self.merge_conv(x, x2=cat_feat[str(x.shape[2])].to(torch.float32))     # concat fused into the 1x1 conv's operand loader
+                if chain:
+                    x = self.merge_conv(x, x2=cat_feat[f'{x.shape[2]}_c8'], out_c8=True)
+                else:
+                    x = self.merge_conv(x, x2=cat_feat[str(x.shape[2])].to(torch.float32))     # concat fused into the 1x1 conv's operand loader
         if img is not None:
             misc.assert_shape(img, [None, self.img_channels, self.resolution // 2, self.resolution // 2])
         parsing = None
@@ -808,6 +858,7 @@ class SynthesisBlockFull(OpsModule):
             if fused is not None:                           # one streaming kernel: upsample2d(img) + clamp(1x1 modconv + b)
                 img, parsing = fused
             else:
+                assert x.ndim == 4, 'channel-blocked activations need the fused ToRGB kernel'
                 if img is not None:
                     img = self.ops.upsample2d(img, self.resample_filter)
                 y, parsing = self.torgb(x, w_rgb, fused_modconv=fused_modconv)
@@ -898,6 +949,7 @@ class SynthesisNetworkFull(OpsModule):
     def _forward_blocks(self, block_ws, pose_feat, cat_feat, denorm_upper_input, denorm_lower_input, denorm_upper_mask, denorm_lower_mask,
                         label_override=None, **block_kwargs):
         x = img = parsing = None
+        cat_feat = _with_c8_cat_feats(self, cat_feat)
         for res, cur in zip(self.block_resolutions, block_ws):
             x, img, parsing = getattr(self, f'b{res}')(x, img, cur, pose_feat, cat_feat, force_fp32=True, **block_kwargs)
             if res == 128:
@@ -1007,15 +1059,23 @@ class SynthesisBlock512(OpsModule):
         if self.in_channels == 0:
             x = self.conv1(pose_feature.to(torch.float32), next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
         else:
-            x = self.conv0(x.to(torch.float32), next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
-            x = self.conv1(x, next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
+            chain = _c8_chain_ok(self, x, cat_feat)            # channel-blocked fp16 chain, as in SynthesisBlockFull
+            if x.ndim == 4:
+                x = x.to(torch.float32)
+            c8kw = dict(out_c8=True) if chain else {}
+            x = self.conv0(x, next(w_iter), fused_modconv=fused_modconv, **layer_kwargs, **c8kw)
+            x = self.conv1(x, next(w_iter), fused_modconv=fused_modconv, **layer_kwargs, **c8kw)
             if x.shape[2] > 32:
-                x = self.merge_conv(x, x2=cat_feat[str(x.shape[2])].to(torch.float32))     # concat fused into the 1x1 conv's operand loader
+                if chain:
+                    x = self.merge_conv(x, x2=cat_feat[f'{x.shape[2]}_c8'], out_c8=True)
+                else:
+                    x = self.merge_conv(x, x2=cat_feat[str(x.shape[2])].to(torch.float32))     # concat fused into the 1x1 conv's operand loader
         w_rgb = next(w_iter)
         fused = self.torgb.forward_skip(x, w_rgb, img, self.resample_filter)
         if fused is not None:
             img = fused[0]
         else:
+            assert x.ndim == 4, 'channel-blocked activations need the fused ToRGB kernel'
             if img is not None:
                 img = self.ops.upsample2d(img, self.resample_filter)
             y = self.torgb(x, w_rgb, fused_modconv=fused_modconv).to(torch.float32)
@@ -1053,6 +1113,7 @@ class SynthesisNetwork512(OpsModule):
             if not hasattr(self, '_bank'):
                 object.__setattr__(self, '_bank', StyleBank())
             self._bank.fill(entries)
+        cat_feat = _with_c8_cat_feats(self, cat_feat)
         try:
             for block, cur in plan:
                 x, img = block(x, img, cur, pose_feat, cat_feat, **block_kwargs)

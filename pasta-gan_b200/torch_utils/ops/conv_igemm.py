@@ -75,9 +75,9 @@ def half_input_ok(x, w, up=1, down=1, x2=None):
 
 def c8_input_ok(c, h, wd, k, up=1, down=1):
     """A channel-blocked input is loaded by TMA: plain stride-1 (or up-2) 1x1 / 3x3 layer, fp16 operands, whole 16-channel chunks; 3x3 layers wider than
-    127 columns run in 64-column bands (even W), 1x1 layers take at most 128 columns."""
+    127 columns run in 64-column bands (even W); 1x1 layers wider than 128 columns are viewed as rows of 128 pixels (W % 128 == 0)."""
     return (enabled and operand_format == 'fp16' and down == 1 and up in (1, 2) and k in (1, 3) and c % 16 == 0 and (k == 1 or c * k * k > 160) and
-            (wd <= 128 if k == 1 else (wd <= 127 or wd % 2 == 0)) and
+            ((wd <= 128 or wd % 128 == 0) if k == 1 else (wd <= 127 or wd % 2 == 0)) and
             os.environ.get('PASTA_B200_CONV_TMA', '1') != '0')
 
 
@@ -131,8 +131,8 @@ class _PackEntry:
 _pack_store = {}          # (id(w), cfg) -> _PackEntry
 
 
-def _pack_cfg(w_scale, mode, flip_weight, fmt_code):
-    return (float(w_scale), int(mode), bool(flip_weight), int(fmt_code))
+def _pack_cfg(w_scale, mode, flip_weight, fmt_code, n_tile=0):
+    return (float(w_scale), int(mode), bool(flip_weight), int(fmt_code), int(n_tile))
 
 
 def _drop_entries(wid):
@@ -140,12 +140,12 @@ def _drop_entries(wid):
         _pack_store.pop(key, None)
 
 
-def _run_prepack(capi, w, f, w_scale, mode, flip_weight, fmt_code, ws, batch=1, w_batch_stride=0, styles=None):
+def _run_prepack(capi, w, f, w_scale, mode, flip_weight, fmt_code, ws, batch=1, w_batch_stride=0, styles=None, n_tile=0):
     cout, cin, k = int(w.shape[-4]), int(w.shape[-3]), int(w.shape[-1])
     wc = w.detach().contiguous()
     rc = capi.load().pg_conv2d_igemm_prepack_batched(capi.ptr(wc), int(w_batch_stride), capi.ptr(styles), int(batch),
                                                      capi.ptr(f) if mode != 1 else None, float(w_scale), cin, cout, k, mode,
-                                                     int(bool(flip_weight)), fmt_code, capi.ptr(ws), int(ws.numel()), capi.current_stream(w.device))
+                                                     int(bool(flip_weight)), fmt_code, int(n_tile), capi.ptr(ws), int(ws.numel()), capi.current_stream(w.device))
     capi.check(rc, 'pg_conv2d_igemm_prepack')
 
 
@@ -156,15 +156,15 @@ def _workspace_bytes(capi, cin, cout, k, mode):
     return n
 
 
-def _packed_weights(capi, w, f, w_scale, mode, flip_weight, fmt_code, cache):
+def _packed_weights(capi, w, f, w_scale, mode, flip_weight, fmt_code, cache, n_tile=0):
     """fp16/bf16 GEMM tiles of ``w * w_scale`` (pg_conv2d_igemm_prepack).  With ``cache=True`` the caller promises that ``w`` is a
     long-lived tensor (a Parameter / buffer): the packed copy lives in the store above and is refreshed in place when ``w`` changes."""
     cout, cin, k, _ = (int(v) for v in w.shape)
     if not cache:
         ws = torch.empty(_workspace_bytes(capi, cin, cout, k, mode), dtype=torch.uint8, device=w.device)
-        _run_prepack(capi, w, f, w_scale, mode, flip_weight, fmt_code, ws)
+        _run_prepack(capi, w, f, w_scale, mode, flip_weight, fmt_code, ws, n_tile=n_tile)
         return ws
-    key = (id(w), _pack_cfg(w_scale, mode, flip_weight, fmt_code))
+    key = (id(w), _pack_cfg(w_scale, mode, flip_weight, fmt_code, n_tile))
     e = _pack_store.get(key)
     if e is not None and e.wref() is not w:               # id() reuse after the old tensor died without its finalizer having run yet
         _pack_store.pop(key, None)
@@ -176,12 +176,12 @@ def _packed_weights(capi, w, f, w_scale, mode, flip_weight, fmt_code, cache):
         wid = id(w)
         e.wref = weakref.ref(w, lambda _r, wid=wid: _drop_entries(wid))
         e.ws = torch.empty(_workspace_bytes(capi, cin, cout, k, mode), dtype=torch.uint8, device=w.device)
-        e.cfg = (mode, flip_weight, fmt_code, w_scale)
+        e.cfg = (mode, flip_weight, fmt_code, w_scale, n_tile)
         e.version = None
         _pack_store[key] = e
     f_ver = None if mode == 1 else (f.data_ptr(), f._version)
     if fresh or e.version != w._version or e.ptr != w.data_ptr() or (mode != 1 and (e.f is not f or e.f_version != f_ver)):
-        _run_prepack(capi, w, f, w_scale, mode, flip_weight, fmt_code, e.ws)
+        _run_prepack(capi, w, f, w_scale, mode, flip_weight, fmt_code, e.ws, n_tile=n_tile)
         e.version, e.ptr = w._version, w.data_ptr()
         e.f, e.f_version = (None, None) if mode == 1 else (f, f_ver)
         e.stream = cur
@@ -200,21 +200,21 @@ def refresh_packed_weights(device=None):
     CUDA graphs captured earlier read the new weights on their next replay.  Returns the number of re-packed entries."""
     capi = _backend.capi()
     done = 0
+    for hit in _cat_cache.values():                       # [gamma ; beta] concatenations first: rebuilt in place, their packed copies follow below
+        done += _refresh_cat(hit)
     for (wid, _cfg), e in list(_pack_store.items()):
         w = e.wref()
         if w is None or (device is not None and w.device != torch.device(device)):
             continue
         if e.version != w._version or e.ptr != w.data_ptr():
-            mode, flip_weight, fmt_code, w_scale = e.cfg
+            mode, flip_weight, fmt_code, w_scale, n_tile = e.cfg
             with torch.cuda.device(w.device):
-                _run_prepack(capi, w, e.f, w_scale, mode, flip_weight, fmt_code, e.ws)
+                _run_prepack(capi, w, e.f, w_scale, mode, flip_weight, fmt_code, e.ws, n_tile=n_tile)
             e.version, e.ptr = w._version, w.data_ptr()
             e.stream = torch.cuda.current_stream(w.device)
             e.event = torch.cuda.Event()
             e.event.record(e.stream)
             done += 1
-    for hit in _cat_cache.values():                       # [gamma ; beta] concatenations: rebuild in place, then their packed copy
-        done += _refresh_cat(hit)
     return done
 
 
@@ -238,10 +238,11 @@ def conv2d_igemm(x, w, f=None, up=1, down=1, flip_weight=True, styles=None, dcoe
     if x_c8:
         n, cb_in, h, wd, _ = (int(v) for v in x.shape)
         cin1 = cb_in * 8
-        assert x2 is None
+        assert x2 is None or (is_c8(x2) and cin1 % 16 == 0 and tuple(x2.shape[2:4]) == (h, wd) and int(x2.shape[0]) == n), 'a channel-blocked x needs a channel-blocked x2'
+        cin = cin1 + (int(x2.shape[1]) * 8 if x2 is not None else 0)
     else:
         n, cin1, h, wd = (int(v) for v in x.shape)
-    cin = cin1 + (int(x2.shape[1]) if x2 is not None else 0)
+        cin = cin1 + (int(x2.shape[1]) if x2 is not None else 0)
     if per_sample_weights:
         assert w.ndim == 5 and int(w.shape[0]) == n and not cache_weights and styles is None
         cout, cin_w, k = int(w.shape[1]), int(w.shape[2]), int(w.shape[4])
@@ -249,8 +250,9 @@ def conv2d_igemm(x, w, f=None, up=1, down=1, flip_weight=True, styles=None, dcoe
         cout, cin_w, k, _ = (int(v) for v in w.shape)
     assert cin_w == cin, 'weight / input channel mismatch'
     x = x.contiguous()
-    if x2 is not None:
+    if x2 is not None and not x_c8:
         assert x2.dtype == torch.float32 and tuple(x2.shape[2:]) == (h, wd) and int(x2.shape[0]) == n and down == 1 and cin1 % 8 == 0
+    if x2 is not None:
         x2 = x2.contiguous()
     assert not (up == 2 and down == 2)
     mode = -2 if down == 2 else up                       # PG_CONV_DOWN2 / 2 / 1
@@ -262,7 +264,7 @@ def conv2d_igemm(x, w, f=None, up=1, down=1, flip_weight=True, styles=None, dcoe
     elif x.dtype == torch.float16:
         assert styles is None and in_act == 'linear' and in_gain == 1.0 and half_input_ok(x, w, up, down, x2), 'float16 input: plain stride-1 layer only'
     if out_c8:
-        assert cout % 16 == 0 and up == 1 and residual is None
+        assert cout % 16 == 0 and (up == 1 or cout <= 128) and residual is None
         y = torch.empty([n, cout // 8, oh, ow, 8], dtype=torch.float16, device=x.device)
     else:
         y = torch.empty([n, cout, oh, ow], dtype=out_dtype, device=x.device)
@@ -312,7 +314,7 @@ def conv2d_igemm(x, w, f=None, up=1, down=1, flip_weight=True, styles=None, dcoe
             wpack = _packed_weights(capi, w, f, w_scale, mode, flip_weight, fmt_code, cache_weights)
         # algorithmic FLOPs: output pixels for stride-1 / down-2, INPUT pixels for up-2 (zero-inserted taps excluded)
         sp = capi.span('conv_igemm', flops=2 * n * cout * cin * k * k * (oh * ow if up == 1 else h * wd),
-                       nbytes=x.element_size() * x.numel() + 4 * ((x2.numel() if x2 is not None else 0) + (y.numel() if residual is not None else 0) + w.numel()) + y.element_size() * y.numel(),
+                       nbytes=x.element_size() * x.numel() + (x2.element_size() * x2.numel() if x2 is not None else 0) + 4 * ((y.numel() if residual is not None else 0) + w.numel()) + y.element_size() * y.numel(),
                        tag=f'{cin}->{cout} @{h}x{wd} k{k} mode{mode}' + (' mod' if styles is not None else '') + (' cat' if x2 is not None else '') + (' res' if residual is not None else '') +
                            (f' in_{in_act}' if in_act != 'linear' else '') + (' tma' if x_c8 else '') + (' psw' if sample_stride else '') + (' oc8' if out_c8 else ''))
         a = capi.ConvArgs()
@@ -350,23 +352,26 @@ def _refresh_cat(hit):
     if ver == hit['ver']:
         return 0
     with torch.no_grad():
-        c = int(wg.shape[0])
-        hit['cat'][:c].copy_(wg.detach())
-        hit['cat'][c:].copy_(wb.detach())                # in place: the tensor (and its packed copy's storage) keep their addresses
+        c, ct = int(wg.shape[0]), hit['ct']
+        cat = hit['cat'].view(c // ct, 2, ct, *wg.shape[1:])            # tile t: [gamma[t*ct:(t+1)*ct] ; beta[t*ct:(t+1)*ct]]
+        cat[:, 0].copy_(wg.detach().view(c // ct, ct, *wg.shape[1:]))
+        cat[:, 1].copy_(wb.detach().view(c // ct, ct, *wb.shape[1:]))   # in place: the tensor (and its packed copy's storage) keep their addresses
     hit['ver'] = ver
     return 1
 
 
-def _gamma_beta_weights(w_gamma, w_beta):
-    """[w_gamma ; w_beta] as one long-lived tensor (so the packed-weight store can key on it), rebuilt IN PLACE when either parameter changes."""
-    key = (id(w_gamma), id(w_beta))
+def _gamma_beta_weights(w_gamma, w_beta, ct=None):
+    """[w_gamma ; w_beta] as one long-lived tensor (so the packed-weight store can key on it), rebuilt IN PLACE when either parameter changes.
+    ``ct``: channels per N tile -- rows are ordered tile by tile, [gamma_t ; beta_t] (default: one tile)."""
+    ct = int(w_gamma.shape[0]) if ct is None else int(ct)
+    key = (id(w_gamma), id(w_beta), ct)
     hit = _cat_cache.get(key)
     if hit is not None and (hit['g']() is not w_gamma or hit['b']() is not w_beta):
         _cat_cache.pop(key, None)
         hit = None
     if hit is None:
         drop = lambda _r, key=key: _cat_cache.pop(key, None)
-        hit = dict(g=weakref.ref(w_gamma, drop), b=weakref.ref(w_beta, drop), ver=None,
+        hit = dict(g=weakref.ref(w_gamma, drop), b=weakref.ref(w_beta, drop), ver=None, ct=ct,
                    cat=torch.empty([2 * int(w_gamma.shape[0])] + list(w_gamma.shape[1:]), dtype=torch.float32, device=w_gamma.device))
         _cat_cache[key] = hit
     _refresh_cat(hit)
@@ -422,12 +427,15 @@ def spade_conv_norm(x, feat, w_gamma, w_beta, w_scale=1.0, act='linear', alpha=0
     x = x.contiguous()
     feat = feat.contiguous()
     mean, rstd = stats if stats is not None else instance_stats(x, eps)      # `stats`: reuse when several norm blocks share x
-    wcat = _gamma_beta_weights(w_gamma, w_beta)
+    # 2C = 256 output columns with a TMA-fed A operand: two N tiles [gamma_t | beta_t] of 128 columns, so that two CTAs share an SM and one's epilogue
+    # overlaps the other's main loop (the A boxes are re-read from L2 by TMA, no converter work is duplicated)
+    n_tile = 128 if (f_c8 and 2 * c == 256 and os.environ.get('PASTA_B200_SPADE_TILE', '128') == '128') else 0
+    wcat = _gamma_beta_weights(w_gamma, w_beta, ct=(n_tile // 2 if n_tile else None))
     fmt_code = _FMT[fmt or operand_format]
     y = torch.empty([n, c // 8, h, wd, 8], dtype=torch.float16, device=x.device) if out_c8 else torch.empty_like(x, dtype=out_dtype)
     with torch.cuda.device(x.device):
         capi.require_device()
-        wpack = _packed_weights(capi, wcat, None, w_scale, 1, True, fmt_code, True)
+        wpack = _packed_weights(capi, wcat, None, w_scale, 1, True, fmt_code, True, n_tile=n_tile)
         sp = capi.span('conv_igemm', flops=2 * n * 2 * c * cin * k * k * h * wd, nbytes=4 * (x.numel() + wcat.numel()) + feat.element_size() * feat.numel() + y.element_size() * y.numel(),
                        tag=f'{cin}->{2 * c} @{h}x{wd} k{k} spade' + (' tma' if f_c8 else (' in16' if feat.dtype == torch.float16 else '')) +
                            (' oc8' if out_c8 else (' out16' if out_dtype == torch.float16 else '')))
@@ -439,7 +447,7 @@ def spade_conv_norm(x, feat, w_gamma, w_beta, w_scale=1.0, act='linear', alpha=0
         a.y, a.y_dtype, a.y_layout = capi.ptr(y), capi.dtype_code(y.dtype), capi.LAYOUT_C8 if out_c8 else capi.LAYOUT_NCHW
         a.in_act, a.in_alpha, a.in_gain = _ACT['linear'], 0.0, 1.0
         a.act, a.alpha, a.gain, a.clamp = _ACT[act], float(alpha), float(gain), -1.0
-        a.operand_format = fmt_code
+        a.operand_format, a.n_tile = fmt_code, n_tile
         a.spade_x, a.spade_mean, a.spade_rstd = capi.ptr(x), capi.ptr(mean), capi.ptr(rstd)
         a.stream = capi.current_stream(x.device)
         rc = capi.load().pg_conv2d_igemm_launch(_byref(a))

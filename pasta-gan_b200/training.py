@@ -3,9 +3,15 @@
 Mirrors the arithmetic of the reference's loss (training/loss_wo_flow_fullbody.py:106-254: non-saturating logistic GAN loss on the
 coarse and the fine-tuned image, L1 x 40, parsing cross-entropy x 20, R1 with gamma 10 evaluated by a double backward under
 conv2d_gradfix.no_weight_gradients()) and of the loop's phase schedule (training_loop_wo_flow_fullbody.py:332-343, :484-518:
-Gmain and Dmain every iteration, Dreg every 16th with lazy-regularisation Adam hyper-parameters, NaN guard, Adam step).  VGG /
-contextual losses need downloaded weights and are left out (vgg_weight = 0), the augmentation pipe is off (aug = noaug), as stated in
-BASELINE.md.  Gradients are averaged across ranks with one flat all-reduce per phase (data_parallel.FlatGradBucket).
+Gmain and Dmain every iteration, Dreg every 16th with lazy-regularisation Adam hyper-parameters for BOTH networks -- G_reg_interval = 4,
+D_reg_interval = 16, so lr and betas are scaled by 4/5 and 16/17 even though the G regulariser itself is a no-op (pl_weight = 0) -- NaN guard, Adam
+step).  VGG / contextual losses need downloaded weights and are left out (vgg_weight = 0), the augmentation pipe is off (aug = noaug), as stated
+in BASELINE.md.  Gradients are averaged across ranks with one flat all-reduce per phase (data_parallel.FlatGradBucket), launched asynchronously on
+a communication stream; parameters that get no gradient in a phase see zeros where the reference has grad = None (an Adam update with zero first
+and second moments leaves the parameter unchanged, so the trajectories agree).
+
+``capture()`` records each phase as two CUDA graphs (zero-grad + forward + backward | NaN guard + Adam step) with the all-reduce between them: the
+training step is host-issue bound when launched op by op (~5 100 launches per iteration), a graph replay is not.
 """
 import numpy as np
 import torch
@@ -15,17 +21,20 @@ from .torch_utils.ops import conv2d_gradfix
 
 
 class TryOnTrainer:
-    def __init__(self, G, D, lr=0.002, r1_gamma=10.0, l1_weight=40.0, mask_weight=20.0, d_reg_interval=16, group=None):
+    def __init__(self, G, D, lr=0.002, r1_gamma=10.0, l1_weight=40.0, mask_weight=20.0, d_reg_interval=16, g_reg_interval=4, group=None, capturable=False):
         self.G, self.D, self.group = G, D, group
         self.r1_gamma, self.l1_weight, self.mask_weight, self.d_reg_interval = r1_gamma, l1_weight, mask_weight, d_reg_interval
         conv2d_gradfix.enabled = True                          # training_loop_wo_flow_fullbody.py:255
         self.g_bucket = dp.FlatGradBucket(G.parameters())
         self.d_bucket = dp.FlatGradBucket(D.parameters())
-        mb = d_reg_interval / (d_reg_interval + 1)             # lazy regularisation (training_loop...py:336-343)
-        self.g_opt = torch.optim.Adam(self.g_bucket.params, lr=lr, betas=(0.0, 0.99), eps=1e-8)
-        self.d_opt = torch.optim.Adam(self.d_bucket.params, lr=lr * mb, betas=(0.0 ** mb, 0.99 ** mb), eps=1e-8)
+        mb = d_reg_interval / (d_reg_interval + 1)             # lazy regularisation (training_loop...py:336-343), applied to G as well (G_reg_interval = 4)
+        mg = g_reg_interval / (g_reg_interval + 1) if g_reg_interval else 1.0
+        self.g_opt = torch.optim.Adam(self.g_bucket.params, lr=lr * mg, betas=(0.0 ** mg, 0.99 ** mg), eps=1e-8, capturable=capturable)
+        self.d_opt = torch.optim.Adam(self.d_bucket.params, lr=lr * mb, betas=(0.0 ** mb, 0.99 ** mb), eps=1e-8, capturable=capturable)
         self.ce = torch.nn.CrossEntropyLoss(reduction='none')
         self.it = 0
+        self.graphs = None
+        self.comm_stream = torch.cuda.Stream(self.g_bucket.flat.device) if self.g_bucket.flat.is_cuda else None
 
     # --- forward helpers -----------------------------------------------------------------------------------------
     def _run_G(self, b, stylecode, feats):
@@ -35,13 +44,28 @@ class TryOnTrainer:
         cat = {str(f.shape[2]): f for f in feats}
         return G.synthesis(ws, pose_feat, cat, b['denorm_upper_input'], b['denorm_lower_input'], b['denorm_upper_mask'], b['denorm_lower_mask'])
 
-    def _finish(self, bucket, opt):
-        bucket.allreduce(self.group)
+    def _exchange(self, bucket):
+        """Average the phase's gradients across ranks: one asynchronous all-reduce of the flat buffer on the communication stream, so the host goes
+        straight on to issuing the next phase's forward while NCCL runs; the optimizer step (same stream order) waits for it."""
+        if self.comm_stream is None or not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            bucket.allreduce(self.group)
+            return
+        cur = torch.cuda.current_stream()
+        self.comm_stream.wait_stream(cur)
+        with torch.cuda.stream(self.comm_stream):
+            bucket.allreduce(self.group)
+        cur.wait_stream(self.comm_stream)
+
+    def _apply(self, bucket, opt):
         bucket.sanitize()
         opt.step()
 
+    def _finish(self, bucket, opt):
+        self._exchange(bucket)
+        self._apply(bucket, opt)
+
     # --- phases ----------------------------------------------------------------------------------------------------
-    def g_main(self, b):
+    def g_main(self, b, finish=True):
         self.g_bucket.zero()
         self.D.requires_grad_(False)
         stylecode, feats = self.G.style_encoding(b['c'], b['retain'])
@@ -53,10 +77,11 @@ class TryOnTrainer:
         loss = loss_adv + loss_l1 + loss_mask
         loss.backward()
         self.D.requires_grad_(True)
-        self._finish(self.g_bucket, self.g_opt)
+        if finish:
+            self._finish(self.g_bucket, self.g_opt)
         return dict(G_adv=loss_adv.detach(), G_l1=loss_l1.detach(), G_mask=loss_mask.detach())
 
-    def d_phase(self, b, do_main, do_r1):
+    def d_phase(self, b, do_main, do_r1, finish=True):
         self.d_bucket.zero()
         sp = torch.nn.functional.softplus
         out = {}
@@ -82,11 +107,60 @@ class TryOnTrainer:
         (logits * 0 + loss_real + loss_r1).mean().mul(gain).backward()
         if do_main:
             out['D_real'] = loss_real.mean().detach()
-        self._finish(self.d_bucket, self.d_opt)
+        if finish:
+            self._finish(self.d_bucket, self.d_opt)
         return out
+
+    # --- CUDA graphs ---------------------------------------------------------------------------------------------------
+    def capture(self, batch, warmup=3):
+        """Record the three phases as CUDA graphs over static copies of ``batch`` (later batches are copied into them by ``step``).  Needs
+        ``capturable=True`` optimizers.  Each phase = graph A (zero-grad, forward, backward) -> eager flat all-reduce -> graph B (NaN guard, Adam)."""
+        assert self.g_opt.defaults.get('capturable') and self.d_opt.defaults.get('capturable'), 'construct the trainer with capturable=True'
+        self.static = {k: v.clone() for k, v in batch.items()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                       # allocator pools, cuDNN plans, optimizer state, NCCL communicators
+                self.g_main(self.static)
+                self.d_phase(self.static, True, False)
+                self.d_phase(self.static, False, True)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        phases = dict(g_main=(lambda: self.g_main(self.static, finish=False), self.g_bucket, self.g_opt),
+                      d_main=(lambda: self.d_phase(self.static, True, False, finish=False), self.d_bucket, self.d_opt),
+                      d_reg=(lambda: self.d_phase(self.static, False, True, finish=False), self.d_bucket, self.d_opt))
+        graphs = {}
+        pool = None
+        for name, (fn, bucket, opt) in phases.items():
+            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga, pool=pool):
+                stats = fn()
+            pool = ga.pool()
+            with torch.cuda.graph(gb, pool=pool):
+                self._apply(bucket, opt)
+            graphs[name] = (ga, gb, bucket, stats)
+        self.graphs = graphs
+        return self
+
+    def _replay(self, name):
+        ga, gb, bucket, stats = self.graphs[name]
+        ga.replay()
+        self._exchange(bucket)
+        gb.replay()
+        return stats
 
     def step(self, batch):
         """Gmain + Dmain, plus Dreg (R1) on every ``d_reg_interval``-th iteration.  ``batch`` is this rank's shard."""
+        if self.graphs is not None:
+            if batch is not self.static:
+                for k, v in batch.items():
+                    self.static[k].copy_(v, non_blocking=True)
+            stats = dict(self._replay('g_main'))
+            stats.update(self._replay('d_main'))
+            if self.it % self.d_reg_interval == 0:
+                stats.update(self._replay('d_reg'))
+            self.it += 1
+            return stats
         stats = {}
         stats.update(self.g_main(batch))
         stats.update(self.d_phase(batch, do_main=True, do_r1=False))

@@ -49,6 +49,24 @@ def test_argument_errors_are_reported_not_crashed():
         capi.check(rc, 'pg_upfirdn2d')
 
 
+def test_conv_args_struct_matches_header():
+    """pg_conv2d_igemm_launch checks pg_conv_args.struct_bytes against its own sizeof before touching the device: an N = 0 call with the binding's
+    ctypes Structure must pass that check (rc 0), a wrong size must be refused; pg_set_tuning knows its keys."""
+    import ctypes
+    capi = pasta_gan_b200.capi
+    lib = capi.load()
+    a = capi.ConvArgs()
+    a.struct_bytes = ctypes.sizeof(capi.ConvArgs)
+    a.N, a.Cin, a.Cout, a.H, a.W, a.ksize, a.up = 0, 16, 16, 8, 8, 3, 1
+    a.in_act, a.act, a.gain, a.in_gain, a.clamp = 1, 1, 1.0, 1.0, -1.0
+    assert lib.pg_conv2d_igemm_launch(ctypes.byref(a)) == 0, lib.pg_last_error()
+    a.struct_bytes -= 8
+    assert lib.pg_conv2d_igemm_launch(ctypes.byref(a)) == 1 and b'struct_bytes' in lib.pg_last_error()
+    assert lib.pg_set_tuning(b'conv_bands', 1) == 0
+    assert lib.pg_set_tuning(b'no_such_key', 1) == 1 and b'unknown key' in lib.pg_last_error()
+    assert not hasattr(ctypes.CDLL(capi.lib_path()), 'pg_debug_set_buffer'), 'the release library must not export the debug hook'
+
+
 def test_no_cpu_fallback():
     x = torch.randn(1, 2, 8, 8)
     f = upfirdn2d.setup_filter([1, 3, 3, 1])

@@ -469,6 +469,13 @@ def test_c8_tma_up2_spade_and_folded_styles(cv):
     r = cv.spade_conv_norm(xs, feat, wg, wb, act='relu', gain=1.1, out_dtype=torch.float16)
     rc = cv.spade_conv_norm(xs, cv.to_c8(feat), wg, wb, act='relu', gain=1.1, out_c8=True)
     assert torch.equal(cv.from_c8(rc, 64, dtype=torch.float16), r)
+    # SPADE at C = 128 (the generator's shape): two [gamma_t | beta_t] N tiles of 128 columns on the TMA path vs one 256-column tile on the converter path
+    xs = torch.randn(2, 128, 20, 128, device=DEV); feat = torch.randn(2, 128, 20, 128, device=DEV).half()
+    wg = torch.randn(128, 128, 3, 3, device=DEV) / 34; wb = torch.randn(128, 128, 3, 3, device=DEV) / 34
+    r = cv.spade_conv_norm(xs, feat, wg, wb, act='relu', gain=1.1, out_dtype=torch.float16)
+    rc = cv.spade_conv_norm(xs, cv.to_c8(feat), wg, wb, act='relu', gain=1.1, out_c8=True)
+    assert torch.equal(cv.from_c8(rc, 128, dtype=torch.float16), r)
+    assert torch.equal(cv.spade_conv_norm(xs, cv.to_c8(feat), wg, wb, act='relu', gain=1.1), cv.spade_conv_norm(xs, feat, wg, wb, act='relu', gain=1.1))
     # styles folded into the weights vs styles on the activations: same math, different fp16 roundings -> oracle tolerance
     x = torch.randn(3, 64, 40, 40); wm = torch.randn(48, 64, 3, 3); st = 1 + 0.5 * torch.randn(3, 64); nz = torch.randn(40, 40) * 0.3; b = torch.randn(48) * 0.1
     ref = O.bias_act(O.modulated_conv2d(x.double(), wm.double(), st.double(), noise=nz.double(), padding=1), b.double(), act='lrelu', clamp=256)

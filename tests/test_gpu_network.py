@@ -163,9 +163,16 @@ def test_fused_inference_paths_are_equivalent(cuda_generator, monkeypatch):
         return out
 
     base = run()
+    # SPADE section alone (channel-blocked chain of the synthesis blocks off): fp16 / channel-blocked intermediates carry the same operand bits the
+    # consumer's loader would produce from fp32, in the same accumulation order -> bit-identical outputs
+    spade_only = run(PASTA_B200_C8_CHAIN='0')
     no_half = run(PASTA_B200_HALF_INTERMEDIATES='0')
-    for a, b in zip(base, no_half):
+    for a, b in zip(spade_only, no_half):
         assert torch.equal(a, b)
+    # the channel-blocked chain of the >= 128 px synthesis blocks rounds activations to fp16 one layer earlier and folds styles into the weights
+    # instead of the activations: same math, different roundings
+    assert rel_err(base[0], no_half[0]) < 3e-3 and rel_err(base[2], no_half[2]) < 3e-3
+    assert float((base[1] - no_half[1]).norm() / no_half[1].norm()) < 1e-2
     # StyleBank: the batched styles / demodulation coefficients themselves agree with the per-layer path to fp32 GEMM rounding ...
     syn = G.synthesis
     ws = torch.randn(2, syn.num_ws, syn.w_dim, device=DEV)

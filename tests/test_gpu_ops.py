@@ -63,6 +63,11 @@ FORMS = [
     dict(name='filter_513', shape=[1, 2, 513, 513], kw=dict(padding=[1, 1, 1, 1], gain=4)),
     dict(name='down2_512', shape=[1, 2, 512, 512], kw=dict(down=2, padding=[1, 1, 1, 1])),
     dict(name='bwd_of_down2', shape=[2, 8, 64, 64], kw=dict(up=2, padding=[2, 1, 2, 1], gain=1, flip_filter=True)),
+    # polyphase up-2 band kernel: odd pads (both tap parities), ragged widths (scalar stores), many bands, a general (non rank-1) filter below
+    dict(name='up2_rgb_128', shape=[2, 3, 128, 128], kw=dict(up=2, padding=[2, 1, 2, 1], gain=4)),
+    dict(name='up2_oddpad', shape=[2, 5, 37, 45], kw=dict(up=2, padding=[1, 2, 3, 0], gain=4)),
+    dict(name='up2_ragged', shape=[1, 4, 33, 21], kw=dict(up=2, padding=[2, 2, 2, 2], gain=2, flip_filter=True)),
+    dict(name='up2_bigpad', shape=[1, 3, 20, 20], kw=dict(up=2, padding=[5, 4, 4, 6], gain=4)),
     dict(name='small_33', shape=[3, 5, 33, 33], kw=dict(padding=[1, 1, 1, 1], gain=4)),
     dict(name='tiny_9', shape=[2, 7, 9, 9], kw=dict(padding=[1, 1, 1, 1], gain=4)),
     dict(name='nonsquare', shape=[2, 3, 40, 70], kw=dict(padding=[2, 2, 2, 2])),
@@ -311,6 +316,11 @@ def test_empty_and_degenerate_inputs(ops):
     assert rel_err(ops.up.downsample2d(x[:, :, :36, :40].contiguous(), f), O.downsample2d(x.cpu()[:, :, :36, :40], f.cpu())) < TOL
     g = torch.randn(4, 4, device=DEV)                               # a general (rank-4) 4x4 filter takes the non-separable path of the band kernel
     assert rel_err(ops.up.upfirdn2d(x, g, padding=[1, 2, 2, 1], flip_filter=True), O.upfirdn2d(x.cpu(), g.cpu(), padding=[1, 2, 2, 1], flip_filter=True)) < TOL
+    xu = torch.randn(2, 2, 24, 30, device=DEV)                      # ... and the polyphase up-2 band kernel has no rank-1 assumption at all
+    assert rel_err(ops.up.upfirdn2d(xu, g, up=2, padding=[2, 1, 1, 2], gain=3), O.upfirdn2d(xu.cpu(), g.cpu(), up=2, padding=[2, 1, 1, 2], gain=3)) < TOL
+    b = torch.randn(2, device=DEV)                                  # fused bias_act epilogue on the up-2 kernel
+    assert rel_err(ops.up.upfirdn2d_bias_act(xu, f, b, up=2, padding=[2, 1, 2, 1], gain=4, act='lrelu', clamp=1.5),
+                   O.bias_act(O.upfirdn2d(xu.cpu(), f.cpu(), up=2, padding=[2, 1, 2, 1], gain=4), b.cpu(), act='lrelu', clamp=1.5)) < TOL
     from pasta_gan_b200.torch_utils.ops import conv_igemm
     y = conv_igemm.conv2d_igemm(torch.randn(1, 16, 1, 1, device=DEV), torch.randn(8, 16, 3, 3, device=DEV))    # 1x1 image, 3x3 kernel
     assert y.shape == (1, 8, 1, 1)

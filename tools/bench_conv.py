@@ -48,7 +48,21 @@ def main():
             x = torch.randn(N, cin, res, res, device=dev)
             w = torch.randn(cout, cin, k, k, device=dev) / (cin * k * k) ** 0.5
             flops = 2 * N * cout * cin * k * k * res * res
+            exec_flops = flops * (4 if up == 2 else 1)
             ours = lambda: conv_igemm.conv2d_igemm(x, w, f=f if up == 2 else None, up=up, flip_weight=(up == 1))
+            t_tma = t_tma_o = t_psw = None
+            if conv_igemm.c8_input_ok(cin, res, res, k, up):
+                # channel-blocked fp16 input loaded by TMA (no converter warps); and with a channel-blocked output as well
+                xc = conv_igemm.to_c8(x)
+                t_tma = timeit(lambda: conv_igemm.conv2d_igemm(xc, w, f=f if up == 2 else None, up=up, flip_weight=(up == 1)))
+                if up == 1 and cout % 16 == 0:
+                    t_tma_o = timeit(lambda: conv_igemm.conv2d_igemm(xc, w, out_c8=True))
+                del xc
+            if cin * cout * k * k * N * 2 <= 64e6:
+                # groups = N form (per-sample weights, packed per call): the reference's fused modulated conv through conv2d_resample
+                wn = w.unsqueeze(0).repeat(N, 1, 1, 1, 1)
+                t_psw = timeit(lambda: conv_igemm.conv2d_igemm(x, wn, f=f if up == 2 else None, up=up, flip_weight=(up == 1), per_sample_weights=True))
+                del wn
             conv_igemm.enabled = False
             lib = lambda: conv2d_resample.conv2d_resample(x, w, f=f, up=up, padding=k // 2, flip_weight=(up == 1))
             t_ours = timeit(ours)
@@ -58,9 +72,10 @@ def main():
             t_fp32 = timeit(lib)
             torch.backends.cudnn.allow_tf32 = True
             conv_igemm.enabled = True
-            exec_flops = flops * (4 if up == 2 else 1)
             line = dict(cin=cin, cout=cout, res=res, k=k, up=up, N=N, gflop=round(flops / 1e9, 2),
                         ours_us=round(t_ours * 1e6, 1), cudnn_tf32_us=round(t_tf32 * 1e6, 1), cudnn_fp32_us=round(t_fp32 * 1e6, 1),
+                        tma_us=None if t_tma is None else round(t_tma * 1e6, 1), tma_c8out_us=None if t_tma_o is None else round(t_tma_o * 1e6, 1),
+                        tma_tflops=None if t_tma is None else round(exec_flops / t_tma / 1e12, 1), groupsN_us=None if t_psw is None else round(t_psw * 1e6, 1),
                         ours_tflops=round(flops / t_ours / 1e12, 1), ours_executed_tflops=round(exec_flops / t_ours / 1e12, 1),
                         frac_of_bf16_peak=round(exec_flops / t_ours / 1e12 / peak, 3), speedup_vs_tf32=round(t_tf32 / t_ours, 2))
             lines.append(line)
