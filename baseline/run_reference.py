@@ -222,9 +222,15 @@ def main():
                     '\nfrom pasta_gan_b200.networks import modulated_conv2d\n'
             return meta
         buf = io.BytesIO()
-        pickle.dump(dict(G_ema=G), buf)
+        D_small = R_net.Discriminator(c_dim=512, img_resolution=256, img_channels=3, channel_base=1024, channel_max=32, num_fp16_res=3, conv_clamp=256)
+        pickle.dump(dict(G=G, D=D_small, G_ema=G), buf)       # the snapshot layout of training_loop_wo_flow_fullbody.py:587-602
         buf.seek(0)
-        G = legacy.load_network_pkl(buf)['G_ema'].eval().requires_grad_(False)
+        real = torch.version.cuda
+        torch.version.cuda = '11.0'                      # the pickled module source is exec'd again on load (persistence.py:216-227)
+        try:
+            G = legacy.load_network_pkl(buf)['G_ema'].eval().requires_grad_(False)
+        finally:
+            torch.version.cuda = real
         out['hooked'] = 'pasta_gan_b200' in sys.modules
     G = G.to(device)
     if overlay:

@@ -196,7 +196,7 @@ typedef struct pg_conv_args {
     uint32_t struct_bytes;
     int32_t  N, Cin, Cout, H, W, ksize, up;
     const void* x;  int32_t x_dtype, x_layout;
-    const void* x2; int32_t cin1, reserved0;
+    const void* x2; int32_t cin1, residual_layout;   /* residual_layout: PG_LAYOUT_NCHW (float32) or PG_LAYOUT_C8 (float16, Cout % 16 == 0) */
     const void* wpack; int64_t wpack_sample_stride;
     const float* styles; const float* dcoefs; const float* noise; int64_t noise_batch_stride; const float* bias; const float* residual;
     void* y; int32_t y_dtype, y_layout;

@@ -61,7 +61,7 @@ class ConvArgs(ctypes.Structure):
         ('struct_bytes', ctypes.c_uint32),
         ('N', c_i32), ('Cin', c_i32), ('Cout', c_i32), ('H', c_i32), ('W', c_i32), ('ksize', c_i32), ('up', c_i32),
         ('x', c_ptr), ('x_dtype', c_i32), ('x_layout', c_i32),
-        ('x2', c_ptr), ('cin1', c_i32), ('reserved0', c_i32),
+        ('x2', c_ptr), ('cin1', c_i32), ('residual_layout', c_i32),
         ('wpack', c_ptr), ('wpack_sample_stride', c_i64),
         ('styles', c_ptr), ('dcoefs', c_ptr), ('noise', c_ptr), ('noise_batch_stride', c_i64), ('bias', c_ptr), ('residual', c_ptr),
         ('y', c_ptr), ('y_dtype', c_i32), ('y_layout', c_i32),

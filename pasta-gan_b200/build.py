@@ -55,8 +55,12 @@ def nvcc_path():
     return 'nvcc'
 
 
-def build(force=False, verbose=False):
-    """Compile every .cu under csrc/ for sm_100a and link libpasta_b200.so.  Returns the library path."""
+def build(force=False, verbose=False, debug=False):
+    """Compile every .cu under csrc/ for sm_100a and link libpasta_b200.so.  Returns the library path.
+    ``debug``: a second library, lib/libpasta_b200_dbg.so, compiled with -DPG_DEBUG (per-CTA phase timestamps, load / store suppression and the
+    loader experiments of tools/conv_timeline.py; results may be wrong by design) — never loaded unless PASTA_B200_LIB points at it."""
+    if debug:
+        return _build_debug(verbose)
     if not force and is_current():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
@@ -83,5 +87,16 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def _build_debug(verbose=False):
+    os.makedirs(LIBDIR, exist_ok=True)
+    nvcc = nvcc_path()
+    out = os.path.join(LIBDIR, 'libpasta_b200_dbg.so')
+    cmd = [nvcc] + NVCC_FLAGS + ['-DPG_DEBUG', '-shared', '-o', out] + sources() + ['-lcudart_static', '-lpthread', '-ldl', '-lrt']
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f'debug build failed:\n{r.stdout}\n{r.stderr}')
+    return out
+
+
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv))
+    print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv, debug='--debug' in sys.argv))

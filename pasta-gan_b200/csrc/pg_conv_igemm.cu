@@ -66,6 +66,7 @@ struct ConvParams {
     uint32_t a_tx_bytes;                       // bytes one A box delivers (the stage itself is rounded up to 128 B)
     uint32_t a_lbo16;                          // A descriptor leading-dimension byte offset >> 4 (distance between the two 8-channel planes of a stage)
     int y_c8, cb_out;                          // y is fp16 channel-blocked [N][cb_out][H][W][8]
+    int res_c8;                                // the residual is fp16 channel-blocked (same shape as a channel-blocked y)
     int vec2; uint32_t w_magic;   // aligned 8-byte loader (see the converter section); ceil(2^32 / W)
     uint32_t pw_magic;         // ceil(2^32 / PW): q / PW == umulhi(q, pw_magic) for the strip positions that occur
 };
@@ -651,6 +652,21 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const int n, 
         for (int i = 0; i < 16; i++) res[i] = 0.f;
         auto fetch_res = [&](int cc, float (&dst)[16]) {
             if (!p.residual || !ok || cc >= ncol_chunks) return;
+            if (p.res_c8) {
+                // channel-blocked fp16 residual: the chunk's 16 channels are two 16-byte rows at this pixel
+                const uint4* rb = reinterpret_cast<const uint4*>(p.residual) + ((size_t)n * p.cb_out + (size_t)(jn * p.BN + cc * 16) / 8) * HW + (size_t)h * p.Wimg + w;
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const uint4 q4 = __ldg(rb + (size_t)j * HW);
+                    const unsigned int wds[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&wds[e]));
+                        dst[8 * j + 2 * e] = f2.x; dst[8 * j + 2 * e + 1] = f2.y;
+                    }
+                }
+                return;
+            }
             size_t off, ystride; int oy, ox;
             const int nvalid = chunk_out(cc, off, ystride, oy, ox);
 #pragma unroll
@@ -1275,6 +1291,145 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_igemm_persistent_kernel(con
 }
 
 
+// ---------------------------------------------------------------------------------------------- persistent TMA kernel
+// Channel-blocked fp16 input (TMA operand path): no converter warps, so the whole CTA is three pipelines with nothing else in the way.
+//   warp 0      producer: per 16-channel chunk one A box (cp.async.bulk.tensor) and the chunk's weight slots (cp.async.bulk), rings run on across tiles
+//   warp 1      MMA issuer: tcgen05.mma into TMEM accumulator buffer (tile & 1); commits acc_full[buf] and goes straight on to the next tile
+//   warps 2..9  epilogue: wait acc_full[buf], drain TMEM (2 warps per lane quarter), arrive acc_empty[buf]
+// One CTA per SM walks tiles t = blockIdx.x, + gridDim.x, ... of the list (jn, n, band, tile); TMEM holds two accumulator buffers of NACC * BN <= 256
+// columns, so the epilogue of tile i overlaps the main loop of tile i + 1 and the per-CTA prologue (TMEM allocation, barrier setup, pipeline fill)
+// is paid once per SM instead of once per tile.
+constexpr int kTEpiWarps = 8;
+constexpr int kTThreads  = 64 + 32 * kTEpiWarps;
+
+__global__ void __launch_bounds__(kTThreads, 1) conv_igemm_tma_persistent_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ CUtensorMap tmap_a,
+                                                                                  const __grid_constant__ CUtensorMap tmap_a2) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const int BM = 128 * p.NACC;
+    const int HW = p.H * p.Wimg;
+    const int tiles_s = p.nbands * p.tiles_per_img;          // tiles of one (n-tile, sample)
+    const int tiles_n = p.N * tiles_s;                       // tiles of one n-tile
+    const int total = tiles_n * p.ntiles_n;
+    const int halo = (p.ks == 3) ? p.PW + 1 : 0;
+
+    uint8_t* a_base = smem;
+    uint8_t* b_base = a_base + (size_t)p.SA * p.a_stage_bytes;
+    float*   s_scale = reinterpret_cast<float*>(b_base + (size_t)p.SB * p.b_slot_bytes);      // [2][BN]
+    float*   s_shift = s_scale + 2 * p.BN;                                                     // [2][BN]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 2 * p.BN);
+    uint64_t* a_full = bars, *a_empty = bars + p.SA, *b_full = bars + 2 * p.SA, *b_empty = bars + 2 * p.SA + p.SB;
+    uint64_t* acc_full = bars + 2 * p.SA + 2 * p.SB, *acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < p.SA; i++) { mbar_init(smem_u32(&a_full[i]), 1); mbar_init(smem_u32(&a_empty[i]), 1); }
+        for (int i = 0; i < p.SB; i++) { mbar_init(smem_u32(&b_full[i]), 1); mbar_init(smem_u32(&b_empty[i]), 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), kTEpiWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+        if (p.tma_cb2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a2) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // tile list decode: t -> (jn, n, band, tile); first staged strip position q0 = m0 - halo, box row r0 = floor(q0 / PW)
+    auto decode = [&](int t, int& jn, int& n, int& band, int& m0) {
+        jn = t / tiles_n;
+        int r = t - jn * tiles_n;
+        n = r / tiles_s; r -= n * tiles_s;
+        band = r / p.tiles_per_img;
+        m0 = (r - band * p.tiles_per_img) * BM;
+    };
+
+    if (warp == 0) {
+        // ===================== producer =====================
+        if (lane == 0) {
+            const int spc = p.ntaps / p.tps;                   // weight slots per chunk
+            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                int jn, n, band, m0;
+                decode(t, jn, n, band, m0);
+                const int q0 = m0 - halo;
+                const int r0 = q0 >= 0 ? q0 / p.PW : -((-q0 + p.PW - 1) / p.PW);
+                const int col0 = p.band_tw ? 2 * (band * p.band_tw - 2) : 0;
+                const uint8_t* wsrc = (const uint8_t*)p.wpack + (size_t)n * p.wpack_sample_stride + (size_t)jn * p.nchunks * p.ntaps * p.b_tile_bytes;
+                for (int ci = 0; ci < p.nchunks; ci++) {
+                    mbar_wait(smem_u32(&a_empty[sa]), pa ^ 1);
+                    mbar_expect_tx(smem_u32(&a_full[sa]), p.a_tx_bytes);
+                    const int cb = 2 * ci;
+                    if (cb < p.tma_cb) tma_load_3d(smem_u32(a_base + (size_t)sa * p.a_stage_bytes), &tmap_a, col0, r0, n * p.tma_cb + cb, smem_u32(&a_full[sa]));
+                    else               tma_load_3d(smem_u32(a_base + (size_t)sa * p.a_stage_bytes), &tmap_a2, col0, r0, n * p.tma_cb2 + cb - p.tma_cb, smem_u32(&a_full[sa]));
+                    if (++sa == p.SA) { sa = 0; pa ^= 1; }
+                    for (int g = 0; g < spc; g++) {
+                        mbar_wait(smem_u32(&b_empty[sb]), pb ^ 1);
+                        mbar_expect_tx(smem_u32(&b_full[sb]), p.b_slot_bytes);
+                        bulk_g2s(smem_u32(b_base + (size_t)sb * p.b_slot_bytes), wsrc + (size_t)(ci * spc + g) * p.b_slot_bytes, p.b_slot_bytes, smem_u32(&b_full[sb]));
+                        if (++sb == p.SB) { sb = 0; pb ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t issue = elect_one();
+        const uint32_t ab = smem_u32(a_base), bb = smem_u32(b_base), af = smem_u32(a_full), ae = smem_u32(a_empty), bf = smem_u32(b_full),
+                       be = smem_u32(b_empty);
+        const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+        MmaRing ring = {0, 0, 0u, 0u};
+        int it = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, it++) {
+            int jn, n, band, m0;
+            decode(t, jn, n, band, m0);
+            const int q0 = m0 - halo;
+            const int r0 = q0 >= 0 ? q0 / p.PW : -((-q0 + p.PW - 1) / p.PW);
+            const uint32_t a_off16 = (uint32_t)(q0 - r0 * p.PW);
+            const int buf = it & 1;
+            mbar_wait(smem_u32(&acc_empty[buf]), (((uint32_t)it >> 1) & 1u) ^ 1u);       // the epilogue has drained this buffer (tile it - 2)
+            tc_fence_after();
+            const uint32_t accf = smem_u32(&acc_full[buf]), tacc = tb + (uint32_t)buf * 256u;
+#define PG_ISSUE(KS_, NACC_) mma_issue_loop<KS_, NACC_>(p, ab, bb, af, ae, bf, be, accf, tacc, issue, ring, a_off16)
+            if (p.ks == 3) { if (p.NACC == 2) PG_ISSUE(3, 2); else PG_ISSUE(3, 1); }
+            else           { if (p.NACC == 2) PG_ISSUE(1, 2); else PG_ISSUE(1, 1); }
+#undef PG_ISSUE
+        }
+    } else {
+        // ===================== epilogue warps =====================
+        const int ew = warp - 2;                                      // 0..7: TMEM lane quarter warp & 3, column part ew >> 2
+        const int et = (int)threadIdx.x - 64;
+        int it = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, it++) {
+            int jn, n, band, m0;
+            decode(t, jn, n, band, m0);
+            const int buf = it & 1;
+            float* sc = s_scale + buf * p.BN; float* sh = s_shift + buf * p.BN;
+            // buffer `buf` of the constants was last read for tile it - 2; every epilogue warp finished that tile before it arrived on acc_empty and
+            // passed the named barrier of tile it - 1, so it is free to overwrite
+            stage_epilogue_constants(p, n, jn, sc, sh, et, 32 * kTEpiWarps);
+            asm volatile("bar.sync 2, %0;" ::"r"(32 * kTEpiWarps) : "memory");
+            mbar_wait(smem_u32(&acc_full[buf]), ((uint32_t)it >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + (uint32_t)buf * 256u;
+            if (p.up2_pair) epilogue_tile_up2_pair(p, n, jn, m0, HW, tacc, sc, sh, warp & 3, ew >> 2, kTEpiWarps / 4, lane, band);
+            else            epilogue_tile(p, n, jn, m0, HW, tacc, sc, sh, warp & 3, ew >> 2, kTEpiWarps / 4, lane, band);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 struct ConvPlan {
     int BN, ntiles_n, nchunks, ntaps, NACC, PW, Lp, tiles_per_img, PA, SA, SB, tps;
@@ -1287,7 +1442,7 @@ static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 // Plan / loader choices that were measured against each other.  Defaults are the measured best; the environment is read ONCE, when
 // the library is first used, and pg_set_tuning() changes a value for the rest of the process (tests and tools/ compare variants through it).
 struct Tuning {
-    int bands = 1, band_tw = 64, band_minw = 128, band_ratio10 = 0, persist = 0, nacc = 0, pair = 1, vec2 = 1, lean = 1, cgroups = 1, tma = 1;
+    int bands = 1, band_tw = 64, band_minw = 128, band_ratio10 = 0, persist = 0, nacc = 0, pair = 1, vec2 = 1, lean = 1, cgroups = 1, tma = 1, tma_persist = 1;
 #ifdef PG_DEBUG
     int pipe = 0, ldmode = 0, dbgmode = 0;
 #endif
@@ -1299,7 +1454,7 @@ static const TuningKey kTuningKeys[] = {
     {"conv_persist", "PASTA_B200_CONV_PERSIST", &Tuning::persist}, {"conv_nacc", "PASTA_B200_CONV_NACC", &Tuning::nacc},
     {"conv_pair", "PASTA_B200_CONV_PAIR", &Tuning::pair}, {"conv_vec2", "PASTA_B200_CONV_VEC2", &Tuning::vec2},
     {"conv_lean", "PASTA_B200_CONV_LEAN", &Tuning::lean}, {"conv_cgroups", "PASTA_B200_CONV_CGROUPS", &Tuning::cgroups},
-    {"conv_tma", "PASTA_B200_CONV_TMA", &Tuning::tma},
+    {"conv_tma", "PASTA_B200_CONV_TMA", &Tuning::tma}, {"conv_tma_persist", "PASTA_B200_CONV_TMA_PERSIST", &Tuning::tma_persist},
 #ifdef PG_DEBUG
     {"conv_pipe", "PASTA_B200_CONV_PIPE", &Tuning::pipe}, {"conv_ldmode", "PASTA_B200_CONV_LDMODE", &Tuning::ldmode},
     {"conv_dbgmode", "PASTA_B200_CONV_DBGMODE", &Tuning::dbgmode},
@@ -1314,7 +1469,8 @@ static Tuning& tuning() {
     return t;
 }
 
-static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int ks, int up2, bool band = false, int max_nacc = 4, bool tma = false, int n_tile = 0) {
+static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int ks, int up2, bool band = false, int max_nacc = 4, bool tma = false, int n_tile = 0,
+                     int forced_nacc = 0) {
     const Tuning& tn = tuning();
     pl.nvirt = up2 ? 4 * Cout : Cout;
     pl.ntaps = ks * ks;
@@ -1330,7 +1486,7 @@ static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int k
     // Two co-resident CTAs per SM when the N tile is narrow (BN <= 128): each gets half of TMEM (256 columns) and ~100 KB of shared
     // memory, so one CTA's prologue / pipeline fill / epilogue overlaps the other's main loop.  Wide tiles (BN = 256) keep the SM alone.
     bool pair = bn <= 128;
-    const int force_nacc = tn.nacc;
+    const int force_nacc = forced_nacc ? forced_nacc : tn.nacc;
     if (tn.pair == 0 || force_nacc * bn > 256) pair = false;
     const int tmem_budget = pair ? 256 : 512;
     const int max_acc = tmem_budget / bn < max_nacc ? tmem_budget / bn : max_nacc;
@@ -1522,8 +1678,11 @@ static int conv_run_impl(const pg_conv_args& a) {
         PG_REQUIRE(!x2 || (a.cin1 % 16 == 0 && ((uintptr_t)x2 & 15) == 0), "conv2d_igemm: a channel-blocked split input needs Cin1 %% 16 == 0 (x2 is channel-blocked float16 too)");
     }
     if (a.y_layout == PG_LAYOUT_C8)
-        PG_REQUIRE(a.y_dtype == PG_F16 && (up != 2 || Cout <= 128) && !a.residual && (a.spade_x ? (Cout / 2) % 16 == 0 : Cout % 16 == 0) && ((uintptr_t)a.y & 15) == 0,
-                   "conv2d_igemm: a channel-blocked output needs float16, no residual, Cout %% 16 == 0 (and Cout <= 128 with up-2)");
+        PG_REQUIRE(a.y_dtype == PG_F16 && (up != 2 || Cout <= 128) && (!a.residual || a.residual_layout == PG_LAYOUT_C8) &&
+                   (a.spade_x ? (Cout / 2) % 16 == 0 : Cout % 16 == 0) && ((uintptr_t)a.y & 15) == 0,
+                   "conv2d_igemm: a channel-blocked output needs float16, Cout %% 16 == 0 (and Cout <= 128 with up-2); a residual added to it must be channel-blocked too");
+    PG_REQUIRE(a.residual_layout == PG_LAYOUT_NCHW || (a.residual_layout == PG_LAYOUT_C8 && Cout % 16 == 0 && up != 2 && !a.spade_x && ((uintptr_t)a.residual & 15) == 0),
+               "conv2d_igemm: a channel-blocked residual needs Cout %% 16 == 0 and no up-sampling");
     if (tma && ksize == 1 && W > 128) {
         // a 1x1 convolution does not care how H * W pixels are cut into rows: view a wide image as rows of 128 pixels so that a row fits one TMA box
         PG_REQUIRE(W % 128 == 0, "conv2d_igemm: a channel-blocked input of a 1x1 layer wider than 128 columns needs W %% 128 == 0");
@@ -1601,6 +1760,7 @@ static int conv_run_impl(const pg_conv_args& a) {
                             "conv2d_igemm_spade: every N tile must hold [gamma_t | beta_t] of whole 16-channel groups (2C = %d, tile %d)", Cout, pl.BN);
     p.tma_a = tma; p.tma_rows = pl.tma_rows; p.tma_cb = (x2 ? a.cin1 : cin_real) / 8; p.tma_cb2 = (tma && x2) ? (cin_real - a.cin1) / 8 : 0; p.a_lbo16 = pl.a_lbo16; p.a_tx_bytes = (uint32_t)(2 * pl.tma_rows * pl.PW * 16);
     p.y_c8 = a.y_layout == PG_LAYOUT_C8; p.cb_out = (p.spade ? Cout / 2 : Cout) / 8;
+    p.res_c8 = (a.residual && a.residual_layout == PG_LAYOUT_C8) ? 1 : 0;
 #ifdef PG_DEBUG
     p.dbg = g_conv_dbg; p.pipe = tn.pipe; p.ldmode = tn.ldmode; p.dbgmode = tn.dbgmode;
 #endif
@@ -1623,7 +1783,7 @@ static int conv_run_impl(const pg_conv_args& a) {
         if (p.vec2 && (p.lean || p.in_half) && cg == 2 && (nt + kConvWarps / 2 - 1) / (kConvWarps / 2) <= 6) p.cgroups = 2;
         if (p.vec2 && p.lean && !p.in_half && p.cgroups == 1 && (nt + kConvWarps - 1) / kConvWarps > 6) p.lean = 0;
     }
-    PG_REQUIRE(!(p.out_half && a.residual), "conv2d_igemm: the residual add is not available with a float16 output");
+    PG_REQUIRE(!(p.out_half && a.residual && !p.y_c8), "conv2d_igemm: the residual add is not available with a dense float16 output");
     p.ntiles_n = pl.ntiles_n;
     CUtensorMap tmap, tmap2;
     memset(&tmap, 0, sizeof(tmap));
@@ -1658,6 +1818,42 @@ static int conv_run_impl(const pg_conv_args& a) {
                 const unsigned gridp = (unsigned)(total_tiles < kNumSMs ? total_tiles : kNumSMs);
                 pk<<<gridp, kPThreads, smem_p, s>>>(p);
                 return launch_status("conv2d_igemm(persistent)", 1);
+            }
+        }
+    }
+    if (tma && tn.tma_persist) {
+        // persistent TMA kernel: one CTA per SM, two TMEM accumulator buffers of <= 256 columns.  Re-plan the strip length for that budget.
+        ConvPlan pp;
+        const int wband = band_tw ? kBandTW + 4 : W;
+        const long long nimg = (long long)N * nbands;
+        // accumulators per buffer: as many as fit 256 columns (<= 2 keeps the staged box small), fewer if the image is shorter
+        int nacc = 256 / pl.BN; if (nacc > 2) nacc = 2; if (nacc < 1) nacc = 1;
+        const int prc = make_plan(pp, (int)nimg, Cin, Cout, H, wband, ksize, up == 2, band_tw != 0, 2, true, n_tile, nacc);
+        if (prc == PG_OK && pp.NACC * pp.BN <= 256 && pp.BN == pl.BN) {
+            const long long total_tiles = nimg * pp.tiles_per_img * pp.ntiles_n;
+            const size_t fixed_p = (size_t)4 * pp.BN * 4 + (size_t)(2 * 8 + 2 * 24 + 4) * 8 + 64;
+            const size_t budget = 200 * 1024;
+            int SA = 6;
+            while (SA > 2 && (size_t)SA * pp.a_stage + 3 * (size_t)pp.b_slot + fixed_p + 128 > budget) SA--;
+            const size_t used = (size_t)SA * pp.a_stage + fixed_p + 128;
+            int SB = used < budget ? (int)((budget - used) / pp.b_slot) : 0;
+            if (SB > 24) SB = 24;
+            if (SB >= 2 && total_tiles < (1ll << 30) && 2 * pp.PW <= 256 && pp.tma_rows <= 256) {
+                ConvParams q = p;
+                q.PW = pp.PW; q.Lp = pp.Lp; q.tiles_per_img = pp.tiles_per_img; q.NACC = pp.NACC; q.PA = pp.PA;
+                q.a_stage_bytes = pp.a_stage; q.SA = SA; q.SB = SB;
+                q.tma_rows = pp.tma_rows; q.a_lbo16 = pp.a_lbo16; q.a_tx_bytes = (uint32_t)(2 * pp.tma_rows * pp.PW * 16);
+                q.pw_magic = (uint32_t)((0x100000000ull + (uint64_t)pp.PW - 1) / (uint64_t)pp.PW);
+                CUtensorMap m1, m2;
+                memset(&m1, 0, sizeof(m1)); memset(&m2, 0, sizeof(m2));
+                rc = make_a_tensor_map(m1, x, N, q.tma_cb, H, Wimg, pp.PW, pp.tma_rows);
+                if (rc != PG_OK) return rc;
+                if (x2) { rc = make_a_tensor_map(m2, x2, N, q.tma_cb2, H, Wimg, pp.PW, pp.tma_rows); if (rc != PG_OK) return rc; }
+                const size_t smem_p = (size_t)SA * pp.a_stage + (size_t)SB * pp.b_slot + fixed_p + 128;
+                PG_CUDA(cudaFuncSetAttribute(conv_igemm_tma_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+                const unsigned gridp = (unsigned)(total_tiles < kNumSMs ? total_tiles : kNumSMs);
+                conv_igemm_tma_persistent_kernel<<<gridp, kTThreads, smem_p, s>>>(q, m1, m2);
+                return launch_status("conv2d_igemm(tma persistent)", 1);
             }
         }
     }

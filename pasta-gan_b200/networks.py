@@ -455,7 +455,7 @@ class Conv2dLayer(OpsModule):
         if layer is None:
             return None
         w = self.weight                                   # raw parameter: weight_gain is applied when the GEMM tiles are packed
-        b = self.bias.float() if self.bias is not None else None
+        b = self.bias.to(torch.float32 if x.ndim == 5 else x.dtype) if self.bias is not None else None
         clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
         kw = dict(f=self.resample_filter, up=self.up, down=self.down, padding=self.padding, flip_weight=(self.up == 1),
                   w_scale=float(self.weight_gain), cache_weights=True, x2=x2, residual=residual)
@@ -571,7 +571,7 @@ class SynthesisLayer(OpsModule):
         layer = getattr(self.ops, 'modconv_layer', None)
         if layer is not None:
             return layer(x, self.weight, styles, noise=noise, up=self.up, padding=self.padding, resample_filter=self.resample_filter,
-                         flip_weight=(self.up == 1), fused_modconv=fused_modconv, bias=self.bias.float(), act=self.activation,
+                         flip_weight=(self.up == 1), fused_modconv=fused_modconv, bias=self.bias.to(torch.float32 if x.ndim == 5 else x.dtype), act=self.activation,
                          act_gain=self.act_gain * gain, clamp=clamp, dcoefs=dcoefs, styles_normalized=normalized, **(dict(out_c8=True) if out_c8 else {}))
         x = self.ops.modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=noise, up=self.up, padding=self.padding,
                                       resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv)

@@ -125,7 +125,7 @@ def from_c8(x, channels=None, dtype=torch.float32):
 
 
 class _PackEntry:
-    __slots__ = ('wref', 'version', 'ptr', 'f', 'f_version', 'ws', 'event', 'stream', 'cfg')
+    __slots__ = ('wref', 'version', 'ptr', 'f', 'f_version', 'ws', 'event', 'stream', 'cfg', 'synced')
 
 
 _pack_store = {}          # (id(w), cfg) -> _PackEntry
@@ -184,14 +184,17 @@ def _packed_weights(capi, w, f, w_scale, mode, flip_weight, fmt_code, cache, n_t
         _run_prepack(capi, w, f, w_scale, mode, flip_weight, fmt_code, e.ws, n_tile=n_tile)
         e.version, e.ptr = w._version, w.data_ptr()
         e.f, e.f_version = (None, None) if mode == 1 else (f, f_ver)
-        e.stream = cur
+        e.stream, e.synced = cur, {cur.cuda_stream}
         if not torch.cuda.is_current_stream_capturing():
             e.event = torch.cuda.Event()
             e.event.record(cur)
         else:
             e.event = None
-    elif e.stream != cur and e.event is not None:
-        cur.wait_event(e.event)                           # packed on another stream: order this consumer after the pack
+    elif cur.cuda_stream not in e.synced and e.event is not None and not torch.cuda.is_current_stream_capturing():
+        # packed on another stream: order this consumer (and everything later on its stream) after the pack -- once per stream.  Not while capturing:
+        # a graph is always preceded by an eager warm-up on the same stream, which has done the wait
+        cur.wait_event(e.event)
+        e.synced.add(cur.cuda_stream)
     return e.ws
 
 
@@ -200,18 +203,26 @@ def refresh_packed_weights(device=None):
     CUDA graphs captured earlier read the new weights on their next replay.  Returns the number of re-packed entries."""
     capi = _backend.capi()
     done = 0
+    if device is not None:
+        device = torch.device(device)
+        if device.type == 'cuda' and device.index is None:
+            device = torch.device('cuda', torch.cuda.current_device())
     for hit in _cat_cache.values():                       # [gamma ; beta] concatenations first: rebuilt in place, their packed copies follow below
         done += _refresh_cat(hit)
     for (wid, _cfg), e in list(_pack_store.items()):
         w = e.wref()
-        if w is None or (device is not None and w.device != torch.device(device)):
+        if w is None or (device is not None and w.device != device):
             continue
-        if e.version != w._version or e.ptr != w.data_ptr():
+        f_moved = e.f is not None and e.f_version != (e.f.data_ptr(), e.f._version)
+        if e.version != w._version or e.ptr != w.data_ptr() or f_moved:
             mode, flip_weight, fmt_code, w_scale, n_tile = e.cfg
             with torch.cuda.device(w.device):
                 _run_prepack(capi, w, e.f, w_scale, mode, flip_weight, fmt_code, e.ws, n_tile=n_tile)
             e.version, e.ptr = w._version, w.data_ptr()
+            if e.f is not None:
+                e.f_version = (e.f.data_ptr(), e.f._version)
             e.stream = torch.cuda.current_stream(w.device)
+            e.synced = {e.stream.cuda_stream}
             e.event = torch.cuda.Event()
             e.event.record(e.stream)
             done += 1
@@ -264,7 +275,7 @@ def conv2d_igemm(x, w, f=None, up=1, down=1, flip_weight=True, styles=None, dcoe
     elif x.dtype == torch.float16:
         assert styles is None and in_act == 'linear' and in_gain == 1.0 and half_input_ok(x, w, up, down, x2), 'float16 input: plain stride-1 layer only'
     if out_c8:
-        assert cout % 16 == 0 and (up == 1 or cout <= 128) and residual is None
+        assert cout % 16 == 0 and (up == 1 or cout <= 128) and (residual is None or is_c8(residual))
         y = torch.empty([n, cout // 8, oh, ow, 8], dtype=torch.float16, device=x.device)
     else:
         y = torch.empty([n, cout, oh, ow], dtype=out_dtype, device=x.device)
@@ -293,8 +304,12 @@ def conv2d_igemm(x, w, f=None, up=1, down=1, flip_weight=True, styles=None, dcoe
         assert tuple(bias.shape) == (cout,)
     if mode != 1:
         f = f.to(torch.float32).contiguous()
+    res_c8 = residual is not None and is_c8(residual)
     if residual is not None:
-        assert residual.dtype == torch.float32 and residual.shape == y.shape
+        if res_c8:
+            assert tuple(residual.shape) == (n, cout // 8, oh, ow, 8) and cout % 16 == 0 and up == 1
+        else:
+            assert residual.dtype == torch.float32 and residual.shape == y.shape
         residual = residual.contiguous()
     fmt_code = _FMT[fmt or operand_format]
     with torch.cuda.device(x.device):
@@ -314,14 +329,14 @@ def conv2d_igemm(x, w, f=None, up=1, down=1, flip_weight=True, styles=None, dcoe
             wpack = _packed_weights(capi, w, f, w_scale, mode, flip_weight, fmt_code, cache_weights)
         # algorithmic FLOPs: output pixels for stride-1 / down-2, INPUT pixels for up-2 (zero-inserted taps excluded)
         sp = capi.span('conv_igemm', flops=2 * n * cout * cin * k * k * (oh * ow if up == 1 else h * wd),
-                       nbytes=x.element_size() * x.numel() + (x2.element_size() * x2.numel() if x2 is not None else 0) + 4 * ((y.numel() if residual is not None else 0) + w.numel()) + y.element_size() * y.numel(),
+                       nbytes=x.element_size() * x.numel() + (x2.element_size() * x2.numel() if x2 is not None else 0) + (residual.element_size() * residual.numel() if residual is not None else 0) + 4 * w.numel() + y.element_size() * y.numel(),
                        tag=f'{cin}->{cout} @{h}x{wd} k{k} mode{mode}' + (' mod' if styles is not None else '') + (' cat' if x2 is not None else '') + (' res' if residual is not None else '') +
                            (f' in_{in_act}' if in_act != 'linear' else '') + (' tma' if x_c8 else '') + (' psw' if sample_stride else '') + (' oc8' if out_c8 else ''))
         a = capi.ConvArgs()
         a.struct_bytes = _ARGS_BYTES
         a.N, a.Cin, a.Cout, a.H, a.W, a.ksize, a.up = n, cin, cout, h, wd, k, mode
         a.x, a.x_dtype, a.x_layout = capi.ptr(x), capi.dtype_code(x.dtype), capi.LAYOUT_C8 if x_c8 else capi.LAYOUT_NCHW
-        a.x2, a.cin1 = capi.ptr(x2), cin1
+        a.x2, a.cin1, a.residual_layout = capi.ptr(x2), cin1, (capi.LAYOUT_C8 if res_c8 else capi.LAYOUT_NCHW)
         a.wpack, a.wpack_sample_stride = capi.ptr(wpack), sample_stride
         a.styles, a.dcoefs, a.noise, a.noise_batch_stride, a.bias, a.residual = capi.ptr(styles), capi.ptr(dcoefs), capi.ptr(noise), nb_stride, capi.ptr(bias), capi.ptr(residual)
         a.y, a.y_dtype, a.y_layout = capi.ptr(y), capi.dtype_code(y.dtype), capi.LAYOUT_C8 if out_c8 else capi.LAYOUT_NCHW

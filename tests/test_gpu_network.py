@@ -103,13 +103,15 @@ def test_session_refresh_weights(cuda_generator):
     G = copy.deepcopy(cuda_generator)
     inp = procedural.synth_inputs(2, seed=5, device=DEV)
     sess = TryOnSession(G, inp, DEV, use_graph=True, warmup=1)
-    before = [o.clone() for o in sess.step()]
-    sess.synchronize()
+    sess.step()
+    sess.synchronize()                                     # the replay runs on the session's stream
+    before = [o.clone() for o in sess.out]
     sd = {k: (v * 1.05 if v.is_floating_point() and v.ndim >= 2 else v) for k, v in G.state_dict().items()}
     G.load_state_dict(sd)
     sess.refresh_weights()
-    after = [o.clone() for o in sess.step()]
+    sess.step()
     sess.synchronize()
+    after = [o.clone() for o in sess.out]
     with torch.no_grad():
         eager = G(**inp, noise_mode='const')
     assert rel_err(after[0], eager[0]) < 1e-5 and rel_err(after[2], eager[2]) < 1e-5

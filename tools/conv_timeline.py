@@ -3,11 +3,17 @@
 converter finish, epilogue.  usage: conv_timeline.py [--cin 128 --cout 128 --res 128 --k 3 --up 1 --n 16]"""
 import argparse, os, sys
 import torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+# the phase stamps exist only in the -DPG_DEBUG build of the library (pasta-gan_b200/build.py --debug); load that one in this process
+os.environ.setdefault('PASTA_B200_LIB', os.path.join(ROOT, 'pasta-gan_b200', 'lib', 'libpasta_b200_dbg.so'))
+if not os.path.exists(os.environ['PASTA_B200_LIB']):
+    import subprocess
+    subprocess.run([sys.executable, os.path.join(ROOT, 'pasta-gan_b200', 'build.py'), '--debug'], check=True)
 import pasta_gan_b200
 from pasta_gan_b200.torch_utils.ops import conv_igemm, upfirdn2d
 ap = argparse.ArgumentParser()
-for k, d in dict(cin=128, cout=128, res=128, k=3, up=1, n=16).items():
+for k, d in dict(cin=128, cout=128, res=128, k=3, up=1, n=16, tma=0).items():
     ap.add_argument('--' + k, type=int, default=d)
 a = ap.parse_args()
 dev = torch.device('cuda:0')
@@ -15,7 +21,8 @@ x = torch.randn(a.n, a.cin, a.res, a.res, device=dev)
 w = torch.randn(a.cout, a.cin, a.k, a.k, device=dev) / (a.cin * a.k * a.k) ** 0.5
 f = upfirdn2d.setup_filter([1, 3, 3, 1]).to(dev)
 lib = pasta_gan_b200.capi.load()
-run = lambda: conv_igemm.conv2d_igemm(x, w, f=f if a.up == 2 else None, up=a.up)
+xin = conv_igemm.to_c8(x) if a.tma else x
+run = lambda: conv_igemm.conv2d_igemm(xin, w, f=f if a.up == 2 else None, up=a.up)
 with torch.no_grad():
     for _ in range(3):
         run()
