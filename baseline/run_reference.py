@@ -184,6 +184,11 @@ def main():
     if args.mode in ('gpu', 'ops'):
         os.environ.setdefault('TORCH_CUDA_ARCH_LIST', '10.0')
         os.environ.setdefault('TORCH_EXTENSIONS_DIR', os.path.join(tempfile.gettempdir(), 'pasta_ref_plugins'))
+        # custom_ops.get_plugin builds with torch.utils.cpp_extension.load and then does importlib.import_module(name) (custom_ops.py:107-111); current
+        # torch no longer leaves the built module importable by name, so put the build directories on sys.path (environment, not a source change)
+        import torch.utils.cpp_extension as _ce
+        for _name in ('bias_act_plugin', 'upfirdn2d_plugin'):
+            sys.path.insert(0, _ce._get_build_directory(_name, verbose=False))
     R_net, legacy = import_reference(tree)
     import procedural
     device = 'cpu' if args.mode == 'cpu' else 'cuda'

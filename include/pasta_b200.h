@@ -221,6 +221,22 @@ int pg_conv2d_igemm_fwd(const float* x, const float* w, const float* fir, const 
                         int32_t act, float alpha, float gain, float clamp, int32_t operand_format,
                         void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * conv2d_wgrad — weight gradient of the stride-1 'same' convolution on tcgen05 / TMEM (k in {1, 3}):
+ *
+ *   dw[o, c, kh, kw] (+)= scale * sum_{n,h,w} dy[n, o, h, w] * x[n, c, h + kh - k/2, w + kw - k/2]
+ *
+ * Replaces the cuDNN call behind the reference's conv2d_gradfix weight gradient (torch_utils/ops/conv2d_gradfix.py:140-148,
+ * aten::cudnn_convolution_backward_weight).  x [N,Cin,H,W], dy [N,Cout,H,W] dense NCHW float32; dw [Cout,Cin,k,k] float32 in the layout of
+ * F.conv2d's weight (cross-correlation taps).  bf16 tensor-core operands (gradients need the exponent range), fp32 accumulation; the pixel
+ * dimension is split over CTAs and summed by a second kernel (deterministic, no atomics).  accumulate != 0 adds to dw instead of overwriting.
+ * workspace: at least pg_conv2d_wgrad_workspace_bytes(...) bytes, 16-byte aligned, caller-owned.
+ * The INPUT gradient of the same convolution needs no entry point of its own: it is pg_conv2d_igemm_* on dy with the weights transposed
+ * (Cin <-> Cout) and flip_weight = 0. */
+int64_t pg_conv2d_wgrad_workspace_bytes(int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t ksize);
+int pg_conv2d_wgrad(const float* x, const float* dy, float* dw, int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t ksize,
+                    float scale, int32_t accumulate, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* SPADE normalisation fused into the epilogue of the convolution that produces its modulation maps (reference Spade_Norm_Block.forward,
  * training/networks.py:4371-4379, plus the pre-activation of the Spade_Conv2dLayer that consumes the result, :4345-4349):
  *

@@ -46,6 +46,8 @@ SIGNATURES = {
     'pg_torgb_skip_c8': [c_ptr] * 7 + [c_i32] * 5 + [c_f32, c_ptr],
     'pg_conv2d_igemm_prepack_batched': [c_ptr, c_i64, c_ptr, c_i32, c_ptr, c_f32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr, c_i64, c_ptr],
     'pg_conv2d_igemm_launch': [c_ptr],
+    'pg_conv2d_wgrad_workspace_bytes': [c_i32] * 6,
+    'pg_conv2d_wgrad': [c_ptr, c_ptr, c_ptr] + [c_i32] * 6 + [c_f32, c_i32, c_ptr, c_i64, c_ptr],
     'pg_set_tuning': [ctypes.c_char_p, c_i32],
     'pg_masked_fill_c8': [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_ptr],
     'pg_nchw_to_c8': [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i32, c_ptr],
@@ -100,7 +102,7 @@ def load():
         for name, argtypes in SIGNATURES.items():
             fn = getattr(lib, name)                     # AttributeError if the symbol is not exported
             fn.argtypes = argtypes
-            fn.restype = {'pg_last_error': ctypes.c_char_p, 'pg_launch_count': c_i64, 'pg_conv2d_igemm_workspace_bytes': c_i64}.get(name, c_int)
+            fn.restype = {'pg_last_error': ctypes.c_char_p, 'pg_launch_count': c_i64, 'pg_conv2d_igemm_workspace_bytes': c_i64, 'pg_conv2d_wgrad_workspace_bytes': c_i64}.get(name, c_int)
         if lib.pg_abi_version() != 2:
             raise PastaB200Error(f'ABI mismatch: library reports {lib.pg_abi_version()}, binding expects 2')
         if hasattr(lib, 'pg_debug_set_buffer'):                      # -DPG_DEBUG builds only (tools/conv_timeline.py)

@@ -634,8 +634,22 @@ class ResBlock(OpsModule):
         self.skip = Conv2dLayer(in_channels, out_channels, kernel_size=1, bias=False, up=up, down=down,
                                 resample_filter=resample_filter, conv_clamp=conv_clamp)
 
-    def forward(self, x):
+    def forward(self, x, out_c8=False):
+        """Inference on the CUDA table: the tensors that only travel inside the block (conv0's result, and the skip branch when the input is already
+        channel-blocked) are channel-blocked fp16 and feed the next convolution by TMA; ``out_c8`` asks for a channel-blocked result as well."""
+        c8_ok = getattr(self.ops, 'c8_ok', None)
+        cout = int(self.conv1.weight.shape[0])
+        inner = False
+        if c8_ok is not None and x.is_cuda and not torch.is_grad_enabled() and self.conv0.up == 1 and cout % 16 == 0:
+            oh, ow = (int(x.shape[2]) // self.conv0.down, int(x.shape[3]) // self.conv0.down)
+            inner = bool(c8_ok(cout, oh, ow, 3))
+        if x.ndim == 5:
+            assert inner and self.conv0.down == 1, 'a channel-blocked input needs the channel-blocked chain (stride 1)'
+            y = self.skip(x, gain=np.sqrt(0.5), out_c8=True)
+            return self.conv1(self.conv0(x, out_c8=True), gain=np.sqrt(0.5), residual=y, out_c8=out_c8)
         y = self.skip(x, gain=np.sqrt(0.5))
+        if inner:
+            return self.conv1(self.conv0(x, out_c8=True), gain=np.sqrt(0.5), residual=y)
         return self.conv1(self.conv0(x), gain=np.sqrt(0.5), residual=y)          # y + conv1(...): the add rides in conv1's epilogue
 
 
@@ -893,7 +907,18 @@ class SynthesisNetworkFull(OpsModule):
                                            ResBlock(ngf, ngf, kernel_size=4, activation='relu'),
                                            ResBlock(ngf, ngf * 2, kernel_size=4, activation='relu', down=2))
 
-    def get_spade_feat(self, mask_256, denorm_mask, denorm_input, out=None):
+    def encode_garment(self, x):
+        """spade_encoder (7x7 conv + two ResBlocks, reference :5768-5771).  Inference on the CUDA table: the 7x7 layer hands the first ResBlock a
+        channel-blocked fp16 tensor, so that block's three convolutions load their operand by TMA and move half the bytes."""
+        enc = self.spade_encoder
+        c8_ok = getattr(self.ops, 'c8_ok', None)
+        c0 = int(enc[0].weight.shape[0])
+        if c8_ok is not None and x.is_cuda and not torch.is_grad_enabled() and os.environ.get('PASTA_B200_C8_CHAIN', '1') != '0' and \
+                c0 % 16 == 0 and c8_ok(c0, x.shape[2], x.shape[3], 3) and c8_ok(c0, x.shape[2], x.shape[3], 1):
+            return enc[2](enc[1](enc[0](x, out_c8=True)))
+        return enc(x)
+
+    def get_spade_feat(self, mask_256, denorm_mask, denorm_input, out=None, feat=None):
         """Garment features at 128 px; pixels the predicted mask covers but the source garment does not are filled with the
         garment's mean feature (reference :5777-5800).  ``out``: channel slice of the concatenated upper|lower tensor to write into
         (fused path: two streaming kernels instead of five elementwise passes and the torch.cat)."""
@@ -904,7 +929,7 @@ class SynthesisNetworkFull(OpsModule):
         denorm_mask_128 = binar(half(denorm_mask))
         valid = ((mask_128 + denorm_mask_128) == 2.0).to(mask_256.dtype)
         rest = mask_128 - valid
-        feat = self.spade_encoder(denorm_input * mask_256 - (1 - mask_256))
+        feat = self.encode_garment(denorm_input * mask_256 - (1 - mask_256)) if feat is None else feat
         fused = getattr(self.ops, 'masked_mean_fill', None)
         if fused is not None and out is not None:
             y = fused(feat, valid, rest, out)
@@ -964,15 +989,22 @@ class SynthesisNetworkFull(OpsModule):
         feat_dtype = torch.float16 if (half is not None and label.is_cuda and half(label[:, :, ::2, ::2])) else torch.float32   # read by conv_mlp only
         fh, fw = label.shape[2] // 2, label.shape[3] // 2
         c8_ok = getattr(self.ops, 'c8_ok', None)
+        m_up, m_lo = (label == 1).float(), (label == 2).float()
+        f_up = f_lo = None
+        if label.is_cuda and not torch.is_grad_enabled():
+            # one encoder pass over both garments (batch 2N): same weights, half the launches, fuller waves
+            binar = lambda t: (t > 0.9).to(t.dtype)
+            both = torch.cat([denorm_upper_input * binar(m_up) - (1 - binar(m_up)), denorm_lower_input * binar(m_lo) - (1 - binar(m_lo))], dim=0)
+            f_up, f_lo = self.encode_garment(both).chunk(2, dim=0)
         if c8_ok is not None and label.is_cuda and feat_dtype == torch.float16 and cf % 8 == 0 and c8_ok(2 * cf, fh, fw, 3):
             # channel-blocked fp16: the nine conv_mlp convolutions that read this tensor load it by TMA
             spade_feat = torch.empty([label.shape[0], 2 * cf // 8, fh, fw, 8], dtype=torch.float16, device=label.device)
-            self.get_spade_feat((label == 1).float(), denorm_upper_mask, denorm_upper_input, out=(spade_feat, 0))
-            self.get_spade_feat((label == 2).float(), denorm_lower_mask, denorm_lower_input, out=(spade_feat, cf // 8))
+            self.get_spade_feat(m_up, denorm_upper_mask, denorm_upper_input, out=(spade_feat, 0), feat=f_up)
+            self.get_spade_feat(m_lo, denorm_lower_mask, denorm_lower_input, out=(spade_feat, cf // 8), feat=f_lo)
         else:
             spade_feat = torch.empty([label.shape[0], 2 * cf, fh, fw], dtype=feat_dtype, device=label.device)
-            self.get_spade_feat((label == 1).float(), denorm_upper_mask, denorm_upper_input, out=spade_feat[:, :cf])      # upper | lower (:5831)
-            self.get_spade_feat((label == 2).float(), denorm_lower_mask, denorm_lower_input, out=spade_feat[:, cf:])
+            self.get_spade_feat(m_up, denorm_upper_mask, denorm_upper_input, out=spade_feat[:, :cf], feat=f_up)      # upper | lower (:5831)
+            self.get_spade_feat(m_lo, denorm_lower_mask, denorm_lower_input, out=spade_feat[:, cf:], feat=f_lo)
         x = x_128
         for k in (1, 2, 3):
             x = getattr(self, f'spade_b128_{k}')(x, spade_feat)

@@ -56,22 +56,36 @@ def conv_transpose2d(input, weight, bias=None, stride=1, padding=0, output_paddi
                                                 output_padding=output_padding, groups=groups, dilation=dilation)
 
 
-# Opt-in: run the stride-1 'same' 1x1 / 3x3 convolutions of the custom op (forward AND the input-gradient conv) on the tcgen05 kernel.
-# Off by default: at the training batch (4 per GPU) it measured 2x slower than cuDNN (weights are re-packed every step, tiles under-fill the
-# GPU) and fp16 operands cost ~1.5e-4 on D's logits; the training path keeps fp32 library convolutions until dgrad/wgrad kernels exist.
-tensor_core_forward = os.environ.get('PASTA_B200_TC_TRAIN', '0') == '1'
+# Training on the tensor cores: the stride-1 'same' 1x1 / 3x3 fp32 convolutions of the custom op run their forward, their input gradient (the same
+# tcgen05 kernel on dy with transposed, mirrored weights -- itself differentiable, which R1's double backward needs) and their weight gradient
+# (pg_conv2d_wgrad) on tcgen05 with bf16 operands and fp32 accumulation.  Everything else (strided / transposed-strided forms, fp16 blocks of the
+# discriminator, grouped convs) stays on the library path.  PASTA_B200_TC_TRAIN=0 switches it off (pure library convolutions).
+tensor_core_training = os.environ.get('PASTA_B200_TC_TRAIN', '1') != '0'
+tensor_core_format = os.environ.get('PASTA_B200_TC_TRAIN_FMT', 'bf16')
+# Layers below this many FLOPs per call stay on the library path: at the training batch (4 per GPU) a 512-channel layer at 4^2..32^2 is a few
+# microseconds of math behind a weight tensor that has to be re-packed every step (measured: 65.8 ms / step with every layer on tcgen05 vs 57.8 on
+# cuDNN TF32); the tensor cores pay where pixels, not weights, dominate (SPADE blocks, >= 64^2 layers).
+tensor_core_min_flops = float(os.environ.get('PASTA_B200_TC_TRAIN_MIN_GFLOP', '8')) * 1e9
+
+
+def _tc_ok(input, weight_shape, transpose, stride, padding, output_padding, dilation, groups):
+    if not (tensor_core_training and output_padding == (0, 0) and weight_shape[2] in (1, 3)):
+        return False
+    from . import conv_igemm
+    if not conv_igemm.grad_supported(input.shape, weight_shape, input.dtype, input.device, stride, padding, dilation, groups):
+        return False
+    flops = 2.0 * input.shape[0] * input.shape[2] * input.shape[3] * weight_shape[0] * weight_shape[1] * weight_shape[2] * weight_shape[3]
+    return flops >= tensor_core_min_flops
 
 
 def _forward(input, weight, bias, transpose, stride, padding, output_padding, dilation, groups):
     """Dense convolution of the custom autograd op.  Called with grad mode off (inside Function.forward), so the tensor-core kernel may be
     used for the shapes it covers: a stride-1 'same' conv, and the stride-1 transposed conv that is its input gradient
     (conv_transpose2d(x, w) == conv2d(x, w^T mirrored))."""
-    if tensor_core_forward and bias is None and groups == 1 and stride == (1, 1) and dilation == (1, 1) and output_padding == (0, 0) \
-            and input.dtype == torch.float32 and weight.shape[2] == weight.shape[3] and padding == (weight.shape[2] // 2,) * 2:
+    if bias is None and _tc_ok(input, weight.shape, transpose, stride, padding, output_padding, dilation, groups):
         from . import conv_igemm
         w = weight.transpose(0, 1) if transpose else weight
-        if conv_igemm.supported(input, w, padding=(padding[0],) * 4):
-            return conv_igemm.conv2d_igemm(input, w, flip_weight=not transpose)
+        return conv_igemm.conv2d_igemm(input, w, flip_weight=not transpose, fmt=tensor_core_format)
     if not transpose:
         return torch.nn.functional.conv2d(input, weight, bias, stride, padding, dilation, groups)
     return torch.nn.functional.conv_transpose2d(input, weight, bias, stride, padding, output_padding, groups, dilation)
@@ -112,6 +126,9 @@ class _ConvGradWeight(torch.autograd.Function):
         transpose, stride, padding, output_padding, dilation, groups = cfg
         ctx.save_for_backward(grad_output, input)
         ctx.cfg, ctx.weight_shape = cfg, weight_shape
+        if not transpose and grad_output.dtype == torch.float32 and _tc_ok(input, weight_shape, transpose, stride, padding, output_padding, dilation, groups):
+            from . import conv_igemm
+            return conv_igemm.conv2d_wgrad(input, grad_output, int(weight_shape[2]))
         dummy_w = input.new_empty(weight_shape)
         _, gw, _ = torch.ops.aten.convolution_backward(grad_output, input, dummy_w, None, list(stride), list(padding), list(dilation),
                                                        transpose, list(output_padding), groups, [False, True, False])

@@ -470,3 +470,45 @@ def spade_conv_norm(x, feat, w_gamma, w_beta, w_scale=1.0, act='linear', alpha=0
         if sp:
             sp.close()
     return y
+
+
+# ---------------------------------------------------------------------------------------------------------------- training: dgrad / wgrad
+
+def grad_supported(x_shape, w_shape, dtype, device, stride=(1, 1), padding=(0, 0), dilation=(1, 1), groups=1):
+    """Convolutions whose gradients the tcgen05 kernels cover: dense fp32 NCHW on CUDA, stride 1, 'same' padding, 1x1 / 3x3, groups 1."""
+    k = int(w_shape[2])
+    return (enabled and device.type == 'cuda' and dtype == torch.float32 and groups == 1 and tuple(stride) == (1, 1) and tuple(dilation) == (1, 1) and
+            int(w_shape[2]) == int(w_shape[3]) and k in (1, 3) and tuple(padding) == (k // 2, k // 2) and (k == 1 or int(x_shape[3]) <= 256) and
+            int(x_shape[0]) * int(x_shape[1]) * int(x_shape[2]) * int(x_shape[3]) < 2 ** 31 and int(x_shape[0]) > 0)
+
+
+def conv2d_dgrad(dy, w, fmt='bf16'):
+    """Input gradient of y = conv2d(x, w, padding=k//2): dx = conv2d(dy, w^T mirrored) -- the forward kernel on dy with Cin <-> Cout swapped and
+    flip_weight=False (true convolution).  bf16 operands by default: gradients need the exponent range."""
+    return conv2d_igemm(dy, w.transpose(0, 1), flip_weight=False, fmt=fmt)
+
+
+def conv2d_wgrad(x, dy, ksize, scale=1.0, out=None):
+    """Weight gradient of y = conv2d(x, w, padding=k//2) (pg_conv2d_wgrad): dw [Cout, Cin, k, k]; ``out``: accumulate into this tensor."""
+    capi = _backend.capi()
+    _backend.require_cuda(x, 'conv2d_wgrad')
+    x, dy = x.contiguous(), dy.contiguous()
+    n, cin, h, wd = (int(v) for v in x.shape)
+    cout = int(dy.shape[1])
+    assert x.dtype == torch.float32 and dy.dtype == torch.float32 and tuple(dy.shape) == (n, cout, h, wd)
+    lib = capi.load()
+    nbytes = int(lib.pg_conv2d_wgrad_workspace_bytes(n, cin, cout, h, wd, ksize))
+    if nbytes < 0:
+        capi.check(2, 'pg_conv2d_wgrad_workspace_bytes')
+    dw = out if out is not None else torch.empty([cout, cin, ksize, ksize], dtype=torch.float32, device=x.device)
+    assert dw.is_contiguous() and tuple(dw.shape) == (cout, cin, ksize, ksize)
+    with torch.cuda.device(x.device):
+        capi.require_device()
+        ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=x.device)
+        sp = capi.span('conv_wgrad', flops=2 * n * cout * cin * ksize * ksize * h * wd, nbytes=4 * (x.numel() + dy.numel() + dw.numel()), tag=f'{cin}->{cout} @{h}x{wd} k{ksize}')
+        rc = lib.pg_conv2d_wgrad(capi.ptr(x), capi.ptr(dy), capi.ptr(dw), n, cin, cout, h, wd, ksize, float(scale), int(out is not None),
+                                 capi.ptr(ws), nbytes, capi.current_stream(x.device))
+        capi.check(rc, 'pg_conv2d_wgrad')
+        if sp:
+            sp.close()
+    return dw

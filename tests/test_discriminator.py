@@ -35,14 +35,22 @@ def test_discriminator_parameters_and_forward_cpu(golden):
 
 
 @pytest.mark.gpu
-def test_discriminator_r1_double_backward_gpu(golden):
+@pytest.mark.parametrize('tensor_cores', [False, True], ids=['library_fp32', 'tcgen05_bf16'])
+def test_discriminator_r1_double_backward_gpu(golden, tensor_cores):
+    """The complete R1 chain (logits -> image gradient under no_weight_gradients -> penalty -> second-order parameter gradients) against the
+    reference's CPU run.  library_fp32: every convolution on the fp32 library path (tight bounds).  tcgen05_bf16: the stride-1 'same' fp32
+    convolutions run forward / dgrad / wgrad on the tcgen05 kernels with bf16 operands -- the north_star's 1e-2 class for tensor-core convolutions."""
     from pasta_gan_b200.torch_utils.ops import conv2d_gradfix
     g = golden('discriminator')
     meta = g.meta[0]
-    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, conv2d_gradfix.enabled)
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, conv2d_gradfix.enabled, conv2d_gradfix.tensor_core_training,
+           conv2d_gradfix.tensor_core_min_flops)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     conv2d_gradfix.enabled = True
+    conv2d_gradfix.tensor_core_training = tensor_cores
+    conv2d_gradfix.tensor_core_min_flops = 0                     # every eligible layer, whatever its size
+    tol = dict(logits=1e-2, grad=3e-2, pen=2e-2, params=3e-2) if tensor_cores else dict(logits=1e-4, grad=1e-2, pen=1e-3, params=1e-2)
     try:
         D = N.build_discriminator(num_fp16_res=0)
         procedural.fill_(D)
@@ -50,7 +58,7 @@ def test_discriminator_r1_double_backward_gpu(golden):
         img, c = _inputs('cuda')
         img.requires_grad_(True)
         logits = D(img, c)
-        assert rel_err(logits, g.t('logits')) < 1e-4
+        assert rel_err(logits, g.t('logits')) < tol['logits']
         with conv2d_gradfix.no_weight_gradients():
             r1_grad, = torch.autograd.grad(logits.sum(), img, create_graph=True)
         e_grad = rel_err(r1_grad[:, :, ::4, ::4], g.t('r1_grad'))
@@ -59,8 +67,8 @@ def test_discriminator_r1_double_backward_gpu(golden):
         print('r1 grad rel err', e_grad, 'penalty rel err', e_pen, 'penalty', penalty.tolist(), 'golden', g.t('penalty').tolist())
         # pointwise image gradient: ~20 fp32 convolutions deep in two different libraries (oneDNN vs cuDNN): 1e-2 max-abs; its norm (the R1
         # penalty) is held to 1e-3
-        assert e_grad < 1e-2
-        assert e_pen < 1e-3
+        assert e_grad < tol['grad']
+        assert e_pen < tol['pen']
         (penalty.mean() * 5).backward()
         params = dict(D.named_parameters())
         errs = {}
@@ -70,9 +78,10 @@ def test_discriminator_r1_double_backward_gpu(golden):
             got = gr if gr.numel() <= 70000 else gr.flatten()[::37]
             errs[name] = rel_err(got, ref)
         print('second-order parameter gradient rel errs', errs)
-        assert all(v < 1e-2 for v in errs.values()), errs
+        assert all(v < tol['params'] for v in errs.values()), errs
     finally:
-        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, conv2d_gradfix.enabled = old
+        (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, conv2d_gradfix.enabled, conv2d_gradfix.tensor_core_training,
+         conv2d_gradfix.tensor_core_min_flops) = old
 
 
 @pytest.mark.gpu

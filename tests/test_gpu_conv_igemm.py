@@ -539,3 +539,62 @@ def test_packed_weight_store_refreshes_in_place(cv):
     import gc
     gc.collect()
     assert len(cv._pack_store) == n0
+
+
+# ------------------------------------------------------------------------------------------------ training: tcgen05 dgrad / wgrad
+
+WGRAD = [(2, 32, 32, 16, 16, 3), (3, 48, 64, 20, 28, 3), (1, 128, 128, 64, 64, 3), (2, 64, 200, 33, 31, 3), (4, 20, 24, 12, 12, 3), (2, 3, 64, 40, 40, 1),
+         (2, 192, 128, 24, 24, 1), (1, 512, 512, 4, 4, 3), (2, 64, 64, 128, 128, 3), (1, 40, 16, 9, 256, 3)]
+
+
+@pytest.mark.parametrize('shape', WGRAD, ids=[str(s) for s in WGRAD])
+def test_wgrad_and_dgrad_vs_autograd(cv, shape):
+    """pg_conv2d_wgrad and the dgrad form of the forward kernel against fp64 autograd of F.conv2d on the same inputs.  bf16 operands, fp32
+    accumulation over up to N*H*W products: 1e-2 relative (max-abs / max-abs), the tolerance the north_star gives tensor-core convolutions."""
+    n, cin, cout, h, w, k = shape
+    torch.manual_seed(sum(shape))
+    x = torch.randn(n, cin, h, w)
+    wt = torch.randn(cout, cin, k, k) / (cin * k * k) ** 0.5
+    dy = torch.randn(n, cout, h, w) * 1e-3                       # gradient-like magnitudes
+    xr, wr = x.double().requires_grad_(True), wt.double().requires_grad_(True)
+    yr = torch.nn.functional.conv2d(xr, wr, padding=k // 2)
+    dx_ref, dw_ref = torch.autograd.grad(yr, [xr, wr], dy.double())
+    dw = cv.conv2d_wgrad(x.to(DEV), dy.to(DEV), k)
+    assert dw.shape == dw_ref.shape and rel_err(dw, dw_ref) < 1e-2
+    dx = cv.conv2d_dgrad(dy.to(DEV), wt.to(DEV))
+    assert dx.shape == dx_ref.shape and rel_err(dx, dx_ref) < 1e-2
+    acc = torch.ones_like(dw)
+    cv.conv2d_wgrad(x.to(DEV), dy.to(DEV), k, scale=2.0, out=acc)
+    assert rel_err(acc - 1, 2 * dw_ref) < 1e-2
+
+
+def test_conv2d_gradfix_trains_on_tensor_cores():
+    """conv2d_gradfix.conv2d under autograd: forward, input gradient, weight gradient and the double backward of R1 (grad of grad_input w.r.t. the
+    weights, under no_weight_gradients for the inner grad) run on the tcgen05 kernels for a stride-1 'same' fp32 convolution and match fp64
+    autograd within 1e-2; the launch counter proves the kernels ran."""
+    from pasta_gan_b200.torch_utils.ops import conv2d_gradfix as G
+    torch.manual_seed(3)
+    old = (G.enabled, G.tensor_core_training, G.tensor_core_min_flops)
+    G.enabled, G.tensor_core_training, G.tensor_core_min_flops = True, True, 0
+    try:
+        x = torch.randn(2, 32, 24, 24); w = torch.randn(48, 32, 3, 3) / 17
+        xg, wg = x.to(DEV).requires_grad_(True), w.to(DEV).requires_grad_(True)
+        xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+        l0 = capi.launch_count()
+        y = G.conv2d(xg, wg, padding=1)
+        yr = torch.nn.functional.conv2d(xr, wr, padding=1)
+        assert rel_err(y, yr) < 1e-2
+        dy = torch.randn_like(yr)
+        dx, dw = torch.autograd.grad(y, [xg, wg], dy.float().to(DEV), create_graph=True)
+        dxr, dwr = torch.autograd.grad(yr, [xr, wr], dy, create_graph=True)
+        assert rel_err(dx, dxr) < 1e-2 and rel_err(dw, dwr) < 1e-2
+        assert capi.launch_count() - l0 >= 6                      # 3 weight packs (fwd, dgrad) + fwd + dgrad + wgrad (+ reduce)
+        # R1-style second order: penalty = |dL/dx|^2, gradient w.r.t. the weights
+        with G.no_weight_gradients():
+            gx, = torch.autograd.grad(G.conv2d(xg, wg, padding=1).sum(), xg, create_graph=True)
+        gxr, = torch.autograd.grad(torch.nn.functional.conv2d(xr, wr, padding=1).sum(), xr, create_graph=True)
+        pw, = torch.autograd.grad(gx.square().sum(), wg)
+        pwr, = torch.autograd.grad(gxr.square().sum(), wr)
+        assert rel_err(pw, pwr) < 2e-2
+    finally:
+        G.enabled, G.tensor_core_training, G.tensor_core_min_flops = old
