@@ -79,7 +79,8 @@ def build(force=False, verbose=False, debug=False):
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, sources()))
-    r = subprocess.run([nvcc, '-shared', '-o', LIB] + objs + ['-lcudart_static', '-lpthread', '-ldl', '-lrt'], capture_output=True, text=True)
+    r = subprocess.run([nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', LIB] + objs + ['-lcudart_static', '-lpthread', '-ldl', '-lrt'],
+                       capture_output=True, text=True)      # (the arch flag also on the link line: without it nvcc adds an empty default-arch fatbin entry)
     if r.returncode != 0:
         raise RuntimeError(f'link failed:\n{r.stdout}\n{r.stderr}')
     with open(STAMP, 'w') as fh:

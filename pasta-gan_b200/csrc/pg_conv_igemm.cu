@@ -1528,6 +1528,8 @@ static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int k
     pl.b_slot = pl.b_tile * pl.tps;
     size_t budget = pair ? 100 * 1024 : 200 * 1024;
     pl.SA = 3;
+    // small strips (4^2 .. 16^2 images): the layer is a latency chain of nchunks (load chunk -> convert -> MMA) round trips, so run the ring deep
+    if (!tma && (size_t)8 * pl.a_stage <= budget / 4) pl.SA = 8;
     if ((size_t)pl.SA * pl.a_stage > budget / 2) pl.SA = 2;
     if ((size_t)pl.SA * pl.a_stage + 2 * (size_t)pl.b_slot + fixed + 128 > budget) budget = 200 * 1024;   // large strips: one CTA per SM after all
     if (pl.nchunks < pl.SA) pl.SA = pl.nchunks < 2 ? 2 : pl.nchunks;
@@ -1781,6 +1783,12 @@ static int conv_run_impl(const pg_conv_args& a) {
         const int cg = tn.cgroups;      // measured neutral (profiles/r1 notes in DESIGN.md): off by default
         const int pairs = (pl.PA + 3) / 2, nt = 2 * ((pairs + 31) / 32);
         if (p.vec2 && (p.lean || p.in_half) && cg == 2 && (nt + kConvWarps / 2 - 1) / (kConvWarps / 2) <= 6) p.cgroups = 2;
+        // tiny strips (<= 2 tasks per chunk): four groups of two warps take alternate chunks, so four chunks' load round trips are in flight
+        // (the in-kernel task count only covers real image elements: H * W / 64 tasks when the whole image is one tile)
+        if (p.vec2 && p.lean && !p.in_half && !band_tw && pl.SA >= 4 && tn.cgroups != 0 && p.cgroups == 1) {
+            if ((long long)H * W <= 128 && (nt + 1) / 2 <= 6) p.cgroups = 4;
+            else if ((long long)H * W <= 512 && (nt + 3) / 4 <= 6) p.cgroups = 2;
+        }
         if (p.vec2 && p.lean && !p.in_half && p.cgroups == 1 && (nt + kConvWarps - 1) / kConvWarps > 6) p.lean = 0;
     }
     PG_REQUIRE(!(p.out_half && a.residual && !p.y_c8), "conv2d_igemm: the residual add is not available with a dense float16 output");

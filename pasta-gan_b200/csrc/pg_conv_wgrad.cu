@@ -14,7 +14,7 @@
 //   * bf16 operands (gradients need the exponent range; 8-bit mantissa), fp32 accumulation in TMEM: taps x BN columns (9 x 48 = 432 of 512).
 //   * The K dimension is split over CTAs (a CTA owns a contiguous range of 128-position chunks over all samples); each CTA writes its partial
 //     [tap][o][c] block to a workspace with coalesced stores and a second kernel sums the splits into dW (deterministic, no atomics).
-//   * Warp roles: 8 converter warps (fp32 NCHW -> bf16 strip stage, later the epilogue), one MMA warp; a 2..3 stage mbarrier ring.
+//   * Warp roles: 16 converter warps (fp32 NCHW -> bf16 strip stage, four tasks of loads in flight each; later the epilogue), one MMA warp; a 2..3 stage mbarrier ring.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <string.h>
@@ -23,8 +23,9 @@
 namespace pg {
 namespace wg {
 
-constexpr int kWarps = 8;
-constexpr int kThreads = 32 + 32 * kWarps;       // warp 0: MMA issuer, warps 1..8: converters / epilogue
+constexpr int kWarps = 16;
+constexpr int kThreads = 32 + 32 * kWarps;       // warp 0: MMA issuer, warps 1..16: converters / epilogue
+constexpr int kBatch = 4;                        // converter tasks whose loads are issued together (32 independent 128-byte requests per warp in flight)
 constexpr int kChunk = 128;                      // strip positions per pipeline stage (8 MMA K steps of 16)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -80,14 +81,14 @@ struct Params {
     uint32_t dy_stage_bytes, x_stage_bytes, pw_magic, idesc;
 };
 
-// One task = 32 strip positions x 8 channels of `src` (fp32 NCHW planes of one sample) -> one 16-byte bf16 row per position in `dst_plane`.
-__device__ __forceinline__ void stage_task(const Params& p, const float* src_n, const int C, const int c0, const int q0, const int lane, uint8_t* dst_plane, const int slot0) {
+// One task = 32 strip positions x 8 channels of `src_n` (fp32 NCHW planes of one sample) -> one 16-byte bf16 row per position.  Loads and stores are
+// separate so that a warp can put the loads of kBatch tasks in flight before it converts the first one.
+__device__ __forceinline__ void task_load(const Params& p, const float* src_n, const int C, const int c0, const int q0, const int lane, float (&v)[8]) {
     const int HW = p.H * p.W;
     const int q = q0 + lane;
     bool ok = q >= 0 && q < p.Lp;
     int h = 0, w = 0;
     if (ok) { h = (int)__umulhi((uint32_t)q, p.pw_magic); w = q - h * p.PW; ok = w < p.W; }
-    float v[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) v[i] = 0.f;
     if (ok) {
@@ -95,9 +96,11 @@ __device__ __forceinline__ void stage_task(const Params& p, const float* src_n, 
 #pragma unroll
         for (int i = 0; i < 8; i++) if (c0 + i < C) v[i] = __ldg(s + (size_t)i * HW);
     }
+}
+__device__ __forceinline__ void task_store(const float (&v)[8], uint8_t* dst_plane, const int slot) {
     uint4 pk;
     pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]); pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(dst_plane + (size_t)(slot0 + lane) * 16) = pk;
+    *reinterpret_cast<uint4*>(dst_plane + (size_t)slot * 16) = pk;
 }
 
 __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_constant__ Params p) {
@@ -172,15 +175,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
             mbar_wait(smem_u32(&empty[st]), ph ^ 1);
             const float* dyn = p.dy + (size_t)n * p.Cout * p.H * p.W;
             const float* xn = p.x + (size_t)n * p.Cin * p.H * p.W;
-            for (int t = cw; t < dy_tasks + x_tasks; t += kWarps) {
-                if (t < dy_tasks) {
-                    const int plane = t / (kChunk / 32), g = t - plane * (kChunk / 32);
-                    stage_task(p, dyn, p.Cout, o0 + plane * 8, m0 + g * 32, lane, sdy + (size_t)plane * kChunk * 16, g * 32);
-                } else {
-                    const int tt = t - dy_tasks;
-                    const int plane = tt / (p.PAx / 32), g = tt - plane * (p.PAx / 32);
-                    stage_task(p, xn, p.Cin, c0 + plane * 8, m0 - p.halo + g * 32, lane, sx + (size_t)plane * p.PAx * 16, g * 32);
+            const int ntasks = dy_tasks + x_tasks;
+            for (int tb = cw; tb < ntasks; tb += kWarps * kBatch) {
+                float v[kBatch][8];
+                uint8_t* dst[kBatch]; int slot[kBatch];
+#pragma unroll
+                for (int u = 0; u < kBatch; u++) {
+                    const int t = tb + u * kWarps;
+                    dst[u] = nullptr; slot[u] = 0;
+                    if (t >= ntasks) continue;
+                    if (t < dy_tasks) {
+                        const int plane = t / (kChunk / 32), g = t - plane * (kChunk / 32);
+                        task_load(p, dyn, p.Cout, o0 + plane * 8, m0 + g * 32, lane, v[u]);
+                        dst[u] = sdy + (size_t)plane * kChunk * 16; slot[u] = g * 32 + lane;
+                    } else {
+                        const int tt = t - dy_tasks;
+                        const int plane = tt / (p.PAx / 32), g = tt - plane * (p.PAx / 32);
+                        task_load(p, xn, p.Cin, c0 + plane * 8, m0 - p.halo + g * 32, lane, v[u]);
+                        dst[u] = sx + (size_t)plane * p.PAx * 16; slot[u] = g * 32 + lane;
+                    }
                 }
+#pragma unroll
+                for (int u = 0; u < kBatch; u++) if (dst[u]) task_store(v[u], dst[u], slot[u]);
             }
             fence_proxy_async();
             __syncwarp();
@@ -221,15 +237,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
 // dW[o][c][tap] = sum_split partial[split][tap][o][c]   (taps in cross-correlation order: the gradient of F.conv2d's weight)
 __global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int ntaps, int Cout, int Cin,
                                                                 int cout_pad, int cin_pad, float scale, int accumulate) {
+    // thread order (tap, o, c) with c fastest: the reads of every split are coalesced; the (small) write to dw[o][c][tap] is strided
     const int total = Cout * Cin * ntaps;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        const int tap = idx % ntaps;
-        const int c = (idx / ntaps) % Cin;
-        const int o = idx / (ntaps * Cin);
-        float s = 0.f;
-        for (int sp = 0; sp < splits; sp++) s += __ldg(partial + (((size_t)sp * ntaps + tap) * cout_pad + o) * cin_pad + c);
-        s *= scale;
-        dw[idx] = accumulate ? dw[idx] + s : s;
+        const int c = idx % Cin;
+        const int o = (idx / Cin) % Cout;
+        const int tap = idx / (Cin * Cout);
+        const float* src = partial + ((size_t)tap * cout_pad + o) * cin_pad + c;
+        const size_t sstride = (size_t)ntaps * cout_pad * cin_pad;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int sp = 0;
+        for (; sp + 4 <= splits; sp += 4) {
+            s0 += __ldg(src + (size_t)sp * sstride); s1 += __ldg(src + (size_t)(sp + 1) * sstride);
+            s2 += __ldg(src + (size_t)(sp + 2) * sstride); s3 += __ldg(src + (size_t)(sp + 3) * sstride);
+        }
+        for (; sp < splits; sp++) s0 += __ldg(src + (size_t)sp * sstride);
+        const float s = ((s0 + s1) + (s2 + s3)) * scale;
+        float* d = dw + ((size_t)o * Cin + c) * ntaps + tap;
+        *d = accumulate ? *d + s : s;
     }
 }
 
@@ -254,9 +279,9 @@ static int make_plan(Plan& pl, int N, int Cin, int Cout, int H, int W, int ks) {
     while (pl.S > 2 && pl.S * stage + 256 > 200 * 1024) pl.S--;
     if (pl.S * stage + 256 > 220 * 1024) return fail(PG_ERR_UNSUPPORTED, "conv2d_wgrad: image too wide for the staged strip (W = %d)", W);
     pl.smem = pl.S * stage + 256;
-    // split K so that the grid covers the SMs about twice, but keep at least 4 chunks per CTA
+    // split K so that the grid is one wave of CTAs (one CTA per SM: 512 TMEM columns), but keep at least 4 chunks per CTA
     const int tiles = pl.c_tiles * pl.o_tiles;
-    int splits = (2 * kNumSMs + tiles - 1) / tiles;
+    int splits = kNumSMs / tiles;
     if (splits > pl.total_chunks / 4) splits = pl.total_chunks / 4;
     if (splits < 1) splits = 1;
     pl.chunks_per_split = (pl.total_chunks + splits - 1) / splits;

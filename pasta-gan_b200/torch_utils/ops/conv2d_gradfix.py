@@ -66,10 +66,15 @@ tensor_core_format = os.environ.get('PASTA_B200_TC_TRAIN_FMT', 'bf16')
 # microseconds of math behind a weight tensor that has to be re-packed every step (measured: 65.8 ms / step with every layer on tcgen05 vs 57.8 on
 # cuDNN TF32); the tensor cores pay where pixels, not weights, dominate (SPADE blocks, >= 64^2 layers).
 tensor_core_min_flops = float(os.environ.get('PASTA_B200_TC_TRAIN_MIN_GFLOP', '8')) * 1e9
-
+# R1's inner gradient (the image gradient taken under no_weight_gradients(), loss_wo_flow_fullbody.py:246-247) is differentiated again and its
+# magnitude is ~1e-7: a chain of ~14 bf16 input-gradient convolutions measured 2e-1 pointwise / 2e-2 on the penalty against the reference, so by
+# default that pass stays on the fp32 library path and the tensor cores serve the first-order passes.  PASTA_B200_TC_TRAIN_R1=1 puts it on tcgen05 too.
+tensor_core_r1 = os.environ.get('PASTA_B200_TC_TRAIN_R1', '0') == '1'
 
 def _tc_ok(input, weight_shape, transpose, stride, padding, output_padding, dilation, groups):
     if not (tensor_core_training and output_padding == (0, 0) and weight_shape[2] in (1, 3)):
+        return False
+    if weight_gradients_disabled and not tensor_core_r1:
         return False
     from . import conv_igemm
     if not conv_igemm.grad_supported(input.shape, weight_shape, input.dtype, input.device, stride, padding, dilation, groups):

@@ -234,6 +234,23 @@ def packed_weight_buffers():
     return [e.ws for e in _pack_store.values()] + [h['cat'] for h in _cat_cache.values()]
 
 
+def _auto_n_tile(n, cout, oh, ow, k, up):
+    """Latency-bound layers (4^2 .. 16^2, 512 channels): with the default 256-column N tile only N * tiles * ceil(Cout / 256) CTAs exist (32 at 4^2) and
+    each streams ~2.4 MB of weights through one SM.  A narrower N tile spreads the weight stream over all SMs.  0 = the library default."""
+    if up != 1 or cout < 128 or _NT_AUTO == '0':
+        return 0
+    tiles = (oh * (ow + 1 if k == 3 else ow) + 127) // 128
+    if n * tiles * ((cout + 255) // 256) >= 148:
+        return 0
+    for bn in (128, 64, 32):
+        if cout % bn == 0 and n * tiles * (cout // bn) >= 148:
+            return bn
+    return 32 if cout % 32 == 0 else 0
+
+
+_NT_AUTO = os.environ.get('PASTA_B200_CONV_AUTO_NTILE', '1')
+
+
 def conv2d_igemm(x, w, f=None, up=1, down=1, flip_weight=True, styles=None, dcoefs=None, noise=None, bias=None,
                  in_act='linear', in_alpha=0.2, in_gain=1.0, act='linear', alpha=0.2, gain=1.0, clamp=None, fmt=None,
                  w_scale=1.0, cache_weights=False, x2=None, residual=None, out_dtype=torch.float32, out_c8=False,
@@ -312,6 +329,7 @@ def conv2d_igemm(x, w, f=None, up=1, down=1, flip_weight=True, styles=None, dcoe
             assert residual.dtype == torch.float32 and residual.shape == y.shape
         residual = residual.contiguous()
     fmt_code = _FMT[fmt or operand_format]
+    n_tile = _auto_n_tile(n, cout, oh, ow, k, up)
     with torch.cuda.device(x.device):
         capi.require_device()
         sample_stride = 0
@@ -320,13 +338,13 @@ def conv2d_igemm(x, w, f=None, up=1, down=1, flip_weight=True, styles=None, dcoe
             per = _workspace_bytes(capi, cin, cout, k, mode)
             wpack = torch.empty(per * n, dtype=torch.uint8, device=x.device)
             if per_sample_weights:
-                _run_prepack(capi, w, f, w_scale, mode, flip_weight, fmt_code, wpack, batch=n, w_batch_stride=cout * cin * k * k)
+                _run_prepack(capi, w, f, w_scale, mode, flip_weight, fmt_code, wpack, batch=n, w_batch_stride=cout * cin * k * k, n_tile=n_tile)
             else:
-                _run_prepack(capi, w, f, w_scale, mode, flip_weight, fmt_code, wpack, batch=n, w_batch_stride=0, styles=styles)
+                _run_prepack(capi, w, f, w_scale, mode, flip_weight, fmt_code, wpack, batch=n, w_batch_stride=0, styles=styles, n_tile=n_tile)
                 styles = None
             sample_stride = per
         else:
-            wpack = _packed_weights(capi, w, f, w_scale, mode, flip_weight, fmt_code, cache_weights)
+            wpack = _packed_weights(capi, w, f, w_scale, mode, flip_weight, fmt_code, cache_weights, n_tile=n_tile)
         # algorithmic FLOPs: output pixels for stride-1 / down-2, INPUT pixels for up-2 (zero-inserted taps excluded)
         sp = capi.span('conv_igemm', flops=2 * n * cout * cin * k * k * (oh * ow if up == 1 else h * wd),
                        nbytes=x.element_size() * x.numel() + (x2.element_size() * x2.numel() if x2 is not None else 0) + (residual.element_size() * residual.numel() if residual is not None else 0) + 4 * w.numel() + y.element_size() * y.numel(),
@@ -342,7 +360,7 @@ def conv2d_igemm(x, w, f=None, up=1, down=1, flip_weight=True, styles=None, dcoe
         a.y, a.y_dtype, a.y_layout = capi.ptr(y), capi.dtype_code(y.dtype), capi.LAYOUT_C8 if out_c8 else capi.LAYOUT_NCHW
         a.in_act, a.in_alpha, a.in_gain = _ACT[in_act], float(in_alpha), float(in_gain)
         a.act, a.alpha, a.gain, a.clamp = _ACT[act], float(alpha), float(gain), float(-1 if clamp is None else clamp)
-        a.operand_format = fmt_code
+        a.operand_format, a.n_tile = fmt_code, n_tile
         a.stream = capi.current_stream(x.device)
         rc = capi.load().pg_conv2d_igemm_launch(_byref(a))
         capi.check(rc, 'pg_conv2d_igemm_launch')

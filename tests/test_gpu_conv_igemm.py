@@ -574,8 +574,8 @@ def test_conv2d_gradfix_trains_on_tensor_cores():
     autograd within 1e-2; the launch counter proves the kernels ran."""
     from pasta_gan_b200.torch_utils.ops import conv2d_gradfix as G
     torch.manual_seed(3)
-    old = (G.enabled, G.tensor_core_training, G.tensor_core_min_flops)
-    G.enabled, G.tensor_core_training, G.tensor_core_min_flops = True, True, 0
+    old = (G.enabled, G.tensor_core_training, G.tensor_core_min_flops, G.tensor_core_r1)
+    G.enabled, G.tensor_core_training, G.tensor_core_min_flops, G.tensor_core_r1 = True, True, 0, True
     try:
         x = torch.randn(2, 32, 24, 24); w = torch.randn(48, 32, 3, 3) / 17
         xg, wg = x.to(DEV).requires_grad_(True), w.to(DEV).requires_grad_(True)
@@ -597,4 +597,4 @@ def test_conv2d_gradfix_trains_on_tensor_cores():
         pwr, = torch.autograd.grad(gxr.square().sum(), wr)
         assert rel_err(pw, pwr) < 2e-2
     finally:
-        G.enabled, G.tensor_core_training, G.tensor_core_min_flops = old
+        G.enabled, G.tensor_core_training, G.tensor_core_min_flops, G.tensor_core_r1 = old

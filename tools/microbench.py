@@ -76,6 +76,8 @@ def main():
                           4 * N * C * (res ** 2 + (res + 1) ** 2)))
             cases.append(('down2', lambda x: upfirdn2d.downsample2d(x, f), [(x,) for x in xs2], 4 * N * C * (res ** 2 + (res // 2) ** 2)))
             cases.append(('bias_act_lrelu_clamp', lambda x: bias_act.bias_act(x, b, act='lrelu', clamp=256), [(x,) for x in xs2], 8 * N * C * res * res))
+            xs4 = pool([N, C, res // 2, res // 2])                  # full-channel up-2: the backward of every down-2 (upfirdn2d.py:251-261)
+            cases.append(('up2_full_channels', lambda x: upfirdn2d.upsample2d(x, f), [(x,) for x in xs4], 4 * N * C * ((res // 2) ** 2 + res ** 2)))
             xs3 = pool([N, 3, res // 2, res // 2])
             cases.append(('up2_rgb', lambda x: upfirdn2d.upsample2d(x, f), [(x,) for x in xs3], 4 * N * 3 * ((res // 2) ** 2 + res ** 2)))
             for name, fn, inputs, nbytes in cases:
@@ -85,7 +87,7 @@ def main():
                             frac_of_hbm=round(nbytes / t / 1e9 / hbm, 3), peak=hbm, peak_src=src, bytes=nbytes)
                 lines.append(line)
                 print(json.dumps(line), flush=True)
-            del xs, xs2, xs3
+            del xs, xs2, xs3, xs4
             torch.cuda.empty_cache()
     if a.out:
         with open(a.out, 'w') as fh:

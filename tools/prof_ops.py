@@ -14,13 +14,21 @@ with torch.no_grad():
         upfirdn2d.upfirdn2d(x257, f, padding=[1, 1, 1, 1], gain=4)                                  # upfirdn2d_band_kernel<1,0>
         upfirdn2d.upfirdn2d_bias_act(x257, f, b, padding=[1, 1, 1, 1], gain=4, act='lrelu', clamp=256)   # <1,1> fused epilogue
         upfirdn2d.downsample2d(x, f)                                                                # <2,0>
+        upfirdn2d.upsample2d(x[:, :, :128, :128].contiguous(), f)                                   # upfirdn2d_up2_band_kernel (polyphase up-2)
     w3 = torch.randn(3, 64, 1, 1, device=dev); s = torch.randn(16, 64, device=dev) / 8; img = torch.randn(16, 3, 128, 128, device=dev)
     for _ in range(2):
         torgb.torgb_skip(x, w3, styles=s, bias=torch.zeros(3, device=dev), clamp=256, img=img, f=f)  # torgb_skip_kernel<3>
     xa = torch.randn(16, 256, 128, 128, device=dev); wa = torch.randn(128, 256, 3, 3, device=dev) / 48
     xb = torch.randn(16, 128, 128, 128, device=dev); wb = torch.randn(128, 128, 3, 3, device=dev) / 34
+    xac, xbc = conv_igemm.to_c8(xa), conv_igemm.to_c8(xb)
+    xs = torch.randn(16, 128, 128, 128, device=dev); wg = torch.randn(128, 128, 3, 3, device=dev) / 34; wbeta = torch.randn(128, 128, 3, 3, device=dev) / 34
+    dyb = torch.randn(16, 128, 128, 128, device=dev) * 1e-3
     for _ in range(2):
-        conv_igemm.conv2d_igemm(xa, wa, bias=torch.zeros(128, device=dev), act='lrelu', gain=2 ** 0.5, clamp=256)   # 256->128 @128^2
-        conv_igemm.conv2d_igemm(xb, wb)                                                                            # 128->128 @128^2
+        conv_igemm.conv2d_igemm(xa, wa, bias=torch.zeros(128, device=dev), act='lrelu', gain=2 ** 0.5, clamp=256)   # 256->128 @128^2, converter path (conv_igemm_kernel)
+        conv_igemm.conv2d_igemm(xb, wb)                                                                            # 128->128 @128^2, converter path
+        conv_igemm.conv2d_igemm(xac, wa, act='relu', out_c8=True)                                                  # 256->128 @128^2, TMA persistent kernel, channel-blocked in / out
+        conv_igemm.conv2d_igemm(xbc, wb)                                                                           # 128->128 @128^2, TMA persistent kernel, fp32 out
+        conv_igemm.spade_conv_norm(xs, xbc, wg, wbeta, act='relu', gain=1.0, out_c8=True)                          # SPADE gamma|beta 128->256, TMA persistent
+        conv_igemm.conv2d_wgrad(xb, dyb, 3)                                                                        # conv_wgrad_kernel + reduce
 torch.cuda.synchronize()
 print('ok')

@@ -1,9 +1,13 @@
+# Round-2 measurement pass (run under gpurun; every step has its own hard timeout; outputs land in gpurun_out/ and are copied to profiles/ by hand).
 set -x
-timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_r1.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke_r1.log
-timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_r1_final.log 2>&1
-timeout 240 python bench.py > gpurun_out/bench_r1_final.json 2> gpurun_out/bench_r1_final.err
-timeout 240 python bench.py --workload gen512 --skip-cpu-baseline > gpurun_out/bench512_r1_final.json 2> gpurun_out/bench512_r1_final.err
-timeout 200 python tools/bench_conv.py --out gpurun_out/bench_conv_r1_final.jsonl > /dev/null 2>&1
-timeout 200 python tools/microbench.py --out gpurun_out/microbench_r1_final.jsonl > /dev/null 2>&1
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches_bench_r1_final.csv python bench.py --steps 2 --warmup 1 --skip-cpu-baseline --no-graph > gpurun_out/ncu_bench_final.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:"pg::|bias_act|upfirdn2d|torgb|conv_igemm|instance_stats" -o gpurun_out/ops_r1_final python tools/prof_ops.py > gpurun_out/ncu_ops_final.log 2>&1
+R=gpurun_out
+timeout -s KILL 120 python -c "import __graft_entry__ as g; g.smoke()" > $R/r2_smoke.log 2>&1; echo "smoke rc=$?" >> $R/r2_smoke.log
+timeout -s KILL 700 python -m pytest tests -m gpu -q > $R/r2_pytest_gpu.log 2>&1
+timeout -s KILL 900 python bench.py --steps 20 --warmup 5 > $R/r2_bench_gen256.json 2> $R/r2_bench_gen256.err
+timeout -s KILL 300 python bench.py --steps 200 --warmup 5 --no-extras --skip-cpu-baseline > $R/r2_bench_gen256_long.json 2> $R/r2_bench_gen256_long.err
+timeout -s KILL 300 python bench.py --workload gen512 --skip-cpu-baseline --no-extras > $R/r2_bench_gen512.json 2> $R/r2_bench_gen512.err
+timeout -s KILL 300 python tools/bench_conv.py --out $R/r2_conv_microbench.jsonl > /dev/null 2>&1
+timeout -s KILL 300 python tools/microbench.py --out $R/r2_op_microbench.jsonl > /dev/null 2>&1
+timeout -s KILL 300 python baseline/run_reference.py --mode ops > $R/r2_reference_cuda_ops.json 2> $R/r2_reference_cuda_ops.err
+timeout -s KILL 200 python tools/step_breakdown.py > $R/r2_step_breakdown_gen256.txt 2>&1
+timeout -s KILL 200 python tools/step_breakdown.py --workload gen512 > $R/r2_step_breakdown_gen512.txt 2>&1
