@@ -336,6 +336,9 @@ def run_b200(args, world, rank, local):
         l0 = capi.launch_count()
         sess.G(**sess.static_in, noise_mode='const')            # eager warm-up on the session stream (allocator pools, cuDNN plans)
         per_fwd = capi.launch_count() - l0                      # launches of OUR kernels in one forward (what each graph replay re-issues)
+        # per-launch CUDA events only measure the kernels if the GPU never waits for the host: park ~15 ms of spin in front of the step so that the host
+        # has queued every launch before the first one executes (otherwise a 5 us kernel shows up as the ~50 us it takes Python to issue the next call)
+        torch.cuda._sleep(int(3e7))
         with capi.LaunchProfiler() as prof:
             sess.G(**sess.static_in, noise_mode='const')
     roof, profile = roofline_from(prof.summary(), pk)

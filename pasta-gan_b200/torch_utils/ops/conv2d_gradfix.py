@@ -58,18 +58,35 @@ def conv_transpose2d(input, weight, bias=None, stride=1, padding=0, output_paddi
 
 # Training on the tensor cores: the stride-1 'same' 1x1 / 3x3 fp32 convolutions of the custom op run their forward, their input gradient (the same
 # tcgen05 kernel on dy with transposed, mirrored weights -- itself differentiable, which R1's double backward needs) and their weight gradient
-# (pg_conv2d_wgrad) on tcgen05 with bf16 operands and fp32 accumulation.  Everything else (strided / transposed-strided forms, fp16 blocks of the
+# (pg_conv2d_wgrad) on tcgen05 with fp16 (forward) / bf16 (gradient) operands and fp32 accumulation.  Everything else (strided / transposed-strided forms, fp16 blocks of the
 # discriminator, grouped convs) stays on the library path.  PASTA_B200_TC_TRAIN=0 switches it off (pure library convolutions).
 tensor_core_training = os.environ.get('PASTA_B200_TC_TRAIN', '1') != '0'
-tensor_core_format = os.environ.get('PASTA_B200_TC_TRAIN_FMT', 'bf16')
+# operand formats: the forward convolution multiplies activations and weights (O(1), clamped at 256 in the synthesis layers) -> fp16, 11-bit mantissa,
+# as in inference; gradients are tiny (R1's are ~1e-7) -> bf16 for the exponent range.  (Forward in bf16 measured 2e-1 pointwise on R1's image gradient.)
+tensor_core_format = os.environ.get('PASTA_B200_TC_TRAIN_FMT', 'fp16')
+tensor_core_grad_format = os.environ.get('PASTA_B200_TC_TRAIN_GRAD_FMT', 'bf16')
 # Layers below this many FLOPs per call stay on the library path: at the training batch (4 per GPU) a 512-channel layer at 4^2..32^2 is a few
 # microseconds of math behind a weight tensor that has to be re-packed every step (measured: 65.8 ms / step with every layer on tcgen05 vs 57.8 on
 # cuDNN TF32); the tensor cores pay where pixels, not weights, dominate (SPADE blocks, >= 64^2 layers).
 tensor_core_min_flops = float(os.environ.get('PASTA_B200_TC_TRAIN_MIN_GFLOP', '8')) * 1e9
-# R1's inner gradient (the image gradient taken under no_weight_gradients(), loss_wo_flow_fullbody.py:246-247) is differentiated again and its
-# magnitude is ~1e-7: a chain of ~14 bf16 input-gradient convolutions measured 2e-1 pointwise / 2e-2 on the penalty against the reference, so by
-# default that pass stays on the fp32 library path and the tensor cores serve the first-order passes.  PASTA_B200_TC_TRAIN_R1=1 puts it on tcgen05 too.
+# R1 (loss_wo_flow_fullbody.py:231-254) differentiates the image gradient a second time and its values are ~1e-7: with 10-bit-mantissa products in the
+# forward pass the pointwise image gradient measured 9e-2 and some second-order parameter gradients 3e-1 against the reference (2e-1 / 4e-1 with bf16),
+# while the fp32 library path holds 1e-2.  So the tensor cores serve the first-order phases (Gmain, Dmain) and the trainer runs the Dreg phase -- one
+# iteration in 16 -- under tensor_cores(False); the inner gradient taken under no_weight_gradients() never uses them unless PASTA_B200_TC_TRAIN_R1=1.
 tensor_core_r1 = os.environ.get('PASTA_B200_TC_TRAIN_R1', '0') == '1'
+
+@contextlib.contextmanager
+def tensor_cores(on):
+    """Switch the tcgen05 training path on / off for a region (the trainer runs the R1 phase, whose second-order gradients need fp32 products, with
+    it off)."""
+    global tensor_core_training
+    old = tensor_core_training
+    tensor_core_training = bool(on) and old
+    try:
+        yield
+    finally:
+        tensor_core_training = old
+
 
 def _tc_ok(input, weight_shape, transpose, stride, padding, output_padding, dilation, groups):
     if not (tensor_core_training and output_padding == (0, 0) and weight_shape[2] in (1, 3)):
@@ -90,7 +107,7 @@ def _forward(input, weight, bias, transpose, stride, padding, output_padding, di
     if bias is None and _tc_ok(input, weight.shape, transpose, stride, padding, output_padding, dilation, groups):
         from . import conv_igemm
         w = weight.transpose(0, 1) if transpose else weight
-        return conv_igemm.conv2d_igemm(input, w, flip_weight=not transpose, fmt=tensor_core_format)
+        return conv_igemm.conv2d_igemm(input, w, flip_weight=not transpose, fmt=tensor_core_grad_format if transpose else tensor_core_format)
     if not transpose:
         return torch.nn.functional.conv2d(input, weight, bias, stride, padding, dilation, groups)
     return torch.nn.functional.conv_transpose2d(input, weight, bias, stride, padding, output_padding, groups, dilation)

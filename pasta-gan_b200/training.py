@@ -82,6 +82,11 @@ class TryOnTrainer:
         return dict(G_adv=loss_adv.detach(), G_l1=loss_l1.detach(), G_mask=loss_mask.detach())
 
     def d_phase(self, b, do_main, do_r1, finish=True):
+        # the R1 phase needs fp32 products (second-order gradients of ~1e-7-sized values, see conv2d_gradfix): tensor cores off for it
+        with conv2d_gradfix.tensor_cores(not do_r1):
+            return self._d_phase(b, do_main, do_r1, finish)
+
+    def _d_phase(self, b, do_main, do_r1, finish=True):
         self.d_bucket.zero()
         sp = torch.nn.functional.softplus
         out = {}

@@ -15,17 +15,23 @@ from pasta_gan_b200.torch_utils.ops import conv_igemm, conv2d_resample, upfirdn2
 
 
 def timeit(fn, iters=10):
+    """Median of 3 runs of `iters` back-to-back launches between two CUDA events.  A spin kernel is parked in front so that the host has queued all
+    launches before the first executes: short kernels are then timed on the device, not by the ~50 us Python needs to issue each call."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
-    evs = []
-    for _ in range(iters):
+    ts = []
+    for _ in range(3):
+        torch.cuda._sleep(int(4e6))
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); fn(); b.record()
-        evs.append((a, b))
-    torch.cuda.synchronize()
-    ts = sorted(a.elapsed_time(b) for a, b in evs)
-    return ts[len(ts) // 2] * 1e-3
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) / iters)
+    ts.sort()
+    return ts[1] * 1e-3
 
 
 def main():

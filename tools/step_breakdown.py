@@ -28,6 +28,7 @@ with torch.no_grad():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); G(**inp, noise_mode='const'); e1.record(); torch.cuda.synchronize()
     print(f'eager step (no profiler): {e0.elapsed_time(e1):.2f} ms')
+    torch.cuda._sleep(int(3e7))          # ~15 ms of spin: the host queues every launch before the first executes, so the events bracket kernels, not host gaps
     with capi.LaunchProfiler() as prof:
         G(**inp, noise_mode='const')
     torch.cuda.synchronize()
