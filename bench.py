@@ -233,16 +233,16 @@ def run_reference(args, world, rank):
 # ------------------------------------------------------------------------------------------------ B200 arm
 
 def ncu_traffic(kernel):
-    """dram__bytes_read + dram__bytes_write of one `ncu --set full` launch of this kernel family (profiles/r1_kernels_ncu_full.csv, captured
+    """dram__bytes_read + dram__bytes_write of one `ncu --set full` launch of this kernel family (profiles/r2_kernels_ncu_full.csv, captured
     with tools/prof_ops.py at the kernel's largest generator shape); None if the capture is not in the tree."""
     import csv
-    match = {'conv_igemm': 'conv_igemm_kernel', 'bias_act': 'bias_act_vec_kernel', 'upfirdn2d': 'upfirdn2d_band_kernel<float, 1, 0>',
+    match = {'conv_igemm': 'conv_igemm_tma_persistent_kernel', 'bias_act': 'bias_act_vec_kernel', 'upfirdn2d': 'upfirdn2d_band_kernel<float, 1, 0>',
              'upfirdn2d_bias_act': 'upfirdn2d_band_kernel<float, 1, 1>', 'torgb_skip': 'torgb_skip_kernel'}.get(kernel)
-    shape = {'conv_igemm': '3x3 256->128 @128^2, N=16 (algorithmic 403 MB)', 'bias_act': '[16,64,256,256] lrelu (algorithmic 537 MB)',
+    shape = {'conv_igemm': '3x3 256->128 @128^2, N=16, channel-blocked fp16 in / out, persistent TMA kernel (algorithmic 134 + 67 MB + weights)', 'bias_act': '[16,64,256,256] lrelu (algorithmic 537 MB)',
              'upfirdn2d': '[16,64,257,257]->256^2 (algorithmic 539 MB)', 'upfirdn2d_bias_act': '[16,64,257,257]->256^2 (algorithmic 539 MB)',
              'torgb_skip': '[16,64,256,256]->3 ch (algorithmic 284 MB)'}.get(kernel)
     try:
-        for r in csv.DictReader(open(os.path.join(ROOT, 'profiles', 'r1_kernels_ncu_full.csv'))):
+        for r in csv.DictReader(open(os.path.join(ROOT, 'profiles', 'r2_kernels_ncu_full.csv'))):
             if match and match in r['Kernel Name']:
                 tot = (float(r['dram__bytes_read.sum [Mbyte]']) + float(r['dram__bytes_write.sum [Mbyte]'])) * 1e6
                 return dict(traffic=tot, traffic_note=f'ncu --set full, one launch, {shape}; writes still resident in L2 at kernel end are not counted by ncu')
@@ -415,7 +415,7 @@ def run_b200(args, world, rank, local):
                    'batch_per_gpu': args.batch, 'global_batch': world * args.batch, 'parallelism': f'replicas x{world} (batch-sharded, no collective)',
                    'cuda_graph': not args.no_graph, 'e2e_pipeline': 'H2D / compute / D2H on three streams, 2 buffer sets',
                    'l2': f'no explicit flush: one step streams ~{act_bytes / 1e9:.1f} GB of activations through the operators (> 126 MB L2)',
-                   'weights': 'procedural (name-keyed, tests/golden/procedural.py)', 'noise_mode': 'const'},
+                   'weights': 'procedural (name-keyed, pasta-gan_b200/synthetic.py)', 'noise_mode': 'const'},
         'e2e': {'value': imgs / t_e2e, 'unit': UNIT, 'ms_per_step': 1e3 * t_e2e / args.steps,
                 'h2d_bytes_per_step': sess.h2d_bytes, 'd2h_bytes_per_step': sess.d2h_bytes},
         'e2e_u8': {'value': imgs / t_u8, 'unit': UNIT, 'ms_per_step': 1e3 * t_u8 / args.steps, 'h2d_bytes_per_step': sess.h2d_bytes_u8,
