@@ -254,7 +254,8 @@ def modconv_layer(x, weight, styles, noise=None, up=1, padding=0, resample_filte
         return K.conv2d_igemm(x, weight, f=resample_filter, up=up, flip_weight=flip_weight, styles=styles, dcoefs=dcoefs, noise=noise,
                               bias=bias, act=act, gain=act_gain, clamp=clamp, cache_weights=isinstance(weight, nn.Parameter),
                               styles_normalized=styles_normalized, out_c8=out_c8)
-    assert not styles_normalized and not out_c8, 'normalised styles / channel-blocked outputs are only produced for the tcgen05 path'
+    # (unit-inf-norm styles from the StyleBank are fine here: a demodulated layer is invariant to the scale of its styles, and only those get normalised)
+    assert not out_c8 and (demodulate or not styles_normalized), 'channel-blocked outputs are only produced on the tcgen05 path'
     x = modulated_conv2d(x=x, weight=weight, styles=styles, noise=noise, up=up, padding=padding, resample_filter=resample_filter,
                          demodulate=demodulate, flip_weight=flip_weight, fused_modconv=fused_modconv)
     return B.bias_act(x, bias, act=act, gain=act_gain, clamp=clamp)

@@ -69,6 +69,17 @@ def main():
                 wn = w.unsqueeze(0).repeat(N, 1, 1, 1, 1)
                 t_psw = timeit(lambda: conv_igemm.conv2d_igemm(x, wn, f=f if up == 2 else None, up=up, flip_weight=(up == 1), per_sample_weights=True))
                 del wn
+            t_wg = t_dg = t_lib_wg = t_lib_dg = None
+            if up == 1 and conv_igemm.grad_supported(x.shape, w.shape, x.dtype, x.device, (1, 1), (k // 2, k // 2)):
+                # training kernels: weight gradient (pg_conv2d_wgrad) and input gradient (forward kernel on dy, transposed weights) vs cuDNN (TF32 allowed)
+                dy = torch.randn(N, cout, res, res, device=dev) * 1e-3
+                t_wg = timeit(lambda: conv_igemm.conv2d_wgrad(x, dy, k), iters=6)
+                t_dg = timeit(lambda: conv_igemm.conv2d_dgrad(dy, w), iters=6)
+                cb = lambda mask: torch.ops.aten.convolution_backward(dy, x, w, None, [1, 1], [k // 2, k // 2], [1, 1], False, [0, 0], 1, mask)
+                torch.backends.cudnn.allow_tf32 = True
+                t_lib_wg = timeit(lambda: cb([False, True, False]), iters=6)
+                t_lib_dg = timeit(lambda: cb([True, False, False]), iters=6)
+                del dy
             conv_igemm.enabled = False
             lib = lambda: conv2d_resample.conv2d_resample(x, w, f=f, up=up, padding=k // 2, flip_weight=(up == 1))
             t_ours = timeit(ours)
@@ -82,6 +93,8 @@ def main():
                         ours_us=round(t_ours * 1e6, 1), cudnn_tf32_us=round(t_tf32 * 1e6, 1), cudnn_fp32_us=round(t_fp32 * 1e6, 1),
                         tma_us=None if t_tma is None else round(t_tma * 1e6, 1), tma_c8out_us=None if t_tma_o is None else round(t_tma_o * 1e6, 1),
                         tma_tflops=None if t_tma is None else round(exec_flops / t_tma / 1e12, 1), groupsN_us=None if t_psw is None else round(t_psw * 1e6, 1),
+                        wgrad_us=None if t_wg is None else round(t_wg * 1e6, 1), cudnn_tf32_wgrad_us=None if t_lib_wg is None else round(t_lib_wg * 1e6, 1),
+                        dgrad_us=None if t_dg is None else round(t_dg * 1e6, 1), cudnn_tf32_dgrad_us=None if t_lib_dg is None else round(t_lib_dg * 1e6, 1),
                         ours_tflops=round(flops / t_ours / 1e12, 1), ours_executed_tflops=round(exec_flops / t_ours / 1e12, 1),
                         frac_of_bf16_peak=round(exec_flops / t_ours / 1e12 / peak, 3), speedup_vs_tf32=round(t_tf32 / t_ours, 2))
             lines.append(line)
