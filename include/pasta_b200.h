@@ -253,6 +253,10 @@ int pg_conv2d_igemm_spade_run(const float* feat, const void* wpack_gamma_beta, c
 /* Instance-norm statistics of x [planes = N*C, hw] (dense, fp32): mean and rstd = rsqrt(biased variance + eps), one streaming pass.
  * Feeds pg_conv2d_igemm_spade_run; replaces nn.InstanceNorm2d(affine=False) inside Spade_Norm_Block (training/networks.py:4363, :4377). */
 int pg_instance_norm_stats(const float* x, float* mean, float* rstd, int64_t planes, int64_t hw, float eps, void* stream);
+/* nn.InstanceNorm2d(affine=False) + activation in one pass for planes of <= 24576 elements (staged in shared memory):
+ *   y[p, :] = act((x[p, :] - mean_p) * rsqrt(var_p + eps)) * gain,  act in linear / relu / lrelu(alpha).
+ * The InstanceNorm -> LeakyReLU tail of the style encoder's Dense blocks (training/networks.py:594-611). */
+int pg_instance_norm_act(const float* x, float* y, int64_t planes, int64_t hw, float eps, int32_t act, float alpha, float gain, void* stream);
 
 /* Garment-feature completion of SynthesisNetworkFull.get_spade_feat (training/networks.py:5777-5800), the two passes over the feature map:
  *   pg_masked_plane_sum: out[n,c] = sum_hw feat[n,c,hw] * mask[n,hw]                      feat [N,C,hw], mask [N,hw], out [N,C]

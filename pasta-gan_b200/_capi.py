@@ -39,6 +39,7 @@ SIGNATURES = {
     'pg_masked_plane_sum': [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr],
     'pg_masked_fill': [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i32, c_ptr],
     'pg_instance_norm_stats': [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_f32, c_ptr],
+    'pg_instance_norm_act': [c_ptr, c_ptr, c_i64, c_i64, c_f32, c_i32, c_f32, c_f32, c_ptr],
     'pg_conv2d_igemm_spade_run': [c_ptr] * 6 + [c_i32] * 6 + [c_i32, c_f32, c_f32, c_i32, c_i32, c_i32, c_ptr],
     'pg_conv2d_igemm_fwd': [c_ptr] * 6 + [c_i64, c_ptr, c_ptr] + [c_i32] * 7 + [c_i32, c_i32, c_f32, c_f32, c_i32, c_f32, c_f32, c_f32, c_i32,
                             c_ptr, c_i64, c_ptr],

@@ -679,6 +679,17 @@ class Dense(nn.Module):
         self.linear = nn.Linear(in_channels, out_channels)
 
     def forward(self, x):
+        if x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled() and x.shape[2] * x.shape[3] <= 24576 and not self.bn.affine:
+            # inference on the sm_100a kernels: the per-pixel Linear is a 1x1 convolution (tcgen05), InstanceNorm + LeakyReLU one streaming kernel
+            from .torch_utils.ops import conv_igemm as K
+            if K.enabled:
+                w4 = getattr(self, '_w4', None)
+                if w4 is None or w4.data_ptr() != self.linear.weight.data_ptr():
+                    # a detached 4-D view of the Linear weight: shares storage and version counter, so the packed-weight store tracks updates
+                    w4 = self.linear.weight.detach().view(self.out_channels, self.in_channels, 1, 1)
+                    object.__setattr__(self, '_w4', w4)
+                y = K.conv2d_igemm(x, w4, bias=self.linear.bias, cache_weights=True)
+                return K.instance_norm_act(y, act='lrelu', alpha=float(self.activation.negative_slope), eps=float(self.bn.eps))
         y = self.linear(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
         return self.activation(self.bn(y))
 

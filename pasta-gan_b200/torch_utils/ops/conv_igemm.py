@@ -449,6 +449,23 @@ def instance_stats(x, eps=1e-5):
     return mean, rstd
 
 
+def instance_norm_act(x, act='lrelu', alpha=0.01, gain=1.0, eps=1e-5):
+    """act(InstanceNorm2d(affine=False)(x)) * gain in one pass (pg_instance_norm_act); planes of at most 24576 elements."""
+    capi = _backend.capi()
+    _backend.require_cuda(x, 'instance_norm_act')
+    x = x.contiguous()
+    n, c, h, wd = (int(v) for v in x.shape)
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        capi.require_device()
+        sp = capi.span('instance_norm_act', nbytes=8 * x.numel(), tag=f'{n * c} x {h * wd}')
+        rc = capi.load().pg_instance_norm_act(capi.ptr(x), capi.ptr(y), n * c, h * wd, float(eps), _ACT[act], float(alpha), float(gain), capi.current_stream(x.device))
+        capi.check(rc, 'pg_instance_norm_act')
+        if sp:
+            sp.close()
+    return y
+
+
 def spade_conv_norm(x, feat, w_gamma, w_beta, w_scale=1.0, act='linear', alpha=0.2, gain=1.0, eps=1e-5, fmt=None, stats=None, out_dtype=torch.float32,
                     out_c8=False):
     """act(instance_norm(x) * (1 + conv(feat, w_gamma)) + conv(feat, w_beta)) * gain  in one tcgen05 launch (gamma / beta stay in TMEM).
