@@ -286,6 +286,33 @@ int pg_u8_normalize(const void* const* src, void* const* dst, const int64_t* row
 int pg_image_to_u8_bgr(const float* img, void* out, int32_t N, int32_t H, int32_t W, int32_t x0, int32_t x1, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Patch routing — replaces the cv2.warpPerspective calls of the reference's data loader
+ * (training/dataset.py:838-927, UvitonDatasetFull*.normalize: 28 rectifying warps + 28 back-warps per sample on the CPU).
+ * uint8 images, fixed-point INTER_LINEAR exactly as OpenCV evaluates it (1/32-pixel coordinates, 2^15-scaled int16 weights).
+ *
+ *   pg_warp_perspective_u8: njobs independent warps in one launch.  Job i is one
+ *       cv2.warpPerspective(src, M, (dst_w, dst_h), flags=INTER_LINEAR, borderMode=border, borderValue=0)
+ *     with m = the DESTINATION -> SOURCE matrix (cv2 inverts M first: pass inv(M), row-major, as doubles).  Strides are in bytes, so a job can
+ *     read a channel slice of a wider image and write one (the reference concatenates the ten patches on the channel axis, dataset.py:920-923).
+ *     channels <= 4; border: 0 = BORDER_CONSTANT (value 0), 1 = BORDER_REPLICATE.  The job table lives in DEVICE memory;
+ *     max_dst_pixels = max over jobs of dst_h * dst_w (sizes the grid).
+ *   pg_patch_denorm_u8: the composite of dataset.py:882-886 / :892-897 for P parts (<= 16) of B samples:
+ *       for p in 0..P-1 (valid[b][p] != 0):   keep = warp(masks[b][..., 3p], m[b][p], BORDER_CONSTANT) == 255
+ *                                             denorm[b] = keep ? warp(patches[b][..., 3p:3p+3], m[b][p], BORDER_CONSTANT) : denorm[b]
+ *     patches / masks [B][h][w][3P] uint8 (what pg_warp_perspective_u8 wrote), m [B][P][9] doubles (image pixel -> patch coordinates, i.e. inv(M_inv)),
+ *     valid [B][P] uint8, denorm [B][H][W][3] (written in full; 0 where no part claims the pixel), part_masks [B][P][H][W] 0 / 1 or NULL. */
+typedef struct pg_warp_job {
+    double m[9];
+    const uint8_t* src; uint8_t* dst;
+    int32_t src_h, src_w, src_row_stride, src_pix_stride;
+    int32_t dst_h, dst_w, dst_row_stride, dst_pix_stride;
+    int32_t channels, border;
+} pg_warp_job;                                                  /* 128 bytes */
+int pg_warp_perspective_u8(const pg_warp_job* jobs_device, int32_t njobs, int32_t max_dst_pixels, void* stream);
+int pg_patch_denorm_u8(const void* patches, const void* masks, const double* m, const void* valid, void* denorm, void* part_masks,
+                       int32_t B, int32_t P, int32_t h, int32_t w, int32_t H, int32_t W, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * torgb_skip — the ToRGB skip path of a synthesis block in one streaming kernel (north_star kernel 3):
  *
  *   out[n,o] = upsample2d(img_in[n,o], fir)  +  clamp( sum_c w[o,c] * styles[n,c] * x[n,c] + bias[o] )

@@ -55,7 +55,20 @@ SIGNATURES = {
     'pg_c8_to_nchw': [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i32, c_ptr],
     'pg_upfirdn2d_bias_act': [c_ptr, c_ptr, c_ptr, c_ptr, I32x4, I64x4, I32x4, I64x4, c_i32, c_i32, c_i64, c_i64] + [c_i32] * 8 +
                              [c_i32, c_f32, c_i32, c_f32, c_f32, c_f32, c_i32, c_ptr],
+    'pg_warp_perspective_u8': [c_ptr, c_i32, c_i32, c_ptr],
+    'pg_patch_denorm_u8': [c_ptr] * 6 + [c_i32] * 6 + [c_ptr],
 }
+
+
+class WarpJob(ctypes.Structure):
+    """pg_warp_job of include/pasta_b200.h (128 bytes; one cv2.warpPerspective call)."""
+    _fields_ = [
+        ('m', ctypes.c_double * 9),
+        ('src', c_ptr), ('dst', c_ptr),
+        ('src_h', c_i32), ('src_w', c_i32), ('src_row_stride', c_i32), ('src_pix_stride', c_i32),
+        ('dst_h', c_i32), ('dst_w', c_i32), ('dst_row_stride', c_i32), ('dst_pix_stride', c_i32),
+        ('channels', c_i32), ('border', c_i32),
+    ]
 
 
 class ConvArgs(ctypes.Structure):

@@ -1,0 +1,272 @@
+"""Patch routing on the GPU: batched replacement for the perspective warps of the reference's data loader.
+
+The reference rectifies ten body-part quadrilaterals of the garment images into 64 x 64 patches and warps them back, one
+``cv2.warpPerspective`` call at a time on the CPU (``UvitonDatasetFull*.normalize``, training/dataset.py:838-927; crop geometry
+``get_crop``, :751-836).  Here the geometry (a handful of float32 operations and 8 x 8 linear systems per part) stays on the host,
+vectorised over the batch, and every pixel operation runs in two kernel launches per batch (csrc/pg_patch_route.cu):
+``pg_warp_perspective_u8`` (all rectifying warps of all samples, written straight into the channel-concatenated tensors) and
+``pg_patch_denorm_u8`` (the back-warp + mask == 255 composite).  The arithmetic is OpenCV's fixed-point bilinear path, restated
+bit for bit; there is no CPU fallback.
+
+``PatchRouter.normalize`` keeps the argument order and the 8-tuple of the reference method, with a leading batch axis on every array.
+``warp_perspective`` is the single-call analogue of ``cv2.warpPerspective`` for uint8 images.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _capi
+
+BORDER_CONSTANT, BORDER_REPLICATE = 0, 1
+
+# (joints of the part, joints of its fall-back or None)  -- training/dataset.py:847-857 and the fall-backs of :756-776
+_ORDER = ['cnose', 'cneck', 'rshoulder', 'relbow', 'rwrist', 'lshoulder', 'lelbow', 'lwrist', 'rhip', 'rknee', 'rankle', 'lhip', 'lknee',
+          'lankle', 'reye', 'leye', 'rear', 'lear']
+_J = {n: i for i, n in enumerate(_ORDER)}
+_PARTS = [
+    (('lshoulder', 'lhip', 'rhip', 'rshoulder'), None),
+    (('lshoulder', 'rshoulder', 'cnose'), ('lshoulder', 'rshoulder', 'rshoulder')),
+    (('lshoulder', 'lelbow'), None),
+    (('lelbow', 'lwrist'), None),
+    (('rshoulder', 'relbow'), None),
+    (('relbow', 'rwrist'), None),
+    (('lhip', 'lknee'), ('lhip',)),
+    (('lknee', 'lankle'), None),
+    (('rhip', 'rknee'), ('rhip',)),
+    (('rknee', 'rankle'), None),
+]
+NUM_PARTS = len(_PARTS)
+FIRST_LOWER_PART = 6                      # parts 6..9 (the legs) are also cut from the lower-garment image (dataset.py:888)
+
+
+def _segment_box(p0, p1, half_width):
+    """Quadrilateral around the segment p0 -> p1, half_width x |segment| to either side (dataset.py:822-829).  float32 throughout."""
+    seg = p1 - p0
+    nrm = np.array([-seg[1], seg[0]])
+    off = half_width * nrm
+    return np.float32([p0 + off, p0 - off, p1 - off, p1 + off])
+
+
+def part_quadrilateral(keypoints, part, o_h, ar=0.5):
+    """Source quadrilateral (4 x 2 float32, in the padded frame) of body part ``part`` for one sample, or None if its joints are not all
+    confident (>= 0.1) even after the reference's fall-back.  keypoints: [18, 3] (x, y, confidence), un-padded 192-wide frame."""
+    names, fallback = _PARTS[part]
+    idx = [_J[n] for n in names]
+    if not (keypoints[idx, 2] >= 0.1).all():
+        if fallback is None:
+            return None
+        names = fallback
+        idx = [_J[n] for n in names]
+        if not (keypoints[idx, 2] >= 0.1).all():
+            return None
+    pts = np.float32(keypoints[idx, :2])
+    pts[:, 0] += 32                                                        # the 192 -> 256 padding of the frame (dataset.py:780)
+    if len(names) == 4:
+        return pts
+    if len(names) == 1:                                                    # hip without knee: drop a vertical to the bottom edge
+        return _segment_box(pts[0], np.float32([pts[0][0], o_h - 1]), ar / 2.0)
+    if len(names) == 2:
+        return _segment_box(pts[0], pts[1], ar / 2.0)
+    if names[2] == 'rshoulder':                                            # shoulders without nose: a square above the shoulder line
+        seg = pts[1] - pts[0]
+        nrm = np.array([-seg[1], seg[0]])
+        if nrm[1] > 0.0:
+            nrm = -nrm
+        return np.float32([pts[0] + nrm, pts[0], pts[1], pts[1] + nrm])
+    neck = 0.5 * (pts[0] + pts[1])                                         # head box: from twice the neck-to-nose vector down to the neck
+    top = np.float32(neck + 2 * (pts[2] - neck))
+    a, b, c, d = _segment_box(top, np.float32(neck), 0.5)
+    return np.float32([b, c, d, a])
+
+
+def perspective_transforms(src, dst):
+    """Batched ``cv2.getPerspectiveTransform``: src, dst [J, 4, 2] float32 -> [J, 3, 3] float64.  Same elimination order as OpenCV's LU solver
+    (row pivoting on the first largest magnitude, updates ``a += alpha * pivot_row``), vectorised over the J systems; singular systems give zeros
+    with M[2,2] = 1."""
+    src = np.asarray(src, np.float32).reshape(-1, 4, 2)
+    dst = np.asarray(dst, np.float32).reshape(-1, 4, 2)
+    J = src.shape[0]
+    A = np.zeros((J, 8, 8), np.float64)
+    b = np.zeros((J, 8), np.float64)
+    A[:, :4, 0] = A[:, 4:, 3] = src[:, :, 0]
+    A[:, :4, 1] = A[:, 4:, 4] = src[:, :, 1]
+    A[:, :4, 2] = A[:, 4:, 5] = 1
+    A[:, :4, 6] = -src[:, :, 0] * dst[:, :, 0]                             # float32 products, widened on assignment
+    A[:, :4, 7] = -src[:, :, 1] * dst[:, :, 0]
+    A[:, 4:, 6] = -src[:, :, 0] * dst[:, :, 1]
+    A[:, 4:, 7] = -src[:, :, 1] * dst[:, :, 1]
+    b[:, :4] = dst[:, :, 0]
+    b[:, 4:] = dst[:, :, 1]
+    ok = np.ones(J, bool)
+    rows = np.arange(J)
+    eps = np.finfo(np.float64).eps * 100
+    for i in range(8):
+        k = i + np.argmax(np.abs(A[:, i:, i]), axis=1)
+        ok &= np.abs(A[rows, k, i]) >= eps
+        Ai, Ak = A[rows, i].copy(), A[rows, k].copy()
+        A[rows, i], A[rows, k] = Ak, Ai
+        bi, bk = b[rows, i].copy(), b[rows, k].copy()
+        b[rows, i], b[rows, k] = bk, bi
+        with np.errstate(divide='ignore', invalid='ignore'):
+            d = -1.0 / A[:, i, i]
+            alpha = A[:, i + 1:, i] * d[:, None]                           # [J, rows below]
+            A[:, i + 1:, i + 1:] += alpha[:, :, None] * A[:, i, None, i + 1:]
+            b[:, i + 1:] += alpha * b[:, i, None]
+    with np.errstate(divide='ignore', invalid='ignore'):
+        for i in range(7, -1, -1):
+            s = b[:, i].copy()
+            for c in range(i + 1, 8):
+                s -= A[:, i, c] * b[:, c]
+            b[:, i] = s / A[:, i, i]
+    b[~ok] = 0.0
+    return np.concatenate([b, np.ones((J, 1))], axis=1).reshape(J, 3, 3)
+
+
+def invert3x3(M):
+    """Batched closed-form inverse as ``cv::invert`` evaluates it for 3 x 3 doubles (adjugate times 1/det, zeros when det == 0).  M [..., 3, 3]."""
+    S = np.asarray(M, np.float64)
+    c00 = S[..., 1, 1] * S[..., 2, 2] - S[..., 1, 2] * S[..., 2, 1]
+    c01 = S[..., 1, 0] * S[..., 2, 2] - S[..., 1, 2] * S[..., 2, 0]
+    c02 = S[..., 1, 0] * S[..., 2, 1] - S[..., 1, 1] * S[..., 2, 0]
+    det = S[..., 0, 0] * c00 - S[..., 0, 1] * c01 + S[..., 0, 2] * c02
+    with np.errstate(divide='ignore'):
+        d = np.where(det != 0, 1.0 / det, 0.0)
+    t = np.empty(S.shape, np.float64)
+    t[..., 0, 0] = c00 * d
+    t[..., 0, 1] = (S[..., 0, 2] * S[..., 2, 1] - S[..., 0, 1] * S[..., 2, 2]) * d
+    t[..., 0, 2] = (S[..., 0, 1] * S[..., 1, 2] - S[..., 0, 2] * S[..., 1, 1]) * d
+    t[..., 1, 0] = (S[..., 1, 2] * S[..., 2, 0] - S[..., 1, 0] * S[..., 2, 2]) * d
+    t[..., 1, 1] = (S[..., 0, 0] * S[..., 2, 2] - S[..., 0, 2] * S[..., 2, 0]) * d
+    t[..., 1, 2] = (S[..., 0, 2] * S[..., 1, 0] - S[..., 0, 0] * S[..., 1, 2]) * d
+    t[..., 2, 0] = c02 * d
+    t[..., 2, 1] = (S[..., 0, 1] * S[..., 2, 0] - S[..., 0, 0] * S[..., 2, 1]) * d
+    t[..., 2, 2] = (S[..., 0, 0] * S[..., 1, 1] - S[..., 0, 1] * S[..., 1, 0]) * d
+    return t
+
+
+def crop_transforms(keypoints, h, w, o_h, ar=0.5):
+    """``get_crop`` for every (sample, part): keypoints [B, 18, 3] -> (M [B,10,3,3], M_inv [B,10,3,3], valid [B,10] bool); invalid parts are zero."""
+    keypoints = np.asarray(keypoints)
+    B = keypoints.shape[0]
+    dst = np.float32(np.array([[w, h]]) * np.float32([[0.0, 0.0], [0.0, 1.0], [1.0, 1.0], [1.0, 0.0]]))
+    quads, where = [], []
+    for bi in range(B):
+        for p in range(NUM_PARTS):
+            q = part_quadrilateral(keypoints[bi], p, o_h, ar)
+            if q is not None:
+                quads.append(q)
+                where.append((bi, p))
+    M = np.zeros((B, NUM_PARTS, 3, 3), np.float64)
+    M_inv = np.zeros((B, NUM_PARTS, 3, 3), np.float64)
+    valid = np.zeros((B, NUM_PARTS), bool)
+    if quads:
+        quads = np.stack(quads)
+        dsts = np.broadcast_to(dst, quads.shape)
+        fwd = perspective_transforms(quads, dsts)
+        bwd = perspective_transforms(dsts, quads)
+        bi, pi = np.array(where).T
+        M[bi, pi], M_inv[bi, pi], valid[bi, pi] = fwd, bwd, True
+    return M, M_inv, valid
+
+
+def _check_u8(t, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.uint8 and t.is_contiguous()):
+        raise _capi.PastaB200Error(f'{name}: expected a contiguous uint8 CUDA tensor (the patch-routing path has no CPU implementation)')
+
+
+def _launch_warps(jobs, device):
+    """jobs: list of WarpJob (host).  One H2D copy of the table + one launch."""
+    table = (_capi.WarpJob * len(jobs))(*jobs)
+    host = torch.frombuffer(ctypes.string_at(ctypes.addressof(table), ctypes.sizeof(table)), dtype=torch.uint8).clone()
+    dev = host.to(device, non_blocking=False)
+    max_pix = max(j.dst_h * j.dst_w for j in jobs)
+    _capi.require_device()
+    _capi.check(_capi.load().pg_warp_perspective_u8(dev.data_ptr(), len(jobs), max_pix, _capi.current_stream(device)), 'pg_warp_perspective_u8')
+    return dev                                                             # keep alive until the caller synchronises or reuses the stream
+
+
+def _job(src, src_off, dst, dst_off, coeffs, src_hw, src_strides, dst_hw, dst_strides, channels, border):
+    j = _capi.WarpJob()
+    for i, v in enumerate(np.asarray(coeffs, np.float64).reshape(9)):
+        j.m[i] = float(v)
+    j.src, j.dst = src + src_off, dst + dst_off
+    j.src_h, j.src_w = src_hw
+    j.src_row_stride, j.src_pix_stride = src_strides
+    j.dst_h, j.dst_w = dst_hw
+    j.dst_row_stride, j.dst_pix_stride = dst_strides
+    j.channels, j.border = channels, border
+    return j
+
+
+def warp_perspective(src, M, dsize, border_mode=BORDER_CONSTANT):
+    """``cv2.warpPerspective(src, M, dsize, flags=INTER_LINEAR, borderMode=border_mode, borderValue=0)`` for a uint8 CUDA image [H, W, C] (C <= 4)
+    or [H, W].  dsize = (width, height) as in OpenCV."""
+    squeeze = src.dim() == 2
+    img = src.unsqueeze(-1) if squeeze else src
+    _check_u8(img, 'warp_perspective')
+    H, W, C = img.shape
+    if C > 4:
+        raise _capi.PastaB200Error('warp_perspective: at most 4 channels')
+    w, h = int(dsize[0]), int(dsize[1])
+    out = torch.empty((h, w, C), dtype=torch.uint8, device=img.device)
+    coeffs = invert3x3(np.asarray(M, np.float64).reshape(3, 3))
+    keep = _launch_warps([_job(img.data_ptr(), 0, out.data_ptr(), 0, coeffs, (H, W), (W * C, C), (h, w), (w * C, C), C, int(border_mode))], img.device)
+    del keep
+    return out[..., 0] if squeeze else out
+
+
+class PatchRouter:
+    """Batched ``normalize`` of the reference's datasets (training/dataset.py:838-927)."""
+
+    def __init__(self, box_factor=2, ar=0.5):
+        self.box_factor, self.ar = box_factor, ar
+
+    def normalize(self, upper_img, lower_img, upper_clothes_mask, lower_clothes_mask, keypoints, box_factor=None):
+        """upper_img, lower_img, upper_clothes_mask, lower_clothes_mask: uint8 CUDA tensors [B, H, W, 3] (masks are 0 / 255 triples);
+        keypoints: array [B, 18, 3] (x, y, confidence) in the un-padded frame.  Returns the reference's tuple with a leading batch axis:
+        (img [B,h,w,30], img_lower [B,h,w,12], denorm_upper_img [B,H,W,3], denorm_lower_img [B,H,W,3], M_invs [B,10,3,3] float64 (numpy),
+        denorm_hand_masks [B,4,H,W,1], clothes_masks [B,h,w,30], clothes_masks_lower [B,h,w,12])."""
+        for name, t in (('upper_img', upper_img), ('lower_img', lower_img), ('upper_clothes_mask', upper_clothes_mask), ('lower_clothes_mask', lower_clothes_mask)):
+            _check_u8(t, name)
+            if t.shape != upper_img.shape or t.dim() != 4 or t.shape[-1] != 3:
+                raise _capi.PastaB200Error(f'{name}: expected [B, H, W, 3] like upper_img, got {tuple(t.shape)}')
+        box_factor = self.box_factor if box_factor is None else box_factor
+        B, H, W, _ = upper_img.shape
+        h, w = H // 2 ** box_factor, W // 2 ** box_factor
+        dev = upper_img.device
+        M, M_inv, valid = crop_transforms(keypoints, h, w, H, self.ar)
+        to_patch = invert3x3(M)                                            # cv2.warpPerspective(img, M, ...) walks the patch and samples img at inv(M)
+        to_image = invert3x3(M_inv)                                        # ... and the back-warp samples the patch at inv(M_inv)
+        P, PL = NUM_PARTS, NUM_PARTS - FIRST_LOWER_PART
+        img = torch.zeros((B, h, w, 3 * P), dtype=torch.uint8, device=dev)
+        masks = torch.zeros((B, h, w, 3 * P), dtype=torch.uint8, device=dev)
+        img_lower = torch.zeros((B, h, w, 3 * PL), dtype=torch.uint8, device=dev)
+        masks_lower = torch.zeros((B, h, w, 3 * PL), dtype=torch.uint8, device=dev)
+        jobs = []
+        src_bytes = H * W * 3
+        for bi in range(B):
+            for p in range(P):
+                if not valid[bi, p]:
+                    continue
+                for src, dst, nch, col in ((upper_img, img, 3 * P, p), (upper_clothes_mask, masks, 3 * P, p)) + \
+                        (((lower_img, img_lower, 3 * PL, p - FIRST_LOWER_PART), (lower_clothes_mask, masks_lower, 3 * PL, p - FIRST_LOWER_PART))
+                         if p >= FIRST_LOWER_PART else ()):
+                    jobs.append(_job(src.data_ptr(), bi * src_bytes, dst.data_ptr(), bi * h * w * nch + 3 * col, to_patch[bi, p],
+                                     (H, W), (W * 3, 3), (h, w), (w * nch, nch), 3, BORDER_REPLICATE))
+        keep = _launch_warps(jobs, dev) if jobs else None
+        lib, stream = _capi.load(), _capi.current_stream(dev)
+        denorm_upper = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev)
+        denorm_lower = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev)
+        part_masks = torch.empty((B, P, H, W), dtype=torch.uint8, device=dev)
+        m_up = torch.from_numpy(np.ascontiguousarray(to_image.reshape(B, P, 9))).to(dev)
+        m_lo = torch.from_numpy(np.ascontiguousarray(to_image[:, FIRST_LOWER_PART:].reshape(B, PL, 9))).to(dev)
+        v_up = torch.from_numpy(valid.astype(np.uint8)).to(dev)
+        v_lo = torch.from_numpy(np.ascontiguousarray(valid[:, FIRST_LOWER_PART:]).astype(np.uint8)).to(dev)
+        _capi.check(lib.pg_patch_denorm_u8(img.data_ptr(), masks.data_ptr(), m_up.data_ptr(), v_up.data_ptr(), denorm_upper.data_ptr(),
+                                           part_masks.data_ptr(), B, P, h, w, H, W, stream), 'pg_patch_denorm_u8')
+        _capi.check(lib.pg_patch_denorm_u8(img_lower.data_ptr(), masks_lower.data_ptr(), m_lo.data_ptr(), v_lo.data_ptr(), denorm_lower.data_ptr(),
+                                           None, B, PL, h, w, H, W, stream), 'pg_patch_denorm_u8')
+        del keep
+        hand_masks = part_masks[:, 2:6].unsqueeze(-1)                      # the four arm parts (dataset.py:903-907)
+        return img, img_lower, denorm_upper, denorm_lower, M_inv, hand_masks, masks, masks_lower

@@ -117,3 +117,37 @@ def synth_inputs_u8(batch, res=256, parts_ch=42, parts_res=64, seed=1234, full_b
     if full_body:
         d.update(denorm_upper_clothes=u8(3, 3, res), denorm_lower_clothes=u8(4, 3, res), denorm_upper_mask=u8(5, 1, res, 2), denorm_lower_mask=u8(6, 1, res, 2))
     return {k: v.to(device) for k, v in d.items()}
+
+
+_STICK_FIGURE = {   # (x, y) in the un-padded 192 x 256 frame, OpenPose-18 names as the reference orders them (training/dataset.py:859-861)
+    'cnose': (96, 30), 'cneck': (96, 50), 'rshoulder': (70, 55), 'relbow': (60, 95), 'rwrist': (55, 130), 'lshoulder': (122, 55), 'lelbow': (132, 95),
+    'lwrist': (138, 130), 'rhip': (80, 135), 'rknee': (78, 185), 'rankle': (77, 235), 'lhip': (112, 135), 'lknee': (114, 185), 'lankle': (115, 235),
+    'reye': (90, 25), 'leye': (102, 25), 'rear': (85, 28), 'lear': (107, 28)}
+_STICK_ORDER = ['cnose', 'cneck', 'rshoulder', 'relbow', 'rwrist', 'lshoulder', 'lelbow', 'lwrist', 'rhip', 'rknee', 'rankle', 'lhip', 'lknee',
+                'lankle', 'reye', 'leye', 'rear', 'lear']
+
+
+def synth_patch_routing_inputs(batch, res=256, seed=77, drop_joints=True):
+    """Synthetic inputs of the patch-routing step (training/dataset.py:553-565): garment images and 0 / 255 garment masks as uint8 [B, res, res, 3]
+    (numpy), and jittered stick-figure keypoints [B, 18, 3] (x, y, confidence).  Masks are unions of discs so that back-warped masks reach 255;
+    with ``drop_joints`` a few joints per sample get confidence 0 to exercise the reference's fall-backs and the invalid-part path."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:res, 0:res]
+    kps = np.zeros((batch, 18, 3), np.float64)
+    imgs = rng.integers(0, 256, (2, batch, res, res, 3), dtype=np.uint8)
+    masks = np.zeros((2, batch, res, res, 1), np.uint8)
+    for b in range(batch):
+        for i, n in enumerate(_STICK_ORDER):
+            x, y = _STICK_FIGURE[n]
+            kps[b, i] = (x + rng.normal(0, 4), y + rng.normal(0, 4), 0.9)
+        if drop_joints and b % 4:
+            kps[b, rng.choice(18, size=b % 4, replace=False), 2] = 0.0
+        for which, (cy, ry) in enumerate(((95, 60), (185, 70))):              # upper garment around the torso and arms, lower around the legs
+            for _ in range(6):
+                cx, cyy, r = 128 + rng.normal(0, 30), cy + rng.normal(0, ry / 2), rng.uniform(20, 45)
+                masks[which, b, :, :, 0] |= ((xx - cx) ** 2 + (yy - cyy) ** 2 < r * r).astype(np.uint8)
+    upper_mask, lower_mask = masks[0], masks[1] * (1 - masks[0])
+    rgb = lambda m: np.repeat(m, 3, axis=-1) * np.uint8(255)
+    return dict(upper_img=imgs[0] * upper_mask, lower_img=imgs[1] * lower_mask, upper_clothes_mask=rgb(upper_mask), lower_clothes_mask=rgb(lower_mask),
+                keypoints=kps)

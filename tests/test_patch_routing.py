@@ -1,0 +1,146 @@
+"""Patch-routing perspective warp (reference training/dataset.py:751-927).
+
+CPU: the oracle's restatement of OpenCV's fixed-point warp against hand-derivable properties (cv2 is not in this image: parity is UNPINNED, see
+oracle/warp_oracle.py), and the product's batched host geometry against the oracle's per-call version.
+GPU: the two kernels, through the C ABI, bit-exact against the oracle."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import warp_oracle as WO
+from pasta_gan_b200 import _capi, patch_routing as PR, synthetic
+
+
+def _rand_img(rng, h, w, c=3):
+    return rng.integers(0, 256, (h, w, c), dtype=np.uint8)
+
+
+# ------------------------------------------------------------------------------------------------------------------ oracle properties (CPU)
+
+def test_oracle_interpolation_table():
+    t = WO.bilinear_tab_i().astype(np.int64)
+    assert t.shape == (1024, 4)
+    assert (t.sum(1) == 1 << 15).all()
+    assert t[0].tolist() == [32767, 0, 0, 1]                                  # OpenCV's saturation + sum correction at the integer position
+    fy, fx = np.divmod(np.arange(1024), 32)
+    closed = np.stack([(32 - fy) * (32 - fx), (32 - fy) * fx, fy * (32 - fx), fy * fx], 1) * 32
+    assert (t[1:] == closed[1:]).all()                                       # what csrc/pg_patch_route.cu evaluates instead of a table
+
+
+def test_oracle_identity_and_translation_are_copies():
+    rng = np.random.default_rng(0)
+    img = _rand_img(rng, 96, 160)
+    for border in (WO.BORDER_CONSTANT, WO.BORDER_REPLICATE):
+        assert (WO.warp_perspective_u8(img, np.eye(3), (160, 96), border) == img).all()
+    T = np.array([[1, 0, 7], [0, 1, -4], [0, 0, 1.0]])
+    out = WO.warp_perspective_u8(img, T, (160, 96), WO.BORDER_CONSTANT)
+    assert (out[:-4, 7:] == img[4:, :-7]).all() and out[:, :7].max() == 0 and out[-4:].max() == 0
+    rep = WO.warp_perspective_u8(img, T, (160, 96), WO.BORDER_REPLICATE)
+    assert (rep[:-4, :7] == img[4:, :1]).all() and (rep[-4:, 7:] == img[-1:, :-7]).all()
+
+
+def test_oracle_subpixel_values():
+    """A shift by k/32 px interpolates with weights (32-k)/32, k/32 exactly: (a*(32-k)*1024 + b*k*1024 + 2^14) >> 15."""
+    rng = np.random.default_rng(1)
+    img = _rand_img(rng, 8, 64, 1)
+    for k in (1, 5, 16, 31):
+        T = np.array([[1, 0, -k / 32.0], [0, 1, 0], [0, 0, 1.0]])
+        out = WO.warp_perspective_u8(img, T, (64, 8), WO.BORDER_REPLICATE)[:, :-1, 0].astype(np.int64)
+        a, b = img[:, :-1, 0].astype(np.int64), img[:, 1:, 0].astype(np.int64)
+        assert (out == (a * (32 - k) * 1024 + b * k * 1024 + (1 << 14)) >> 15).all()
+
+
+def test_oracle_perspective_transform_maps_its_points():
+    rng = np.random.default_rng(2)
+    for _ in range(20):
+        src = np.float32([[30, 40], [20, 200], [180, 220], [200, 30]] + rng.normal(0, 8, (4, 2)))
+        dst = np.float32([[0, 0], [0, 64], [64, 64], [64, 0]])
+        M = WO.get_perspective_transform(src, dst)
+        p = np.c_[src, np.ones(4)] @ M.T
+        assert np.abs(p[:, :2] / p[:, 2:] - dst).max() < 1e-9
+        assert np.abs(WO.invert3x3(M) @ M - np.eye(3)).max() < 1e-9
+
+
+# ------------------------------------------------------------------------------------------------------------------ host geometry (CPU)
+
+def test_host_geometry_matches_oracle():
+    d = synthetic.synth_patch_routing_inputs(8, seed=5)
+    M, M_inv, valid = PR.crop_transforms(d['keypoints'], 64, 64, 256)
+    assert valid.any() and not valid.all()                                   # the synthetic set exercises valid, fall-back and invalid parts
+    wh = np.expand_dims(np.array([64, 64]), 0)
+    for b in range(8):
+        for p in range(10):
+            m, mi = WO.get_crop(d['keypoints'][b], list(WO.BPARTS[p]), wh, 256, 256, 0.5)
+            assert (m is not None) == bool(valid[b, p])
+            if m is not None:
+                assert np.array_equal(M[b, p], m) and np.array_equal(M_inv[b, p], mi)          # same operations in the same order: bit-equal
+                assert np.array_equal(PR.invert3x3(M[b, p]), WO.invert3x3(m))
+            else:
+                assert not M[b, p].any() and not M_inv[b, p].any()
+
+
+def test_host_fallback_parts():
+    kp = synthetic.synth_patch_routing_inputs(1, drop_joints=False)['keypoints'][0]
+    for joint, part, expect in (('lknee', 6, True), ('cnose', 1, True), ('lelbow', 2, False), ('lhip', 6, False)):
+        k = kp.copy()
+        k[WO.ORDER.index(joint), 2] = 0.0
+        assert (PR.part_quadrilateral(k, part, 256) is not None) == expect
+
+
+def test_warp_job_struct_is_128_bytes():
+    assert ctypes.sizeof(_capi.WarpJob) == 128
+
+
+def test_no_cpu_path():
+    with pytest.raises(_capi.PastaB200Error):
+        PR.warp_perspective(torch.zeros(8, 8, 3, dtype=torch.uint8), np.eye(3), (8, 8))
+
+
+# ------------------------------------------------------------------------------------------------------------------ kernels (GPU)
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('border', [WO.BORDER_CONSTANT, WO.BORDER_REPLICATE])
+def test_warp_perspective_bit_exact(border):
+    rng = np.random.default_rng(10 + border)
+    for trial in range(12):
+        H, W, C = [(256, 256, 3), (64, 64, 3), (100, 37, 1), (33, 130, 4)][trial % 4]
+        h, w = [(64, 64), (256, 256), (50, 90), (200, 70)][trial % 4]
+        img = _rand_img(rng, H, W, C)
+        src = np.float32([[0.1 * W, 0.1 * H], [0.05 * W, 0.9 * H], [0.95 * W, 0.85 * H], [0.9 * W, 0.05 * H]] + rng.normal(0, 0.08 * min(H, W), (4, 2)))
+        if trial % 3 == 0:
+            src -= np.float32([0.4 * W, 0.3 * H])                              # quadrilateral partly outside the image: border handling
+        dst = np.float32([[0, 0], [0, h], [w, h], [w, 0]])
+        M = WO.get_perspective_transform(src, dst)
+        want = WO.warp_perspective_u8(img, M, (w, h), border)
+        got = PR.warp_perspective(torch.from_numpy(img).cuda(), M, (w, h), border).cpu().numpy()
+        assert np.array_equal(got, want), (trial, int((got != want).sum()))
+
+
+@pytest.mark.gpu
+def test_warp_perspective_exact_copies():
+    rng = np.random.default_rng(3)
+    img = _rand_img(rng, 256, 256)
+    t = torch.from_numpy(img).cuda()
+    assert torch.equal(PR.warp_perspective(t, np.eye(3), (256, 256)), t)
+    out = PR.warp_perspective(t, np.array([[1, 0, 70], [0, 1, 0], [0, 0, 1.0]]), (256, 256)).cpu().numpy()   # crosses the 64-column block boundary
+    assert (out[:, 70:] == img[:, :-70]).all() and out[:, :70].max() == 0
+
+
+@pytest.mark.gpu
+def test_normalize_matches_oracle():
+    B = 6
+    d = synthetic.synth_patch_routing_inputs(B, seed=9)
+    dev = {k: torch.from_numpy(v).cuda() for k, v in d.items() if k != 'keypoints'}
+    got = PR.PatchRouter().normalize(dev['upper_img'], dev['lower_img'], dev['upper_clothes_mask'], dev['lower_clothes_mask'], d['keypoints'], 2)
+    claimed = 0
+    for b in range(B):
+        want = WO.normalize(d['upper_img'][b], d['lower_img'][b], d['upper_clothes_mask'][b], d['lower_clothes_mask'][b], d['keypoints'][b], 2)
+        for i in (0, 1, 2, 3, 6, 7):
+            assert np.array_equal(got[i][b].cpu().numpy(), want[i]), (b, i)
+        assert np.array_equal(got[4][b], np.asarray(want[4], np.float64))
+        for k in range(4):
+            assert np.array_equal(got[5][b, k].cpu().numpy(), want[5][k]), (b, 'hand mask', k)
+        claimed += int((want[2] > 0).sum())
+    assert claimed > 1000                                                     # the composite is not trivially empty
