@@ -223,12 +223,12 @@ __device__ float down2_tap(const PackParams& p, int o, int c, int a, int b, int 
     return acc;
 }
 
-__global__ void conv_prepack_kernel(PackParams p) {
+__global__ void conv_prepack_kernel(PackParams p, long long out_sample_stride_halves) {
     const size_t total = (size_t)p.ntiles * p.nchunks * p.ntaps * 2 * p.BN * 8;
     const int nvirt = p.up2 ? 4 * p.Cout : p.Cout;
     const int sample = blockIdx.y;
     p.w += (size_t)sample * p.w_bstride;
-    p.out = (void*)((uint16_t*)p.out + (size_t)sample * total);
+    p.out = (void*)((uint16_t*)p.out + (size_t)sample * out_sample_stride_halves);
     const float* sty = p.styles ? p.styles + (size_t)sample * p.Cin : nullptr;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         size_t r = idx;
@@ -1430,6 +1430,172 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_igemm_tma_persistent_kernel
     }
 }
 
+// ---------------------------------------------------------------------------------------------- row-folded kernel (first layers)
+// Small-Cin layers on wide images (the 3 -> 64 channel 7x7 / 3x3 first layers of the encoders, W % 128 == 0).  The folded-tap form above gathers
+// Cin * k * k scalar values per output pixel through L1 (160 loads per pixel for 3 x 7 x 7: 465 us for one launch of the garment encoder).  Here only
+// the kernel ROWS are folded into K: GEMM channel r = c * k + kh holds input row h + kh - pad of channel c, so a staged A row is
+// "column w, the (c, kh) pairs" -- 21 coalesced row reads per column instead of 147 gathers -- and the k horizontal taps are k descriptor start
+// addresses 16 bytes apart into the same staged tile, exactly like the taps of the main kernel.  K = 32 (4 planes of 8 pairs, zero padded), a tile
+// is 128 consecutive pixels of one image row, k x (K / 16) MMAs of M = 128, N = Cout.  One accumulator, one A stage: several CTAs per SM overlap
+// each other's build / MMA / epilogue phases; CTAs walk the tile list with stride gridDim.x, so concurrently processed tiles are vertical
+// neighbours and the k-fold re-read of every input row is served by L2.
+constexpr int kRfThreads = 256;
+constexpr int kRfPlanes  = 4;       // K = 32 = 4 planes of 8 (channel, kernel row) pairs
+constexpr int kRfPA      = 136;     // staged columns per tile: 128 outputs + k - 1 <= 6 halo columns, padded to a multiple of 8
+
+struct RowFoldParams {
+    const float* x; const void* wpack; const float* bias; void* y;
+    int N, Cin, Cout, H, W, ks, BN, nrows, nchunks;       // nrows = Cin * ks real pairs, nchunks = K / 16 in use (1 or 2)
+    int act; float alpha, gain, clamp;
+    int y_c8, cb_out;
+    uint32_t idesc, tmem_cols;
+    int tiles_total, wsegs;
+};
+
+__global__ void conv_rowfold_prepack_kernel(PackParams p, long long out_sample_stride_halves) {
+    // w [Cout, Cin, ks, ks] -> [tap kw][plane (4)][BN rows][8] fp16; GEMM channel r = plane * 8 + e = c * ks + kh
+    const size_t total = (size_t)p.ks * kRfPlanes * p.BN * 8;
+    const int sample = blockIdx.y;
+    const float* w = p.w + (size_t)sample * p.w_bstride;
+    __half* out = (__half*)p.out + (size_t)sample * out_sample_stride_halves;
+    const float* sty = p.styles ? p.styles + (size_t)sample * p.Cin : nullptr;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        size_t q = idx;
+        const int e = q % 8; q /= 8;
+        const int o = q % p.BN; q /= p.BN;
+        const int j = q % kRfPlanes; q /= kRfPlanes;
+        const int kw = (int)q;
+        const int r = j * 8 + e;
+        float val = 0.f;
+        if (o < p.Cout && r < p.Cin * p.ks) {
+            const int c = r / p.ks, kh = r - c * p.ks;
+            const int wh = p.flip_weight ? kh : p.ks - 1 - kh, ww = p.flip_weight ? kw : p.ks - 1 - kw;
+            val = w[((size_t)(o * p.Cin + c) * p.ks + wh) * p.ks + ww] * p.w_scale;
+            if (sty) val *= sty[c];
+        }
+        out[idx] = __float2half_rn(fminf(fmaxf(val, -65504.f), 65504.f));
+    }
+}
+
+__global__ void __launch_bounds__(kRfThreads) conv_rowfold_kernel(const __grid_constant__ RowFoldParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    uint8_t* a_base = smem;                                              // [plane][column][16 B]
+    uint8_t* b_base = a_base + kRfPlanes * kRfPA * 16;                   // [tap][plane][BN][16 B]
+    const uint32_t b_tap_bytes = (uint32_t)(kRfPlanes * p.BN * 16);
+    float* s_shift = reinterpret_cast<float*>(b_base + (size_t)p.ks * b_tap_bytes);
+    int2* s_tab = reinterpret_cast<int2*>(s_shift + p.BN);               // per GEMM channel: (plane offset of its input channel, kernel row - pad)
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_tab + 8 * kRfPlanes);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    const int HW = p.H * p.W, pad = p.ks >> 1;
+
+    if (warp == 0 && lane == 0) {
+        mbar_init(smem_u32(bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    {   // one-time staging: zero A (padding planes / columns stay zero for the life of the CTA), the packed weights, epilogue constants, row table
+        uint4* z = reinterpret_cast<uint4*>(a_base);
+        for (int i = threadIdx.x; i < kRfPlanes * kRfPA; i += kRfThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        const uint4* wsrc = reinterpret_cast<const uint4*>(p.wpack);
+        uint4* wdst = reinterpret_cast<uint4*>(b_base);
+        const int nw = (int)((size_t)p.ks * b_tap_bytes / 16);
+        for (int i = threadIdx.x; i < nw; i += kRfThreads) wdst[i] = __ldg(wsrc + i);
+        for (int j = threadIdx.x; j < p.BN; j += kRfThreads) s_shift[j] = (j < p.Cout && p.bias) ? p.bias[j] * p.gain : 0.f;
+        for (int r = threadIdx.x; r < 8 * kRfPlanes; r += kRfThreads) {
+            const int c = r / p.ks, kh = r - c * p.ks;
+            s_tab[r] = r < p.nrows ? make_int2(c * HW, kh - pad) : make_int2(0, 1 << 20);      // padding channel: row out of range
+        }
+        fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t issue = elect_one();
+    const int nplanes = (p.nrows + 7) >> 3;
+    const int ncols = 128 + p.ks - 1;                                   // staged columns that carry data
+    const float slope = (p.act == PG_ACT_LINEAR) ? 1.f : (p.act == PG_ACT_RELU ? 0.f : p.alpha);
+    const bool do_act = p.act != PG_ACT_LINEAR, do_clamp = p.clamp >= 0.f;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
+        const int wseg = tile % p.wsegs, hn = tile / p.wsegs, h = hn % p.H, n = hn / p.H;
+        const int w0 = wseg * 128;
+        const float* xn = p.x + (size_t)n * p.Cin * HW;
+        // ---- build: A[plane j][column t] = the 8 (channel, kernel row) pairs of plane j at image column w0 - pad + t (zeros outside the image)
+        for (int task = threadIdx.x; task < nplanes * kRfPA; task += kRfThreads) {
+            const int j = task / kRfPA, t = task - j * kRfPA;
+            const int col = w0 - pad + t;
+            const bool col_ok = t < ncols && col >= 0 && col < p.W;
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int2 tb = s_tab[j * 8 + i];
+                const int row = h + tb.y;
+                v[i] = (col_ok && (unsigned)row < (unsigned)p.H) ? __ldg(xn + tb.x + row * p.W + col) : 0.f;
+            }
+            *reinterpret_cast<uint4*>(a_base + (size_t)task * 16) = pack_half8(v);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        // ---- MMA: k horizontal taps x K / 16 chunks into one accumulator
+        if (warp == 0) {
+            tc_fence_after();
+            if (issue) {
+                const uint32_t hi = (128u >> 4) | (1u << 14);
+                const uint32_t a_lo = ((uint32_t)kRfPA << 16) | (smem_u32(a_base) >> 4);
+                const uint32_t b_lo = (((uint32_t)p.BN & 0x3FFF) << 16) | (smem_u32(b_base) >> 4);
+                for (int kw = 0; kw < p.ks; kw++)
+                    for (int c = 0; c < p.nchunks; c++) {
+                        const uint64_t adesc = ((uint64_t)hi << 32) | (uint64_t)(a_lo + (uint32_t)(c * 2 * kRfPA + kw));
+                        const uint64_t bdesc = ((uint64_t)hi << 32) | (uint64_t)(b_lo + (((uint32_t)kw * b_tap_bytes + (uint32_t)(c * 2 * p.BN * 16)) >> 4));
+                        umma_f16(tmem_base, adesc, bdesc, p.idesc, (kw | c) ? 1u : 0u);
+                    }
+                umma_commit(smem_u32(bar));
+            }
+            __syncwarp();
+        }
+        // ---- epilogue: warps (quarter = TMEM lane group, half = alternate 16-column chunks)
+        mbar_wait(smem_u32(bar), phase);
+        phase ^= 1u;
+        tc_fence_after();
+        {
+            const int quarter = warp & 3, half = warp >> 2;
+            const int w = w0 + quarter * 32 + lane;
+            for (int cc = half; cc < p.BN / 16; cc += kRfThreads / 128) {
+                uint32_t rg[16];
+                tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cc * 16), rg);
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    float t = fmaf(__uint_as_float(rg[i]), p.gain, s_shift[cc * 16 + i]);
+                    if (do_act) t = fmaxf(t, 0.f) + slope * fminf(t, 0.f);
+                    if (do_clamp) t = fminf(fmaxf(t, -p.clamp), p.clamp);
+                    v[i] = t;
+                }
+                if (p.y_c8) {
+                    uint4* yb = reinterpret_cast<uint4*>(p.y) + ((size_t)n * p.cb_out + (size_t)cc * 2) * HW + (size_t)h * p.W + w;
+                    yb[0] = pack_half8(v); yb[HW] = pack_half8(v + 8);
+                } else {
+                    float* yp = reinterpret_cast<float*>(p.y) + ((size_t)n * p.Cout + (size_t)cc * 16) * HW + (size_t)h * p.W + w;
+#pragma unroll
+                    for (int i = 0; i < 16; i++) if (cc * 16 + i < p.Cout) yp[(size_t)i * HW] = v[i];
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();                 // every warp is done with the accumulator and the MMAs are done with the A stage
+    }
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 struct ConvPlan {
     int BN, ntiles_n, nchunks, ntaps, NACC, PW, Lp, tiles_per_img, PA, SA, SB, tps;
@@ -1442,7 +1608,7 @@ static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 // Plan / loader choices that were measured against each other.  Defaults are the measured best; the environment is read ONCE, when
 // the library is first used, and pg_set_tuning() changes a value for the rest of the process (tests and tools/ compare variants through it).
 struct Tuning {
-    int bands = 1, band_tw = 64, band_minw = 128, band_ratio10 = 0, persist = 0, nacc = 0, pair = 1, vec2 = 1, lean = 1, cgroups = 1, tma = 1, tma_persist = 1;
+    int bands = 1, band_tw = 64, band_minw = 128, band_ratio10 = 0, persist = 0, nacc = 0, pair = 1, vec2 = 1, lean = 1, cgroups = 1, tma = 1, tma_persist = 1, rowfold = 1;
 #ifdef PG_DEBUG
     int pipe = 0, ldmode = 0, dbgmode = 0;
 #endif
@@ -1455,6 +1621,7 @@ static const TuningKey kTuningKeys[] = {
     {"conv_pair", "PASTA_B200_CONV_PAIR", &Tuning::pair}, {"conv_vec2", "PASTA_B200_CONV_VEC2", &Tuning::vec2},
     {"conv_lean", "PASTA_B200_CONV_LEAN", &Tuning::lean}, {"conv_cgroups", "PASTA_B200_CONV_CGROUPS", &Tuning::cgroups},
     {"conv_tma", "PASTA_B200_CONV_TMA", &Tuning::tma}, {"conv_tma_persist", "PASTA_B200_CONV_TMA_PERSIST", &Tuning::tma_persist},
+    {"conv_rowfold", "PASTA_B200_CONV_ROWFOLD", &Tuning::rowfold},
 #ifdef PG_DEBUG
     {"conv_pipe", "PASTA_B200_CONV_PIPE", &Tuning::pipe}, {"conv_ldmode", "PASTA_B200_CONV_LDMODE", &Tuning::ldmode},
     {"conv_dbgmode", "PASTA_B200_CONV_DBGMODE", &Tuning::dbgmode},
@@ -1596,11 +1763,20 @@ extern "C" void pg_debug_set_buffer(void* buf) { g_conv_dbg = (long long*)buf; }
 // instead of k * k shifted MMAs over a 16-channel chunk that is mostly padding.
 static bool use_im2col(int Cin, int ksize, int up) { return up == 1 && ksize > 1 && Cin * ksize * ksize <= 160; }
 
+// Row-folded form of the same layers (conv_rowfold_kernel): its packed weights follow the folded-tap pack in the same workspace, so the choice
+// between the two can be made per launch (the row-folded kernel needs W % 128 == 0 and a plain epilogue).
+static bool rowfold_shape_ok(int Cin, int Cout, int ksize, int up) {
+    return use_im2col(Cin, ksize, up) && Cin * ksize <= 8 * pg::kRfPlanes && ksize <= 7 && Cout >= 16 && Cout <= 128;
+}
+static int64_t rowfold_pack_bytes(int Cin, int Cout, int ksize, int up) {
+    return rowfold_shape_ok(Cin, Cout, ksize, up) ? (int64_t)ksize * pg::kRfPlanes * ((Cout + 15) / 16 * 16) * 16 : 0;
+}
+
 extern "C" int64_t pg_conv2d_igemm_workspace_bytes(int32_t Cin, int32_t Cout, int32_t ksize, int32_t up) {
     pg::ConvPlan pl;
     const bool im2col = use_im2col(Cin, ksize, up);
     if (pg::make_plan(pl, 1, up == PG_CONV_DOWN2 ? 4 * Cin : (im2col ? Cin * ksize * ksize : Cin), Cout, 8, 8, im2col ? 1 : ksize, up == 2) != PG_OK) return -1;
-    return (int64_t)pl.ntiles_n * pl.nchunks * pl.b_stage;
+    return (int64_t)pl.ntiles_n * pl.nchunks * pl.b_stage + rowfold_pack_bytes(Cin, Cout, ksize, up);
 }
 
 static int conv_validate(int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t ksize, int32_t up, int32_t operand_format) {
@@ -1630,23 +1806,65 @@ extern "C" int pg_conv2d_igemm_prepack_batched(const float* w, int64_t w_batch_s
     rc = make_plan(pl, 1, down2 ? 4 * Cin : (im2col ? Cin * ksize * ksize : Cin), Cout, 8, 8, im2col ? 1 : ksize, up == 2, false, 4, false, n_tile);
     if (rc != PG_OK) return rc;
     PG_REQUIRE(n_tile == 0 || (n_tile % 16 == 0 && Cout % n_tile == 0 && up != 2), "conv2d_igemm: n_tile must be a multiple of 16 that divides Cout (no up-2)");
-    const int64_t need = (int64_t)pl.ntiles_n * pl.nchunks * pl.b_stage;
+    const int64_t need_main = (int64_t)pl.ntiles_n * pl.nchunks * pl.b_stage;
+    const int64_t need = need_main + rowfold_pack_bytes(Cin, Cout, ksize, up);                          // per-sample stride of the workspace
     PG_REQUIRE(workspace_bytes >= need * batch, "conv2d_igemm: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)(need * batch));
     PackParams pp;
     pp.w = w; pp.fir = fir; pp.out = workspace; pp.Cout = Cout; pp.Cin = Cin; pp.ks = ksize; pp.BN = pl.BN; pp.nchunks = pl.nchunks;
     pp.ntaps = pl.ntaps; pp.ntiles = pl.ntiles_n; pp.flip_weight = flip_weight ? 1 : 0; pp.fmt = operand_format; pp.up2 = up == 2; pp.down2 = down2; pp.w_scale = w_scale; pp.im2col = im2col;
     pp.w_bstride = w_batch_stride; pp.styles = styles;
-    const size_t pack_total = (size_t)need / 2;
+    const size_t pack_total = (size_t)need_main / 2;
     int pblocks = (int)((pack_total + 255) / 256);
     const int cap = kNumSMs * 16 / (batch < 16 ? batch : 16);
     if (pblocks > cap) pblocks = cap < 1 ? 1 : cap;
-    conv_prepack_kernel<<<dim3((unsigned)pblocks, (unsigned)batch), 256, 0, (cudaStream_t)stream>>>(pp);
+    conv_prepack_kernel<<<dim3((unsigned)pblocks, (unsigned)batch), 256, 0, (cudaStream_t)stream>>>(pp, (long long)(need / 2));
+    if (need > need_main) {
+        // the same weights in the row-folded layout, behind the folded-tap pack (conv_rowfold_kernel)
+        PackParams pr = pp;
+        pr.out = (uint8_t*)workspace + need_main; pr.BN = round_up(Cout, 16);
+        const int rblocks = (int)(((size_t)(need - need_main) / 2 + 255) / 256);
+        conv_rowfold_prepack_kernel<<<dim3((unsigned)rblocks, (unsigned)batch), 256, 0, (cudaStream_t)stream>>>(pr, (long long)(need / 2));
+        return launch_status("conv2d_igemm_prepack", 2);
+    }
     return launch_status("conv2d_igemm_prepack", 1);
 }
 
 extern "C" int pg_conv2d_igemm_prepack(const float* w, const float* fir, float w_scale, int32_t Cin, int32_t Cout, int32_t ksize, int32_t up,
                                        int32_t flip_weight, int32_t operand_format, void* workspace, int64_t workspace_bytes, void* stream) {
     return pg_conv2d_igemm_prepack_batched(w, 0, nullptr, 1, fir, w_scale, Cin, Cout, ksize, up, flip_weight, operand_format, 0, workspace, workspace_bytes, stream);
+}
+
+// Launch of conv_rowfold_kernel (eligibility is checked by the caller).  The packed weights sit behind the folded-tap pack of the same workspace.
+static int launch_rowfold(const pg_conv_args& a) {
+    using namespace pg;
+    RowFoldParams p;
+    memset(&p, 0, sizeof(p));
+    ConvPlan pl;
+    int rc = make_plan(pl, 1, a.Cin * a.ksize * a.ksize, a.Cout, 8, 8, 1, false);
+    if (rc != PG_OK) return rc;
+    p.x = (const float*)a.x; p.wpack = (const uint8_t*)a.wpack + (size_t)pl.ntiles_n * pl.nchunks * pl.b_stage; p.bias = a.bias; p.y = a.y;
+    p.N = a.N; p.Cin = a.Cin; p.Cout = a.Cout; p.H = a.H; p.W = a.W; p.ks = a.ksize; p.BN = round_up(a.Cout, 16);
+    p.nrows = a.Cin * a.ksize; p.nchunks = (p.nrows + 15) / 16;
+    p.act = a.act; p.alpha = a.alpha; p.gain = a.gain; p.clamp = a.clamp;
+    p.y_c8 = a.y_layout == PG_LAYOUT_C8; p.cb_out = a.Cout / 8;
+    p.idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | (8u << 24);
+    uint32_t cols = 32;
+    while (cols < (uint32_t)p.BN) cols <<= 1;
+    p.tmem_cols = cols;
+    p.wsegs = a.W / 128;
+    const long long tiles = (long long)a.N * a.H * p.wsegs;
+    PG_REQUIRE(tiles < (1ll << 31), "conv2d_igemm: too many tiles");
+    p.tiles_total = (int)tiles;
+    size_t smem = (size_t)kRfPlanes * kRfPA * 16 + (size_t)a.ksize * kRfPlanes * p.BN * 16 + (size_t)p.BN * 4 + 8 * kRfPlanes * 8 + 64;
+    // co-resident CTAs share the SM's 512 TMEM columns: never let more CTAs fit than can allocate (a CTA spinning in tcgen05.alloc until a
+    // persistent neighbour exits would run its tiles alone at the end)
+    const int want = (int)(512 / cols) < 5 ? (int)(512 / cols) : 5;
+    const size_t floor_smem = (size_t)(227 * 1024) / (size_t)(want + 1) + 1024;
+    if (smem < floor_smem) smem = floor_smem;
+    PG_CUDA(cudaFuncSetAttribute(conv_rowfold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long cap = (long long)kNumSMs * want;
+    conv_rowfold_kernel<<<(unsigned)(tiles < cap ? tiles : cap), kRfThreads, smem, (cudaStream_t)a.stream>>>(p);
+    return launch_status("conv2d_igemm(rowfold)", 1);
 }
 
 static int conv_run_impl(const pg_conv_args& a) {
@@ -1693,6 +1911,10 @@ static int conv_run_impl(const pg_conv_args& a) {
     if (down2) { H /= 2; W /= 2; Cin *= 4; }                      // the GEMM runs over the space-to-depth view at the output resolution
     const bool im2col = use_im2col(Cin, ksize, up);
     const int ks_real = ksize;
+    if (tn.rowfold && rowfold_shape_ok(Cin, Cout, ksize, up) && W % 128 == 0 && !scale && !x2 && !a.spade_x && !a.residual && !a.noise && !a.dcoefs &&
+        a.x_dtype == PG_F32 && a.x_layout == PG_LAYOUT_NCHW && operand_format == 0 && n_tile == 0 && a.wpack_sample_stride == 0 &&
+        (a.y_layout == PG_LAYOUT_C8 || a.y_dtype == PG_F32) && ((uintptr_t)a.wpack & 15) == 0)
+        return launch_rowfold(a);
     if (im2col) { Cin *= ksize * ksize; ksize = 1; }              // taps folded into K: a 1x1 convolution over Cin * k * k virtual channels
     ConvPlan pl;
     // Column bands for wide images (W >= 256): with the full-width strip a 256..512-position tile is 1..2 rows and stages 2..3x what it outputs

@@ -178,7 +178,7 @@ def _check_u8(t, name):
 def _launch_warps(jobs, device):
     """jobs: list of WarpJob (host).  One H2D copy of the table + one launch."""
     table = (_capi.WarpJob * len(jobs))(*jobs)
-    host = torch.frombuffer(ctypes.string_at(ctypes.addressof(table), ctypes.sizeof(table)), dtype=torch.uint8).clone()
+    host = torch.frombuffer(bytearray(ctypes.string_at(ctypes.addressof(table), ctypes.sizeof(table))), dtype=torch.uint8)
     dev = host.to(device, non_blocking=False)
     max_pix = max(j.dst_h * j.dst_w for j in jobs)
     _capi.require_device()

@@ -52,6 +52,39 @@ def test_plain_conv(cv, shape, fmt):
         assert rel_err(y, ref) < TOL[fmt], (shape, flip_weight)
 
 
+ROWFOLD = [
+    # (N, Cin, Cout, H, W, k): W % 128 == 0 and Cin * k <= 32 -> the row-folded first-layer kernel
+    (2, 3, 64, 40, 128, 7), (1, 3, 64, 256, 256, 7), (3, 3, 64, 17, 256, 3), (1, 4, 32, 9, 128, 5), (2, 6, 128, 12, 384, 3), (1, 1, 16, 5, 128, 7), (1, 3, 48, 300, 128, 7),
+]
+
+
+@pytest.mark.parametrize('shape', ROWFOLD, ids=[str(s) for s in ROWFOLD])
+def test_rowfold_first_layer(cv, shape):
+    """Small-Cin layers on wide images run conv_rowfold_kernel (kernel rows folded into K, horizontal taps as descriptor offsets): against the fp64
+    oracle, against the folded-tap path it replaces (same fp16 operand roundings, different summation order), and with a channel-blocked output."""
+    n, cin, cout, h, w, k = shape
+    torch.manual_seed(sum(shape))
+    x = torch.randn(n, cin, h, w)
+    wt = torch.randn(cout, cin, k, k) / (cin * k * k) ** 0.5
+    b = torch.randn(cout) * 0.2
+    xd, wd, bd = x.to(DEV), wt.to(DEV), b.to(DEV)
+    for flip_weight, act, gain, clamp in ((True, 'relu', 2 ** 0.5, None), (False, 'lrelu', 1.3, 1.5), (True, 'linear', 1.0, None)):
+        ref = O.bias_act(O._conv(x.double(), wt.double(), padding=k // 2, flip_weight=flip_weight), b.double(), act=act, gain=gain, clamp=clamp)
+        n0 = capi.launch_count()
+        y = cv.conv2d_igemm(xd, wd, flip_weight=flip_weight, bias=bd, act=act, gain=gain, clamp=clamp)
+        assert rel_err(y, ref) < TOL['fp16'], (shape, act)
+        capi.set_tuning('conv_rowfold', 0)
+        try:
+            y_old = cv.conv2d_igemm(xd, wd, flip_weight=flip_weight, bias=bd, act=act, gain=gain, clamp=clamp)
+        finally:
+            capi.set_tuning('conv_rowfold', 1)
+        assert rel_err(y, y_old) < 5e-5                                    # same operand roundings, different summation order
+        if cout % 16 == 0:
+            yc = cv.conv2d_igemm(xd, wd, flip_weight=flip_weight, bias=bd, act=act, gain=gain, clamp=clamp, out_c8=True)
+            assert torch.equal(cv.from_c8(yc, cout, dtype=torch.float16), y.half())
+        assert capi.launch_count() > n0
+
+
 def test_fused_epilogue_and_modulation(cv):
     """SynthesisLayer in one launch: styles, demodulation, noise, bias, lrelu, gain, clamp."""
     torch.manual_seed(1)
