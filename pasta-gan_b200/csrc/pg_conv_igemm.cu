@@ -646,37 +646,30 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const int n, 
             }
             return nvalid;
         };
-        // the residual of chunk cc + step is fetched while chunk cc is read from TMEM, transformed and stored (one memory round trip hidden)
-                    float res[16];
+        // the residual of chunk cc + step is fetched while chunk cc is read from TMEM, transformed and stored (one memory round trip hidden).  It stays
+        // in its raw form (16 floats, or 8 words of packed halves) until it is added: converting at fetch time would wait for the load on the spot
+        uint32_t res[16];
 #pragma unroll
-        for (int i = 0; i < 16; i++) res[i] = 0.f;
-        auto fetch_res = [&](int cc, float (&dst)[16]) {
+        for (int i = 0; i < 16; i++) res[i] = 0u;
+        auto fetch_res = [&](int cc, uint32_t (&dst)[16]) {
             if (!p.residual || !ok || cc >= ncol_chunks) return;
             if (p.res_c8) {
                 // channel-blocked fp16 residual: the chunk's 16 channels are two 16-byte rows at this pixel
                 const uint4* rb = reinterpret_cast<const uint4*>(p.residual) + ((size_t)n * p.cb_out + (size_t)(jn * p.BN + cc * 16) / 8) * HW + (size_t)h * p.Wimg + w;
-#pragma unroll
-                for (int j = 0; j < 2; j++) {
-                    const uint4 q4 = __ldg(rb + (size_t)j * HW);
-                    const unsigned int wds[4] = {q4.x, q4.y, q4.z, q4.w};
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&wds[e]));
-                        dst[8 * j + 2 * e] = f2.x; dst[8 * j + 2 * e + 1] = f2.y;
-                    }
-                }
+                const uint4 q0 = __ldg(rb), q1 = __ldg(rb + HW);
+                dst[0] = q0.x; dst[1] = q0.y; dst[2] = q0.z; dst[3] = q0.w; dst[4] = q1.x; dst[5] = q1.y; dst[6] = q1.z; dst[7] = q1.w;
                 return;
             }
             size_t off, ystride; int oy, ox;
             const int nvalid = chunk_out(cc, off, ystride, oy, ox);
 #pragma unroll
-            for (int i = 0; i < 16; i++) if (i < nvalid) dst[i] = __ldg(p.residual + off + (size_t)i * ystride);
+            for (int i = 0; i < 16; i++) if (i < nvalid) dst[i] = __float_as_uint(__ldg(p.residual + off + (size_t)i * ystride));
         };
         fetch_res(part, res);
         for (int cc = part; cc < ncol_chunks; cc += step) {
-            float res_next[16];
+            uint32_t res_next[16];
 #pragma unroll
-            for (int i = 0; i < 16; i++) res_next[i] = 0.f;
+            for (int i = 0; i < 16; i++) res_next[i] = 0u;
             fetch_res(cc + step, res_next);
             uint32_t r[16];
             tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.BN + cc * 16), r);
@@ -704,8 +697,16 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const int n, 
 #pragma unroll
                 for (int i = 0; i < 16; i++) v[i] = fminf(fmaxf(v[i], -cl), cl);
             }
+            if (p.res_c8) {
 #pragma unroll
-            for (int i = 0; i < 16; i++) v[i] += res[i];
+                for (int e = 0; e < 8; e++) {
+                    const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&res[e]));
+                    v[2 * e] += f2.x; v[2 * e + 1] += f2.y;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; i++) v[i] += __uint_as_float(res[i]);
+            }
             float* yp = p.y + off;
             if (p.y_c8) {
                 // channel-blocked fp16: the 16 channels of this chunk are two 16-byte rows, consecutive lanes write consecutive rows (host side
@@ -729,6 +730,42 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const int n, 
             }
 #pragma unroll
             for (int i = 0; i < 16; i++) res[i] = res_next[i];
+        }
+    }
+}
+
+// Residual prefetch.  The epilogue reads the residual one 16-channel chunk ahead of its use, i.e. ~1 KB in flight per warp: with one persistent CTA
+// per SM that is ~1 MB in flight on the whole GPU, and the layer becomes bound by DRAM latency instead of bandwidth (128->128 @128^2 with a residual:
+// 135 us against 73 us without).  The epilogue warps therefore pull the tile's residual lines into L2 BEFORE they wait for the accumulator (the main
+// loop of the tile is still running); the demand loads of epilogue_tile then hit L2.  One lane per 128-byte line issues the prefetch.
+__device__ __forceinline__ void prefetch_residual_tile(const ConvParams& p, const int n, const int jn, const int m0, const int HW, const int quarter,
+                                                       const int part, const int step, const int lane, const int band = 0) {
+    if (!p.residual || p.up2 || p.spade) return;
+    const int ncol_chunks = p.BN / 16;
+    for (int a = 0; a < p.NACC; a++) {
+        const int q = m0 + a * 128 + quarter * 32 + lane;
+        const int h = (int)__umulhi((uint32_t)q, p.pw_magic), ws = q - h * p.PW;
+        const int w = p.band_tw ? band * p.band_tw + ws - 2 : ws;
+        const bool ok = q < p.Lp && (p.band_tw ? (ws >= 2 && ws < p.band_tw + 2 && w < p.Wimg) : ws < p.W);
+        if (!ok) continue;
+        const size_t pix = (size_t)h * p.Wimg + w;
+        if (p.res_c8) {
+            if (lane != 0 && (pix & 7) != 0) continue;                       // 8 pixels x 16 B per line
+            const uint4* rb = reinterpret_cast<const uint4*>(p.residual) + ((size_t)n * p.cb_out + (size_t)(jn * p.BN) / 8) * HW + pix;
+            for (int cc = part; cc < ncol_chunks; cc += step) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rb + (size_t)(2 * cc) * HW));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rb + (size_t)(2 * cc + 1) * HW));
+            }
+        } else {
+            if (lane != 0 && (pix & 31) != 0) continue;                      // 32 pixels x 4 B per line
+            const int v0 = jn * p.BN;
+            const float* rp = p.residual + ((size_t)n * p.Cout + v0) * HW + pix;
+            for (int cc = part; cc < ncol_chunks; cc += step) {
+                const int nv = p.Cout - v0 - cc * 16;
+#pragma unroll 4
+                for (int i = 0; i < 16; i++)
+                    if (i < nv) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + (size_t)(cc * 16 + i) * HW));
+            }
         }
     }
 }
@@ -1124,6 +1161,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
         }
         if (cw == 0 && lane == 0) { PG_TS(6); PG_PUT(10, wait_e); PG_PUT(14, t_issue); PG_PUT(15, t_store); }
         // ===================== epilogue (same warps) =====================
+        prefetch_residual_tile(p, n, jn, m0, HW, warp & 3, cw >> 2, kConvWarps / 4, lane, band);
         mbar_wait(smem_u32(acc_full), 0);
         tc_fence_after();
         if (cw == 0 && lane == 0) PG_TS(4);
@@ -1295,7 +1333,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_igemm_persistent_kernel(con
 // Channel-blocked fp16 input (TMA operand path): no converter warps, so the whole CTA is three pipelines with nothing else in the way.
 //   warp 0      producer: per 16-channel chunk one A box (cp.async.bulk.tensor) and the chunk's weight slots (cp.async.bulk), rings run on across tiles
 //   warp 1      MMA issuer: tcgen05.mma into TMEM accumulator buffer (tile & 1); commits acc_full[buf] and goes straight on to the next tile
-//   warps 2..9  epilogue: wait acc_full[buf], drain TMEM (2 warps per lane quarter), arrive acc_empty[buf]
+//   warps 2..9  epilogue: wait acc_full[buf], drain TMEM (2 warps per lane quarter; 16 epilogue warps were measured: no gain), arrive acc_empty[buf]
 // One CTA per SM walks tiles t = blockIdx.x, + gridDim.x, ... of the list (jn, n, band, tile); TMEM holds two accumulator buffers of NACC * BN <= 256
 // columns, so the epilogue of tile i overlaps the main loop of tile i + 1 and the per-CTA prologue (TMEM allocation, barrier setup, pipeline fill)
 // is paid once per SM instead of once per tile.
@@ -1413,6 +1451,7 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_igemm_tma_persistent_kernel
             // passed the named barrier of tile it - 1, so it is free to overwrite
             stage_epilogue_constants(p, n, jn, sc, sh, et, 32 * kTEpiWarps);
             asm volatile("bar.sync 2, %0;" ::"r"(32 * kTEpiWarps) : "memory");
+            prefetch_residual_tile(p, n, jn, m0, HW, warp & 3, ew >> 2, kTEpiWarps / 4, lane, band);
             mbar_wait(smem_u32(&acc_full[buf]), ((uint32_t)it >> 1) & 1u);
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)buf * 256u;

@@ -489,10 +489,11 @@ class SpadeConv2dLayer(Conv2dLayer):
     def __init__(self, in_channels, out_channels, kernel_size, bias=True, activation='relu', **kw):
         super().__init__(in_channels, out_channels, kernel_size, bias=bias, activation=activation, **kw)
 
-    def forward(self, x, gain=1, no_act=False, residual=None):
-        y = self._fused(x, gain, not no_act, None, residual)
+    def forward(self, x, gain=1, no_act=False, residual=None, out_c8=False):
+        y = self._fused(x, gain, not no_act, None, residual, out_c8)
         if y is not None:
             return y
+        assert not out_c8
         if not no_act:
             x = self._act(x, gain)
         y = self._conv(x)
@@ -623,6 +624,15 @@ class ToRGBLayerFull(OpsModule):
         return head(self.weight, self.bias), parsing
 
 
+def K_supported_c8_out(layer, x):
+    """True when ``layer`` (a plain stride-1 Conv2dLayer) applied to the fp32 NCHW tensor ``x`` runs on the tcgen05 kernel, i.e. can write a
+    channel-blocked result."""
+    from .torch_utils.ops import conv_igemm as K
+    pad = int(layer.padding)
+    return x.ndim == 4 and layer.up == 1 and layer.down == 1 and int(layer.weight.shape[0]) % 16 == 0 and \
+        K.supported(x, layer.weight, up=1, down=1, f=layer.resample_filter, padding=(pad,) * 4)
+
+
 class ResBlock(OpsModule):
     def __init__(self, in_channels, out_channels, kernel_size, bias=True, activation='linear', up=1, down=1,
                  resample_filter=_FIR, conv_clamp=None, channels_last=False, trainable=True):
@@ -648,6 +658,10 @@ class ResBlock(OpsModule):
             assert inner and self.conv0.down == 1, 'a channel-blocked input needs the channel-blocked chain (stride 1)'
             y = self.skip(x, gain=np.sqrt(0.5), out_c8=True)
             return self.conv1(self.conv0(x, out_c8=True), gain=np.sqrt(0.5), residual=y, out_c8=out_c8)
+        if inner and self.conv0.down == 1 and K_supported_c8_out(self.skip, x):
+            # the skip branch is only ever read back as conv1's residual: channel-blocked fp16 (two 16-byte loads per thread and chunk in the
+            # epilogue instead of sixteen strided 4-byte loads)
+            return self.conv1(self.conv0(x, out_c8=True), gain=np.sqrt(0.5), residual=self.skip(x, gain=np.sqrt(0.5), out_c8=True))
         y = self.skip(x, gain=np.sqrt(0.5))
         if inner:
             return self.conv1(self.conv0(x, out_c8=True), gain=np.sqrt(0.5), residual=y)
@@ -791,9 +805,14 @@ class SpadeResBlockV2(OpsModule):
         pre = lambda conv, gain: (conv.activation, float(conv.act_gain * gain))
         stats_fn = getattr(self.ops, 'instance_stats', None)
         stats = stats_fn(x) if stats_fn is not None and not (torch.is_grad_enabled() and x.requires_grad) else None   # shared by spade_skip / spade0
-        y = self.skip(self.spade_skip(x, denorm_feat, post_act=pre(self.skip, np.sqrt(0.5)), stats=stats, out_half=True, out_k=1), no_act=True)
+        s_in = self.spade_skip(x, denorm_feat, post_act=pre(self.skip, np.sqrt(0.5)), stats=stats, out_half=True, out_k=1)
+        # inside a channel-blocked chain the skip branch (read back only as conv1's residual) stays channel-blocked fp16 too
+        y = self.skip(s_in, no_act=True, out_c8=(s_in.ndim == 5 and int(self.skip.weight.shape[0]) % 16 == 0))
         x = self.conv0(self.spade0(x, denorm_feat, post_act=pre(self.conv0, 1), stats=stats, out_half=True, out_k=3), no_act=True)
-        return self.conv1(self.spade1(x, denorm_feat, post_act=pre(self.conv1, np.sqrt(0.5)), out_half=True, out_k=3), no_act=True, residual=y)
+        t = self.spade1(x, denorm_feat, post_act=pre(self.conv1, np.sqrt(0.5)), out_half=True, out_k=3)
+        if y.ndim == 5 and t.ndim != 5:
+            y = _spade_to_nchw(y).float()                 # conv1 is not on the TMA path: its residual must be plain fp32
+        return self.conv1(t, no_act=True, residual=y)
 
 
 def _c8_chain_ok(block, x, cat_feat):

@@ -487,6 +487,22 @@ def test_c8_tma_path_bit_identical(cv, shape):
         assert torch.equal(y2, yc)
 
 
+@pytest.mark.parametrize('shape', [(2, 64, 64, 24, 24, 3), (1, 128, 128, 40, 128, 3), (2, 32, 48, 16, 256, 1)], ids=str)
+def test_channel_blocked_residual_with_dense_output(cv, shape):
+    """A skip branch that is only read back as a residual travels channel-blocked fp16 while the block's result stays fp32 NCHW: the same numbers
+    as the dense fp32 residual holding the fp16-rounded values, for the TMA and the converter operand paths."""
+    n, cin, cout, h, w, k = shape
+    torch.manual_seed(sum(shape))
+    xh = torch.randn(n, cin, h, w, device=DEV).half()
+    wt = torch.randn(cout, cin, k, k, device=DEV) / (cin * k * k) ** 0.5
+    b = torch.randn(cout, device=DEV) * 0.2
+    res = torch.randn(n, cout, h, w, device=DEV).half()
+    for x in (cv.to_c8(xh), xh.float()):
+        ref = cv.conv2d_igemm(x, wt, bias=b, gain=0.7, residual=res.float())
+        got = cv.conv2d_igemm(x, wt, bias=b, gain=0.7, residual=cv.to_c8(res))
+        assert got.dtype == torch.float32 and torch.equal(got, ref)
+
+
 def test_c8_tma_up2_spade_and_folded_styles(cv):
     """TMA operand path under the other epilogues: polyphase up-2, the SPADE epilogue (blocked in, blocked out), and a modulated layer whose styles
     are folded into per-sample packed weights (the activations cannot be scaled on the way in)."""

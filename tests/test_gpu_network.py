@@ -149,8 +149,8 @@ def test_generator_512_cuda_vs_reference(golden):
 
 
 def test_fused_inference_paths_are_equivalent(cuda_generator, monkeypatch):
-    """The host-side inference fusions do not change what is computed: fp16 intermediates between the SPADE blocks' convolutions are bit-identical
-    (the consumer multiplies the same fp16 operands either way), and the batched StyleBank agrees with the per-layer affine / demodulation path
+    """The host-side inference fusions do not change what is computed: fp16 intermediates between the SPADE blocks' convolutions carry the operand
+    bits the consumer would round to anyway (only the fp16 skip-branch residual adds a rounding), and the batched StyleBank agrees with the per-layer affine / demodulation path
     to GEMM rounding."""
     G = cuda_generator
     inp = procedural.synth_inputs(2, seed=77, device=DEV)
@@ -169,8 +169,10 @@ def test_fused_inference_paths_are_equivalent(cuda_generator, monkeypatch):
     # consumer's loader would produce from fp32, in the same accumulation order -> bit-identical outputs
     spade_only = run(PASTA_B200_C8_CHAIN='0')
     no_half = run(PASTA_B200_HALF_INTERMEDIATES='0')
+    # ... except the skip branch of each SPADE res-block, which is read back as a channel-blocked fp16 residual (one extra 2^-11 rounding of
+    # an addend, added in fp32): agreement to that rounding, not bit for bit
     for a, b in zip(spade_only, no_half):
-        assert torch.equal(a, b)
+        assert rel_err(a, b) < 2e-3
     # the channel-blocked chain of the >= 128 px synthesis blocks rounds activations to fp16 one layer earlier and folds styles into the weights
     # instead of the activations: same math, different roundings
     assert rel_err(base[0], no_half[0]) < 3e-3 and rel_err(base[2], no_half[2]) < 3e-3
