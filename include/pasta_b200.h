@@ -133,7 +133,8 @@ int pg_upfirdn2d_bias_act(const void* x, const float* f, const void* b, void* y,
  * polyphase form on the low-resolution input; `fir` is the [4,4] float32 filter (ignored when up == 1).
  * styles [N,Cin], dcoefs [N,Cout], bias [Cout], noise ([H*up,W*up] with noise_batch_stride 0, or per-sample with stride in
  * elements) may each be NULL.  in_act / act: PG_ACT_LINEAR / RELU / LRELU.  clamp < 0: none.
- * operand_format: 0 = fp16 (10-bit mantissa, saturating), 1 = bf16.
+ * operand_format: 0 = fp16 (10-bit mantissa, saturating), 1 = bf16, 2 = tf32 (10-bit mantissa, fp32 exponent range; half the tensor rate, dense fp32 / fp16
+ *                 NCHW inputs only: no channel-blocked input, packed weights take twice the bytes -> pg_conv2d_igemm_workspace_bytes_fmt).
  * workspace: device scratch of at least pg_conv2d_igemm_workspace_bytes(...) bytes (packed weights), caller-owned.
  * Forward only: gradients of convolutions stay on conv2d_gradfix in this release.
  */
@@ -141,7 +142,8 @@ int pg_upfirdn2d_bias_act(const void* x, const float* f, const void* b, void* y,
  * conv2d_resample.py:119-122 (4x4 FIR with padding 2, then the 3x3 convolution at stride 2; y is [N,Cout,H/2,W/2]) evaluated as a
  * 'same' 3x3 convolution over the four space-to-depth planes of x with the 6x6 composite kernel w (*) f — no filtered intermediate. */
 #define PG_CONV_DOWN2 (-2)
-int64_t pg_conv2d_igemm_workspace_bytes(int32_t Cin, int32_t Cout, int32_t ksize, int32_t up);
+int64_t pg_conv2d_igemm_workspace_bytes(int32_t Cin, int32_t Cout, int32_t ksize, int32_t up);                 /* operand_format 0 / 1 */
+int64_t pg_conv2d_igemm_workspace_bytes_fmt(int32_t Cin, int32_t Cout, int32_t ksize, int32_t up, int32_t operand_format);
 /* The same operation in two steps, so that inference can pack the weights once per parameter version:
  *   prepack: w * w_scale (the layer's weight_gain, training/networks.py:171) -> fp16/bf16 GEMM tiles in `workspace`
  *   run:     the convolution proper on packed weights.  pg_conv2d_igemm_fwd == prepack(w_scale = 1) + run. */

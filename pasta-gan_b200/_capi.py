@@ -31,6 +31,7 @@ SIGNATURES = {
     'pg_upfirdn2d': [c_ptr, c_ptr, c_ptr, I32x4, I64x4, I32x4, I64x4, c_i32, c_i32, c_i64, c_i64] + [c_i32] * 8 +
                     [c_i32, c_f32, c_i32, c_ptr],
     'pg_conv2d_igemm_workspace_bytes': [c_i32, c_i32, c_i32, c_i32],
+    'pg_conv2d_igemm_workspace_bytes_fmt': [c_i32, c_i32, c_i32, c_i32, c_i32],
     'pg_conv2d_igemm_prepack': [c_ptr, c_ptr, c_f32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr, c_i64, c_ptr],
     'pg_conv2d_igemm_run': [c_ptr] * 5 + [c_i64, c_ptr, c_ptr] + [c_i32] * 7 + [c_i32, c_f32, c_f32, c_i32, c_f32, c_f32, c_f32, c_i32, c_ptr],
     'pg_conv2d_igemm_run2': [c_ptr, c_ptr, c_i32] + [c_ptr] * 4 + [c_i64, c_ptr, c_ptr, c_ptr] + [c_i32] * 7 + [c_i32, c_f32, c_f32, c_i32, c_f32, c_f32, c_f32, c_i32, c_i32, c_i32, c_ptr],
@@ -116,7 +117,7 @@ def load():
         for name, argtypes in SIGNATURES.items():
             fn = getattr(lib, name)                     # AttributeError if the symbol is not exported
             fn.argtypes = argtypes
-            fn.restype = {'pg_last_error': ctypes.c_char_p, 'pg_launch_count': c_i64, 'pg_conv2d_igemm_workspace_bytes': c_i64, 'pg_conv2d_wgrad_workspace_bytes': c_i64}.get(name, c_int)
+            fn.restype = {'pg_last_error': ctypes.c_char_p, 'pg_launch_count': c_i64, 'pg_conv2d_igemm_workspace_bytes': c_i64, 'pg_conv2d_igemm_workspace_bytes_fmt': c_i64, 'pg_conv2d_wgrad_workspace_bytes': c_i64}.get(name, c_int)
         if lib.pg_abi_version() != 2:
             raise PastaB200Error(f'ABI mismatch: library reports {lib.pg_abi_version()}, binding expects 2')
         if hasattr(lib, 'pg_debug_set_buffer'):                      # -DPG_DEBUG builds only (tools/conv_timeline.py)

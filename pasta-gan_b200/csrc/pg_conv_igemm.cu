@@ -143,6 +143,19 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// fp32 -> tf32 (10-bit mantissa, round to nearest, ties away): the tensor core would otherwise just drop the low 13 bits
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -228,17 +241,18 @@ __global__ void conv_prepack_kernel(PackParams p, long long out_sample_stride_ha
     const int nvirt = p.up2 ? 4 * p.Cout : p.Cout;
     const int sample = blockIdx.y;
     p.w += (size_t)sample * p.w_bstride;
-    p.out = (void*)((uint16_t*)p.out + (size_t)sample * out_sample_stride_halves);
+    p.out = (void*)((uint16_t*)p.out + (size_t)sample * out_sample_stride_halves);      // (stride counted in 2-byte units for every format)
     const float* sty = p.styles ? p.styles + (size_t)sample * p.Cin : nullptr;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         size_t r = idx;
-        const int e = r % 8; r /= 8;
+        const int epp = p.fmt == 2 ? 4 : 8, npl = p.fmt == 2 ? 4 : 2;      // elements per 16-byte row, planes per 16-channel chunk
+        const int e = r % epp; r /= epp;
         const int nl = r % p.BN; r /= p.BN;
-        const int j = r % 2; r /= 2;
+        const int j = r % npl; r /= npl;
         const int tap = r % p.ntaps; r /= p.ntaps;
         const int ci = r % p.nchunks; r /= p.nchunks;
         const int jn = (int)r;
-        const int v = jn * p.BN + nl, c = ci * kKC + j * 8 + e;
+        const int v = jn * p.BN + nl, c = ci * kKC + j * epp + e;
         float val = 0.f;
         if (p.down2) {
             // c runs over the 4 * Cin virtual channels (row parity a, then real channel, then column parity b: the order in which the
@@ -270,8 +284,9 @@ __global__ void conv_prepack_kernel(PackParams p, long long out_sample_stride_ha
             const int cr = p.down2 ? ((c % (2 * p.Cin)) >> 1) : (p.im2col ? c / (p.ks * p.ks) : c);
             val *= sty[cr];
         }
-        if (p.fmt == 0) ((__half*)p.out)[idx] = __float2half_rn(fminf(fmaxf(val, -65504.f), 65504.f));
-        else            ((__nv_bfloat16*)p.out)[idx] = __float2bfloat16_rn(val);
+        if (p.fmt == 0)      ((__half*)p.out)[idx] = __float2half_rn(fminf(fmaxf(val, -65504.f), 65504.f));
+        else if (p.fmt == 1) ((__nv_bfloat16*)p.out)[idx] = __float2bfloat16_rn(val);
+        else                 ((uint32_t*)p.out)[idx] = to_tf32(val);
     }
 }
 
@@ -314,6 +329,19 @@ __device__ __forceinline__ void mma_issue_loop(const ConvParams& p, uint32_t a_b
                     const uint32_t s0 = (KS == 3) ? (uint32_t)kh * pw + (uint32_t)kw : 0u;     // tap shift in strip positions == 16-byte rows
                     const uint64_t bdesc = ((uint64_t)hi << 32) | (uint64_t)(b_lo + (uint32_t)kw * b_tile16);
                     const uint32_t acc_flag = (ci | kh | kw) ? 1u : 0u;
+                    if (p.fmt == 2) {
+                        // tf32: K = 8 per MMA, a 16-channel chunk is two K steps; step 1 starts two 4-channel planes further into the stage / weight tile
+#pragma unroll
+                        for (int kstep = 0; kstep < 2; kstep++) {
+                            const uint64_t bd = bdesc + (uint64_t)((uint32_t)kstep * 2u * bn);
+#pragma unroll
+                            for (int a = 0; a < NACC; a++) {
+                                const uint64_t adesc = ((uint64_t)hi << 32) | (uint64_t)(a_lo + s0 + (uint32_t)a * 128u + (uint32_t)kstep * 2u * p.a_lbo16);
+                                umma_tf32(tmem_base + (uint32_t)a * bn, adesc, bd, idesc, acc_flag | (uint32_t)kstep);
+                            }
+                        }
+                        continue;
+                    }
 #pragma unroll
                     for (int a = 0; a < NACC; a++) {
                         const uint64_t adesc = ((uint64_t)hi << 32) | (uint64_t)(a_lo + s0 + (uint32_t)a * 128u);
@@ -1147,6 +1175,11 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
                 if (tt < ntasks && !(PG_DBGMODE(p) & 2)) {
                     const int plane = tt & 1, spos = (tt >> 1) * 32 + lane;
                     if (SCALE) scale8(v, ci, plane);
+                    if (p.fmt == 2) {       // tf32: the 8 channels of this task are two 4-channel planes
+                        uint8_t* dst = a_base + (size_t)s_st * p.a_stage_bytes + (size_t)(2 * plane) * p.PA * 16 + (size_t)spos * 16;
+                        *reinterpret_cast<uint4*>(dst) = make_uint4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
+                        *reinterpret_cast<uint4*>(dst + (size_t)p.PA * 16) = make_uint4(to_tf32(v[4]), to_tf32(v[5]), to_tf32(v[6]), to_tf32(v[7]));
+                    } else
                     *reinterpret_cast<uint4*>(a_base + (size_t)s_st * p.a_stage_bytes + (size_t)plane * p.PA * 16 + (size_t)spos * 16) = pack8(v);
                 }
                 if (idx == tpw - 1) stage_end();
@@ -1676,7 +1709,8 @@ static Tuning& tuning() {
 }
 
 static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int ks, int up2, bool band = false, int max_nacc = 4, bool tma = false, int n_tile = 0,
-                     int forced_nacc = 0) {
+                     int forced_nacc = 0, int wide = 0) {
+    // wide: tf32 operands (4-byte elements): a 16-channel chunk is four planes of four channels, stages and weight tiles are twice as large
     const Tuning& tn = tuning();
     pl.nvirt = up2 ? 4 * Cout : Cout;
     pl.ntaps = ks * ks;
@@ -1719,7 +1753,7 @@ static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int k
     pl.tiles_per_img = (pl.Lp + BM - 1) / BM;
     const int halo = (ks == 3) ? 2 * pl.PW + 2 : 0;
     pl.PA = round_up(BM + halo, 32);
-    pl.a_stage = (uint32_t)pl.PA * 32u;                        // 2 planes x 16 B per position
+    pl.a_stage = (uint32_t)pl.PA * 32u * (wide ? 2u : 1u);     // 2 planes x 16 B per position (tf32: 4 planes)
     pl.tma_rows = 0; pl.a_lbo16 = (uint32_t)pl.PA;
     if (tma) {
         // the box starts at the image row that holds the tile's first staged position: up to PW - 1 positions before it, BM + halo after
@@ -1727,7 +1761,7 @@ static int make_plan(ConvPlan& pl, int N, int Cin, int Cout, int H, int W, int k
         pl.a_lbo16 = (uint32_t)(pl.tma_rows * pl.PW);
         pl.a_stage = (uint32_t)round_up(2 * pl.tma_rows * pl.PW * 16, 128);
     }
-    pl.b_tile = (uint32_t)bn * 32u;
+    pl.b_tile = (uint32_t)bn * 32u * (wide ? 2u : 1u);
     pl.b_stage = pl.b_tile * pl.ntaps;
     const size_t fixed = (size_t)pl.nchunks * kKC * 4 + (size_t)bn * 8 + 96 * 8 + ((ks == 1 && Cin <= 160) ? 160 * 8 : 0);   // last term: folded-tap offset table
     pl.tps = (ks == 3) ? 3 : 1;
@@ -1811,11 +1845,15 @@ static int64_t rowfold_pack_bytes(int Cin, int Cout, int ksize, int up) {
     return rowfold_shape_ok(Cin, Cout, ksize, up) ? (int64_t)ksize * pg::kRfPlanes * ((Cout + 15) / 16 * 16) * 16 : 0;
 }
 
-extern "C" int64_t pg_conv2d_igemm_workspace_bytes(int32_t Cin, int32_t Cout, int32_t ksize, int32_t up) {
+extern "C" int64_t pg_conv2d_igemm_workspace_bytes_fmt(int32_t Cin, int32_t Cout, int32_t ksize, int32_t up, int32_t operand_format) {
     pg::ConvPlan pl;
     const bool im2col = use_im2col(Cin, ksize, up);
-    if (pg::make_plan(pl, 1, up == PG_CONV_DOWN2 ? 4 * Cin : (im2col ? Cin * ksize * ksize : Cin), Cout, 8, 8, im2col ? 1 : ksize, up == 2) != PG_OK) return -1;
+    if (pg::make_plan(pl, 1, up == PG_CONV_DOWN2 ? 4 * Cin : (im2col ? Cin * ksize * ksize : Cin), Cout, 8, 8, im2col ? 1 : ksize, up == 2,
+                      false, 4, false, 0, 0, operand_format == 2) != PG_OK) return -1;
     return (int64_t)pl.ntiles_n * pl.nchunks * pl.b_stage + rowfold_pack_bytes(Cin, Cout, ksize, up);
+}
+extern "C" int64_t pg_conv2d_igemm_workspace_bytes(int32_t Cin, int32_t Cout, int32_t ksize, int32_t up) {
+    return pg_conv2d_igemm_workspace_bytes_fmt(Cin, Cout, ksize, up, 0);
 }
 
 static int conv_validate(int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t ksize, int32_t up, int32_t operand_format) {
@@ -1825,7 +1863,7 @@ static int conv_validate(int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_
     PG_REQUIRE(up == 1 || ((up == 2 || up == PG_CONV_DOWN2) && ksize == 3), "conv2d_igemm: resample must be 1, 2 (up) or PG_CONV_DOWN2, the latter two with a 3x3 kernel");
     PG_REQUIRE(up != PG_CONV_DOWN2 || (Cin % 16 == 0 && H % 2 == 0 && W % 2 == 0), "conv2d_igemm: down-2 needs Cin %% 16 == 0 and even H, W");
     PG_REQUIRE(N >= 0 && Cin >= 1 && Cout >= 1 && H >= 1 && W >= 1, "conv2d_igemm: bad sizes");
-    PG_REQUIRE(operand_format == 0 || operand_format == 1, "conv2d_igemm: operand_format must be 0 (fp16) or 1 (bf16)");
+    PG_REQUIRE(operand_format >= 0 && operand_format <= 2, "conv2d_igemm: operand_format must be 0 (fp16), 1 (bf16) or 2 (tf32)");
     PG_REQUIRE(up == 1 || Cout % 16 == 0, "conv2d_igemm: up=2 needs Cout to be a multiple of 16");
     return PG_OK;
 }
@@ -1842,7 +1880,7 @@ extern "C" int pg_conv2d_igemm_prepack_batched(const float* w, int64_t w_batch_s
     const bool down2 = up == PG_CONV_DOWN2;
     ConvPlan pl;
     const bool im2col = use_im2col(Cin, ksize, up);
-    rc = make_plan(pl, 1, down2 ? 4 * Cin : (im2col ? Cin * ksize * ksize : Cin), Cout, 8, 8, im2col ? 1 : ksize, up == 2, false, 4, false, n_tile);
+    rc = make_plan(pl, 1, down2 ? 4 * Cin : (im2col ? Cin * ksize * ksize : Cin), Cout, 8, 8, im2col ? 1 : ksize, up == 2, false, 4, false, n_tile, 0, operand_format == 2);
     if (rc != PG_OK) return rc;
     PG_REQUIRE(n_tile == 0 || (n_tile % 16 == 0 && Cout % n_tile == 0 && up != 2), "conv2d_igemm: n_tile must be a multiple of 16 that divides Cout (no up-2)");
     const int64_t need_main = (int64_t)pl.ntiles_n * pl.nchunks * pl.b_stage;
@@ -1852,7 +1890,7 @@ extern "C" int pg_conv2d_igemm_prepack_batched(const float* w, int64_t w_batch_s
     pp.w = w; pp.fir = fir; pp.out = workspace; pp.Cout = Cout; pp.Cin = Cin; pp.ks = ksize; pp.BN = pl.BN; pp.nchunks = pl.nchunks;
     pp.ntaps = pl.ntaps; pp.ntiles = pl.ntiles_n; pp.flip_weight = flip_weight ? 1 : 0; pp.fmt = operand_format; pp.up2 = up == 2; pp.down2 = down2; pp.w_scale = w_scale; pp.im2col = im2col;
     pp.w_bstride = w_batch_stride; pp.styles = styles;
-    const size_t pack_total = (size_t)need_main / 2;
+    const size_t pack_total = (size_t)need_main / (operand_format == 2 ? 4 : 2);
     int pblocks = (int)((pack_total + 255) / 256);
     const int cap = kNumSMs * 16 / (batch < 16 ? batch : 16);
     if (pblocks > cap) pblocks = cap < 1 ? 1 : cap;
@@ -1971,7 +2009,8 @@ static int conv_run_impl(const pg_conv_args& a) {
     // (W is the GEMM's width here: the output width for down-2, the input width for up-2.)
     // TMA boxes hold at most 128 strip positions per row, so a channel-blocked input wider than 127 columns (3x3) is always processed in bands.
     const bool tma_needs_bands = tma && ksize == 3 && W + 1 > 128;
-    if ((tn.bands || tma_needs_bands) && ksize == 3 && !im2col && W >= (tma_needs_bands ? 1 : tn.band_minw) && W % 2 == 0 &&
+    const int wide = operand_format == 2;     // tf32 operands: generic converter path only (no bands, no lean / pair loaders, no TMA)
+    if ((tn.bands || tma_needs_bands) && !wide && ksize == 3 && !im2col && W >= (tma_needs_bands ? 1 : tn.band_minw) && W % 2 == 0 &&
         (tma || (((uintptr_t)x & 7) == 0 && ((uintptr_t)x2 & 7) == 0 && tn.vec2 && tn.lean))) {
         ConvPlan pb, pf;
         const int nb = (W + kBandTW - 1) / kBandTW;
@@ -1991,7 +2030,7 @@ static int conv_run_impl(const pg_conv_args& a) {
     }
     PG_REQUIRE(!tma_needs_bands || band_tw, "conv2d_igemm: no band plan for a channel-blocked input of width %d", Wimg);
     if (!band_tw) {
-        rc = make_plan(pl, N, Cin, Cout, H, W, ksize, up == 2, false, max_nacc, tma, n_tile);
+        rc = make_plan(pl, N, Cin, Cout, H, W, ksize, up == 2, false, max_nacc, tma, n_tile, 0, wide);
         if (rc != PG_OK) return rc;
     }
     PG_REQUIRE(!tma || (2 * pl.PW <= 256 && pl.tma_rows <= 256), "conv2d_igemm: TMA box out of range (PW=%d rows=%d)", pl.PW, pl.tma_rows);
@@ -2031,7 +2070,8 @@ static int conv_run_impl(const pg_conv_args& a) {
     p.cgroups = 1;
     p.pw_magic = (uint32_t)((0x100000000ull + (uint64_t)pl.PW - 1) / (uint64_t)pl.PW);
     p.w_magic = (uint32_t)((0x100000000ull + (uint64_t)W - 1) / (uint64_t)W);
-    p.vec2 = (!tma && !down2 && !im2col && W % 2 == 0 && ((uintptr_t)x & 7) == 0 && ((uintptr_t)x2 & 7) == 0 && tn.vec2) ? 1 : 0;
+    p.vec2 = (!tma && !down2 && !im2col && !wide && W % 2 == 0 && ((uintptr_t)x & 7) == 0 && ((uintptr_t)x2 & 7) == 0 && tn.vec2) ? 1 : 0;
+    if (wide) p.lean = 0;
     p.in_half = a.x_dtype == PG_F16; p.out_half = a.y_dtype == PG_F16;
     if (p.in_half && !tma) {
         // fp16 NCHW input: taken as the operand bits (no conversion), so no input scale / activation, fp16 operand format, the aligned pair loader

@@ -15,7 +15,7 @@ import torch
 from . import _backend
 
 _ACT = {'linear': 1, 'relu': 2, 'lrelu': 3}
-_FMT = {'fp16': 0, 'bf16': 1}
+_FMT = {'fp16': 0, 'bf16': 1, 'tf32': 2}
 
 enabled = os.environ.get('PASTA_B200_CONV', '1') != '0'
 operand_format = os.environ.get('PASTA_B200_CONV_FMT', 'fp16')
@@ -149,8 +149,8 @@ def _run_prepack(capi, w, f, w_scale, mode, flip_weight, fmt_code, ws, batch=1, 
     capi.check(rc, 'pg_conv2d_igemm_prepack')
 
 
-def _workspace_bytes(capi, cin, cout, k, mode):
-    n = int(capi.load().pg_conv2d_igemm_workspace_bytes(cin, cout, k, mode))
+def _workspace_bytes(capi, cin, cout, k, mode, fmt_code=0):
+    n = int(capi.load().pg_conv2d_igemm_workspace_bytes_fmt(cin, cout, k, mode, fmt_code))
     if n < 0:
         capi.check(2, 'pg_conv2d_igemm_workspace_bytes')
     return n
@@ -161,7 +161,7 @@ def _packed_weights(capi, w, f, w_scale, mode, flip_weight, fmt_code, cache, n_t
     long-lived tensor (a Parameter / buffer): the packed copy lives in the store above and is refreshed in place when ``w`` changes."""
     cout, cin, k, _ = (int(v) for v in w.shape)
     if not cache:
-        ws = torch.empty(_workspace_bytes(capi, cin, cout, k, mode), dtype=torch.uint8, device=w.device)
+        ws = torch.empty(_workspace_bytes(capi, cin, cout, k, mode, fmt_code), dtype=torch.uint8, device=w.device)
         _run_prepack(capi, w, f, w_scale, mode, flip_weight, fmt_code, ws, n_tile=n_tile)
         return ws
     key = (id(w), _pack_cfg(w_scale, mode, flip_weight, fmt_code, n_tile))
@@ -175,7 +175,7 @@ def _packed_weights(capi, w, f, w_scale, mode, flip_weight, fmt_code, cache, n_t
         e = _PackEntry()
         wid = id(w)
         e.wref = weakref.ref(w, lambda _r, wid=wid: _drop_entries(wid))
-        e.ws = torch.empty(_workspace_bytes(capi, cin, cout, k, mode), dtype=torch.uint8, device=w.device)
+        e.ws = torch.empty(_workspace_bytes(capi, cin, cout, k, mode, fmt_code), dtype=torch.uint8, device=w.device)
         e.cfg = (mode, flip_weight, fmt_code, w_scale, n_tile)
         e.version = None
         _pack_store[key] = e
@@ -329,13 +329,15 @@ def conv2d_igemm(x, w, f=None, up=1, down=1, flip_weight=True, styles=None, dcoe
             assert residual.dtype == torch.float32 and residual.shape == y.shape
         residual = residual.contiguous()
     fmt_code = _FMT[fmt or operand_format]
+    if fmt_code == 2:
+        assert not x_c8 and x.dtype == torch.float32, 'tf32 operands are converted from dense float32 activations (no channel-blocked / float16 input)'
     n_tile = _auto_n_tile(n, cout, oh, ow, k, up)
     with torch.cuda.device(x.device):
         capi.require_device()
         sample_stride = 0
         if per_sample_weights or (fold_styles and styles is not None):
             # one packed weight set per sample, built per call (the weights are a function of this batch's styles)
-            per = _workspace_bytes(capi, cin, cout, k, mode)
+            per = _workspace_bytes(capi, cin, cout, k, mode, fmt_code)
             wpack = torch.empty(per * n, dtype=torch.uint8, device=x.device)
             if per_sample_weights:
                 _run_prepack(capi, w, f, w_scale, mode, flip_weight, fmt_code, wpack, batch=n, w_batch_stride=cout * cin * k * k, n_tile=n_tile)

@@ -11,7 +11,7 @@ from oracle import ops_oracle as O
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda'
-TOL = {'fp16': 2e-3, 'bf16': 1.5e-2}
+TOL = {'fp16': 2e-3, 'bf16': 1.5e-2, 'tf32': 2e-3}
 
 
 @pytest.fixture(scope='module')
@@ -39,7 +39,7 @@ PLAIN = [
 
 
 @pytest.mark.parametrize('shape', PLAIN, ids=[str(s) for s in PLAIN])
-@pytest.mark.parametrize('fmt', ['fp16', 'bf16'])
+@pytest.mark.parametrize('fmt', ['fp16', 'bf16', 'tf32'])
 def test_plain_conv(cv, shape, fmt):
     n, cin, cout, h, w, k = shape
     torch.manual_seed(sum(shape))
@@ -83,6 +83,38 @@ def test_rowfold_first_layer(cv, shape):
             yc = cv.conv2d_igemm(xd, wd, flip_weight=flip_weight, bias=bd, act=act, gain=gain, clamp=clamp, out_c8=True)
             assert torch.equal(cv.from_c8(yc, cout, dtype=torch.float16), y.half())
         assert capi.launch_count() > n0
+
+
+def test_tf32_operand_kind(cv):
+    """kind::tf32 (north_star: "TF32/BF16 tensor cores, fp32 accumulate"): fp32 exponent range, 10-bit mantissa.  Modulated layer with noise / bias /
+    lrelu / clamp, up-2 and down-2 forms, the fused concat, a SPADE-style input activation -- all against the fp64 oracle -- and activations far
+    outside the fp16 range (1e6), which the fp16 operand format cannot represent."""
+    torch.manual_seed(7)
+    n, cin, cout, h, w = 2, 48, 64, 20, 28
+    x = torch.randn(n, cin, h, w)
+    wt = torch.randn(cout, cin, 3, 3) / (cin * 9) ** 0.5
+    st = 1 + 0.3 * torch.randn(n, cin)
+    dc = (torch.einsum('oikl,ni->no', wt.square(), st.square()) + 1e-8).rsqrt()
+    b = torch.randn(cout) * 0.2
+    nz = torch.randn(h, w) * 0.1
+    ref = O.bias_act(O._conv(x.double() * st.double()[:, :, None, None], wt.double(), padding=1) * dc.double()[:, :, None, None] + nz.double(), b.double(),
+                     act='lrelu', gain=2 ** 0.5, clamp=3.0)
+    y = cv.conv2d_igemm(x.to(DEV), wt.to(DEV), styles=st.to(DEV), dcoefs=dc.to(DEV), noise=nz.to(DEV), bias=b.to(DEV), act='lrelu', gain=2 ** 0.5, clamp=3.0, fmt='tf32')
+    assert rel_err(y, ref) < TOL['tf32']
+    f = O.setup_filter([1, 3, 3, 1])
+    for up, down in ((2, 1), (1, 2)):
+        ref = O.conv2d_resample(x.double(), wt.double(), f.double(), up=up, down=down, padding=1, flip_weight=(up == 1))
+        y = cv.conv2d_igemm(x.to(DEV), wt.to(DEV), f=f.to(DEV), up=up, down=down, flip_weight=(up == 1), fmt='tf32')
+        assert rel_err(y, ref) < TOL['tf32'], (up, down)
+    x2 = torch.randn(n, 16, h, w)
+    w2 = torch.randn(cout, cin + 16, 1, 1) / (cin + 16) ** 0.5
+    ref = O._conv(torch.relu(torch.cat([x, x2], 1).double()) * 1.3, w2.double(), padding=0)
+    y = cv.conv2d_igemm(x.to(DEV), w2.to(DEV), x2=x2.to(DEV), in_act='relu', in_gain=1.3, fmt='tf32')
+    assert rel_err(y, ref) < TOL['tf32']
+    big = x * 1e6                                                         # fp16 saturates at 65504: tf32 keeps the fp32 exponent
+    ref = O._conv(big.double(), wt.double(), padding=1)
+    assert rel_err(cv.conv2d_igemm(big.to(DEV), wt.to(DEV), fmt='tf32'), ref) < TOL['tf32']
+    assert rel_err(cv.conv2d_igemm(big.to(DEV), wt.to(DEV), fmt='fp16'), ref) > 0.5
 
 
 def test_fused_epilogue_and_modulation(cv):

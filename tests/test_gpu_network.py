@@ -63,6 +63,21 @@ def test_generator_cuda_vs_reference(golden, cuda_generator):
     assert flips < 1e-3, flips
 
 
+def test_generator_tf32_operands(golden, cuda_generator, monkeypatch):
+    """The same generator with every convolution on kind::tf32 (PASTA_B200_CONV_FMT=tf32; the channel-blocked fp16 chains switch themselves off):
+    the north_star's other named operand format, held to the same 1e-2 on the coarse image and the parsing logits."""
+    from pasta_gan_b200.torch_utils.ops import conv_igemm
+    monkeypatch.setattr(conv_igemm, 'operand_format', 'tf32')
+    g = golden('generator_full')
+    inp = procedural.synth_inputs(2, device=DEV)
+    with torch.no_grad():
+        img, fimg, parsing = cuda_generator(**inp, noise_mode='const')
+    assert rel_err(img, g.t('img', dtype=torch.float32)) < 1e-2
+    assert rel_err(parsing, g.t('pred_parsing', dtype=torch.float32)) < 1e-2
+    ref = g.t('finetune_img', dtype=torch.float32)
+    assert float((fimg.cpu().double() - ref.double()).norm() / ref.double().norm()) < 1e-2
+
+
 def test_fine_image_with_pinned_labels(golden, cuda_generator):
     """The fine-tuned image with the reference's own argmax labels fed to the fine stage (label_override): with the discontinuity of
     networks.py:5823-5826 out of the way it is a smooth function of the inputs and is held to the north_star's 1e-2 in MAX-ABS relative error."""
