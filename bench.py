@@ -212,6 +212,34 @@ def time_cpu_oracle(steps, warmup, batch=1):
                 seconds=dt, ms_per_step=1e3 * dt / steps)
 
 
+def time_patch_routing(batch=16, reps=5):
+    """the data loader's patch routing (training/dataset.py:838-927: 56 cv2.warpPerspective calls per sample) as two launches per batch
+    on the GPU, beside the oracle's restatement of the OpenCV arithmetic on one host core.  Wall clock around whole normalize() calls (host geometry +
+    job table upload + kernels + sync), uint8 images resident on the device."""
+    import numpy as np
+    from pasta_gan_b200 import patch_routing as PR, synthetic
+    d = synthetic.synth_patch_routing_inputs(batch, seed=3)
+    dev = {k: torch.from_numpy(v).cuda() for k, v in d.items() if k != 'keypoints'}
+    router = PR.PatchRouter()
+    run = lambda: router.normalize(dev['upper_img'], dev['lower_img'], dev['upper_clothes_mask'], dev['lower_clothes_mask'], d['keypoints'], 2)
+    run(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        out = run()
+    torch.cuda.synchronize()
+    t_gpu = (time.perf_counter() - t0) / reps
+    from oracle import warp_oracle as WO                                  # checker + CPU baseline only
+    t0 = time.perf_counter()
+    ncpu = 2
+    for b in range(ncpu):
+        ref = WO.normalize(d['upper_img'][b], d['lower_img'][b], d['upper_clothes_mask'][b], d['lower_clothes_mask'][b], d['keypoints'][b], 2)
+    t_cpu = (time.perf_counter() - t0) / ncpu
+    exact = all(np.array_equal(out[i][ncpu - 1].cpu().numpy(), ref[i]) for i in (0, 1, 2, 3, 6, 7))
+    return dict(value=batch / t_gpu, unit='samples/s', ms_per_batch=1e3 * t_gpu, batch=batch, launches_per_batch=3, bit_exact_vs_oracle=bool(exact),
+                cpu_baseline=dict(value=1.0 / t_cpu, unit='samples/s', cores=1, kind='port', sample=f'{ncpu} samples, numpy restatement of cv2.warpPerspective (cv2 is not in this image: parity unpinned)'),
+                what='PatchRouter.normalize: 28 rectifying warps + the back-warp composite per sample, uint8, OpenCV fixed-point bilinear')
+
+
 def run_reference(args, world, rank):
     if rank != 0:
         return
@@ -410,6 +438,10 @@ def run_b200(args, world, rank, local):
                     extra['gen512'] = {k: g[k] for k in ('metric', 'value', 'unit', 'ms_per_step', 'e2e', 'e2e_u8', 'roofline', 'gpu_launches_per_step', 'config')}
                 except Exception as e:  # noqa: BLE001
                     extra['gen512'] = dict(unavailable=repr(e)[:300])
+            try:
+                extra['patch_routing'] = time_patch_routing(args.batch)
+            except Exception as e:  # noqa: BLE001
+                extra['patch_routing'] = dict(unavailable=repr(e)[:300])
         except Exception as e:  # noqa: BLE001 -- side legs never take the headline line down
             extra['error'] = repr(e)[:300]
     act_bytes = sum(v['bytes'] for v in profile.values())

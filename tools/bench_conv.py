@@ -47,6 +47,7 @@ def main():
         (512, 512, 4, 3, 1), (512, 512, 8, 3, 1), (512, 512, 16, 3, 1), (512, 512, 32, 3, 1), (256, 256, 64, 3, 1), (128, 128, 128, 3, 1),
         (256, 128, 128, 3, 1), (64, 64, 256, 3, 1), (128, 64, 256, 3, 1), (192, 128, 128, 1, 1), (128, 64, 256, 1, 1), (64, 3, 256, 1, 1),
         (512, 512, 16, 3, 2), (512, 256, 32, 3, 2), (256, 128, 64, 3, 2), (128, 64, 128, 3, 2),
+        (3, 64, 256, 7, 1), (3, 64, 256, 3, 1),          # first layers: row-folded kernel
     ]
     lines = []
     with torch.no_grad():
@@ -83,6 +84,7 @@ def main():
             conv_igemm.enabled = False
             lib = lambda: conv2d_resample.conv2d_resample(x, w, f=f, up=up, padding=k // 2, flip_weight=(up == 1))
             t_ours = timeit(ours)
+            t_ours_tf32 = timeit(lambda: conv_igemm.conv2d_igemm(x, w, f=f if up == 2 else None, up=up, flip_weight=(up == 1), fmt='tf32'))   # kind::tf32 operands
             torch.backends.cudnn.allow_tf32 = True
             t_tf32 = timeit(lib)
             torch.backends.cudnn.allow_tf32 = False
@@ -90,7 +92,7 @@ def main():
             torch.backends.cudnn.allow_tf32 = True
             conv_igemm.enabled = True
             line = dict(cin=cin, cout=cout, res=res, k=k, up=up, N=N, gflop=round(flops / 1e9, 2),
-                        ours_us=round(t_ours * 1e6, 1), cudnn_tf32_us=round(t_tf32 * 1e6, 1), cudnn_fp32_us=round(t_fp32 * 1e6, 1),
+                        ours_us=round(t_ours * 1e6, 1), ours_tf32_us=round(t_ours_tf32 * 1e6, 1), cudnn_tf32_us=round(t_tf32 * 1e6, 1), cudnn_fp32_us=round(t_fp32 * 1e6, 1),
                         tma_us=None if t_tma is None else round(t_tma * 1e6, 1), tma_c8out_us=None if t_tma_o is None else round(t_tma_o * 1e6, 1),
                         tma_tflops=None if t_tma is None else round(exec_flops / t_tma / 1e12, 1), groupsN_us=None if t_psw is None else round(t_psw * 1e6, 1),
                         wgrad_us=None if t_wg is None else round(t_wg * 1e6, 1), cudnn_tf32_wgrad_us=None if t_lib_wg is None else round(t_lib_wg * 1e6, 1),
