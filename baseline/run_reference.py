@@ -35,6 +35,7 @@ REF = os.environ.get('PASTA_REFERENCE_TREE', os.path.join(ROOT, 'baseline', '_re
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--mode', required=True, choices=['cpu', 'gpu', 'overlay', 'overlay_hook', 'ops'])
+    ap.add_argument('--profile', action='store_true', help='print the top CUDA kernels of one forward (torch.profiler) to stderr')
     ap.add_argument('--batch', type=int, default=1)
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=1)
@@ -120,6 +121,35 @@ def time_generator(G, batch, steps, warmup, device):
         else:
             dt = time.perf_counter() - t0
     return dict(img_s=batch * steps / dt, ms_per_step=1e3 * dt / steps, batch=batch, steps=steps, warmup=warmup)
+
+
+def time_generator_graph(G, batch, steps, device):
+    """The same forward captured once into a CUDA graph and replayed: what is left of the drop-in's time when the host's per-op overhead
+    (1 960 launches per step from the unmodified reference code) is taken out.  Returns {} when the reference code cannot be captured."""
+    import torch
+    import procedural
+    inp = procedural.synth_inputs(batch, seed=1234, device=device)
+    try:
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        g = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.stream(s):
+            G(**inp, noise_mode='const')
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g, stream=s):
+                out = G(**inp, noise_mode='const')
+        torch.cuda.synchronize()
+        g.replay(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            g.replay()
+        e1.record(); torch.cuda.synchronize()
+        dt = e0.elapsed_time(e1) * 1e-3
+        return dict(graph_img_s=batch * steps / dt, graph_ms_per_step=1e3 * dt / steps)
+    except Exception as e:  # noqa: BLE001
+        torch.cuda.synchronize()
+        return dict(graph_unavailable=repr(e)[:200])
 
 
 def run_ops(out):
@@ -247,8 +277,18 @@ def main():
         capi = sys.modules.get('pasta_b200_capi')              # our C-ABI binding, if the overlay loaded it into this process
         l0 = capi.launch_count() if capi is not None else 0
     out.update(time_generator(G, args.batch, args.steps, args.warmup, device))
+    if args.profile and device == 'cuda':
+        import procedural
+        from torch.profiler import profile, ProfilerActivity
+        inp = procedural.synth_inputs(args.batch, seed=1234, device=device)
+        with torch.no_grad(), profile(activities=[ProfilerActivity.CUDA]) as prof:
+            G(**inp, noise_mode='const')
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=30, max_name_column_width=90), file=sys.stderr)
     if device == 'cuda':
         out['our_kernel_launches'] = (capi.launch_count() - l0) if capi is not None else 0
+        if overlay and not args.check:
+            out.update(time_generator_graph(G, args.batch, args.steps, device))
         if args.mode == 'gpu':
             from torch_utils.ops import upfirdn2d, bias_act
             out['plugins'] = dict(upfirdn2d=upfirdn2d._plugin is not None, bias_act=bias_act._plugin is not None)

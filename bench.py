@@ -425,6 +425,7 @@ def run_b200(args, world, rank, local):
             # the real drop-in: unmodified reference networks.py over OUR ops on this GPU (eager; every modulated conv arrives as groups = N)
             d = run_harness('overlay', args.batch, 5, 2, timeout=300)
             extra['dropin'] = d if 'unavailable' in d else dict(value=d['img_s'], unit=UNIT, ms_per_step=d['ms_per_step'], our_kernel_launches=d['our_kernel_launches'],
+                                                                  **{k: d[k] for k in ('graph_img_s', 'graph_ms_per_step', 'graph_unavailable') if k in d},
                                                                   what='UNMODIFIED reference training/networks.py GeneratorFull over our torch_utils/ops overlay, eager, batch %d' % args.batch)
             if time.perf_counter() - t_x < 240:
                 d = run_harness('gpu', args.batch, 5, 2, timeout=420)

@@ -290,6 +290,110 @@ __global__ void conv_prepack_kernel(PackParams p, long long out_sample_stride_ha
     }
 }
 
+// Plain layers (no resampling, no folded taps), tiled: one CTA packs 32 output channels x one 16-channel chunk x all taps.  Its source is 32 runs of
+// 16 * k * k contiguous floats, read coalesced into shared memory once; its destination is, per (tap, plane), 32 consecutive 16-byte rows (512
+// contiguous bytes).  The element-per-thread kernel above reads the weight tensor with a k * k element stride between neighbouring threads and
+// decodes six indices per element: on the drop-in path, where the reference re-creates `weight * weight_gain` (and the per-sample modulated weights)
+// on every call and every convolution therefore packs its weights anew, that kernel was a quarter of the step (7.7 of 31 ms).
+constexpr int kPackRows = 32;
+__global__ void __launch_bounds__(256) conv_prepack_tiled_kernel(PackParams p, long long out_sample_stride_halves) {
+    extern __shared__ float psrc[];                                   // [kPackRows][16 * kk + 1]
+    const int kk = p.ks * p.ks, rowlen = 16 * kk, pitch = rowlen + 1;
+    const int rblocks = (p.BN + kPackRows - 1) / kPackRows;
+    int b = blockIdx.x;
+    const int rb = b % rblocks; b /= rblocks;
+    const int ci = b % p.nchunks; const int jn = b / p.nchunks;
+    const int sample = blockIdx.y;
+    const float* w = p.w + (size_t)sample * p.w_bstride;
+    const float* sty = p.styles ? p.styles + (size_t)sample * p.Cin : nullptr;
+    const int c0 = ci * kKC, nl0 = rb * kPackRows;
+    const int cvalid = p.Cin - c0 < 16 ? p.Cin - c0 : 16;            // channels of this chunk that exist
+    for (int i = threadIdx.x; i < kPackRows * rowlen; i += 256) {
+        const int r = i / rowlen, t = i - r * rowlen;
+        const int v = jn * p.BN + nl0 + r;
+        float val = 0.f;
+        if (nl0 + r < p.BN && v < p.Cout && t < cvalid * kk) {
+            val = __ldg(w + ((size_t)v * p.Cin + c0) * kk + t) * p.w_scale;
+            if (sty) val *= sty[c0 + t / kk];
+        }
+        psrc[r * pitch + t] = val;
+    }
+    __syncthreads();
+    const int epp = p.fmt == 2 ? 4 : 8, npl = p.fmt == 2 ? 4 : 2;
+    uint16_t* out = (uint16_t*)p.out + (size_t)sample * out_sample_stride_halves;
+    const size_t blk = ((size_t)(jn * p.nchunks + ci) * p.ntaps) * (size_t)(16 * p.BN);       // first element of this (n-tile, chunk) block
+    const int per_tap = 16 * kPackRows;                               // elements this CTA writes per tap
+    for (int i = threadIdx.x; i < p.ntaps * per_tap; i += 256) {
+        const int tap = i / per_tap; int q = i - tap * per_tap;
+        const int j = q / (kPackRows * epp); q -= j * (kPackRows * epp);
+        const int r = q / epp, e = q - r * epp;
+        if (nl0 + r >= p.BN) continue;
+        const int cc = j * epp + e;
+        const float val = psrc[r * pitch + cc * kk + (p.flip_weight ? tap : kk - 1 - tap)];
+        const size_t dst = blk + ((size_t)(tap * npl + j) * p.BN + nl0 + r) * epp + e;
+        if (p.fmt == 0)      ((__half*)out)[dst] = __float2half_rn(fminf(fmaxf(val, -65504.f), 65504.f));
+        else if (p.fmt == 1) ((__nv_bfloat16*)out)[dst] = __float2bfloat16_rn(val);
+        else                 ((uint32_t*)out)[dst] = to_tf32(val);
+    }
+}
+
+// Up-2 composite weights, one thread per (output channel, input channel): the 6x6 composite Kc = w' (*) (4 k) is formed once in registers (144 FMAs)
+// and its 36 entries are the 4 output-parity phases x 9 taps of the polyphase form (composite_tap above evaluates each of the 36 with its own 9-term
+// loop, index arithmetic and loads: ~13x the instructions).  This matters where the weights are packed per call: the reference's fused modulated
+// convolution hands conv2d_resample a fresh [N*O, I, 3, 3] tensor every step (networks.py:84-94), 550 M packed elements per generator forward.
+__global__ void __launch_bounds__(256) conv_prepack_up2_kernel(PackParams p, long long out_sample_stride_halves) {
+    const int cin_pad = p.nchunks * kKC;
+    const long long total = (long long)p.Cout * cin_pad;
+    const int sample = blockIdx.y;
+    const float* w = p.w + (size_t)sample * p.w_bstride;
+    const float* sty = p.styles ? p.styles + (size_t)sample * p.Cin : nullptr;
+    uint16_t* out = (uint16_t*)p.out + (size_t)sample * out_sample_stride_halves;
+    float ff[4][4];                                                    // ff[a][b] = 4 * fir[3 - a][3 - b]  (upfirdn2d applies f as a true convolution; gain 4)
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) ff[a][b] = 4.f * __ldg(p.fir + (3 - a) * 4 + (3 - b));
+    const int epp = p.fmt == 2 ? 4 : 8, npl = p.fmt == 2 ? 4 : 2;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % cin_pad), o = (int)(idx / cin_pad);
+        float kc[6][6];
+#pragma unroll
+        for (int u = 0; u < 6; u++)
+#pragma unroll
+            for (int v = 0; v < 6; v++) kc[u][v] = 0.f;
+        if (c < p.Cin) {
+            const float* wp = w + ((size_t)o * p.Cin + c) * 9;
+            const float scale = p.w_scale * (sty ? sty[c] : 1.f);
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    const float wv = __ldg(wp + (p.flip_weight ? i * 3 + j : (2 - i) * 3 + (2 - j))) * scale;
+#pragma unroll
+                    for (int a = 0; a < 4; a++)
+#pragma unroll
+                        for (int b = 0; b < 4; b++) kc[i + a][j + b] = fmaf(wv, ff[a][b], kc[i + a][j + b]);
+                }
+        }
+        const int ci = c / kKC, cc = c - ci * kKC, j = cc / epp, e = cc - j * epp;
+#pragma unroll
+        for (int phase = 0; phase < 4; phase++) {
+            const int v = phase * p.Cout + o, jn = v / p.BN, nl = v - jn * p.BN;
+            const size_t base = ((size_t)(jn * p.nchunks + ci) * p.ntaps) * (size_t)(16 * p.BN) + ((size_t)j * p.BN + nl) * epp + e;
+#pragma unroll
+            for (int th = 0; th < 3; th++)
+#pragma unroll
+                for (int tw = 0; tw < 3; tw++) {
+                    const float val = kc[2 * th + 1 - (phase >> 1)][2 * tw + 1 - (phase & 1)];
+                    const size_t dst = base + (size_t)((th * 3 + tw) * npl) * p.BN * epp;
+                    if (p.fmt == 0)      ((__half*)out)[dst] = __float2half_rn(fminf(fmaxf(val, -65504.f), 65504.f));
+                    else if (p.fmt == 1) ((__nv_bfloat16*)out)[dst] = __float2bfloat16_rn(val);
+                    else                 ((uint32_t*)out)[dst] = to_tf32(val);
+                }
+        }
+    }
+}
+
 struct MmaRing { int sa, sb; uint32_t pa, pb; };
 
 // MMA issue loop of one CTA, executed by ALL lanes of the MMA warp (uniform control flow); `issue` != 0 on the one lane that issues.
@@ -1894,6 +1998,18 @@ extern "C" int pg_conv2d_igemm_prepack_batched(const float* w, int64_t w_batch_s
     int pblocks = (int)((pack_total + 255) / 256);
     const int cap = kNumSMs * 16 / (batch < 16 ? batch : 16);
     if (pblocks > cap) pblocks = cap < 1 ? 1 : cap;
+    if (up == 2 && pl.ntiles_n * pl.BN == 4 * Cout) {
+        // (every row of every N tile is a real virtual channel: nothing left for the element-wise kernel to zero-fill)
+        const long long work = (long long)Cout * pl.nchunks * kKC;
+        long long blocks = (work + 255) / 256;
+        const long long bcap = (long long)kNumSMs * 32 / (batch < 32 ? batch : 32);
+        if (blocks > bcap) blocks = bcap < 1 ? 1 : bcap;
+        conv_prepack_up2_kernel<<<dim3((unsigned)blocks, (unsigned)batch), 256, 0, (cudaStream_t)stream>>>(pp, (long long)(need / 2));
+    } else if (up == 1 && !im2col && ksize <= 3) {
+        const unsigned blocks = (unsigned)(pl.ntiles_n * pl.nchunks * ((pl.BN + kPackRows - 1) / kPackRows));
+        const size_t smem = (size_t)kPackRows * (16 * ksize * ksize + 1) * sizeof(float);
+        conv_prepack_tiled_kernel<<<dim3(blocks, (unsigned)batch), 256, smem, (cudaStream_t)stream>>>(pp, (long long)(need / 2));
+    } else
     conv_prepack_kernel<<<dim3((unsigned)pblocks, (unsigned)batch), 256, 0, (cudaStream_t)stream>>>(pp, (long long)(need / 2));
     if (need > need_main) {
         // the same weights in the row-folded layout, behind the folded-tap pack (conv_rowfold_kernel)
