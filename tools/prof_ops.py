@@ -30,5 +30,15 @@ with torch.no_grad():
         conv_igemm.conv2d_igemm(xbc, wb)                                                                           # 128->128 @128^2, TMA persistent kernel, fp32 out
         conv_igemm.spade_conv_norm(xs, xbc, wg, wbeta, act='relu', gain=1.0, out_c8=True)                          # SPADE gamma|beta 128->256, TMA persistent
         conv_igemm.conv2d_wgrad(xb, dyb, 3)                                                                        # conv_wgrad_kernel + reduce
+    x3 = torch.randn(32, 3, 256, 256, device=dev); w7 = torch.randn(64, 3, 7, 7, device=dev) / 12
+    for _ in range(2):
+        conv_igemm.conv2d_igemm(x3, w7, bias=torch.zeros(64, device=dev), act='relu', gain=2 ** 0.5, out_c8=True)  # conv_rowfold_kernel: 3->64 7x7 @256^2, batch 32 (garment encoder stem)
+        conv_igemm.conv2d_igemm(xb, wb, fmt='tf32')                                                                # 128->128 @128^2, kind::tf32 operands (conv_igemm_kernel)
+    # patch routing: all rectifying warps of a batch in one launch + the back-warp composite
+    from pasta_gan_b200 import patch_routing, synthetic
+    d = synthetic.synth_patch_routing_inputs(16, seed=3)
+    t = {k: torch.from_numpy(v).to(dev) for k, v in d.items() if k != 'keypoints'}
+    for _ in range(2):
+        patch_routing.PatchRouter().normalize(t['upper_img'], t['lower_img'], t['upper_clothes_mask'], t['lower_clothes_mask'], d['keypoints'], 2)
 torch.cuda.synchronize()
 print('ok')

@@ -8,7 +8,7 @@ lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, 'pasta-gan_b200',
 sass = subprocess.run(['cuobjdump', '-sass', lib], capture_output=True, text=True).stdout
 res = subprocess.run(['cuobjdump', '-res-usage', lib], capture_output=True, text=True).stdout
 regs = dict(re.findall(r'Function (\S+):\s*\n\s*REG:(\d+)', res))
-pat = re.compile(r'\b(UTC[A-Z]*MMA|UTCBAR|LDTM|STTM|UTMALDG|UTMASTG|UBLKCP|UTMAPF|SYNCS|HMMA|HGMMA|QGMMA|IGMMA|LDGSTS|ELECT|UTCATOMSWS|REDG|ATOMG)\b')
+pat = re.compile(r'\b(UTC[A-Z]*MMA|UTCBAR|LDTM|STTM|UTMALDG|UTMASTG|UBLKCP|UTMAPF|SYNCS|HMMA|HGMMA|QGMMA|IGMMA|LDGSTS|ELECT|UTCATOMSWS|REDG|ATOMG|FFMA2|FMUL2)\b')
 per = collections.OrderedDict()
 cur = None
 for ln in sass.splitlines():
