@@ -142,6 +142,9 @@ int pg_upfirdn2d_bias_act(const void* x, const float* f, const void* b, void* y,
  * conv2d_resample.py:119-122 (4x4 FIR with padding 2, then the 3x3 convolution at stride 2; y is [N,Cout,H/2,W/2]) evaluated as a
  * 'same' 3x3 convolution over the four space-to-depth planes of x with the 6x6 composite kernel w (*) f — no filtered intermediate. */
 #define PG_CONV_DOWN2 (-2)
+/* The same down-2 form for a channel-blocked float16 input (PG_LAYOUT_C8, loaded by a strided TMA box): the packed weights order the 4 * Cin
+ * space-to-depth channels parity-major, so prepack and launch must both be given this value. */
+#define PG_CONV_DOWN2_C8 (-3)
 int64_t pg_conv2d_igemm_workspace_bytes(int32_t Cin, int32_t Cout, int32_t ksize, int32_t up);                 /* operand_format 0 / 1 */
 int64_t pg_conv2d_igemm_workspace_bytes_fmt(int32_t Cin, int32_t Cout, int32_t ksize, int32_t up, int32_t operand_format);
 /* The same operation in two steps, so that inference can pack the weights once per parameter version:

@@ -69,6 +69,8 @@ struct ConvParams {
     int res_c8;                                // the residual is fp16 channel-blocked (same shape as a channel-blocked y)
     int vec2; uint32_t w_magic;   // aligned 8-byte loader (see the converter section); ceil(2^32 / W)
     uint32_t pw_magic;         // ceil(2^32 / PW): q / PW == umulhi(q, pw_magic) for the strip positions that occur
+    int tma_down2;             // TMA A operand of the down-2 form: x is channel-blocked [N][cin_real/8][hin][win][8]; chunk ci is parity (a, b) = ci / (cin_real/16) of two
+                               // channel blocks, brought by a 4-D box with element stride 2 along rows and columns (space-to-depth done by the tensor map)
 };
 
 // Phase timestamps, load / store / fence suppression and the loader experiments exist only in -DPG_DEBUG builds (tools/conv_timeline.py builds its
@@ -123,6 +125,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int c0, int c1, int c2, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
 }
 
 // Shared-memory matrix descriptors (K-major, SWIZZLE_NONE, rows 16 B apart: SBO = 128 B, K chunks LBO bytes apart, descriptor version 1) are
@@ -258,8 +265,13 @@ __global__ void conv_prepack_kernel(PackParams p, long long out_sample_stride_ha
             // c runs over the 4 * Cin virtual channels (row parity a, then real channel, then column parity b: the order in which the
             // activation loader's 8-byte reads deliver them); p.Cin is the real channel count
             if (v < p.Cout && c < 4 * p.Cin) {
-                const int a = c / (2 * p.Cin), rem = c - a * 2 * p.Cin;          // virtual channel = a * 2Cin + 2 * c_real + b
-                val = down2_tap(p, v, rem >> 1, a, rem & 1, tap / 3, tap % 3);
+                if (p.down2 == 2) {      // channel-blocked input (TMA): parity-major, virtual channel = (2a + b) * Cin + c_real
+                    const int q = c / p.Cin;
+                    val = down2_tap(p, v, c - q * p.Cin, q >> 1, q & 1, tap / 3, tap % 3);
+                } else {
+                    const int a = c / (2 * p.Cin), rem = c - a * 2 * p.Cin;      // virtual channel = a * 2Cin + 2 * c_real + b
+                    val = down2_tap(p, v, rem >> 1, a, rem & 1, tap / 3, tap % 3);
+                }
             }
         } else if (p.im2col) {
             // one "tap", Cin * ks * ks virtual channels in the weight tensor's memory order; a true convolution mirrors the taps
@@ -281,7 +293,7 @@ __global__ void conv_prepack_kernel(PackParams p, long long out_sample_stride_ha
         val *= p.w_scale;
         if (sty && val != 0.f) {
             // real input channel of GEMM channel c (down-2: (row parity, channel, column parity) order; folded taps: channel-major)
-            const int cr = p.down2 ? ((c % (2 * p.Cin)) >> 1) : (p.im2col ? c / (p.ks * p.ks) : c);
+            const int cr = p.down2 == 2 ? c % p.Cin : p.down2 ? ((c % (2 * p.Cin)) >> 1) : (p.im2col ? c / (p.ks * p.ks) : c);
             val *= sty[cr];
         }
         if (p.fmt == 0)      ((__half*)p.out)[idx] = __float2half_rn(fminf(fmaxf(val, -65504.f), 65504.f));
@@ -1083,6 +1095,10 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
                     mbar_wait(smem_u32(&a_empty[sa]), pa ^ 1);
                     mbar_expect_tx(smem_u32(&a_full[sa]), p.a_tx_bytes);
                     const int cb = 2 * (g / spc);                // first channel block of this chunk; blocks >= tma_cb come from the second input (fused concat)
+                    if (p.tma_down2) {
+                        const int cpp = p.tma_cb >> 1, q = (g / spc) / cpp, cbk = 2 * ((g / spc) - q * cpp);       // chunks per parity, parity (a, b), first block
+                        tma_load_4d(smem_u32(a_base + (size_t)sa * p.a_stage_bytes), &tmap_a, 0, col0 + (q & 1), 2 * tma_r0 + (q >> 1), n * p.tma_cb + cbk, smem_u32(&a_full[sa]));
+                    } else
                     if (cb < p.tma_cb) tma_load_3d(smem_u32(a_base + (size_t)sa * p.a_stage_bytes), &tmap_a, col0, tma_r0, n * p.tma_cb + cb, smem_u32(&a_full[sa]));
                     else               tma_load_3d(smem_u32(a_base + (size_t)sa * p.a_stage_bytes), &tmap_a2, col0, tma_r0, n * p.tma_cb2 + cb - p.tma_cb, smem_u32(&a_full[sa]));
                     if (++sa == p.SA) { sa = 0; pa ^= 1; }
@@ -1539,6 +1555,10 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_igemm_tma_persistent_kernel
                     mbar_wait(smem_u32(&a_empty[sa]), pa ^ 1);
                     mbar_expect_tx(smem_u32(&a_full[sa]), p.a_tx_bytes);
                     const int cb = 2 * ci;
+                    if (p.tma_down2) {
+                        const int cpp = p.tma_cb >> 1, q = ci / cpp, cbk = 2 * (ci - q * cpp);
+                        tma_load_4d(smem_u32(a_base + (size_t)sa * p.a_stage_bytes), &tmap_a, 0, col0 + (q & 1), 2 * r0 + (q >> 1), n * p.tma_cb + cbk, smem_u32(&a_full[sa]));
+                    } else
                     if (cb < p.tma_cb) tma_load_3d(smem_u32(a_base + (size_t)sa * p.a_stage_bytes), &tmap_a, col0, r0, n * p.tma_cb + cb, smem_u32(&a_full[sa]));
                     else               tma_load_3d(smem_u32(a_base + (size_t)sa * p.a_stage_bytes), &tmap_a2, col0, r0, n * p.tma_cb2 + cb - p.tma_cb, smem_u32(&a_full[sa]));
                     if (++sa == p.SA) { sa = 0; pa ^= 1; }
@@ -1920,6 +1940,23 @@ static int make_a_tensor_map(CUtensorMap& tm, const void* x, int N, int CB, int 
     return PG_OK;
 }
 
+// The same tensor seen through the space-to-depth view of the down-2 form: a box samples every second column and every second row (element strides
+// 2), so one (row parity, column parity) plane of two channel blocks arrives as a dense [2 blocks][rows][PW positions][16 B] tile.  Box sizes count
+// the elements traversed before striding (2 * PW columns, 2 * rows rows; both <= 256); out-of-range coordinates (the pad of the 'same' 3x3 over
+// the planes, negative or past the image) are zero-filled.
+static int make_a_tensor_map_down2(CUtensorMap& tm, const void* x, int N, int CB, int Hin, int Win, int PW, int rows) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return fail(PG_ERR_CUDA, "conv2d_igemm: cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[4] = {2u, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)N * CB};
+    const cuuint64_t strides[3] = {16u, (cuuint64_t)Win * 16, (cuuint64_t)Hin * Win * 16};
+    const cuuint32_t box[4] = {2u, (cuuint32_t)2 * PW, (cuuint32_t)2 * rows, 2u};
+    const cuuint32_t estr[4] = {1u, 2u, 2u, 1u};
+    const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(PG_ERR_CUDA, "conv2d_igemm: cuTensorMapEncodeTiled (down-2 view) failed (%d) for W=%d H=%d PW=%d rows=%d", (int)r, Win, Hin, PW, rows);
+    return PG_OK;
+}
+
 }  // namespace pg
 
 extern "C" int pg_set_tuning(const char* key, int32_t value) {
@@ -1952,7 +1989,7 @@ static int64_t rowfold_pack_bytes(int Cin, int Cout, int ksize, int up) {
 extern "C" int64_t pg_conv2d_igemm_workspace_bytes_fmt(int32_t Cin, int32_t Cout, int32_t ksize, int32_t up, int32_t operand_format) {
     pg::ConvPlan pl;
     const bool im2col = use_im2col(Cin, ksize, up);
-    if (pg::make_plan(pl, 1, up == PG_CONV_DOWN2 ? 4 * Cin : (im2col ? Cin * ksize * ksize : Cin), Cout, 8, 8, im2col ? 1 : ksize, up == 2,
+    if (pg::make_plan(pl, 1, (up == PG_CONV_DOWN2 || up == PG_CONV_DOWN2_C8) ? 4 * Cin : (im2col ? Cin * ksize * ksize : Cin), Cout, 8, 8, im2col ? 1 : ksize, up == 2,
                       false, 4, false, 0, 0, operand_format == 2) != PG_OK) return -1;
     return (int64_t)pl.ntiles_n * pl.nchunks * pl.b_stage + rowfold_pack_bytes(Cin, Cout, ksize, up);
 }
@@ -1964,8 +2001,8 @@ static int conv_validate(int32_t N, int32_t Cin, int32_t Cout, int32_t H, int32_
     using namespace pg;
     PG_REQUIRE(ksize == 1 || ksize == 3 || (ksize % 2 == 1 && ksize <= 7 && use_im2col(Cin, ksize, up)),
                "conv2d_igemm: kernel size must be 1 or 3, or odd <= 7 with Cin * k * k <= 160 (got k = %d, Cin = %d)", ksize, Cin);
-    PG_REQUIRE(up == 1 || ((up == 2 || up == PG_CONV_DOWN2) && ksize == 3), "conv2d_igemm: resample must be 1, 2 (up) or PG_CONV_DOWN2, the latter two with a 3x3 kernel");
-    PG_REQUIRE(up != PG_CONV_DOWN2 || (Cin % 16 == 0 && H % 2 == 0 && W % 2 == 0), "conv2d_igemm: down-2 needs Cin %% 16 == 0 and even H, W");
+    PG_REQUIRE(up == 1 || ((up == 2 || up == PG_CONV_DOWN2 || up == PG_CONV_DOWN2_C8) && ksize == 3), "conv2d_igemm: resample must be 1, 2 (up), PG_CONV_DOWN2 or PG_CONV_DOWN2_C8, the latter three with a 3x3 kernel");
+    PG_REQUIRE((up != PG_CONV_DOWN2 && up != PG_CONV_DOWN2_C8) || (Cin % 16 == 0 && H % 2 == 0 && W % 2 == 0), "conv2d_igemm: down-2 needs Cin %% 16 == 0 and even H, W");
     PG_REQUIRE(N >= 0 && Cin >= 1 && Cout >= 1 && H >= 1 && W >= 1, "conv2d_igemm: bad sizes");
     PG_REQUIRE(operand_format >= 0 && operand_format <= 2, "conv2d_igemm: operand_format must be 0 (fp16), 1 (bf16) or 2 (tf32)");
     PG_REQUIRE(up == 1 || Cout % 16 == 0, "conv2d_igemm: up=2 needs Cout to be a multiple of 16");
@@ -1981,7 +2018,7 @@ extern "C" int pg_conv2d_igemm_prepack_batched(const float* w, int64_t w_batch_s
     PG_REQUIRE(up == 1 || fir != nullptr, "conv2d_igemm: resampling needs the 4x4 FIR");
     PG_REQUIRE(w && workspace, "conv2d_igemm: w and workspace must be device pointers");
     PG_REQUIRE(batch >= 1 && batch <= 65535 && w_batch_stride >= 0, "conv2d_igemm: batch must be in [1, 65535]");
-    const bool down2 = up == PG_CONV_DOWN2;
+    const bool down2 = up == PG_CONV_DOWN2 || up == PG_CONV_DOWN2_C8;
     ConvPlan pl;
     const bool im2col = use_im2col(Cin, ksize, up);
     rc = make_plan(pl, 1, down2 ? 4 * Cin : (im2col ? Cin * ksize * ksize : Cin), Cout, 8, 8, im2col ? 1 : ksize, up == 2, false, 4, false, n_tile, 0, operand_format == 2);
@@ -1992,7 +2029,7 @@ extern "C" int pg_conv2d_igemm_prepack_batched(const float* w, int64_t w_batch_s
     PG_REQUIRE(workspace_bytes >= need * batch, "conv2d_igemm: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)(need * batch));
     PackParams pp;
     pp.w = w; pp.fir = fir; pp.out = workspace; pp.Cout = Cout; pp.Cin = Cin; pp.ks = ksize; pp.BN = pl.BN; pp.nchunks = pl.nchunks;
-    pp.ntaps = pl.ntaps; pp.ntiles = pl.ntiles_n; pp.flip_weight = flip_weight ? 1 : 0; pp.fmt = operand_format; pp.up2 = up == 2; pp.down2 = down2; pp.w_scale = w_scale; pp.im2col = im2col;
+    pp.ntaps = pl.ntaps; pp.ntiles = pl.ntiles_n; pp.flip_weight = flip_weight ? 1 : 0; pp.fmt = operand_format; pp.up2 = up == 2; pp.down2 = up == PG_CONV_DOWN2_C8 ? 2 : (down2 ? 1 : 0); pp.w_scale = w_scale; pp.im2col = im2col;
     pp.w_bstride = w_batch_stride; pp.styles = styles;
     const size_t pack_total = (size_t)need_main / (operand_format == 2 ? 4 : 2);
     int pblocks = (int)((pack_total + 255) / 256);
@@ -2075,8 +2112,9 @@ static int conv_run_impl(const pg_conv_args& a) {
     const float* x = (const float*)a.x; const float* x2 = (const float*)a.x2;
     PG_REQUIRE(x && a.wpack && a.y, "conv2d_igemm: x, packed weights and y must be device pointers");
     PG_REQUIRE(a.wpack_sample_stride >= 0 && a.wpack_sample_stride % 16 == 0, "conv2d_igemm: the per-sample weight stride must be a multiple of 16 bytes");
-    const bool down2 = up == PG_CONV_DOWN2;
+    const bool down2 = up == PG_CONV_DOWN2 || up == PG_CONV_DOWN2_C8;
     PG_REQUIRE(!down2 || ((uintptr_t)x & 7) == 0, "conv2d_igemm: down-2 needs an 8-byte aligned input");
+    PG_REQUIRE((up == PG_CONV_DOWN2_C8) == (down2 && a.x_layout == PG_LAYOUT_C8), "conv2d_igemm: PG_CONV_DOWN2_C8 goes with a channel-blocked input (and PG_CONV_DOWN2 with a dense one): the packed weights order their channels differently");
     const int hin = H, win = W, cin_real = Cin;
     const bool scale = a.styles != nullptr || a.in_act != PG_ACT_LINEAR || a.in_gain != 1.f;
     PG_REQUIRE((a.x_dtype == PG_F32 || a.x_dtype == PG_F16) && (a.y_dtype == PG_F32 || a.y_dtype == PG_F16), "conv2d_igemm: x / y must be float32 or float16");
@@ -2086,7 +2124,7 @@ static int conv_run_impl(const pg_conv_args& a) {
     PG_REQUIRE(n_tile == 0 || (n_tile % 16 == 0 && Cout % n_tile == 0 && up != 2), "conv2d_igemm: n_tile must be a multiple of 16 that divides Cout (no up-2)");
     if (tma) {
         // channel-blocked fp16 input: taken as the operand bits by TMA, so no input scale / activation / concat, fp16 operands, whole 16-channel chunks
-        PG_REQUIRE(a.x_dtype == PG_F16 && !scale && !down2 && operand_format == 0 && Cin % 16 == 0 && !use_im2col(Cin, ksize, up) && ((uintptr_t)x & 15) == 0,
+        PG_REQUIRE(a.x_dtype == PG_F16 && !scale && (!down2 || !x2) && operand_format == 0 && Cin % 16 == 0 && !use_im2col(Cin, ksize, up) && ((uintptr_t)x & 15) == 0,
                    "conv2d_igemm: a channel-blocked input needs float16, a plain (unmodulated, no input activation) stride-1 or up-2 layer, fp16 operands and Cin %% 16 == 0");
         PG_REQUIRE(!x2 || (a.cin1 % 16 == 0 && ((uintptr_t)x2 & 15) == 0), "conv2d_igemm: a channel-blocked split input needs Cin1 %% 16 == 0 (x2 is channel-blocked float16 too)");
     }
@@ -2096,7 +2134,7 @@ static int conv_run_impl(const pg_conv_args& a) {
                    "conv2d_igemm: a channel-blocked output needs float16, Cout %% 16 == 0 (and Cout <= 128 with up-2); a residual added to it must be channel-blocked too");
     PG_REQUIRE(a.residual_layout == PG_LAYOUT_NCHW || (a.residual_layout == PG_LAYOUT_C8 && Cout % 16 == 0 && up != 2 && !a.spade_x && ((uintptr_t)a.residual & 15) == 0),
                "conv2d_igemm: a channel-blocked residual needs Cout %% 16 == 0 and no up-sampling");
-    if (tma && ksize == 1 && W > 128) {
+    if (tma && ksize == 1 && W > 128 && !down2) {
         // a 1x1 convolution does not care how H * W pixels are cut into rows: view a wide image as rows of 128 pixels so that a row fits one TMA box
         PG_REQUIRE(W % 128 == 0, "conv2d_igemm: a channel-blocked input of a 1x1 layer wider than 128 columns needs W %% 128 == 0");
         H *= W / 128; W = 128;
@@ -2213,8 +2251,9 @@ static int conv_run_impl(const pg_conv_args& a) {
     CUtensorMap tmap, tmap2;
     memset(&tmap, 0, sizeof(tmap));
     memset(&tmap2, 0, sizeof(tmap2));
+    p.tma_down2 = (tma && down2) ? 1 : 0;
     if (tma) {
-        rc = make_a_tensor_map(tmap, x, N, p.tma_cb, H, Wimg, pl.PW, pl.tma_rows);
+        rc = down2 ? make_a_tensor_map_down2(tmap, x, N, p.tma_cb, hin, win, pl.PW, pl.tma_rows) : make_a_tensor_map(tmap, x, N, p.tma_cb, H, Wimg, pl.PW, pl.tma_rows);
         if (rc != PG_OK) return rc;
         if (x2) {
             rc = make_a_tensor_map(tmap2, x2, N, p.tma_cb2, H, Wimg, pl.PW, pl.tma_rows);
@@ -2271,7 +2310,7 @@ static int conv_run_impl(const pg_conv_args& a) {
                 q.pw_magic = (uint32_t)((0x100000000ull + (uint64_t)pp.PW - 1) / (uint64_t)pp.PW);
                 CUtensorMap m1, m2;
                 memset(&m1, 0, sizeof(m1)); memset(&m2, 0, sizeof(m2));
-                rc = make_a_tensor_map(m1, x, N, q.tma_cb, H, Wimg, pp.PW, pp.tma_rows);
+                rc = down2 ? make_a_tensor_map_down2(m1, x, N, q.tma_cb, hin, win, pp.PW, pp.tma_rows) : make_a_tensor_map(m1, x, N, q.tma_cb, H, Wimg, pp.PW, pp.tma_rows);
                 if (rc != PG_OK) return rc;
                 if (x2) { rc = make_a_tensor_map(m2, x2, N, q.tma_cb2, H, Wimg, pp.PW, pp.tma_rows); if (rc != PG_OK) return rc; }
                 const size_t smem_p = (size_t)SA * pp.a_stage + (size_t)SB * pp.b_slot + fixed_p + 128;

@@ -206,8 +206,8 @@ def conv_layer(x, w, b=None, f=None, up=1, down=1, padding=0, flip_weight=True, 
     if K.is_c8(x):
         # channel-blocked fp16 from one of our own epilogues: TMA operand path.  The producer only emits this layout for consumers it has checked
         # (K.c8_input_ok), so there is nothing to fall back to here.
-        assert in_act is None and act in ('linear', 'relu', 'lrelu') and padding == int(w.shape[2]) // 2 and down == 1
-        return K.conv2d_igemm(x, w, f=f, up=up, flip_weight=flip_weight, bias=b, act=act, gain=act_gain, clamp=clamp, w_scale=w_scale,
+        assert in_act is None and act in ('linear', 'relu', 'lrelu') and padding == int(w.shape[2]) // 2 and (down == 1 or (down == 2 and up == 1 and x2 is None))
+        return K.conv2d_igemm(x, w, f=f, up=up, down=down, flip_weight=flip_weight, bias=b, act=act, gain=act_gain, clamp=clamp, w_scale=w_scale,
                               cache_weights=cache_weights, x2=x2, residual=residual, out_dtype=out_dtype or torch.float32, out_c8=out_c8)
     if act in ('linear', 'relu', 'lrelu') and in_act in (None, 'relu', 'lrelu') and \
             K.supported(x, w, up=up, down=down, f=f, padding=pad4, x2=x2, residual=residual, allow_half=half_ok):
@@ -281,10 +281,11 @@ def _half_intermediates(x):
             not torch.is_grad_enabled() and x.shape[3] % 2 == 0 and x.shape[3] <= 256)
 
 
-def _c8_ok(channels, h, w, k, up=1):
+def _c8_ok(channels, h, w, k, up=1, down=1):
     """May a tensor [N, channels, h, w] consumed only by a plain k x k tcgen05 convolution travel as channel-blocked fp16 (TMA operand path)?"""
     from .torch_utils.ops import conv_igemm as K
-    return (not torch.is_grad_enabled()) and os.environ.get('PASTA_B200_HALF_INTERMEDIATES', '1') != '0' and K.c8_input_ok(int(channels), int(h), int(w), int(k), up)
+    return (not torch.is_grad_enabled()) and os.environ.get('PASTA_B200_HALF_INTERMEDIATES', '1') != '0' and \
+        K.c8_input_ok(int(channels), int(h), int(w), int(k), up, down)
 
 
 def _masked_mean_fill(feat, valid, rest, out):
@@ -679,7 +680,29 @@ class ConstEncoderNetwork(OpsModule):
         self.model = nn.Sequential(*layers)
 
     def forward(self, x):
-        return self.model(x)
+        """Inference on the CUDA table: the tensors between the stem and the stride-2 convolutions travel channel-blocked fp16; each down-2 layer reads
+        its space-to-depth planes through a strided TMA box (half the bytes of the fp32 NCHW tensor, no converter warps).  The last layer's
+        result is dense fp32 as everywhere else."""
+        c8_ok = getattr(self.ops, 'c8_ok', None)
+        layers = list(self.model)
+        if c8_ok is None or not x.is_cuda or torch.is_grad_enabled() or os.environ.get('PASTA_B200_C8_CHAIN', '1') == '0':
+            return self.model(x)
+        h, w = int(x.shape[2]), int(x.shape[3])
+        for i, layer in enumerate(layers):
+            nxt = layers[i + 1] if i + 1 < len(layers) else None
+            oh, ow = h // layer.down, w // layer.down
+            out_c8 = bool(nxt is not None and nxt.down == 2 and int(layer.weight.shape[0]) % 16 == 0 and
+                          c8_ok(int(nxt.weight.shape[1]), oh, ow, int(nxt.weight.shape[2]), 1, 2) and
+                          (x.ndim == 5 or K_supported_c8_out(layer, x) or (layer.down == 2 and _down2_supported(layer, x))))
+            x = layer(x, out_c8=out_c8)
+            h, w = oh, ow
+        return x
+
+
+def _down2_supported(layer, x):
+    from .torch_utils.ops import conv_igemm as K
+    pad = int(layer.padding)
+    return x.ndim == 4 and K.supported(x, layer.weight, up=1, down=2, f=layer.resample_filter, padding=(pad,) * 4)
 
 
 class Dense(nn.Module):

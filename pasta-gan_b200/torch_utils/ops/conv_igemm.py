@@ -76,6 +76,10 @@ def half_input_ok(x, w, up=1, down=1, x2=None):
 def c8_input_ok(c, h, wd, k, up=1, down=1):
     """A channel-blocked input is loaded by TMA: plain stride-1 (or up-2) 1x1 / 3x3 layer, fp16 operands, whole 16-channel chunks; 3x3 layers wider than
     127 columns run in 64-column bands (even W); 1x1 layers wider than 128 columns are viewed as rows of 128 pixels (W % 128 == 0)."""
+    if down == 2:
+        # down-2 3x3: the space-to-depth planes come through a strided TMA box; the GEMM runs at the output resolution (bands above 127 columns)
+        return (enabled and operand_format == 'fp16' and up == 1 and k == 3 and c % 16 == 0 and h % 2 == 0 and wd % 2 == 0 and h >= 4 and
+                (wd // 2 <= 127 or (wd // 2) % 2 == 0) and os.environ.get('PASTA_B200_CONV_TMA', '1') != '0')
     return (enabled and operand_format == 'fp16' and down == 1 and up in (1, 2) and k in (1, 3) and c % 16 == 0 and (k == 1 or c * k * k > 160) and
             ((wd <= 128 or wd % 128 == 0) if k == 1 else (wd <= 127 or wd % 2 == 0)) and
             os.environ.get('PASTA_B200_CONV_TMA', '1') != '0')
@@ -283,7 +287,7 @@ def conv2d_igemm(x, w, f=None, up=1, down=1, flip_weight=True, styles=None, dcoe
     if x2 is not None:
         x2 = x2.contiguous()
     assert not (up == 2 and down == 2)
-    mode = -2 if down == 2 else up                       # PG_CONV_DOWN2 / 2 / 1
+    mode = (-3 if x_c8 else -2) if down == 2 else up     # PG_CONV_DOWN2_C8 / PG_CONV_DOWN2 / 2 / 1
     oh, ow = (h // 2, wd // 2) if down == 2 else (h * up, wd * up)
     assert out_dtype in (torch.float32, torch.float16) and x.dtype in (torch.float32, torch.float16)
     if x_c8:

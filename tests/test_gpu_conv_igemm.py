@@ -535,6 +535,27 @@ def test_channel_blocked_residual_with_dense_output(cv, shape):
         assert got.dtype == torch.float32 and torch.equal(got, ref)
 
 
+@pytest.mark.parametrize('shape', [(2, 64, 128, 256, 256), (1, 128, 256, 128, 128), (3, 32, 48, 36, 20), (2, 256, 256, 32, 32), (1, 16, 16, 8, 512), (1, 64, 64, 6, 260)], ids=str)
+def test_c8_tma_down2(cv, shape):
+    """Down-2 3x3 from a channel-blocked input: the space-to-depth planes come through a strided 4-D TMA box (PG_CONV_DOWN2_C8).  Against the fp64
+    oracle of conv2d_resample(down=2) and against the converter path on the same fp16-rounded input (same products, different K order)."""
+    n, cin, cout, h, w = shape
+    torch.manual_seed(sum(shape))
+    xh = torch.randn(n, cin, h, w, device=DEV).half()
+    wt = torch.randn(cout, cin, 3, 3, device=DEV) / (cin * 9) ** 0.5
+    b = torch.randn(cout, device=DEV) * 0.2
+    f = O.setup_filter([1, 3, 3, 1]).to(DEV)
+    assert cv.c8_input_ok(cin, h, w, 3, 1, 2)
+    ref = O.bias_act(O.conv2d_resample(xh.double().cpu(), wt.double().cpu(), f.double().cpu(), down=2, padding=1), b.double().cpu(), act='lrelu', gain=1.2)
+    y = cv.conv2d_igemm(cv.to_c8(xh), wt, f=f, down=2, bias=b, act='lrelu', gain=1.2)
+    assert y.shape == ref.shape and rel_err(y, ref) < TOL['fp16']
+    y_conv = cv.conv2d_igemm(xh.float(), wt, f=f, down=2, bias=b, act='lrelu', gain=1.2)
+    assert rel_err(y, y_conv) < 5e-5
+    if cout % 16 == 0:
+        yc = cv.conv2d_igemm(cv.to_c8(xh), wt, f=f, down=2, bias=b, act='lrelu', gain=1.2, out_c8=True)
+        assert torch.equal(cv.from_c8(yc, cout, dtype=torch.float16), y.half())
+
+
 def test_c8_tma_up2_spade_and_folded_styles(cv):
     """TMA operand path under the other epilogues: polyphase up-2, the SPADE epilogue (blocked in, blocked out), and a modulated layer whose styles
     are folded into per-sample packed weights (the activations cannot be scaled on the way in)."""
