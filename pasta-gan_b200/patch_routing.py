@@ -11,8 +11,6 @@ bit for bit; there is no CPU fallback.
 ``PatchRouter.normalize`` keeps the argument order and the 8-tuple of the reference method, with a leading batch axis on every array.
 ``warp_perspective`` is the single-call analogue of ``cv2.warpPerspective`` for uint8 images.
 """
-import ctypes
-
 import numpy as np
 import torch
 
@@ -145,29 +143,75 @@ def invert3x3(M):
     return t
 
 
+def _segment_boxes(p0, p1, half_width):
+    """``_segment_box`` for arrays of segments: p0, p1 [B, 2] float32 -> [B, 4, 2] float32 (same float32 operations, element for element)."""
+    seg = p1 - p0
+    nrm = np.stack([-seg[:, 1], seg[:, 0]], axis=1)
+    off = half_width * nrm
+    return np.stack([p0 + off, p0 - off, p1 - off, p1 + off], axis=1).astype(np.float32)
+
+
+def part_quadrilaterals(keypoints, part, o_h, ar=0.5):
+    """``part_quadrilateral`` over the batch: keypoints [B, 18, 3] -> (quads [B, 4, 2] float32, valid [B] bool).  Rows of invalid samples are
+    unspecified.  Every value is produced by the same float32 operations, in the same order, as the per-sample function (tests compare them)."""
+    kp = np.asarray(keypoints)
+    B = kp.shape[0]
+    names, fallback = _PARTS[part]
+    idx = [_J[n] for n in names]
+    ok = (kp[:, idx, 2] >= 0.1).all(axis=1)
+    pts = np.float32(kp[:, idx, :2])
+    pts[:, :, 0] += 32
+    if len(names) == 4:
+        return pts, ok
+    if len(names) == 2:
+        quads = _segment_boxes(pts[:, 0], pts[:, 1], ar / 2.0)
+        if fallback is not None:                                           # hip without knee: a vertical from the hip to the bottom edge
+            fidx = _J[fallback[0]]
+            fok = ~ok & (kp[:, fidx, 2] >= 0.1)
+            hip = np.float32(kp[:, fidx, :2])
+            hip[:, 0] += 32
+            foot = np.stack([hip[:, 0], np.full(B, o_h - 1, np.float32)], axis=1).astype(np.float32)
+            fq = _segment_boxes(hip, foot, ar / 2.0)
+            quads = np.where(fok[:, None, None], fq, quads)
+            ok = ok | fok
+        return quads, ok
+    # head box: from twice the neck-to-nose vector down to the neck; without the nose, a square above the shoulder line
+    neck = 0.5 * (pts[:, 0] + pts[:, 1])
+    top = np.float32(neck + 2 * (pts[:, 2] - neck))
+    box = _segment_boxes(top, np.float32(neck), 0.5)
+    quads = box[:, [1, 2, 3, 0]]
+    fok = ~ok & (kp[:, [_J['lshoulder'], _J['rshoulder']], 2] >= 0.1).all(axis=1)
+    seg = pts[:, 1] - pts[:, 0]
+    nrm = np.stack([-seg[:, 1], seg[:, 0]], axis=1)
+    nrm = np.where((nrm[:, 1] > 0.0)[:, None], -nrm, nrm)
+    fq = np.stack([pts[:, 0] + nrm, pts[:, 0], pts[:, 1], pts[:, 1] + nrm], axis=1).astype(np.float32)
+    quads = np.where(fok[:, None, None], fq, quads)
+    return np.ascontiguousarray(quads, np.float32), ok | fok
+
+
 def crop_transforms(keypoints, h, w, o_h, ar=0.5):
-    """``get_crop`` for every (sample, part): keypoints [B, 18, 3] -> (M [B,10,3,3], M_inv [B,10,3,3], valid [B,10] bool); invalid parts are zero."""
+    """``get_crop`` for every (sample, part): keypoints [B, 18, 3] -> (M [B,10,3,3], M_inv [B,10,3,3], valid [B,10] bool); invalid parts are zero.
+    Vectorised over the batch: ten array-valued quadrilateral constructions and two batched 8 x 8 solves."""
     keypoints = np.asarray(keypoints)
     B = keypoints.shape[0]
     dst = np.float32(np.array([[w, h]]) * np.float32([[0.0, 0.0], [0.0, 1.0], [1.0, 1.0], [1.0, 0.0]]))
-    quads, where = [], []
-    for bi in range(B):
-        for p in range(NUM_PARTS):
-            q = part_quadrilateral(keypoints[bi], p, o_h, ar)
-            if q is not None:
-                quads.append(q)
-                where.append((bi, p))
+    quads = np.empty((B, NUM_PARTS, 4, 2), np.float32)
+    valid = np.empty((B, NUM_PARTS), bool)
+    for p in range(NUM_PARTS):
+        quads[:, p], valid[:, p] = part_quadrilaterals(keypoints, p, o_h, ar)
     M = np.zeros((B, NUM_PARTS, 3, 3), np.float64)
     M_inv = np.zeros((B, NUM_PARTS, 3, 3), np.float64)
-    valid = np.zeros((B, NUM_PARTS), bool)
-    if quads:
-        quads = np.stack(quads)
-        dsts = np.broadcast_to(dst, quads.shape)
-        fwd = perspective_transforms(quads, dsts)
-        bwd = perspective_transforms(dsts, quads)
-        bi, pi = np.array(where).T
-        M[bi, pi], M_inv[bi, pi], valid[bi, pi] = fwd, bwd, True
+    if valid.any():
+        q = quads[valid]
+        dsts = np.broadcast_to(dst, q.shape)
+        M[valid] = perspective_transforms(q, dsts)
+        M_inv[valid] = perspective_transforms(dsts, q)
     return M, M_inv, valid
+
+
+WARP_JOB_DTYPE = np.dtype([('m', '<f8', (9,)), ('src', '<u8'), ('dst', '<u8'), ('src_h', '<i4'), ('src_w', '<i4'), ('src_row_stride', '<i4'),
+                           ('src_pix_stride', '<i4'), ('dst_h', '<i4'), ('dst_w', '<i4'), ('dst_row_stride', '<i4'), ('dst_pix_stride', '<i4'),
+                           ('channels', '<i4'), ('border', '<i4')])          # pg_warp_job of include/pasta_b200.h (128 bytes)
 
 
 def _check_u8(t, name):
@@ -176,27 +220,17 @@ def _check_u8(t, name):
 
 
 def _launch_warps(jobs, device):
-    """jobs: list of WarpJob (host).  One H2D copy of the table + one launch."""
-    table = (_capi.WarpJob * len(jobs))(*jobs)
-    host = torch.frombuffer(bytearray(ctypes.string_at(ctypes.addressof(table), ctypes.sizeof(table))), dtype=torch.uint8)
-    dev = host.to(device, non_blocking=False)
-    max_pix = max(j.dst_h * j.dst_w for j in jobs)
+    """jobs: structured array of WARP_JOB_DTYPE records (host).  One H2D copy of the table + one launch."""
+    assert jobs.dtype == WARP_JOB_DTYPE and jobs.dtype.itemsize == 128
+    dev = torch.from_numpy(jobs.view(np.uint8)).to(device, non_blocking=False)
+    max_pix = int((jobs['dst_h'].astype(np.int64) * jobs['dst_w']).max())
     _capi.require_device()
-    _capi.check(_capi.load().pg_warp_perspective_u8(dev.data_ptr(), len(jobs), max_pix, _capi.current_stream(device)), 'pg_warp_perspective_u8')
+    _capi.check(_capi.load().pg_warp_perspective_u8(dev.data_ptr(), int(jobs.shape[0]), max_pix, _capi.current_stream(device)), 'pg_warp_perspective_u8')
     return dev                                                             # keep alive until the caller synchronises or reuses the stream
 
 
-def _job(src, src_off, dst, dst_off, coeffs, src_hw, src_strides, dst_hw, dst_strides, channels, border):
-    j = _capi.WarpJob()
-    for i, v in enumerate(np.asarray(coeffs, np.float64).reshape(9)):
-        j.m[i] = float(v)
-    j.src, j.dst = src + src_off, dst + dst_off
-    j.src_h, j.src_w = src_hw
-    j.src_row_stride, j.src_pix_stride = src_strides
-    j.dst_h, j.dst_w = dst_hw
-    j.dst_row_stride, j.dst_pix_stride = dst_strides
-    j.channels, j.border = channels, border
-    return j
+def _jobs(n):
+    return np.zeros(n, WARP_JOB_DTYPE)
 
 
 def warp_perspective(src, M, dsize, border_mode=BORDER_CONSTANT):
@@ -211,7 +245,13 @@ def warp_perspective(src, M, dsize, border_mode=BORDER_CONSTANT):
     w, h = int(dsize[0]), int(dsize[1])
     out = torch.empty((h, w, C), dtype=torch.uint8, device=img.device)
     coeffs = invert3x3(np.asarray(M, np.float64).reshape(3, 3))
-    keep = _launch_warps([_job(img.data_ptr(), 0, out.data_ptr(), 0, coeffs, (H, W), (W * C, C), (h, w), (w * C, C), C, int(border_mode))], img.device)
+    j = _jobs(1)
+    j['m'][0] = coeffs.reshape(9)
+    j['src'], j['dst'] = img.data_ptr(), out.data_ptr()
+    j['src_h'], j['src_w'], j['src_row_stride'], j['src_pix_stride'] = H, W, W * C, C
+    j['dst_h'], j['dst_w'], j['dst_row_stride'], j['dst_pix_stride'] = h, w, w * C, C
+    j['channels'], j['border'] = C, int(border_mode)
+    keep = _launch_warps(j, img.device)
     del keep
     return out[..., 0] if squeeze else out
 
@@ -243,18 +283,24 @@ class PatchRouter:
         masks = torch.zeros((B, h, w, 3 * P), dtype=torch.uint8, device=dev)
         img_lower = torch.zeros((B, h, w, 3 * PL), dtype=torch.uint8, device=dev)
         masks_lower = torch.zeros((B, h, w, 3 * PL), dtype=torch.uint8, device=dev)
-        jobs = []
+        # one record per cv2.warpPerspective call of the reference: (upper image, upper mask) for every valid part, plus (lower image, lower mask) for the legs
         src_bytes = H * W * 3
-        for bi in range(B):
-            for p in range(P):
-                if not valid[bi, p]:
-                    continue
-                for src, dst, nch, col in ((upper_img, img, 3 * P, p), (upper_clothes_mask, masks, 3 * P, p)) + \
-                        (((lower_img, img_lower, 3 * PL, p - FIRST_LOWER_PART), (lower_clothes_mask, masks_lower, 3 * PL, p - FIRST_LOWER_PART))
-                         if p >= FIRST_LOWER_PART else ()):
-                    jobs.append(_job(src.data_ptr(), bi * src_bytes, dst.data_ptr(), bi * h * w * nch + 3 * col, to_patch[bi, p],
-                                     (H, W), (W * 3, 3), (h, w), (w * nch, nch), 3, BORDER_REPLICATE))
-        keep = _launch_warps(jobs, dev) if jobs else None
+        bi, pi = np.nonzero(valid)
+        tables = []
+        for src, dst, nch, first in ((upper_img, img, 3 * P, 0), (upper_clothes_mask, masks, 3 * P, 0),
+                                     (lower_img, img_lower, 3 * PL, FIRST_LOWER_PART), (lower_clothes_mask, masks_lower, 3 * PL, FIRST_LOWER_PART)):
+            sel = pi >= first
+            b_, p_ = bi[sel], pi[sel]
+            j = _jobs(b_.shape[0])
+            j['m'] = to_patch[b_, p_].reshape(-1, 9)
+            j['src'] = src.data_ptr() + b_.astype(np.uint64) * np.uint64(src_bytes)
+            j['dst'] = dst.data_ptr() + b_.astype(np.uint64) * np.uint64(h * w * nch) + (3 * (p_ - first)).astype(np.uint64)
+            j['src_h'], j['src_w'], j['src_row_stride'], j['src_pix_stride'] = H, W, W * 3, 3
+            j['dst_h'], j['dst_w'], j['dst_row_stride'], j['dst_pix_stride'] = h, w, w * nch, nch
+            j['channels'], j['border'] = 3, BORDER_REPLICATE
+            tables.append(j)
+        jobs = np.concatenate(tables)
+        keep = _launch_warps(jobs, dev) if jobs.shape[0] else None
         lib, stream = _capi.load(), _capi.current_stream(dev)
         denorm_upper = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev)
         denorm_lower = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev)

@@ -21,7 +21,7 @@ from .torch_utils.ops import conv2d_gradfix
 
 
 class TryOnTrainer:
-    def __init__(self, G, D, lr=0.002, r1_gamma=10.0, l1_weight=40.0, mask_weight=20.0, d_reg_interval=16, g_reg_interval=4, group=None, capturable=False):
+    def __init__(self, G, D, lr=0.0025, r1_gamma=10.0, l1_weight=40.0, mask_weight=20.0, d_reg_interval=16, g_reg_interval=4, group=None, capturable=False):
         self.G, self.D, self.group = G, D, group
         self.r1_gamma, self.l1_weight, self.mask_weight, self.d_reg_interval = r1_gamma, l1_weight, mask_weight, d_reg_interval
         conv2d_gradfix.enabled = True                          # training_loop_wo_flow_fullbody.py:255
