@@ -71,7 +71,41 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
 
+    def _nvml_loop(self):
+        import pynvml as nv
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        bits = {'hw_slowdown': nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, 'nvmlClocksEventReasonHwSlowdown') else nv.nvmlClocksThrottleReasonHwSlowdown,
+                'hw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonHwThermalSlowdown', None) or nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                'sw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonSwThermalSlowdown', None) or nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                'sw_power_cap': getattr(nv, 'nvmlClocksEventReasonSwPowerCap', None) or nv.nvmlClocksThrottleReasonSwPowerCap}
+        get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        self.nvml_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        while not self._stop.is_set():
+            self.nvml_sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            r = int(get_reasons(h))
+            for nm, b in bits.items():
+                if r & int(b):
+                    self.nvml_reasons.add(nm)
+            self._stop.wait(0.01)
+
     def start(self):
+        # NVML in-process (a sample every ~10 ms: a 0.2 s timed region gets ~20 samples); nvidia-smi -lms as the fall-back
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # physical index of this process's device (CUDA_VISIBLE_DEVICES may remap): NVML enumerates all GPUs of the box
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            if vis:
+                ids = [v.strip() for v in vis.split(',') if v.strip()]
+                if self.index < len(ids) and ids[self.index].isdigit():
+                    self.index = int(ids[self.index])
+            self.nvml_sm, self.nvml_reasons, self.nvml_max, self._stop = [], set(), None, threading.Event()
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            self.proc = 'nvml'
+            return
+        except Exception:
+            self.proc = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '200', '-i', str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -87,6 +121,11 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        if self.proc == 'nvml':
+            self._stop.set()
+            self.thread.join(timeout=2)
+            sm = sorted(self.nvml_sm)
+            return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=self.nvml_max, reasons=sorted(self.nvml_reasons), samples=len(sm), source='nvml')
         time.sleep(0.25)
         self.proc.terminate()
         try:
@@ -427,6 +466,13 @@ def run_b200(args, world, rank, local):
             extra['dropin'] = d if 'unavailable' in d else dict(value=d['img_s'], unit=UNIT, ms_per_step=d['ms_per_step'], our_kernel_launches=d['our_kernel_launches'],
                                                                   **{k: d[k] for k in ('graph_img_s', 'graph_ms_per_step', 'graph_unavailable') if k in d},
                                                                   what='UNMODIFIED reference training/networks.py GeneratorFull over our torch_utils/ops overlay, eager, batch %d' % args.batch)
+            if time.perf_counter() - t_x < 120:
+                # the same after a legacy.load_network_pkl round trip with the persistence.import_hook recipe of INTEGRATION.md 2 (the reference's own
+                # hook re-routes modulated_conv2d of the pickled source to our one-launch layer; everything else stays the reference's code)
+                d = run_harness('overlay_hook', args.batch, 5, 2, timeout=300)
+                extra['dropin_hook'] = d if 'unavailable' in d else dict(value=d['img_s'], unit=UNIT, ms_per_step=d['ms_per_step'], our_kernel_launches=d['our_kernel_launches'],
+                                                                           **{k: d[k] for k in ('graph_img_s', 'graph_ms_per_step', 'graph_unavailable') if k in d},
+                                                                           what='UNMODIFIED reference networks, pickled and re-loaded through legacy.load_network_pkl with the import_hook that swaps modulated_conv2d, eager, batch %d' % args.batch)
             if time.perf_counter() - t_x < 240:
                 d = run_harness('gpu', args.batch, 5, 2, timeout=420)
                 extra['reference_gpu'] = d if 'unavailable' in d else dict(value=d['img_s'], unit=UNIT, ms_per_step=d['ms_per_step'], plugins=d.get('plugins'),
