@@ -748,11 +748,32 @@ class StyleEncoderNetworkV16(OpsModule):
         feat = [Conv2dLayer(3, ngf, kernel_size=3)] + [Conv2dLayer(ngf, ngf, kernel_size=3, down=2) for _ in range(3)]
         self.feat_enc = nn.Sequential(*feat)
 
-    def forward(self, x, const_input):
+    def _retain_features(self, x):
+        """feat_enc.  Inference on the CUDA table: the >= 128 px feature maps are only read by the merge convolutions of the channel-blocked synthesis
+        blocks and by the next stride-2 layer, so they are produced channel-blocked fp16 straight away (no fp32 copy, no nchw -> c8 pass); the
+        stride-2 layers read them through the strided TMA box.  Below 128 px the maps are dense fp32 as before."""
+        c8_ok = getattr(self.ops, 'c8_ok', None)
+        chain = c8_ok is not None and x.is_cuda and not torch.is_grad_enabled() and os.environ.get('PASTA_B200_C8_CHAIN', '1') != '0'
         feats = []
+        h, w = int(x.shape[2]), int(x.shape[3])
         for layer in self.feat_enc:
-            const_input = layer(const_input)
-            feats.append(const_input)
+            if not chain:
+                x = layer(x)
+                feats.append(x)
+                continue
+            cin, cout, k = int(layer.weight.shape[1]), int(layer.weight.shape[0]), int(layer.weight.shape[2])
+            oh, ow = h // layer.down, w // layer.down
+            if x.ndim == 5 and not (layer.down == 2 and c8_ok(cin, h, w, k, 1, 2)):
+                x = _spade_to_nchw(x).float()
+            want = oh >= 128 and cout % 16 == 0 and c8_ok(cout, oh, ow, 1)
+            out_c8 = bool(want and (x.ndim == 5 or K_supported_c8_out(layer, x) or (layer.down == 2 and _down2_supported(layer, x))))
+            x = layer(x, out_c8=out_c8)
+            feats.append(x)
+            h, w = oh, ow
+        return feats
+
+    def forward(self, x, const_input):
+        feats = self._retain_features(const_input)
         x = self.model(x)
         return self.fc(x.view(x.size(0), -1)), feats
 
@@ -859,9 +880,23 @@ def _with_c8_cat_feats(module, cat_feat):
     cat_feat = dict(cat_feat)
     for key in [k for k in cat_feat if k.isdigit() and int(k) >= 128]:
         t = cat_feat[key]
-        if t.is_cuda and t.ndim == 4 and t.shape[1] % 16 == 0 and c8_ok(t.shape[1], t.shape[2], t.shape[3], 1):
+        if t.ndim == 5:                                   # already channel-blocked (StyleEncoderNetworkV16._retain_features)
+            cat_feat[key + '_c8'] = t
+            cat_feat[key] = _LazyDense(t)
+        elif t.is_cuda and t.ndim == 4 and t.shape[1] % 16 == 0 and c8_ok(t.shape[1], t.shape[2], t.shape[3], 1):
             cat_feat[key + '_c8'] = K.to_c8(t)
     return cat_feat
+
+
+class _LazyDense:
+    """A channel-blocked feature map standing in for its dense form: converted only if a consumer outside the channel-blocked chain asks for it."""
+
+    def __init__(self, t):
+        self.t = t
+
+    def to(self, dtype):
+        from .torch_utils.ops import conv_igemm as K
+        return K.from_c8(self.t, dtype=torch.float16).to(dtype)
 
 
 class SynthesisBlockFull(OpsModule):
@@ -1219,11 +1254,10 @@ class StyleEncoderNetwork512(OpsModule):
         self.fc = FullyConnectedLayer(output_nc, output_nc)
         self.feat_enc = nn.Sequential(Conv2dLayer(3, ngf, kernel_size=3), *[Conv2dLayer(ngf, ngf, kernel_size=3, down=2) for _ in range(3)])
 
+    _retain_features = StyleEncoderNetworkV16._retain_features
+
     def forward(self, x, const_input):
-        feats = []
-        for layer in self.feat_enc:
-            const_input = layer(const_input)
-            feats.append(const_input)
+        feats = self._retain_features(const_input)
         x = self.model(x)
         return self.fc(x.view(x.size(0), -1)), feats
 
