@@ -1703,7 +1703,7 @@ __global__ void __launch_bounds__(kRfThreads) conv_rowfold_kernel(const __grid_c
         for (int j = threadIdx.x; j < p.BN; j += kRfThreads) s_shift[j] = (j < p.Cout && p.bias) ? p.bias[j] * p.gain : 0.f;
         for (int r = threadIdx.x; r < 8 * kRfPlanes; r += kRfThreads) {
             const int c = r / p.ks, kh = r - c * p.ks;
-            s_tab[r] = r < p.nrows ? make_int2(c * HW, kh - pad) : make_int2(0, 1 << 20);      // padding channel: row out of range
+            s_tab[r] = r < p.nrows ? make_int2(c * HW + (kh - pad) * p.W, kh - pad) : make_int2(0, 1 << 20);      // padding channel: row out of range
         }
         fence_proxy_async();
     }
@@ -1717,10 +1717,12 @@ __global__ void __launch_bounds__(kRfThreads) conv_rowfold_kernel(const __grid_c
     const float slope = (p.act == PG_ACT_LINEAR) ? 1.f : (p.act == PG_ACT_RELU ? 0.f : p.alpha);
     const bool do_act = p.act != PG_ACT_LINEAR, do_clamp = p.clamp >= 0.f;
     uint32_t phase = 0;
+    // tile -> (segment of 128 columns, row, sample), advanced by gridDim.x per iteration with carries: the divisions happen once per CTA, not per tile
+    int wseg = (int)blockIdx.x % p.wsegs, hn0 = (int)blockIdx.x / p.wsegs, h = hn0 % p.H, n = hn0 / p.H;
+    const int step_w = (int)gridDim.x % p.wsegs, step_hn = (int)gridDim.x / p.wsegs, step_h = step_hn % p.H, step_n = step_hn / p.H;
     for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
-        const int wseg = tile % p.wsegs, hn = tile / p.wsegs, h = hn % p.H, n = hn / p.H;
         const int w0 = wseg * 128;
-        const float* xn = p.x + (size_t)n * p.Cin * HW;
+        const float* xn = p.x + (size_t)n * p.Cin * HW + h * p.W;
         // ---- build: A[plane j][column t] = the 8 (channel, kernel row) pairs of plane j at image column w0 - pad + t (zeros outside the image)
         for (int task = threadIdx.x; task < nplanes * kRfPA; task += kRfThreads) {
             const int j = task / kRfPA, t = task - j * kRfPA;
@@ -1729,9 +1731,8 @@ __global__ void __launch_bounds__(kRfThreads) conv_rowfold_kernel(const __grid_c
             float v[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                const int2 tb = s_tab[j * 8 + i];
-                const int row = h + tb.y;
-                v[i] = (col_ok && (unsigned)row < (unsigned)p.H) ? __ldg(xn + tb.x + row * p.W + col) : 0.f;
+                const int2 tb = s_tab[j * 8 + i];                          // (element offset of (channel, kernel row) relative to row h, kernel row - pad)
+                v[i] = (col_ok && (unsigned)(h + tb.y) < (unsigned)p.H) ? __ldg(xn + tb.x + col) : 0.f;
             }
             *reinterpret_cast<uint4*>(a_base + (size_t)task * 16) = pack_half8(v);
         }
@@ -1766,12 +1767,17 @@ __global__ void __launch_bounds__(kRfThreads) conv_rowfold_kernel(const __grid_c
                 uint32_t rg[16];
                 tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cc * 16), rg);
                 float v[16];
+                if (do_act && slope == 0.f && !do_clamp) {                // relu, no clamp (the encoder stems): two instructions per value
 #pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    float t = fmaf(__uint_as_float(rg[i]), p.gain, s_shift[cc * 16 + i]);
-                    if (do_act) t = fmaxf(t, 0.f) + slope * fminf(t, 0.f);
-                    if (do_clamp) t = fminf(fmaxf(t, -p.clamp), p.clamp);
-                    v[i] = t;
+                    for (int i = 0; i < 16; i++) v[i] = fmaxf(fmaf(__uint_as_float(rg[i]), p.gain, s_shift[cc * 16 + i]), 0.f);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        float t = fmaf(__uint_as_float(rg[i]), p.gain, s_shift[cc * 16 + i]);
+                        if (do_act) t = fmaxf(t, 0.f) + slope * fminf(t, 0.f);
+                        if (do_clamp) t = fminf(fmaxf(t, -p.clamp), p.clamp);
+                        v[i] = t;
+                    }
                 }
                 if (p.y_c8) {
                     uint4* yb = reinterpret_cast<uint4*>(p.y) + ((size_t)n * p.cb_out + (size_t)cc * 2) * HW + (size_t)h * p.W + w;
@@ -1785,6 +1791,9 @@ __global__ void __launch_bounds__(kRfThreads) conv_rowfold_kernel(const __grid_c
         }
         tc_fence_before();
         __syncthreads();                 // every warp is done with the accumulator and the MMAs are done with the A stage
+        wseg += step_w; h += step_h; n += step_n;
+        if (wseg >= p.wsegs) { wseg -= p.wsegs; h++; }
+        if (h >= p.H) { h -= p.H; n++; }
     }
     if (warp == 1) {
         tc_fence_after();
@@ -1980,7 +1989,8 @@ static bool use_im2col(int Cin, int ksize, int up) { return up == 1 && ksize > 1
 // Row-folded form of the same layers (conv_rowfold_kernel): its packed weights follow the folded-tap pack in the same workspace, so the choice
 // between the two can be made per launch (the row-folded kernel needs W % 128 == 0 and a plain epilogue).
 static bool rowfold_shape_ok(int Cin, int Cout, int ksize, int up) {
-    return use_im2col(Cin, ksize, up) && Cin * ksize <= 8 * pg::kRfPlanes && ksize <= 7 && Cout >= 16 && Cout <= 128;
+    // (k = 1 with a handful of input channels -- the 6-channel pose stem -- is the degenerate case: one tap, Cin "rows")
+    return (use_im2col(Cin, ksize, up) || (up == 1 && ksize == 1 && Cin < 16)) && Cin * ksize <= 8 * pg::kRfPlanes && ksize <= 7 && Cout >= 16 && Cout <= 128;
 }
 static int64_t rowfold_pack_bytes(int Cin, int Cout, int ksize, int up) {
     return rowfold_shape_ok(Cin, Cout, ksize, up) ? (int64_t)ksize * pg::kRfPlanes * ((Cout + 15) / 16 * 16) * 16 : 0;

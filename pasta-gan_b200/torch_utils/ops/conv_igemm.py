@@ -73,12 +73,16 @@ def half_input_ok(x, w, up=1, down=1, x2=None):
             x.shape[3] % 2 == 0 and x.shape[3] <= 256 and x.data_ptr() % 4 == 0)
 
 
+_DOWN2_TMA_MIN = 256        # smallest input height for which channel-blocked down-2 layers are routed through the strided TMA box (tests lower it)
+
+
 def c8_input_ok(c, h, wd, k, up=1, down=1):
     """A channel-blocked input is loaded by TMA: plain stride-1 (or up-2) 1x1 / 3x3 layer, fp16 operands, whole 16-channel chunks; 3x3 layers wider than
     127 columns run in 64-column bands (even W); 1x1 layers wider than 128 columns are viewed as rows of 128 pixels (W % 128 == 0)."""
     if down == 2:
         # down-2 3x3: the space-to-depth planes come through a strided TMA box; the GEMM runs at the output resolution (bands above 127 columns)
-        return (enabled and operand_format == 'fp16' and up == 1 and k == 3 and c % 16 == 0 and h % 2 == 0 and wd % 2 == 0 and h >= 4 and
+        # (measured: wins from 256-px inputs up -- 64->128 @512^2 584 -> 480 us; at 128 px and below the converter path's per-sample CTAs are faster)
+        return (enabled and operand_format == 'fp16' and up == 1 and k == 3 and c % 16 == 0 and h % 2 == 0 and wd % 2 == 0 and h >= _DOWN2_TMA_MIN and
                 (wd // 2 <= 127 or (wd // 2) % 2 == 0) and os.environ.get('PASTA_B200_CONV_TMA', '1') != '0')
     return (enabled and operand_format == 'fp16' and down == 1 and up in (1, 2) and k in (1, 3) and c % 16 == 0 and (k == 1 or c * k * k > 160) and
             ((wd <= 128 or wd % 128 == 0) if k == 1 else (wd <= 127 or wd % 2 == 0)) and

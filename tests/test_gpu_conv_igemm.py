@@ -54,7 +54,7 @@ def test_plain_conv(cv, shape, fmt):
 
 ROWFOLD = [
     # (N, Cin, Cout, H, W, k): W % 128 == 0 and Cin * k <= 32 -> the row-folded first-layer kernel
-    (2, 3, 64, 40, 128, 7), (1, 3, 64, 256, 256, 7), (3, 3, 64, 17, 256, 3), (1, 4, 32, 9, 128, 5), (2, 6, 128, 12, 384, 3), (1, 1, 16, 5, 128, 7), (1, 3, 48, 300, 128, 7),
+    (2, 3, 64, 40, 128, 7), (1, 3, 64, 256, 256, 7), (3, 3, 64, 17, 256, 3), (1, 4, 32, 9, 128, 5), (2, 6, 128, 12, 384, 3), (1, 1, 16, 5, 128, 7), (1, 3, 48, 300, 128, 7), (2, 6, 64, 20, 256, 1), (1, 4, 32, 8, 128, 1), (3, 3, 64, 7, 384, 7),
 ]
 
 
@@ -536,10 +536,11 @@ def test_channel_blocked_residual_with_dense_output(cv, shape):
 
 
 @pytest.mark.parametrize('shape', [(2, 64, 128, 256, 256), (1, 128, 256, 128, 128), (3, 32, 48, 36, 20), (2, 256, 256, 32, 32), (1, 16, 16, 8, 512), (1, 64, 64, 6, 260)], ids=str)
-def test_c8_tma_down2(cv, shape):
+def test_c8_tma_down2(cv, shape, monkeypatch):
     """Down-2 3x3 from a channel-blocked input: the space-to-depth planes come through a strided 4-D TMA box (PG_CONV_DOWN2_C8).  Against the fp64
     oracle of conv2d_resample(down=2) and against the converter path on the same fp16-rounded input (same products, different K order)."""
     n, cin, cout, h, w = shape
+    monkeypatch.setattr(cv, '_DOWN2_TMA_MIN', 4)                            # (the network only routes >= 256-px inputs this way)
     torch.manual_seed(sum(shape))
     xh = torch.randn(n, cin, h, w, device=DEV).half()
     wt = torch.randn(cout, cin, 3, 3, device=DEV) / (cin * 9) ** 0.5
