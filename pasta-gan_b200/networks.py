@@ -842,7 +842,10 @@ class SpadeResBlockV2(OpsModule):
         self.spade0 = SpadeNormBlock(feat_channels, in_channels)
         self.spade1 = SpadeNormBlock(feat_channels, out_channels)
 
-    def forward(self, x, denorm_feat):
+    def forward(self, x, denorm_feat, out_c8=False):
+        """``out_c8``: the caller's consumer loads a channel-blocked tensor (the next SPADE block's first convolution, or the up-2 convolution of the
+        texture block): the block result then leaves conv1's epilogue as channel-blocked fp16 -- half the bytes written, and the consumer runs on
+        the TMA operand path instead of the fp32 converter path."""
         x = self.conv(x, no_act=True)
         # the pre-activation (relu * act_gain * gain) of each consuming Spade conv is handed to the norm block, which applies it in the
         # same pass (fused: in the GEMM epilogue that produces gamma / beta); the convs then run bare
@@ -856,7 +859,7 @@ class SpadeResBlockV2(OpsModule):
         t = self.spade1(x, denorm_feat, post_act=pre(self.conv1, np.sqrt(0.5)), out_half=True, out_k=3)
         if y.ndim == 5 and t.ndim != 5:
             y = _spade_to_nchw(y).float()                 # conv1 is not on the TMA path: its residual must be plain fp32
-        return self.conv1(t, no_act=True, residual=y)
+        return self.conv1(t, no_act=True, residual=y, out_c8=bool(out_c8 and t.ndim == 5 and y.ndim == 5))
 
 
 def _c8_chain_ok(block, x, cat_feat):
@@ -1095,8 +1098,15 @@ class SynthesisNetworkFull(OpsModule):
             self.get_spade_feat(m_up, denorm_upper_mask, denorm_upper_input, out=spade_feat[:, :cf], feat=f_up)      # upper | lower (:5831)
             self.get_spade_feat(m_lo, denorm_lower_mask, denorm_lower_input, out=spade_feat[:, cf:], feat=f_lo)
         x = x_128
+        # the trunk between the SPADE blocks (and into the texture block) stays channel-blocked when the consumers load it by TMA
+        import types
+        n_, c_ = int(x.shape[0]), int(self.spade_b128_3.conv1.weight.shape[0])
+        probe = types.SimpleNamespace(is_cuda=x.is_cuda, ndim=5, shape=(n_, c_ // 8, int(x.shape[2]), int(x.shape[3]), 8))
+        trunk_c8 = c8_ok is not None and x.is_cuda and not torch.is_grad_enabled() and c_ % 16 == 0 and os.environ.get('PASTA_B200_C8_CHAIN', '1') != '0' and \
+            bool(c8_ok(c_, int(x.shape[2]), int(x.shape[3]), 3))
+        tex_c8 = trunk_c8 and _c8_chain_ok(self.texture_b256, probe, cat_feat)
         for k in (1, 2, 3):
-            x = getattr(self, f'spade_b128_{k}')(x, spade_feat)
+            x = getattr(self, f'spade_b128_{k}')(x, spade_feat, out_c8=(trunk_c8 if k < 3 else tex_c8))
         _, finetune_img, _ = self.texture_b256(x, img_128, block_ws[-1], pose_feat, cat_feat, force_fp32=True, **block_kwargs)
         return img, finetune_img, parsing
 
