@@ -656,7 +656,10 @@ class ResBlock(OpsModule):
             oh, ow = (int(x.shape[2]) // self.conv0.down, int(x.shape[3]) // self.conv0.down)
             inner = bool(c8_ok(cout, oh, ow, 3))
         if x.ndim == 5:
-            assert inner and self.conv0.down == 1, 'a channel-blocked input needs the channel-blocked chain (stride 1)'
+            # channel-blocked input: every convolution of the block loads by TMA -- stride 1, or (down-sampling block) the 3x3 and the 1x1 skip both
+            # through the strided space-to-depth box, the 1x1 as a centre-tap 3x3
+            assert inner and (self.conv0.down == 1 or c8_ok(int(x.shape[1]) * 8, int(x.shape[2]), int(x.shape[3]), 3, 1, 2)), \
+                'a channel-blocked input needs the channel-blocked chain'
             y = self.skip(x, gain=np.sqrt(0.5), out_c8=True)
             return self.conv1(self.conv0(x, out_c8=True), gain=np.sqrt(0.5), residual=y, out_c8=out_c8)
         if inner and self.conv0.down == 1 and K_supported_c8_out(self.skip, x):
@@ -1007,7 +1010,8 @@ class SynthesisNetworkFull(OpsModule):
         c0 = int(enc[0].weight.shape[0])
         if c8_ok is not None and x.is_cuda and not torch.is_grad_enabled() and os.environ.get('PASTA_B200_C8_CHAIN', '1') != '0' and \
                 c0 % 16 == 0 and c8_ok(c0, x.shape[2], x.shape[3], 3) and c8_ok(c0, x.shape[2], x.shape[3], 1):
-            return enc[2](enc[1](enc[0](x, out_c8=True)))
+            down_c8 = bool(c8_ok(c0, x.shape[2], x.shape[3], 3, 1, 2))     # the down-sampling block reads its input through the strided TMA box
+            return enc[2](enc[1](enc[0](x, out_c8=True), out_c8=down_c8))
         return enc(x)
 
     def get_spade_feat(self, mask_256, denorm_mask, denorm_input, out=None, feat=None):

@@ -82,7 +82,7 @@ def c8_input_ok(c, h, wd, k, up=1, down=1):
     if down == 2:
         # down-2 3x3: the space-to-depth planes come through a strided TMA box; the GEMM runs at the output resolution (bands above 127 columns)
         # (measured: wins from 256-px inputs up -- 64->128 @512^2 584 -> 480 us; at 128 px and below the converter path's per-sample CTAs are faster)
-        return (enabled and operand_format == 'fp16' and up == 1 and k == 3 and c % 16 == 0 and h % 2 == 0 and wd % 2 == 0 and h >= _DOWN2_TMA_MIN and
+        return (enabled and operand_format == 'fp16' and up == 1 and k in (1, 3) and c % 16 == 0 and h % 2 == 0 and wd % 2 == 0 and h >= _DOWN2_TMA_MIN and
                 (wd // 2 <= 127 or (wd // 2) % 2 == 0) and os.environ.get('PASTA_B200_CONV_TMA', '1') != '0')
     return (enabled and operand_format == 'fp16' and down == 1 and up in (1, 2) and k in (1, 3) and c % 16 == 0 and (k == 1 or c * k * k > 160) and
             ((wd <= 128 or wd % 128 == 0) if k == 1 else (wd <= 127 or wd % 2 == 0)) and
@@ -146,6 +146,30 @@ def _pack_cfg(w_scale, mode, flip_weight, fmt_code, n_tile=0):
 def _drop_entries(wid):
     for key in [k for k in _pack_store if k[0] == wid]:
         _pack_store.pop(key, None)
+
+
+_center_cache = {}        # id(w1x1) -> dict(ref, version, ptr, w3): 1x1 weights embedded as the centre tap of a 3x3 kernel
+
+
+def _center_3x3(w):
+    """A 1x1 down-2 layer (FIR + stride-2 1x1, the skip branch of a down-sampling res-block) is the 3x3 down-2 form with only the centre tap set:
+    conv2d_resample(down=2) of a 3x3 kernel filters with pad 2 and strides from offset 0, the 1x1 form filters with pad 1, and the centre tap sits one
+    sample in.  The embedded tensor is kept per parameter and refreshed in place when the parameter moves, so the packed-weight store and captured
+    CUDA graphs follow weight updates (refresh_packed_weights)."""
+    hit = _center_cache.get(id(w))
+    if hit is not None and hit['ref']() is not w:
+        _center_cache.pop(id(w), None)
+        hit = None
+    if hit is None:
+        wid = id(w)
+        hit = dict(ref=weakref.ref(w, lambda _r, wid=wid: _center_cache.pop(wid, None)), version=None, ptr=None,
+                   w3=torch.zeros([int(w.shape[0]), int(w.shape[1]), 3, 3], dtype=torch.float32, device=w.device))
+        _center_cache[id(w)] = hit
+    if hit['version'] != w._version or hit['ptr'] != w.data_ptr():
+        with torch.no_grad():
+            hit['w3'][:, :, 1, 1].copy_(w.detach()[:, :, 0, 0])
+        hit['version'], hit['ptr'] = w._version, w.data_ptr()
+    return hit['w3']
 
 
 def _run_prepack(capi, w, f, w_scale, mode, flip_weight, fmt_code, ws, batch=1, w_batch_stride=0, styles=None, n_tile=0):
@@ -217,6 +241,10 @@ def refresh_packed_weights(device=None):
             device = torch.device('cuda', torch.cuda.current_device())
     for hit in _cat_cache.values():                       # [gamma ; beta] concatenations first: rebuilt in place, their packed copies follow below
         done += _refresh_cat(hit)
+    for hit in list(_center_cache.values()):              # centre-tap embeddings of 1x1 down-2 weights likewise
+        w1 = hit['ref']()
+        if w1 is not None:
+            _center_3x3(w1)
     for (wid, _cfg), e in list(_pack_store.items()):
         w = e.wref()
         if w is None or (device is not None and w.device != device):
@@ -284,6 +312,8 @@ def conv2d_igemm(x, w, f=None, up=1, down=1, flip_weight=True, styles=None, dcoe
         cout, cin_w, k = int(w.shape[1]), int(w.shape[2]), int(w.shape[4])
     else:
         cout, cin_w, k, _ = (int(v) for v in w.shape)
+        if x_c8 and down == 2 and k == 1:                 # skip branch of a down-sampling res-block on the strided-TMA path
+            w, k = _center_3x3(w), 3
     assert cin_w == cin, 'weight / input channel mismatch'
     x = x.contiguous()
     if x2 is not None and not x_c8:

@@ -557,6 +557,23 @@ def test_c8_tma_down2(cv, shape, monkeypatch):
         assert torch.equal(cv.from_c8(yc, cout, dtype=torch.float16), y.half())
 
 
+def test_c8_tma_down2_1x1_skip(cv, monkeypatch):
+    """The 1x1 down-2 skip of a down-sampling res-block on the strided-TMA path: a centre-tap 3x3 (conv2d_resample(down=2) of a 1x1 kernel filters with
+    pad 1, of a 3x3 kernel with pad 2 -- the centre tap sits one sample in).  Against the oracle's 1x1 form, and following an in-place weight update."""
+    monkeypatch.setattr(cv, '_DOWN2_TMA_MIN', 4)
+    torch.manual_seed(3)
+    n, cin, cout, h, w = 2, 64, 128, 64, 96
+    xh = torch.randn(n, cin, h, w, device=DEV).half()
+    wt = torch.nn.Parameter(torch.randn(cout, cin, 1, 1, device=DEV) / cin ** 0.5)
+    f = O.setup_filter([1, 3, 3, 1]).to(DEV)
+    for _ in range(2):
+        ref = O.conv2d_resample(xh.double().cpu(), wt.detach().double().cpu(), f.double().cpu(), down=2, padding=0)
+        y = cv.conv2d_igemm(cv.to_c8(xh), wt, f=f, down=2, gain=0.7, cache_weights=True)
+        assert y.shape == ref.shape and rel_err(y, ref * 0.7) < TOL['fp16']
+        with torch.no_grad():
+            wt.mul_(-1.5)                                                    # optimizer-style in-place update: the embedded copy and its pack must follow
+
+
 def test_c8_tma_up2_spade_and_folded_styles(cv):
     """TMA operand path under the other epilogues: polyphase up-2, the SPADE epilogue (blocked in, blocked out), and a modulated layer whose styles
     are folded into per-sample packed weights (the activations cannot be scaled on the way in)."""
