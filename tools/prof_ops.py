@@ -34,6 +34,11 @@ with torch.no_grad():
     for _ in range(2):
         conv_igemm.conv2d_igemm(x3, w7, bias=torch.zeros(64, device=dev), act='relu', gain=2 ** 0.5, out_c8=True)  # conv_rowfold_kernel: 3->64 7x7 @256^2, batch 32 (garment encoder stem)
         conv_igemm.conv2d_igemm(xb, wb, fmt='tf32')                                                                # 128->128 @128^2, kind::tf32 operands (conv_igemm_kernel)
+    x32 = torch.randn(16, 512, 32, 32, device=dev); w512 = torch.randn(3, 512, 1, 1, device=dev); s512 = torch.randn(16, 512, device=dev) / 16
+    xd = conv_igemm.to_c8(torch.randn(16, 64, 256, 256, device=dev)); wd = torch.randn(128, 64, 3, 3, device=dev) / 24
+    for _ in range(2):
+        torgb.torgb_skip(x32, w512, styles=s512, bias=torch.zeros(3, device=dev), clamp=256, img=torch.randn(16, 3, 16, 16, device=dev), f=f)   # torgb_skip_splitc_kernel<3>
+        conv_igemm.conv2d_igemm(xd, wd, f=f, down=2, act='lrelu', gain=2 ** 0.5, out_c8=True)                      # down-2 64->128 @256^2 from C8: strided 4-D TMA box
     # patch routing: all rectifying warps of a batch in one launch + the back-warp composite
     from pasta_gan_b200 import patch_routing, synthetic
     d = synthetic.synth_patch_routing_inputs(16, seed=3)

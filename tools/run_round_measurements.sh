@@ -15,6 +15,6 @@ timeout -s KILL 200 python tools/step_breakdown.py --workload gen512 > $R/r2_ste
 # ncu passes (each only after the same command has exited 0 without ncu above): launch list of a 2-step eager bench run, and --set full on the op driver
 timeout -s KILL 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $R/r2_bench_launches.csv python bench.py --steps 2 --warmup 1 --no-graph --no-extras --skip-cpu-baseline > $R/r2_ncu_bench.log 2>&1
 timeout -s KILL 200 python tools/prof_ops.py > $R/r2_prof_ops_plain.log 2>&1 && \
-timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:"bias_act|upfirdn2d|conv_igemm|conv_rowfold_kernel|conv_wgrad|torgb|instance_stats|warp_perspective|patch_denorm" -c 60 -o $R/r2_ops_full -f python tools/prof_ops.py > $R/r2_ncu_ops.log 2>&1
-python tools/ncu_summary.py $R/r2_ops_full.ncu-rep > $R/r2_kernels_ncu_full.csv 2>> $R/r2_ncu_ops.log
+timeout -s KILL 700 ncu --set full --clock-control none -k regex:"bias_act|upfirdn2d|conv_igemm|conv_rowfold_kernel|conv_wgrad|torgb|instance_stats|warp_perspective|patch_denorm" -c 60 -o /tmp/r2_ops_full -f python tools/prof_ops.py > $R/r2_ncu_ops.log 2>&1
+python tools/ncu_summary.py /tmp/r2_ops_full.ncu-rep > $R/r2_kernels_ncu_full.csv 2>> $R/r2_ncu_ops.log
 python tools/summarize_launches.py $R/r2_bench_launches.csv 40 > $R/r2_bench_launches_summary.txt 2>&1
