@@ -184,11 +184,11 @@ HAVE_REF = os.path.isdir(os.path.join(ROOT, 'baseline', '_ref', 'torch_utils'))
 DTYPE = 'f16 tensor-core operands, f32 accumulate (TMEM), f32 I/O at the API boundary'
 
 
-def run_harness(mode, batch, steps, warmup, timeout, check=False, env=None):
+def run_harness(mode, batch, steps, warmup, timeout, check=False, env=None, extra_args=()):
     """One arrangement of the unmodified reference in its own process -> its JSON dict (or {'unavailable': why})."""
     if not HAVE_REF:
         return dict(unavailable='baseline/_ref not present')
-    cmd = [sys.executable, HARNESS, '--mode', mode, '--batch', str(batch), '--steps', str(steps), '--warmup', str(warmup)] + (['--check'] if check else [])
+    cmd = [sys.executable, HARNESS, '--mode', mode, '--batch', str(batch), '--steps', str(steps), '--warmup', str(warmup)] + (['--check'] if check else []) + list(extra_args)
     try:
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=dict(os.environ, **(env or {})))
         lines = [ln for ln in r.stdout.splitlines() if ln.startswith('{')]
@@ -205,7 +205,9 @@ def time_cpu_reference(steps, warmup, batch=1):
     """The reference's own CPU implementation (impl='ref' ops, unmodified networks.py) on the host cores; falls back to the oracle port only where the
     shipped copy of the reference tree is absent."""
     if HAVE_REF:
-        r = run_harness('cpu', batch, steps, warmup, timeout=1200)
+        # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to its workers: the CPU arm would otherwise run on one thread)
+        ncpu = str(os.cpu_count() or 1)
+        r = run_harness('cpu', batch, steps, warmup, timeout=1200, env=dict(OMP_NUM_THREADS=ncpu, MKL_NUM_THREADS=ncpu), extra_args=['--threads', ncpu])
         if 'unavailable' not in r:
             return dict(value=r['img_s'], unit=UNIT, cores=r['cores'], threads=r['threads'], kind='reference',
                         sample=f'{steps} forward(s) of batch {batch}: UNMODIFIED reference GeneratorFull 256x256 (training/networks.py:5844) with its impl=ref ops '
