@@ -625,7 +625,7 @@ class ToRGBLayerFull(OpsModule):
         return head(self.weight, self.bias), parsing
 
 
-def K_supported_c8_out(layer, x):
+def _supported_c8_out(layer, x):
     """True when ``layer`` (a plain stride-1 Conv2dLayer) applied to the fp32 NCHW tensor ``x`` runs on the tcgen05 kernel, i.e. can write a
     channel-blocked result."""
     from .torch_utils.ops import conv_igemm as K
@@ -662,7 +662,7 @@ class ResBlock(OpsModule):
                 'a channel-blocked input needs the channel-blocked chain'
             y = self.skip(x, gain=np.sqrt(0.5), out_c8=True)
             return self.conv1(self.conv0(x, out_c8=True), gain=np.sqrt(0.5), residual=y, out_c8=out_c8)
-        if inner and self.conv0.down == 1 and K_supported_c8_out(self.skip, x):
+        if inner and self.conv0.down == 1 and _supported_c8_out(self.skip, x):
             # the skip branch is only ever read back as conv1's residual: channel-blocked fp16 (two 16-byte loads per thread and chunk in the
             # epilogue instead of sixteen strided 4-byte loads)
             return self.conv1(self.conv0(x, out_c8=True), gain=np.sqrt(0.5), residual=self.skip(x, gain=np.sqrt(0.5), out_c8=True))
@@ -696,7 +696,7 @@ class ConstEncoderNetwork(OpsModule):
             oh, ow = h // layer.down, w // layer.down
             out_c8 = bool(nxt is not None and nxt.down == 2 and int(layer.weight.shape[0]) % 16 == 0 and
                           c8_ok(int(nxt.weight.shape[1]), oh, ow, int(nxt.weight.shape[2]), 1, 2) and
-                          (x.ndim == 5 or K_supported_c8_out(layer, x) or (layer.down == 2 and _down2_supported(layer, x))))
+                          (x.ndim == 5 or _supported_c8_out(layer, x) or (layer.down == 2 and _down2_supported(layer, x))))
             x = layer(x, out_c8=out_c8)
             h, w = oh, ow
         return x
@@ -769,7 +769,7 @@ class StyleEncoderNetworkV16(OpsModule):
             if x.ndim == 5 and not (layer.down == 2 and c8_ok(cin, h, w, k, 1, 2)):
                 x = _spade_to_nchw(x).float()
             want = oh >= 128 and cout % 16 == 0 and c8_ok(cout, oh, ow, 1)
-            out_c8 = bool(want and (x.ndim == 5 or K_supported_c8_out(layer, x) or (layer.down == 2 and _down2_supported(layer, x))))
+            out_c8 = bool(want and (x.ndim == 5 or _supported_c8_out(layer, x) or (layer.down == 2 and _down2_supported(layer, x))))
             x = layer(x, out_c8=out_c8)
             feats.append(x)
             h, w = oh, ow
@@ -1103,7 +1103,6 @@ class SynthesisNetworkFull(OpsModule):
             self.get_spade_feat(m_lo, denorm_lower_mask, denorm_lower_input, out=spade_feat[:, cf:], feat=f_lo)
         x = x_128
         # the trunk between the SPADE blocks (and into the texture block) stays channel-blocked when the consumers load it by TMA
-        import types
         n_, c_ = int(x.shape[0]), int(self.spade_b128_3.conv1.weight.shape[0])
         probe = types.SimpleNamespace(is_cuda=x.is_cuda, ndim=5, shape=(n_, c_ // 8, int(x.shape[2]), int(x.shape[3]), 8))
         trunk_c8 = c8_ok is not None and x.is_cuda and not torch.is_grad_enabled() and c_ % 16 == 0 and os.environ.get('PASTA_B200_C8_CHAIN', '1') != '0' and \
