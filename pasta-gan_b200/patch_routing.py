@@ -225,8 +225,14 @@ def _launch_warps(jobs, device):
     dev = torch.from_numpy(jobs.view(np.uint8)).to(device, non_blocking=False)
     max_pix = int((jobs['dst_h'].astype(np.int64) * jobs['dst_w']).max())
     _capi.require_device()
-    _capi.check(_capi.load().pg_warp_perspective_u8(dev.data_ptr(), int(jobs.shape[0]), max_pix, _capi.current_stream(device)), 'pg_warp_perspective_u8')
+    for first in range(0, int(jobs.shape[0]), _MAX_JOBS_PER_LAUNCH):       # one launch takes at most 65 535 jobs (gridDim.y)
+        n = min(_MAX_JOBS_PER_LAUNCH, int(jobs.shape[0]) - first)
+        _capi.check(_capi.load().pg_warp_perspective_u8(dev.data_ptr() + first * WARP_JOB_DTYPE.itemsize, n, max_pix, _capi.current_stream(device)),
+                    'pg_warp_perspective_u8')
     return dev                                                             # keep alive until the caller synchronises or reuses the stream
+
+
+_MAX_JOBS_PER_LAUNCH = 65535
 
 
 def _jobs(n):

@@ -91,6 +91,23 @@ def test_host_fallback_parts():
 
 def test_warp_job_struct_is_128_bytes():
     assert ctypes.sizeof(_capi.WarpJob) == 128
+    # the numpy record the product builds its job tables with has the layout of the C struct (include/pasta_b200.h: pg_warp_job)
+    assert PR.WARP_JOB_DTYPE.itemsize == 128
+    for name, _ in _capi.WarpJob._fields_:
+        assert PR.WARP_JOB_DTYPE.fields[name][1] == getattr(_capi.WarpJob, name).offset, name
+
+
+def test_host_geometry_batched_equals_per_sample():
+    rng = np.random.default_rng(11)
+    kp = synthetic.synth_patch_routing_inputs(12, seed=2, drop_joints=False)['keypoints']
+    kp[:, :, 2] = np.where(rng.random((12, 18)) < 0.3, 0.0, kp[:, :, 2])       # many missing joints: fall-backs and invalid parts in every sample
+    for p in range(PR.NUM_PARTS):
+        quads, ok = PR.part_quadrilaterals(kp, p, 256)
+        for b in range(12):
+            q = PR.part_quadrilateral(kp[b], p, 256)
+            assert (q is not None) == bool(ok[b])
+            if q is not None:
+                assert np.array_equal(q, quads[b])
 
 
 def test_no_cpu_path():
