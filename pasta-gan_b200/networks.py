@@ -797,6 +797,8 @@ class SpadeNormBlock(OpsModule):
         conv, so it may be an fp16 tensor when the operator table keeps fp16 intermediates; ``out_k``: that conv's kernel size -- when the table's
         ``c8_ok`` agrees, the result (and ``actv`` in between) travel channel-blocked and are loaded by TMA."""
         fused = getattr(self.ops, 'spade_conv_norm', None)
+        if fused is not None and torch.is_grad_enabled() and (x.requires_grad or denorm_feats.requires_grad or self.conv_gamma.weight.requires_grad):
+            fused = None                                  # training: the fused epilogue has no autograd -- decide before conv_mlp runs, not after (it ran twice)
         if fused is not None:
             half = getattr(self.ops, 'half_intermediates', None)
             half = torch.float16 if (half is not None and half(x)) else None
