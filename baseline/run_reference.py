@@ -16,6 +16,8 @@ files that do not exist).
     --mode overlay_hook   the same after a pickle round trip through legacy.load_network_pkl with the persistence.import_hook recipe of
                      INTEGRATION.md §2 that re-routes the pickled modulated_conv2d to the one-launch kernel.
     --mode ops       per-op timings of the reference's CUDA plugins and cuDNN fp32 on the op-microbenchmark grid (BASELINE configs[4]).
+    --mode patch_routing   the reference's own data-loader patch routing on the host: UvitonDatasetFull.normalize (training/dataset.py:838-927, 56
+                     cv2.warpPerspective calls per sample) on the inputs in --io-in (.npz), outputs of the first samples written to --io-out.
 
 Parity (``--check``): outputs at batch 2 against tests/golden/generator_full.npz (written from this same reference on CPU).
 """
@@ -34,13 +36,15 @@ REF = os.environ.get('PASTA_REFERENCE_TREE', os.path.join(ROOT, 'baseline', '_re
 
 def parse():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--mode', required=True, choices=['cpu', 'gpu', 'overlay', 'overlay_hook', 'ops'])
+    ap.add_argument('--mode', required=True, choices=['cpu', 'gpu', 'overlay', 'overlay_hook', 'ops', 'patch_routing'])
     ap.add_argument('--profile', action='store_true', help='print the top CUDA kernels of one forward (torch.profiler) to stderr')
     ap.add_argument('--batch', type=int, default=1)
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=1)
     ap.add_argument('--check', action='store_true', help='also run batch 2 and compare with tests/golden/generator_full.npz')
     ap.add_argument('--threads', type=int, default=0)
+    ap.add_argument('--io-in', default='', help='patch_routing: .npz with upper_img / lower_img / upper_clothes_mask / lower_clothes_mask / keypoints')
+    ap.add_argument('--io-out', default='', help='patch_routing: where to write the reference outputs (.npz)')
     return ap.parse_args()
 
 
@@ -199,11 +203,72 @@ def run_ops(out):
     out['plugins'] = dict(upfirdn2d=upfirdn2d._plugin is not None, bias_act=bias_act._plugin is not None)
 
 
+NORM_NAMES = ('img', 'img_lower', 'denorm_upper_img', 'denorm_lower_img', 'M_invs', 'hand_masks', 'clothes_masks', 'clothes_masks_lower')
+
+
+def run_patch_routing(args, out):
+    """The unmodified reference methods on the host cores (what a DataLoader worker executes per sample, dataset.py:553-565): needs cv2.  The modules the
+    data-set file imports at its top and that this image lacks (skimage.draw, pycocotools.mask, matplotlib) are irrelevant to the three methods and are
+    satisfied by empty stand-ins; the methods run unbound on an object carrying the sample's ``keypoints`` (set by __getitem__ at dataset.py:744)."""
+    try:
+        import cv2
+    except ImportError as e:
+        out['unavailable'] = f'cv2 cannot be imported here ({e})'
+        return
+    import numpy as np
+    os.environ.setdefault('PYTHONDONTWRITEBYTECODE', '1')
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, REF)
+    for m in ('matplotlib', 'matplotlib.pyplot', 'skimage', 'skimage.draw', 'pycocotools', 'pycocotools.mask'):
+        sys.modules.setdefault(m, types.ModuleType(m))
+    sys.modules['matplotlib'].pyplot = sys.modules['matplotlib.pyplot']
+    sys.modules['skimage'].draw = sys.modules['skimage.draw']
+    if not hasattr(sys.modules['skimage.draw'], 'circle'):
+        sys.modules['skimage.draw'].circle = sys.modules['skimage.draw'].line_aa = None
+    sys.modules['pycocotools'].mask = sys.modules['pycocotools.mask']
+    import training.dataset as R_ds
+
+    class Sample:
+        valid_joints = R_ds.UvitonDatasetFull.valid_joints
+        get_crop = R_ds.UvitonDatasetFull.get_crop
+        normalize = R_ds.UvitonDatasetFull.normalize
+
+        def __init__(self, keypoints):
+            self.keypoints = keypoints
+
+    d = dict(np.load(args.io_in))
+    B = d['keypoints'].shape[0]
+    if args.threads:
+        cv2.setNumThreads(args.threads)
+    run = lambda b: Sample(d['keypoints'][b]).normalize(d['upper_img'][b], d['lower_img'][b], d['upper_clothes_mask'][b], d['lower_clothes_mask'][b], 2)
+    for i in range(args.warmup):
+        run(i % B)
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(args.steps):
+        for b in range(B):
+            res = run(b)
+            n += 1
+    dt = time.perf_counter() - t0
+    out.update(samples_s=n / dt, ms_per_sample=1e3 * dt / n, samples=n, batch=B, opencv=cv2.__version__, cv2_threads=cv2.getNumThreads(), cores=os.cpu_count() or 1)
+    if args.io_out:
+        keep = min(B, 4)
+        cols = {k: [] for k in NORM_NAMES}
+        for b in range(keep):
+            for k, v in zip(NORM_NAMES, run(b)):
+                cols[k].append(np.stack(v) if k == 'hand_masks' else np.asarray(v))
+        np.savez(args.io_out, **{k: np.stack(v) for k, v in cols.items()})
+
+
 def main():
     args = parse()
     out = dict(mode=args.mode, ref_tree=os.path.relpath(REF, ROOT))
     if not os.path.isdir(os.path.join(REF, 'torch_utils')):
         out['unavailable'] = f'{REF} is missing (it is copied from the reference checkout by __graft_entry__.build())'
+        print(json.dumps(out), flush=True)
+        return
+    if args.mode == 'patch_routing':
+        run_patch_routing(args, out)
         print(json.dumps(out), flush=True)
         return
     import torch

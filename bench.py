@@ -255,8 +255,10 @@ def time_cpu_oracle(steps, warmup, batch=1):
 
 def time_patch_routing(batch=16, reps=5):
     """the data loader's patch routing (training/dataset.py:838-927: 56 cv2.warpPerspective calls per sample) as two launches per batch
-    on the GPU, beside the oracle's restatement of the OpenCV arithmetic on one host core.  Wall clock around whole normalize() calls (host geometry +
-    job table upload + kernels + sync), uint8 images resident on the device."""
+    on the GPU, beside the UNMODIFIED reference normalize() with the real cv2 on the host cores (baseline/_ref; the oracle's numpy restatement on one core
+    only where cv2 or the tree is absent).  Wall clock around whole normalize() calls (host geometry + job table upload + kernels + sync), uint8 images
+    resident on the device.  The GPU result is compared byte for byte with what the reference wrote."""
+    import tempfile
     import numpy as np
     from pasta_gan_b200 import patch_routing as PR, synthetic
     d = synthetic.synth_patch_routing_inputs(batch, seed=3)
@@ -271,16 +273,48 @@ def time_patch_routing(batch=16, reps=5):
         torch.cuda.synchronize()
         ts.append(time.perf_counter() - t0)
     t_gpu = sorted(ts)[len(ts) // 2]
-    from oracle import warp_oracle as WO                                  # checker + CPU baseline only
+    res = dict(value=batch / t_gpu, unit='samples/s', ms_per_batch=1e3 * t_gpu, batch=batch, launches_per_batch=3,
+               what='PatchRouter.normalize: 28 rectifying warps + the back-warp composite per sample, uint8, OpenCV fixed-point bilinear')
+    with tempfile.TemporaryDirectory(prefix='pasta_pr_') as tmp:
+        np.savez(os.path.join(tmp, 'in.npz'), **d)
+        r = run_harness('patch_routing', batch, 3, 2, timeout=180, extra_args=['--io-in', os.path.join(tmp, 'in.npz'), '--io-out', os.path.join(tmp, 'out.npz')])
+        if 'unavailable' not in r:
+            ref = np.load(os.path.join(tmp, 'out.npz'))
+            keep = ref['img'].shape[0]
+            names = ('img', 'img_lower', 'denorm_upper_img', 'denorm_lower_img', 'M_invs', 'hand_masks', 'clothes_masks', 'clothes_masks_lower')
+            exact = all(np.array_equal(out[i][:keep].cpu().numpy() if torch.is_tensor(out[i]) else np.asarray(out[i][:keep]), ref[names[i]].astype(np.float64) if i == 4 else ref[names[i]])
+                        for i in range(8))
+            res.update(bit_exact_vs_reference=bool(exact),
+                       cpu_baseline=dict(value=r['samples_s'], unit='samples/s', cores=r['cv2_threads'], kind='reference',
+                                         sample=f"{r['samples']} samples: UNMODIFIED reference UvitonDatasetFull.normalize (training/dataset.py:838-927) with cv2 {r['opencv']}, "
+                                                f"{r['cv2_threads']} cv2 threads of {r['cores']} cores (baseline/_ref via baseline/run_reference.py --mode patch_routing)"))
+            return res
+    from oracle import warp_oracle as WO                                  # checker + CPU baseline only (no cv2 / no reference tree on this box)
     t0 = time.perf_counter()
     ncpu = 2
     for b in range(ncpu):
         ref = WO.normalize(d['upper_img'][b], d['lower_img'][b], d['upper_clothes_mask'][b], d['lower_clothes_mask'][b], d['keypoints'][b], 2)
     t_cpu = (time.perf_counter() - t0) / ncpu
     exact = all(np.array_equal(out[i][ncpu - 1].cpu().numpy(), ref[i]) for i in (0, 1, 2, 3, 6, 7))
-    return dict(value=batch / t_gpu, unit='samples/s', ms_per_batch=1e3 * t_gpu, batch=batch, launches_per_batch=3, bit_exact_vs_oracle=bool(exact),
-                cpu_baseline=dict(value=1.0 / t_cpu, unit='samples/s', cores=1, kind='port', sample=f'{ncpu} samples, numpy restatement of cv2.warpPerspective (cv2 is not in this image: parity unpinned)'),
-                what='PatchRouter.normalize: 28 rectifying warps + the back-warp composite per sample, uint8, OpenCV fixed-point bilinear')
+    res.update(bit_exact_vs_oracle=bool(exact), reference_unavailable=r['unavailable'],
+               cpu_baseline=dict(value=1.0 / t_cpu, unit='samples/s', cores=1, kind='port',
+                                 sample=f'{ncpu} samples, numpy restatement of cv2.warpPerspective (oracle/warp_oracle.py, pinned to OpenCV 4.13.0 by tests/golden/warp.npz)'))
+    return res
+
+
+WORKLOADS = {
+    'gen256': 'GeneratorFull 256x192 (256x256 padded) full-body try-on inference, batch 16 per GPU (BASELINE configs[1])',
+    'gen512': 'Generator_512 512x320 (512x512 padded) try-on inference, batch 16 per GPU (BASELINE configs[2]; the only 512-px generator in the reference tree)',
+}
+
+
+def workload_config(args, world):
+    """The `config` object of the JSON line: names the workload, identical in both arms (the reference arm runs a bounded sample of it, see its
+    `cpu_baseline.sample`); what is specific to how an arm executes it is in the line's `arm` object."""
+    return {'workload': WORKLOADS[args.workload], 'batch_per_gpu': args.batch, 'global_batch': world * args.batch,
+            'parallelism': f'replicas x{world} (batch-sharded, no collective)',
+            'l2': 'no explicit flush: one step streams > 10 GB of activations through the operators (L2 = 126 MB)',
+            'weights': 'procedural (name-keyed, pasta-gan_b200/synthetic.py)', 'noise_mode': 'const'}
 
 
 def run_reference(args, world, rank):
@@ -291,9 +325,11 @@ def run_reference(args, world, rank):
         'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'GeneratorFull 256x192 (256x256 padded) inference on the host cores: ' +
-                               ('the unmodified reference (impl=ref ops)' if r['kind'] == 'reference' else 'CPU oracle port of impl=ref') + '; each step = 1 image',
-                   'batch_per_step': 1, 'l2': 'n/a (CPU)'},
+        'config': workload_config(args, max(1, args.gpus)),
+        'arm': {'what': ('the unmodified reference (impl=ref ops)' if r['kind'] == 'reference' else 'CPU oracle port of impl=ref') + ' on the host cores of rank 0',
+                'sample': 'each step = ONE image of the workload\'s batch (batch 1 is the CPU path\'s fastest shape per image: the reference\'s grouped-conv '
+                          'form makes batch 2 about 5x slower per image, SURVEY 6); value = images / time',
+                'batch_per_step': 1, 'l2': 'n/a (CPU)'},
         'cpu_baseline': {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
         'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -359,11 +395,9 @@ def run_b200(args, world, rank, local):
     if args.workload == 'gen512':
         G = N.build_generator_512().eval().requires_grad_(False)
         inp = procedural.synth_inputs_512(args.batch, seed=4321 + 100 * rank, device=dev)
-        wl = 'Generator_512 512x320 (512x512 padded) try-on inference, batch 16 per GPU (BASELINE configs[2]; the only 512-px generator in the reference tree)'
     else:
         G = N.build_generator_full().eval().requires_grad_(False)
         inp = procedural.synth_inputs(args.batch, seed=1234 + 100 * rank, device=dev)
-        wl = 'GeneratorFull 256x192 (256x256 padded) full-body try-on inference, batch 16 per GPU (BASELINE configs[1])'
     procedural.fill_(G)
     sess = TryOnSession(G, inp, dev, use_graph=not args.no_graph, warmup=max(3, args.warmup))
     sess.synchronize()
@@ -500,11 +534,9 @@ def run_b200(args, world, rank, local):
         'metric': METRIC if args.workload == 'gen256' else METRIC.replace('256x192 padded to 256x256', '512x320 padded to 512x512'), 'value': imgs / t_dev, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * t_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': DTYPE, 'data': 'synthetic',
-        'config': {'workload': wl,
-                   'batch_per_gpu': args.batch, 'global_batch': world * args.batch, 'parallelism': f'replicas x{world} (batch-sharded, no collective)',
-                   'cuda_graph': not args.no_graph, 'e2e_pipeline': 'H2D / compute / D2H on three streams, 2 buffer sets',
-                   'l2': f'no explicit flush: one step streams ~{act_bytes / 1e9:.1f} GB of activations through the operators (> 126 MB L2)',
-                   'weights': 'procedural (name-keyed, pasta-gan_b200/synthetic.py)', 'noise_mode': 'const'},
+        'config': workload_config(args, world),
+        'arm': {'cuda_graph': not args.no_graph, 'e2e_pipeline': 'H2D / compute / D2H on three streams, 2 buffer sets',
+                'activation_bytes_per_step': act_bytes, 'l2': f'one step streams ~{act_bytes / 1e9:.1f} GB of activations through the operators (> 126 MB L2)'},
         'e2e': {'value': imgs / t_e2e, 'unit': UNIT, 'ms_per_step': 1e3 * t_e2e / args.steps,
                 'h2d_bytes_per_step': io_bytes['h2d'], 'd2h_bytes_per_step': io_bytes['d2h']},
         'e2e_u8': {'value': imgs / t_u8, 'unit': UNIT, 'ms_per_step': 1e3 * t_u8 / args.steps, 'h2d_bytes_per_step': io_bytes['h2d_u8'],

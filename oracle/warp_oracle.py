@@ -5,15 +5,17 @@ Restates what the reference's data loader computes in ``UvitonDatasetFull*.norma
 ``cv2.warpPerspective(..., borderMode=BORDER_REPLICATE)``, and warped back with ``BORDER_CONSTANT`` to composite the
 "denormalised" garment images and the hand masks.
 
-Parity status: **UNPINNED**.  The arithmetic lives in a third-party dependency that is absent from the reference tree and
-from this image: ``opencv-python`` (the reference pins no version: ``Dockerfile:14`` / ``README.md:15`` say
-``pip install opencv-python``; the functions restated here are unchanged across the 4.x series).  The reference ships no
-golden vectors for the path, and ``cv2`` cannot be imported here to generate any.  What follows restates OpenCV's published
-algorithm (modules/imgproc/src/imgwarp.cpp: ``getPerspectiveTransform``, ``warpPerspective`` / ``WarpPerspectiveInvoker``,
-``remapBilinear`` with the fixed-point ``BilinearTab_i`` of ``initInterTab2D``; modules/core/src/lapack.cpp / matrix_decomp.cpp:
-``invert`` for 3 x 3, ``LUImpl``) and anchors on the reference's own call sites.  The unit tests pin the restatement to
-hand-derivable properties only: identity / integer-translation warps are exact copies, the interpolation table sums to 2^15,
-exact bilinear values at 1/32-pixel offsets, both border modes, and ``getPerspectiveTransform`` mapping its four points.
+Parity status: **PINNED** to OpenCV 4.13.0 and to the unmodified reference methods.  The arithmetic lives in a third-party dependency that is
+absent from the reference tree: ``opencv-python`` (the reference pins no version: ``Dockerfile:14`` / ``README.md:15`` say
+``pip install opencv-python``).  ``tests/golden/gen_warp_golden.py`` runs, in the authoring container, (a) ``cv2.getPerspectiveTransform`` /
+``cv2.warpPerspective`` directly and (b) the reference's own ``UvitonDatasetFull.normalize`` / ``get_crop`` (imported unmodified from
+/root/reference) on seeded inputs and commits the results as ``tests/golden/warp.npz``; ``tests/test_patch_routing.py`` holds this restatement
+bit-equal to those vectors (matrices as doubles, images as bytes) and, where ``cv2`` is importable, to fresh live calls.
+What is restated is OpenCV's published algorithm (modules/imgproc/src/imgwarp.cpp: ``getPerspectiveTransform``, ``warpPerspective`` /
+``WarpPerspectiveInvoker``, ``remapBilinear`` with the fixed-point ``BilinearTab_i`` of ``initInterTab2D``; modules/core/src/lapack.cpp /
+matrix_decomp.cpp: ``invert`` for 3 x 3, ``LUImpl``), anchored on the reference's own call sites.  Hand-derivable properties are tested as well:
+identity / integer-translation warps are exact copies, the interpolation table sums to 2^15, exact bilinear values at 1/32-pixel offsets,
+both border modes, and ``getPerspectiveTransform`` mapping its four points.
 
 Details that matter for bit-level agreement with OpenCV and are reproduced here:
   * ``warpPerspective`` inverts the matrix first (closed-form 3 x 3 adjugate in double), then walks the destination in blocks

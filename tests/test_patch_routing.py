@@ -1,9 +1,12 @@
 """Patch-routing perspective warp (reference training/dataset.py:751-927).
 
-CPU: the oracle's restatement of OpenCV's fixed-point warp against hand-derivable properties (cv2 is not in this image: parity is UNPINNED, see
-oracle/warp_oracle.py), and the product's batched host geometry against the oracle's per-call version.
-GPU: the two kernels, through the C ABI, bit-exact against the oracle."""
+CPU: the oracle's restatement of OpenCV's fixed-point warp against golden vectors made by the real ``cv2`` and by the UNMODIFIED reference
+``normalize`` / ``get_crop`` (tests/golden/warp.npz, written by tests/golden/gen_warp_golden.py with OpenCV 4.13.0), against ``cv2`` itself where it can be
+imported, and against hand-derivable properties; the product's batched host geometry against the oracle's per-call version and the goldens.
+GPU: the two kernels, through the C ABI, bit-exact against the goldens and against the oracle."""
 import ctypes
+import json
+import os
 
 import numpy as np
 import pytest
@@ -13,8 +16,84 @@ from oracle import warp_oracle as WO
 from pasta_gan_b200 import _capi, patch_routing as PR, synthetic
 
 
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'warp.npz')
+NORM_NAMES = ('img', 'img_lower', 'denorm_upper_img', 'denorm_lower_img', 'M_invs', 'hand_masks', 'clothes_masks', 'clothes_masks_lower')
+BORDERS = (('constant', WO.BORDER_CONSTANT), ('replicate', WO.BORDER_REPLICATE))
+
+
+@pytest.fixture(scope='module')
+def golden():
+    g = dict(np.load(GOLDEN))
+    g['meta'] = json.loads(bytes(g['meta']).decode())
+    return g
+
+
 def _rand_img(rng, h, w, c=3):
     return rng.integers(0, 256, (h, w, c), dtype=np.uint8)
+
+
+# ------------------------------------------------------------------------------------------------------------------ oracle vs OpenCV goldens (CPU)
+
+def test_oracle_pinned_to_opencv_raw_warps(golden):
+    """getPerspectiveTransform (bit-equal doubles) and warpPerspective (bit-equal bytes, both borders, 1 / 3 / 4 channels) as cv2 computed them."""
+    assert golden['meta']['opencv'].startswith('4.')
+    for t in range(golden['meta']['raw_trials']):
+        src, dst, img = golden[f'raw_{t}_src'], golden[f'raw_{t}_dst'], golden[f'raw_{t}_img']
+        M = WO.get_perspective_transform(src, dst)
+        assert np.array_equal(M, golden[f'raw_{t}_M']), t
+        assert np.array_equal(WO.get_perspective_transform(dst, src), golden[f'raw_{t}_Minv']), t
+        for name, border in BORDERS:
+            want = golden[f'raw_{t}_{name}']
+            got = WO.warp_perspective_u8(img, M, (want.shape[1], want.shape[0]), border).reshape(want.shape)
+            assert np.array_equal(got, want), (t, name, int((got != want).sum()))
+
+
+def test_oracle_pinned_to_reference_normalize(golden):
+    """The oracle's normalize / get_crop against the outputs of the unmodified reference methods (training/dataset.py:751-927) on the same inputs."""
+    kp = golden['norm_keypoints']
+    B = kp.shape[0]
+    valid = golden['norm_out_valid']
+    assert valid.any() and not valid.all()
+    wh = np.expand_dims(np.array([64, 64]), 0)
+    for b in range(B):
+        got = WO.normalize(golden['norm_upper_img'][b], golden['norm_lower_img'][b], golden['norm_upper_clothes_mask'][b],
+                           golden['norm_lower_clothes_mask'][b], kp[b], 2)
+        for n, v in zip(NORM_NAMES, got):
+            v = np.stack(v) if n == 'hand_masks' else np.asarray(v)
+            want = golden['norm_out_' + n][b]
+            assert v.shape == want.shape and np.array_equal(v, want), (b, n)
+        for p in range(10):
+            m, _ = WO.get_crop(kp[b], list(WO.BPARTS[p]), wh, 256, 256, 0.5)
+            assert (m is not None) == bool(valid[b, p])
+            if m is not None:
+                assert np.array_equal(m, golden['norm_out_M'][b, p])
+
+
+def test_golden_inputs_are_the_synthetic_set(golden):
+    """The fixture's inputs are what synthetic.synth_patch_routing_inputs(4, seed=9) makes today (so the GPU tests may regenerate them)."""
+    d = synthetic.synth_patch_routing_inputs(4, seed=9)
+    for k, v in d.items():
+        assert np.array_equal(v, golden['norm_' + k]), k
+
+
+def test_oracle_against_live_cv2():
+    """Where cv2 can be imported (the authoring container; not required on the GPU box), fresh random cases beyond the committed ones."""
+    cv2 = pytest.importorskip('cv2')
+    rng = np.random.default_rng(99)
+    modes = {WO.BORDER_CONSTANT: cv2.BORDER_CONSTANT, WO.BORDER_REPLICATE: cv2.BORDER_REPLICATE}
+    for trial in range(16):
+        H, W, C = [(256, 256, 3), (64, 64, 3), (77, 201, 1), (130, 33, 4)][trial % 4]
+        h, w = [(64, 64), (256, 256), (90, 50), (70, 200)][trial % 4]
+        img = _rand_img(rng, H, W, C)
+        src = np.float32([[0.1 * W, 0.1 * H], [0.05 * W, 0.9 * H], [0.95 * W, 0.85 * H], [0.9 * W, 0.05 * H]] + rng.normal(0, 0.1 * min(H, W), (4, 2)))
+        src += np.float32(rng.uniform(-0.5, 0.5, 2) * (W, H)) * (trial % 2)
+        dst = np.float32([[0, 0], [0, h], [w, h], [w, 0]])
+        M = cv2.getPerspectiveTransform(src, dst)
+        assert np.array_equal(WO.get_perspective_transform(src, dst), M)
+        for border, mode in modes.items():
+            want = cv2.warpPerspective(img, M, (w, h), borderMode=mode).reshape(h, w, C)
+            got = WO.warp_perspective_u8(img, M, (w, h), border).reshape(h, w, C)
+            assert np.array_equal(got, want), (trial, border, int((got != want).sum()))
 
 
 # ------------------------------------------------------------------------------------------------------------------ oracle properties (CPU)
@@ -81,6 +160,14 @@ def test_host_geometry_matches_oracle():
                 assert not M[b, p].any() and not M_inv[b, p].any()
 
 
+def test_host_geometry_matches_reference_golden(golden):
+    """The product's batched crop geometry against the matrices the unmodified reference get_crop returned (cv2.getPerspectiveTransform inside)."""
+    M, M_inv, valid = PR.crop_transforms(golden['norm_keypoints'], 64, 64, 256)
+    assert np.array_equal(valid, golden['norm_out_valid'])
+    assert np.array_equal(M, golden['norm_out_M'])
+    assert np.array_equal(M_inv, golden['norm_out_M_invs'].astype(np.float64))
+
+
 def test_host_fallback_parts():
     kp = synthetic.synth_patch_routing_inputs(1, drop_joints=False)['keypoints'][0]
     for joint, part, expect in (('lknee', 6, True), ('cnose', 1, True), ('lelbow', 2, False), ('lhip', 6, False)):
@@ -133,6 +220,30 @@ def test_warp_perspective_bit_exact(border):
         want = WO.warp_perspective_u8(img, M, (w, h), border)
         got = PR.warp_perspective(torch.from_numpy(img).cuda(), M, (w, h), border).cpu().numpy()
         assert np.array_equal(got, want), (trial, int((got != want).sum()))
+
+
+@pytest.mark.gpu
+def test_warp_perspective_matches_opencv_golden(golden):
+    """The warp kernel against bytes written by cv2.warpPerspective itself (no oracle in between)."""
+    for t in range(golden['meta']['raw_trials']):
+        img, M = golden[f'raw_{t}_img'], golden[f'raw_{t}_M']
+        for name, border in BORDERS:
+            want = golden[f'raw_{t}_{name}']
+            got = PR.warp_perspective(torch.from_numpy(img).cuda(), M, (want.shape[1], want.shape[0]), border).cpu().numpy().reshape(want.shape)
+            assert np.array_equal(got, want), (t, name, int((got != want).sum()))
+
+
+@pytest.mark.gpu
+def test_normalize_matches_reference_golden(golden):
+    """PatchRouter.normalize against the outputs of the unmodified reference normalize (56 cv2.warpPerspective calls per sample) on the same inputs."""
+    B = golden['norm_keypoints'].shape[0]
+    dev = {k: torch.from_numpy(golden['norm_' + k]).cuda() for k in ('upper_img', 'lower_img', 'upper_clothes_mask', 'lower_clothes_mask')}
+    got = PR.PatchRouter().normalize(dev['upper_img'], dev['lower_img'], dev['upper_clothes_mask'], dev['lower_clothes_mask'], golden['norm_keypoints'], 2)
+    for i in (0, 1, 2, 3, 6, 7):
+        assert np.array_equal(got[i].cpu().numpy(), golden['norm_out_' + NORM_NAMES[i]]), NORM_NAMES[i]
+    assert np.array_equal(got[4], golden['norm_out_M_invs'].astype(np.float64))
+    assert np.array_equal(got[5].cpu().numpy(), golden['norm_out_hand_masks'])
+    assert int((golden['norm_out_denorm_upper_img'] > 0).sum()) > 1000
 
 
 @pytest.mark.gpu
