@@ -316,6 +316,15 @@ typedef struct pg_warp_job {
 int pg_warp_perspective_u8(const pg_warp_job* jobs_device, int32_t njobs, int32_t max_dst_pixels, void* stream);
 int pg_patch_denorm_u8(const void* patches, const void* masks, const double* m, const void* valid, void* denorm, void* part_masks,
                        int32_t B, int32_t P, int32_t h, int32_t w, int32_t H, int32_t W, void* stream);
+/*   pg_patch_crop_transforms: HOST function (no kernel, all pointers are host memory) — the crop geometry of the whole batch: for every sample b and
+ *     body part p (the ten parts of dataset.py:847-857) what get_crop (dataset.py:751-836) returns,
+ *       M[b][p]     = cv2.getPerspectiveTransform(part quadrilateral, patch corners)     M_inv[b][p] = the transform back,
+ *     and the two matrices cv2.warpPerspective derives from them, to_patch = inv(M) and to_image = inv(M_inv) (either may be NULL), all row-major
+ *     doubles [B][10][9]; valid[b][p] = 0 (and zero matrices) where the part's joints are not confident (>= 0.1) even after the reference's fall-backs.
+ *     keypoints [B][18][3] doubles (x, y, confidence) in the un-padded 192-wide frame, OpenPose-18 order of dataset.py:859-861; patch h x w;
+ *     o_h = image height; ar = the box aspect (0.5 in the reference).  Bit-equal to OpenCV's results (same operations, same order, no FMA). */
+int pg_patch_crop_transforms(const double* keypoints, int32_t B, int32_t h, int32_t w, int32_t o_h, double ar,
+                             double* M, double* M_inv, double* to_patch, double* to_image, uint8_t* valid);
 
 /* ---------------------------------------------------------------------------------------------
  * torgb_skip — the ToRGB skip path of a synthesis block in one streaming kernel (north_star kernel 3):

@@ -58,6 +58,7 @@ SIGNATURES = {
                              [c_i32, c_f32, c_i32, c_f32, c_f32, c_f32, c_i32, c_ptr],
     'pg_warp_perspective_u8': [c_ptr, c_i32, c_i32, c_ptr],
     'pg_patch_denorm_u8': [c_ptr] * 6 + [c_i32] * 6 + [c_ptr],
+    'pg_patch_crop_transforms': [c_ptr, c_i32, c_i32, c_i32, c_i32, ctypes.c_double] + [c_ptr] * 5,
 }
 
 

@@ -21,7 +21,8 @@ STAMP = os.path.join(LIBDIR, 'libpasta_b200.stamp')
 INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-              '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr', '-I', INCLUDE]
+              '-Xcompiler', '-fPIC', '-Xcompiler', '-ffp-contract=off',      # host code (pg_patch_geometry.cu) must round like OpenCV / numpy: no FMA contraction
+              '--expt-relaxed-constexpr', '-I', INCLUDE]
 
 
 def sources():

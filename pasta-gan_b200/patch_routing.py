@@ -2,8 +2,9 @@
 
 The reference rectifies ten body-part quadrilaterals of the garment images into 64 x 64 patches and warps them back, one
 ``cv2.warpPerspective`` call at a time on the CPU (``UvitonDatasetFull*.normalize``, training/dataset.py:838-927; crop geometry
-``get_crop``, :751-836).  Here the geometry (a handful of float32 operations and 8 x 8 linear systems per part) stays on the host,
-vectorised over the batch, and every pixel operation runs in two kernel launches per batch (csrc/pg_patch_route.cu):
+``get_crop``, :751-836).  Here the geometry (a handful of float32 operations and 8 x 8 linear systems per part) stays on the host --
+one native call per batch (``pg_patch_crop_transforms``, csrc/pg_patch_geometry.cu; the numpy functions below are the same arithmetic, kept as the
+readable statement the tests compare it with) -- and every pixel operation runs in two kernel launches per batch (csrc/pg_patch_route.cu):
 ``pg_warp_perspective_u8`` (all rectifying warps of all samples, written straight into the channel-concatenated tensors) and
 ``pg_patch_denorm_u8`` (the back-warp + mask == 255 composite).  The arithmetic is OpenCV's fixed-point bilinear path, restated
 bit for bit; there is no CPU fallback.
@@ -209,6 +210,21 @@ def crop_transforms(keypoints, h, w, o_h, ar=0.5):
     return M, M_inv, valid
 
 
+def crop_transforms_native(keypoints, h, w, o_h, ar=0.5):
+    """``crop_transforms`` plus the two inversions ``cv2.warpPerspective`` applies, in one native host call (``pg_patch_crop_transforms``):
+    keypoints [B, 18, 3] -> (M, M_inv, valid, to_patch = inv(M), to_image = inv(M_inv)); matrices [B,10,3,3] float64, bit-equal to the numpy path."""
+    kp = np.ascontiguousarray(keypoints, np.float64)
+    if kp.ndim != 3 or kp.shape[1:] != (18, 3):
+        raise _capi.PastaB200Error(f'keypoints: expected [B, 18, 3], got {kp.shape}')
+    B = kp.shape[0]
+    out = np.empty((4, B, NUM_PARTS, 3, 3), np.float64)
+    valid = np.empty((B, NUM_PARTS), np.uint8)
+    ptr = lambda a: a.ctypes.data
+    _capi.check(_capi.load().pg_patch_crop_transforms(ptr(kp), B, int(h), int(w), int(o_h), float(ar), ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(out[3]),
+                                                      ptr(valid)), 'pg_patch_crop_transforms')
+    return out[0], out[1], valid.astype(bool), out[2], out[3]
+
+
 WARP_JOB_DTYPE = np.dtype([('m', '<f8', (9,)), ('src', '<u8'), ('dst', '<u8'), ('src_h', '<i4'), ('src_w', '<i4'), ('src_row_stride', '<i4'),
                            ('src_pix_stride', '<i4'), ('dst_h', '<i4'), ('dst_w', '<i4'), ('dst_row_stride', '<i4'), ('dst_pix_stride', '<i4'),
                            ('channels', '<i4'), ('border', '<i4')])          # pg_warp_job of include/pasta_b200.h (128 bytes)
@@ -219,17 +235,28 @@ def _check_u8(t, name):
         raise _capi.PastaB200Error(f'{name}: expected a contiguous uint8 CUDA tensor (the patch-routing path has no CPU implementation)')
 
 
-def _launch_warps(jobs, device):
-    """jobs: structured array of WARP_JOB_DTYPE records (host).  One H2D copy of the table + one launch."""
+def _upload(arrays, device):
+    """Host arrays -> ONE device byte buffer (one H2D copy); returns (buffer, device address of each array).  Every array starts 16-byte aligned."""
+    offs, total = [], 0
+    for a in arrays:
+        offs.append(total)
+        total += (a.nbytes + 15) // 16 * 16
+    host = np.empty(max(total, 16), np.uint8)
+    for a, o in zip(arrays, offs):
+        host[o:o + a.nbytes] = np.ascontiguousarray(a).reshape(-1).view(np.uint8)
+    buf = torch.from_numpy(host).to(device, non_blocking=False)
+    return buf, [buf.data_ptr() + o for o in offs]
+
+
+def _launch_warps(jobs, jobs_dev, device):
+    """jobs: structured array of WARP_JOB_DTYPE records (host), jobs_dev: the device address of its copy.  One launch per 65 535 jobs (gridDim.y)."""
     assert jobs.dtype == WARP_JOB_DTYPE and jobs.dtype.itemsize == 128
-    dev = torch.from_numpy(jobs.view(np.uint8)).to(device, non_blocking=False)
     max_pix = int((jobs['dst_h'].astype(np.int64) * jobs['dst_w']).max())
     _capi.require_device()
-    for first in range(0, int(jobs.shape[0]), _MAX_JOBS_PER_LAUNCH):       # one launch takes at most 65 535 jobs (gridDim.y)
+    for first in range(0, int(jobs.shape[0]), _MAX_JOBS_PER_LAUNCH):
         n = min(_MAX_JOBS_PER_LAUNCH, int(jobs.shape[0]) - first)
-        _capi.check(_capi.load().pg_warp_perspective_u8(dev.data_ptr() + first * WARP_JOB_DTYPE.itemsize, n, max_pix, _capi.current_stream(device)),
+        _capi.check(_capi.load().pg_warp_perspective_u8(jobs_dev + first * WARP_JOB_DTYPE.itemsize, n, max_pix, _capi.current_stream(device)),
                     'pg_warp_perspective_u8')
-    return dev                                                             # keep alive until the caller synchronises or reuses the stream
 
 
 _MAX_JOBS_PER_LAUNCH = 65535
@@ -237,6 +264,30 @@ _MAX_JOBS_PER_LAUNCH = 65535
 
 def _jobs(n):
     return np.zeros(n, WARP_JOB_DTYPE)
+
+
+def _routing_jobs(valid, to_patch, H, W, h, w, groups):
+    """Job table of the rectifying warps of a batch.  groups: (source base address, destination base address, destination channels, first part) per
+    (image, patch tensor) pair; sources are [B, H, W, 3], destinations [B, h, w, channels] with part p at channels 3 (p - first) ..  One record per
+    valid (sample, part >= first) and group, built in one pass over all groups."""
+    bi, pi = np.nonzero(valid)
+    sels = [np.flatnonzero(pi >= first) for _, _, _, first in groups]
+    n = sum(int(x.shape[0]) for x in sels)
+    j = np.zeros(n, WARP_JOB_DTYPE)
+    if n == 0:
+        return j
+    idx = np.concatenate(sels)
+    b_, p_ = bi[idx].astype(np.uint64), pi[idx]
+    per = lambda vals, dt: np.repeat(np.asarray(vals, dt), [int(x.shape[0]) for x in sels])
+    src0, dst0 = per([g[0] for g in groups], np.uint64), per([g[1] for g in groups], np.uint64)
+    nch, first = per([g[2] for g in groups], np.int64), per([g[3] for g in groups], np.int64)
+    j['m'] = to_patch[bi[idx], p_].reshape(-1, 9)
+    j['src'] = src0 + b_ * np.uint64(H * W * 3)
+    j['dst'] = dst0 + b_ * (np.uint64(h * w) * nch.astype(np.uint64)) + (3 * (p_ - first)).astype(np.uint64)
+    j['src_h'], j['src_w'], j['src_row_stride'], j['src_pix_stride'] = H, W, W * 3, 3
+    j['dst_h'], j['dst_w'], j['dst_row_stride'], j['dst_pix_stride'] = h, w, w * nch, nch
+    j['channels'], j['border'] = 3, BORDER_REPLICATE
+    return j
 
 
 def warp_perspective(src, M, dsize, border_mode=BORDER_CONSTANT):
@@ -257,8 +308,9 @@ def warp_perspective(src, M, dsize, border_mode=BORDER_CONSTANT):
     j['src_h'], j['src_w'], j['src_row_stride'], j['src_pix_stride'] = H, W, W * C, C
     j['dst_h'], j['dst_w'], j['dst_row_stride'], j['dst_pix_stride'] = h, w, w * C, C
     j['channels'], j['border'] = C, int(border_mode)
-    keep = _launch_warps(j, img.device)
-    del keep
+    keep, (jobs_dev,) = _upload([j], img.device)
+    _launch_warps(j, jobs_dev, img.device)
+    del keep                                                               # stream-ordered free: the launch above is already queued on this stream
     return out[..., 0] if squeeze else out
 
 
@@ -281,43 +333,30 @@ class PatchRouter:
         B, H, W, _ = upper_img.shape
         h, w = H // 2 ** box_factor, W // 2 ** box_factor
         dev = upper_img.device
-        M, M_inv, valid = crop_transforms(keypoints, h, w, H, self.ar)
-        to_patch = invert3x3(M)                                            # cv2.warpPerspective(img, M, ...) walks the patch and samples img at inv(M)
-        to_image = invert3x3(M_inv)                                        # ... and the back-warp samples the patch at inv(M_inv)
+        # get_crop for every (sample, part); cv2.warpPerspective(img, M, ...) walks the patch and samples img at to_patch = inv(M), the back-warp
+        # samples the patch at to_image = inv(M_inv)
+        M, M_inv, valid, to_patch, to_image = crop_transforms_native(keypoints, h, w, H, self.ar)
         P, PL = NUM_PARTS, NUM_PARTS - FIRST_LOWER_PART
-        img = torch.zeros((B, h, w, 3 * P), dtype=torch.uint8, device=dev)
-        masks = torch.zeros((B, h, w, 3 * P), dtype=torch.uint8, device=dev)
-        img_lower = torch.zeros((B, h, w, 3 * PL), dtype=torch.uint8, device=dev)
-        masks_lower = torch.zeros((B, h, w, 3 * PL), dtype=torch.uint8, device=dev)
+        patch_buf = torch.zeros((B * h * w * 6 * (P + PL),), dtype=torch.uint8, device=dev)      # the four patch tensors in one allocation / one fill
+        cut = np.cumsum([0, 3 * P, 3 * P, 3 * PL, 3 * PL]) * (B * h * w)
+        img, masks, img_lower, masks_lower = (patch_buf[cut[i]:cut[i + 1]].view(B, h, w, -1) for i in range(4))
         # one record per cv2.warpPerspective call of the reference: (upper image, upper mask) for every valid part, plus (lower image, lower mask) for the legs
-        src_bytes = H * W * 3
-        bi, pi = np.nonzero(valid)
-        tables = []
-        for src, dst, nch, first in ((upper_img, img, 3 * P, 0), (upper_clothes_mask, masks, 3 * P, 0),
-                                     (lower_img, img_lower, 3 * PL, FIRST_LOWER_PART), (lower_clothes_mask, masks_lower, 3 * PL, FIRST_LOWER_PART)):
-            sel = pi >= first
-            b_, p_ = bi[sel], pi[sel]
-            j = _jobs(b_.shape[0])
-            j['m'] = to_patch[b_, p_].reshape(-1, 9)
-            j['src'] = src.data_ptr() + b_.astype(np.uint64) * np.uint64(src_bytes)
-            j['dst'] = dst.data_ptr() + b_.astype(np.uint64) * np.uint64(h * w * nch) + (3 * (p_ - first)).astype(np.uint64)
-            j['src_h'], j['src_w'], j['src_row_stride'], j['src_pix_stride'] = H, W, W * 3, 3
-            j['dst_h'], j['dst_w'], j['dst_row_stride'], j['dst_pix_stride'] = h, w, w * nch, nch
-            j['channels'], j['border'] = 3, BORDER_REPLICATE
-            tables.append(j)
-        jobs = np.concatenate(tables)
-        keep = _launch_warps(jobs, dev) if jobs.shape[0] else None
+        jobs = _routing_jobs(valid, to_patch, H, W, h, w,
+                             ((upper_img.data_ptr(), img.data_ptr(), 3 * P, 0), (upper_clothes_mask.data_ptr(), masks.data_ptr(), 3 * P, 0),
+                              (lower_img.data_ptr(), img_lower.data_ptr(), 3 * PL, FIRST_LOWER_PART),
+                              (lower_clothes_mask.data_ptr(), masks_lower.data_ptr(), 3 * PL, FIRST_LOWER_PART)))
+        # the job table, the back-warp matrices and the validity flags of both garments travel in one H2D copy
+        v8 = valid.astype(np.uint8)
+        keep, (jobs_dev, m_up, m_lo, v_up, v_lo) = _upload([jobs, to_image, to_image[:, FIRST_LOWER_PART:], v8, v8[:, FIRST_LOWER_PART:]], dev)
+        if jobs.shape[0]:
+            _launch_warps(jobs, jobs_dev, dev)
         lib, stream = _capi.load(), _capi.current_stream(dev)
         denorm_upper = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev)
         denorm_lower = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev)
         part_masks = torch.empty((B, P, H, W), dtype=torch.uint8, device=dev)
-        m_up = torch.from_numpy(np.ascontiguousarray(to_image.reshape(B, P, 9))).to(dev)
-        m_lo = torch.from_numpy(np.ascontiguousarray(to_image[:, FIRST_LOWER_PART:].reshape(B, PL, 9))).to(dev)
-        v_up = torch.from_numpy(valid.astype(np.uint8)).to(dev)
-        v_lo = torch.from_numpy(np.ascontiguousarray(valid[:, FIRST_LOWER_PART:]).astype(np.uint8)).to(dev)
-        _capi.check(lib.pg_patch_denorm_u8(img.data_ptr(), masks.data_ptr(), m_up.data_ptr(), v_up.data_ptr(), denorm_upper.data_ptr(),
+        _capi.check(lib.pg_patch_denorm_u8(img.data_ptr(), masks.data_ptr(), m_up, v_up, denorm_upper.data_ptr(),
                                            part_masks.data_ptr(), B, P, h, w, H, W, stream), 'pg_patch_denorm_u8')
-        _capi.check(lib.pg_patch_denorm_u8(img_lower.data_ptr(), masks_lower.data_ptr(), m_lo.data_ptr(), v_lo.data_ptr(), denorm_lower.data_ptr(),
+        _capi.check(lib.pg_patch_denorm_u8(img_lower.data_ptr(), masks_lower.data_ptr(), m_lo, v_lo, denorm_lower.data_ptr(),
                                            None, B, PL, h, w, H, W, stream), 'pg_patch_denorm_u8')
         del keep
         hand_masks = part_masks[:, 2:6].unsqueeze(-1)                      # the four arm parts (dataset.py:903-907)

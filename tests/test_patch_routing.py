@@ -168,6 +168,30 @@ def test_host_geometry_matches_reference_golden(golden):
     assert np.array_equal(M_inv, golden['norm_out_M_invs'].astype(np.float64))
 
 
+def test_native_geometry_bit_equal(golden):
+    """pg_patch_crop_transforms (host code of the C-ABI library) against the numpy statement of the same arithmetic, the oracle and the reference's
+    matrices: valid, fall-back and invalid parts, many random drop-outs, jittered and extreme keypoints."""
+    M, M_inv, valid, to_patch, to_image = PR.crop_transforms_native(golden['norm_keypoints'], 64, 64, 256)
+    assert np.array_equal(valid, golden['norm_out_valid']) and np.array_equal(M, golden['norm_out_M'])
+    assert np.array_equal(M_inv, golden['norm_out_M_invs'].astype(np.float64))
+    rng = np.random.default_rng(21)
+    for trial, (res, hw) in enumerate([(256, 64), (256, 64), (512, 128), (256, 32)]):
+        kp = synthetic.synth_patch_routing_inputs(24, seed=40 + trial, drop_joints=False)['keypoints']
+        kp[:, :, :2] *= res / 256.0
+        kp[:, :, :2] += rng.normal(0, 12 if trial else 0.0, kp[:, :, :2].shape)
+        kp[:, :, 2] = np.where(rng.random((24, 18)) < 0.25, rng.choice([0.0, 0.05, 0.0999]), kp[:, :, 2])
+        if trial == 1:
+            kp[0, :, :2] = 100.0                                             # every joint on one point: singular systems -> zero matrices, still 'valid'
+            kp[1, :, 2] = 0.1                                                # confidence exactly at the threshold counts as confident
+        want = PR.crop_transforms(kp, hw, hw, res)
+        got = PR.crop_transforms_native(kp, hw, hw, res)
+        assert np.array_equal(got[2], want[2])
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), trial
+        assert np.array_equal(got[3], PR.invert3x3(want[0])) and np.array_equal(got[4], PR.invert3x3(want[1])), trial
+    with pytest.raises(_capi.PastaB200Error):
+        PR.crop_transforms_native(np.zeros((2, 17, 3)), 64, 64, 256)
+
+
 def test_host_fallback_parts():
     kp = synthetic.synth_patch_routing_inputs(1, drop_joints=False)['keypoints'][0]
     for joint, part, expect in (('lknee', 6, True), ('cnose', 1, True), ('lelbow', 2, False), ('lhip', 6, False)):
@@ -182,6 +206,26 @@ def test_warp_job_struct_is_128_bytes():
     assert PR.WARP_JOB_DTYPE.itemsize == 128
     for name, _ in _capi.WarpJob._fields_:
         assert PR.WARP_JOB_DTYPE.fields[name][1] == getattr(_capi.WarpJob, name).offset, name
+
+
+def test_routing_job_table():
+    """The one-pass job table against a record-by-record construction (one record per cv2.warpPerspective call of dataset.py:879-890)."""
+    kp = synthetic.synth_patch_routing_inputs(5, seed=4)['keypoints']
+    M, M_inv, valid, to_patch, _ = PR.crop_transforms_native(kp, 64, 64, 256)
+    H = W = 256; h = w = 64
+    groups = ((0x10000000, 0x20000000, 30, 0), (0x30000000, 0x40000000, 30, 0), (0x50000000, 0x60000000, 12, 6), (0x70000000, 0x80000000, 12, 6))
+    jobs = PR._routing_jobs(valid, to_patch, H, W, h, w, groups)
+    want = []
+    for src, dst, nch, first in groups:
+        for b in range(5):
+            for p in range(first, 10):
+                if valid[b, p]:
+                    want.append((to_patch[b, p].reshape(9), src + b * H * W * 3, dst + b * h * w * nch + 3 * (p - first), H, W, W * 3, 3, h, w, w * nch, nch, 3, 1))
+    assert jobs.shape[0] == len(want) > 0
+    for j, wnt in zip(jobs, want):
+        assert np.array_equal(j['m'], wnt[0])
+        assert tuple(int(j[f]) for f in PR.WARP_JOB_DTYPE.names[1:]) == wnt[1:]
+    assert PR._routing_jobs(np.zeros((5, 10), bool), to_patch, H, W, h, w, groups).shape == (0,)
 
 
 def test_host_geometry_batched_equals_per_sample():
