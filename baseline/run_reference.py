@@ -16,6 +16,7 @@ files that do not exist).
     --mode overlay_hook   the same after a pickle round trip through legacy.load_network_pkl with the persistence.import_hook recipe of
                      INTEGRATION.md §2 that re-routes the pickled modulated_conv2d to the one-launch kernel.
     --mode ops       per-op timings of the reference's CUDA plugins and cuDNN fp32 on the op-microbenchmark grid (BASELINE configs[4]).
+    --mode ops_cpu   the same grid through the reference's impl='ref' path on CPU tensors (host cores): the "vs impl='ref'" column of BASELINE configs[4].
     --mode patch_routing   the reference's own data-loader patch routing on the host: UvitonDatasetFull.normalize (training/dataset.py:838-927, 56
                      cv2.warpPerspective calls per sample) on the inputs in --io-in (.npz), outputs of the first samples written to --io-out.
 
@@ -36,7 +37,7 @@ REF = os.environ.get('PASTA_REFERENCE_TREE', os.path.join(ROOT, 'baseline', '_re
 
 def parse():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--mode', required=True, choices=['cpu', 'gpu', 'overlay', 'overlay_hook', 'ops', 'patch_routing'])
+    ap.add_argument('--mode', required=True, choices=['cpu', 'gpu', 'overlay', 'overlay_hook', 'ops', 'ops_cpu', 'patch_routing'])
     ap.add_argument('--profile', action='store_true', help='print the top CUDA kernels of one forward (torch.profiler) to stderr')
     ap.add_argument('--batch', type=int, default=1)
     ap.add_argument('--steps', type=int, default=3)
@@ -203,6 +204,57 @@ def run_ops(out):
     out['plugins'] = dict(upfirdn2d=upfirdn2d._plugin is not None, bias_act=bias_act._plugin is not None)
 
 
+def run_ops_cpu(out, R_net, budget_s=150.0):
+    """The op grid of run_ops through the reference's impl='ref' code on CPU tensors (upfirdn2d.py:169-208, bias_act.py:94-123, networks.py:37-94 with
+    fused_modconv=True), all host threads; one untimed call then the best of two timed calls per cell; cells are skipped once the time budget is spent."""
+    import torch
+    from torch_utils.ops import upfirdn2d, bias_act
+    f = upfirdn2d.setup_filter([1, 3, 3, 1])
+    rows, t_start = [], time.perf_counter()
+
+    def bench(fn, *a):
+        if time.perf_counter() - t_start > budget_s:
+            return None
+        with torch.no_grad():
+            fn(*a)
+            ts = []
+            for _ in range(2):
+                t0 = time.perf_counter()
+                fn(*a)
+                ts.append(time.perf_counter() - t0)
+        return min(ts) * 1e6
+
+    n = 16
+    for res, c in [(32, 512), (64, 256), (128, 128), (256, 64), (512, 32)]:
+        numel = n * c * res * res
+        cells = [
+            ('bias_act lrelu+clamp', lambda x, b: bias_act.bias_act(x, b, act='lrelu', clamp=256), (torch.randn(n, c, res, res), torch.randn(c)), 8 * numel, None),
+            ('upfirdn2d filter pad1 gain4', lambda x: upfirdn2d.upfirdn2d(x, f, padding=[1, 1, 1, 1], gain=4), (torch.randn(n, c, res + 1, res + 1),),
+             4 * (numel + n * c * (res + 1) ** 2), None),
+            ('upfirdn2d down2', lambda x: upfirdn2d.upfirdn2d(x, f, down=2, padding=[1, 1, 1, 1]), (torch.randn(n, c, res, res),), 5 * numel, None),
+            ('upfirdn2d up2 rgb', lambda x: upfirdn2d.upsample2d(x, f), (torch.randn(n, 3, res // 2, res // 2),), 5 * n * 3 * res * res, None),
+        ]
+        if res <= 256:
+            cells.append(('upfirdn2d up2 (upsample2d)', lambda x: upfirdn2d.upsample2d(x, f), (torch.randn(n, c, res // 2, res // 2),), 5 * numel, None))
+            w = torch.randn(c, c, 3, 3)
+            st = torch.randn(n, c)
+            cells.append(('modulated_conv2d 3x3 fused', lambda x: R_net.modulated_conv2d(x=x, weight=w, styles=st, padding=1, fused_modconv=True),
+                          (torch.randn(n, c, res, res),), 8 * numel, 2 * numel * c * 9))
+        for name, fn, args, nbytes, flops in cells:
+            us = bench(fn, *args)
+            if us is None:
+                rows.append(dict(op=name, res=res, c=c, skipped='time budget'))
+                continue
+            r = dict(op=name, res=res, c=3 if name.endswith('rgb') else c, us=us, gbs=nbytes / us / 1e3)
+            if flops:
+                r['tflops'] = flops / us / 1e6
+            rows.append(r)
+    out['ops'] = rows
+    out['cores'] = os.cpu_count() or 1
+    out['threads'] = torch.get_num_threads()
+    out['what'] = "UNMODIFIED reference ops, impl='ref' (CPU tensors), N = 16, best of 2 after one warm-up call"
+
+
 NORM_NAMES = ('img', 'img_lower', 'denorm_upper_img', 'denorm_lower_img', 'M_invs', 'hand_masks', 'clothes_masks', 'clothes_masks_lower')
 
 
@@ -286,13 +338,17 @@ def main():
             sys.path.insert(0, _ce._get_build_directory(_name, verbose=False))
     R_net, legacy = import_reference(tree)
     import procedural
-    device = 'cpu' if args.mode == 'cpu' else 'cuda'
+    device = 'cpu' if args.mode in ('cpu', 'ops_cpu') else 'cuda'
     if device == 'cuda':
         torch.backends.cudnn.benchmark = True                  # training_loop_wo_flow_fullbody.py:242
         torch.backends.cudnn.allow_tf32 = False                # :243, :253 — the reference's own GPU convolutions are full fp32
         torch.backends.cuda.matmul.allow_tf32 = False
     if args.mode == 'ops':
         run_ops(out)
+        print(json.dumps(out), flush=True)
+        return
+    if args.mode == 'ops_cpu':
+        run_ops_cpu(out, R_net)
         print(json.dumps(out), flush=True)
         return
     if args.mode == 'cpu':
