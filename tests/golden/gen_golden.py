@@ -384,6 +384,95 @@ def gen_discriminator():
     save('discriminator', arrays, [dict(names=pn, grad_names=names, n_params=sum(p.numel() for p in D.parameters()))])
 
 
+def _grad_summary(module, seed_tag):
+    """Per-parameter gradient fingerprint: L2 norm and the projections on four fixed +-1 vectors (drawn from a generator seeded by the parameter's
+    name), float64.  Parameters whose grad is None (unused in the phase) get NaN norms."""
+    import zlib
+    names, norms, projs = [], [], []
+    for n, p_ in module.named_parameters():
+        names.append(n)
+        if p_.grad is None:
+            norms.append(float('nan')); projs.append([float('nan')] * 4)
+            continue
+        g = p_.grad.detach().double().flatten()
+        gen = torch.Generator().manual_seed(zlib.crc32((seed_tag + n).encode()))
+        signs = torch.randint(0, 2, (4, g.numel()), generator=gen, dtype=torch.int8).double() * 2 - 1
+        norms.append(float(g.norm())); projs.append([float(v) for v in signs @ g])
+    return names, np.array(norms), np.array(projs)
+
+
+def gen_training_step(num_fp16_res=3, name='training_step'):
+    """The reference's own loss object (training/loss_wo_flow_fullbody.py:32-254, StyleGAN2Loss.accumulate_gradients) on BASELINE configs[3] at batch 2:
+    phases Gmain, Dmain and Dreg with the weights of train.sh (l1 40, mask 20, r1_gamma 10, pl 0, contextual 0, style mixing 0 as
+    train_wo_flow_fullbody.py:219 sets it) and vgg_weight 0 (the VGG checkpoint is not available).  G and D are the unmodified reference modules in
+    train mode with procedural weights; noise_strength is zeroed (train mode draws fresh noise per call, which no second implementation can
+    reproduce).  Stored: the loss terms the reference reports (training_stats.report is tapped, a harness shim), and per-parameter gradient
+    fingerprints (norm + four +-1 projections) of every phase, plus a few gradient tensors (every 37th element of the large ones).
+    With num_fp16_res = 3 the R1 phase is degenerate on these weights (the reference's fp16 blocks flush the ~1e-8 gradients to exact zeros: penalty
+    0.0); its parity is pinned by discriminator.npz (fp32 blocks) and by the fp32 variant of this fixture."""
+    import training.loss_wo_flow_fullbody as R_loss
+    from torch_utils import training_stats
+    torch.manual_seed(0)
+    G = R_net.GeneratorFull(z_dim=0, c_dim=512, w_dim=512, img_resolution=256, img_channels=3, mapping_kwargs=dict(num_layers=1),
+                            synthesis_kwargs=dict(channel_base=16384, channel_max=512, num_fp16_res=num_fp16_res, conv_clamp=256, use_noise=True))
+    D = R_net.Discriminator(c_dim=512, img_resolution=256, img_channels=3, channel_base=16384, channel_max=512, num_fp16_res=num_fp16_res,
+                            conv_clamp=256, epilogue_kwargs=dict(mbstd_group_size=4))
+    procedural.fill_(G)
+    procedural.fill_(D)
+    with torch.no_grad():
+        for n_, p_ in G.named_parameters():
+            if n_.endswith('noise_strength'):
+                p_.zero_()
+    G.train().requires_grad_(True)
+    D.train().requires_grad_(True)
+    loss = R_loss.StyleGAN2Loss(device=torch.device('cpu'), G_mapping=G.mapping, G_synthesis=G.synthesis, G_const_encoding=G.const_encoding,
+                                G_style_encoding=G.style_encoding, D=D, augment_pipe=None, style_mixing_prob=0, r1_gamma=10, pl_weight=0,
+                                l1_weight=40, vgg_weight=0, contextual_weight=0, mask_weight=20)
+    b = procedural.synth_inputs(2, seed=1234)
+    g = torch.Generator().manual_seed(1234 + 99)
+    real_img = torch.randint(0, 256, (2, 3, 256, 256), generator=g).float() / 127.5 - 1
+    gt_parsing = torch.randint(0, 6, (2, 1, 256, 256), generator=g).float()
+    reported = {}
+    real_report = training_stats.report
+    tap = lambda name, value: reported.__setitem__(name, torch.as_tensor(value).detach().double().mean().item())
+    training_stats.report = tap
+    R_loss.training_stats.report = tap
+    arrays, meta = {}, {}
+    full = {'Gmain': ['synthesis.b256.conv1.weight', 'synthesis.b256.torgb.weight', 'synthesis.b16.conv1.affine.weight', 'mapping.fc0.weight'],
+            'Dmain': ['b256.fromrgb.weight', 'b32.conv0.weight', 'b4.out.weight'], 'Dreg': ['b256.fromrgb.weight', 'b32.conv0.weight', 'b4.out.weight']}
+    try:
+        for phase, gain, module, tag in (('Gmain', 1, G, 'G'), ('Dmain', 1, D, 'D'), ('Dreg', 16, D, 'D')):
+            G.zero_grad(set_to_none=True)
+            D.zero_grad(set_to_none=True)
+            G.requires_grad_(tag == 'G')                 # training_loop_wo_flow_fullbody.py:489-491: only the phase's module takes gradients
+            D.requires_grad_(tag == 'D')
+            reported.clear()
+            loss.accumulate_gradients(phase=phase, real_img=real_img, gen_z=b['z'], style_input=b['c'], retain=b['retain'], pose=b['pose'],
+                                      denorm_upper_input=b['denorm_upper_input'], denorm_lower_input=b['denorm_lower_input'],
+                                      denorm_upper_mask=b['denorm_upper_mask'], denorm_lower_mask=b['denorm_lower_mask'], gt_parsing=gt_parsing,
+                                      sync=True, gain=gain)
+            names, norms, projs = _grad_summary(module, phase + '/')
+            arrays[phase + '/norm'], arrays[phase + '/proj'] = norms, projs
+            meta[phase] = dict(names=names, reported=dict(reported), gain=gain)
+            params = dict(module.named_parameters())
+            for n in full[phase]:
+                gr = params[n].grad.detach()
+                arrays[f'{phase}/grad/{n}'] = gr.clone() if gr.numel() <= 70000 else gr.flatten()[::37].clone()
+            print(phase, {k: float('%.6g' % v) for k, v in reported.items()}, 'params with grad:', int(np.isfinite(norms).sum()), '/', len(names), flush=True)
+    finally:
+        training_stats.report = real_report
+    meta['full'] = full
+    meta['batch'] = 2
+    meta['num_fp16_res'] = num_fp16_res
+    save(name, arrays, [meta])
+
+
+def gen_training_step_fp32():
+    """The same with every block of G and D in fp32 (num_fp16_res = 0): the fixture that separates the rounding of OUR tensor-core training path from
+    the rounding of the reference's own fp16 blocks (whose CPU and GPU convolutions already differ by a few per cent in the deepest gradients)."""
+    gen_training_step(num_fp16_res=0, name='training_step_fp32')
+
+
 if __name__ == '__main__':
     which = sys.argv[1:] or ['upfirdn2d', 'bias_act', 'conv2d_resample', 'modulated_conv2d', 'layers', 'generator', 'discriminator', 'generator_512',
                              'generator_labels', 'generator_n16']

@@ -13,7 +13,7 @@ from pasta_gan_b200 import networks as N, data_parallel as dp
 from pasta_gan_b200.training import TryOnTrainer, synth_training_batch
 
 ap = argparse.ArgumentParser()
-ap.add_argument('--steps', type=int, default=16); ap.add_argument('--warmup', type=int, default=17); ap.add_argument('--batch-gpu', type=int, default=4); ap.add_argument('--graphs', type=int, default=1); ap.add_argument('--out', default=None)
+ap.add_argument('--steps', type=int, default=16); ap.add_argument('--warmup', type=int, default=17); ap.add_argument('--batch-gpu', type=int, default=4); ap.add_argument('--graphs', type=int, default=1); ap.add_argument('--out', default=None); ap.add_argument('--allow-tf32', type=int, default=0, help='library convolutions / GEMMs on TF32 (the reference trains with it off)')
 a = ap.parse_args()
 world, rank, local = int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('RANK', 0)), int(os.environ.get('LOCAL_RANK', 0))
 dev = torch.device('cuda', local); torch.cuda.set_device(dev)
@@ -25,7 +25,7 @@ G = N.build_generator_full(); D = N.build_discriminator(num_fp16_res=3)
 procedural.fill_(G); procedural.fill_(D)
 G.to(dev).train().requires_grad_(True); D.to(dev).train().requires_grad_(True)
 dp.broadcast_parameters(G); dp.broadcast_parameters(D)
-tr = TryOnTrainer(G, D, capturable=bool(a.graphs))
+tr = TryOnTrainer(G, D, capturable=bool(a.graphs), allow_tf32=bool(a.allow_tf32))
 batch = synth_training_batch(a.batch_gpu, seed=1234 + rank, device=dev)
 if a.graphs:
     tr.capture(batch)
@@ -47,7 +47,7 @@ if rank == 0:
     line = (json.dumps(dict(metric='training images/sec (G+D step, R1 every 16)', value=world * a.batch_gpu * a.steps / sec, unit='img/s', n_gpus=world,
                           steps=a.steps, ms_per_step=1e3 * sec / a.steps, batch_per_gpu=a.batch_gpu, global_batch=world * a.batch_gpu,
                           allreduce_bytes_per_step=dict(G=tr.g_bucket.nbytes, D=tr.d_bucket.nbytes),
-                          losses={k: float(v) for k, v in stats.items()}, max_mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30, cuda_graphs=bool(a.graphs))))
+                          losses={k: float(v) for k, v in stats.items()}, max_mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30, cuda_graphs=bool(a.graphs), library_tf32=bool(a.allow_tf32))))
     print(line, flush=True)
     if a.out:
         open(a.out, 'w').write(line + '\n')
