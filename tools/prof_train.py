@@ -22,7 +22,7 @@ for name, fn in (('g_main', lambda: tr.g_main(batch)), ('d_main', lambda: tr.d_p
     t0 = time.perf_counter(); fn(); t_cpu = time.perf_counter() - t0; torch.cuda.synchronize(); t_all = time.perf_counter() - t0
     print(f'{name}: host issue {1e3 * t_cpu:.1f} ms, until GPU done {1e3 * t_all:.1f} ms')
 from torch.profiler import profile, ProfilerActivity
-with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
     tr.g_main(batch); tr.d_phase(batch, True, False)
     torch.cuda.synchronize()
 ka = prof.key_averages()
@@ -34,3 +34,9 @@ for k in rows:
 print('--- top CPU ops')
 for k in sorted(ka, key=lambda k: -k.self_cpu_time_total)[:15]:
     print(f'{k.self_cpu_time_total / 1e3:8.2f} ms  n={k.count:5d}  {k.key[:100]}')
+print('--- library convolutions by shape (device time of the op, ms; these are the calls conv2d_gradfix leaves on cuDNN)')
+conv_ops = ('aten::cudnn_convolution', 'aten::cudnn_convolution_transpose', 'aten::convolution_backward')
+by = [k for k in prof.key_averages(group_by_input_shape=True) if k.key in conv_ops]
+print(f'total {sum(k.device_time_total for k in by) / 1e3:.2f} ms in {sum(k.count for k in by)} calls')
+for k in sorted(by, key=lambda k: -k.device_time_total)[:24]:
+    print(f'{k.device_time_total / 1e3:8.2f} ms  n={k.count:4d}  {k.key[6:]:28s} {[s_ for s_ in k.input_shapes[:3]]}')
