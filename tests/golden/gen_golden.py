@@ -3,7 +3,7 @@
 
 Run (in the authoring container, where /root/reference is mounted read-only):
 
-    python tests/golden/gen_golden.py            # writes tests/golden/*.npz
+    python tests/golden/gen_golden.py [case ...]  # writes tests/golden/*.npz (into $PASTA_GOLDEN_OUT if set); the patch-routing vectors: gen_warp_golden.py
 
 The reference is imported as-is from /root/reference on CPU, so every op takes its
 ``impl='ref'`` branch (torch_utils/ops/upfirdn2d.py:162-164, bias_act.py:87-89).
@@ -57,7 +57,7 @@ def rnd(seed, *shape, dtype=torch.float32):
 def save(name, arrays, meta):
     arrays = {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in arrays.items()}
     arrays['meta'] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
-    path = os.path.join(HERE, name + '.npz')
+    path = os.path.join(os.environ.get('PASTA_GOLDEN_OUT', HERE), name + '.npz')      # PASTA_GOLDEN_OUT=/tmp/x: regenerate beside the committed files to compare
     np.savez_compressed(path, **arrays)
     print(f'{name}.npz  {os.path.getsize(path) / 1e3:.1f} kB  ({len(meta)} cases)')
 
@@ -475,6 +475,6 @@ def gen_training_step_fp32():
 
 if __name__ == '__main__':
     which = sys.argv[1:] or ['upfirdn2d', 'bias_act', 'conv2d_resample', 'modulated_conv2d', 'layers', 'generator', 'discriminator', 'generator_512',
-                             'generator_labels', 'generator_n16']
+                             'generator_labels', 'generator_n16', 'training_step', 'training_step_fp32']      # (the last two: ~5 + ~3 min of CPU)
     for w in which:
         globals()['gen_' + w]()

@@ -124,7 +124,7 @@ def main():
     meta = dict(opencv=cv2.__version__, algorithm_hint=hint[0] if hint else None, numpy=np.__version__, raw_trials=RAW_TRIALS,
                 reference='training/dataset.py:748-927 (UvitonDatasetFull.valid_joints / get_crop / normalize), unmodified')
     arrays['meta'] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
-    path = os.path.join(HERE, 'warp.npz')
+    path = os.path.join(os.environ.get('PASTA_GOLDEN_OUT', HERE), 'warp.npz')
     np.savez_compressed(path, **arrays)
     print(path, os.path.getsize(path), 'bytes', meta)
 
