@@ -65,10 +65,11 @@ tensor_core_training = os.environ.get('PASTA_B200_TC_TRAIN', '1') != '0'
 # as in inference; gradients are tiny (R1's are ~1e-7) -> bf16 for the exponent range.  (Forward in bf16 measured 2e-1 pointwise on R1's image gradient.)
 tensor_core_format = os.environ.get('PASTA_B200_TC_TRAIN_FMT', 'fp16')
 tensor_core_grad_format = os.environ.get('PASTA_B200_TC_TRAIN_GRAD_FMT', 'bf16')
-# Layers below this many FLOPs per call stay on the library path: at the training batch (4 per GPU) a 512-channel layer at 4^2..32^2 is a few
-# microseconds of math behind a weight tensor that has to be re-packed every step (measured: 65.8 ms / step with every layer on tcgen05 vs 57.8 on
-# cuDNN TF32); the tensor cores pay where pixels, not weights, dominate (SPADE blocks, >= 64^2 layers).
-tensor_core_min_flops = float(os.environ.get('PASTA_B200_TC_TRAIN_MIN_GFLOP', '8')) * 1e9
+# Layers below this many FLOPs per call stay on the library path: at the training batch (4 per GPU) a 512-channel layer at 4^2..16^2 is a few
+# microseconds of math behind a weight tensor that has to be re-packed every step; the tensor cores pay where pixels, not weights, dominate (SPADE
+# blocks, >= 32^2 layers).  Measured with the library in fp32 (the trainer's default): 8 GFLOP 72.2 ms / step, 3 GFLOP 70.6, 1 GFLOP 68.1.  (Against
+# cuDNN TF32 the break-even was higher: 65.8 ms with every layer on tcgen05 vs 57.8 with an 8 GFLOP floor.)
+tensor_core_min_flops = float(os.environ.get('PASTA_B200_TC_TRAIN_MIN_GFLOP', '1')) * 1e9
 # R1 (loss_wo_flow_fullbody.py:231-254) differentiates the image gradient a second time and its values are ~1e-7: with 10-bit-mantissa products in the
 # forward pass the pointwise image gradient measured 9e-2 and some second-order parameter gradients 3e-1 against the reference (2e-1 / 4e-1 with bf16),
 # while the fp32 library path holds 1e-2.  So the tensor cores serve the first-order phases (Gmain, Dmain) and the trainer runs the Dreg phase -- one

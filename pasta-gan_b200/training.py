@@ -26,8 +26,8 @@ class TryOnTrainer:
         self.r1_gamma, self.l1_weight, self.mask_weight, self.d_reg_interval = r1_gamma, l1_weight, mask_weight, d_reg_interval
         conv2d_gradfix.enabled = True                          # training_loop_wo_flow_fullbody.py:255
         # the convolutions and GEMMs left on the library (strided / transposed forms, small layers) run in full fp32 as in the reference's loop
-        # (:243, :253).  allow_tf32=True is 35 % faster (75 vs 55 img/s on one B200) but leaves the style encoder's gradients off by up to 13 % of their
-        # norm against 2 % (tests/test_training_parity.py; it is the LARGE strided convolutions that cause it, not the small ones)
+        # (:243, :253).  allow_tf32=True is ~30 % faster (75 vs 59 img/s on one B200) but leaves the style encoder's gradients off by up to 13 % of their
+        # norm against 2-4 % (tests/test_training_parity.py; it is the LARGE strided convolutions that cause it, not the small ones)
         torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = bool(allow_tf32)
         self.g_bucket = dp.FlatGradBucket(G.parameters())
         self.d_bucket = dp.FlatGradBucket(D.parameters())

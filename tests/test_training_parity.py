@@ -22,8 +22,8 @@ from pasta_gan_b200.training import TryOnTrainer, synth_training_batch
 
 # (projection tolerance, norm tolerance) per phase, as fractions of the reference gradient's norm; about twice the errors measured on a B200
 # (profiles/r2_training_parity.txt)
-TOL_AS_TRAINED = dict(Gmain=(5e-2, 1e-2), Dmain=(1.2e-1, 1e-2))                            # measured 2.3e-2 / 3e-3 and 5.9e-2 / 3e-3 (three fp16 D blocks)
-TOL_TC_VS_FP32 = dict(Gmain=(5e-2, 1e-2), Dmain=(6e-2, 1e-2), Dreg=(1e-3, 1e-3))           # measured 2.3e-2, 2.9e-2, 1.2e-4
+TOL_AS_TRAINED = dict(Gmain=(8e-2, 1e-2), Dmain=(1.2e-1, 1e-2))                            # measured 3.9e-2 / 4e-3 and 4.3e-2 .. 5.9e-2 / 3e-3 (three fp16 D blocks)
+TOL_TC_VS_FP32 = dict(Gmain=(6e-2, 1e-2), Dmain=(6e-2, 1e-2), Dreg=(1e-3, 1e-3))           # measured 3.0e-2, 2.1e-2 .. 2.9e-2, 1.2e-4
 TOL_FP32 = dict(Gmain=(1.5e-2, 1e-3), Dmain=(4e-2, 1e-2), Dreg=(1e-3, 1e-3))               # measured 6.2e-3 / 9e-5, 1.6e-2 / 3e-3, 1.2e-4 / 9e-5
 TOL_LIBRARY_TF32 = dict(Gmain=(3e-1, 2e-2), Dmain=(2e-1, 2e-2))                            # measured 1.3e-1 (style encoder), 5.9e-2
 FP16_BLOCKS = ('b256.', 'b128.', 'b64.')
