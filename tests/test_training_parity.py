@@ -63,6 +63,24 @@ def test_generator_phase_matches_reference_cpu(golden):
     print('CPU oracle-table Gmain: worst (norm error, projection error, parameters above 2e-2):', worst)
 
 
+def test_discriminator_phases_match_reference_cpu(golden):
+    """Dmain and Dreg (R1: a double backward under no_weight_gradients) of the mirror evaluated by the oracle operator table against the all-fp32
+    reference run: loss terms, the R1 penalty and every discriminator gradient (measured: 6e-5 and exact)."""
+    from oracle import ops_oracle as O
+    g = golden('training_step_fp32')
+    G, D = build('cpu', O.operator_table(fast=True), num_fp16_res=0)
+    tr = TryOnTrainer(G, D)
+    b = synth_training_batch(2, device='cpu')
+    out = tr.d_phase(b, do_main=True, do_r1=False, finish=False)
+    want = g.meta[0]['Dmain']['reported']['Loss/D/loss']                     # mean(softplus(fake) + softplus(-real)), coarse image only (:196)
+    assert abs(float(out['D_real']) + float(torch.nn.functional.softplus(torch.tensor(g.meta[0]['Dmain']['reported']['Loss/scores/fake']))) - want) <= 1e-3
+    print('CPU oracle-table Dmain:', compare(D, 'Dmain', g, proj_tol=1e-3, norm_tol=1e-3))
+    out = tr.d_phase(b, do_main=False, do_r1=True, finish=False)
+    want = g.meta[0]['Dreg']['reported']['Loss/r1_penalty']
+    assert want > 0 and abs(float(out['r1_penalty']) - want) <= 1e-4 * want
+    print('CPU oracle-table Dreg:', compare(D, 'Dreg', g, proj_tol=1e-3, norm_tol=1e-3))
+
+
 def fingerprint(module, tag):
     """Same construction as tests/golden/gen_golden.py:_grad_summary."""
     out = {}
