@@ -317,6 +317,36 @@ def workload_config(args, world):
             'weights': 'procedural (name-keyed, pasta-gan_b200/synthetic.py)', 'noise_mode': 'const'}
 
 
+def time_training_step(world, rank, timeout=240, cmd=None):
+    """BASELINE configs[3] -- the one path with a collective: the G + D training step (batch 4 per GPU, CUDA-graph phases, one flat NCCL all-reduce per
+    phase) measured by tools/bench_train.py in a CHILD process per rank, with its own rendezvous on MASTER_PORT + 17.  Isolation on purpose: whatever
+    happens in there (an exception on one rank, a stuck collective) ends with the child's timeout and cannot take the headline line down.  Every rank
+    calls this at the same point; rank 0 returns the child's record, the others None."""
+    env = dict(os.environ)
+    if world > 1:
+        env['MASTER_PORT'] = str(int(os.environ.get('MASTER_PORT', '29511')) + 17)
+    for k in ('TORCHELASTIC_RUN_ID', 'TORCHELASTIC_RESTART_COUNT', 'TORCHELASTIC_MAX_RESTARTS', 'TORCHELASTIC_USE_AGENT_STORE'):
+        env.pop(k, None)                                  # the child is a plain env:// rendezvous between the N children, not a worker of torchrun's agent
+    cmd = cmd or [sys.executable, os.path.join(ROOT, 'tools', 'bench_train.py'), '--steps', '16', '--warmup', '17']
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=env)
+        if rank != 0:
+            return None
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith('{')]
+        if r.returncode != 0 or not lines:
+            return dict(unavailable=f'rc {r.returncode}: {(r.stderr or r.stdout)[-300:]}')
+        d = json.loads(lines[-1])
+        return dict(value=d['value'], unit=d['unit'], ms_per_step=d['ms_per_step'], n_gpus=d['n_gpus'], batch_per_gpu=d.get('batch_per_gpu'),
+                    global_batch=d.get('global_batch'), allreduce_bytes_per_step=d.get('allreduce_bytes_per_step'), cuda_graphs=d.get('cuda_graphs'),
+                    library_tf32=d.get('library_tf32'), scaling='weak',
+                    what='G + D training step of loss_wo_flow_fullbody (Gmain + Dmain every iteration, R1 every 16th), 16 timed steps, device-timed, max over ranks '
+                         '(tools/bench_train.py in a child process per rank)')
+    except subprocess.TimeoutExpired:
+        return dict(unavailable=f'timed out after {timeout} s') if rank == 0 else None
+    except Exception as e:  # noqa: BLE001
+        return dict(unavailable=repr(e)[:300]) if rank == 0 else None
+
+
 def run_reference(args, world, rank):
     if rank != 0:
         return
@@ -485,6 +515,12 @@ def run_b200(args, world, rank, local):
         finally:
             K.enabled, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
+    # configs[3] (training step, the path with the NCCL exchange) at this N, in child processes: every rank takes part
+    train_leg = None
+    if not args.no_extras and args.workload == 'gen256':
+        barrier(world)
+        train_leg = time_training_step(world, rank)
+        barrier(world)
     if rank != 0:
         return
     imgs = world * args.batch * args.steps
@@ -493,6 +529,8 @@ def run_b200(args, world, rank, local):
         cpu = time_cpu_reference(steps=20, warmup=2, batch=1)
         cpu = {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
     extra = {}
+    if train_leg is not None:
+        extra['training'] = train_leg
     io_bytes = dict(h2d=sess.h2d_bytes, d2h=sess.d2h_bytes, h2d_u8=sess.h2d_bytes_u8, d2h_u8=sess.d2h_bytes_u8)
     if extras:
         try:
