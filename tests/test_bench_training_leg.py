@@ -36,7 +36,7 @@ PARENT = textwrap.dedent('''
     world, rank = int(os.environ['WORLD_SIZE']), int(os.environ['RANK'])
     dist.init_process_group('gloo', rank=rank, world_size=world)          # the parents' own group stays up while the children run, as in bench.py
     out = {{}}
-    for mode, timeout in (('ok', 60), ('fail', 20), ('hang', 5)):
+    for mode, timeout in (('ok', 60), ('fail', 8), ('hang', 5)):
         r = bench.time_training_step(world, rank, timeout=timeout, cmd=[sys.executable, {child!r}, mode])
         dist.barrier()
         out[mode] = r
