@@ -190,6 +190,12 @@ def test_native_geometry_bit_equal(golden):
         assert np.array_equal(got[3], PR.invert3x3(want[0])) and np.array_equal(got[4], PR.invert3x3(want[1])), trial
     with pytest.raises(_capi.PastaB200Error):
         PR.crop_transforms_native(np.zeros((2, 17, 3)), 64, 64, 256)
+    # the C entry point itself: bad arguments come back as an error code with a message, an empty batch is a no-op
+    lib = _capi.load()
+    assert lib.pg_patch_crop_transforms(None, 1, 64, 64, 256, 0.5, None, None, None, None, None) != 0 and b'null pointer' in lib.pg_last_error()
+    kp = np.zeros((1, 18, 3)); out = np.zeros((2, 90)); v = np.zeros(10, np.uint8)
+    assert lib.pg_patch_crop_transforms(kp.ctypes.data, 1, 0, 64, 256, 0.5, out[0].ctypes.data, out[1].ctypes.data, None, None, v.ctypes.data) != 0
+    assert lib.pg_patch_crop_transforms(None, 0, 64, 64, 256, 0.5, None, None, None, None, None) == 0
 
 
 def test_host_fallback_parts():
