@@ -10,6 +10,11 @@ timeout -s KILL 300 python tools/bench_conv.py --out $R/r2_conv_microbench.jsonl
 timeout -s KILL 300 python tools/microbench.py --out $R/r2_op_microbench.jsonl > /dev/null 2>&1
 timeout -s KILL 300 python baseline/run_reference.py --mode ops > $R/r2_reference_cuda_ops.json 2> $R/r2_reference_cuda_ops.err
 timeout -s KILL 400 python bench.py --impl reference --steps 3 --warmup 1 > $R/r2_bench_reference_arm.json 2> $R/r2_bench_reference_arm.err
+timeout -s KILL 300 python baseline/run_reference.py --mode ops_cpu > $R/r2_reference_cpu_ops.json 2> $R/r2_reference_cpu_ops.err
+timeout -s KILL 240 python tools/bench_train.py --steps 16 --warmup 17 --out $R/r2_train_1gpu_fp32lib.json > /dev/null 2>&1
+timeout -s KILL 240 python tools/bench_train.py --steps 16 --warmup 17 --allow-tf32 1 --out $R/r2_train_1gpu_tf32lib.json > /dev/null 2>&1
+timeout -s KILL 300 python tools/prof_train.py > $R/r2_prof_train_fp32lib.log 2>&1
+timeout -s KILL 300 python -m pytest tests/test_training_parity.py -m gpu -q -s > $R/r2_training_parity_pytest.log 2>&1     # prints the per-phase worst gradient errors
 timeout -s KILL 200 python tools/step_breakdown.py > $R/r2_step_breakdown_gen256.txt 2>&1
 timeout -s KILL 200 python tools/step_breakdown.py --workload gen512 > $R/r2_step_breakdown_gen512.txt 2>&1
 # ncu passes (each only after the same command has exited 0 without ncu above): launch list of a 2-step eager bench run, and --set full on the op driver
