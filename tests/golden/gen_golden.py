@@ -358,6 +358,18 @@ def gen_generator_512():
          [dict(names=names, n_params=sum(p.numel() for p in G.parameters()), num_ws=int(G.num_ws), img_absmax=float(img.abs().max()))])
 
 
+def gen_generator_512_n16():
+    """Generator_512 at the BASELINE batch of configs[2] (N = 16): the band / tile choices of the CUDA kernels depend on N * H * W.  Output stored
+    float16, every 4th pixel."""
+    G = R_net.Generator_512(z_dim=0, c_dim=512, w_dim=512, img_resolution=512, img_channels=3, mapping_kwargs=dict(num_layers=1),
+                            synthesis_kwargs=dict(channel_base=16384, channel_max=512, num_fp16_res=0, conv_clamp=256, use_noise=True)).eval()
+    procedural.fill_(G)
+    inp = procedural.synth_inputs_512(16, seed=8642)
+    with torch.no_grad():
+        img = G(**inp, noise_mode='const')
+    save('generator_512_n16', {'img': img[:, :, ::4, ::4].half()}, [dict(seed=8642, batch=16, img_absmax=float(img.abs().max()), img_std=float(img.std()))])
+
+
 def gen_discriminator():
     """Discriminator (fp32 blocks) at the BASELINE widths on a 4-image batch: logits, the R1 gradient wrt the image, the R1 penalty and a
     few parameter gradients of the penalty (a full double backward through conv / upfirdn2d / bias_act-lrelu / mbstd / FC)."""
@@ -475,6 +487,6 @@ def gen_training_step_fp32():
 
 if __name__ == '__main__':
     which = sys.argv[1:] or ['upfirdn2d', 'bias_act', 'conv2d_resample', 'modulated_conv2d', 'layers', 'generator', 'discriminator', 'generator_512',
-                             'generator_labels', 'generator_n16', 'training_step', 'training_step_fp32']      # (the last two: ~5 + ~3 min of CPU)
+                             'generator_labels', 'generator_n16', 'generator_512_n16', 'training_step', 'training_step_fp32']      # (the last two: ~5 + ~3 min of CPU)
     for w in which:
         globals()['gen_' + w]()

@@ -163,6 +163,22 @@ def test_generator_512_cuda_vs_reference(golden):
     assert err < 1e-2
 
 
+def test_generator_512_n16_vs_reference(golden):
+    """The same at the batch BASELINE configs[2] is measured on (N = 16: other band / tile choices than N = 1), against the reference's CPU output of
+    that batch (stored every 4th pixel, float16): 1e-2 relative."""
+    g = golden('generator_512_n16')
+    meta = g.meta[0]
+    G = N.build_generator_512().eval()
+    procedural.fill_(G)
+    G.to(DEV).requires_grad_(False)
+    with torch.no_grad():
+        img = G(**procedural.synth_inputs_512(meta['batch'], seed=meta['seed'], device=DEV), noise_mode='const')
+    ref = g.t('img', dtype=torch.float32)
+    err = rel_err(img[:, :, ::4, ::4], ref)
+    print('generator_512 N = 16 rel err', err)
+    assert abs(float(img.abs().max()) - meta['img_absmax']) < 2e-2 * meta['img_absmax'] and err < 1e-2
+
+
 def test_fused_inference_paths_are_equivalent(cuda_generator, monkeypatch):
     """The host-side inference fusions do not change what is computed: fp16 intermediates between the SPADE blocks' convolutions carry the operand
     bits the consumer would round to anyway (only the fp16 skip-branch residual adds a rounding), and the batched StyleBank agrees with the per-layer affine / demodulation path
