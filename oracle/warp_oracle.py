@@ -26,6 +26,8 @@ Details that matter for bit-level agreement with OpenCV and are reproduced here:
     sum correction), the result is ``(sum w*p + 2^14) >> 15``;
   * ``BORDER_REPLICATE`` clamps each of the four taps, ``BORDER_CONSTANT`` substitutes 0 per tap and short-cuts fully outside
     pixels.
+A plain-C twin of the two OpenCV pieces lives in oracle/oracle.c (``orc_get_perspective_transform``, ``orc_warp_perspective_u8``), pinned to the same
+fixture by tests/test_oracle_c.py.
 Only ``tests/`` and bench / smoke checkers may import this file; the product (``pasta-gan_b200/patch_routing.py``) has its own
 batched host code and CUDA kernels.
 """

@@ -106,3 +106,52 @@ def test_c_and_torch_oracles_agree_on_a_down2_layer(lib):
     assert lib.orc_bias_act(ptr(yc), ptr(b), None, ptr(y), ctypes.c_int64(yc.numel()), 5, ctypes.c_int64(30), 0, 3,
                             ctypes.c_float(0.2), ctypes.c_float(2 ** 0.5), ctypes.c_float(1.0)) == 0
     assert rel_err(y, ref) < 2e-6
+
+
+# ----------------------------------------------------------------------------- patch routing: the C restatement of the OpenCV warp
+
+def test_c_warp_matches_opencv_golden(lib):
+    """orc_get_perspective_transform / orc_warp_perspective_u8 against tests/golden/warp.npz: matrices as bit-equal doubles, images as bytes written by
+    cv2.warpPerspective 4.13.0 (both borders, 1 / 3 / 4 channels), and the first warp of the reference's normalize() chain; and against the numpy
+    restatement (oracle/warp_oracle.py) on fresh cases."""
+    import json
+    from oracle import warp_oracle as WO
+    g = dict(np.load(os.path.join(ROOT, 'tests', 'golden', 'warp.npz')))
+    meta = json.loads(bytes(g['meta']).decode())
+    D, U8 = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_ubyte)
+    lib.orc_get_perspective_transform.argtypes = [F, F, D]
+    lib.orc_warp_perspective_u8.argtypes = [U8, ctypes.c_int, ctypes.c_int, ctypes.c_int, D, U8, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+
+    def persp(src, dst):
+        src, dst, m = np.ascontiguousarray(src, np.float32), np.ascontiguousarray(dst, np.float32), np.empty(9, np.float64)
+        assert lib.orc_get_perspective_transform(src.ctypes.data_as(F), dst.ctypes.data_as(F), m.ctypes.data_as(D)) == 0
+        return m.reshape(3, 3)
+
+    def warp(img, M, w, h, border):
+        img = np.ascontiguousarray(img)
+        H, W, C = img.shape
+        M = np.ascontiguousarray(M, np.float64)
+        out = np.empty((h, w, C), np.uint8)
+        assert lib.orc_warp_perspective_u8(img.ctypes.data_as(U8), H, W, C, M.ctypes.data_as(D), out.ctypes.data_as(U8), h, w, border) == 0
+        return out
+
+    for t in range(meta['raw_trials']):
+        M = persp(g[f'raw_{t}_src'], g[f'raw_{t}_dst'])
+        assert np.array_equal(M, g[f'raw_{t}_M']) and np.array_equal(persp(g[f'raw_{t}_dst'], g[f'raw_{t}_src']), g[f'raw_{t}_Minv'])
+        for name, border in (('constant', 0), ('replicate', 1)):
+            want = g[f'raw_{t}_{name}']
+            got = warp(g[f'raw_{t}_img'], M, want.shape[1], want.shape[0], border)
+            assert np.array_equal(got, want), (t, name, int((got != want).sum()))
+    # the reference's own chain: part 0 of sample 0 (torso quadrilateral -> 64 x 64 patch, BORDER_REPLICATE) are channels 0..2 of normalize()'s first output
+    assert g['norm_out_valid'][0, 0]
+    patch = warp(g['norm_upper_img'][0], g['norm_out_M'][0, 0], 64, 64, 1)
+    assert np.array_equal(patch, g['norm_out_img'][0][:, :, 0:3])
+    rng = np.random.default_rng(5)
+    for trial in range(6):
+        img = rng.integers(0, 256, (90, 70, 3), dtype=np.uint8)
+        src = np.float32([[5, 8], [3, 80], [60, 85], [66, 4]] + rng.normal(0, 6, (4, 2)))
+        dst = np.float32([[0, 0], [0, 48], [40, 48], [40, 0]])
+        M = persp(src, dst)
+        assert np.array_equal(M, WO.get_perspective_transform(src, dst))
+        for border in (0, 1):
+            assert np.array_equal(warp(img, M, 40, 48, border), WO.warp_perspective_u8(img, M, (40, 48), border))
