@@ -198,6 +198,28 @@ def test_native_geometry_bit_equal(golden):
     assert lib.pg_patch_crop_transforms(None, 0, 64, 64, 256, 0.5, None, None, None, None, None) == 0
 
 
+def test_native_geometry_against_live_cv2():
+    """pg_patch_crop_transforms against cv2.getPerspectiveTransform itself on a few hundred random poses (where cv2 can be imported)."""
+    cv2 = pytest.importorskip('cv2')
+    rng = np.random.default_rng(123)
+    kp = synthetic.synth_patch_routing_inputs(40, seed=77, drop_joints=False)['keypoints']
+    kp[:, :, :2] += rng.normal(0, 15, kp[:, :, :2].shape)
+    kp[:, :, 2] = np.where(rng.random((40, 18)) < 0.2, 0.0, kp[:, :, 2])
+    M, M_inv, valid, to_patch, to_image = PR.crop_transforms_native(kp, 64, 64, 256)
+    dst = np.float32([[0, 0], [0, 64], [64, 64], [64, 0]])
+    checked = 0
+    for p in range(PR.NUM_PARTS):
+        quads, ok = PR.part_quadrilaterals(kp, p, 256)
+        assert np.array_equal(ok, valid[:, p])
+        for b in np.flatnonzero(ok):
+            q = np.ascontiguousarray(quads[b], np.float32)
+            assert np.array_equal(M[b, p], cv2.getPerspectiveTransform(q, dst)), (b, p)
+            assert np.array_equal(M_inv[b, p], cv2.getPerspectiveTransform(dst, q)), (b, p)
+            assert np.array_equal(to_patch[b, p], cv2.invert(M[b, p])[1]) or np.allclose(to_patch[b, p], cv2.invert(M[b, p])[1], rtol=1e-12, atol=0)
+            checked += 1
+    assert checked > 250
+
+
 def test_host_fallback_parts():
     kp = synthetic.synth_patch_routing_inputs(1, drop_joints=False)['keypoints'][0]
     for joint, part, expect in (('lknee', 6, True), ('cnose', 1, True), ('lelbow', 2, False), ('lhip', 6, False)):
