@@ -215,7 +215,7 @@ def test_native_geometry_against_live_cv2():
             q = np.ascontiguousarray(quads[b], np.float32)
             assert np.array_equal(M[b, p], cv2.getPerspectiveTransform(q, dst)), (b, p)
             assert np.array_equal(M_inv[b, p], cv2.getPerspectiveTransform(dst, q)), (b, p)
-            assert np.array_equal(to_patch[b, p], cv2.invert(M[b, p])[1]) or np.allclose(to_patch[b, p], cv2.invert(M[b, p])[1], rtol=1e-12, atol=0)
+            assert np.array_equal(to_patch[b, p], cv2.invert(M[b, p])[1]) and np.array_equal(to_image[b, p], cv2.invert(M_inv[b, p])[1])
             checked += 1
     assert checked > 250
 
